@@ -1,0 +1,20 @@
+"""curdleproofs_b200 -- B200 (sm_100a) engine for the Curdleproofs MSM / fold hot path.
+
+The product is the C-ABI library ``libcdp_b200.so`` (``include/cdp_msm.h``); this package is the thin
+ctypes mirror of the reference's operator interface for that path:
+
+    reference (Rust)                                   here
+    ------------------------------------------------   -------------------------------
+    util::msm(points, scalars)            util.rs:19    Engine.msm(points, scalars)
+    util::msm_from_projective(...)        util.rs:25    Engine.msm_from_projective(...)
+    fold loops  (L + gamma*R).into_affine()             Engine.fold(L, R, gamma)
+    (s_i * P_i).into_affine()                           Engine.scalar_mul_batch(points, scalars)
+    G1Projective::normalize_batch         util.rs:27    Engine.normalize_batch(points)
+    serialize_compressed                                Engine.compress_batch(points)
+
+There is no CPU fallback: constructing an ``Engine`` without the built extension or without a CUDA
+device raises.
+"""
+from .engine import Engine, CdpError, lib_path, load_library  # noqa: F401
+
+__all__ = ["Engine", "CdpError", "lib_path", "load_library"]

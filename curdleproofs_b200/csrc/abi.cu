@@ -1,0 +1,456 @@
+// C ABI (include/cdp_msm.h) over the sm_100a kernels.  Host-side glue only: buffer management, launch geometry,
+// chunking of large MSMs.  No arithmetic happens on the host and there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/cdp_msm.h"
+#pragma GCC visibility pop
+#include "launch.h"
+
+using namespace cdp;
+
+namespace {
+
+struct scratch_t {
+    void *ptr = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct cdp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err = "ok";
+    uint64_t launches = 0;
+    // grow-on-demand device scratch
+    scratch_t d_pts, d_scalars, d_segs, d_win, d_jac, d_aux, d_out;
+    // pinned host staging
+    scratch_t h_stage;
+    int sm_count = 148;
+};
+
+namespace {
+
+int fail(cdp_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, CDP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+int ensure_dev(cdp_ctx *ctx, scratch_t &s, size_t bytes) {
+    if (bytes <= s.cap) return CDP_OK;
+    if (s.ptr) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaFree(s.ptr));
+        s.ptr = nullptr;
+        s.cap = 0;
+    }
+    size_t cap = std::max<size_t>(bytes, 1 << 16);
+    cap = (cap + (cap >> 2) + 255) & ~size_t(255);
+    CUDA_TRY(ctx, cudaMalloc(&s.ptr, cap));
+    s.cap = cap;
+    return CDP_OK;
+}
+int ensure_host(cdp_ctx *ctx, scratch_t &s, size_t bytes) {
+    if (bytes <= s.cap) return CDP_OK;
+    if (s.ptr) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaFreeHost(s.ptr));
+        s.ptr = nullptr;
+        s.cap = 0;
+    }
+    size_t cap = std::max<size_t>(bytes, 1 << 16);
+    cap = (cap + (cap >> 2) + 255) & ~size_t(255);
+    CUDA_TRY(ctx, cudaMallocHost(&s.ptr, cap));
+    s.cap = cap;
+    return CDP_OK;
+}
+#define TRY(expr)                      \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != CDP_OK) return rc__; \
+    } while (0)
+
+// ---- MSM geometry -------------------------------------------------------------------------------------------
+struct msm_cfg {
+    int c, nwin;
+};
+msm_cfg pick_cfg(size_t max_n) {
+    msm_cfg g;
+    g.c = max_n >= 96 ? 6 : max_n >= 40 ? 5 : max_n >= 12 ? 4 : max_n >= 3 ? 3 : 2;
+    g.nwin = msm_nwin_for(g.c);
+    return g;
+}
+constexpr size_t SMALL_MSM_MAX_N = 2048;  // C = 6, WPB = 11: 11 * 6 * 2048 = 135 KB of shared memory
+
+// window sums for `count` segments -> d_win[count][nwin]
+int msm_buckets_dev(cdp_ctx *ctx, const msm_cfg &g, const uint8_t *d_pts, const uint8_t *d_scalars, const msm_seg_t *d_segs, size_t count,
+                    size_t nmax, uint32_t *d_win) {
+    ctx->launches++;
+    CUDA_TRY(ctx, launch_msm_buckets(ctx->stream, g.c, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars),
+                                     d_segs, (uint32_t)count, (uint32_t)nmax, d_win));
+    return CDP_OK;
+}
+
+int combine_dev(cdp_ctx *ctx, const msm_cfg &g, const uint32_t *d_win, size_t count, uint32_t *d_out_jac) {
+    ctx->launches++;
+    CUDA_TRY(ctx, launch_msm_combine(ctx->stream, d_win, d_out_jac, (uint32_t)count, g.c, g.nwin));
+    return CDP_OK;
+}
+
+int normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_aff, uint8_t *d_comp) {
+    if (n == 0) return CDP_OK;
+    const uint32_t *j = reinterpret_cast<const uint32_t *>(d_jac);
+    uint32_t *a = reinterpret_cast<uint32_t *>(d_aff);
+    // enough threads to fill the machine first, then amortise the inversion over a chunk
+    size_t fill = (size_t)ctx->sm_count * 1024;
+    int chunk = n >= 8 * fill ? 8 : n >= 2 * fill ? 2 : 1;
+    ctx->launches++;
+    CUDA_TRY(ctx, launch_normalize(ctx->stream, chunk, j, a, d_comp, (uint32_t)n));
+    return CDP_OK;
+}
+
+int smul_add_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, const uint32_t *d_sidx, int bcast, const uint8_t *d_add,
+                 size_t n, uint8_t *d_out_jac) {
+    if (n == 0) return CDP_OK;
+    ctx->launches++;
+    CUDA_TRY(ctx, launch_smul_add(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars), d_sidx,
+                                  bcast, reinterpret_cast<const uint32_t *>(d_add), reinterpret_cast<uint32_t *>(d_out_jac), (uint32_t)n));
+    return CDP_OK;
+}
+
+const uint8_t INF_JAC_ZERO[CDP_JACOBIAN_BYTES] = {0};
+
+}  // namespace
+
+// =================================================================================================== context
+extern "C" int cdp_ctx_create(cdp_ctx **out, int device_id, void *stream) {
+    if (!out) return CDP_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device_id < 0 || device_id >= ndev) return CDP_ERR_CUDA;
+    if (cudaSetDevice(device_id) != cudaSuccess) return CDP_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return CDP_ERR_CUDA;
+    if (prop.major != 10) return CDP_ERR_CUDA;  // sm_100a cubins only; fail loudly on anything else
+    cdp_ctx *ctx = new cdp_ctx();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return CDP_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    *out = ctx;
+    return CDP_OK;
+}
+extern "C" void cdp_ctx_destroy(cdp_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (scratch_t *s : {&ctx->d_pts, &ctx->d_scalars, &ctx->d_segs, &ctx->d_win, &ctx->d_jac, &ctx->d_aux, &ctx->d_out})
+        if (s->ptr) cudaFree(s->ptr);
+    if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char *cdp_last_error(const cdp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t cdp_launch_count(const cdp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int cdp_sync(cdp_ctx *ctx) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDP_OK;
+}
+
+// =================================================================================================== device-resident
+extern "C" void *cdp_dev_alloc(cdp_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        ctx->err = "cudaMalloc failed";
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void cdp_dev_free(cdp_ctx *ctx, void *d_ptr) {
+    if (!ctx || !d_ptr) return;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ptr);
+}
+extern "C" void *cdp_host_alloc(cdp_ctx *ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        ctx->err = "cudaMallocHost failed";
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void cdp_host_free(cdp_ctx *ctx, void *h_ptr) {
+    if (!ctx || !h_ptr) return;
+    cudaFreeHost(h_ptr);
+}
+extern "C" int cdp_h2d(cdp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    if (bytes == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return CDP_OK;
+}
+extern "C" int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    if (bytes == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return CDP_OK;
+}
+
+extern "C" int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs,
+                                 size_t count, size_t max_n, uint8_t *d_out_jac) {
+    if (!ctx || !d_out_jac) return CDP_ERR_INVALID_ARG;
+    if (count == 0) return CDP_OK;
+    if (max_n > SMALL_MSM_MAX_N) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm_batch_dev: segment longer than 2048 points; split it");
+    if (max_n == 0) max_n = 1;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    msm_cfg g = pick_cfg(max_n);
+    TRY(ensure_dev(ctx, ctx->d_win, count * g.nwin * CDP_JACOBIAN_BYTES));
+    static_assert(sizeof(cdp_msm_seg) == sizeof(msm_seg_t), "segment layout");
+    TRY(msm_buckets_dev(ctx, g, d_affine_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(d_segs), count, max_n,
+                        reinterpret_cast<uint32_t *>(ctx->d_win.ptr)));
+    return combine_dev(ctx, g, reinterpret_cast<const uint32_t *>(ctx->d_win.ptr), count, reinterpret_cast<uint32_t *>(d_out_jac));
+}
+
+extern "C" int cdp_smul_add_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, const uint32_t *d_scalar_index,
+                                const uint8_t *d_add, size_t n, uint8_t *d_out_jac) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return smul_add_dev(ctx, d_pts, d_scalars, d_scalar_index, 0, d_add, n, d_out_jac);
+}
+
+extern "C" int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return normalize_dev(ctx, d_jac, n, d_out_affine, d_out_compressed);
+}
+
+// =================================================================================================== host-buffer drop-ins
+// One MSM of any size: chunks of <= 2048 points (one CTA pair each), window sums reduced across chunks, one Horner pass.
+static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
+    size_t chunk = std::min<size_t>(SMALL_MSM_MAX_N, n);
+    size_t nchunks = (n + chunk - 1) / chunk;
+    msm_cfg g = pick_cfg(chunk);
+    std::vector<msm_seg_t> segs(nchunks);
+    for (size_t i = 0; i < nchunks; i++) {
+        segs[i].pts_off = (uint32_t)(i * chunk);
+        segs[i].scalars_off = (uint32_t)(i * chunk);
+        segs[i].n = (uint32_t)std::min(chunk, n - i * chunk);
+        segs[i].pad = 0;
+    }
+    TRY(ensure_dev(ctx, ctx->d_segs, nchunks * sizeof(msm_seg_t)));
+    TRY(ensure_host(ctx, ctx->h_stage, nchunks * sizeof(msm_seg_t)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
+    memcpy(ctx->h_stage.ptr, segs.data(), nchunks * sizeof(msm_seg_t));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, ctx->h_stage.ptr, nchunks * sizeof(msm_seg_t), cudaMemcpyHostToDevice, ctx->stream));
+    TRY(ensure_dev(ctx, ctx->d_win, (nchunks + 1) * g.nwin * CDP_JACOBIAN_BYTES));
+    uint32_t *win = reinterpret_cast<uint32_t *>(ctx->d_win.ptr);
+    TRY(msm_buckets_dev(ctx, g, d_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(ctx->d_segs.ptr), nchunks, chunk, win));
+    const uint32_t *win_final = win;
+    if (nchunks > 1) {
+        uint32_t *red = win + 36 * nchunks * g.nwin;
+        ctx->launches++;
+        CUDA_TRY(ctx, launch_sum_groups(ctx->stream, win, red, (uint32_t)g.nwin, (uint32_t)nchunks, (uint32_t)g.nwin));
+        win_final = red;
+    }
+    return combine_dev(ctx, g, win_final, 1, reinterpret_cast<uint32_t *>(d_out_jac));
+}
+
+extern "C" int cdp_msm(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *scalars, size_t n, uint8_t out_jac[CDP_JACOBIAN_BYTES]) {
+    if (!ctx || !out_jac || (n && (!affine_pts || !scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm: null argument");
+    if (n >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm: n too large");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) {  // empty sum = infinity (Z = 0)
+        memcpy(out_jac, INF_JAC_ZERO, CDP_JACOBIAN_BYTES);
+        return CDP_OK;
+    }
+    TRY(ensure_dev(ctx, ctx->d_pts, n * CDP_AFFINE_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_scalars, n * CDP_SCALAR_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_out, CDP_JACOBIAN_BYTES));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, affine_pts, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(msm_single_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_jac, ctx->d_out.ptr, CDP_JACOBIAN_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDP_OK;
+}
+
+extern "C" int cdp_msm_from_projective(cdp_ctx *ctx, const uint8_t *jac_pts, const uint8_t *scalars, size_t n,
+                                       uint8_t out_jac[CDP_JACOBIAN_BYTES]) {
+    if (!ctx || !out_jac || (n && (!jac_pts || !scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_from_projective: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) {
+        memcpy(out_jac, INF_JAC_ZERO, CDP_JACOBIAN_BYTES);
+        return CDP_OK;
+    }
+    TRY(ensure_dev(ctx, ctx->d_jac, n * CDP_JACOBIAN_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_pts, n * CDP_AFFINE_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_scalars, n * CDP_SCALAR_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_out, CDP_JACOBIAN_BYTES));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_jac.ptr, jac_pts, n * CDP_JACOBIAN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(normalize_dev(ctx, (const uint8_t *)ctx->d_jac.ptr, n, (uint8_t *)ctx->d_pts.ptr, nullptr));
+    TRY(msm_single_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_jac, ctx->d_out.ptr, CDP_JACOBIAN_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDP_OK;
+}
+
+extern "C" int cdp_msm_batch(cdp_ctx *ctx, const cdp_msm_desc *descs, size_t count, uint8_t *out_jac) {
+    if (!ctx || (count && (!descs || !out_jac))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_batch: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (count == 0) return CDP_OK;
+    // pack all bases / scalars; MSMs are grouped into launches by window-size class
+    size_t total = 0;
+    for (size_t i = 0; i < count; i++) {
+        if (descs[i].n && (!descs[i].affine_pts || !descs[i].scalars)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_batch: null segment");
+        total += descs[i].n;
+    }
+    if (total >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm_batch: too many points");
+    // segments longer than the CTA capacity go through the single-MSM path
+    std::vector<size_t> order[5], big;
+    auto cls = [](size_t n) { return n >= 96 ? 0 : n >= 40 ? 1 : n >= 12 ? 2 : n >= 3 ? 3 : 4; };
+    for (size_t i = 0; i < count; i++) {
+        if (descs[i].n > SMALL_MSM_MAX_N) big.push_back(i);
+        else if (descs[i].n == 0) memcpy(out_jac + i * CDP_JACOBIAN_BYTES, INF_JAC_ZERO, CDP_JACOBIAN_BYTES);
+        else order[cls(descs[i].n)].push_back(i);
+    }
+    size_t small_total = 0, small_count = 0;
+    for (auto &o : order) for (size_t i : o) { small_total += descs[i].n; small_count++; }
+    if (small_count) {
+        size_t bytes_pts = small_total * CDP_AFFINE_BYTES, bytes_sc = small_total * CDP_SCALAR_BYTES, bytes_seg = small_count * sizeof(msm_seg_t);
+        TRY(ensure_host(ctx, ctx->h_stage, bytes_pts + bytes_sc + bytes_seg + small_count * CDP_JACOBIAN_BYTES));
+        TRY(ensure_dev(ctx, ctx->d_pts, bytes_pts));
+        TRY(ensure_dev(ctx, ctx->d_scalars, bytes_sc));
+        TRY(ensure_dev(ctx, ctx->d_segs, bytes_seg));
+        TRY(ensure_dev(ctx, ctx->d_jac, small_count * CDP_JACOBIAN_BYTES));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        uint8_t *hp = (uint8_t *)ctx->h_stage.ptr, *hs = hp + bytes_pts;
+        msm_seg_t *hseg = (msm_seg_t *)(hs + bytes_sc);
+        uint8_t *hout = (uint8_t *)(hseg + small_count);
+        size_t off = 0, k = 0;
+        for (auto &o : order)
+            for (size_t i : o) {
+                memcpy(hp + off * CDP_AFFINE_BYTES, descs[i].affine_pts, descs[i].n * CDP_AFFINE_BYTES);
+                memcpy(hs + off * CDP_SCALAR_BYTES, descs[i].scalars, descs[i].n * CDP_SCALAR_BYTES);
+                hseg[k].pts_off = (uint32_t)off; hseg[k].scalars_off = (uint32_t)off; hseg[k].n = (uint32_t)descs[i].n; hseg[k].pad = 0;
+                off += descs[i].n; k++;
+            }
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, hp, bytes_pts, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, hs, bytes_sc, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, hseg, bytes_seg, cudaMemcpyHostToDevice, ctx->stream));
+        size_t first = 0;
+        for (auto &o : order) {
+            if (o.empty()) continue;
+            size_t max_n = 0;
+            for (size_t i : o) max_n = std::max(max_n, descs[i].n);
+            TRY(cdp_msm_batch_dev(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr,
+                                  reinterpret_cast<const cdp_msm_seg *>(ctx->d_segs.ptr) + first, o.size(), max_n,
+                                  (uint8_t *)ctx->d_jac.ptr + first * CDP_JACOBIAN_BYTES));
+            first += o.size();
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(hout, ctx->d_jac.ptr, small_count * CDP_JACOBIAN_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        k = 0;
+        for (auto &o : order)
+            for (size_t i : o) memcpy(out_jac + i * CDP_JACOBIAN_BYTES, hout + (k++) * CDP_JACOBIAN_BYTES, CDP_JACOBIAN_BYTES);
+    }
+    for (size_t i : big) TRY(cdp_msm(ctx, descs[i].affine_pts, descs[i].scalars, descs[i].n, out_jac + i * CDP_JACOBIAN_BYTES));
+    return CDP_OK;
+}
+
+static int smul_host(cdp_ctx *ctx, const uint8_t *pts, const uint8_t *scalars, size_t n_scalars, int bcast, const uint8_t *add, size_t n,
+                     uint8_t *out_affine) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return CDP_OK;
+    TRY(ensure_dev(ctx, ctx->d_pts, n * CDP_AFFINE_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_scalars, n_scalars * CDP_SCALAR_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_jac, n * CDP_JACOBIAN_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_out, n * CDP_AFFINE_BYTES));
+    if (add) TRY(ensure_dev(ctx, ctx->d_aux, n * CDP_AFFINE_BYTES));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, pts, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n_scalars * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    if (add) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_aux.ptr, add, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(smul_add_dev(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, nullptr, bcast,
+                     add ? (const uint8_t *)ctx->d_aux.ptr : nullptr, n, (uint8_t *)ctx->d_jac.ptr));
+    TRY(normalize_dev(ctx, (const uint8_t *)ctx->d_jac.ptr, n, (uint8_t *)ctx->d_out.ptr, nullptr));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_affine, ctx->d_out.ptr, n * CDP_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDP_OK;
+}
+
+extern "C" int cdp_fold(cdp_ctx *ctx, const uint8_t *L_affine, const uint8_t *R_affine, const uint8_t gamma[CDP_SCALAR_BYTES], size_t n,
+                        uint8_t *out_affine) {
+    if (!ctx || !gamma || (n && (!L_affine || !R_affine || !out_affine))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_fold: null argument");
+    return smul_host(ctx, R_affine, gamma, 1, 1, L_affine, n, out_affine);
+}
+extern "C" int cdp_scalar_mul_batch(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *scalars, size_t n, uint8_t *out_affine) {
+    if (!ctx || (n && (!affine_pts || !scalars || !out_affine))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_scalar_mul_batch: null argument");
+    return smul_host(ctx, affine_pts, scalars, n, 0, nullptr, n, out_affine);
+}
+
+static int normalize_host(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out, bool compressed) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return CDP_OK;
+    size_t out_bytes = n * (compressed ? CDP_COMPRESSED_BYTES : CDP_AFFINE_BYTES);
+    TRY(ensure_dev(ctx, ctx->d_jac, n * CDP_JACOBIAN_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_out, out_bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_jac.ptr, jac_pts, n * CDP_JACOBIAN_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(normalize_dev(ctx, (const uint8_t *)ctx->d_jac.ptr, n, compressed ? nullptr : (uint8_t *)ctx->d_out.ptr,
+                      compressed ? (uint8_t *)ctx->d_out.ptr : nullptr));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDP_OK;
+}
+extern "C" int cdp_normalize_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out_affine) {
+    if (!ctx || (n && (!jac_pts || !out_affine))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_normalize_batch: null argument");
+    return normalize_host(ctx, jac_pts, n, out_affine, false);
+}
+extern "C" int cdp_compress_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out_compressed) {
+    if (!ctx || (n && (!jac_pts || !out_compressed))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_compress_batch: null argument");
+    return normalize_host(ctx, jac_pts, n, out_compressed, true);
+}
+
+// =================================================================================================== diagnostics
+extern "C" int cdp_bench_kernel(cdp_ctx *ctx, int which, int blocks, int threads, int iters, float *ms_out) {
+    if (!ctx || !ms_out || blocks <= 0 || threads <= 0 || threads > 256) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_bench_kernel: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure_dev(ctx, ctx->d_out, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    CUDA_TRY(ctx, launch_bench(ctx->stream, which, (uint32_t *)ctx->d_out.ptr, blocks, threads, 8));  // warm-up
+    CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+    CUDA_TRY(ctx, launch_bench(ctx->stream, which, (uint32_t *)ctx->d_out.ptr, blocks, threads, iters));
+    CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(e1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms_out, e0, e1));
+    ctx->launches += 2;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return CDP_OK;
+}

@@ -1,0 +1,300 @@
+// BLS12-381 base field Fp for sm_100a: 12 x 32-bit limbs held in registers, Montgomery form (R = 2^384),
+// values always fully reduced to [0, p).
+//
+// This is the device counterpart of what the reference obtains from ark-ff's `Fp384` (Montgomery, 6 x u64 --
+// the same bytes as 12 x u32 little-endian) underneath every group operation reached from
+// `util::msm` (/root/reference/src/util.rs:19-22) and the fold loops
+// (/root/reference/src/inner_product_argument.rs:174-179, src/same_multiscalar_argument.rs:126-131).
+//
+// Multiplication is a column-wise (product-scanning) Montgomery product: every 32x32->64 partial product is one
+// `mad.lo.cc / madc.hi.cc` pair, which ptxas fuses into a single IMAD.WIDE.U32 with carry-out, plus one IADD3.X
+// for the third accumulator word.  300 IMAD-pipe instructions per product, 48 live registers, no local memory.
+// No tensor cores: 381-bit modular integer arithmetic is not a dense contraction.
+#pragma once
+#include <stdint.h>
+#include "constants.cuh"
+
+namespace cdp {
+
+struct fp {
+    uint32_t v[12];
+};
+
+// p as immediates (ptxas folds these into the instruction stream / constant bank)
+#define CDP_P(i) (fp_p_limb(i))
+
+__device__ __forceinline__ void fp_set_zero(fp &r) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = 0;
+}
+__device__ __forceinline__ void fp_set_one(fp &r) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = fp_r_mod_p_limb(i);
+}
+__device__ __forceinline__ bool fp_is_zero(const fp &a) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc |= a.v[i];
+    return acc == 0;
+}
+__device__ __forceinline__ bool fp_eq(const fp &a, const fp &b) {
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc |= a.v[i] ^ b.v[i];
+    return acc == 0;
+}
+__device__ __forceinline__ void fp_select(fp &r, const fp &a, const fp &b, bool take_b) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.v[i] = take_b ? b.v[i] : a.v[i];
+}
+
+// t = a - p, returns borrow (1 when a < p)
+__device__ __forceinline__ uint32_t fp_sub_p(fp &t, const fp &a) {
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %13, %25;\n\t"
+        "subc.cc.u32 %1, %14, %26;\n\t"
+        "subc.cc.u32 %2, %15, %27;\n\t"
+        "subc.cc.u32 %3, %16, %28;\n\t"
+        "subc.cc.u32 %4, %17, %29;\n\t"
+        "subc.cc.u32 %5, %18, %30;\n\t"
+        "subc.cc.u32 %6, %19, %31;\n\t"
+        "subc.cc.u32 %7, %20, %32;\n\t"
+        "subc.cc.u32 %8, %21, %33;\n\t"
+        "subc.cc.u32 %9, %22, %34;\n\t"
+        "subc.cc.u32 %10, %23, %35;\n\t"
+        "subc.cc.u32 %11, %24, %36;\n\t"
+        "subc.u32 %12, 0, 0;"
+        : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]), "=r"(t.v[6]), "=r"(t.v[7]),
+          "=r"(t.v[8]), "=r"(t.v[9]), "=r"(t.v[10]), "=r"(t.v[11]), "=r"(borrow)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]),
+          "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(CDP_P(0)), "r"(CDP_P(1)), "r"(CDP_P(2)), "r"(CDP_P(3)), "r"(CDP_P(4)),
+          "r"(CDP_P(5)), "r"(CDP_P(6)), "r"(CDP_P(7)), "r"(CDP_P(8)), "r"(CDP_P(9)), "r"(CDP_P(10)), "r"(CDP_P(11)));
+    return borrow;  // 0xffffffff when a < p, else 0
+}
+
+__device__ __forceinline__ void fp_add(fp &r, const fp &a, const fp &b) {
+    fp s, t;
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, %33;\n\t"
+        "addc.cc.u32 %10, %22, %34;\n\t"
+        "addc.u32 %11, %23, %35;"
+        : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]), "=r"(s.v[6]), "=r"(s.v[7]),
+          "=r"(s.v[8]), "=r"(s.v[9]), "=r"(s.v[10]), "=r"(s.v[11])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]),
+          "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+          "r"(b.v[6]), "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
+    uint32_t borrow = fp_sub_p(t, s);
+    fp_select(r, t, s, borrow != 0);
+}
+
+__device__ __forceinline__ void fp_sub(fp &r, const fp &a, const fp &b) {
+    fp d;
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %13, %25;\n\t"
+        "subc.cc.u32 %1, %14, %26;\n\t"
+        "subc.cc.u32 %2, %15, %27;\n\t"
+        "subc.cc.u32 %3, %16, %28;\n\t"
+        "subc.cc.u32 %4, %17, %29;\n\t"
+        "subc.cc.u32 %5, %18, %30;\n\t"
+        "subc.cc.u32 %6, %19, %31;\n\t"
+        "subc.cc.u32 %7, %20, %32;\n\t"
+        "subc.cc.u32 %8, %21, %33;\n\t"
+        "subc.cc.u32 %9, %22, %34;\n\t"
+        "subc.cc.u32 %10, %23, %35;\n\t"
+        "subc.cc.u32 %11, %24, %36;\n\t"
+        "subc.u32 %12, 0, 0;"
+        : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]), "=r"(d.v[6]), "=r"(d.v[7]),
+          "=r"(d.v[8]), "=r"(d.v[9]), "=r"(d.v[10]), "=r"(d.v[11]), "=r"(borrow)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]), "r"(a.v[8]),
+          "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+          "r"(b.v[6]), "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
+    // add back (p & borrow)
+    asm("add.cc.u32 %0, %0, %12;\n\t"
+        "addc.cc.u32 %1, %1, %13;\n\t"
+        "addc.cc.u32 %2, %2, %14;\n\t"
+        "addc.cc.u32 %3, %3, %15;\n\t"
+        "addc.cc.u32 %4, %4, %16;\n\t"
+        "addc.cc.u32 %5, %5, %17;\n\t"
+        "addc.cc.u32 %6, %6, %18;\n\t"
+        "addc.cc.u32 %7, %7, %19;\n\t"
+        "addc.cc.u32 %8, %8, %20;\n\t"
+        "addc.cc.u32 %9, %9, %21;\n\t"
+        "addc.cc.u32 %10, %10, %22;\n\t"
+        "addc.u32 %11, %11, %23;"
+        : "+r"(d.v[0]), "+r"(d.v[1]), "+r"(d.v[2]), "+r"(d.v[3]), "+r"(d.v[4]), "+r"(d.v[5]), "+r"(d.v[6]), "+r"(d.v[7]),
+          "+r"(d.v[8]), "+r"(d.v[9]), "+r"(d.v[10]), "+r"(d.v[11])
+        : "r"(CDP_P(0) & borrow), "r"(CDP_P(1) & borrow), "r"(CDP_P(2) & borrow), "r"(CDP_P(3) & borrow), "r"(CDP_P(4) & borrow),
+          "r"(CDP_P(5) & borrow), "r"(CDP_P(6) & borrow), "r"(CDP_P(7) & borrow), "r"(CDP_P(8) & borrow), "r"(CDP_P(9) & borrow),
+          "r"(CDP_P(10) & borrow), "r"(CDP_P(11) & borrow));
+    r = d;
+}
+__device__ __forceinline__ void fp_dbl(fp &r, const fp &a) { fp_add(r, a, a); }
+__device__ __forceinline__ void fp_neg(fp &r, const fp &a) {
+    fp z;
+    fp_set_zero(z);
+    fp_sub(r, z, a);  // 0 - 0 = 0 stays canonical
+}
+
+// acc(96 bit) += x * y
+__device__ __forceinline__ void mac96(uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t x, uint32_t y) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(a0), "+r"(a1), "+r"(a2)
+        : "r"(x), "r"(y));
+}
+// acc(96 bit) += 2 * s(96 bit)   (squaring: the column's cross terms are summed once, then doubled here)
+__device__ __forceinline__ void acc96_add2(uint32_t &a0, uint32_t &a1, uint32_t &a2, uint32_t s0, uint32_t s1, uint32_t s2) {
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, %5;\n\t"
+        "add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, %5;"
+        : "+r"(a0), "+r"(a1), "+r"(a2)
+        : "r"(s0), "r"(s1), "r"(s2));
+}
+
+// Montgomery reduction tail shared by mul and sqr is inlined in both (the m[] words stay in registers).
+__device__ __forceinline__ void fp_final_sub(fp &r) {
+    fp t;
+    uint32_t borrow = fp_sub_p(t, r);
+    fp_select(r, t, r, borrow != 0);
+}
+
+__device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) {
+    uint32_t m[12];
+    fp out;
+    uint32_t a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+#pragma unroll
+        for (int j = 0; j <= c; j++) mac96(a0, a1, a2, a.v[j], b.v[c - j]);
+#pragma unroll
+        for (int j = 0; j < c; j++) mac96(a0, a1, a2, m[j], CDP_P(c - j));
+        m[c] = a0 * FP_INV32;
+        mac96(a0, a1, a2, m[c], CDP_P(0));
+        a0 = a1; a1 = a2; a2 = 0;
+    }
+#pragma unroll
+    for (int c = 12; c < 24; c++) {
+#pragma unroll
+        for (int j = c - 11; j < 12; j++) mac96(a0, a1, a2, a.v[j], b.v[c - j]);
+#pragma unroll
+        for (int j = c - 11; j < 12; j++) mac96(a0, a1, a2, m[j], CDP_P(c - j));
+        out.v[c - 12] = a0;
+        a0 = a1; a1 = a2; a2 = 0;
+    }
+    fp_final_sub(out);
+    r = out;
+}
+
+__device__ __forceinline__ void fp_sqr(fp &r, const fp &a) {
+    uint32_t m[12];
+    fp out;
+    uint32_t a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int c = 0; c < 12; c++) {
+        uint32_t s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; 2 * j < c; j++) mac96(s0, s1, s2, a.v[j], a.v[c - j]);
+        if (c > 0) acc96_add2(a0, a1, a2, s0, s1, s2);
+        if ((c & 1) == 0) mac96(a0, a1, a2, a.v[c / 2], a.v[c / 2]);
+#pragma unroll
+        for (int j = 0; j < c; j++) mac96(a0, a1, a2, m[j], CDP_P(c - j));
+        m[c] = a0 * FP_INV32;
+        mac96(a0, a1, a2, m[c], CDP_P(0));
+        a0 = a1; a1 = a2; a2 = 0;
+    }
+#pragma unroll
+    for (int c = 12; c < 24; c++) {
+        uint32_t s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = c - 11; 2 * j < c; j++) mac96(s0, s1, s2, a.v[j], a.v[c - j]);
+        if (c < 22) acc96_add2(a0, a1, a2, s0, s1, s2);
+        if ((c & 1) == 0) mac96(a0, a1, a2, a.v[c / 2], a.v[c / 2]);
+#pragma unroll
+        for (int j = c - 11; j < 12; j++) mac96(a0, a1, a2, m[j], CDP_P(c - j));
+        out.v[c - 12] = a0;
+        a0 = a1; a1 = a2; a2 = 0;
+    }
+    fp_final_sub(out);
+    r = out;
+}
+
+// Montgomery <-> canonical
+__device__ __forceinline__ void fp_from_mont(fp &r, const fp &a) {
+    fp one;
+    fp_set_zero(one);
+    one.v[0] = 1;
+    fp_mul(r, a, one);
+}
+__device__ __forceinline__ void fp_to_mont(fp &r, const fp &a) {
+    fp r2;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r2.v[i] = FP_R2_MOD_P[i];
+    fp_mul(r, a, r2);
+}
+
+// a^(p-2): fixed exponent, uniform control flow across the warp (4-bit fixed window).
+static __device__ __noinline__ void fp_inv(fp &r, const fp &a) {
+    fp tbl[16];  // tbl[k] = a^k ; lives in local memory -- indexed dynamically, 15 muls to build
+    fp_set_one(tbl[0]);
+    tbl[1] = a;
+#pragma unroll 1
+    for (int k = 2; k < 16; k++) fp_mul(tbl[k], tbl[k - 1], a);
+    fp acc;
+    fp_set_one(acc);
+    bool started = false;
+#pragma unroll 1
+    for (int w = 95; w >= 0; w--) {  // 96 nibbles of the 384-bit exponent
+        uint32_t nib = (FP_P_MINUS_2[w >> 3] >> ((w & 7) * 4)) & 0xF;
+        if (started) {
+            fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc);
+        }
+        if (nib) {
+            fp_mul(acc, acc, tbl[nib]);
+            started = true;
+        }
+    }
+    r = acc;
+}
+
+// true when the canonical value of y is > (p-1)/2, i.e. y > -y : the "sign" bit of the ZCash encoding
+__device__ __forceinline__ bool fp_canon_is_lexicographically_largest(const fp &y_canon) {
+    // compare with (p-1)/2 from the top limb down
+    bool gt = false, decided = false;
+#pragma unroll
+    for (int i = 11; i >= 0; i--) {
+        uint32_t h = FP_P_MINUS_1_DIV_2[i];
+        if (!decided && y_canon.v[i] != h) {
+            gt = y_canon.v[i] > h;
+            decided = true;
+        }
+    }
+    return gt;
+}
+
+__device__ __forceinline__ void fp_load(fp &r, const uint32_t *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1], c = q[2];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+}
+__device__ __forceinline__ void fp_store(uint32_t *p, const fp &r) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+    q[2] = make_uint4(r.v[8], r.v[9], r.v[10], r.v[11]);
+}
+
+}  // namespace cdp

@@ -1,0 +1,68 @@
+#include "launch.h"
+#include "msm_common.cuh"
+
+namespace cdp {
+
+// One thread per MSM: result = sum_w 2^(c*w) * W_w, Horner from the top window down.
+__global__ void __launch_bounds__(64) k_msm_combine(const uint32_t *__restrict__ win_sums, uint32_t *__restrict__ out_jac,
+                                                    uint32_t n_msm, int c, int nwin) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_msm) return;
+    g1j acc;
+    g1j_load(acc, win_sums + 36 * ((size_t)i * nwin + (nwin - 1)));
+#pragma unroll 1
+    for (int w = nwin - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
+        g1j W;
+        g1j_load(W, win_sums + 36 * ((size_t)i * nwin + w));
+        g1j_add(acc, acc, W);
+    }
+    g1j_store(out_jac + 36 * (size_t)i, acc);
+}
+
+
+// out[g] = sum_{s < per_out} in[s * group_stride + g]   -- one warp per output point
+__global__ void __launch_bounds__(128) k_sum_groups(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n_out,
+                                                    uint32_t per_out, uint32_t group_stride) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_out) return;
+    g1j acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t s = lane; s < ((per_out + 31) & ~31u); s += 32) {
+        g1j q;
+        g1j_set_inf(q);
+        if (s < per_out) g1j_load(q, in + 36 * ((size_t)s * group_stride + warp));
+        g1j_add(acc, acc, q);
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        g1j o;
+        shfl_down_g1j(o, acc, d, 32);
+        g1j_add(acc, acc, o);
+    }
+    if (lane == 0) g1j_store(out + 36 * (size_t)warp, acc);
+}
+
+cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, uint32_t count,
+                               uint32_t nmax, uint32_t *win_sums) {
+    switch (c) {
+        case 6: return launch_msm_buckets_c6(st, pts, scalars, segs, count, nmax, win_sums);
+        case 5: return launch_msm_buckets_c5(st, pts, scalars, segs, count, nmax, win_sums);
+        case 4: return launch_msm_buckets_c4(st, pts, scalars, segs, count, nmax, win_sums);
+        case 3: return launch_msm_buckets_c3(st, pts, scalars, segs, count, nmax, win_sums);
+        case 2: return launch_msm_buckets_c2(st, pts, scalars, segs, count, nmax, win_sums);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *win_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin) {
+    k_msm_combine<<<(n_msm + 63) / 64, 64, 0, st>>>(win_sums, out_jac, n_msm, c, nwin);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride) {
+    k_sum_groups<<<(n_out * 32 + 127) / 128, 128, 0, st>>>(in, out, n_out, per_out, group_stride);
+    return cudaGetLastError();
+}
+
+}  // namespace cdp

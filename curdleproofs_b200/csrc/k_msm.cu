@@ -1,0 +1,164 @@
+// Compiled once per window width: -DMSM_C=2..6 (see Makefile); each object exports launch_msm_buckets_c<MSM_C>.
+#include "launch.h"
+#include "msm_common.cuh"
+
+#ifndef MSM_C
+#error "compile with -DMSM_C=<2..6>"
+#endif
+
+namespace cdp {
+
+// k_msm_buckets: bucket phase of a batch of independent small MSMs -- `util::msm` (/root/reference/src/util.rs:19-22).
+// Scalars are GLV-split (2n half-width "points": 2j -> P_j with k1, 2j+1 -> phi(P_j) with k2) and recoded into signed
+// radix-2^c digits; lane (w, b) owns bucket b of window w:
+//   phase 0  split + digits into shared memory (int8, one row per window)
+//   phase 1  each lane counts its bucket, a warp-shuffle scan over the nb lanes of the window gives list offsets
+//   phase 2  each lane writes its own index list (uint16 point id | sign bit) -- no atomics, no contention
+//   phase 3  each lane adds ITS OWN points (different lanes, different points => no serialisation); mixed adds
+//   phase 4  sum_b (b+1) B_b by a suffix scan + tree sum with warp shuffles (2*log2(nb) Jacobian adds deep)
+//   phase 5  lane b = 0 writes the window sum; k_msm_combine does the doublings
+// Handles infinity bases and zero scalars (digits 0) and all-equal scalars (one long list, still correct).
+//
+// dynamic shared memory: int8 digits[WPB][dstride] ; uint16 lists[WPB][2*nmax]
+// grid = (n_msm, ceil(NWIN / WPB)): the windows of one MSM are split over blockIdx.y so that a CTA stays <= 384 threads
+// (<= 168 registers per thread, no spills).
+template <int C, int WPB>
+__global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
+    k_msm_buckets(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars, const msm_seg_t *__restrict__ segs,
+                  uint32_t *__restrict__ win_sums /* [msm][nwin] jacobian */, uint32_t nmax) {
+    constexpr int NB = 1 << (C - 1);
+    constexpr int NWIN = (130 + C - 1) / C;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const msm_seg_t seg = segs[blockIdx.x];
+    const uint32_t n = seg.n, n2 = 2 * n;
+    const int w0 = blockIdx.y * WPB;
+    const uint32_t dstride = 2 * nmax + 4;  // +4: rows of different windows fall into different banks
+    int8_t *digits = reinterpret_cast<int8_t *>(smem);
+    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + ((WPB * dstride + 15) & ~15u));
+    const uint32_t *P = pts + 24 * (size_t)seg.pts_off;
+    const uint32_t *S = scalars + 8 * (size_t)seg.scalars_off;
+
+    // ---- phase 0
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        uint32_t k[8];
+        const uint4 *sp = reinterpret_cast<const uint4 *>(S + 8 * (size_t)j);
+        uint4 a = sp[0], b = sp[1];
+        k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+        // infinity base: contributes nothing
+        const uint4 *pp = reinterpret_cast<const uint4 *>(P + 24 * (size_t)j);
+        uint32_t nz = 0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            uint4 v = pp[q];
+            nz |= v.x | v.y | v.z | v.w;
+        }
+        glv_t g;
+        glv_split(g, k);
+        if (nz == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) g.k1[q] = g.k2[q] = 0;
+        }
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int w = 0; w < NWIN; w++) {
+                const int bit = w * C, li = bit >> 5, sh = bit & 31;
+                uint32_t v = 0;
+                if (li < 4) v = (half ? g.k2[li] : g.k1[li]) >> sh;
+                if (sh + C > 32 && li + 1 < 4) v |= (half ? g.k2[li + 1] : g.k1[li + 1]) << (32 - sh);
+                v = (v & ((1u << C) - 1)) + carry;
+                carry = (v + NB) >> C;  // recentre to [-NB, NB)
+                int d = (int)v - (int)(carry << C);
+                if (w >= w0 && w < w0 + WPB) digits[(w - w0) * dstride + 2 * j + half] = (int8_t)d;
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lane_id = threadIdx.x;
+    const int wl = lane_id / NB, b = lane_id % NB;
+    const int w = w0 + wl;
+    const bool active = wl < WPB && w < NWIN;
+    // ---- phase 1: count
+    uint32_t cnt = 0;
+    if (active) {
+        const int8_t *row = digits + wl * dstride;
+        for (uint32_t p = 0; p < n2; p++) {
+            int d = row[p];
+            int ad = d < 0 ? -d : d;
+            cnt += (ad == b + 1);
+        }
+    }
+    // exclusive scan of cnt over the NB lanes of this window (NB <= 32, windows are NB-aligned inside a warp)
+    uint32_t off = cnt;
+#pragma unroll
+    for (int d = 1; d < NB; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, off, d, NB);
+        if (b >= d) off += o;
+    }
+    off -= cnt;
+    // ---- phase 2: lists
+    if (active) {
+        const int8_t *row = digits + wl * dstride;
+        uint16_t *lst = lists + (size_t)wl * (2 * nmax) + off;
+        uint32_t e = 0;
+        for (uint32_t p = 0; p < n2; p++) {
+            int d = row[p];
+            int ad = d < 0 ? -d : d;
+            if (ad == b + 1) lst[e++] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
+        }
+    }
+    __syncwarp();
+    // ---- phase 3: accumulate own bucket
+    g1j acc;
+    g1j_set_inf(acc);
+    if (active) {
+        const uint16_t *lst = lists + (size_t)wl * (2 * nmax) + off;
+#pragma unroll 1
+        for (uint32_t e = 0; e < cnt; e++) {
+            uint32_t id = lst[e];
+            uint32_t p = id & 0x7FFFu;
+            g1a q;
+            g1a_load(q, P + 24 * (size_t)(p >> 1));
+            if (p & 1) fp_mul_beta(q.x, q.x);
+            if (id & 0x8000u) fp_neg(q.y, q.y);
+            g1j_add_mixed(acc, acc, q);
+        }
+    }
+    // ---- phase 4: window reduction  S = sum_b (b+1) * B_b = sum_j suffix_j.  One loop, one inlined addition:
+    //      steps 0 .. C-2     inclusive suffix scan, distance 1, 2, 4, ...
+    //      steps C-1 .. 2C-3  tree sum of the suffix sums, distance NB/2, ..., 1
+    if (NB > 1) {
+#pragma unroll 1
+        for (int step = 0; step < 2 * (C - 1); step++) {
+            const bool scan = step < C - 1;
+            const int d = scan ? (1 << step) : (NB >> (step - (C - 1) + 1));
+            g1j o;
+            shfl_down_g1j(o, acc, d, NB);
+            const bool take = scan ? (b + d < NB) : (b < d);
+            if (take) g1j_add(acc, acc, o);
+        }
+    }
+    // ---- phase 5
+    if (active && b == 0) g1j_store(win_sums + 36 * ((size_t)blockIdx.x * NWIN + w), acc);
+}
+
+#define CDP_CAT2(a, b) a##b
+#define CDP_CAT(a, b) CDP_CAT2(a, b)
+cudaError_t CDP_CAT(launch_msm_buckets_c, MSM_C)(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs,
+                                                 uint32_t count, uint32_t nmax, uint32_t *win_sums) {
+    constexpr int C = MSM_C, WPB = msm_wpb_for(MSM_C), NWIN = msm_nwin_for(MSM_C);
+    constexpr int threads = ((WPB << (C - 1)) + 31) / 32 * 32;
+    size_t smem = msm_smem_bytes(C, nmax);
+    auto kern = k_msm_buckets<C, WPB>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid(count, (NWIN + WPB - 1) / WPB);
+    kern<<<grid, threads, smem, st>>>(pts, scalars, segs, win_sums, nmax);
+    return cudaGetLastError();
+}
+
+}  // namespace cdp

@@ -1,0 +1,52 @@
+// sm_100a kernels of the curdleproofs MSM / fold hot path.
+//
+//   k_smul_add        out[i] = A[i] + s[idx(i)] * P[i]        fold loops (inner_product_argument.rs:174-179,
+//                                                             same_multiscalar_argument.rs:126-131), the CRS rescale
+//                                                             (grand_product_argument.rs:92-102), shuffling (util.rs:94-95)
+//   k_normalize       Jacobian -> affine (+ 48-byte encoding) `into_affine()` / `normalize_batch` (util.rs:27),
+//                                                             `serialize_compressed` (transcript.rs:29-33)
+//   k_msm_buckets     bucket phase of a batch of independent  `util::msm` (util.rs:19-22) at every call site of
+//                     small MSMs, one CTA per MSM               CurdleproofsProof::new / verify
+//   k_msm_combine     window combine (Horner) per MSM
+//
+// All of it is 32-bit integer multiply-add work on the FMA pipe (IMAD.WIDE.U32); no tensor cores.
+// Host-side launchers, one per translation unit (the kernels are compiled in parallel, without -rdc).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cdp {
+
+struct msm_seg_t {
+    uint32_t pts_off;      // first base, in points, into the launch's base array
+    uint32_t scalars_off;  // first scalar, in scalars
+    uint32_t n;
+    uint32_t pad;
+};
+
+cudaError_t launch_smul_add(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const uint32_t *sidx, int bcast,
+                            const uint32_t *add_pts, uint32_t *out_jac, uint32_t n);
+cudaError_t launch_normalize(cudaStream_t st, int chunk, const uint32_t *jac, uint32_t *out_affine, uint8_t *out_comp, uint32_t n);
+// window sums of `count` MSM segments; c in 2..6 selects the kernel instantiation
+cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, uint32_t count,
+                               uint32_t nmax, uint32_t *win_sums);
+#define CDP_DECL_MSM(C)                                                                                                         \
+    cudaError_t launch_msm_buckets_c##C(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, \
+                                        uint32_t count, uint32_t nmax, uint32_t *win_sums);
+CDP_DECL_MSM(2) CDP_DECL_MSM(3) CDP_DECL_MSM(4) CDP_DECL_MSM(5) CDP_DECL_MSM(6)
+#undef CDP_DECL_MSM
+cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *win_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin);
+cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride);
+
+// which: 0 = raw IMAD.WIDE chains (128 multiply-adds / thread / iteration), 1 = Fp mul chain, 2 = Fp sqr chain (1 / thread / iteration)
+cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, int threads, int iters);
+
+// geometry shared by host and device
+constexpr int msm_nwin_for(int c) { return (130 + c - 1) / c; }
+constexpr int msm_wpb_for(int c) { return c == 6 ? 11 : c == 5 ? 13 : c == 4 ? 33 : c == 3 ? 44 : 65; }
+inline size_t msm_smem_bytes(int c, size_t nmax) {
+    size_t wpb = msm_wpb_for(c), dstride = 2 * nmax + 4;
+    return ((wpb * dstride + 15) & ~size_t(15)) + wpb * 2 * nmax * sizeof(uint16_t);
+}
+
+}  // namespace cdp

@@ -1,0 +1,196 @@
+"""ctypes binding of include/cdp_msm.h.  Byte layouts are documented in that header."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint32, c_uint64, c_void_p
+
+FP_BYTES, SCALAR_BYTES, AFFINE_BYTES, JACOBIAN_BYTES, COMPRESSED_BYTES = 48, 32, 96, 144, 48
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libcdp_b200.so")
+
+
+class CdpError(RuntimeError):
+    pass
+
+
+class _MsmDesc(ctypes.Structure):
+    _fields_ = [("affine_pts", c_void_p), ("scalars", c_void_p), ("n", c_size_t)]
+
+
+_SIGS = {
+    "cdp_ctx_create": (c_int, [POINTER(c_void_p), c_int, c_void_p]),
+    "cdp_ctx_destroy": (None, [c_void_p]),
+    "cdp_last_error": (c_char_p, [c_void_p]),
+    "cdp_launch_count": (c_uint64, [c_void_p]),
+    "cdp_sync": (c_int, [c_void_p]),
+    "cdp_msm": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_msm_from_projective": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_msm_batch": (c_int, [c_void_p, POINTER(_MsmDesc), c_size_t, c_void_p]),
+    "cdp_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_scalar_mul_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_normalize_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_compress_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_dev_alloc": (c_void_p, [c_void_p, c_size_t]),
+    "cdp_dev_free": (None, [c_void_p, c_void_p]),
+    "cdp_h2d": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "cdp_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    "cdp_host_alloc": (c_void_p, [c_void_p, c_size_t]),
+    "cdp_host_free": (None, [c_void_p, c_void_p]),
+    "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "cdp_smul_add_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
+}
+
+_LIB = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libcdp_b200.so (fails loudly when it has not been built -- there is no fallback)."""
+    global _LIB
+    if _LIB is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise CdpError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(make -C curdleproofs_b200/csrc). There is no CPU fallback.")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def _buf(b) -> ctypes.Array:
+    if isinstance(b, (bytes, bytearray, memoryview)):
+        return (ctypes.c_uint8 * len(b)).from_buffer_copy(bytes(b))
+    raise TypeError("expected a bytes-like object")
+
+
+class Engine:
+    """One context on one GPU (``cdp_ctx``)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load_library()
+        h = c_void_p()
+        rc = self._lib.cdp_ctx_create(ctypes.byref(h), device, c_void_p(stream) if stream else None)
+        if rc != 0:
+            raise CdpError(f"cdp_ctx_create failed (code {rc}): no usable sm_100 CUDA device {device}; there is no CPU fallback")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cdp_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise CdpError(f"{what} failed (code {rc}): {self._lib.cdp_last_error(self._h).decode()}")
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def lib(self):
+        return self._lib
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cdp_launch_count(self._h))
+
+    def sync(self):
+        self._check(self._lib.cdp_sync(self._h), "cdp_sync")
+
+    # ---- drop-ins ------------------------------------------------------------------------------------
+    def msm(self, points: bytes, scalars: bytes) -> bytes:
+        """`util::msm` (src/util.rs:19-22): affine points (96 B each), canonical scalars (32 B each) -> Jacobian (144 B).
+        Like the reference (`assert_eq!`, src/util.rs:20) a length mismatch is an error."""
+        if len(points) % AFFINE_BYTES or len(scalars) % SCALAR_BYTES:
+            raise ValueError("malformed input length")
+        n = len(points) // AFFINE_BYTES
+        if n != len(scalars) // SCALAR_BYTES:
+            raise ValueError("number of points != number of scalars")
+        out = (ctypes.c_uint8 * JACOBIAN_BYTES)()
+        self._check(self._lib.cdp_msm(self._h, _buf(points), _buf(scalars), n, out), "cdp_msm")
+        return bytes(out)
+
+    def msm_from_projective(self, points: bytes, scalars: bytes) -> bytes:
+        """`util::msm_from_projective` (src/util.rs:25-29)."""
+        if len(points) % JACOBIAN_BYTES or len(scalars) % SCALAR_BYTES:
+            raise ValueError("malformed input length")
+        n = len(points) // JACOBIAN_BYTES
+        if n != len(scalars) // SCALAR_BYTES:
+            raise ValueError("number of points != number of scalars")
+        out = (ctypes.c_uint8 * JACOBIAN_BYTES)()
+        self._check(self._lib.cdp_msm_from_projective(self._h, _buf(points), _buf(scalars), n, out), "cdp_msm_from_projective")
+        return bytes(out)
+
+    def msm_batch(self, items) -> list[bytes]:
+        """Independent MSMs [(points, scalars), ...] in one call."""
+        keep = []
+        descs = (_MsmDesc * len(items))()
+        for i, (p, s) in enumerate(items):
+            n = len(p) // AFFINE_BYTES
+            if n != len(s) // SCALAR_BYTES or len(p) % AFFINE_BYTES or len(s) % SCALAR_BYTES:
+                raise ValueError("number of points != number of scalars")
+            pb, sb = _buf(p) if n else None, _buf(s) if n else None
+            keep.append((pb, sb))
+            descs[i].affine_pts = ctypes.cast(pb, c_void_p) if n else None
+            descs[i].scalars = ctypes.cast(sb, c_void_p) if n else None
+            descs[i].n = n
+        out = (ctypes.c_uint8 * (JACOBIAN_BYTES * max(1, len(items))))()
+        self._check(self._lib.cdp_msm_batch(self._h, descs, len(items), out), "cdp_msm_batch")
+        raw = bytes(out)
+        return [raw[i * JACOBIAN_BYTES:(i + 1) * JACOBIAN_BYTES] for i in range(len(items))]
+
+    def fold(self, L: bytes, R: bytes, gamma: bytes) -> bytes:
+        """(L[i] + gamma * R[i]).into_affine() -- src/inner_product_argument.rs:177-178, src/same_multiscalar_argument.rs:128-130."""
+        if len(L) != len(R) or len(L) % AFFINE_BYTES or len(gamma) != SCALAR_BYTES:
+            raise ValueError("malformed input length")
+        n = len(L) // AFFINE_BYTES
+        out = (ctypes.c_uint8 * max(1, len(L)))()
+        self._check(self._lib.cdp_fold(self._h, _buf(L) if n else None, _buf(R) if n else None, _buf(gamma), n, out), "cdp_fold")
+        return bytes(out)[:len(L)]
+
+    def scalar_mul_batch(self, points: bytes, scalars: bytes) -> bytes:
+        n = len(points) // AFFINE_BYTES
+        if len(points) % AFFINE_BYTES or len(scalars) != n * SCALAR_BYTES:
+            raise ValueError("number of points != number of scalars")
+        out = (ctypes.c_uint8 * max(1, len(points)))()
+        self._check(self._lib.cdp_scalar_mul_batch(self._h, _buf(points) if n else None, _buf(scalars) if n else None, n, out),
+                    "cdp_scalar_mul_batch")
+        return bytes(out)[:len(points)]
+
+    def normalize_batch(self, jac: bytes) -> bytes:
+        n = len(jac) // JACOBIAN_BYTES
+        if len(jac) % JACOBIAN_BYTES:
+            raise ValueError("malformed input length")
+        out = (ctypes.c_uint8 * max(1, n * AFFINE_BYTES))()
+        self._check(self._lib.cdp_normalize_batch(self._h, _buf(jac) if n else None, n, out), "cdp_normalize_batch")
+        return bytes(out)[:n * AFFINE_BYTES]
+
+    def compress_batch(self, jac: bytes) -> bytes:
+        n = len(jac) // JACOBIAN_BYTES
+        if len(jac) % JACOBIAN_BYTES:
+            raise ValueError("malformed input length")
+        out = (ctypes.c_uint8 * max(1, n * COMPRESSED_BYTES))()
+        self._check(self._lib.cdp_compress_batch(self._h, _buf(jac) if n else None, n, out), "cdp_compress_batch")
+        return bytes(out)[:n * COMPRESSED_BYTES]
+
+    def bench_kernel(self, which: int, blocks: int, threads: int, iters: int) -> float:
+        ms = c_float()
+        self._check(self._lib.cdp_bench_kernel(self._h, which, blocks, threads, iters, ctypes.byref(ms)), "cdp_bench_kernel")
+        return float(ms.value)

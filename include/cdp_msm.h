@@ -1,0 +1,136 @@
+/* cdp_msm.h -- C ABI of the B200 (sm_100a) engine for the Curdleproofs MSM / fold hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one reference-side operation on the path
+ * BASELINE.json's north_star names, and is exactly what a Rust `extern "C"` block in the reference crate would bind
+ * (see INTEGRATION.md for the stub).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Byte layouts (all little-endian 64-bit limbs, i.e. the in-memory form arkworks already holds):
+ *   Fp        48 B   6 x u64, MONTGOMERY form, R = 2^384        (= ark-ff Fp384 backing array)
+ *   scalar    32 B   4 x u64, CANONICAL integer in [0, r)        (= `Fr::into_bigint()`, what ark-ec's MSM consumes)
+ *   affine    96 B   x || y ; the point at infinity is the all-zero encoding ((0,0) is not on y^2 = x^3 + 4)
+ *   jacobian 144 B   X || Y || Z (x = X/Z^2, y = Y/Z^3) ; infinity <=> Z == 0   (= ark-ec `Projective`)
+ *   compressed 48 B  big-endian x with ZCash flag bits (0x80 compressed, 0x40 infinity, 0x20 y > -y)
+ *                    (= `serialize_compressed`, pinned by the KAT at /root/reference/src/whisk.rs:363-368)
+ *
+ * Error behaviour: the reference panics on length mismatch (`assert_eq!` src/util.rs:20,26); a C ABI cannot carry
+ * slice lengths, so the caller passes one `n` for both arrays and every function returns a status code instead of
+ * aborting.  0 = CDP_OK.  Nothing here ever falls back to a CPU implementation: without a usable CUDA device
+ * `cdp_ctx_create` fails with CDP_ERR_CUDA.
+ *
+ * Threading: a context owns one CUDA stream and its scratch buffers; calls on one context are serialised by the
+ * caller.  Use one context per host thread / per GPU.
+ */
+#ifndef CDP_MSM_H
+#define CDP_MSM_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDP_OK 0
+#define CDP_ERR_INVALID_ARG 1
+#define CDP_ERR_CUDA 2
+#define CDP_ERR_TOO_LARGE 3
+#define CDP_ERR_NOT_ON_CURVE 4
+
+#define CDP_FP_BYTES 48
+#define CDP_SCALAR_BYTES 32
+#define CDP_AFFINE_BYTES 96
+#define CDP_JACOBIAN_BYTES 144
+#define CDP_COMPRESSED_BYTES 48
+
+typedef struct cdp_ctx cdp_ctx;
+
+/* ------------------------------------------------------------------ context */
+/* Create a context on CUDA device `device_id`.  `stream` may be NULL (the context creates its own stream) or an
+ * existing `cudaStream_t` cast to void* (e.g. torch.cuda.current_stream().cuda_stream) that all work is queued on. */
+int cdp_ctx_create(cdp_ctx **out, int device_id, void *stream);
+void cdp_ctx_destroy(cdp_ctx *ctx);
+/* Human-readable description of the last error on this context (never NULL). */
+const char *cdp_last_error(const cdp_ctx *ctx);
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+uint64_t cdp_launch_count(const cdp_ctx *ctx);
+/* Block until everything queued on the context's stream has finished. */
+int cdp_sync(cdp_ctx *ctx);
+
+/* ------------------------------------------------------------------ host-buffer entry points (the drop-ins) */
+/* Replaces `util::msm(points: &[G1Affine], scalars: &[Fr]) -> G1Projective`      /root/reference/src/util.rs:19-22
+ * out = sum_i scalars[i] * points[i].  n == 0 yields infinity. */
+int cdp_msm(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *scalars, size_t n, uint8_t out_jac[CDP_JACOBIAN_BYTES]);
+
+/* Replaces `util::msm_from_projective(points: &[G1Projective], scalars)`          /root/reference/src/util.rs:25-29
+ * (batch-normalise, then MSM). */
+int cdp_msm_from_projective(cdp_ctx *ctx, const uint8_t *jac_pts, const uint8_t *scalars, size_t n,
+                            uint8_t out_jac[CDP_JACOBIAN_BYTES]);
+
+/* Many independent MSMs in one launch -- what a prover round issues (4 per IPA round, src/inner_product_argument.rs:
+ * 158-161; 6 per SameMSM round, src/same_multiscalar_argument.rs:107-112), across a batch of proofs. */
+typedef struct {
+    const uint8_t *affine_pts; /* n points  */
+    const uint8_t *scalars;    /* n scalars */
+    size_t n;
+} cdp_msm_desc;
+int cdp_msm_batch(cdp_ctx *ctx, const cdp_msm_desc *descs, size_t count, uint8_t *out_jac /* count * 144 B */);
+
+/* The fold step, which the reference writes as an inline loop:
+ *   L[i] = (L[i] + R[i].mul(gamma)).into_affine()      src/inner_product_argument.rs:177-178
+ *                                                      src/same_multiscalar_argument.rs:128-130
+ * out_affine may alias L. */
+int cdp_fold(cdp_ctx *ctx, const uint8_t *L_affine, const uint8_t *R_affine, const uint8_t gamma[CDP_SCALAR_BYTES], size_t n,
+             uint8_t *out_affine);
+
+/* out[i] = (scalars[i] * pts[i]).into_affine()        src/grand_product_argument.rs:92-102 (CRS rescale),
+ *                                                      src/util.rs:94-95 (shuffling), `GroupCommitment` src/commitments.rs:50-51 */
+int cdp_scalar_mul_batch(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *scalars, size_t n, uint8_t *out_affine);
+
+/* `G1Projective::normalize_batch` / `into_affine()`    src/util.rs:27 */
+int cdp_normalize_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out_affine);
+
+/* Jacobian points -> 48-byte compressed encodings (`serialize_compressed`, src/transcript.rs:29-33, src/util.rs:125-133) */
+int cdp_compress_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out_compressed);
+
+/* ------------------------------------------------------------------ device-resident entry points
+ * Same operations on buffers that already live in HBM (bases stay resident across the rounds of a proof batch).
+ * All `d_*` arguments are device pointers on the context's device; work is queued on the context's stream and is
+ * asynchronous -- call cdp_sync() (or synchronise the stream you supplied) before reading results. */
+void *cdp_dev_alloc(cdp_ctx *ctx, size_t bytes);
+void cdp_dev_free(cdp_ctx *ctx, void *d_ptr);
+int cdp_h2d(cdp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+/* Pinned host memory for the asynchronous copies above. */
+void *cdp_host_alloc(cdp_ctx *ctx, size_t bytes);
+void cdp_host_free(cdp_ctx *ctx, void *h_ptr);
+
+/* A batch of MSMs over device-resident bases and scalars.  Segment i computes
+ *   sum_{j < n} d_scalars[scalars_off + j] * d_pts[pts_off + j]   (offsets in elements, not bytes). */
+typedef struct {
+    uint32_t pts_off;
+    uint32_t scalars_off;
+    uint32_t n;
+    uint32_t reserved;
+} cdp_msm_seg;
+/* `d_segs` is a DEVICE array of `count` cdp_msm_seg; `max_n` >= every segment's n.  Results: count Jacobian points. */
+int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs, size_t count,
+                      size_t max_n, uint8_t *d_out_jac);
+
+/* d_out_jac[i] = (d_add ? d_add[i] : O) + d_scalars[d_scalar_index ? d_scalar_index[i] : i] * d_pts[i]
+ * With d_add = L, d_pts = R and one scalar per proof this is the fold of a whole batch of proofs in one launch. */
+int cdp_smul_add_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, const uint32_t *d_scalar_index, const uint8_t *d_add,
+                     size_t n, uint8_t *d_out_jac);
+
+/* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
+int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);
+
+/* ------------------------------------------------------------------ diagnostics
+ * Integer-pipe micro-benchmarks used by bench.py for the roofline denominators.
+ * which = 0: independent IMAD.WIDE.U32 chains (128 multiply-adds per thread per iteration);
+ * which = 1 / 2: dependent chain of Fp Montgomery multiplications / squarings (one per thread per iteration).
+ * Writes the kernel time (CUDA events on the context's stream) to *ms_out. */
+int cdp_bench_kernel(cdp_ctx *ctx, int which, int blocks, int threads, int iters, float *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDP_MSM_H */
