@@ -111,7 +111,8 @@ int combine_dev(cdp_ctx *ctx, const msm_cfg &g, const uint32_t *d_win, size_t co
     return CDP_OK;
 }
 
-int normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_aff, uint8_t *d_comp) {
+int normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_aff, uint8_t *d_comp, const smul_job_t *jobs = nullptr,
+                  uint32_t elems_per_job = 1) {
     if (n == 0) return CDP_OK;
     const uint32_t *j = reinterpret_cast<const uint32_t *>(d_jac);
     uint32_t *a = reinterpret_cast<uint32_t *>(d_aff);
@@ -119,17 +120,20 @@ int normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_aff, 
     size_t fill = (size_t)ctx->sm_count * 1024;
     int chunk = n >= 8 * fill ? 8 : n >= 2 * fill ? 2 : 1;
     ctx->launches++;
-    CUDA_TRY(ctx, launch_normalize(ctx->stream, chunk, j, a, d_comp, (uint32_t)n));
+    CUDA_TRY(ctx, launch_normalize(ctx->stream, chunk, j, a, d_comp, (uint32_t)n, jobs, elems_per_job));
     return CDP_OK;
 }
 
-int smul_add_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, const uint32_t *d_sidx, int bcast, const uint8_t *d_add,
-                 size_t n, uint8_t *d_out_jac) {
-    if (n == 0) return CDP_OK;
+// d_pts[out] = affine(d_pts[add] + s * d_pts[src]) for every element of every job
+int smul_jobs_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_scalars, const smul_job_t *d_jobs, size_t n_jobs, size_t epj) {
+    size_t total = n_jobs * epj;
+    if (total == 0) return CDP_OK;
+    if (total >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_TOO_LARGE, "smul jobs: too many elements");
+    TRY(ensure_dev(ctx, ctx->d_jac, total * CDP_JACOBIAN_BYTES));
     ctx->launches++;
-    CUDA_TRY(ctx, launch_smul_add(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars), d_sidx,
-                                  bcast, reinterpret_cast<const uint32_t *>(d_add), reinterpret_cast<uint32_t *>(d_out_jac), (uint32_t)n));
-    return CDP_OK;
+    CUDA_TRY(ctx, launch_smul_jobs(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars), d_jobs,
+                                   (uint32_t)n_jobs, (uint32_t)epj, reinterpret_cast<uint32_t *>(ctx->d_jac.ptr)));
+    return normalize_dev(ctx, (const uint8_t *)ctx->d_jac.ptr, total, d_pts, nullptr, d_jobs, (uint32_t)epj);
 }
 
 const uint8_t INF_JAC_ZERO[CDP_JACOBIAN_BYTES] = {0};
@@ -236,11 +240,31 @@ extern "C" int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, cons
     return combine_dev(ctx, g, reinterpret_cast<const uint32_t *>(ctx->d_win.ptr), count, reinterpret_cast<uint32_t *>(d_out_jac));
 }
 
-extern "C" int cdp_smul_add_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, const uint32_t *d_scalar_index,
-                                const uint8_t *d_add, size_t n, uint8_t *d_out_jac) {
-    if (!ctx) return CDP_ERR_INVALID_ARG;
+extern "C" int cdp_smul_jobs_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_scalars, const cdp_smul_job *d_jobs, size_t n_jobs,
+                                 size_t elems_per_job) {
+    if (!ctx || !d_pts || !d_scalars || !d_jobs) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_smul_jobs_dev: null argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return smul_add_dev(ctx, d_pts, d_scalars, d_scalar_index, 0, d_add, n, d_out_jac);
+    static_assert(sizeof(cdp_smul_job) == sizeof(smul_job_t), "job layout");
+    return smul_jobs_dev(ctx, d_pts, d_scalars, reinterpret_cast<const smul_job_t *>(d_jobs), n_jobs, elems_per_job);
+}
+
+extern "C" int cdp_gather_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_src, const uint32_t *d_src_idx, const uint32_t *d_dst_idx, size_t n) {
+    if (!ctx || (n && (!d_pts || !d_src || !d_src_idx || !d_dst_idx))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_gather_dev: null argument");
+    if (n == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->launches++;
+    CUDA_TRY(ctx, launch_gather_points(ctx->stream, reinterpret_cast<uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_src), d_src_idx,
+                                       d_dst_idx, (uint32_t)n));
+    return CDP_OK;
+}
+
+extern "C" int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint32_t *d_index, size_t n, uint8_t *d_out_compressed) {
+    if (!ctx || (n && (!d_pts || !d_out_compressed))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_compress_affine_dev: null argument");
+    if (n == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->launches++;
+    CUDA_TRY(ctx, launch_compress_affine(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), d_index, d_out_compressed, (uint32_t)n));
+    return CDP_OK;
 }
 
 extern "C" int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed) {
@@ -260,7 +284,7 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
         segs[i].pts_off = (uint32_t)(i * chunk);
         segs[i].scalars_off = (uint32_t)(i * chunk);
         segs[i].n = (uint32_t)std::min(chunk, n - i * chunk);
-        segs[i].pad = 0;
+        segs[i].extra = 0;
     }
     TRY(ensure_dev(ctx, ctx->d_segs, nchunks * sizeof(msm_seg_t)));
     TRY(ensure_host(ctx, ctx->h_stage, nchunks * sizeof(msm_seg_t)));
@@ -357,7 +381,7 @@ extern "C" int cdp_msm_batch(cdp_ctx *ctx, const cdp_msm_desc *descs, size_t cou
             for (size_t i : o) {
                 memcpy(hp + off * CDP_AFFINE_BYTES, descs[i].affine_pts, descs[i].n * CDP_AFFINE_BYTES);
                 memcpy(hs + off * CDP_SCALAR_BYTES, descs[i].scalars, descs[i].n * CDP_SCALAR_BYTES);
-                hseg[k].pts_off = (uint32_t)off; hseg[k].scalars_off = (uint32_t)off; hseg[k].n = (uint32_t)descs[i].n; hseg[k].pad = 0;
+                hseg[k].pts_off = (uint32_t)off; hseg[k].scalars_off = (uint32_t)off; hseg[k].n = (uint32_t)descs[i].n; hseg[k].extra = 0;
                 off += descs[i].n; k++;
             }
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, hp, bytes_pts, cudaMemcpyHostToDevice, ctx->stream));
@@ -383,22 +407,31 @@ extern "C" int cdp_msm_batch(cdp_ctx *ctx, const cdp_msm_desc *descs, size_t cou
     return CDP_OK;
 }
 
+// host buffers -> one job over a combined device array [src n | add n]; the result overwrites the src range
 static int smul_host(cdp_ctx *ctx, const uint8_t *pts, const uint8_t *scalars, size_t n_scalars, int bcast, const uint8_t *add, size_t n,
                      uint8_t *out_affine) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (n == 0) return CDP_OK;
-    TRY(ensure_dev(ctx, ctx->d_pts, n * CDP_AFFINE_BYTES));
+    if (n >= (size_t(1) << 30)) return fail(ctx, CDP_ERR_TOO_LARGE, "too many points");
+    TRY(ensure_dev(ctx, ctx->d_pts, 2 * n * CDP_AFFINE_BYTES));
     TRY(ensure_dev(ctx, ctx->d_scalars, n_scalars * CDP_SCALAR_BYTES));
-    TRY(ensure_dev(ctx, ctx->d_jac, n * CDP_JACOBIAN_BYTES));
-    TRY(ensure_dev(ctx, ctx->d_out, n * CDP_AFFINE_BYTES));
-    if (add) TRY(ensure_dev(ctx, ctx->d_aux, n * CDP_AFFINE_BYTES));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, pts, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(ensure_dev(ctx, ctx->d_segs, sizeof(smul_job_t)));
+    TRY(ensure_host(ctx, ctx->h_stage, sizeof(smul_job_t)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    smul_job_t *job = (smul_job_t *)ctx->h_stage.ptr;
+    memset(job, 0, sizeof *job);
+    job->src_off = 0;
+    job->add_off = add ? (uint32_t)n : 0xFFFFFFFFu;
+    job->out_off = 0;
+    job->scalar_off = 0;
+    job->scalar_stride = bcast ? 0 : 1;
+    uint8_t *dp = (uint8_t *)ctx->d_pts.ptr;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dp, pts, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    if (add) CUDA_TRY(ctx, cudaMemcpyAsync(dp + n * CDP_AFFINE_BYTES, add, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n_scalars * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-    if (add) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_aux.ptr, add, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-    TRY(smul_add_dev(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, nullptr, bcast,
-                     add ? (const uint8_t *)ctx->d_aux.ptr : nullptr, n, (uint8_t *)ctx->d_jac.ptr));
-    TRY(normalize_dev(ctx, (const uint8_t *)ctx->d_jac.ptr, n, (uint8_t *)ctx->d_out.ptr, nullptr));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_affine, ctx->d_out.ptr, n * CDP_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, job, sizeof *job, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(smul_jobs_dev(ctx, dp, (const uint8_t *)ctx->d_scalars.ptr, (const smul_job_t *)ctx->d_segs.ptr, 1, n));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_affine, dp, n * CDP_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CDP_OK;
 }

@@ -30,7 +30,9 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
     constexpr int NWIN = (130 + C - 1) / C;
     extern __shared__ __align__(16) uint8_t smem[];
     const msm_seg_t seg = segs[blockIdx.x];
-    const uint32_t n = seg.n, n2 = 2 * n;
+    const uint32_t n_plain = seg.n;
+    const uint32_t n = seg.n + (seg.extra ? 1u : 0u), n2 = 2 * n;  // the optional extra base is logically element n_plain
+    const uint32_t *PX = seg.extra ? pts + 24 * (size_t)(seg.extra - 1) : nullptr;
     const int w0 = blockIdx.y * WPB;
     const uint32_t dstride = 2 * nmax + 4;  // +4: rows of different windows fall into different banks
     int8_t *digits = reinterpret_cast<int8_t *>(smem);
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
         uint4 a = sp[0], b = sp[1];
         k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
         // infinity base: contributes nothing
-        const uint4 *pp = reinterpret_cast<const uint4 *>(P + 24 * (size_t)j);
+        const uint4 *pp = reinterpret_cast<const uint4 *>(j < n_plain ? P + 24 * (size_t)j : PX);
         uint32_t nz = 0;
 #pragma unroll
         for (int q = 0; q < 6; q++) {
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
             uint32_t id = lst[e];
             uint32_t p = id & 0x7FFFu;
             g1a q;
-            g1a_load(q, P + 24 * (size_t)(p >> 1));
+            g1a_load(q, (p >> 1) < n_plain ? P + 24 * (size_t)(p >> 1) : PX);
             if (p & 1) fp_mul_beta(q.x, q.x);
             if (id & 0x8000u) fp_neg(q.y, q.y);
             g1j_add_mixed(acc, acc, q);

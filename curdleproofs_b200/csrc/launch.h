@@ -21,12 +21,24 @@ struct msm_seg_t {
     uint32_t pts_off;      // first base, in points, into the launch's base array
     uint32_t scalars_off;  // first scalar, in scalars
     uint32_t n;
-    uint32_t pad;
+    uint32_t extra;        // 0 = none; otherwise 1 + index of one more base, logically element n, whose scalar is scalars[scalars_off + n]
 };
 
-cudaError_t launch_smul_add(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const uint32_t *sidx, int bcast,
-                            const uint32_t *add_pts, uint32_t *out_jac, uint32_t n);
-cudaError_t launch_normalize(cudaStream_t st, int chunk, const uint32_t *jac, uint32_t *out_affine, uint8_t *out_comp, uint32_t n);
+struct smul_job_t {
+    uint32_t src_off;        // first point to multiply, in points, into the launch's point array
+    uint32_t add_off;        // first point to add (the fold's L half), or 0xFFFFFFFF for none
+    uint32_t out_off;        // where the affine result goes
+    uint32_t scalar_off;     // first scalar
+    uint32_t scalar_stride;  // 0: one scalar for the whole job (fold), 1: one scalar per element
+    uint32_t pad[3];
+};
+
+cudaError_t launch_smul_jobs(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const smul_job_t *jobs, uint32_t n_jobs,
+                             uint32_t elems_per_job, uint32_t *out_jac);
+cudaError_t launch_normalize(cudaStream_t st, int chunk, const uint32_t *jac, uint32_t *out_affine, uint8_t *out_comp, uint32_t n,
+                             const smul_job_t *jobs, uint32_t elems_per_job);
+cudaError_t launch_compress_affine(cudaStream_t st, const uint32_t *pts, const uint32_t *idx, uint8_t *out_comp, uint32_t n);
+cudaError_t launch_gather_points(cudaStream_t st, uint32_t *pts, const uint32_t *src, const uint32_t *src_idx, const uint32_t *dst_idx, uint32_t n);
 // window sums of `count` MSM segments; c in 2..6 selects the kernel instantiation
 cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, uint32_t count,
                                uint32_t nmax, uint32_t *win_sums);

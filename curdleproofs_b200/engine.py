@@ -42,7 +42,9 @@ _SIGS = {
     "cdp_host_alloc": (c_void_p, [c_void_p, c_size_t]),
     "cdp_host_free": (None, [c_void_p, c_void_p]),
     "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
-    "cdp_smul_add_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_smul_jobs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
+    "cdp_gather_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
 }

@@ -1,0 +1,775 @@
+// Batched Curdleproofs prover: host driver above the C ABI of include/cdp_msm.h.
+//
+// Restates `CurdleproofsProof::new` (/root/reference/src/curdleproofs.rs:59-184) and the provers it calls
+//   SamePermutationProof::new   src/same_permutation_argument.rs:40-99
+//   GrandProductProof::new      src/grand_product_argument.rs:43-166
+//   InnerProductProof::new      src/inner_product_argument.rs:98-198
+//   SameScalarProof::new        src/same_scalar_argument.rs:39-84
+//   SameMultiscalarProof::new   src/same_multiscalar_argument.rs:54-150
+// for B independent shuffles advancing in lock-step.  GPU-first restructuring (results are the same group elements):
+//   * every point that the reference appends to the transcript or writes into the proof is expressed as ONE msm over
+//     device-resident affine bases (the CRS, the instance vectors, the folded working vectors) with host-computed
+//     scalars -- e.g. B = A + alpha*M + beta*sum(G) is msm(G|H|M, (a+beta)|r_a|alpha); L_C = msm(G_R, c_L) + ip*H is one
+//     msm with H as an extra base.  The host therefore never touches a curve point: it receives 48-byte encodings.
+//   * all prover randomness is drawn up front in the reference's order (the draws do not depend on the transcript).
+//   * per round: one batched MSM launch over all proofs, one normalise+compress, one D2H, host transcripts in
+//     parallel over proofs, one batched fold launch.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#pragma GCC visibility push(default)
+#include "../../include/cdp_prover.h"
+#pragma GCC visibility pop
+#include "merlin.hpp"
+#include "rng.hpp"
+
+using namespace cdp_host;
+
+namespace {
+
+constexpr size_t NBL = 4;  // N_BLINDERS, src/lib.rs:35
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct SubLaunch {
+    size_t K = 0;      // segments per proof
+    size_t max_n = 0;  // largest segment (including the extra base)
+    std::vector<cdp_msm_seg> segs;  // max_batch * K, proof-major
+    cdp_msm_seg *d_segs = nullptr;
+};
+struct MsmStage {
+    size_t scalars_per_proof = 0;
+    std::vector<SubLaunch> subs;
+    std::vector<std::pair<int, int>> where;  // logical output q -> (sub, k)
+    size_t outputs() const { return where.size(); }
+};
+struct FoldStage {
+    size_t J = 0, epj = 0, scalars_per_proof = 0;
+    std::vector<cdp_smul_job> jobs;
+    cdp_smul_job *d_jobs = nullptr;
+};
+
+// per-proof host state
+struct ProofState {
+    std::unique_ptr<Transcript> tr;
+    std::vector<Fr> vec_a, a_perm, factors, c, d, r_c, r_d, u, x, r_sm;
+    Fr a_bl[2], c_bl[4], r_t, r_u, r_a, r_b, r_k, k, m_bl[4], b_bl[4], rb_alpha[4];
+    Fr alpha_sp, beta_sp, gprod_result, alpha_g, beta_g, r_p, z, alpha_i, beta_i;
+    Fr z_k, z_t, z_u, c_final, d_final, x_final;
+    std::vector<uint32_t> perm;
+    // compressed points collected for the proof
+    uint8_t pts1[15][48];                       // stage-1 outputs
+    uint8_t B[48], C[48], D[48], B_c[48], B_d[48];
+    uint8_t M_comp[48];
+    std::vector<uint8_t> ipa_rounds, sm_rounds;  // m * 4 * 48, m * 6 * 48
+};
+
+enum Stage1Out { O_A = 0, O_R, O_S, O_T1, O_T2, O_U1, O_U2, O_A1, O_A2, O_B1, O_B2, O_AP, O_BA, O_BT, O_BU };
+
+}  // namespace
+
+struct cdp_prover {
+    cdp_ctx *ctx = nullptr;
+    size_t ell = 0, n = 0, m = 0, max_batch = 0;
+    int threads = 1;
+    std::string err = "ok";
+    double timing[4] = {0, 0, 0, 0};
+
+    // device point array: [CRS block | per-proof working blocks]
+    size_t crs_n = 0, PW = 0;
+    size_t o_GHM = 0, o_Gi = 0, o_Gp = 0, o_Gs = 0, o_T = 0, o_U = 0, o_R = 0, o_S = 0;
+    uint8_t *d_pts = nullptr;
+    uint8_t *d_in = nullptr;       // staging for the instance vectors of a batch (R,S,T,U: 4*ell per proof) + M affine
+    uint8_t *d_Mjac = nullptr;
+    uint32_t *d_gsrc = nullptr, *d_gdst = nullptr;      // working-vector assembly from the CRS block
+    uint32_t *d_isrc = nullptr, *d_idst = nullptr;      // working-vector assembly from the instance staging
+    size_t g_count_per_proof = 0, i_count_per_proof = 0;
+    uint32_t *d_cidx = nullptr;                         // indices of the points compressed for the transcript opening
+    uint8_t *d_scal = nullptr, *d_fscal = nullptr;
+    uint8_t *d_jac = nullptr, *d_comp = nullptr;
+    uint8_t *h_scal = nullptr, *h_fscal = nullptr, *h_comp = nullptr, *h_in = nullptr;
+    size_t max_scalars_pp = 0, max_out_pp = 0;
+    uint8_t H_comp[48];
+
+    MsmStage st1, st2, st3, st4;
+    std::vector<MsmStage> st_ipa, st_sm;
+    std::vector<FoldStage> f_ipa, f_sm;
+    FoldStage f_gp;  // G' = u o (G|H)
+
+    std::vector<ProofState> ps;
+};
+
+namespace {
+
+int perr(cdp_prover *p, int code, const std::string &msg) {
+    p->err = msg;
+    return code;
+}
+#define PTRY(expr)                                                                                     \
+    do {                                                                                               \
+        int rc__ = (expr);                                                                             \
+        if (rc__ != CDP_OK) return perr(p, rc__, std::string(#expr) + ": " + cdp_last_error(p->ctx));  \
+    } while (0)
+
+template <class F>
+void parallel_for(int threads, size_t n, F f) {
+    if (threads <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    size_t nt = std::min<size_t>((size_t)threads, n);
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (size_t t = 0; t < nt; t++)
+        pool.emplace_back([=]() {
+            for (size_t i = t; i < n; i += nt) f(i);
+        });
+    for (auto &th : pool) th.join();
+}
+
+void put_fr(uint8_t *dst, const Fr &x) { x.to_bytes(dst); }
+
+// ---- stage table construction --------------------------------------------------------------------------------
+struct SegSpec {
+    size_t pts_rel;    // offset inside the proof block, or absolute when `absolute`
+    bool absolute;
+    size_t scal_rel;   // offset inside the proof's scalar block
+    size_t n;
+    long extra_abs;    // absolute index of the extra base, -1 none
+};
+void build_stage(cdp_prover *p, MsmStage &st, const std::vector<SegSpec> &specs, size_t scalars_pp) {
+    st.scalars_per_proof = scalars_pp;
+    // two size classes keep the tiny (1-3 point) MSMs out of the big-CTA launch
+    auto eff = [](const SegSpec &s) { return s.n + (s.extra_abs >= 0 ? 1 : 0); };
+    size_t big = 0;
+    for (auto &s : specs) big = std::max(big, eff(s));
+    std::vector<int> cls(specs.size(), 0);
+    bool split = false;
+    if (big >= 12) {
+        for (size_t i = 0; i < specs.size(); i++)
+            if (eff(specs[i]) * 8 <= big && eff(specs[i]) < 12) { cls[i] = 1; split = true; }
+    }
+    st.subs.assign(split ? 2 : 1, SubLaunch());
+    st.where.resize(specs.size());
+    for (size_t i = 0; i < specs.size(); i++) {
+        SubLaunch &sl = st.subs[cls[i]];
+        st.where[i] = {cls[i], (int)sl.K};
+        sl.K++;
+        sl.max_n = std::max(sl.max_n, eff(specs[i]));
+    }
+    for (size_t c = 0; c < st.subs.size(); c++) {
+        SubLaunch &sl = st.subs[c];
+        sl.segs.resize(p->max_batch * sl.K);
+        for (size_t pr = 0; pr < p->max_batch; pr++) {
+            size_t bp = p->crs_n + pr * p->PW;
+            for (size_t i = 0; i < specs.size(); i++) {
+                if (cls[i] != (int)c) continue;
+                cdp_msm_seg &sg = sl.segs[pr * sl.K + st.where[i].second];
+                sg.pts_off = (uint32_t)(specs[i].absolute ? specs[i].pts_rel : bp + specs[i].pts_rel);
+                sg.scalars_off = (uint32_t)(pr * scalars_pp + specs[i].scal_rel);
+                sg.n = (uint32_t)specs[i].n;
+                sg.extra = specs[i].extra_abs >= 0 ? (uint32_t)(specs[i].extra_abs + 1) : 0;
+            }
+        }
+    }
+    p->max_scalars_pp = std::max(p->max_scalars_pp, scalars_pp);
+    p->max_out_pp = std::max(p->max_out_pp, specs.size());
+}
+struct JobSpec {
+    size_t src_rel, add_rel, out_rel;
+    bool has_add;
+    size_t scal_rel, stride;
+};
+void build_fold(cdp_prover *p, FoldStage &fs, const std::vector<JobSpec> &specs, size_t epj, size_t scalars_pp) {
+    fs.J = specs.size();
+    fs.epj = epj;
+    fs.scalars_per_proof = scalars_pp;
+    fs.jobs.resize(p->max_batch * fs.J);
+    for (size_t pr = 0; pr < p->max_batch; pr++) {
+        size_t bp = p->crs_n + pr * p->PW;
+        for (size_t j = 0; j < fs.J; j++) {
+            cdp_smul_job &jb = fs.jobs[pr * fs.J + j];
+            memset(&jb, 0, sizeof jb);
+            jb.src_off = (uint32_t)(bp + specs[j].src_rel);
+            jb.add_off = specs[j].has_add ? (uint32_t)(bp + specs[j].add_rel) : CDP_NONE;
+            jb.out_off = (uint32_t)(bp + specs[j].out_rel);
+            jb.scalar_off = (uint32_t)(pr * scalars_pp + specs[j].scal_rel);
+            jb.scalar_stride = (uint32_t)specs[j].stride;
+        }
+    }
+}
+
+int upload_tables(cdp_prover *p) {
+    auto up_stage = [&](MsmStage &st) -> int {
+        for (auto &sl : st.subs) {
+            size_t bytes = sl.segs.size() * sizeof(cdp_msm_seg);
+            sl.d_segs = (cdp_msm_seg *)cdp_dev_alloc(p->ctx, bytes);
+            if (!sl.d_segs) return CDP_ERR_CUDA;
+            int rc = cdp_h2d(p->ctx, sl.d_segs, sl.segs.data(), bytes);
+            if (rc) return rc;
+        }
+        return CDP_OK;
+    };
+    auto up_fold = [&](FoldStage &fs) -> int {
+        size_t bytes = fs.jobs.size() * sizeof(cdp_smul_job);
+        fs.d_jobs = (cdp_smul_job *)cdp_dev_alloc(p->ctx, bytes);
+        if (!fs.d_jobs) return CDP_ERR_CUDA;
+        return cdp_h2d(p->ctx, fs.d_jobs, fs.jobs.data(), bytes);
+    };
+    PTRY(up_stage(p->st1)); PTRY(up_stage(p->st2)); PTRY(up_stage(p->st3)); PTRY(up_stage(p->st4));
+    for (auto &s : p->st_ipa) PTRY(up_stage(s));
+    for (auto &s : p->st_sm) PTRY(up_stage(s));
+    for (auto &f : p->f_ipa) PTRY(up_fold(f));
+    for (auto &f : p->f_sm) PTRY(up_fold(f));
+    PTRY(up_fold(p->f_gp));
+    PTRY(cdp_sync(p->ctx));  // the host vectors are pageable: make sure the copies are done before they can move
+    return CDP_OK;
+}
+
+// ---- running a stage -----------------------------------------------------------------------------------------
+// scalars for all proofs are already in p->h_scal (proof-major, st.scalars_per_proof each)
+int run_msm_stage(cdp_prover *p, MsmStage &st, size_t B, double &t_wait, double &t_copy) {
+    double t0 = now_ms();
+    PTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * st.scalars_per_proof * 32));
+    size_t out_off = 0;
+    for (auto &sl : st.subs) {
+        PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, p->d_jac + out_off * 144));
+        out_off += B * sl.K;
+    }
+    PTRY(cdp_normalize_dev(p->ctx, p->d_jac, out_off, nullptr, p->d_comp));
+    PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, out_off * 48));
+    double t1 = now_ms();
+    PTRY(cdp_sync(p->ctx));
+    double t2 = now_ms();
+    t_copy += t1 - t0;
+    t_wait += t2 - t1;
+    return CDP_OK;
+}
+// compressed output q of proof pr after run_msm_stage
+const uint8_t *stage_out(const cdp_prover *p, const MsmStage &st, size_t B, size_t pr, size_t q) {
+    size_t base = 0;
+    for (int s = 0; s < st.where[q].first; s++) base += B * st.subs[s].K;
+    const SubLaunch &sl = st.subs[st.where[q].first];
+    return p->h_comp + 48 * (base + pr * sl.K + st.where[q].second);
+}
+int run_fold_stage(cdp_prover *p, FoldStage &fs, size_t B) {
+    PTRY(cdp_h2d(p->ctx, p->d_fscal, p->h_fscal, B * fs.scalars_per_proof * 32));
+    PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, fs.d_jobs, B * fs.J, fs.epj));
+    return CDP_OK;
+}
+
+}  // namespace
+
+extern "C" size_t cdp_proof_size(size_t ell) {
+    size_t n = ell + NBL, m = 0;
+    while (((size_t)1 << m) < n) m++;
+    return 1088 + 480 * m;
+}
+
+extern "C" const char *cdp_prover_last_error(const cdp_prover *p) { return p ? p->err.c_str() : "null prover"; }
+extern "C" void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]) {
+    for (int i = 0; i < 4; i++) out_ms[i] = p ? p->timing[i] : 0.0;
+}
+
+extern "C" void cdp_prover_destroy(cdp_prover *p) {
+    if (!p) return;
+    cdp_ctx *c = p->ctx;
+    auto free_stage = [&](MsmStage &st) { for (auto &sl : st.subs) cdp_dev_free(c, sl.d_segs); };
+    free_stage(p->st1); free_stage(p->st2); free_stage(p->st3); free_stage(p->st4);
+    for (auto &s : p->st_ipa) free_stage(s);
+    for (auto &s : p->st_sm) free_stage(s);
+    for (auto &f : p->f_ipa) cdp_dev_free(c, f.d_jobs);
+    for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
+    cdp_dev_free(c, p->f_gp.d_jobs);
+    for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
+                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp})
+        cdp_dev_free(c, d);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_comp, (void *)p->h_in}) cdp_host_free(c, h);
+    delete p;
+}
+
+extern "C" int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
+    if (!out || !ctx || !crs_points || max_batch == 0 || ell < 4) return CDP_ERR_INVALID_ARG;
+    *out = nullptr;
+    size_t n = ell + NBL, m = 0;
+    while (((size_t)1 << m) < n) m++;
+    if (((size_t)1 << m) != n) return CDP_ERR_INVALID_ARG;  // n must be a power of two (src/inner_product_argument.rs:116)
+    if (n + 1 > 2048) return CDP_ERR_TOO_LARGE;
+    cdp_prover *p = new cdp_prover();
+    p->ctx = ctx; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch;
+    p->threads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    // ---- device point layout
+    const size_t cG = 0, cH = n, cGt = n + 1, cGu = n + 2;  // CRS block: G (ell) | Hvec (4) | H | G_t | G_u
+    (void)cG;
+    p->crs_n = n + 3;
+    p->o_GHM = 0; p->o_Gi = n + 1; p->o_Gp = 2 * n + 1; p->o_Gs = 3 * n + 1; p->o_T = 4 * n + 1; p->o_U = 5 * n + 1;
+    p->o_R = 6 * n + 1; p->o_S = 6 * n + 1 + ell;
+    p->PW = 6 * n + 1 + 2 * ell;
+    size_t total_pts = p->crs_n + max_batch * p->PW;
+    if (total_pts >= ((size_t)1 << 31)) { delete p; return CDP_ERR_TOO_LARGE; }
+
+    // ---- stage tables
+    {   // stage 1: everything that depends only on vec_a and the prover's own randomness
+        size_t sA = 0, sa = n, sT = sa + ell, sU = sT + ell + 1, sCA = sU + ell + 1, sCB = sCA + ell + 1, sAP = sCB + ell + 1, sR = sAP + n;
+        std::vector<SegSpec> v(15);
+        v[O_A] = {p->o_GHM, false, sA, n, -1};                       // A = msm(G|Hvec, a_perm | r_a')            curdleproofs.rs:93
+        v[O_R] = {p->o_R, false, sa, ell, -1};                       // R = msm(vec_R, a)                         :112
+        v[O_S] = {p->o_S, false, sa, ell, -1};                       // S = msm(vec_S, a)                         :113
+        v[O_T1] = {cGt, true, sT + ell, 1, -1};                      // cm_T.T_1 = r_t G_t                        :115 / commitments.rs:50
+        v[O_T2] = {p->o_R, false, sT, ell, (long)cH};                // cm_T.T_2 = k R + r_t H = msm(vec_R|H, k a | r_t)
+        v[O_U1] = {cGu, true, sU + ell, 1, -1};
+        v[O_U2] = {p->o_S, false, sU, ell, (long)cH};
+        v[O_A1] = {cGt, true, sCA + ell, 1, -1};                     // cm_A = GroupCommitment(G_t, H, r_k R, r_a)  same_scalar_argument.rs:60
+        v[O_A2] = {p->o_R, false, sCA, ell, (long)cH};
+        v[O_B1] = {cGu, true, sCB + ell, 1, -1};                     // cm_B                                       :61
+        v[O_B2] = {p->o_S, false, sCB, ell, (long)cH};
+        v[O_AP] = {p->o_Gs, false, sAP, n, -1};                      // A' = A + T_1 + U_1 = msm(G_with_blinders, a_with_blinders)  :131
+        v[O_BA] = {p->o_Gs, false, sR, n, -1};                       // B_a, B_t, B_u                              same_multiscalar_argument.rs:80-82
+        v[O_BT] = {p->o_T, false, sR, n, -1};
+        v[O_BU] = {p->o_U, false, sR, n, -1};
+        build_stage(p, p->st1, v, sR + n);
+    }
+    build_stage(p, p->st2, {{p->o_GHM, false, 0, n + 1, -1}}, n + 1);              // B     same_permutation_argument.rs:75-76
+    build_stage(p, p->st3, {{p->o_GHM, false, 0, n, -1}}, n);                      // C     grand_product_argument.rs:76
+    build_stage(p, p->st4, {{p->o_GHM, false, 0, n + 1, -1},                       // D     grand_product_argument.rs:132
+                            {p->o_GHM, false, n + 1, n, -1},                       // B_c   inner_product_argument.rs:126
+                            {p->o_GHM, false, 2 * n + 1, n, -1}},                  // B_d = msm(G', r_d) = msm(G|H, r_d o u)   :127
+                3 * n + 1);
+    build_fold(p, p->f_gp, {{p->o_GHM, 0, p->o_Gp, false, 0, 1}}, n, n);           // G' = u o (G|Hvec)   grand_product_argument.rs:92-102
+    p->st_ipa.resize(m); p->f_ipa.resize(m); p->st_sm.resize(m); p->f_sm.resize(m);
+    for (size_t k = 0; k < m; k++) {
+        size_t h = n >> (k + 1);
+        // inner_product_argument.rs:158-161; scalars: c_L | ipL | d_R | c_R | ipR | d_L
+        build_stage(p, p->st_ipa[k], {{p->o_Gi + h, false, 0, h, (long)cH},               // L_C = msm(G_R, c_L) + <c_L,d_R> H
+                                      {p->o_Gp, false, h + 1, h, -1},                      // L_D = msm(G'_L, d_R)
+                                      {p->o_Gi, false, 2 * h + 1, h, (long)cH},            // R_C = msm(G_L, c_R) + <c_R,d_L> H
+                                      {p->o_Gp + h, false, 3 * h + 2, h, -1}},             // R_D = msm(G'_R, d_L)
+                    4 * h + 2);
+        build_fold(p, p->f_ipa[k], {{p->o_Gi + h, p->o_Gi, p->o_Gi, true, 0, 0},           // G_L += gamma G_R       :177
+                                    {p->o_Gp + h, p->o_Gp, p->o_Gp, true, 1, 0}},          // G'_L += gamma^-1 G'_R  :178
+                   h, 2);
+        // same_multiscalar_argument.rs:107-112; scalars: x_L | x_R
+        build_stage(p, p->st_sm[k], {{p->o_Gs + h, false, 0, h, -1}, {p->o_T + h, false, 0, h, -1}, {p->o_U + h, false, 0, h, -1},
+                                     {p->o_Gs, false, h, h, -1}, {p->o_T, false, h, h, -1}, {p->o_U, false, h, h, -1}},
+                    2 * h);
+        build_fold(p, p->f_sm[k], {{p->o_T + h, p->o_T, p->o_T, true, 0, 0}, {p->o_U + h, p->o_U, p->o_U, true, 0, 0},
+                                   {p->o_Gs + h, p->o_Gs, p->o_Gs, true, 0, 0}},           // :128-130
+                   h, 1);
+    }
+
+    // ---- device buffers
+    bool ok = true;
+    auto dalloc = [&](size_t bytes) { void *d = cdp_dev_alloc(ctx, bytes); ok = ok && d; return d; };
+    auto halloc = [&](size_t bytes) { void *h = cdp_host_alloc(ctx, bytes); ok = ok && h; return h; };
+    p->d_pts = (uint8_t *)dalloc((total_pts + 1) * 96);  // +1: an all-zero point (infinity) used by the gather tables
+    size_t in_pp = 4 * ell + 1;  // R,S,T,U of every proof (proof-major), then the affine M of every proof
+    p->d_in = (uint8_t *)dalloc(max_batch * in_pp * 96);
+    p->d_Mjac = (uint8_t *)dalloc(max_batch * 144);
+    p->h_in = (uint8_t *)halloc(max_batch * (4 * ell * 96 + 144));
+    size_t max_out = std::max(p->max_out_pp, in_pp);
+    p->d_scal = (uint8_t *)dalloc(max_batch * p->max_scalars_pp * 32);
+    p->h_scal = (uint8_t *)halloc(max_batch * p->max_scalars_pp * 32);
+    p->d_fscal = (uint8_t *)dalloc(max_batch * n * 32);
+    p->h_fscal = (uint8_t *)halloc(max_batch * n * 32);
+    p->d_jac = (uint8_t *)dalloc(max_batch * p->max_out_pp * 144);
+    p->d_comp = (uint8_t *)dalloc(max_batch * max_out * 48);
+    p->h_comp = (uint8_t *)halloc(max_batch * max_out * 48);
+    // gather tables.  From the CRS block: G|Hvec -> o_GHM and o_Gi ; G|H0|H1|G_t|G_u -> o_Gs ; T/U blinder slots (H) ;
+    std::vector<uint32_t> gsrc, gdst, isrc, idst, cidx;
+    const uint32_t INF_SRC = (uint32_t)(total_pts);  // one all-zero point appended after the array (the point at infinity)
+    for (size_t pr = 0; pr < max_batch; pr++) {
+        size_t bp = p->crs_n + pr * p->PW;
+        for (size_t i = 0; i < n; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + p->o_GHM + i)); }
+        for (size_t i = 0; i < n; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + p->o_Gi + i)); }
+        for (size_t i = 0; i < ell + 2; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + p->o_Gs + i)); }
+        gsrc.push_back((uint32_t)cGt); gdst.push_back((uint32_t)(bp + p->o_Gs + ell + 2));
+        gsrc.push_back((uint32_t)cGu); gdst.push_back((uint32_t)(bp + p->o_Gs + ell + 3));
+        // vec_T_with_blinders = T | inf inf H inf ; vec_U_with_blinders = U | inf inf inf H   (curdleproofs.rs:142-155)
+        const uint32_t tb[4] = {INF_SRC, INF_SRC, (uint32_t)cH, INF_SRC}, ub[4] = {INF_SRC, INF_SRC, INF_SRC, (uint32_t)cH};
+        for (int i = 0; i < 4; i++) {
+            gsrc.push_back(tb[i]); gdst.push_back((uint32_t)(bp + p->o_T + ell + i));
+            gsrc.push_back(ub[i]); gdst.push_back((uint32_t)(bp + p->o_U + ell + i));
+        }
+        if (pr == 0) p->g_count_per_proof = gsrc.size();
+        // from the instance staging: [R | S | T | U] of this proof, M in the block behind all proofs
+        size_t ib = pr * 4 * ell;
+        const size_t dsts[4] = {p->o_R, p->o_S, p->o_T, p->o_U};
+        for (int v = 0; v < 4; v++)
+            for (size_t i = 0; i < ell; i++) { isrc.push_back((uint32_t)(ib + v * ell + i)); idst.push_back((uint32_t)(bp + dsts[v] + i)); }
+        isrc.push_back((uint32_t)(max_batch * 4 * ell + pr)); idst.push_back((uint32_t)(bp + p->o_GHM + n));  // M behind G|Hvec
+        if (pr == 0) p->i_count_per_proof = isrc.size();
+    }
+    p->d_gsrc = (uint32_t *)dalloc(gsrc.size() * 4); p->d_gdst = (uint32_t *)dalloc(gdst.size() * 4);
+    p->d_isrc = (uint32_t *)dalloc(isrc.size() * 4); p->d_idst = (uint32_t *)dalloc(idst.size() * 4);
+    if (!ok) { p->err = "allocation failed"; cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+    int rc = CDP_OK;
+    // CRS block + the trailing all-zero point
+    std::vector<uint8_t> zero(96, 0);
+    rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 7) * 96);
+    rc |= cdp_h2d(ctx, p->d_pts + total_pts * 96, zero.data(), 96);
+    rc |= cdp_h2d(ctx, p->d_gsrc, gsrc.data(), gsrc.size() * 4);
+    rc |= cdp_h2d(ctx, p->d_gdst, gdst.data(), gdst.size() * 4);
+    rc |= cdp_h2d(ctx, p->d_isrc, isrc.data(), isrc.size() * 4);
+    rc |= cdp_h2d(ctx, p->d_idst, idst.data(), idst.size() * 4);
+    // compressed H for the blinder slots of the same_msm transcript message
+    rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_comp);
+    rc |= cdp_d2h(ctx, p->h_comp, p->d_comp, 48);
+    rc |= cdp_sync(ctx);
+    if (rc) { p->err = std::string("setup: ") + cdp_last_error(ctx); cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+    memcpy(p->H_comp, p->h_comp, 48);
+    if (upload_tables(p) != CDP_OK) { cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+    p->ps.resize(max_batch);
+    *out = p;
+    return CDP_OK;
+}
+
+extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *in, uint8_t *proofs_out) {
+    if (!p) return CDP_ERR_INVALID_ARG;
+    if (!in || !proofs_out || B == 0 || B > p->max_batch) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: bad argument");
+    const size_t ell = p->ell, n = p->n, m = p->m;
+    const int T = p->threads;
+    double t_start = now_ms(), t_host = 0, t_wait = 0, t_copy = 0, t0;
+    const size_t proof_size = cdp_proof_size(ell);
+    const size_t Moff = p->max_batch * 4 * ell;  // index of the first affine M in d_in
+
+    // ---- stage 0: instance to the device, working vectors assembled, transcript openings compressed
+    t0 = now_ms();
+    for (size_t pr = 0; pr < B; pr++) {
+        uint8_t *dst = p->h_in + pr * 4 * ell * 96;
+        memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
+        memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
+        memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
+        memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
+    }
+    memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
+    PTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+    PTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
+    PTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));  // M.into_affine()
+    PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_gsrc, p->d_gdst, B * p->g_count_per_proof));
+    PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_count_per_proof));
+    PTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp));
+    PTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp + B * 4 * ell * 48));
+    PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * 4 * ell + B) * 48));
+    t_copy += now_ms() - t0;
+    t0 = now_ms();
+    PTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
+
+    // ---- transcript opening, randomness, stage-1 scalars (curdleproofs.rs:78-93,110-116; same_scalar_argument.rs:56-61;
+    //      same_multiscalar_argument.rs:78-82)
+    t0 = now_ms();
+    std::vector<uint8_t> tu_comp(B * 2 * n * 48);  // vec_T_with_blinders | vec_U_with_blinders encodings, kept for same_msm_step1
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        const uint8_t *cmp = p->h_comp + pr * 4 * ell * 48;
+        memcpy(s.M_comp, p->h_comp + (B * 4 * ell + pr) * 48, 48);
+        s.tr.reset(new Transcript("curdleproofs"));
+        for (int v = 0; v < 4; v++) s.tr->append_point_vec("curdleproofs_step1", cmp + v * ell * 48, ell);
+        s.tr->append_point("curdleproofs_step1", s.M_comp);
+        uint8_t *tu = tu_comp.data() + pr * 2 * n * 48;
+        uint8_t inf[48] = {0xC0};
+        memcpy(tu, cmp + 2 * ell * 48, ell * 48);
+        memcpy(tu + ell * 48, inf, 48); memcpy(tu + (ell + 1) * 48, inf, 48); memcpy(tu + (ell + 2) * 48, p->H_comp, 48); memcpy(tu + (ell + 3) * 48, inf, 48);
+        uint8_t *uu = tu + n * 48;
+        memcpy(uu, cmp + 3 * ell * 48, ell * 48);
+        memcpy(uu + ell * 48, inf, 48); memcpy(uu + (ell + 1) * 48, inf, 48); memcpy(uu + (ell + 2) * 48, inf, 48); memcpy(uu + (ell + 3) * 48, p->H_comp, 48);
+        s.vec_a.resize(ell);
+        for (size_t i = 0; i < ell; i++) s.vec_a[i] = s.tr->challenge("curdleproofs_vec_a");
+        // witnesses
+        s.perm.assign(in->permutation + pr * ell, in->permutation + (pr + 1) * ell);
+        Fr::from_bytes(in->k + 32 * pr, s.k);
+        for (int i = 0; i < 4; i++) Fr::from_bytes(in->vec_m_blinders + 32 * (4 * pr + i), s.m_bl[i]);
+        // all prover randomness, in the reference's draw order
+        StdRng rng(in->rng_seed[pr]);
+        if (in->rng_skip_words) rng.skip_words(in->rng_skip_words[pr]);
+        s.a_bl[0] = rng.fr_rand(); s.a_bl[1] = rng.fr_rand();                 // curdleproofs.rs:86
+        for (int i = 0; i < 4; i++) s.c_bl[i] = rng.fr_rand();                  // grand_product_argument.rs:75
+        s.r_c.resize(n); s.r_d.resize(n);
+        for (size_t i = 0; i < n; i++) s.r_c[i] = rng.fr_rand();                // inner_product_argument.rs:46
+        for (size_t i = 0; i + 2 < n; i++) s.r_d[i] = rng.fr_rand();            // :47
+        s.r_t = rng.fr_rand(); s.r_u = rng.fr_rand();                           // curdleproofs.rs:110-111
+        s.r_a = rng.fr_rand(); s.r_b = rng.fr_rand(); s.r_k = rng.fr_rand();    // same_scalar_argument.rs:56-58
+        s.r_sm.resize(n);
+        for (size_t i = 0; i < n; i++) s.r_sm[i] = rng.fr_rand();               // same_multiscalar_argument.rs:78
+        s.a_perm.resize(ell);
+        for (size_t i = 0; i < ell; i++) s.a_perm[i] = s.vec_a[s.perm[i]];
+        // stage-1 scalar block (layout fixed in cdp_prover_create)
+        uint8_t *sc = p->h_scal + pr * p->st1.scalars_per_proof * 32;
+        size_t o = 0;
+        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.a_perm[i]);                 // A
+        put_fr(sc + 32 * (o++), s.a_bl[0]); put_fr(sc + 32 * (o++), s.a_bl[1]);
+        memset(sc + 32 * o, 0, 64); o += 2;
+        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.vec_a[i]);                  // R, S
+        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.k * s.vec_a[i]);            // cm_T
+        put_fr(sc + 32 * (o++), s.r_t);
+        memcpy(sc + 32 * o, sc + 32 * (o - ell - 1), 32 * ell); o += ell;                      // cm_U
+        put_fr(sc + 32 * (o++), s.r_u);
+        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.r_k * s.vec_a[i]);          // cm_A
+        put_fr(sc + 32 * (o++), s.r_a);
+        memcpy(sc + 32 * o, sc + 32 * (o - ell - 1), 32 * ell); o += ell;                      // cm_B
+        put_fr(sc + 32 * (o++), s.r_b);
+        memcpy(sc + 32 * o, sc, 32 * (ell + 2)); o += ell + 2;                                 // A' : a_perm | a_bl | r_t | r_u
+        put_fr(sc + 32 * (o++), s.r_t); put_fr(sc + 32 * (o++), s.r_u);
+        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (o++), s.r_sm[i]);                     // B_a, B_t, B_u
+        s.ipa_rounds.resize(m * 4 * 48);
+        s.sm_rounds.resize(m * 6 * 48);
+    });
+    t_host += now_ms() - t0;
+    if (int rc = run_msm_stage(p, p->st1, B, t_wait, t_copy)) return rc;
+
+    // ---- same_perm (same_permutation_argument.rs:60-82) -> stage 2: B
+    t0 = now_ms();
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        for (int q = 0; q < 15; q++) memcpy(s.pts1[q], stage_out(p, p->st1, B, pr, q), 48);
+        s.tr->append_point("same_perm_step1", s.pts1[O_A]);
+        s.tr->append_point("same_perm_step1", s.M_comp);
+        s.tr->append_fr_vec("same_perm_step1", s.vec_a.data(), ell);
+        s.alpha_sp = s.tr->challenge("same_perm_alpha");
+        s.beta_sp = s.tr->challenge("same_perm_beta");
+        s.factors.resize(ell);
+        s.gprod_result = Fr::one();
+        for (size_t i = 0; i < ell; i++) {
+            s.factors[i] = s.a_perm[i] + Fr::from_u64(s.perm[i]) * s.alpha_sp + s.beta_sp;
+            s.gprod_result *= s.factors[i];
+        }
+        const Fr r_a_prime[4] = {s.a_bl[0], s.a_bl[1], Fr::zero(), Fr::zero()};
+        for (int i = 0; i < 4; i++) s.b_bl[i] = r_a_prime[i] + s.alpha_sp * s.m_bl[i];
+        // B = A + alpha M + beta sum(G) = msm(G | Hvec | M, (a_perm + beta) | r_a' | alpha)
+        uint8_t *sc = p->h_scal + pr * p->st2.scalars_per_proof * 32;
+        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * i, s.a_perm[i] + s.beta_sp);
+        for (int i = 0; i < 4; i++) put_fr(sc + 32 * (ell + i), r_a_prime[i]);
+        put_fr(sc + 32 * n, s.alpha_sp);
+    });
+    t_host += now_ms() - t0;
+    if (int rc = run_msm_stage(p, p->st2, B, t_wait, t_copy)) return rc;
+
+    // ---- gprod step 1-2 (grand_product_argument.rs:63-83) -> stage 3: C
+    t0 = now_ms();
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        memcpy(s.B, stage_out(p, p->st2, B, pr, 0), 48);
+        s.tr->append_point("gprod_step1", s.B);
+        s.tr->append_fr("gprod_step1", s.gprod_result);
+        s.alpha_g = s.tr->challenge("gprod_alpha");
+        s.c.assign(n, Fr::zero());
+        s.c[0] = Fr::one();
+        for (size_t i = 0; i + 1 < ell; i++) s.c[i + 1] = s.c[i] * s.factors[i];
+        for (int i = 0; i < 4; i++) s.c[ell + i] = s.c_bl[i];
+        for (int i = 0; i < 4; i++) s.rb_alpha[i] = s.b_bl[i] + s.alpha_g;
+        s.r_p = inner_product(s.rb_alpha, s.c_bl, 4);
+        uint8_t *sc = p->h_scal + pr * p->st3.scalars_per_proof * 32;
+        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * i, s.c[i]);
+    });
+    t_host += now_ms() - t0;
+    if (int rc = run_msm_stage(p, p->st3, B, t_wait, t_copy)) return rc;
+
+    // ---- gprod step 3-4 (grand_product_argument.rs:85-147) + IPA step 1 (inner_product_argument.rs:124-127) -> stage 4: D, B_c, B_d ; G'
+    t0 = now_ms();
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        memcpy(s.C, stage_out(p, p->st3, B, pr, 0), 48);
+        s.tr->append_point("gprod_step2", s.C);
+        s.tr->append_fr("gprod_step2", s.r_p);
+        s.beta_g = s.tr->challenge("gprod_beta");
+        const Fr beta = s.beta_g, beta_inv = beta.inverse();
+        s.u.resize(n);
+        Fr pw = beta_inv;
+        for (size_t i = 0; i < ell; i++) { s.u[i] = pw; pw *= beta_inv; }     // beta^-(i+1)
+        for (size_t i = 0; i < 4; i++) s.u[ell + i] = pw;                       // beta^-(ell+1)
+        s.d.assign(n, Fr::zero());
+        Fr pb = beta, p1 = Fr::one();
+        for (size_t i = 0; i < ell; i++) {                                      // d_i = b_i beta^(i+1) - beta^i
+            s.d[i] = s.factors[i] * pb - p1;
+            p1 = pb;
+            pb *= beta;
+        }
+        const Fr beta_l = p1, beta_l1 = pb;                                     // beta^ell, beta^(ell+1)
+        for (int i = 0; i < 4; i++) s.d[ell + i] = beta_l1 * s.rb_alpha[i];
+        s.z = s.r_p * beta_l1 + s.gprod_result * beta_l - Fr::one();            // inner_prod
+        // generate_ipa_blinders: the two left-out blinders solve <r_c,d> + <r_d,c> = 0 and <r_c,r_d> = 0   (:53-77)
+        {
+            const std::vector<Fr> &c = s.c, &d = s.d;
+            std::vector<Fr> &r = s.r_c, &z = s.r_d;
+            Fr omega = inner_product(r.data(), d.data(), n) + inner_product(z.data(), c.data(), n - 2);
+            Fr delta = inner_product(r.data(), z.data(), n - 2);
+            Fr inv_c = c[n - 2].inverse();
+            Fr last_z = (r[n - 2] * inv_c * omega - delta) * (r[n - 2].neg() * inv_c * c[n - 1] + r[n - 1]).inverse();
+            Fr pen_z = inv_c.neg() * (last_z * c[n - 1] + omega);
+            z[n - 2] = pen_z;
+            z[n - 1] = last_z;
+        }
+        uint8_t *sc = p->h_scal + pr * p->st4.scalars_per_proof * 32;
+        const Fr r_a_prime[4] = {s.a_bl[0], s.a_bl[1], Fr::zero(), Fr::zero()};
+        // D = B - beta^-1 sum(G) + alpha_g sum(Hvec) = msm(G | Hvec | M, (a_perm + beta_sp - beta^-1) | (r_a' + alpha_g) | alpha_sp)
+        Fr shift = s.beta_sp - beta_inv;
+        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * i, s.a_perm[i] + shift);
+        for (int i = 0; i < 4; i++) put_fr(sc + 32 * (ell + i), r_a_prime[i] + s.alpha_g);
+        put_fr(sc + 32 * n, s.alpha_sp);
+        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (n + 1 + i), s.r_c[i]);                // B_c = msm(G|Hvec, r_c)
+        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (2 * n + 1 + i), s.r_d[i] * s.u[i]);   // B_d = msm(G', r_d)
+        uint8_t *fs = p->h_fscal + pr * n * 32;                                                // G'_i = u_i (G|Hvec)_i
+        for (size_t i = 0; i < n; i++) put_fr(fs + 32 * i, s.u[i]);
+    });
+    t_host += now_ms() - t0;
+    t0 = now_ms();
+    if (int rc = run_fold_stage(p, p->f_gp, B)) return rc;
+    t_copy += now_ms() - t0;
+    if (int rc = run_msm_stage(p, p->st4, B, t_wait, t_copy)) return rc;
+
+    // ---- IPA step 1 transcript + rewrite of c, d (inner_product_argument.rs:129-140), then the rounds (:150-186)
+    t0 = now_ms();
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        memcpy(s.D, stage_out(p, p->st4, B, pr, 0), 48);
+        memcpy(s.B_c, stage_out(p, p->st4, B, pr, 1), 48);
+        memcpy(s.B_d, stage_out(p, p->st4, B, pr, 2), 48);
+        s.tr->append_point("ipa_step1", s.C);
+        s.tr->append_point("ipa_step1", s.D);
+        s.tr->append_fr("ipa_step1", s.z);
+        s.tr->append_point("ipa_step1", s.B_c);
+        s.tr->append_point("ipa_step1", s.B_d);
+        s.alpha_i = s.tr->challenge("ipa_alpha");
+        s.beta_i = s.tr->challenge("ipa_beta");
+        for (size_t i = 0; i < n; i++) {
+            s.c[i] = s.r_c[i] + s.alpha_i * s.c[i];
+            s.d[i] = s.r_d[i] + s.alpha_i * s.d[i];
+        }
+    });
+    t_host += now_ms() - t0;
+    for (size_t k = 0; k < m; k++) {
+        const size_t h = n >> (k + 1);
+        MsmStage &st = p->st_ipa[k];
+        t0 = now_ms();
+        parallel_for(T, B, [&](size_t pr) {
+            ProofState &s = p->ps[pr];
+            const Fr *cL = s.c.data(), *cR = s.c.data() + h, *dL = s.d.data(), *dR = s.d.data() + h;
+            uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
+            size_t o = 0;
+            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), cL[i]);
+            put_fr(sc + 32 * (o++), s.beta_i * inner_product(cL, dR, h));   // H = beta crs_H ; L_C += <c_L,d_R> H
+            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), dR[i]);
+            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), cR[i]);
+            put_fr(sc + 32 * (o++), s.beta_i * inner_product(cR, dL, h));
+            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), dL[i]);
+        });
+        t_host += now_ms() - t0;
+        if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
+        t0 = now_ms();
+        parallel_for(T, B, [&](size_t pr) {
+            ProofState &s = p->ps[pr];
+            uint8_t *rp = s.ipa_rounds.data() + k * 4 * 48;
+            for (int q = 0; q < 4; q++) {  // L_C, L_D, R_C, R_D
+                memcpy(rp + 48 * q, stage_out(p, st, B, pr, q), 48);
+                s.tr->append_point("ipa_loop", rp + 48 * q);
+            }
+            Fr gamma = s.tr->challenge("ipa_gamma"), gamma_inv = gamma.inverse();
+            for (size_t i = 0; i < h; i++) {
+                s.c[i] += gamma_inv * s.c[h + i];
+                s.d[i] += gamma * s.d[h + i];
+            }
+            put_fr(p->h_fscal + (pr * 2) * 32, gamma);
+            put_fr(p->h_fscal + (pr * 2 + 1) * 32, gamma_inv);
+        });
+        t_host += now_ms() - t0;
+        if (h > 1) {  // after the last round the folded bases are never used again
+            t0 = now_ms();
+            if (int rc = run_fold_stage(p, p->f_ipa[k], B)) return rc;
+            t_copy += now_ms() - t0;
+        }
+    }
+
+    // ---- same_scalar (same_scalar_argument.rs:64-75) and same_msm step 1 (same_multiscalar_argument.rs:84-91)
+    t0 = now_ms();
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        s.c_final = s.c[0];
+        s.d_final = s.d[0];
+        static const int order[10] = {O_R, O_S, O_T1, O_T2, O_U1, O_U2, O_A1, O_A2, O_B1, O_B2};
+        for (int q = 0; q < 10; q++) s.tr->append_point("sameexp_points", s.pts1[order[q]]);
+        Fr alpha = s.tr->challenge("same_scalar_alpha");
+        s.z_k = s.r_k + s.k * alpha;
+        s.z_t = s.r_a + s.r_t * alpha;
+        s.z_u = s.r_b + s.r_u * alpha;
+        s.tr->append_point("same_msm_step1", s.pts1[O_AP]);
+        s.tr->append_point("same_msm_step1", s.pts1[O_T2]);
+        s.tr->append_point("same_msm_step1", s.pts1[O_U2]);
+        const uint8_t *tu = tu_comp.data() + pr * 2 * n * 48;
+        s.tr->append_point_vec("same_msm_step1", tu, n);
+        s.tr->append_point_vec("same_msm_step1", tu + n * 48, n);
+        s.tr->append_point("same_msm_step1", s.pts1[O_BA]);
+        s.tr->append_point("same_msm_step1", s.pts1[O_BT]);
+        s.tr->append_point("same_msm_step1", s.pts1[O_BU]);
+        Fr a_sm = s.tr->challenge("same_msm_alpha");
+        s.x.resize(n);
+        for (size_t i = 0; i < ell; i++) s.x[i] = s.r_sm[i] + a_sm * s.a_perm[i];
+        const Fr tail[4] = {s.a_bl[0], s.a_bl[1], s.r_t, s.r_u};  // vec_a_with_blinders, curdleproofs.rs:157-160
+        for (int i = 0; i < 4; i++) s.x[ell + i] = s.r_sm[ell + i] + a_sm * tail[i];
+    });
+    t_host += now_ms() - t0;
+    for (size_t k = 0; k < m; k++) {
+        const size_t h = n >> (k + 1);
+        MsmStage &st = p->st_sm[k];
+        t0 = now_ms();
+        parallel_for(T, B, [&](size_t pr) {
+            ProofState &s = p->ps[pr];
+            uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
+            for (size_t i = 0; i < 2 * h; i++) put_fr(sc + 32 * i, s.x[i]);
+        });
+        t_host += now_ms() - t0;
+        if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
+        t0 = now_ms();
+        parallel_for(T, B, [&](size_t pr) {
+            ProofState &s = p->ps[pr];
+            uint8_t *rp = s.sm_rounds.data() + k * 6 * 48;
+            for (int q = 0; q < 6; q++) {  // L_A, L_T, L_U, R_A, R_T, R_U
+                memcpy(rp + 48 * q, stage_out(p, st, B, pr, q), 48);
+                s.tr->append_point("same_msm_loop", rp + 48 * q);
+            }
+            Fr gamma = s.tr->challenge("same_msm_gamma"), gamma_inv = gamma.inverse();
+            for (size_t i = 0; i < h; i++) s.x[i] += gamma_inv * s.x[h + i];
+            put_fr(p->h_fscal + pr * 32, gamma);
+        });
+        t_host += now_ms() - t0;
+        if (h > 1) {
+            t0 = now_ms();
+            if (int rc = run_fold_stage(p, p->f_sm[k], B)) return rc;
+            t_copy += now_ms() - t0;
+        }
+    }
+
+    // ---- serialise (curdleproofs.rs:300-310 and the per-argument serialisers)
+    t0 = now_ms();
+    parallel_for(T, B, [&](size_t pr) {
+        ProofState &s = p->ps[pr];
+        s.x_final = s.x[0];
+        uint8_t *w = proofs_out + pr * proof_size;
+        auto pt = [&](const uint8_t *c) { memcpy(w, c, 48); w += 48; };
+        auto fr = [&](const Fr &x) { x.to_bytes(w); w += 32; };
+        pt(s.pts1[O_A]); pt(s.pts1[O_T1]); pt(s.pts1[O_T2]); pt(s.pts1[O_U1]); pt(s.pts1[O_U2]); pt(s.pts1[O_R]); pt(s.pts1[O_S]);
+        pt(s.B); pt(s.C); fr(s.r_p);
+        pt(s.B_c); pt(s.B_d);
+        static const int ipa_order[4] = {0, 2, 1, 3};  // serialised as vec_L_C, vec_R_C, vec_L_D, vec_R_D; rounds hold L_C, L_D, R_C, R_D
+        for (int v = 0; v < 4; v++)
+            for (size_t k = 0; k < m; k++) pt(s.ipa_rounds.data() + (k * 4 + ipa_order[v]) * 48);
+        fr(s.c_final); fr(s.d_final);
+        pt(s.pts1[O_A1]); pt(s.pts1[O_A2]); pt(s.pts1[O_B1]); pt(s.pts1[O_B2]);
+        fr(s.z_k); fr(s.z_t); fr(s.z_u);
+        pt(s.pts1[O_BA]); pt(s.pts1[O_BT]); pt(s.pts1[O_BU]);
+        for (int v = 0; v < 6; v++)  // vec_L_A, vec_L_T, vec_L_U, vec_R_A, vec_R_T, vec_R_U
+            for (size_t k = 0; k < m; k++) pt(s.sm_rounds.data() + (k * 6 + v) * 48);
+        fr(s.x_final);
+    });
+    t_host += now_ms() - t0;
+    p->timing[0] = now_ms() - t_start;
+    p->timing[1] = t_host;
+    p->timing[2] = t_wait;
+    p->timing[3] = t_copy;
+    return CDP_OK;
+}

@@ -1,0 +1,107 @@
+"""ctypes binding of include/cdp_prover.h: the batched prover, mirroring `CurdleproofsProof::new`
+(/root/reference/src/curdleproofs.rs:59-184) for a batch of independent shuffles."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_uint32, c_uint64, c_void_p
+
+from .engine import AFFINE_BYTES, JACOBIAN_BYTES, SCALAR_BYTES, CdpError, Engine, _HERE, load_library
+
+
+class _ProveInputs(ctypes.Structure):
+    _fields_ = [("vec_R", c_void_p), ("vec_S", c_void_p), ("vec_T", c_void_p), ("vec_U", c_void_p), ("M", c_void_p),
+                ("permutation", c_void_p), ("k", c_void_p), ("vec_m_blinders", c_void_p), ("rng_seed", c_void_p),
+                ("rng_skip_words", c_void_p)]
+
+
+_PLIB = None
+
+
+def load_prover_library() -> ctypes.CDLL:
+    global _PLIB
+    if _PLIB is None:
+        load_library()  # libcdp_b200.so first (fails loudly if missing)
+        path = os.path.join(_HERE, "libcdp_prover.so")
+        if not os.path.exists(path):
+            raise CdpError(f"{path} is missing: run __graft_entry__.build()")
+        lib = ctypes.CDLL(path)
+        lib.cdp_proof_size.restype = c_size_t
+        lib.cdp_proof_size.argtypes = [c_size_t]
+        lib.cdp_prover_create.restype = c_int
+        lib.cdp_prover_create.argtypes = [POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_size_t, c_int]
+        lib.cdp_prover_destroy.argtypes = [c_void_p]
+        lib.cdp_prover_last_error.restype = c_char_p
+        lib.cdp_prover_last_error.argtypes = [c_void_p]
+        lib.cdp_prove_batch.restype = c_int
+        lib.cdp_prove_batch.argtypes = [c_void_p, c_size_t, POINTER(_ProveInputs), c_void_p]
+        lib.cdp_prover_last_timing.argtypes = [c_void_p, POINTER(c_double)]
+        _PLIB = lib
+    return _PLIB
+
+
+def _arr(b: bytes):
+    return (ctypes.c_uint8 * max(1, len(b))).from_buffer_copy(b if len(b) else b"\0")
+
+
+class BatchProver:
+    """`CurdleproofsProof::new` for `batch` shuffles at a time on one GPU.
+
+    crs_points: ell + 7 affine points, `CurdleproofsCrs::from_points` order (src/crs.rs:37-58)."""
+
+    def __init__(self, engine: Engine, ell: int, crs_points: bytes, max_batch: int, host_threads: int = 0):
+        self._lib = load_prover_library()
+        self.engine = engine
+        self.ell = ell
+        self.max_batch = max_batch
+        self.proof_size = int(self._lib.cdp_proof_size(ell))
+        if len(crs_points) != (ell + 7) * AFFINE_BYTES:
+            raise ValueError("crs_points must hold ell + 7 affine points")
+        h = c_void_p()
+        rc = self._lib.cdp_prover_create(ctypes.byref(h), engine.handle, ell, _arr(crs_points), max_batch, host_threads)
+        if rc != 0:
+            raise CdpError(f"cdp_prover_create failed (code {rc})")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cdp_prover_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def prove_batch(self, instances, rng_seeds, rng_skip_words=None) -> list[bytes]:
+        """instances: list of dicts with R, S, T, U (ell affine each), M (jacobian), perm (list of int), k, m_blinders.
+        rng_seeds[i] seeds the prover's StdRng for proof i (the reference's `rng` argument)."""
+        B = len(instances)
+        ell = self.ell
+        cat = lambda key: b"".join(i[key] for i in instances)  # noqa: E731
+        bufs = dict(R=_arr(cat("R")), S=_arr(cat("S")), T=_arr(cat("T")), U=_arr(cat("U")), M=_arr(cat("M")), k=_arr(cat("k")),
+                    mb=_arr(cat("m_blinders")))
+        perm = (c_uint32 * (B * ell))(*[x for i in instances for x in i["perm"]])
+        seeds = (c_uint64 * B)(*rng_seeds)
+        skips = (c_uint64 * B)(*rng_skip_words) if rng_skip_words is not None else None
+        return self.prove_raw(B, bufs["R"], bufs["S"], bufs["T"], bufs["U"], bufs["M"], perm, bufs["k"], bufs["mb"], seeds, skips)
+
+    def prove_raw(self, B, R, S, T, U, M, perm, k, mb, seeds, skips=None, out=None, split=True):
+        inp = _ProveInputs(ctypes.cast(R, c_void_p), ctypes.cast(S, c_void_p), ctypes.cast(T, c_void_p), ctypes.cast(U, c_void_p),
+                           ctypes.cast(M, c_void_p), ctypes.cast(perm, c_void_p), ctypes.cast(k, c_void_p), ctypes.cast(mb, c_void_p),
+                           ctypes.cast(seeds, c_void_p), ctypes.cast(skips, c_void_p) if skips is not None else None)
+        if out is None:
+            out = (ctypes.c_uint8 * (B * self.proof_size))()
+        rc = self._lib.cdp_prove_batch(self._h, B, ctypes.byref(inp), out)
+        if rc != 0:
+            raise CdpError(f"cdp_prove_batch failed (code {rc}): {self._lib.cdp_prover_last_error(self._h).decode()}")
+        if not split:
+            return out
+        raw = bytes(out)
+        return [raw[i * self.proof_size:(i + 1) * self.proof_size] for i in range(B)]
+
+    def last_timing(self) -> dict:
+        t = (c_double * 4)()
+        self._lib.cdp_prover_last_timing(self._h, t)
+        return {"total_ms": t[0], "host_ms": t[1], "gpu_wait_ms": t[2], "copy_issue_ms": t[3]}

@@ -109,16 +109,34 @@ typedef struct {
     uint32_t pts_off;
     uint32_t scalars_off;
     uint32_t n;
-    uint32_t reserved;
+    uint32_t extra; /* 0 = none; else 1 + index (into d_affine_pts) of one more base, logically element n, whose scalar is
+                       d_scalars[scalars_off + n].  Lets `msm(G_R, c_L) + ip * H` (src/inner_product_argument.rs:158) be ONE msm. */
 } cdp_msm_seg;
 /* `d_segs` is a DEVICE array of `count` cdp_msm_seg; `max_n` >= every segment's n.  Results: count Jacobian points. */
 int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs, size_t count,
                       size_t max_n, uint8_t *d_out_jac);
 
-/* d_out_jac[i] = (d_add ? d_add[i] : O) + d_scalars[d_scalar_index ? d_scalar_index[i] : i] * d_pts[i]
- * With d_add = L, d_pts = R and one scalar per proof this is the fold of a whole batch of proofs in one launch. */
-int cdp_smul_add_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, const uint32_t *d_scalar_index, const uint8_t *d_add,
-                     size_t n, uint8_t *d_out_jac);
+/* Batched scalar multiplication / fold over device-resident points.  For every job j and element e < elems_per_job:
+ *   d_pts[out_off + e] = ( (add_off != CDP_NONE ? d_pts[add_off + e] : O)
+ *                          + d_scalars[scalar_off + e * scalar_stride] * d_pts[src_off + e] ).into_affine()
+ * One job = one vector of one proof.  With src = R half, add = out = L half and scalar_stride = 0 this is the fold loop
+ * (src/inner_product_argument.rs:174-179, src/same_multiscalar_argument.rs:126-131) for a whole batch of proofs in one
+ * launch; with add = CDP_NONE and scalar_stride = 1 it is the CRS rescale (src/grand_product_argument.rs:92-102).
+ * `d_jobs` is a DEVICE array.  out ranges may alias add ranges (results are staged before they are written). */
+#define CDP_NONE 0xFFFFFFFFu
+typedef struct {
+    uint32_t src_off, add_off, out_off, scalar_off, scalar_stride;
+    uint32_t reserved[3];
+} cdp_smul_job;
+int cdp_smul_jobs_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_scalars, const cdp_smul_job *d_jobs, size_t n_jobs,
+                      size_t elems_per_job);
+
+/* d_pts[d_dst_idx[i]] = d_src[d_src_idx[i]] for i < n (96-byte points): assembles per-proof working vectors. */
+int cdp_gather_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_src, const uint32_t *d_src_idx, const uint32_t *d_dst_idx, size_t n);
+
+/* Affine points (d_pts[d_index[i]], or d_pts[i] when d_index is NULL) -> 48-byte encodings (`serialize_compressed` of the
+ * instance vectors, src/curdleproofs.rs:81). */
+int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint32_t *d_index, size_t n, uint8_t *d_out_compressed);
 
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);

@@ -1,0 +1,60 @@
+/* cdp_prover.h -- C ABI of the batched Curdleproofs prover / verifier host driver.
+ *
+ * The driver restates `CurdleproofsProof::new` (/root/reference/src/curdleproofs.rs:59-184) and, through it, the
+ * SamePermutation / GrandProduct / InnerProduct / SameScalar / SameMultiscalar provers, for a BATCH of independent
+ * shuffles that advance in lock-step through the Fiat-Shamir rounds.  All group arithmetic (every MSM, every fold,
+ * every normalisation / compression) runs on the GPU through include/cdp_msm.h; the host keeps only the transcript
+ * (merlin), the prover's RNG stream and O(n) scalar-field bookkeeping.  Proofs are byte-identical to the reference's
+ * for the same inputs and the same RNG stream.
+ *
+ * Layouts are those of cdp_msm.h: affine 96 B (Montgomery), jacobian 144 B, scalars 32 B canonical little-endian.
+ */
+#ifndef CDP_PROVER_H
+#define CDP_PROVER_H
+#include <stddef.h>
+#include <stdint.h>
+
+#include "cdp_msm.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cdp_prover cdp_prover;
+
+/* Serialised proof size, 1088 + 480 * log2(ell + 4) bytes (`CurdleproofsProof::serialize`, src/curdleproofs.rs:300-310). */
+size_t cdp_proof_size(size_t ell);
+
+/* `crs_points`: ell + 7 affine points in `CurdleproofsCrs::from_points` order (src/crs.rs:37-58):
+ * vec_G (ell) | vec_H (4) | H | G_t | G_u.  ell + 4 must be a power of two (src/inner_product_argument.rs:116).
+ * `ctx` must outlive the prover.  `host_threads` <= 0 selects all host cores. */
+int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads);
+void cdp_prover_destroy(cdp_prover *p);
+const char *cdp_prover_last_error(const cdp_prover *p);
+
+/* Inputs of `batch` independent shuffles, proof-major.  Argument names follow CurdleproofsProof::new. */
+typedef struct {
+    const uint8_t *vec_R;          /* batch * ell affine   */
+    const uint8_t *vec_S;          /* batch * ell affine   */
+    const uint8_t *vec_T;          /* batch * ell affine   */
+    const uint8_t *vec_U;          /* batch * ell affine   */
+    const uint8_t *M;              /* batch jacobian       */
+    const uint32_t *permutation;   /* batch * ell          */
+    const uint8_t *k;              /* batch scalars        */
+    const uint8_t *vec_m_blinders; /* batch * 4 scalars    */
+    const uint64_t *rng_seed;      /* batch: the prover's `rng` is StdRng::seed_from_u64(rng_seed[i]) ...            */
+    const uint64_t *rng_skip_words;/* ... advanced by this many u32 outputs first (NULL = 0): lets a caller that already
+                                      consumed part of the stream (src/whisk.rs:153-154, src/util.rs:102) hand it over. */
+} cdp_prove_inputs;
+
+/* proofs_out: batch * cdp_proof_size(ell) bytes.  Host buffers in, host buffers out (copies are inside the call). */
+int cdp_prove_batch(cdp_prover *p, size_t batch, const cdp_prove_inputs *in, uint8_t *proofs_out);
+
+/* Timing breakdown of the last cdp_prove_batch call, milliseconds: [0] total, [1] host transcript/scalar work,
+ * [2] waiting on the GPU (stream synchronisation), [3] H2D/D2H staging issue time. */
+void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDP_PROVER_H */

@@ -110,7 +110,9 @@ EXPORT int oracle_whisk_tracker_proof_seed0(uint8_t out[128]) {
 /* whisk_shuffle_proof test, src/whisk.rs:416-456 with N = 128 (generic in ell here so that the same
  * driver also produces the seed-0 instances for other sizes).  Outputs:
  *   proof_out : 48 (M) + curdle_proof_size(m) bytes              (the 4496-byte golden string at ell=124)
- *   inst_out  : optional, 4*ell affine points R,S,T,U (96 B each) followed by M (144 B jacobian)
+ *   inst_out  : optional, 4*ell affine points R,S,T,U (96 B each), M (144 B jacobian), permutation (ell x u32), k (32 B),
+ *               vec_m_blinders (4 x 32 B) and, as a u64, the number of u32 words the rng had produced when
+ *               CurdleproofsProof::new was entered (so that a prover can be handed the same stream)
  *   verified  : result of is_valid_whisk_shuffle_proof on the serialised proof with the same rng */
 EXPORT int oracle_whisk_shuffle_proof_seed0(size_t ell, uint8_t *proof_out, uint8_t *inst_out, int *verified, int threads) {
     stdrng_t rng; stdrng_seed_from_u64(&rng, 0);
@@ -129,12 +131,18 @@ EXPORT int oracle_whisk_shuffle_proof_seed0(size_t ell, uint8_t *proof_out, uint
     fr_t k; fr_rand(&k, &rng);                                             /* :154 */
     g1j_t M; fr_t m_bl[N_BLINDERS];
     shuffle_permute_and_commit(&crs, vR, vS, perm, &k, &rng, vT, vU, &M, m_bl, threads);
+    uint64_t words_before = (rng.counter / 4 - 1) * 64 + (uint64_t)rng.index;
     curdle_proof_t pf; curdle_prove(&pf, &crs, vR, vS, vT, vU, &M, perm, &k, m_bl, &rng, threads);
     g1j_compress(proof_out, &M); size_t sz = curdle_serialize(proof_out + 48, &pf);
     if (inst_out) {
         memcpy(inst_out, vR, 96 * ell); memcpy(inst_out + 96 * ell, vS, 96 * ell);
         memcpy(inst_out + 192 * ell, vT, 96 * ell); memcpy(inst_out + 288 * ell, vU, 96 * ell);
         memcpy(inst_out + 384 * ell, &M, 144);
+        uint8_t *w = inst_out + 384 * ell + 144;
+        memcpy(w, perm, 4 * ell); w += 4 * ell;
+        fr_to_bytes(w, &k); w += 32;
+        for (int i = 0; i < N_BLINDERS; i++) { fr_to_bytes(w, &m_bl[i]); w += 32; }
+        memcpy(w, &words_before, 8);
     }
     if (verified) { /* is_valid_whisk_shuffle_proof :106-130 */
         curdle_proof_t pf2; g1j_t M2; const uint8_t *rd = proof_out;
