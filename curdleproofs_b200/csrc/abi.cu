@@ -35,6 +35,14 @@ struct cdp_ctx {
     // pinned host staging
     scratch_t h_stage;
     int sm_count = 148;
+    // optional per-kernel profiling (cdp_profile_*): CUDA events around every launch on the context's stream
+    bool profiling = false;
+    struct prof_rec { int kind; cudaEvent_t e0, e1; uint64_t units; };
+    std::vector<prof_rec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[CDP_PROFILE_KINDS] = {0};
+    uint64_t prof_launches[CDP_PROFILE_KINDS] = {0};
+    uint64_t prof_units[CDP_PROFILE_KINDS] = {0};
 };
 
 namespace {
@@ -78,6 +86,30 @@ int ensure_host(cdp_ctx *ctx, scratch_t &s, size_t bytes) {
     s.cap = cap;
     return CDP_OK;
 }
+// RAII bracket around one kernel launch: counts it and, when profiling is on, times it with CUDA events
+struct launch_scope {
+    cdp_ctx *ctx;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int kind;
+    uint64_t units;
+    launch_scope(cdp_ctx *c, int k, uint64_t u) : ctx(c), kind(k), units(u) {
+        ctx->launches++;
+        if (!ctx->profiling) return;
+        auto get = [&]() {
+            cudaEvent_t e = nullptr;
+            if (!ctx->prof_pool.empty()) { e = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get(); e1 = get();
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~launch_scope() {
+        if (!e0) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->prof_pending.push_back({kind, e0, e1, units});
+    }
+};
 #define TRY(expr)                      \
     do {                               \
         int rc__ = (expr);             \
@@ -98,15 +130,15 @@ constexpr size_t SMALL_MSM_MAX_N = 2048;  // C = 6, WPB = 11: 11 * 6 * 2048 = 13
 
 // window sums for `count` segments -> d_win[count][nwin]
 int msm_buckets_dev(cdp_ctx *ctx, const msm_cfg &g, const uint8_t *d_pts, const uint8_t *d_scalars, const msm_seg_t *d_segs, size_t count,
-                    size_t nmax, uint32_t *d_win) {
-    ctx->launches++;
+                    size_t nmax, uint32_t *d_win, uint64_t pairs) {
+    launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, pairs);
     CUDA_TRY(ctx, launch_msm_buckets(ctx->stream, g.c, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars),
                                      d_segs, (uint32_t)count, (uint32_t)nmax, d_win));
     return CDP_OK;
 }
 
 int combine_dev(cdp_ctx *ctx, const msm_cfg &g, const uint32_t *d_win, size_t count, uint32_t *d_out_jac) {
-    ctx->launches++;
+    launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, count);
     CUDA_TRY(ctx, launch_msm_combine(ctx->stream, d_win, d_out_jac, (uint32_t)count, g.c, g.nwin));
     return CDP_OK;
 }
@@ -119,7 +151,7 @@ int normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_aff, 
     // enough threads to fill the machine first, then amortise the inversion over a chunk
     size_t fill = (size_t)ctx->sm_count * 1024;
     int chunk = n >= 8 * fill ? 8 : n >= 2 * fill ? 2 : 1;
-    ctx->launches++;
+    launch_scope ls(ctx, CDP_PROFILE_NORMALIZE, n);
     CUDA_TRY(ctx, launch_normalize(ctx->stream, chunk, j, a, d_comp, (uint32_t)n, jobs, elems_per_job));
     return CDP_OK;
 }
@@ -130,15 +162,19 @@ int smul_jobs_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_scalars, const 
     if (total == 0) return CDP_OK;
     if (total >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_TOO_LARGE, "smul jobs: too many elements");
     TRY(ensure_dev(ctx, ctx->d_jac, total * CDP_JACOBIAN_BYTES));
-    ctx->launches++;
-    CUDA_TRY(ctx, launch_smul_jobs(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars), d_jobs,
-                                   (uint32_t)n_jobs, (uint32_t)epj, reinterpret_cast<uint32_t *>(ctx->d_jac.ptr)));
+    {
+        launch_scope ls(ctx, CDP_PROFILE_SMUL, total);
+        CUDA_TRY(ctx, launch_smul_jobs(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars), d_jobs,
+                                       (uint32_t)n_jobs, (uint32_t)epj, reinterpret_cast<uint32_t *>(ctx->d_jac.ptr)));
+    }
     return normalize_dev(ctx, (const uint8_t *)ctx->d_jac.ptr, total, d_pts, nullptr, d_jobs, (uint32_t)epj);
 }
 
 const uint8_t INF_JAC_ZERO[CDP_JACOBIAN_BYTES] = {0};
 
 }  // namespace
+
+static void prof_drain(cdp_ctx *ctx);
 
 // =================================================================================================== context
 extern "C" int cdp_ctx_create(cdp_ctx **out, int device_id, void *stream) {
@@ -172,6 +208,8 @@ extern "C" void cdp_ctx_destroy(cdp_ctx *ctx) {
     for (scratch_t *s : {&ctx->d_pts, &ctx->d_scalars, &ctx->d_segs, &ctx->d_win, &ctx->d_jac, &ctx->d_aux, &ctx->d_out})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
+    prof_drain(ctx);
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -226,7 +264,7 @@ extern "C" int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t byte
 }
 
 extern "C" int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs,
-                                 size_t count, size_t max_n, uint8_t *d_out_jac) {
+                                 size_t count, size_t max_n, size_t total_pairs, uint8_t *d_out_jac) {
     if (!ctx || !d_out_jac) return CDP_ERR_INVALID_ARG;
     if (count == 0) return CDP_OK;
     if (max_n > SMALL_MSM_MAX_N) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm_batch_dev: segment longer than 2048 points; split it");
@@ -236,7 +274,7 @@ extern "C" int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, cons
     TRY(ensure_dev(ctx, ctx->d_win, count * g.nwin * CDP_JACOBIAN_BYTES));
     static_assert(sizeof(cdp_msm_seg) == sizeof(msm_seg_t), "segment layout");
     TRY(msm_buckets_dev(ctx, g, d_affine_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(d_segs), count, max_n,
-                        reinterpret_cast<uint32_t *>(ctx->d_win.ptr)));
+                        reinterpret_cast<uint32_t *>(ctx->d_win.ptr), total_pairs));
     return combine_dev(ctx, g, reinterpret_cast<const uint32_t *>(ctx->d_win.ptr), count, reinterpret_cast<uint32_t *>(d_out_jac));
 }
 
@@ -252,7 +290,7 @@ extern "C" int cdp_gather_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_src
     if (!ctx || (n && (!d_pts || !d_src || !d_src_idx || !d_dst_idx))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_gather_dev: null argument");
     if (n == 0) return CDP_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->launches++;
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, n);
     CUDA_TRY(ctx, launch_gather_points(ctx->stream, reinterpret_cast<uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_src), d_src_idx,
                                        d_dst_idx, (uint32_t)n));
     return CDP_OK;
@@ -262,7 +300,7 @@ extern "C" int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const
     if (!ctx || (n && (!d_pts || !d_out_compressed))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_compress_affine_dev: null argument");
     if (n == 0) return CDP_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    ctx->launches++;
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, n);
     CUDA_TRY(ctx, launch_compress_affine(ctx->stream, reinterpret_cast<const uint32_t *>(d_pts), d_index, d_out_compressed, (uint32_t)n));
     return CDP_OK;
 }
@@ -293,11 +331,11 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, ctx->h_stage.ptr, nchunks * sizeof(msm_seg_t), cudaMemcpyHostToDevice, ctx->stream));
     TRY(ensure_dev(ctx, ctx->d_win, (nchunks + 1) * g.nwin * CDP_JACOBIAN_BYTES));
     uint32_t *win = reinterpret_cast<uint32_t *>(ctx->d_win.ptr);
-    TRY(msm_buckets_dev(ctx, g, d_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(ctx->d_segs.ptr), nchunks, chunk, win));
+    TRY(msm_buckets_dev(ctx, g, d_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(ctx->d_segs.ptr), nchunks, chunk, win, n));
     const uint32_t *win_final = win;
     if (nchunks > 1) {
         uint32_t *red = win + 36 * nchunks * g.nwin;
-        ctx->launches++;
+        launch_scope ls(ctx, CDP_PROFILE_OTHER, nchunks);
         CUDA_TRY(ctx, launch_sum_groups(ctx->stream, win, red, (uint32_t)g.nwin, (uint32_t)nchunks, (uint32_t)g.nwin));
         win_final = red;
     }
@@ -390,10 +428,10 @@ extern "C" int cdp_msm_batch(cdp_ctx *ctx, const cdp_msm_desc *descs, size_t cou
         size_t first = 0;
         for (auto &o : order) {
             if (o.empty()) continue;
-            size_t max_n = 0;
-            for (size_t i : o) max_n = std::max(max_n, descs[i].n);
+            size_t max_n = 0, pairs = 0;
+            for (size_t i : o) { max_n = std::max(max_n, descs[i].n); pairs += descs[i].n; }
             TRY(cdp_msm_batch_dev(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr,
-                                  reinterpret_cast<const cdp_msm_seg *>(ctx->d_segs.ptr) + first, o.size(), max_n,
+                                  reinterpret_cast<const cdp_msm_seg *>(ctx->d_segs.ptr) + first, o.size(), max_n, pairs,
                                   (uint8_t *)ctx->d_jac.ptr + first * CDP_JACOBIAN_BYTES));
             first += o.size();
         }
@@ -466,6 +504,40 @@ extern "C" int cdp_normalize_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t 
 extern "C" int cdp_compress_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out_compressed) {
     if (!ctx || (n && (!jac_pts || !out_compressed))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_compress_batch: null argument");
     return normalize_host(ctx, jac_pts, n, out_compressed, true);
+}
+
+// =================================================================================================== profiling
+static void prof_drain(cdp_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            ctx->prof_ms[r.kind] += ms;
+            ctx->prof_launches[r.kind]++;
+            ctx->prof_units[r.kind] += r.units;
+        }
+        ctx->prof_pool.push_back(r.e0);
+        ctx->prof_pool.push_back(r.e1);
+    }
+    ctx->prof_pending.clear();
+}
+extern "C" int cdp_profile_enable(cdp_ctx *ctx, int on) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    prof_drain(ctx);
+    ctx->profiling = on != 0;
+    return CDP_OK;
+}
+extern "C" int cdp_profile_reset(cdp_ctx *ctx) {
+    if (!ctx) return CDP_ERR_INVALID_ARG;
+    prof_drain(ctx);
+    for (int k = 0; k < CDP_PROFILE_KINDS; k++) { ctx->prof_ms[k] = 0; ctx->prof_launches[k] = 0; ctx->prof_units[k] = 0; }
+    return CDP_OK;
+}
+extern "C" int cdp_profile_read(cdp_ctx *ctx, double ms[CDP_PROFILE_KINDS], uint64_t launches[CDP_PROFILE_KINDS], uint64_t units[CDP_PROFILE_KINDS]) {
+    if (!ctx || !ms || !launches || !units) return CDP_ERR_INVALID_ARG;
+    prof_drain(ctx);
+    for (int k = 0; k < CDP_PROFILE_KINDS; k++) { ms[k] = ctx->prof_ms[k]; launches[k] = ctx->prof_launches[k]; units[k] = ctx->prof_units[k]; }
+    return CDP_OK;
 }
 
 // =================================================================================================== diagnostics

@@ -41,7 +41,10 @@ _SIGS = {
     "cdp_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "cdp_host_alloc": (c_void_p, [c_void_p, c_size_t]),
     "cdp_host_free": (None, [c_void_p, c_void_p]),
-    "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    "cdp_profile_enable": (c_int, [c_void_p, c_int]),
+    "cdp_profile_reset": (c_int, [c_void_p]),
+    "cdp_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(c_uint64)]),
     "cdp_smul_jobs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
     "cdp_gather_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -191,6 +194,22 @@ class Engine:
         out = (ctypes.c_uint8 * max(1, n * COMPRESSED_BYTES))()
         self._check(self._lib.cdp_compress_batch(self._h, _buf(jac) if n else None, n, out), "cdp_compress_batch")
         return bytes(out)[:n * COMPRESSED_BYTES]
+
+    PROFILE_KINDS = ("msm_buckets", "msm_combine", "smul", "normalize", "other")
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.cdp_profile_enable(self._h, int(on)), "cdp_profile_enable")
+
+    def profile_reset(self):
+        self._check(self._lib.cdp_profile_reset(self._h), "cdp_profile_reset")
+
+    def profile_read(self) -> dict:
+        """{kind: {"ms": device time, "launches": count, "units": work items}} accumulated since the last reset."""
+        ms = (ctypes.c_double * 5)()
+        ln = (c_uint64 * 5)()
+        un = (c_uint64 * 5)()
+        self._check(self._lib.cdp_profile_read(self._h, ms, ln, un), "cdp_profile_read")
+        return {k: {"ms": ms[i], "launches": int(ln[i]), "units": int(un[i])} for i, k in enumerate(self.PROFILE_KINDS)}
 
     def bench_kernel(self, which: int, blocks: int, threads: int, iters: int) -> float:
         ms = c_float()

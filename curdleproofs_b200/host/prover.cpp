@@ -40,6 +40,7 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 struct SubLaunch {
     size_t K = 0;      // segments per proof
     size_t max_n = 0;  // largest segment (including the extra base)
+    size_t pairs_per_proof = 0;
     std::vector<cdp_msm_seg> segs;  // max_batch * K, proof-major
     cdp_msm_seg *d_segs = nullptr;
 };
@@ -80,6 +81,7 @@ struct cdp_prover {
     int threads = 1;
     std::string err = "ok";
     double timing[4] = {0, 0, 0, 0};
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // of the last cdp_prove_batch call
 
     // device point array: [CRS block | per-proof working blocks]
     size_t crs_n = 0, PW = 0;
@@ -95,6 +97,7 @@ struct cdp_prover {
     uint8_t *d_jac = nullptr, *d_comp = nullptr;
     uint8_t *h_scal = nullptr, *h_fscal = nullptr, *h_comp = nullptr, *h_in = nullptr;
     size_t max_scalars_pp = 0, max_out_pp = 0;
+    size_t staged_batch = 0;
     uint8_t H_comp[48];
 
     MsmStage st1, st2, st3, st4;
@@ -162,6 +165,7 @@ void build_stage(cdp_prover *p, MsmStage &st, const std::vector<SegSpec> &specs,
         st.where[i] = {cls[i], (int)sl.K};
         sl.K++;
         sl.max_n = std::max(sl.max_n, eff(specs[i]));
+        sl.pairs_per_proof += eff(specs[i]);
     }
     for (size_t c = 0; c < st.subs.size(); c++) {
         SubLaunch &sl = st.subs[c];
@@ -237,13 +241,15 @@ int upload_tables(cdp_prover *p) {
 int run_msm_stage(cdp_prover *p, MsmStage &st, size_t B, double &t_wait, double &t_copy) {
     double t0 = now_ms();
     PTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * st.scalars_per_proof * 32));
+    p->h2d_bytes += B * st.scalars_per_proof * 32;
     size_t out_off = 0;
     for (auto &sl : st.subs) {
-        PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, p->d_jac + out_off * 144));
+        PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
         out_off += B * sl.K;
     }
     PTRY(cdp_normalize_dev(p->ctx, p->d_jac, out_off, nullptr, p->d_comp));
     PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, out_off * 48));
+    p->d2h_bytes += out_off * 48;
     double t1 = now_ms();
     PTRY(cdp_sync(p->ctx));
     double t2 = now_ms();
@@ -260,6 +266,7 @@ const uint8_t *stage_out(const cdp_prover *p, const MsmStage &st, size_t B, size
 }
 int run_fold_stage(cdp_prover *p, FoldStage &fs, size_t B) {
     PTRY(cdp_h2d(p->ctx, p->d_fscal, p->h_fscal, B * fs.scalars_per_proof * 32));
+    p->h2d_bytes += B * fs.scalars_per_proof * 32;
     PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, fs.d_jobs, B * fs.J, fs.epj));
     return CDP_OK;
 }
@@ -275,6 +282,10 @@ extern "C" size_t cdp_proof_size(size_t ell) {
 extern "C" const char *cdp_prover_last_error(const cdp_prover *p) { return p ? p->err.c_str() : "null prover"; }
 extern "C" void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]) {
     for (int i = 0; i < 4; i++) out_ms[i] = p ? p->timing[i] : 0.0;
+}
+extern "C" void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]) {
+    out_bytes[0] = p ? p->h2d_bytes : 0;
+    out_bytes[1] = p ? p->d2h_bytes : 0;
 }
 
 extern "C" void cdp_prover_destroy(cdp_prover *p) {
@@ -432,6 +443,9 @@ extern "C" int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, con
 extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *in, uint8_t *proofs_out) {
     if (!p) return CDP_ERR_INVALID_ARG;
     if (!in || !proofs_out || B == 0 || B > p->max_batch) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: bad argument");
+    const bool resident = in->vec_R == nullptr;  // instance vectors of the previous call are still staged in HBM
+    if (resident && p->staged_batch < B) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: no resident instance batch of that size");
+    p->h2d_bytes = p->d2h_bytes = 0;
     const size_t ell = p->ell, n = p->n, m = p->m;
     const int T = p->threads;
     double t_start = now_ms(), t_host = 0, t_wait = 0, t_copy = 0, t0;
@@ -440,22 +454,27 @@ extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *
 
     // ---- stage 0: instance to the device, working vectors assembled, transcript openings compressed
     t0 = now_ms();
-    for (size_t pr = 0; pr < B; pr++) {
-        uint8_t *dst = p->h_in + pr * 4 * ell * 96;
-        memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
-        memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
-        memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
-        memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
+    if (!resident) {
+        for (size_t pr = 0; pr < B; pr++) {
+            uint8_t *dst = p->h_in + pr * 4 * ell * 96;
+            memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
+            memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
+            memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
+            memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
+        }
+        memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
+        PTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+        PTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
+        p->h2d_bytes += B * (4 * ell * 96 + 144);
+        PTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));  // M.into_affine()
+        p->staged_batch = B;
     }
-    memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
-    PTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
-    PTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
-    PTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));  // M.into_affine()
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_gsrc, p->d_gdst, B * p->g_count_per_proof));
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_count_per_proof));
     PTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp));
     PTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp + B * 4 * ell * 48));
     PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * 4 * ell + B) * 48));
+    p->d2h_bytes += (B * 4 * ell + B) * 48;
     t_copy += now_ms() - t0;
     t0 = now_ms();
     PTRY(cdp_sync(p->ctx));

@@ -36,6 +36,7 @@ def load_prover_library() -> ctypes.CDLL:
         lib.cdp_prove_batch.restype = c_int
         lib.cdp_prove_batch.argtypes = [c_void_p, c_size_t, POINTER(_ProveInputs), c_void_p]
         lib.cdp_prover_last_timing.argtypes = [c_void_p, POINTER(c_double)]
+        lib.cdp_prover_last_traffic.argtypes = [c_void_p, POINTER(c_uint64)]
         _PLIB = lib
     return _PLIB
 
@@ -88,8 +89,9 @@ class BatchProver:
         return self.prove_raw(B, bufs["R"], bufs["S"], bufs["T"], bufs["U"], bufs["M"], perm, bufs["k"], bufs["mb"], seeds, skips)
 
     def prove_raw(self, B, R, S, T, U, M, perm, k, mb, seeds, skips=None, out=None, split=True):
-        inp = _ProveInputs(ctypes.cast(R, c_void_p), ctypes.cast(S, c_void_p), ctypes.cast(T, c_void_p), ctypes.cast(U, c_void_p),
-                           ctypes.cast(M, c_void_p), ctypes.cast(perm, c_void_p), ctypes.cast(k, c_void_p), ctypes.cast(mb, c_void_p),
+        # R is None: reuse the instance batch staged in HBM by the previous call ("inputs already resident" mode)
+        vp = lambda x: ctypes.cast(x, c_void_p) if x is not None else None  # noqa: E731
+        inp = _ProveInputs(vp(R), vp(S), vp(T), vp(U), vp(M), ctypes.cast(perm, c_void_p), ctypes.cast(k, c_void_p), ctypes.cast(mb, c_void_p),
                            ctypes.cast(seeds, c_void_p), ctypes.cast(skips, c_void_p) if skips is not None else None)
         if out is None:
             out = (ctypes.c_uint8 * (B * self.proof_size))()
@@ -100,6 +102,11 @@ class BatchProver:
             return out
         raw = bytes(out)
         return [raw[i * self.proof_size:(i + 1) * self.proof_size] for i in range(B)]
+
+    def last_traffic(self) -> dict:
+        t = (c_uint64 * 2)()
+        self._lib.cdp_prover_last_traffic(self._h, t)
+        return {"h2d_bytes": int(t[0]), "d2h_bytes": int(t[1])}
 
     def last_timing(self) -> dict:
         t = (c_double * 4)()

@@ -113,8 +113,9 @@ typedef struct {
                        d_scalars[scalars_off + n].  Lets `msm(G_R, c_L) + ip * H` (src/inner_product_argument.rs:158) be ONE msm. */
 } cdp_msm_seg;
 /* `d_segs` is a DEVICE array of `count` cdp_msm_seg; `max_n` >= every segment's n.  Results: count Jacobian points. */
+/* `total_pairs` = sum of the segments' lengths (incl. extras); used for profiling accounting only, may be 0. */
 int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs, size_t count,
-                      size_t max_n, uint8_t *d_out_jac);
+                      size_t max_n, size_t total_pairs, uint8_t *d_out_jac);
 
 /* Batched scalar multiplication / fold over device-resident points.  For every job j and element e < elems_per_job:
  *   d_pts[out_off + e] = ( (add_off != CDP_NONE ? d_pts[add_off + e] : O)
@@ -140,6 +141,21 @@ int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint32_t *
 
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);
+
+/* ------------------------------------------------------------------ per-kernel profiling
+ * When enabled, every kernel launch of the context is bracketed by CUDA events on the context's stream and the elapsed
+ * device time is accumulated per kernel kind.  `units` accumulates the work items each launch processed: (scalar, point)
+ * pairs for the MSM bucket kernel, MSMs for the combine kernel, elements for smul / normalise.  bench.py derives the
+ * roofline figures from these. */
+#define CDP_PROFILE_MSM_BUCKETS 0
+#define CDP_PROFILE_MSM_COMBINE 1
+#define CDP_PROFILE_SMUL 2
+#define CDP_PROFILE_NORMALIZE 3
+#define CDP_PROFILE_OTHER 4
+#define CDP_PROFILE_KINDS 5
+int cdp_profile_enable(cdp_ctx *ctx, int on);
+int cdp_profile_reset(cdp_ctx *ctx);
+int cdp_profile_read(cdp_ctx *ctx, double ms[CDP_PROFILE_KINDS], uint64_t launches[CDP_PROFILE_KINDS], uint64_t units[CDP_PROFILE_KINDS]);
 
 /* ------------------------------------------------------------------ diagnostics
  * Integer-pipe micro-benchmarks used by bench.py for the roofline denominators.

@@ -47,12 +47,17 @@ typedef struct {
                                       consumed part of the stream (src/whisk.rs:153-154, src/util.rs:102) hand it over. */
 } cdp_prove_inputs;
 
-/* proofs_out: batch * cdp_proof_size(ell) bytes.  Host buffers in, host buffers out (copies are inside the call). */
+/* proofs_out: batch * cdp_proof_size(ell) bytes.  Host buffers in, host buffers out (copies are inside the call).
+ * If in->vec_R is NULL the instance vectors (R, S, T, U, M) staged in HBM by the previous call are reused -- the
+ * "inputs already resident" mode; witnesses and rng fields are still read from `in`. */
 int cdp_prove_batch(cdp_prover *p, size_t batch, const cdp_prove_inputs *in, uint8_t *proofs_out);
 
 /* Timing breakdown of the last cdp_prove_batch call, milliseconds: [0] total, [1] host transcript/scalar work,
  * [2] waiting on the GPU (stream synchronisation), [3] H2D/D2H staging issue time. */
 void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]);
+
+/* Host<->device bytes moved by the last cdp_prove_batch call: [0] host-to-device, [1] device-to-host. */
+void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]);
 
 #ifdef __cplusplus
 }
