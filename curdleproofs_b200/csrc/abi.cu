@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -120,9 +121,19 @@ struct launch_scope {
 struct msm_cfg {
     int c, nwin;
 };
+// Window width by MSM size.  Cost model (lane-steps per MSM, GLV doubles the point count):
+//   accumulate  nwin(c) * 2n / 2^(c-1) mixed additions per lane (+ imbalance), reduce  nwin(c) * 2(c-1) full additions per lane.
+// For the in-proof sizes the reduction dominates at c = 6, so narrow windows win until n reaches the thousands.
+// Override for tuning: CDP_MSM_THRESH="T6,T5,T4,T3" (smallest n that uses c = 6, 5, 4, 3).
 msm_cfg pick_cfg(size_t max_n) {
+    static size_t T[4] = {0, 0, 0, 0};
+    if (T[3] == 0) {
+        size_t d[4] = {1536, 160, 40, 10};
+        if (const char *e = getenv("CDP_MSM_THRESH")) sscanf(e, "%zu,%zu,%zu,%zu", &d[0], &d[1], &d[2], &d[3]);
+        for (int i = 0; i < 4; i++) T[i] = d[i] ? d[i] : 1;
+    }
     msm_cfg g;
-    g.c = max_n >= 96 ? 6 : max_n >= 40 ? 5 : max_n >= 12 ? 4 : max_n >= 3 ? 3 : 2;
+    g.c = max_n >= T[0] ? 6 : max_n >= T[1] ? 5 : max_n >= T[2] ? 4 : max_n >= T[3] ? 3 : 2;
     g.nwin = msm_nwin_for(g.c);
     return g;
 }
@@ -215,6 +226,7 @@ extern "C" void cdp_ctx_destroy(cdp_ctx *ctx) {
 }
 extern "C" const char *cdp_last_error(const cdp_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" uint64_t cdp_launch_count(const cdp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int cdp_ctx_device(const cdp_ctx *ctx) { return ctx ? ctx->device : -1; }
 extern "C" int cdp_sync(cdp_ctx *ctx) {
     if (!ctx) return CDP_ERR_INVALID_ARG;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -395,7 +407,7 @@ extern "C" int cdp_msm_batch(cdp_ctx *ctx, const cdp_msm_desc *descs, size_t cou
     if (total >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm_batch: too many points");
     // segments longer than the CTA capacity go through the single-MSM path
     std::vector<size_t> order[5], big;
-    auto cls = [](size_t n) { return n >= 96 ? 0 : n >= 40 ? 1 : n >= 12 ? 2 : n >= 3 ? 3 : 4; };
+    auto cls = [](size_t n) { return 6 - pick_cfg(n).c; };
     for (size_t i = 0; i < count; i++) {
         if (descs[i].n > SMALL_MSM_MAX_N) big.push_back(i);
         else if (descs[i].n == 0) memcpy(out_jac + i * CDP_JACOBIAN_BYTES, INF_JAC_ZERO, CDP_JACOBIAN_BYTES);
@@ -509,9 +521,12 @@ extern "C" int cdp_compress_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n
 // =================================================================================================== profiling
 static void prof_drain(cdp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
+    static const char *dump = getenv("CDP_PROFILE_DUMP");  // optional per-launch log: "kind units ms" per line
+    FILE *f = (dump && !ctx->prof_pending.empty()) ? fopen(dump, "a") : nullptr;
     for (auto &r : ctx->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            if (f) fprintf(f, "%d %llu %.4f\n", r.kind, (unsigned long long)r.units, ms);
             ctx->prof_ms[r.kind] += ms;
             ctx->prof_launches[r.kind]++;
             ctx->prof_units[r.kind] += r.units;
@@ -519,6 +534,7 @@ static void prof_drain(cdp_ctx *ctx) {
         ctx->prof_pool.push_back(r.e0);
         ctx->prof_pool.push_back(r.e1);
     }
+    if (f) fclose(f);
     ctx->prof_pending.clear();
 }
 extern "C" int cdp_profile_enable(cdp_ctx *ctx, int on) {

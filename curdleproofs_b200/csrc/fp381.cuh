@@ -170,7 +170,7 @@ __device__ __forceinline__ void fp_final_sub(fp &r) {
     fp_select(r, t, r, borrow != 0);
 }
 
-__device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) {
+__device__ __forceinline__ void fp_mul_inl(fp &r, const fp &a, const fp &b) {
     uint32_t m[12];
     fp out;
     uint32_t a0 = 0, a1 = 0, a2 = 0;
@@ -197,7 +197,7 @@ __device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) {
     r = out;
 }
 
-__device__ __forceinline__ void fp_sqr(fp &r, const fp &a) {
+__device__ __forceinline__ void fp_sqr_inl(fp &r, const fp &a) {
     uint32_t m[12];
     fp out;
     uint32_t a0 = 0, a1 = 0, a2 = 0;
@@ -229,6 +229,28 @@ __device__ __forceinline__ void fp_sqr(fp &r, const fp &a) {
     fp_final_sub(out);
     r = out;
 }
+
+// Out-of-line entry points.  Fully inlined, a kernel built on these products is 250-330 KB of straight-line SASS and
+// stalls on instruction fetch (ncu: smsp__average_warps_issue_stalled_no_instruction 2.5-5 per issue, profiles/r01_*_v0).
+// Called, the whole hot working set (mul + sqr + the point-formula glue) is ~20 KB and stays in the 32 KB L1.5 I-cache.
+// Arguments and result travel in registers (by-value structs), nothing goes through local memory.
+#ifndef CDP_INLINE_FP_MUL
+static __device__ __noinline__ fp fp_mul_fn(const fp a, const fp b) {
+    fp r;
+    fp_mul_inl(r, a, b);
+    return r;
+}
+static __device__ __noinline__ fp fp_sqr_fn(const fp a) {
+    fp r;
+    fp_sqr_inl(r, a);
+    return r;
+}
+__device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_fn(a, b); }
+__device__ __forceinline__ void fp_sqr(fp &r, const fp &a) { r = fp_sqr_fn(a); }
+#else
+__device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) { fp_mul_inl(r, a, b); }
+__device__ __forceinline__ void fp_sqr(fp &r, const fp &a) { fp_sqr_inl(r, a); }
+#endif
 
 // Montgomery <-> canonical
 __device__ __forceinline__ void fp_from_mont(fp &r, const fp &a) {

@@ -82,14 +82,26 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
     const int wl = lane_id / NB, b = lane_id % NB;
     const int w = w0 + wl;
     const bool active = wl < WPB && w < NWIN;
+    // The top window only holds the few leftover bits (plus the recoding carry): NBT distinct non-zero digits.  Lane-per-
+    // bucket would leave NB - NBT lanes idle and put 2n/NBT points on each of the others, and that one slow warp would keep
+    // the whole CTA resident (measured: 10% warps active, profiles/r01_ncu_msm_buckets_v0.txt).  So in the top window every
+    // bucket is spread over SP = NB / NBT lanes (by point index); phase 4 first folds the SP partial sums of a bucket.
+    constexpr int TB = 128 - C * (NWIN - 1);
+    constexpr int NBT = TB > 0 ? (1 << TB) : 1;
+    constexpr int SP = NB / NBT >= 1 ? NB / NBT : 1;
+    static_assert(NBT <= NB, "top-window digits must fit the lanes");
+    const bool is_top = (w == NWIN - 1);
+    auto bucket_of = [&](int d, uint32_t pidx) -> int {
+        int ad = d < 0 ? -d : d;
+        if (ad == 0) return -1;
+        return is_top ? (ad - 1) * SP + (int)(pidx & (SP - 1)) : ad - 1;
+    };
     // ---- phase 1: count
     uint32_t cnt = 0;
     if (active) {
         const int8_t *row = digits + wl * dstride;
         for (uint32_t p = 0; p < n2; p++) {
-            int d = row[p];
-            int ad = d < 0 ? -d : d;
-            cnt += (ad == b + 1);
+            cnt += (bucket_of(row[p], p) == b);
         }
     }
     // exclusive scan of cnt over the NB lanes of this window (NB <= 32, windows are NB-aligned inside a warp)
@@ -107,8 +119,7 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
         uint32_t e = 0;
         for (uint32_t p = 0; p < n2; p++) {
             int d = row[p];
-            int ad = d < 0 ? -d : d;
-            if (ad == b + 1) lst[e++] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
+            if (bucket_of(d, p) == b) lst[e++] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
         }
     }
     __syncwarp();
@@ -128,17 +139,30 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
             g1j_add_mixed(acc, acc, q);
         }
     }
-    // ---- phase 4: window reduction  S = sum_b (b+1) * B_b = sum_j suffix_j.  One loop, one inlined addition:
-    //      steps 0 .. C-2     inclusive suffix scan, distance 1, 2, 4, ...
-    //      steps C-1 .. 2C-3  tree sum of the suffix sums, distance NB/2, ..., 1
+    // ---- phase 4: window reduction  S = sum_b (b+1) * B_b = sum_j suffix_j, all with warp shuffles; one loop, one inlined
+    //      addition.  Ordinary window:  C-1 suffix-scan steps (distance 1, 2, 4, ...), then C-1 tree-sum steps.
+    //      Top window: log2(SP) steps fold the SP lanes of each bucket, then scan + tree over the NBT bucket leaders.
     if (NB > 1) {
+        constexpr int LS = SP >= 16 ? 4 : SP >= 8 ? 3 : SP >= 4 ? 2 : SP >= 2 ? 1 : 0;
+        constexpr int LN = NBT >= 16 ? 4 : NBT >= 8 ? 3 : NBT >= 4 ? 2 : NBT >= 2 ? 1 : 0;
+        static_assert(LS + 2 * LN <= 2 * (C - 1), "top-window schedule must fit the step count");
 #pragma unroll 1
         for (int step = 0; step < 2 * (C - 1); step++) {
-            const bool scan = step < C - 1;
-            const int d = scan ? (1 << step) : (NB >> (step - (C - 1) + 1));
+            int d;
+            bool take;
+            if (!is_top) {
+                const bool scan = step < C - 1;
+                d = scan ? (1 << step) : (NB >> (step - (C - 1) + 1));
+                take = scan ? (b + d < NB) : (b < d);
+            } else {
+                const bool leader = (b & (SP - 1)) == 0;
+                if (step < LS) { d = SP >> (step + 1); take = (b & (SP - 1)) < d; }
+                else if (step < LS + LN) { d = SP << (step - LS); take = leader && (b + d < NB); }
+                else if (step < LS + 2 * LN) { d = NB >> (step - LS - LN + 1); take = leader && (b < d); }
+                else { d = 1; take = false; }
+            }
             g1j o;
             shfl_down_g1j(o, acc, d, NB);
-            const bool take = scan ? (b + d < NB) : (b < d);
             if (take) g1j_add(acc, acc, o);
         }
     }

@@ -28,6 +28,7 @@ _SIGS = {
     "cdp_last_error": (c_char_p, [c_void_p]),
     "cdp_launch_count": (c_uint64, [c_void_p]),
     "cdp_sync": (c_int, [c_void_p]),
+    "cdp_ctx_device": (c_int, [c_void_p]),
     "cdp_msm": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_msm_from_projective": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_msm_batch": (c_int, [c_void_p, POINTER(_MsmDesc), c_size_t, c_void_p]),

@@ -75,7 +75,7 @@ enum Stage1Out { O_A = 0, O_R, O_S, O_T1, O_T2, O_U1, O_U2, O_A1, O_A2, O_B1, O_
 
 }  // namespace
 
-struct cdp_prover {
+struct Lane {
     cdp_ctx *ctx = nullptr;
     size_t ell = 0, n = 0, m = 0, max_batch = 0;
     int threads = 1;
@@ -110,7 +110,7 @@ struct cdp_prover {
 
 namespace {
 
-int perr(cdp_prover *p, int code, const std::string &msg) {
+int perr(Lane *p, int code, const std::string &msg) {
     p->err = msg;
     return code;
 }
@@ -146,7 +146,7 @@ struct SegSpec {
     size_t n;
     long extra_abs;    // absolute index of the extra base, -1 none
 };
-void build_stage(cdp_prover *p, MsmStage &st, const std::vector<SegSpec> &specs, size_t scalars_pp) {
+void build_stage(Lane *p, MsmStage &st, const std::vector<SegSpec> &specs, size_t scalars_pp) {
     st.scalars_per_proof = scalars_pp;
     // two size classes keep the tiny (1-3 point) MSMs out of the big-CTA launch
     auto eff = [](const SegSpec &s) { return s.n + (s.extra_abs >= 0 ? 1 : 0); };
@@ -190,7 +190,7 @@ struct JobSpec {
     bool has_add;
     size_t scal_rel, stride;
 };
-void build_fold(cdp_prover *p, FoldStage &fs, const std::vector<JobSpec> &specs, size_t epj, size_t scalars_pp) {
+void build_fold(Lane *p, FoldStage &fs, const std::vector<JobSpec> &specs, size_t epj, size_t scalars_pp) {
     fs.J = specs.size();
     fs.epj = epj;
     fs.scalars_per_proof = scalars_pp;
@@ -209,7 +209,7 @@ void build_fold(cdp_prover *p, FoldStage &fs, const std::vector<JobSpec> &specs,
     }
 }
 
-int upload_tables(cdp_prover *p) {
+int upload_tables(Lane *p) {
     auto up_stage = [&](MsmStage &st) -> int {
         for (auto &sl : st.subs) {
             size_t bytes = sl.segs.size() * sizeof(cdp_msm_seg);
@@ -238,7 +238,7 @@ int upload_tables(cdp_prover *p) {
 
 // ---- running a stage -----------------------------------------------------------------------------------------
 // scalars for all proofs are already in p->h_scal (proof-major, st.scalars_per_proof each)
-int run_msm_stage(cdp_prover *p, MsmStage &st, size_t B, double &t_wait, double &t_copy) {
+int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_copy) {
     double t0 = now_ms();
     PTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * st.scalars_per_proof * 32));
     p->h2d_bytes += B * st.scalars_per_proof * 32;
@@ -258,13 +258,13 @@ int run_msm_stage(cdp_prover *p, MsmStage &st, size_t B, double &t_wait, double 
     return CDP_OK;
 }
 // compressed output q of proof pr after run_msm_stage
-const uint8_t *stage_out(const cdp_prover *p, const MsmStage &st, size_t B, size_t pr, size_t q) {
+const uint8_t *stage_out(const Lane *p, const MsmStage &st, size_t B, size_t pr, size_t q) {
     size_t base = 0;
     for (int s = 0; s < st.where[q].first; s++) base += B * st.subs[s].K;
     const SubLaunch &sl = st.subs[st.where[q].first];
     return p->h_comp + 48 * (base + pr * sl.K + st.where[q].second);
 }
-int run_fold_stage(cdp_prover *p, FoldStage &fs, size_t B) {
+int run_fold_stage(Lane *p, FoldStage &fs, size_t B) {
     PTRY(cdp_h2d(p->ctx, p->d_fscal, p->h_fscal, B * fs.scalars_per_proof * 32));
     p->h2d_bytes += B * fs.scalars_per_proof * 32;
     PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, fs.d_jobs, B * fs.J, fs.epj));
@@ -279,16 +279,7 @@ extern "C" size_t cdp_proof_size(size_t ell) {
     return 1088 + 480 * m;
 }
 
-extern "C" const char *cdp_prover_last_error(const cdp_prover *p) { return p ? p->err.c_str() : "null prover"; }
-extern "C" void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]) {
-    for (int i = 0; i < 4; i++) out_ms[i] = p ? p->timing[i] : 0.0;
-}
-extern "C" void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]) {
-    out_bytes[0] = p ? p->h2d_bytes : 0;
-    out_bytes[1] = p ? p->d2h_bytes : 0;
-}
-
-extern "C" void cdp_prover_destroy(cdp_prover *p) {
+static void lane_destroy(Lane *p) {
     if (!p) return;
     cdp_ctx *c = p->ctx;
     auto free_stage = [&](MsmStage &st) { for (auto &sl : st.subs) cdp_dev_free(c, sl.d_segs); };
@@ -305,16 +296,16 @@ extern "C" void cdp_prover_destroy(cdp_prover *p) {
     delete p;
 }
 
-extern "C" int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
+static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
     if (!out || !ctx || !crs_points || max_batch == 0 || ell < 4) return CDP_ERR_INVALID_ARG;
     *out = nullptr;
     size_t n = ell + NBL, m = 0;
     while (((size_t)1 << m) < n) m++;
     if (((size_t)1 << m) != n) return CDP_ERR_INVALID_ARG;  // n must be a power of two (src/inner_product_argument.rs:116)
     if (n + 1 > 2048) return CDP_ERR_TOO_LARGE;
-    cdp_prover *p = new cdp_prover();
+    Lane *p = new Lane();
     p->ctx = ctx; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch;
-    p->threads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    p->threads = std::max(1, host_threads);
     // ---- device point layout
     const size_t cG = 0, cH = n, cGt = n + 1, cGu = n + 2;  // CRS block: G (ell) | Hvec (4) | H | G_t | G_u
     (void)cG;
@@ -418,7 +409,7 @@ extern "C" int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, con
     }
     p->d_gsrc = (uint32_t *)dalloc(gsrc.size() * 4); p->d_gdst = (uint32_t *)dalloc(gdst.size() * 4);
     p->d_isrc = (uint32_t *)dalloc(isrc.size() * 4); p->d_idst = (uint32_t *)dalloc(idst.size() * 4);
-    if (!ok) { p->err = "allocation failed"; cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+    if (!ok) { p->err = "allocation failed"; lane_destroy(p); return CDP_ERR_CUDA; }
     int rc = CDP_OK;
     // CRS block + the trailing all-zero point
     std::vector<uint8_t> zero(96, 0);
@@ -432,17 +423,18 @@ extern "C" int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, con
     rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_comp);
     rc |= cdp_d2h(ctx, p->h_comp, p->d_comp, 48);
     rc |= cdp_sync(ctx);
-    if (rc) { p->err = std::string("setup: ") + cdp_last_error(ctx); cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+    if (rc) { p->err = std::string("setup: ") + cdp_last_error(ctx); lane_destroy(p); return CDP_ERR_CUDA; }
     memcpy(p->H_comp, p->h_comp, 48);
-    if (upload_tables(p) != CDP_OK) { cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+    if (upload_tables(p) != CDP_OK) { lane_destroy(p); return CDP_ERR_CUDA; }
     p->ps.resize(max_batch);
     *out = p;
     return CDP_OK;
 }
 
-extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *in, uint8_t *proofs_out) {
+static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *proofs_out) {
     if (!p) return CDP_ERR_INVALID_ARG;
-    if (!in || !proofs_out || B == 0 || B > p->max_batch) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: bad argument");
+    if (!in || !proofs_out || B > p->max_batch) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: bad argument");
+    if (B == 0) return CDP_OK;
     const bool resident = in->vec_R == nullptr;  // instance vectors of the previous call are still staged in HBM
     if (resident && p->staged_batch < B) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: no resident instance batch of that size");
     p->h2d_bytes = p->d2h_bytes = 0;
@@ -790,5 +782,113 @@ extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *
     p->timing[1] = t_host;
     p->timing[2] = t_wait;
     p->timing[3] = t_copy;
+    return CDP_OK;
+}
+
+// =================================================================================================== public C ABI
+// The prover runs `lanes` independent sub-batches concurrently, each on its own CUDA stream (its own cdp_ctx) driven by its
+// own host thread: while one lane hashes transcripts on the host, or sits in a latency-bound tail of a small launch, the
+// others keep the SMs busy.
+struct cdp_prover {
+    std::vector<Lane *> lanes;
+    std::vector<cdp_ctx *> owned;
+    std::vector<size_t> last_split;
+    size_t ell = 0, max_batch = 0;
+    std::string err = "ok";
+    double timing[4] = {0, 0, 0, 0};
+    uint64_t traffic[2] = {0, 0};
+};
+
+extern "C" const char *cdp_prover_last_error(const cdp_prover *p) { return p ? p->err.c_str() : "null prover"; }
+extern "C" void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]) {
+    for (int i = 0; i < 4; i++) out_ms[i] = p ? p->timing[i] : 0.0;
+}
+extern "C" void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]) {
+    out_bytes[0] = p ? p->traffic[0] : 0;
+    out_bytes[1] = p ? p->traffic[1] : 0;
+}
+extern "C" void cdp_prover_destroy(cdp_prover *p) {
+    if (!p) return;
+    for (Lane *l : p->lanes) lane_destroy(l);
+    for (cdp_ctx *c : p->owned) cdp_ctx_destroy(c);
+    delete p;
+}
+extern "C" int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
+    return cdp_prover_create_lanes(out, ctx, ell, crs_points, max_batch, host_threads, 0);
+}
+extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads,
+                                       int lanes) {
+    if (!out || !ctx || !crs_points || max_batch == 0) return CDP_ERR_INVALID_ARG;
+    *out = nullptr;
+    int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (host_threads <= 0) host_threads = hw;
+    if (lanes <= 0) lanes = max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
+    lanes = (int)std::min<size_t>((size_t)lanes, max_batch);
+    cdp_prover *p = new cdp_prover();
+    p->ell = ell;
+    p->max_batch = max_batch;
+    size_t per_lane = (max_batch + lanes - 1) / lanes;
+    int threads_per_lane = std::max(1, host_threads / lanes);
+    for (int i = 0; i < lanes; i++) {
+        cdp_ctx *c = ctx;
+        if (i > 0) {
+            if (cdp_ctx_create(&c, cdp_ctx_device(ctx), nullptr) != CDP_OK) { cdp_prover_destroy(p); return CDP_ERR_CUDA; }
+            p->owned.push_back(c);
+        }
+        Lane *l = nullptr;
+        int rc = lane_create(&l, c, ell, crs_points, per_lane, threads_per_lane);
+        if (rc != CDP_OK) { cdp_prover_destroy(p); return rc; }
+        p->lanes.push_back(l);
+    }
+    *out = p;
+    return CDP_OK;
+}
+extern "C" int cdp_prover_lane_count(const cdp_prover *p) { return p ? (int)p->lanes.size() : 0; }
+extern "C" cdp_ctx *cdp_prover_lane_ctx(const cdp_prover *p, int lane) {
+    return (p && lane >= 0 && lane < (int)p->lanes.size()) ? p->lanes[lane]->ctx : nullptr;
+}
+
+extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *in, uint8_t *proofs_out) {
+    if (!p) return CDP_ERR_INVALID_ARG;
+    if (!in || !proofs_out || B == 0 || B > p->max_batch) { p->err = "cdp_prove_batch: bad argument"; return CDP_ERR_INVALID_ARG; }
+    const size_t L = p->lanes.size(), ell = p->ell, psz = cdp_proof_size(ell);
+    // contiguous split, as even as possible
+    std::vector<size_t> off(L + 1, 0);
+    for (size_t i = 0; i < L; i++) off[i + 1] = off[i] + (B / L + (i < B % L ? 1 : 0));
+    if (!in->vec_R && p->last_split != off) { p->err = "cdp_prove_batch: resident mode needs the same batch size as the staged call"; return CDP_ERR_INVALID_ARG; }
+    p->last_split = off;
+    std::vector<int> rcs(L, CDP_OK);
+    double t0 = now_ms();
+    auto run = [&](size_t i) {
+        size_t o = off[i], cnt = off[i + 1] - off[i];
+        if (cnt == 0) return;
+        cdp_prove_inputs sub = *in;
+        if (in->vec_R) {
+            sub.vec_R = in->vec_R + o * ell * 96; sub.vec_S = in->vec_S + o * ell * 96;
+            sub.vec_T = in->vec_T + o * ell * 96; sub.vec_U = in->vec_U + o * ell * 96;
+            sub.M = in->M + o * 144;
+        }
+        sub.permutation = in->permutation + o * ell;
+        sub.k = in->k + o * 32;
+        sub.vec_m_blinders = in->vec_m_blinders + o * 128;
+        sub.rng_seed = in->rng_seed + o;
+        sub.rng_skip_words = in->rng_skip_words ? in->rng_skip_words + o : nullptr;
+        rcs[i] = lane_prove(p->lanes[i], cnt, &sub, proofs_out + o * psz);
+    };
+    if (L == 1) run(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < L; i++) th.emplace_back(run, i);
+        for (auto &t : th) t.join();
+    }
+    p->timing[0] = now_ms() - t0;
+    p->timing[1] = p->timing[2] = p->timing[3] = 0;
+    p->traffic[0] = p->traffic[1] = 0;
+    for (size_t i = 0; i < L; i++) {
+        if (rcs[i] != CDP_OK) { p->err = "lane " + std::to_string(i) + ": " + p->lanes[i]->err; return rcs[i]; }
+        for (int k = 1; k < 4; k++) p->timing[k] = std::max(p->timing[k], p->lanes[i]->timing[k]);
+        p->traffic[0] += p->lanes[i]->h2d_bytes;
+        p->traffic[1] += p->lanes[i]->d2h_bytes;
+    }
     return CDP_OK;
 }

@@ -30,6 +30,12 @@ def load_prover_library() -> ctypes.CDLL:
         lib.cdp_proof_size.argtypes = [c_size_t]
         lib.cdp_prover_create.restype = c_int
         lib.cdp_prover_create.argtypes = [POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_size_t, c_int]
+        lib.cdp_prover_create_lanes.restype = c_int
+        lib.cdp_prover_create_lanes.argtypes = [POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int]
+        lib.cdp_prover_lane_count.restype = c_int
+        lib.cdp_prover_lane_count.argtypes = [c_void_p]
+        lib.cdp_prover_lane_ctx.restype = c_void_p
+        lib.cdp_prover_lane_ctx.argtypes = [c_void_p, c_int]
         lib.cdp_prover_destroy.argtypes = [c_void_p]
         lib.cdp_prover_last_error.restype = c_char_p
         lib.cdp_prover_last_error.argtypes = [c_void_p]
@@ -50,7 +56,7 @@ class BatchProver:
 
     crs_points: ell + 7 affine points, `CurdleproofsCrs::from_points` order (src/crs.rs:37-58)."""
 
-    def __init__(self, engine: Engine, ell: int, crs_points: bytes, max_batch: int, host_threads: int = 0):
+    def __init__(self, engine: Engine, ell: int, crs_points: bytes, max_batch: int, host_threads: int = 0, lanes: int = 0):
         self._lib = load_prover_library()
         self.engine = engine
         self.ell = ell
@@ -59,10 +65,12 @@ class BatchProver:
         if len(crs_points) != (ell + 7) * AFFINE_BYTES:
             raise ValueError("crs_points must hold ell + 7 affine points")
         h = c_void_p()
-        rc = self._lib.cdp_prover_create(ctypes.byref(h), engine.handle, ell, _arr(crs_points), max_batch, host_threads)
+        rc = self._lib.cdp_prover_create_lanes(ctypes.byref(h), engine.handle, ell, _arr(crs_points), max_batch, host_threads, lanes)
         if rc != 0:
             raise CdpError(f"cdp_prover_create failed (code {rc})")
         self._h = h
+        self.lanes = int(self._lib.cdp_prover_lane_count(h))
+        self._lane_ctx = [c_void_p(self._lib.cdp_prover_lane_ctx(h, i)) for i in range(self.lanes)]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -102,6 +110,33 @@ class BatchProver:
             return out
         raw = bytes(out)
         return [raw[i * self.proof_size:(i + 1) * self.proof_size] for i in range(B)]
+
+    # ---- accounting across the lanes' contexts (lane 0 is the caller's Engine) ----
+    @property
+    def launch_count(self) -> int:
+        return sum(int(self.engine.lib.cdp_launch_count(c)) for c in self._lane_ctx)
+
+    def profile_enable(self, on: bool = True):
+        for c in self._lane_ctx:
+            self.engine.lib.cdp_profile_enable(c, int(on))
+
+    def profile_reset(self):
+        for c in self._lane_ctx:
+            self.engine.lib.cdp_profile_reset(c)
+
+    def profile_read(self) -> dict:
+        """Per-kernel device time summed over lanes (lanes overlap on the GPU, so the sum can exceed the wall time)."""
+        tot = {k: {"ms": 0.0, "launches": 0, "units": 0} for k in Engine.PROFILE_KINDS}
+        for c in self._lane_ctx:
+            ms = (c_double * 5)()
+            ln = (c_uint64 * 5)()
+            un = (c_uint64 * 5)()
+            self.engine.lib.cdp_profile_read(c, ms, ln, un)
+            for i, k in enumerate(Engine.PROFILE_KINDS):
+                tot[k]["ms"] += ms[i]
+                tot[k]["launches"] += int(ln[i])
+                tot[k]["units"] += int(un[i])
+        return tot
 
     def last_traffic(self) -> dict:
         t = (c_uint64 * 2)()

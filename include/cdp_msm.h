@@ -52,6 +52,8 @@ void cdp_ctx_destroy(cdp_ctx *ctx);
 const char *cdp_last_error(const cdp_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 uint64_t cdp_launch_count(const cdp_ctx *ctx);
+/* CUDA device ordinal the context was created on. */
+int cdp_ctx_device(const cdp_ctx *ctx);
 /* Block until everything queued on the context's stream has finished. */
 int cdp_sync(cdp_ctx *ctx);
 

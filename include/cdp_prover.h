@@ -29,6 +29,15 @@ size_t cdp_proof_size(size_t ell);
  * vec_G (ell) | vec_H (4) | H | G_t | G_u.  ell + 4 must be a power of two (src/inner_product_argument.rs:116).
  * `ctx` must outlive the prover.  `host_threads` <= 0 selects all host cores. */
 int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads);
+/* Same, with an explicit number of concurrent lanes.  A lane is an independent sub-batch pipeline with its own CUDA stream
+ * (lane 0 uses `ctx`, the others create private contexts on the same device) and its own host threads, so that host-side
+ * transcript work and latency-bound launches of one lane overlap with GPU work of the others.  lanes <= 0 picks a default
+ * (4 for max_batch >= 128).  cdp_prover_create is cdp_prover_create_lanes with lanes = 0. */
+int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads,
+                            int lanes);
+int cdp_prover_lane_count(const cdp_prover *p);
+/* The cdp_ctx a lane runs on (for cdp_profile_* / cdp_launch_count accounting across lanes). */
+cdp_ctx *cdp_prover_lane_ctx(const cdp_prover *p, int lane);
 void cdp_prover_destroy(cdp_prover *p);
 const char *cdp_prover_last_error(const cdp_prover *p);
 
