@@ -48,6 +48,7 @@ struct MsmStage {
     size_t scalars_per_proof = 0;
     std::vector<SubLaunch> subs;
     std::vector<std::pair<int, int>> where;  // logical output q -> (sub, k)
+    size_t aff_region = (size_t)-1;          // when set: the stage's normalised points are also stored (affine) at this point index
     size_t outputs() const { return where.size(); }
 };
 struct FoldStage {
@@ -71,7 +72,14 @@ struct ProofState {
     std::vector<uint8_t> ipa_rounds, sm_rounds;  // m * 4 * 48, m * 6 * 48
 };
 
-enum Stage1Out { O_A = 0, O_R, O_S, O_T1, O_T2, O_U1, O_U2, O_A1, O_A2, O_B1, O_B2, O_AP, O_BA, O_BT, O_BU };
+// proof-level names of the 15 points produced before the IPA rounds
+enum ProofPt { O_A = 0, O_R, O_S, O_T1, O_T2, O_U1, O_U2, O_A1, O_A2, O_B1, O_B2, O_AP, O_BA, O_BT, O_BU };
+// stage 1: the six full-size MSMs (their affine results are kept in HBM for stage 2) and four single scalar-muls
+enum Stage1Out { S1_A = 0, S1_R, S1_S, S1_BA, S1_BT, S1_BU, S1_T1, S1_U1, S1_A1, S1_B1, S1_COUNT };
+// stage 2: short combinations of points that already exist (B plus the second halves of the four GroupCommitments and A')
+enum Stage2Out { S2_B = 0, S2_T2, S2_A2, S2_U2, S2_B2, S2_AP, S2_COUNT };
+// per-proof scratch block X of gathered affine points feeding the short MSMs
+enum XSlot { X_A = 0, X_M, X_GSUM, X_R, X_H1, X_S, X_H2, X_A2, X_GT, X_GU, X_B, X_GSUM2, X_HSUM, X_COUNT };
 
 }  // namespace
 
@@ -85,7 +93,9 @@ struct Lane {
 
     // device point array: [CRS block | per-proof working blocks]
     size_t crs_n = 0, PW = 0;
-    size_t o_GHM = 0, o_Gi = 0, o_Gp = 0, o_Gs = 0, o_T = 0, o_U = 0, o_R = 0, o_S = 0;
+    size_t o_GHM = 0, o_Gi = 0, o_Gp = 0, o_Gs = 0, o_T = 0, o_U = 0, o_R = 0, o_S = 0, o_X = 0;
+    size_t reg1 = 0, reg2 = 0;  // affine outputs of stage 1 / stage 2, proof-major (index pr * K + k), kept for the next stage
+    uint32_t *d_x1src = nullptr, *d_x1dst = nullptr, *d_x2src = nullptr, *d_x2dst = nullptr;
     uint8_t *d_pts = nullptr;
     uint8_t *d_in = nullptr;       // staging for the instance vectors of a batch (R,S,T,U: 4*ell per proof) + M affine
     uint8_t *d_Mjac = nullptr;
@@ -247,7 +257,7 @@ int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_cop
         PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
         out_off += B * sl.K;
     }
-    PTRY(cdp_normalize_dev(p->ctx, p->d_jac, out_off, nullptr, p->d_comp));
+    PTRY(cdp_normalize_dev(p->ctx, p->d_jac, out_off, st.aff_region != (size_t)-1 ? p->d_pts + st.aff_region * 96 : nullptr, p->d_comp));
     PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, out_off * 48));
     p->d2h_bytes += out_off * 48;
     double t1 = now_ms();
@@ -290,7 +300,7 @@ static void lane_destroy(Lane *p) {
     for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
     cdp_dev_free(c, p->f_gp.d_jobs);
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
-                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp})
+                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp})
         cdp_dev_free(c, d);
     for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_comp, (void *)p->h_in}) cdp_host_free(c, h);
     delete p;
@@ -307,42 +317,51 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
     p->ctx = ctx; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch;
     p->threads = std::max(1, host_threads);
     // ---- device point layout
-    const size_t cG = 0, cH = n, cGt = n + 1, cGu = n + 2;  // CRS block: G (ell) | Hvec (4) | H | G_t | G_u
+    const size_t cG = 0, cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;  // CRS block: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec)
     (void)cG;
-    p->crs_n = n + 3;
+    p->crs_n = n + 5;
     p->o_GHM = 0; p->o_Gi = n + 1; p->o_Gp = 2 * n + 1; p->o_Gs = 3 * n + 1; p->o_T = 4 * n + 1; p->o_U = 5 * n + 1;
-    p->o_R = 6 * n + 1; p->o_S = 6 * n + 1 + ell;
-    p->PW = 6 * n + 1 + 2 * ell;
-    size_t total_pts = p->crs_n + max_batch * p->PW;
+    p->o_R = 6 * n + 1; p->o_S = 6 * n + 1 + ell; p->o_X = 6 * n + 1 + 2 * ell;
+    p->PW = 6 * n + 1 + 2 * ell + X_COUNT;
+    p->reg1 = p->crs_n + max_batch * p->PW;
+    p->reg2 = p->reg1 + max_batch * S1_COUNT;
+    size_t total_pts = p->reg2 + max_batch * S2_COUNT;
     if (total_pts >= ((size_t)1 << 31)) { delete p; return CDP_ERR_TOO_LARGE; }
 
     // ---- stage tables
     {   // stage 1: everything that depends only on vec_a and the prover's own randomness
-        size_t sA = 0, sa = n, sT = sa + ell, sU = sT + ell + 1, sCA = sU + ell + 1, sCB = sCA + ell + 1, sAP = sCB + ell + 1, sR = sAP + n;
-        std::vector<SegSpec> v(15);
-        v[O_A] = {p->o_GHM, false, sA, n, -1};                       // A = msm(G|Hvec, a_perm | r_a')            curdleproofs.rs:93
-        v[O_R] = {p->o_R, false, sa, ell, -1};                       // R = msm(vec_R, a)                         :112
-        v[O_S] = {p->o_S, false, sa, ell, -1};                       // S = msm(vec_S, a)                         :113
-        v[O_T1] = {cGt, true, sT + ell, 1, -1};                      // cm_T.T_1 = r_t G_t                        :115 / commitments.rs:50
-        v[O_T2] = {p->o_R, false, sT, ell, (long)cH};                // cm_T.T_2 = k R + r_t H = msm(vec_R|H, k a | r_t)
-        v[O_U1] = {cGu, true, sU + ell, 1, -1};
-        v[O_U2] = {p->o_S, false, sU, ell, (long)cH};
-        v[O_A1] = {cGt, true, sCA + ell, 1, -1};                     // cm_A = GroupCommitment(G_t, H, r_k R, r_a)  same_scalar_argument.rs:60
-        v[O_A2] = {p->o_R, false, sCA, ell, (long)cH};
-        v[O_B1] = {cGu, true, sCB + ell, 1, -1};                     // cm_B                                       :61
-        v[O_B2] = {p->o_S, false, sCB, ell, (long)cH};
-        v[O_AP] = {p->o_Gs, false, sAP, n, -1};                      // A' = A + T_1 + U_1 = msm(G_with_blinders, a_with_blinders)  :131
-        v[O_BA] = {p->o_Gs, false, sR, n, -1};                       // B_a, B_t, B_u                              same_multiscalar_argument.rs:80-82
-        v[O_BT] = {p->o_T, false, sR, n, -1};
-        v[O_BU] = {p->o_U, false, sR, n, -1};
-        build_stage(p, p->st1, v, sR + n);
+        // scalars: a_perm|r_a' (n) | vec_a (ell) | r_sm (n) | r_t | r_u | r_a | r_b
+        const size_t sa = n, sR = n + ell, sx = 2 * n + ell;
+        std::vector<SegSpec> v(S1_COUNT);
+        v[S1_A] = {p->o_GHM, false, 0, n, -1};         // A = msm(G|Hvec, a_perm | r_a')            curdleproofs.rs:93
+        v[S1_R] = {p->o_R, false, sa, ell, -1};        // R = msm(vec_R, a)                         :112
+        v[S1_S] = {p->o_S, false, sa, ell, -1};        // S = msm(vec_S, a)                         :113
+        v[S1_BA] = {p->o_Gs, false, sR, n, -1};        // B_a, B_t, B_u                              same_multiscalar_argument.rs:80-82
+        v[S1_BT] = {p->o_T, false, sR, n, -1};
+        v[S1_BU] = {p->o_U, false, sR, n, -1};
+        v[S1_T1] = {cGt, true, sx, 1, -1};             // cm_T.T_1 = r_t G_t                        :115 / commitments.rs:50
+        v[S1_U1] = {cGu, true, sx + 1, 1, -1};         // cm_U.T_1 = r_u G_u                        :116
+        v[S1_A1] = {cGt, true, sx + 2, 1, -1};         // cm_A.T_1 = r_a G_t                        same_scalar_argument.rs:60
+        v[S1_B1] = {cGu, true, sx + 3, 1, -1};         // cm_B.T_1 = r_b G_u                        :61
+        build_stage(p, p->st1, v, sx + 4);
+        p->st1.aff_region = p->reg1;
     }
-    build_stage(p, p->st2, {{p->o_GHM, false, 0, n + 1, -1}}, n + 1);              // B     same_permutation_argument.rs:75-76
+    {   // stage 2: values that are short combinations of points already in HBM (gathered into the proof's X block)
+        std::vector<SegSpec> v(S2_COUNT);
+        v[S2_B] = {p->o_X + X_A, false, 0, 3, -1};     // B = A + alpha M + beta sum(G)             same_permutation_argument.rs:75-76
+        v[S2_T2] = {p->o_X + X_R, false, 3, 2, -1};    // cm_T.T_2 = k R + r_t H                    curdleproofs.rs:115 / commitments.rs:51
+        v[S2_A2] = {p->o_X + X_R, false, 5, 2, -1};    // cm_A.T_2 = r_k R + r_a H                  same_scalar_argument.rs:60
+        v[S2_U2] = {p->o_X + X_S, false, 7, 2, -1};    // cm_U.T_2 = k S + r_u H
+        v[S2_B2] = {p->o_X + X_S, false, 9, 2, -1};    // cm_B.T_2 = r_k S + r_b H
+        v[S2_AP] = {p->o_X + X_A2, false, 11, 3, -1};  // A' = A + cm_T.T_1 + cm_U.T_1 = A + r_t G_t + r_u G_u   curdleproofs.rs:131
+        build_stage(p, p->st2, v, 14);
+        p->st2.aff_region = p->reg2;
+    }
     build_stage(p, p->st3, {{p->o_GHM, false, 0, n, -1}}, n);                      // C     grand_product_argument.rs:76
-    build_stage(p, p->st4, {{p->o_GHM, false, 0, n + 1, -1},                       // D     grand_product_argument.rs:132
-                            {p->o_GHM, false, n + 1, n, -1},                       // B_c   inner_product_argument.rs:126
-                            {p->o_GHM, false, 2 * n + 1, n, -1}},                  // B_d = msm(G', r_d) = msm(G|H, r_d o u)   :127
-                3 * n + 1);
+    build_stage(p, p->st4, {{p->o_X + X_B, false, 0, 3, -1},                       // D = B - beta^-1 sum(G) + alpha sum(Hvec)   grand_product_argument.rs:132
+                            {p->o_GHM, false, 3, n, -1},                           // B_c   inner_product_argument.rs:126
+                            {p->o_GHM, false, 3 + n, n, -1}},                      // B_d = msm(G', r_d) = msm(G|H, r_d o u)   :127
+                2 * n + 3);
     build_fold(p, p->f_gp, {{p->o_GHM, 0, p->o_Gp, false, 0, 1}}, n, n);           // G' = u o (G|Hvec)   grand_product_argument.rs:92-102
     p->st_ipa.resize(m); p->f_ipa.resize(m); p->st_sm.resize(m); p->f_sm.resize(m);
     for (size_t k = 0; k < m; k++) {
@@ -398,15 +417,32 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
             gsrc.push_back(tb[i]); gdst.push_back((uint32_t)(bp + p->o_T + ell + i));
             gsrc.push_back(ub[i]); gdst.push_back((uint32_t)(bp + p->o_U + ell + i));
         }
+        {   // constant entries of the X block
+            const std::pair<int, size_t> cx[] = {{X_GSUM, cGsum}, {X_H1, cH}, {X_H2, cH}, {X_GT, cGt}, {X_GU, cGu}, {X_GSUM2, cGsum}, {X_HSUM, cHsum}};
+            for (auto &e : cx) { gsrc.push_back((uint32_t)e.second); gdst.push_back((uint32_t)(bp + p->o_X + e.first)); }
+        }
         if (pr == 0) p->g_count_per_proof = gsrc.size();
         // from the instance staging: [R | S | T | U] of this proof, M in the block behind all proofs
         size_t ib = pr * 4 * ell;
         const size_t dsts[4] = {p->o_R, p->o_S, p->o_T, p->o_U};
         for (int v = 0; v < 4; v++)
             for (size_t i = 0; i < ell; i++) { isrc.push_back((uint32_t)(ib + v * ell + i)); idst.push_back((uint32_t)(bp + dsts[v] + i)); }
-        isrc.push_back((uint32_t)(max_batch * 4 * ell + pr)); idst.push_back((uint32_t)(bp + p->o_GHM + n));  // M behind G|Hvec
+        isrc.push_back((uint32_t)(max_batch * 4 * ell + pr)); idst.push_back((uint32_t)(bp + p->o_GHM + n));  // M behind G|Hvec (unused since stage 2 became short MSMs)
+        isrc.push_back((uint32_t)(max_batch * 4 * ell + pr)); idst.push_back((uint32_t)(bp + p->o_X + X_M));
         if (pr == 0) p->i_count_per_proof = isrc.size();
     }
+    // after stage 1: A, R, S (affine) into the X block; after stage 2: B
+    std::vector<uint32_t> x1s, x1d, x2s, x2d;
+    for (size_t pr = 0; pr < max_batch; pr++) {
+        // stored outputs sit proof-major inside sub-launch 0 of their stage (index pr * K + k, independent of the batch size)
+        size_t bp = p->crs_n + pr * p->PW, r1 = p->reg1 + pr * p->st1.subs[0].K, r2 = p->reg2 + pr * p->st2.subs[0].K;
+        auto k1 = [&](int q) { return (size_t)p->st1.where[q].second; };
+        const std::pair<int, size_t> e1[] = {{X_A, r1 + k1(S1_A)}, {X_R, r1 + k1(S1_R)}, {X_S, r1 + k1(S1_S)}, {X_A2, r1 + k1(S1_A)}};
+        for (auto &e : e1) { x1s.push_back((uint32_t)e.second); x1d.push_back((uint32_t)(bp + p->o_X + e.first)); }
+        x2s.push_back((uint32_t)(r2 + p->st2.where[S2_B].second)); x2d.push_back((uint32_t)(bp + p->o_X + X_B));
+    }
+    p->d_x1src = (uint32_t *)dalloc(x1s.size() * 4); p->d_x1dst = (uint32_t *)dalloc(x1d.size() * 4);
+    p->d_x2src = (uint32_t *)dalloc(x2s.size() * 4); p->d_x2dst = (uint32_t *)dalloc(x2d.size() * 4);
     p->d_gsrc = (uint32_t *)dalloc(gsrc.size() * 4); p->d_gdst = (uint32_t *)dalloc(gdst.size() * 4);
     p->d_isrc = (uint32_t *)dalloc(isrc.size() * 4); p->d_idst = (uint32_t *)dalloc(idst.size() * 4);
     if (!ok) { p->err = "allocation failed"; lane_destroy(p); return CDP_ERR_CUDA; }
@@ -415,6 +451,19 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
     std::vector<uint8_t> zero(96, 0);
     rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 7) * 96);
     rc |= cdp_h2d(ctx, p->d_pts + total_pts * 96, zero.data(), 96);
+    {   // sum(G), sum(Hvec): CRS constants (the reference keeps them as crs.G_sum / crs.H_sum, src/crs.rs:46-47)
+        std::vector<uint8_t> ones(32 * ell, 0), sums(2 * 144), aff(2 * 96);
+        for (size_t i = 0; i < ell; i++) ones[32 * i] = 1;
+        rc |= cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
+        rc |= cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
+        rc |= cdp_normalize_batch(ctx, sums.data(), 2, aff.data());
+        rc |= cdp_h2d(ctx, p->d_pts + cGsum * 96, aff.data(), 2 * 96);
+        rc |= cdp_sync(ctx);
+    }
+    rc |= cdp_h2d(ctx, p->d_x1src, x1s.data(), x1s.size() * 4);
+    rc |= cdp_h2d(ctx, p->d_x1dst, x1d.data(), x1d.size() * 4);
+    rc |= cdp_h2d(ctx, p->d_x2src, x2s.data(), x2s.size() * 4);
+    rc |= cdp_h2d(ctx, p->d_x2dst, x2d.data(), x2d.size() * 4);
     rc |= cdp_h2d(ctx, p->d_gsrc, gsrc.data(), gsrc.size() * 4);
     rc |= cdp_h2d(ctx, p->d_gdst, gdst.data(), gdst.size() * 4);
     rc |= cdp_h2d(ctx, p->d_isrc, isrc.data(), isrc.size() * 4);
@@ -510,24 +559,16 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         for (size_t i = 0; i < n; i++) s.r_sm[i] = rng.fr_rand();               // same_multiscalar_argument.rs:78
         s.a_perm.resize(ell);
         for (size_t i = 0; i < ell; i++) s.a_perm[i] = s.vec_a[s.perm[i]];
-        // stage-1 scalar block (layout fixed in cdp_prover_create)
+        // stage-1 scalar block (layout fixed in lane_create)
         uint8_t *sc = p->h_scal + pr * p->st1.scalars_per_proof * 32;
         size_t o = 0;
         for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.a_perm[i]);                 // A
         put_fr(sc + 32 * (o++), s.a_bl[0]); put_fr(sc + 32 * (o++), s.a_bl[1]);
         memset(sc + 32 * o, 0, 64); o += 2;
         for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.vec_a[i]);                  // R, S
-        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.k * s.vec_a[i]);            // cm_T
-        put_fr(sc + 32 * (o++), s.r_t);
-        memcpy(sc + 32 * o, sc + 32 * (o - ell - 1), 32 * ell); o += ell;                      // cm_U
-        put_fr(sc + 32 * (o++), s.r_u);
-        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * (o++), s.r_k * s.vec_a[i]);          // cm_A
-        put_fr(sc + 32 * (o++), s.r_a);
-        memcpy(sc + 32 * o, sc + 32 * (o - ell - 1), 32 * ell); o += ell;                      // cm_B
-        put_fr(sc + 32 * (o++), s.r_b);
-        memcpy(sc + 32 * o, sc, 32 * (ell + 2)); o += ell + 2;                                 // A' : a_perm | a_bl | r_t | r_u
-        put_fr(sc + 32 * (o++), s.r_t); put_fr(sc + 32 * (o++), s.r_u);
         for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (o++), s.r_sm[i]);                     // B_a, B_t, B_u
+        put_fr(sc + 32 * (o++), s.r_t); put_fr(sc + 32 * (o++), s.r_u);                        // cm_T.T_1, cm_U.T_1
+        put_fr(sc + 32 * (o++), s.r_a); put_fr(sc + 32 * (o++), s.r_b);                        // cm_A.T_1, cm_B.T_1
         s.ipa_rounds.resize(m * 4 * 48);
         s.sm_rounds.resize(m * 6 * 48);
     });
@@ -538,7 +579,8 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     t0 = now_ms();
     parallel_for(T, B, [&](size_t pr) {
         ProofState &s = p->ps[pr];
-        for (int q = 0; q < 15; q++) memcpy(s.pts1[q], stage_out(p, p->st1, B, pr, q), 48);
+        static const int map1[S1_COUNT] = {O_A, O_R, O_S, O_BA, O_BT, O_BU, O_T1, O_U1, O_A1, O_B1};
+        for (int q = 0; q < S1_COUNT; q++) memcpy(s.pts1[map1[q]], stage_out(p, p->st1, B, pr, q), 48);
         s.tr->append_point("same_perm_step1", s.pts1[O_A]);
         s.tr->append_point("same_perm_step1", s.M_comp);
         s.tr->append_fr_vec("same_perm_step1", s.vec_a.data(), ell);
@@ -552,20 +594,26 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         }
         const Fr r_a_prime[4] = {s.a_bl[0], s.a_bl[1], Fr::zero(), Fr::zero()};
         for (int i = 0; i < 4; i++) s.b_bl[i] = r_a_prime[i] + s.alpha_sp * s.m_bl[i];
-        // B = A + alpha M + beta sum(G) = msm(G | Hvec | M, (a_perm + beta) | r_a' | alpha)
+        // stage-2 scalars: B = 1 A + alpha M + beta sum(G) | T_2 = k R + r_t H | A_2 = r_k R + r_a H | U_2 | B_2 | A' = 1 A + r_t G_t + r_u G_u
         uint8_t *sc = p->h_scal + pr * p->st2.scalars_per_proof * 32;
-        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * i, s.a_perm[i] + s.beta_sp);
-        for (int i = 0; i < 4; i++) put_fr(sc + 32 * (ell + i), r_a_prime[i]);
-        put_fr(sc + 32 * n, s.alpha_sp);
+        const Fr one = Fr::one();
+        const Fr v2[14] = {one, s.alpha_sp, s.beta_sp, s.k, s.r_t, s.r_k, s.r_a, s.k, s.r_u, s.r_k, s.r_b, one, s.r_t, s.r_u};
+        for (int i = 0; i < 14; i++) put_fr(sc + 32 * i, v2[i]);
     });
     t_host += now_ms() - t0;
+    PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_x1src, p->d_x1dst, B * 4));  // A, R, S (affine, from stage 1) -> X block
     if (int rc = run_msm_stage(p, p->st2, B, t_wait, t_copy)) return rc;
 
     // ---- gprod step 1-2 (grand_product_argument.rs:63-83) -> stage 3: C
     t0 = now_ms();
     parallel_for(T, B, [&](size_t pr) {
         ProofState &s = p->ps[pr];
-        memcpy(s.B, stage_out(p, p->st2, B, pr, 0), 48);
+        memcpy(s.B, stage_out(p, p->st2, B, pr, S2_B), 48);
+        memcpy(s.pts1[O_T2], stage_out(p, p->st2, B, pr, S2_T2), 48);
+        memcpy(s.pts1[O_A2], stage_out(p, p->st2, B, pr, S2_A2), 48);
+        memcpy(s.pts1[O_U2], stage_out(p, p->st2, B, pr, S2_U2), 48);
+        memcpy(s.pts1[O_B2], stage_out(p, p->st2, B, pr, S2_B2), 48);
+        memcpy(s.pts1[O_AP], stage_out(p, p->st2, B, pr, S2_AP), 48);
         s.tr->append_point("gprod_step1", s.B);
         s.tr->append_fr("gprod_step1", s.gprod_result);
         s.alpha_g = s.tr->challenge("gprod_alpha");
@@ -617,19 +665,16 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             z[n - 1] = last_z;
         }
         uint8_t *sc = p->h_scal + pr * p->st4.scalars_per_proof * 32;
-        const Fr r_a_prime[4] = {s.a_bl[0], s.a_bl[1], Fr::zero(), Fr::zero()};
-        // D = B - beta^-1 sum(G) + alpha_g sum(Hvec) = msm(G | Hvec | M, (a_perm + beta_sp - beta^-1) | (r_a' + alpha_g) | alpha_sp)
-        Fr shift = s.beta_sp - beta_inv;
-        for (size_t i = 0; i < ell; i++) put_fr(sc + 32 * i, s.a_perm[i] + shift);
-        for (int i = 0; i < 4; i++) put_fr(sc + 32 * (ell + i), r_a_prime[i] + s.alpha_g);
-        put_fr(sc + 32 * n, s.alpha_sp);
-        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (n + 1 + i), s.r_c[i]);                // B_c = msm(G|Hvec, r_c)
-        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (2 * n + 1 + i), s.r_d[i] * s.u[i]);   // B_d = msm(G', r_d)
+        // D = 1 B - beta^-1 sum(G) + alpha_g sum(Hvec)   (the reference's verifier uses the same identity, grand_product_argument.rs:223)
+        put_fr(sc, Fr::one()); put_fr(sc + 32, beta_inv.neg()); put_fr(sc + 64, s.alpha_g);
+        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + i), s.r_c[i]);                    // B_c = msm(G|Hvec, r_c)
+        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + n + i), s.r_d[i] * s.u[i]);       // B_d = msm(G', r_d)
         uint8_t *fs = p->h_fscal + pr * n * 32;                                                // G'_i = u_i (G|Hvec)_i
         for (size_t i = 0; i < n; i++) put_fr(fs + 32 * i, s.u[i]);
     });
     t_host += now_ms() - t0;
     t0 = now_ms();
+    PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_x2src, p->d_x2dst, B));  // B (affine, from stage 2) -> X block
     if (int rc = run_fold_stage(p, p->f_gp, B)) return rc;
     t_copy += now_ms() - t0;
     if (int rc = run_msm_stage(p, p->st4, B, t_wait, t_copy)) return rc;
@@ -822,7 +867,7 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     *out = nullptr;
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (host_threads <= 0) host_threads = hw;
-    if (lanes <= 0) lanes = max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
+    if (lanes <= 0) lanes = max_batch >= 512 ? 8 : max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
     lanes = (int)std::min<size_t>((size_t)lanes, max_batch);
     cdp_prover *p = new cdp_prover();
     p->ell = ell;
