@@ -16,6 +16,6 @@ There is no CPU fallback: constructing an ``Engine`` without the built extension
 device raises.
 """
 from .engine import Engine, CdpError, lib_path, load_library  # noqa: F401
-from .prover import BatchProver, load_prover_library  # noqa: F401
+from .prover import BatchProver, BatchVerifier, load_prover_library  # noqa: F401
 
-__all__ = ["Engine", "CdpError", "lib_path", "load_library", "BatchProver", "load_prover_library"]
+__all__ = ["Engine", "CdpError", "lib_path", "load_library", "BatchProver", "BatchVerifier", "load_prover_library"]

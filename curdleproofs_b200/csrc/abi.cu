@@ -317,6 +317,33 @@ extern "C" int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const
     return CDP_OK;
 }
 
+extern "C" int cdp_decompress_dev(cdp_ctx *ctx, const uint8_t *d_compressed, const uint32_t *d_dst_index, size_t n, uint8_t *d_out_affine,
+                                  uint8_t *d_status) {
+    if (!ctx || (n && (!d_compressed || !d_out_affine || !d_status))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_decompress_dev: null argument");
+    if (n == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, n);
+    CUDA_TRY(ctx, launch_decompress(ctx->stream, d_compressed, d_dst_index, reinterpret_cast<uint32_t *>(d_out_affine), d_status, (uint32_t)n));
+    return CDP_OK;
+}
+
+extern "C" int cdp_decompress_batch(cdp_ctx *ctx, const uint8_t *compressed, size_t n, uint8_t *out_affine, uint8_t *status) {
+    if (!ctx || (n && (!compressed || !out_affine || !status))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_decompress_batch: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) return CDP_OK;
+    TRY(ensure_dev(ctx, ctx->d_aux, n * CDP_COMPRESSED_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_out, n * CDP_AFFINE_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_segs, n));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_aux.ptr, compressed, n * CDP_COMPRESSED_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(cdp_decompress_dev(ctx, (const uint8_t *)ctx->d_aux.ptr, nullptr, n, (uint8_t *)ctx->d_out.ptr, (uint8_t *)ctx->d_segs.ptr));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_affine, ctx->d_out.ptr, n * CDP_AFFINE_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status, ctx->d_segs.ptr, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int bad = 0;
+    for (size_t i = 0; i < n; i++) bad |= status[i];
+    return bad ? fail(ctx, CDP_ERR_NOT_ON_CURVE, "cdp_decompress_batch: at least one encoding is invalid (see status[])") : CDP_OK;
+}
+
 extern "C" int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed) {
     if (!ctx) return CDP_ERR_INVALID_ARG;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

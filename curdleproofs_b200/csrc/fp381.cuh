@@ -266,8 +266,8 @@ __device__ __forceinline__ void fp_to_mont(fp &r, const fp &a) {
     fp_mul(r, a, r2);
 }
 
-// a^(p-2): fixed exponent, uniform control flow across the warp (4-bit fixed window).
-static __device__ __noinline__ void fp_inv(fp &r, const fp &a) {
+// a^e for a fixed 384-bit exponent held in constant memory: uniform control flow across the warp (4-bit fixed window).
+static __device__ __noinline__ void fp_pow_fixed(fp &r, const fp &a, const uint32_t *e) {
     fp tbl[16];  // tbl[k] = a^k ; lives in local memory -- indexed dynamically, 15 muls to build
     fp_set_one(tbl[0]);
     tbl[1] = a;
@@ -278,7 +278,7 @@ static __device__ __noinline__ void fp_inv(fp &r, const fp &a) {
     bool started = false;
 #pragma unroll 1
     for (int w = 95; w >= 0; w--) {  // 96 nibbles of the 384-bit exponent
-        uint32_t nib = (FP_P_MINUS_2[w >> 3] >> ((w & 7) * 4)) & 0xF;
+        uint32_t nib = (e[w >> 3] >> ((w & 7) * 4)) & 0xF;
         if (started) {
             fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc);
         }
@@ -288,6 +288,16 @@ static __device__ __noinline__ void fp_inv(fp &r, const fp &a) {
         }
     }
     r = acc;
+}
+// a^(p-2) (Fermat inverse; 0 -> 0)
+__device__ __forceinline__ void fp_inv(fp &r, const fp &a) { fp_pow_fixed(r, a, FP_P_MINUS_2); }
+// square root for p = 3 mod 4: candidate a^((p+1)/4); returns false when a is not a square
+__device__ __forceinline__ bool fp_sqrt(fp &r, const fp &a) {
+    fp s, s2;
+    fp_pow_fixed(s, a, FP_P_PLUS_1_DIV_4);
+    fp_sqr(s2, s);
+    r = s;
+    return fp_eq(s2, a);
 }
 
 // true when the canonical value of y is > (p-1)/2, i.e. y > -y : the "sign" bit of the ZCash encoding

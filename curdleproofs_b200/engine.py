@@ -48,6 +48,8 @@ _SIGS = {
     "cdp_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(c_uint64)]),
     "cdp_smul_jobs_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
     "cdp_gather_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "cdp_decompress_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "cdp_decompress_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
@@ -195,6 +197,18 @@ class Engine:
         out = (ctypes.c_uint8 * max(1, n * COMPRESSED_BYTES))()
         self._check(self._lib.cdp_compress_batch(self._h, _buf(jac) if n else None, n, out), "cdp_compress_batch")
         return bytes(out)[:n * COMPRESSED_BYTES]
+
+    def decompress_batch(self, comp: bytes):
+        """48-byte encodings -> (affine bytes, status list); status 0 ok / 1 malformed / 2 not on curve / 3 not in subgroup."""
+        n = len(comp) // COMPRESSED_BYTES
+        if len(comp) % COMPRESSED_BYTES:
+            raise ValueError("malformed input length")
+        out = (ctypes.c_uint8 * max(1, n * AFFINE_BYTES))()
+        st = (ctypes.c_uint8 * max(1, n))()
+        rc = self._lib.cdp_decompress_batch(self._h, _buf(comp) if n else None, n, out, st)
+        if rc not in (0, 4):
+            self._check(rc, "cdp_decompress_batch")
+        return bytes(out)[:n * AFFINE_BYTES], list(st)[:n]
 
     PROFILE_KINDS = ("msm_buckets", "msm_combine", "smul", "normalize", "other")
 

@@ -147,3 +147,61 @@ class BatchProver:
         t = (c_double * 4)()
         self._lib.cdp_prover_last_timing(self._h, t)
         return {"total_ms": t[0], "host_ms": t[1], "gpu_wait_ms": t[2], "copy_issue_ms": t[3]}
+
+
+class _VerifyInputs(ctypes.Structure):
+    _fields_ = [("vec_R", c_void_p), ("vec_S", c_void_p), ("vec_T", c_void_p), ("vec_U", c_void_p), ("M", c_void_p), ("proofs", c_void_p),
+                ("rng_seed", c_void_p)]
+
+
+class BatchVerifier:
+    """`CurdleproofsProof::deserialize` + `verify` (/root/reference/src/curdleproofs.rs:197-323) for a batch of proofs on one GPU.
+    Results: 1 = Ok(()), 0 = Err(VerificationError), 2 = proof does not deserialise."""
+
+    def __init__(self, engine: Engine, ell: int, crs_points: bytes, max_batch: int, host_threads: int = 0, lanes: int = 0):
+        self._lib = lib = load_prover_library()
+        lib.cdp_verifier_create.restype = c_int
+        lib.cdp_verifier_create.argtypes = [POINTER(c_void_p), c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int]
+        lib.cdp_verifier_destroy.argtypes = [c_void_p]
+        lib.cdp_verifier_last_error.restype = c_char_p
+        lib.cdp_verifier_last_error.argtypes = [c_void_p]
+        lib.cdp_verify_batch.restype = c_int
+        lib.cdp_verify_batch.argtypes = [c_void_p, c_size_t, POINTER(_VerifyInputs), c_void_p]
+        self.engine, self.ell, self.max_batch = engine, ell, max_batch
+        self.proof_size = int(lib.cdp_proof_size(ell))
+        if len(crs_points) != (ell + 7) * AFFINE_BYTES:
+            raise ValueError("crs_points must hold ell + 7 affine points")
+        h = c_void_p()
+        rc = lib.cdp_verifier_create(ctypes.byref(h), engine.handle, ell, _arr(crs_points), max_batch, host_threads, lanes)
+        if rc != 0:
+            raise CdpError(f"cdp_verifier_create failed (code {rc})")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cdp_verifier_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def verify_batch(self, instances, proofs, rng_seeds=None) -> list[int]:
+        B = len(instances)
+        cat = lambda key: b"".join(i[key] for i in instances)  # noqa: E731
+        R, S, T, U, M = (_arr(cat(k)) for k in ("R", "S", "T", "U", "M"))
+        P = _arr(b"".join(proofs))
+        seeds = (c_uint64 * B)(*rng_seeds) if rng_seeds is not None else None
+        return list(self.verify_raw(B, R, S, T, U, M, P, seeds))
+
+    def verify_raw(self, B, R, S, T, U, M, proofs, seeds=None, out=None):
+        vp = lambda x: ctypes.cast(x, c_void_p) if x is not None else None  # noqa: E731
+        inp = _VerifyInputs(vp(R), vp(S), vp(T), vp(U), vp(M), vp(proofs), vp(seeds))
+        if out is None:
+            out = (ctypes.c_uint8 * B)()
+        rc = self._lib.cdp_verify_batch(self._h, B, ctypes.byref(inp), out)
+        if rc != 0:
+            raise CdpError(f"cdp_verify_batch failed (code {rc}): {self._lib.cdp_verifier_last_error(self._h).decode()}")
+        return out

@@ -93,6 +93,12 @@ int cdp_normalize_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t 
 /* Jacobian points -> 48-byte compressed encodings (`serialize_compressed`, src/transcript.rs:29-33, src/util.rs:125-133) */
 int cdp_compress_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n, uint8_t *out_compressed);
 
+/* 48-byte encodings -> affine points (`G1Affine::deserialize_compressed`, src/whisk.rs:313-315; every point of
+ * `CurdleproofsProof::deserialize`, src/curdleproofs.rs:312-323) with ark-serialize's validation: canonical x, on the
+ * curve, in the prime-order subgroup.  status[i]: 0 ok, 1 malformed, 2 not on the curve, 3 not in the subgroup (the
+ * output is then the all-zero point).  Returns CDP_ERR_NOT_ON_CURVE when any status is non-zero. */
+int cdp_decompress_batch(cdp_ctx *ctx, const uint8_t *compressed, size_t n, uint8_t *out_affine, uint8_t *status);
+
 /* ------------------------------------------------------------------ device-resident entry points
  * Same operations on buffers that already live in HBM (bases stay resident across the rounds of a proof batch).
  * All `d_*` arguments are device pointers on the context's device; work is queued on the context's stream and is
@@ -136,6 +142,10 @@ int cdp_smul_jobs_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_scalars, co
 
 /* d_pts[d_dst_idx[i]] = d_src[d_src_idx[i]] for i < n (96-byte points): assembles per-proof working vectors. */
 int cdp_gather_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_src, const uint32_t *d_src_idx, const uint32_t *d_dst_idx, size_t n);
+
+/* Device-resident cdp_decompress_batch; point i is written to d_out_affine[d_dst_index ? d_dst_index[i] : i]. */
+int cdp_decompress_dev(cdp_ctx *ctx, const uint8_t *d_compressed, const uint32_t *d_dst_index, size_t n, uint8_t *d_out_affine,
+                       uint8_t *d_status);
 
 /* Affine points (d_pts[d_index[i]], or d_pts[i] when d_index is NULL) -> 48-byte encodings (`serialize_compressed` of the
  * instance vectors, src/curdleproofs.rs:81). */

@@ -65,6 +65,27 @@ int cdp_prove_batch(cdp_prover *p, size_t batch, const cdp_prove_inputs *in, uin
  * [2] waiting on the GPU (stream synchronisation), [3] H2D/D2H staging issue time. */
 void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]);
 
+/* ------------------------------------------------------------------ batched verifier
+ * `CurdleproofsProof::deserialize` + `verify` (src/curdleproofs.rs:197-323) for `batch` independent proofs.
+ * Proof points are decompressed and subgroup-checked on the GPU; the eight accumulated checks of a proof become one MSM
+ * over [CRS | R | S | T | U | M | proof points] compared with the identity (the reference's MsmAccumulator, without the
+ * HashMap); SameScalar's four point equalities are checked exactly. */
+typedef struct cdp_verifier cdp_verifier;
+int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads, int lanes);
+void cdp_verifier_destroy(cdp_verifier *v);
+const char *cdp_verifier_last_error(const cdp_verifier *v);
+typedef struct {
+    const uint8_t *vec_R;     /* batch * ell affine */
+    const uint8_t *vec_S;
+    const uint8_t *vec_T;
+    const uint8_t *vec_U;
+    const uint8_t *M;         /* batch jacobian */
+    const uint8_t *proofs;    /* batch * cdp_proof_size(ell) bytes, `CurdleproofsProof::serialize` format */
+    const uint64_t *rng_seed; /* batch, or NULL: seeds the random factors of the accumulated checks (msm_accumulator.rs:44) */
+} cdp_verify_inputs;
+/* result[i]: 1 = Ok(()), 0 = Err(VerificationError), 2 = the proof does not deserialise (bad encoding / not in the subgroup) */
+int cdp_verify_batch(cdp_verifier *v, size_t batch, const cdp_verify_inputs *in, uint8_t *result);
+
 /* Host<->device bytes moved by the last cdp_prove_batch call: [0] host-to-device, [1] device-to-host. */
 void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]);
 
