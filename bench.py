@@ -175,7 +175,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from curdleproofs_b200 import BatchProver, Engine
+    from curdleproofs_b200 import BatchProver, BatchVerifier, Engine
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -247,6 +247,31 @@ def main():
     ms_e2e, _ = timed(False, args.steps)
     traffic = bp.last_traffic()
     proof0 = bytes(out[:bp.proof_size])
+    # ---- secondary metric: verifies/s on the proofs just produced (CurdleproofsProof::deserialize + verify through cdp_verify_batch)
+    bp.close()
+    VB = min(B, 512)
+    bv = BatchVerifier(eng, ell, crs, max_batch=VB)
+    vout = (ctypes.c_uint8 * VB)()
+
+    def vstep():
+        bv.verify_raw(VB, R, S, T, U, M, out, None, out=vout)
+
+    vstep()
+    barrier()
+    ve0, ve1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ve0.record(stream)
+    for _ in range(args.steps):
+        vstep()
+    with torch.cuda.stream(stream):
+        ve1.record(stream)
+    barrier()
+    ms_ver = ve0.elapsed_time(ve1)
+    if world > 1:
+        t = torch.tensor([ms_ver], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_ver = float(t.item())
+    all_ok = all(x == 1 for x in vout)
 
     if rank != 0:
         return
@@ -284,6 +309,9 @@ def main():
             "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": traffic["h2d_bytes"], "d2h_bytes_per_step": traffic["d2h_bytes"],
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+            "verify": {"metric": f"shuffle_verifies_per_sec_ell{ell}", "value": world * VB * args.steps / (ms_ver * 1e-3), "unit": "verifies/s",
+                       "batch_per_gpu": VB, "ms_per_step": ms_ver / args.steps, "all_accepted": all_ok,
+                       "note": "host buffers in (instance + serialised proofs), verdicts out; README.md:49 reference: 35 ms/verify on i7-8550U"},
             "host_breakdown_last_step_ms": timing}
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample, and a parity check of proof 0
     if world == 1 and not args.no_cpu_baseline:
@@ -298,6 +326,9 @@ def main():
         count = 2 * cores
         t = o.L.oracle_time_prove(ell, *a, pc, arr(inst["k"]), arr(inst["m_blinders"]), count, cores, last)
         want0 = o.prove(inst, rng_seed=int(seeds[0]), threads=cores)
+        allok = ctypes.c_int(0)
+        tv = o.L.oracle_time_verify(ell, *a, arr(want0), 4 * cores, cores, ctypes.byref(allok))
+        line["verify"]["cpu_baseline"] = {"value": 4 * cores / tv, "unit": "verifies/s", "cores": cores, "kind": "port", "all_accepted": bool(allok.value)}
         line["cpu_baseline"] = {"value": count / t, "unit": "proofs/s", "cores": cores, "kind": "port",
                                 "sample": f"{count} ell={ell} proofs, one per host thread ({cores} threads), oracle C port",
                                 "parity_proof0_bit_exact": bool(want0 == proof0), "oracle_verifies_gpu_proof": o.verify(inst, proof0) == 1}
