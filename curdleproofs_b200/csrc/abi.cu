@@ -33,6 +33,7 @@ struct cdp_ctx {
     uint64_t launches = 0;
     // grow-on-demand device scratch
     scratch_t d_pts, d_scalars, d_segs, d_win, d_jac, d_aux, d_out;
+    scratch_t d_big;  // large-MSM workspace (keys, values, offsets, buckets, weights, sort temp)
     // pinned host staging
     scratch_t h_stage;
     int sm_count = 148;
@@ -160,7 +161,7 @@ int normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_aff, 
     const uint32_t *j = reinterpret_cast<const uint32_t *>(d_jac);
     uint32_t *a = reinterpret_cast<uint32_t *>(d_aff);
     // enough threads to fill the machine first, then amortise the inversion over a chunk
-    size_t fill = (size_t)ctx->sm_count * 1024;
+    size_t fill = (size_t)ctx->sm_count * 256;
     int chunk = n >= 8 * fill ? 8 : n >= 2 * fill ? 2 : 1;
     launch_scope ls(ctx, CDP_PROFILE_NORMALIZE, n);
     CUDA_TRY(ctx, launch_normalize(ctx->stream, chunk, j, a, d_comp, (uint32_t)n, jobs, elems_per_job));
@@ -216,7 +217,7 @@ extern "C" void cdp_ctx_destroy(cdp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (scratch_t *s : {&ctx->d_pts, &ctx->d_scalars, &ctx->d_segs, &ctx->d_win, &ctx->d_jac, &ctx->d_aux, &ctx->d_out})
+    for (scratch_t *s : {&ctx->d_pts, &ctx->d_scalars, &ctx->d_segs, &ctx->d_win, &ctx->d_jac, &ctx->d_aux, &ctx->d_out, &ctx->d_big})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
     prof_drain(ctx);
@@ -275,14 +276,21 @@ extern "C" int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t byte
     return CDP_OK;
 }
 
+static int msm_batch_dev_c(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs, size_t count,
+                           size_t max_n, size_t total_pairs, uint8_t *d_out_jac, int force_c);
 extern "C" int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs,
                                  size_t count, size_t max_n, size_t total_pairs, uint8_t *d_out_jac) {
+    return msm_batch_dev_c(ctx, d_affine_pts, d_scalars, d_segs, count, max_n, total_pairs, d_out_jac, 0);
+}
+static int msm_batch_dev_c(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs, size_t count,
+                           size_t max_n, size_t total_pairs, uint8_t *d_out_jac, int force_c) {
     if (!ctx || !d_out_jac) return CDP_ERR_INVALID_ARG;
     if (count == 0) return CDP_OK;
     if (max_n > SMALL_MSM_MAX_N) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm_batch_dev: segment longer than 2048 points; split it");
     if (max_n == 0) max_n = 1;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     msm_cfg g = pick_cfg(max_n);
+    if (force_c) { g.c = force_c; g.nwin = msm_nwin_for(force_c); }
     TRY(ensure_dev(ctx, ctx->d_win, count * g.nwin * CDP_JACOBIAN_BYTES));
     static_assert(sizeof(cdp_msm_seg) == sizeof(msm_seg_t), "segment layout");
     TRY(msm_buckets_dev(ctx, g, d_affine_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(d_segs), count, max_n,
@@ -381,6 +389,88 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
     return combine_dev(ctx, g, win_final, 1, reinterpret_cast<uint32_t *>(d_out_jac));
 }
 
+// ---- large Pippenger (k_bigmsm.cu) ---------------------------------------------------------------------------
+constexpr size_t BIG_MSM_MIN_N = size_t(1) << 13;  // CDP_BIG_MIN_LOG2 overrides (tuning)
+static int big_c_for(size_t n) {
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("CDP_BIG_C"); forced = e ? atoi(e) : 0; }
+    if (forced >= 12 && forced <= 16) return forced;
+    return n < (size_t(1) << 15) ? 12 : n < (size_t(1) << 17) ? 13 : n < (size_t(1) << 19) ? 14 : n < (size_t(1) << 20) ? 15 : 16;
+}
+static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
+    const int c = big_c_for(n), nwin = (130 + c - 1) / c;
+    const uint32_t nb = 1u << (c - 1), n2 = (uint32_t)(2 * n);
+    const int top_bits = 128 - c * (nwin - 1);
+    const uint32_t nbt = top_bits > 0 ? (1u << top_bits) : 1u;   // upper bound of the top window's digits (incl. the carry)
+    const uint32_t sp_top = nb / nbt;                             // threads per top-window bucket
+    const size_t slots = (size_t)nwin * nb, items = (size_t)nwin * n2;
+    const size_t sort_tmp = big_msm_sort_temp_bytes(n2, nwin, c);
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    // workspace: keys/values (double-buffered for the sort), bucket offsets, buckets, two ping-pong (A, Bv) level buffers, sort temp
+    const size_t lvl = slots / 2 + nwin;  // first level output is at most slots / 2 nodes
+    size_t o_keys = 0, o_vals = o_keys + al(items * 4), o_keys2 = o_vals + al(items * 4), o_vals2 = o_keys2 + al(items * 4),
+           o_start = o_vals2 + al(items * 4), o_bjac = o_start + al((size_t)nwin * (nb + 1) * 4), o_top = o_bjac + al(slots * 144),
+           o_A0 = o_top + al((size_t)nb * 144), o_B0 = o_A0 + al(lvl * 144), o_A1 = o_B0 + al(lvl * 144), o_B1 = o_A1 + al(lvl * 144),
+           o_tmp = o_B1 + al(lvl * 144), total = o_tmp + al(sort_tmp);
+    TRY(ensure_dev(ctx, ctx->d_big, total));
+    uint8_t *ws = (uint8_t *)ctx->d_big.ptr;
+    uint32_t *keys = (uint32_t *)(ws + o_keys), *vals = (uint32_t *)(ws + o_vals), *keys2 = (uint32_t *)(ws + o_keys2), *vals2 = (uint32_t *)(ws + o_vals2);
+    uint32_t *start = (uint32_t *)(ws + o_start), *bjac = (uint32_t *)(ws + o_bjac);
+    const uint32_t *P = reinterpret_cast<const uint32_t *>(d_pts), *S = reinterpret_cast<const uint32_t *>(d_scalars);
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, n); CUDA_TRY(ctx, launch_big_digits(ctx->stream, P, S, (uint32_t)n, c, nwin, keys, vals)); }
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_sort(ctx->stream, ws + o_tmp, sort_tmp, keys, keys2, vals, vals2, n2, nwin, c, nullptr)); }
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_offsets(ctx->stream, keys2, n2, nwin, nb, c, start)); }
+    { launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, (uint64_t)n); CUDA_TRY(ctx, launch_big_accumulate(ctx->stream, P, vals2, start, n2, nwin, nb, sp_top, 1, bjac)); }
+    // top window: fold the sp_top partial sums of each bucket (two steps when a bucket has many), back into the window's slot array
+    {
+        uint32_t *top_slots = bjac + 36 * (size_t)(nwin - 1) * nb, *tmp = (uint32_t *)(ws + o_top);
+        uint32_t nw = sp_top > 1024 ? 32u : 1u;
+        if (nw > 1) {
+            launch_scope ls(ctx, CDP_PROFILE_OTHER, nbt * nw);
+            CUDA_TRY(ctx, launch_big_fold_top(ctx->stream, top_slots, nbt, sp_top, nw, 0, tmp));
+            CUDA_TRY(ctx, cudaMemcpyAsync(top_slots, tmp, (size_t)nbt * nw * 144, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        launch_scope ls(ctx, CDP_PROFILE_OTHER, nb);
+        CUDA_TRY(ctx, launch_big_fold_top(ctx->stream, top_slots, nbt, nw > 1 ? nw : sp_top, 1, nb, tmp));
+        CUDA_TRY(ctx, cudaMemcpyAsync(top_slots, tmp, (size_t)nb * 144, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    // hierarchical reduction: sum_b (b+1) B_b = Bv_root + A_root per window
+    const uint32_t *Ain = bjac, *Bin = nullptr;
+    uint32_t *Aout = (uint32_t *)(ws + o_A0), *Bout = (uint32_t *)(ws + o_B0);
+    uint32_t len = nb;
+    int shift = 0, flip = 0;
+    while (len > 1) {
+        uint32_t g = std::min<uint32_t>(16, len);
+        uint32_t n_out = (uint32_t)((size_t)nwin * (len / g));
+        launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, n_out);
+        CUDA_TRY(ctx, launch_big_reduce_level(ctx->stream, Ain, Bin, n_out, g, shift, Aout, Bout));
+        Ain = Aout; Bin = Bout;
+        flip ^= 1;
+        Aout = (uint32_t *)(ws + (flip ? o_A1 : o_A0)); Bout = (uint32_t *)(ws + (flip ? o_B1 : o_B0));
+        len /= g;
+        while (g > 1) { shift++; g >>= 1; }
+    }
+    { launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, nwin); CUDA_TRY(ctx, launch_big_horner(ctx->stream, Ain, Bin, nwin, c, reinterpret_cast<uint32_t *>(d_out_jac))); }
+    return CDP_OK;
+}
+
+extern "C" int cdp_sum_jacobian_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t count, uint8_t *d_out_jac) {
+    if (!ctx || !d_jac_in || !d_out_jac || count == 0) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_sum_jacobian_dev: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, count);
+    CUDA_TRY(ctx, launch_sum_groups(ctx->stream, reinterpret_cast<const uint32_t *>(d_jac_in), reinterpret_cast<uint32_t *>(d_out_jac), 1,
+                                    (uint32_t)count, 1));
+    return CDP_OK;
+}
+
+extern "C" int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
+    if (!ctx || !d_out_jac || (n && (!d_affine_pts || !d_scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: null argument");
+    if (n == 0 || n >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: n out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n >= BIG_MSM_MIN_N) return msm_big_resident(ctx, d_affine_pts, d_scalars, n, d_out_jac);
+    return msm_single_resident(ctx, d_affine_pts, d_scalars, n, d_out_jac);
+}
+
 extern "C" int cdp_msm(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *scalars, size_t n, uint8_t out_jac[CDP_JACOBIAN_BYTES]) {
     if (!ctx || !out_jac || (n && (!affine_pts || !scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm: null argument");
     if (n >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm: n too large");
@@ -394,7 +484,8 @@ extern "C" int cdp_msm(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *s
     TRY(ensure_dev(ctx, ctx->d_out, CDP_JACOBIAN_BYTES));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, affine_pts, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-    TRY(msm_single_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
+    if (n >= BIG_MSM_MIN_N) TRY(msm_big_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
+    else TRY(msm_single_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_jac, ctx->d_out.ptr, CDP_JACOBIAN_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return CDP_OK;

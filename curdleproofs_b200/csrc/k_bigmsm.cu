@@ -1,0 +1,297 @@
+// Large Pippenger MSM (n >= 2^13): the standalone sweep of BASELINE.json config 5 and any accumulated-verify MSM that is
+// merged across a batch.  `util::msm` semantics (/root/reference/src/util.rs:19-22): out = sum_i s_i * P_i.
+//
+//   k_big_digits     one thread per pair: GLV split (2n half-width points), signed radix-2^c recoding; writes one
+//                    (bucket key, point id | sign) pair per (window, half-point) -- coalesced 128-bit scalar loads, coalesced stores
+//   one cub::DeviceRadixSort over (window | bucket) keys groups the point ids of each bucket (every window keeps exactly 2n items,
+//                    so window w is the slice [w * 2n, (w+1) * 2n) of the sorted array)
+//   k_big_offsets    bucket boundaries from the sorted keys
+//   k_big_accumulate one thread per (window, bucket): mixed additions over the bucket's points (gathered 96-byte loads, the
+//                    base array is L2-resident up to ~2^20 points)
+//   bucket reduction: sum_b (b+1) B_b per window.  The buckets are normalised to affine and handed to the batched small-MSM
+//                    kernel with the constant weights 1..2^(c-1) as (15/16-bit) scalars -- a segmented weighted sum -- followed by
+//   k_big_final      per-window chunk sums + Horner over the windows.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "launch.h"
+#include "msm_common.cuh"
+
+namespace cdp {
+
+__global__ void __launch_bounds__(256) k_big_digits(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars, uint32_t n, int c,
+                                                    int nwin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t k[8];
+    const uint4 *sp = reinterpret_cast<const uint4 *>(scalars + 8 * (size_t)j);
+    uint4 a = sp[0], b = sp[1];
+    k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
+    const uint4 *pp = reinterpret_cast<const uint4 *>(pts + 24 * (size_t)j);
+    uint32_t nz = 0;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        uint4 v = pp[q];
+        nz |= v.x | v.y | v.z | v.w;
+    }
+    glv_t g;
+    glv_split(g, k);
+    if (nz == 0) {  // infinity base contributes nothing
+#pragma unroll
+        for (int q = 0; q < 4; q++) g.k1[q] = g.k2[q] = 0;
+    }
+    const uint32_t nb = 1u << (c - 1), n2 = 2 * n;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t kk[5] = {half ? g.k2[0] : g.k1[0], half ? g.k2[1] : g.k1[1], half ? g.k2[2] : g.k1[2], half ? g.k2[3] : g.k1[3], 0};
+        uint32_t carry = 0;
+        const uint32_t id = 2 * j + half;
+        for (int w = 0; w < nwin; w++) {
+            int bit = w * c, li = bit >> 5, sh = bit & 31;
+            uint32_t v = 0;
+            if (li < 4) {
+                v = kk[li] >> sh;
+                if (sh + c > 32) v |= kk[li + 1] << (32 - sh);
+            }
+            v = (v & ((1u << c) - 1)) + carry;
+            carry = (v + nb) >> c;
+            int d = (int)v - (int)(carry << c);
+            uint32_t ad = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            // key = window | bucket; bucket nb = "digit zero", sorted behind every real bucket of its window
+            keys[(size_t)w * n2 + id] = ((uint32_t)w << c) | (ad ? ad - 1 : nb);
+            vals[(size_t)w * n2 + id] = id | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// start[w][b] = first position (inside window w's sorted segment) whose key is >= b, for b = 0..nb (inclusive)
+__global__ void __launch_bounds__(256) k_big_offsets(const uint32_t *__restrict__ keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c,
+                                                     uint32_t *__restrict__ start) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nwin * n2) return;
+    uint32_t w = (uint32_t)(t / n2), i = (uint32_t)(t % n2);
+    const uint32_t mask = (1u << c) - 1;
+    uint32_t key = keys_sorted[t] & mask;
+    uint32_t prev = i ? (keys_sorted[t - 1] & mask) : 0xFFFFFFFFu;
+    uint32_t *st = start + (size_t)w * (nb + 1);
+    if (i == 0) {
+        for (uint32_t b = 0; b <= key && b <= nb; b++) st[b] = 0;
+    } else if (key != prev) {
+        for (uint32_t b = prev + 1; b <= key && b <= nb; b++) st[b] = i;
+    }
+    if (i == n2 - 1) {
+        for (uint32_t b = key + 1; b <= nb; b++) st[b] = n2;
+    }
+}
+
+// Every window owns nb slots (threads).  In an ordinary window slot = bucket.  The top window only sees the few leftover
+// bits (plus the recoding carry), i.e. a handful of very long buckets: there slot = (bucket, s) and the sp_top threads of a
+// bucket take every sp_top-th point, producing sp_top partial sums that all carry the bucket's weight.
+__global__ void __launch_bounds__(128) k_big_accumulate(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted,
+                                                        const uint32_t *__restrict__ start, uint32_t n2, int nwin, uint32_t nb, uint32_t sp_top,
+                                                        uint32_t chunks, uint32_t *__restrict__ buckets_jac) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nwin * nb) return;
+    uint32_t w = (uint32_t)(t / nb), slot = (uint32_t)(t % nb);
+    const bool top = (int)w == nwin - 1;
+    const uint32_t nbt = nb / sp_top;  // buckets of the top window; slot = r * nbt + b there (b fastest, so that the fold is a strided sum)
+    const uint32_t b = top ? slot % nbt : slot, stride = top ? sp_top : 1u, first = top ? slot / nbt : 0u;
+    const uint32_t *st = start + (size_t)w * (nb + 1);
+    uint32_t lo = st[b] + first, hi = st[b + 1];
+    const uint32_t *v = vals_sorted + (size_t)w * n2;
+    g1j acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t e = lo; e < hi; e += stride) {
+        uint32_t id = v[e];
+        uint32_t p = id & 0x7FFFFFFFu;
+        g1a q;
+        g1a_load(q, pts + 24 * (size_t)(p >> 1));
+        if (p & 1) fp_mul_beta(q.x, q.x);
+        if (id & 0x80000000u) fp_neg(q.y, q.y);
+        g1j_add_mixed(acc, acc, q);
+    }
+    (void)chunks;
+    g1j_store(buckets_jac + 36 * t, acc);
+}
+
+// One level of the hierarchical bucket reduction.  Every node carries A = sum of its buckets and Bv = sum of (local index) * bucket.
+// A parent of g children (child k spans 2^shift buckets):  A = sum_k A_k ,  Bv = sum_k Bv_k + 2^shift * sum_k k * A_k,
+// the last sum by the running-sum trick.  One thread per parent; Bin == nullptr at the leaves (Bv = 0).
+__global__ void __launch_bounds__(128) k_big_reduce_level(const uint32_t *__restrict__ Ain, const uint32_t *__restrict__ Bin, uint32_t n_out,
+                                                          uint32_t g, int shift, uint32_t *__restrict__ Aout, uint32_t *__restrict__ Bout) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_out) return;
+    g1j run, wsum, bsum;
+    g1j_set_inf(run);
+    g1j_set_inf(wsum);
+    g1j_set_inf(bsum);
+#pragma unroll 1
+    for (int k = (int)g - 1; k >= 0; k--) {
+        size_t idx = (size_t)q * g + k;
+        g1j a;
+        g1j_load(a, Ain + 36 * idx);
+        g1j_add(run, run, a);
+        // second addition of the step: the running sum into the weighted sum, or (last step / leaves) nothing
+        if (k >= 1) g1j_add(wsum, wsum, run);
+    }
+    if (Bin) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < g; k++) {
+            g1j bb;
+            g1j_load(bb, Bin + 36 * ((size_t)q * g + k));
+            g1j_add(bsum, bsum, bb);
+        }
+    }
+#pragma unroll 1
+    for (int s2 = 0; s2 < shift; s2++) g1j_dbl(wsum, wsum);
+    g1j_add(bsum, bsum, wsum);
+    g1j_store(Aout + 36 * (size_t)q, run);
+    g1j_store(Bout + 36 * (size_t)q, bsum);
+}
+
+// total = sum_w 2^(c w) * (Bv_w + A_w)   (weight of bucket b is b + 1); one thread, Horner from the top window down
+__global__ void k_big_horner(const uint32_t *__restrict__ A, const uint32_t *__restrict__ Bv, int nwin, int c, uint32_t *__restrict__ out_jac) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    g1j total;
+    g1j_set_inf(total);
+#pragma unroll 1
+    for (int w = nwin - 1; w >= 0; w--) {
+        if (w != nwin - 1) {
+#pragma unroll 1
+            for (int k = 0; k < c; k++) g1j_dbl(total, total);
+        }
+        g1j a, b;
+        g1j_load(a, A + 36 * (size_t)w);
+        g1j_load(b, Bv + 36 * (size_t)w);
+        g1j_add(total, total, a);
+        g1j_add(total, total, b);
+    }
+    g1j_store(out_jac, total);
+}
+
+// top window fold, one step: out[j * nbt + b] = sum over r = j, j + nw, j + 2 nw, ... < sp of in[r * nbt + b]   (warp (b, j)).
+// Called twice (sp -> nw partial sums per bucket, then nw -> 1); the last call (nw == 1) also pads out[nbt .. nb) with infinity.
+__global__ void __launch_bounds__(128) k_big_fold_top(const uint32_t *__restrict__ in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to,
+                                                      uint32_t *__restrict__ out) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = nbt * nw > pad_to ? nbt * nw : pad_to;
+    if (warp >= n_warps) return;
+    g1j acc;
+    g1j_set_inf(acc);
+    if (warp < nbt * nw) {
+        const uint32_t b = warp % nbt, jj = warp / nbt;
+        const uint32_t cnt = (sp - jj + nw - 1) / nw;  // elements of this warp
+#pragma unroll 1
+        for (uint32_t it = lane; it < ((cnt + 31) & ~31u); it += 32) {
+            g1j q;
+            g1j_set_inf(q);
+            if (it < cnt) g1j_load(q, in + 36 * ((size_t)(jj + (size_t)it * nw) * nbt + b));
+            g1j_add(acc, acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            g1j o;
+            shfl_down_g1j(o, acc, d, 32);
+            g1j_add(acc, acc, o);
+        }
+    }
+    if (lane == 0) g1j_store(out + 36 * (size_t)warp, acc);
+}
+
+// weight of slot i as a 32-byte scalar: bucket index + 1 (the constant scalars of the bucket reduction)
+__global__ void k_big_weights(uint32_t *__restrict__ w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t slot = i % nb;
+    (void)chunks;
+    uint32_t bucket = ((int)(i / nb) == nwin - 1) ? slot / sp_top : slot;
+    uint4 *d = reinterpret_cast<uint4 *>(w + 8 * (size_t)i);
+    d[0] = make_uint4(bucket + 1, 0, 0, 0);
+    d[1] = make_uint4(0, 0, 0, 0);
+}
+
+// in: [nwin][chunks] Jacobian partial weighted sums; out = sum_w 2^(c w) * sum_chunk in[w][chunk].  One warp.
+__global__ void __launch_bounds__(32) k_big_final(const uint32_t *__restrict__ in, int nwin, int chunks, int c, uint32_t *__restrict__ out_jac) {
+    const int lane = threadIdx.x;
+    g1j total;
+    g1j_set_inf(total);
+#pragma unroll 1
+    for (int w = nwin - 1; w >= 0; w--) {
+        // lanes sum the chunk results of window w
+        g1j acc;
+        g1j_set_inf(acc);
+        for (int s = lane; s < ((chunks + 31) & ~31); s += 32) {
+            g1j q;
+            g1j_set_inf(q);
+            if (s < chunks) g1j_load(q, in + 36 * ((size_t)w * chunks + s));
+            g1j_add(acc, acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            g1j o;
+            shfl_down_g1j(o, acc, d, 32);
+            g1j_add(acc, acc, o);
+        }
+        if (lane == 0) {
+            if (w != nwin - 1) {
+#pragma unroll 1
+                for (int k = 0; k < c; k++) g1j_dbl(total, total);
+            }
+            g1j_add(total, total, acc);
+        }
+    }
+    if (lane == 0) g1j_store(out_jac, total);
+}
+
+size_t big_msm_sort_temp_bytes(uint32_t n2, int nwin, int c) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, (size_t)n2 * nwin, 0, c + 4);
+    return bytes;
+}
+
+cudaError_t launch_big_digits(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, uint32_t n, int c, int nwin, uint32_t *keys,
+                              uint32_t *vals) {
+    k_big_digits<<<(n + 255) / 256, 256, 0, st>>>(pts, scalars, n, c, nwin, keys, vals);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, const uint32_t *keys, uint32_t *keys_out, const uint32_t *vals,
+                            uint32_t *vals_out, uint32_t n2, int nwin, int c, const uint32_t *seg_offsets /* nwin + 1 */) {
+    (void)seg_offsets;
+    return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, vals, vals_out, (size_t)n2 * nwin, 0, c + 4, st);
+}
+cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c, uint32_t *start) {
+    size_t total = (size_t)nwin * n2;
+    k_big_offsets<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys_sorted, n2, nwin, nb, c, start);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
+                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac) {
+    size_t total = (size_t)nwin * nb;
+    k_big_accumulate<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pts, vals_sorted, start, n2, nwin, nb, sp_top, chunks, buckets_jac);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_weights(cudaStream_t st, uint32_t *w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks) {
+    k_big_weights<<<(total + 255) / 256, 256, 0, st>>>(w, total, nb, nwin, sp_top, chunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
+                                    uint32_t *Bout) {
+    k_big_reduce_level<<<(n_out + 127) / 128, 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac) {
+    k_big_horner<<<1, 32, 0, st>>>(A, Bv, nwin, c, out_jac);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out) {
+    uint32_t n_warps = nbt * nw > pad_to ? nbt * nw : pad_to;
+    k_big_fold_top<<<(n_warps * 32 + 127) / 128, 128, 0, st>>>(in, nbt, sp, nw, pad_to, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_final(cudaStream_t st, const uint32_t *in, int nwin, int chunks, int c, uint32_t *out_jac) {
+    k_big_final<<<1, 32, 0, st>>>(in, nwin, chunks, c, out_jac);
+    return cudaGetLastError();
+}
+
+}  // namespace cdp

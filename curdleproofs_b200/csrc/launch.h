@@ -51,6 +51,21 @@ CDP_DECL_MSM(2) CDP_DECL_MSM(3) CDP_DECL_MSM(4) CDP_DECL_MSM(5) CDP_DECL_MSM(6)
 cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *win_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin);
 cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride);
 
+// large Pippenger MSM (k_bigmsm.cu)
+size_t big_msm_sort_temp_bytes(uint32_t n2, int nwin, int c);
+cudaError_t launch_big_digits(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, uint32_t n, int c, int nwin, uint32_t *keys, uint32_t *vals);
+cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, const uint32_t *keys, uint32_t *keys_out, const uint32_t *vals,
+                            uint32_t *vals_out, uint32_t n2, int nwin, int c, const uint32_t *seg_offsets);
+cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c, uint32_t *start);
+cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
+                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac);
+cudaError_t launch_big_weights(cudaStream_t st, uint32_t *w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks);
+cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
+                                    uint32_t *Bout);
+cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac);
+cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out);
+cudaError_t launch_big_final(cudaStream_t st, const uint32_t *in, int nwin, int chunks, int c, uint32_t *out_jac);
+
 // which: 0 = raw IMAD.WIDE chains (128 multiply-adds / thread / iteration), 1 = Fp mul chain, 2 = Fp sqr chain (1 / thread / iteration)
 cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, int threads, int iters);
 

@@ -42,6 +42,8 @@ _SIGS = {
     "cdp_d2h": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
     "cdp_host_alloc": (c_void_p, [c_void_p, c_size_t]),
     "cdp_host_free": (None, [c_void_p, c_void_p]),
+    "cdp_msm_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_sum_jacobian_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "cdp_profile_enable": (c_int, [c_void_p, c_int]),
     "cdp_profile_reset": (c_int, [c_void_p]),

@@ -111,6 +111,13 @@ int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 void *cdp_host_alloc(cdp_ctx *ctx, size_t bytes);
 void cdp_host_free(cdp_ctx *ctx, void *h_ptr);
 
+/* One MSM of any size over device-resident bases and scalars (n >= 1); asynchronous, result = one Jacobian point. */
+int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac);
+
+/* d_out_jac = sum of `count` Jacobian points.  The multi-GPU combine of a base-range-sharded MSM: every rank all-gathers the
+ * 144-byte partial sums (NCCL has no elliptic-curve reduction op) and adds them locally. */
+int cdp_sum_jacobian_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t count, uint8_t *d_out_jac);
+
 /* A batch of MSMs over device-resident bases and scalars.  Segment i computes
  *   sum_{j < n} d_scalars[scalars_off + j] * d_pts[pts_off + j]   (offsets in elements, not bytes). */
 typedef struct {

@@ -183,3 +183,21 @@ def test_generator_kat_through_gpu(engine, oracle):
     jac = g + pr.fp_to_mont_bytes(1)
     want = open(os.path.join(HERE, "golden", "g1_generator_compressed.hex")).read().strip()
     assert engine.compress_batch(jac).hex() == want
+
+
+@pytest.mark.parametrize("n", [8192, 8192 + 37, 20000])
+def test_msm_large_pippenger(engine, oracle, pool, n):
+    """n >= 2^13 takes the sort-based Pippenger path (k_bigmsm.cu); bit-exact vs the oracle, with infinity bases, zero scalars
+    and small scalars mixed in."""
+    rnd = random.Random(n)
+    pts = bytearray((pool * (n // 2100 + 1))[:96 * n])
+    sc = bytearray(rand_scalars(rnd, n))
+    for i in (0, 17, n - 1):
+        pts[96 * i:96 * i + 96] = bytes(96)
+    for i in (3, 18, n - 2):
+        sc[32 * i:32 * i + 32] = bytes(32)
+    for i in range(100, 140):
+        sc[32 * i:32 * i + 32] = pr.fr_to_bytes(rnd.randrange(1 << 20))
+    sc[32 * 50:32 * 51] = pr.fr_to_bytes(pr.R_ORDER - 1)
+    pts, sc = bytes(pts), bytes(sc)
+    assert oracle.compress_jac(engine.msm(pts, sc)) == oracle.compress_jac(oracle.msm(pts, sc, threads=8))
