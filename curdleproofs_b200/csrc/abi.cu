@@ -33,6 +33,7 @@ struct cdp_ctx {
     uint64_t launches = 0;
     // grow-on-demand device scratch
     scratch_t d_pts, d_scalars, d_segs, d_win, d_jac, d_aux, d_out;
+    scratch_t d_dig;  // digit rows of the small-MSM path
     scratch_t d_big;  // large-MSM workspace (keys, values, offsets, buckets, weights, sort temp)
     // pinned host staging
     scratch_t h_stage;
@@ -143,9 +144,11 @@ constexpr size_t SMALL_MSM_MAX_N = 2048;  // C = 6, WPB = 11: 11 * 6 * 2048 = 13
 // window sums for `count` segments -> d_win[count][nwin]
 int msm_buckets_dev(cdp_ctx *ctx, const msm_cfg &g, const uint8_t *d_pts, const uint8_t *d_scalars, const msm_seg_t *d_segs, size_t count,
                     size_t nmax, uint32_t *d_win, uint64_t pairs) {
+    TRY(ensure_dev(ctx, ctx->d_dig, msm_dig_bytes(g.c, nmax, count)));
     launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, pairs);
+    ctx->launches++;  // digit kernel + bucket kernel
     CUDA_TRY(ctx, launch_msm_buckets(ctx->stream, g.c, reinterpret_cast<const uint32_t *>(d_pts), reinterpret_cast<const uint32_t *>(d_scalars),
-                                     d_segs, (uint32_t)count, (uint32_t)nmax, d_win));
+                                     d_segs, (uint32_t)count, (uint32_t)nmax, reinterpret_cast<int8_t *>(ctx->d_dig.ptr), d_win));
     return CDP_OK;
 }
 
@@ -217,7 +220,7 @@ extern "C" void cdp_ctx_destroy(cdp_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (scratch_t *s : {&ctx->d_pts, &ctx->d_scalars, &ctx->d_segs, &ctx->d_win, &ctx->d_jac, &ctx->d_aux, &ctx->d_out, &ctx->d_big})
+    for (scratch_t *s : {&ctx->d_pts, &ctx->d_scalars, &ctx->d_segs, &ctx->d_win, &ctx->d_jac, &ctx->d_aux, &ctx->d_out, &ctx->d_big, &ctx->d_dig})
         if (s->ptr) cudaFree(s->ptr);
     if (ctx->h_stage.ptr) cudaFreeHost(ctx->h_stage.ptr);
     prof_drain(ctx);

@@ -46,13 +46,13 @@ __global__ void __launch_bounds__(128) k_sum_groups(const uint32_t *__restrict__
 }
 
 cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, uint32_t count,
-                               uint32_t nmax, uint32_t *win_sums) {
+                               uint32_t nmax, int8_t *dig, uint32_t *win_sums) {
     switch (c) {
-        case 6: return launch_msm_buckets_c6(st, pts, scalars, segs, count, nmax, win_sums);
-        case 5: return launch_msm_buckets_c5(st, pts, scalars, segs, count, nmax, win_sums);
-        case 4: return launch_msm_buckets_c4(st, pts, scalars, segs, count, nmax, win_sums);
-        case 3: return launch_msm_buckets_c3(st, pts, scalars, segs, count, nmax, win_sums);
-        case 2: return launch_msm_buckets_c2(st, pts, scalars, segs, count, nmax, win_sums);
+        case 6: return launch_msm_buckets_c6(st, pts, scalars, segs, count, nmax, dig, win_sums);
+        case 5: return launch_msm_buckets_c5(st, pts, scalars, segs, count, nmax, dig, win_sums);
+        case 4: return launch_msm_buckets_c4(st, pts, scalars, segs, count, nmax, dig, win_sums);
+        case 3: return launch_msm_buckets_c3(st, pts, scalars, segs, count, nmax, dig, win_sums);
+        case 2: return launch_msm_buckets_c2(st, pts, scalars, segs, count, nmax, dig, win_sums);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -8,40 +8,33 @@
 
 namespace cdp {
 
-// k_msm_buckets: bucket phase of a batch of independent small MSMs -- `util::msm` (/root/reference/src/util.rs:19-22).
-// Scalars are GLV-split (2n half-width "points": 2j -> P_j with k1, 2j+1 -> phi(P_j) with k2) and recoded into signed
-// radix-2^c digits; lane (w, b) owns bucket b of window w:
-//   phase 0  split + digits into shared memory (int8, one row per window)
+// The small-MSM path -- `util::msm` (/root/reference/src/util.rs:19-22) for a batch of independent MSMs -- runs in two kernels:
+//
+// k_msm_digits   one thread per (segment, pair): coalesced 128-bit scalar loads, GLV split (2n half-width "points": 2j -> P_j
+//                with k1, 2j+1 -> phi(P_j) with k2), signed radix-2^c recoding; digit rows (int8, one row per window) go to global
+//                memory once per MSM, so the bucket kernel can use as many small CTAs per MSM as it likes without redoing this.
+// k_msm_buckets  grid = (n_msm, ceil(NWIN / WPB)), CTAs of <= 128 threads (3 resident per SM at <= 168 registers).
+//                Lane (w, b) owns bucket b of window w:
+//   phase 0  the CTA's WPB digit rows are staged global -> shared memory with 16-byte loads
 //   phase 1  each lane counts its bucket, a warp-shuffle scan over the nb lanes of the window gives list offsets
 //   phase 2  each lane writes its own index list (uint16 point id | sign bit) -- no atomics, no contention
 //   phase 3  each lane adds ITS OWN points (different lanes, different points => no serialisation); mixed adds
 //   phase 4  sum_b (b+1) B_b by a suffix scan + tree sum with warp shuffles (2*log2(nb) Jacobian adds deep)
 //   phase 5  lane b = 0 writes the window sum; k_msm_combine does the doublings
 // Handles infinity bases and zero scalars (digits 0) and all-equal scalars (one long list, still correct).
-//
-// dynamic shared memory: int8 digits[WPB][dstride] ; uint16 lists[WPB][2*nmax]
-// grid = (n_msm, ceil(NWIN / WPB)): the windows of one MSM are split over blockIdx.y so that a CTA stays <= 384 threads
-// (<= 168 registers per thread, no spills).
-template <int C, int WPB>
-__global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
-    k_msm_buckets(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars, const msm_seg_t *__restrict__ segs,
-                  uint32_t *__restrict__ win_sums /* [msm][nwin] jacobian */, uint32_t nmax) {
+template <int C>
+__global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
+                                                    const msm_seg_t *__restrict__ segs, int8_t *__restrict__ dig, uint32_t rowstride) {
     constexpr int NB = 1 << (C - 1);
     constexpr int NWIN = (130 + C - 1) / C;
-    extern __shared__ __align__(16) uint8_t smem[];
     const msm_seg_t seg = segs[blockIdx.x];
     const uint32_t n_plain = seg.n;
-    const uint32_t n = seg.n + (seg.extra ? 1u : 0u), n2 = 2 * n;  // the optional extra base is logically element n_plain
+    const uint32_t n = seg.n + (seg.extra ? 1u : 0u);  // the optional extra base is logically element n_plain
     const uint32_t *PX = seg.extra ? pts + 24 * (size_t)(seg.extra - 1) : nullptr;
-    const int w0 = blockIdx.y * WPB;
-    const uint32_t dstride = 2 * nmax + 4;  // +4: rows of different windows fall into different banks
-    int8_t *digits = reinterpret_cast<int8_t *>(smem);
-    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + ((WPB * dstride + 15) & ~15u));
     const uint32_t *P = pts + 24 * (size_t)seg.pts_off;
     const uint32_t *S = scalars + 8 * (size_t)seg.scalars_off;
-
-    // ---- phase 0
-    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+    int8_t *digits = dig + (size_t)blockIdx.x * NWIN * rowstride;
+    for (uint32_t j = blockIdx.y * blockDim.x + threadIdx.x; j < n; j += blockDim.x * gridDim.y) {
         uint32_t k[8];
         const uint4 *sp = reinterpret_cast<const uint4 *>(S + 8 * (size_t)j);
         uint4 a = sp[0], b = sp[1];
@@ -72,8 +65,39 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
                 v = (v & ((1u << C) - 1)) + carry;
                 carry = (v + NB) >> C;  // recentre to [-NB, NB)
                 int d = (int)v - (int)(carry << C);
-                if (w >= w0 && w < w0 + WPB) digits[(w - w0) * dstride + 2 * j + half] = (int8_t)d;
+                digits[(size_t)w * rowstride + 2 * j + half] = (int8_t)d;
             }
+        }
+    }
+}
+
+// dynamic shared memory: int8 digits[WPB][dstride] ; uint16 lists[WPB][2*nmax]
+template <int C, int WPB>
+__global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32, 3)
+    k_msm_buckets(const uint32_t *__restrict__ pts, const msm_seg_t *__restrict__ segs, const int8_t *__restrict__ dig, uint32_t rowstride,
+                  uint32_t *__restrict__ win_sums /* [msm][nwin] jacobian */, uint32_t nmax) {
+    constexpr int NB = 1 << (C - 1);
+    constexpr int NWIN = (130 + C - 1) / C;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const msm_seg_t seg = segs[blockIdx.x];
+    const uint32_t n_plain = seg.n;
+    const uint32_t n = seg.n + (seg.extra ? 1u : 0u), n2 = 2 * n;
+    const uint32_t *PX = seg.extra ? pts + 24 * (size_t)(seg.extra - 1) : nullptr;
+    const int w0 = blockIdx.y * WPB;
+    const uint32_t dstride = ((2 * nmax + 15) & ~15u) + 16;  // 16-byte aligned rows; the extra 16 bytes spread the rows over the banks
+    int8_t *digits = reinterpret_cast<int8_t *>(smem);
+    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + (size_t)WPB * dstride);
+    const uint32_t *P = pts + 24 * (size_t)seg.pts_off;
+
+    // ---- phase 0: stage this CTA's digit rows
+    {
+        const int8_t *gd = dig + (size_t)blockIdx.x * NWIN * rowstride;
+        const uint32_t vec_per_row = (n2 + 15) / 16;
+        for (uint32_t t = threadIdx.x; t < WPB * vec_per_row; t += blockDim.x) {
+            uint32_t wl = t / vec_per_row, v = t % vec_per_row;
+            if (w0 + (int)wl < NWIN)
+                reinterpret_cast<uint4 *>(digits + (size_t)wl * dstride)[v] =
+                    reinterpret_cast<const uint4 *>(gd + (size_t)(w0 + wl) * rowstride)[v];
         }
     }
     __syncthreads();
@@ -173,17 +197,22 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32)
 #define CDP_CAT2(a, b) a##b
 #define CDP_CAT(a, b) CDP_CAT2(a, b)
 cudaError_t CDP_CAT(launch_msm_buckets_c, MSM_C)(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs,
-                                                 uint32_t count, uint32_t nmax, uint32_t *win_sums) {
+                                                 uint32_t count, uint32_t nmax, int8_t *dig, uint32_t *win_sums) {
     constexpr int C = MSM_C, WPB = msm_wpb_for(MSM_C), NWIN = msm_nwin_for(MSM_C);
     constexpr int threads = ((WPB << (C - 1)) + 31) / 32 * 32;
+    const uint32_t rowstride = msm_dig_rowstride(nmax);
+    dim3 dgrid(count, nmax > 512 ? (nmax + 511) / 512 : 1);
+    k_msm_digits<C><<<dgrid, 128, 0, st>>>(pts, scalars, segs, dig, rowstride);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     size_t smem = msm_smem_bytes(C, nmax);
     auto kern = k_msm_buckets<C, WPB>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     dim3 grid(count, (NWIN + WPB - 1) / WPB);
-    kern<<<grid, threads, smem, st>>>(pts, scalars, segs, win_sums, nmax);
+    kern<<<grid, threads, smem, st>>>(pts, segs, dig, rowstride, win_sums, nmax);
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ namespace cdp {
 //   (1,0) -> P = (x, y)      (0,1) -> phi(P) = (beta x, y)      (1,1) -> P + phi(P) = -phi^2(P) = (beta^2 x, -y)
 // so each step is one doubling plus at most one mixed addition.  Within one fold job all threads share the scalar, so
 // the add/skip pattern is warp-uniform whenever a job spans whole warps.
-__global__ void __launch_bounds__(128) k_smul_jobs(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
+__global__ void __launch_bounds__(128, 3) k_smul_jobs(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
                                                    const smul_job_t *__restrict__ jobs, uint32_t elems_per_job, uint32_t total,
                                                    uint32_t *__restrict__ out_jac) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -41,11 +41,12 @@ cudaError_t launch_compress_affine(cudaStream_t st, const uint32_t *pts, const u
 cudaError_t launch_decompress(cudaStream_t st, const uint8_t *comp, const uint32_t *dst_idx, uint32_t *out_affine, uint8_t *status, uint32_t n);
 cudaError_t launch_gather_points(cudaStream_t st, uint32_t *pts, const uint32_t *src, const uint32_t *src_idx, const uint32_t *dst_idx, uint32_t n);
 // window sums of `count` MSM segments; c in 2..6 selects the kernel instantiation
+// `dig`: scratch for the digit rows, msm_dig_bytes(c, nmax, count) bytes
 cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, uint32_t count,
-                               uint32_t nmax, uint32_t *win_sums);
+                               uint32_t nmax, int8_t *dig, uint32_t *win_sums);
 #define CDP_DECL_MSM(C)                                                                                                         \
     cudaError_t launch_msm_buckets_c##C(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs, \
-                                        uint32_t count, uint32_t nmax, uint32_t *win_sums);
+                                        uint32_t count, uint32_t nmax, int8_t *dig, uint32_t *win_sums);
 CDP_DECL_MSM(2) CDP_DECL_MSM(3) CDP_DECL_MSM(4) CDP_DECL_MSM(5) CDP_DECL_MSM(6)
 #undef CDP_DECL_MSM
 cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *win_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin);
@@ -71,10 +72,13 @@ cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, 
 
 // geometry shared by host and device
 constexpr int msm_nwin_for(int c) { return (130 + c - 1) / c; }
-constexpr int msm_wpb_for(int c) { return c == 6 ? 11 : c == 5 ? 13 : c == 4 ? 33 : c == 3 ? 44 : 65; }
+// windows per CTA: CTAs of 96-128 threads (c = 6: 4 windows x 32 buckets, 5: 7 x 16, 4: 11 x 8, 3: 22 x 4, 2: 33 x 2)
+constexpr int msm_wpb_for(int c) { return c == 6 ? 4 : c == 5 ? 7 : c == 4 ? 11 : c == 3 ? 22 : 33; }
+inline uint32_t msm_dig_rowstride(size_t nmax) { return (uint32_t)((2 * nmax + 15) & ~size_t(15)); }
+inline size_t msm_dig_bytes(int c, size_t nmax, size_t count) { return count * (size_t)msm_nwin_for(c) * msm_dig_rowstride(nmax); }
 inline size_t msm_smem_bytes(int c, size_t nmax) {
-    size_t wpb = msm_wpb_for(c), dstride = 2 * nmax + 4;
-    return ((wpb * dstride + 15) & ~size_t(15)) + wpb * 2 * nmax * sizeof(uint16_t);
+    size_t wpb = msm_wpb_for(c), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
+    return wpb * dstride + wpb * 2 * nmax * sizeof(uint16_t);
 }
 
 }  // namespace cdp
