@@ -6,6 +6,7 @@ ctypes mirror of the reference's operator interface for that path:
     reference (Rust)                                   here
     ------------------------------------------------   -------------------------------
     util::msm(points, scalars)            util.rs:19    Engine.msm(points, scalars)
+    util::msm(&crs.vec_G[a..b], scalars)  (CRS bases)   Engine.msm_fixed(table, a, scalars)
     util::msm_from_projective(...)        util.rs:25    Engine.msm_from_projective(...)
     fold loops  (L + gamma*R).into_affine()             Engine.fold(L, R, gamma)
     (s_i * P_i).into_affine()                           Engine.scalar_mul_batch(points, scalars)
@@ -15,7 +16,7 @@ ctypes mirror of the reference's operator interface for that path:
 There is no CPU fallback: constructing an ``Engine`` without the built extension or without a CUDA
 device raises.
 """
-from .engine import Engine, CdpError, lib_path, load_library  # noqa: F401
+from .engine import Engine, CdpError, FixedSeg, FixedTable, lib_path, load_library  # noqa: F401
 from .prover import BatchProver, BatchVerifier, load_prover_library  # noqa: F401
 
-__all__ = ["Engine", "CdpError", "lib_path", "load_library", "BatchProver", "BatchVerifier", "load_prover_library"]
+__all__ = ["Engine", "CdpError", "FixedSeg", "FixedTable", "lib_path", "load_library", "BatchProver", "BatchVerifier", "load_prover_library"]

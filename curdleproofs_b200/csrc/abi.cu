@@ -639,6 +639,118 @@ extern "C" int cdp_compress_batch(cdp_ctx *ctx, const uint8_t *jac_pts, size_t n
     return normalize_host(ctx, jac_pts, n, out_compressed, true);
 }
 
+// =================================================================================================== fixed-base MSM
+struct cdp_fixed_table {
+    uint32_t *d_table = nullptr;
+    size_t n_bases = 0, bytes = 0;
+    int device = 0;
+    fixed_kparams_t kp;
+};
+
+extern "C" int cdp_fixed_table_create(cdp_ctx *ctx, const uint8_t *affine_pts, size_t n_bases, int window_bits, cdp_fixed_table **out) {
+    if (!ctx || !out || !affine_pts || n_bases == 0) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_fixed_table_create: bad argument");
+    *out = nullptr;
+    if (window_bits == 0) window_bits = 16;
+    if (window_bits < 2 || window_bits > 16) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_fixed_table_create: window_bits must be 2..16");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int c = window_bits, nw = (256 + c - 1) / c;
+    const uint32_t nd = 1u << (c - 1);
+    const size_t chains = n_bases * (size_t)nw;
+    if (chains * nd >= (size_t(1) << 32)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_fixed_table_create: table too large");
+    cdp_fixed_table *t = new cdp_fixed_table();
+    t->n_bases = n_bases;
+    t->device = ctx->device;
+    t->kp.c = c; t->kp.nw = nw; t->kp.nd = nd;
+    for (int i = 0; i < 8; i++) t->kp.recode[i] = 0;
+    for (int w = 0; w + 1 < nw; w++) {
+        int bit = c * w + c - 1;
+        t->kp.recode[bit >> 5] |= 1u << (bit & 31);
+    }
+    t->bytes = chains * nd * CDP_AFFINE_BYTES;
+    if (cudaMalloc(&t->d_table, t->bytes) != cudaSuccess) {
+        delete t;
+        return fail(ctx, CDP_ERR_CUDA, "cdp_fixed_table_create: cudaMalloc of the digit table failed");
+    }
+    auto bail = [&](int rc) { cudaStreamSynchronize(ctx->stream); cudaFree(t->d_table); delete t; return rc; };
+    // bases -> 2^(c w) B (Jacobian) -> affine -> digit 1 of every chain -> c - 1 doubling levels
+    if (int rc = ensure_dev(ctx, ctx->d_pts, n_bases * CDP_AFFINE_BYTES)) return bail(rc);
+    if (int rc = ensure_dev(ctx, ctx->d_jac, chains * CDP_JACOBIAN_BYTES)) return bail(rc);
+    if (int rc = ensure_dev(ctx, ctx->d_out, chains * CDP_AFFINE_BYTES)) return bail(rc);
+    cudaError_t e = cudaMemcpyAsync(ctx->d_pts.ptr, affine_pts, n_bases * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_fixed_pow(ctx->stream, (const uint32_t *)ctx->d_pts.ptr, (uint32_t)n_bases, c, nw, (uint32_t *)ctx->d_jac.ptr);
+    if (e == cudaSuccess) e = launch_normalize(ctx->stream, 1, (const uint32_t *)ctx->d_jac.ptr, (uint32_t *)ctx->d_out.ptr, nullptr, (uint32_t)chains, nullptr, 1);
+    if (e == cudaSuccess) e = launch_fixed_seed(ctx->stream, (const uint32_t *)ctx->d_out.ptr, (uint32_t)chains, nd, t->d_table);
+    ctx->launches += 3;
+    for (uint32_t half = 1; half < nd && e == cudaSuccess; half <<= 1) {
+        e = launch_fixed_level(ctx->stream, t->d_table, (uint32_t)chains, nd, half);
+        ctx->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bail(fail(ctx, CDP_ERR_CUDA, std::string("cdp_fixed_table_create: ") + cudaGetErrorString(e)));
+    *out = t;
+    return CDP_OK;
+}
+extern "C" void cdp_fixed_table_destroy(cdp_ctx *ctx, cdp_fixed_table *t) {
+    if (!t) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(t->d_table);
+    delete t;
+}
+extern "C" size_t cdp_fixed_table_bytes(const cdp_fixed_table *t) { return t ? t->bytes : 0; }
+extern "C" size_t cdp_fixed_table_bases(const cdp_fixed_table *t) { return t ? t->n_bases : 0; }
+
+extern "C" int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                                       size_t total_pairs, uint8_t *d_out_jac) {
+    if (!ctx || !t || (count && (!d_scalars || !d_segs || !d_out_jac))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev: null argument");
+    if (count == 0) return CDP_OK;
+    if (t->device != ctx->device) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev: table lives on another device");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cdp_fixed_seg) == sizeof(fixed_seg_t), "fixed segment layout");
+    launch_scope ls(ctx, CDP_PROFILE_MSM_FIXED, total_pairs);
+    CUDA_TRY(ctx, launch_fixed_msm(ctx->stream, t->d_table, reinterpret_cast<const uint32_t *>(d_scalars), reinterpret_cast<const fixed_seg_t *>(d_segs),
+                                   (uint32_t)count, t->kp, reinterpret_cast<uint32_t *>(d_out_jac)));
+    return CDP_OK;
+}
+
+extern "C" int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base_off, const uint8_t *scalars, size_t n,
+                             uint8_t out_jac[CDP_JACOBIAN_BYTES]) {
+    if (!ctx || !t || !out_jac || (n && !scalars)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed: null argument");
+    if (base_off + n > t->n_bases) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed: base range outside the table");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) {
+        memcpy(out_jac, INF_JAC_ZERO, CDP_JACOBIAN_BYTES);
+        return CDP_OK;
+    }
+    // one warp per 64 pairs, partial sums added by one more warp
+    const size_t chunk = 64, nseg = (n + chunk - 1) / chunk;
+    TRY(ensure_dev(ctx, ctx->d_scalars, n * CDP_SCALAR_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_segs, nseg * sizeof(fixed_seg_t)));
+    TRY(ensure_dev(ctx, ctx->d_jac, (nseg + 1) * CDP_JACOBIAN_BYTES));
+    TRY(ensure_host(ctx, ctx->h_stage, nseg * sizeof(fixed_seg_t)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    fixed_seg_t *hs = (fixed_seg_t *)ctx->h_stage.ptr;
+    for (size_t i = 0; i < nseg; i++) {
+        memset(&hs[i], 0, sizeof hs[i]);
+        hs[i].base_off = (uint32_t)(base_off + i * chunk);
+        hs[i].scalars_off = (uint32_t)(i * chunk);
+        hs[i].n = (uint32_t)std::min(chunk, n - i * chunk);
+        hs[i].remap_from = 0xFFFFFFFFu;
+        hs[i].out_idx = (uint32_t)i;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, hs, nseg * sizeof(fixed_seg_t), cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t *dj = (uint8_t *)ctx->d_jac.ptr;
+    TRY(cdp_msm_fixed_batch_dev(ctx, t, (const uint8_t *)ctx->d_scalars.ptr, (const cdp_fixed_seg *)ctx->d_segs.ptr, nseg, n, dj));
+    const uint8_t *res = dj;
+    if (nseg > 1) {
+        TRY(cdp_sum_jacobian_dev(ctx, dj, nseg, dj + nseg * CDP_JACOBIAN_BYTES));
+        res = dj + nseg * CDP_JACOBIAN_BYTES;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_jac, res, CDP_JACOBIAN_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CDP_OK;
+}
+
 // =================================================================================================== profiling
 static void prof_drain(cdp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);

@@ -1,0 +1,225 @@
+// Fixed-base MSM: `util::msm` (/root/reference/src/util.rs:19-22) for the call sites whose bases are CRS points
+// (crs.vec_G, vec_H, H, G_t, G_u -- /root/reference/src/crs.rs:19-34), which never change between proofs:
+//   A, C, B_c, B_d, B_a, the four GroupCommitment T_1 points, and -- once the IPA / SameMSM round MSMs are written over the
+//   ORIGINAL bases with the fold challenges moved into the scalars (the reference's own verifier identity,
+//   src/inner_product_argument.rs:202-250) -- every L/R cross term over G, G' = u o G and G_with_blinders.
+//
+// B200-first layout: with 180 GB of HBM per GPU the whole digit table fits on the device,
+//   table[(base * nw + w) * nd + (d - 1)] = d * 2^(c w) * B_base   (affine, 96 B; c = 16: 16 windows x 32768 digits = 50 MB per base)
+// so one (scalar, base) pair costs nw = 16 mixed additions -- gathered 96-byte reads, no buckets, no doublings, no window
+// combine -- instead of ~52 bucket additions plus the bucket reduction of the variable-base kernel.
+#include "launch.h"
+#include "msm_common.cuh"
+
+namespace cdp {
+
+// ------------------------------------------------------------------------------------------------ table construction
+// jac_out[base * nw + w] = 2^(c w) * B_base : one thread per base, c doublings between windows.
+__global__ void __launch_bounds__(64) k_fixed_pow(const uint32_t *__restrict__ bases, uint32_t n_bases, int c, int nw, uint32_t *__restrict__ jac_out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_bases) return;
+    g1a P;
+    g1a_load(P, bases + 24 * (size_t)j);
+    g1j acc;
+    g1j_from_affine(acc, P);
+#pragma unroll 1
+    for (int w = 0; w < nw; w++) {
+        g1j_store(jac_out + 36 * ((size_t)j * nw + w), acc);
+#pragma unroll 1
+        for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
+    }
+}
+
+// table[chain * nd + 0] = aff[chain]   (digit 1 of every (base, window) chain)
+__global__ void __launch_bounds__(256) k_fixed_seed(const uint32_t *__restrict__ aff, uint32_t chains, uint32_t nd, uint32_t *__restrict__ table) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t ch = t / 6, q = t % 6;
+    if (ch >= chains) return;
+    reinterpret_cast<uint4 *>(table + 24 * (size_t)ch * nd)[q] = reinterpret_cast<const uint4 *>(aff + 24 * (size_t)ch)[q];
+}
+
+// One doubling level of every chain: entries [0, half) hold 1Q .. half*Q; this writes (half + e + 1) Q = (e + 1) Q + half Q for
+// e < half.  Affine + affine with Montgomery's simultaneous inversion over CH entries per thread (one Fp inversion per CH points).
+// e == half - 1 is the doubling (half Q + half Q).  Bases are prime-order points (or infinity: the whole chain stays all-zero), so no
+// other coincidence of x-coordinates can occur below the group order.
+constexpr int FIXED_CH = 16;
+__global__ void __launch_bounds__(128) k_fixed_level(uint32_t *__restrict__ table, uint32_t chains, uint32_t nd, uint32_t half) {
+    const uint32_t parts = (half + FIXED_CH - 1) / FIXED_CH;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ch = t / parts, part = t - ch * parts;
+    if (ch >= chains) return;
+    const uint32_t e0 = part * FIXED_CH;
+    const uint32_t cnt = half - e0 < (uint32_t)FIXED_CH ? half - e0 : (uint32_t)FIXED_CH;
+    uint32_t *T = table + 24 * (size_t)ch * nd;
+    g1a Bp;
+    g1a_load(Bp, T + 24 * (size_t)(half - 1));
+    const bool binf = g1a_is_inf(Bp);
+    fp prefix[FIXED_CH];
+    fp run;
+    fp_set_one(run);
+#pragma unroll 1
+    for (uint32_t i = 0; i < cnt; i++) {
+        prefix[i] = run;
+        fp den;
+        if (binf) {
+            fp_set_one(den);
+        } else if (e0 + i == half - 1) {
+            fp_dbl(den, Bp.y);
+        } else {
+            fp ax;
+            fp_load(ax, T + 24 * (size_t)(e0 + i));
+            fp_sub(den, Bp.x, ax);
+        }
+        fp_mul(run, run, den);
+    }
+    fp inv;
+    fp_inv(inv, run);
+#pragma unroll 1
+    for (int i = (int)cnt - 1; i >= 0; i--) {
+        g1a A, R;
+        g1a_load(A, T + 24 * (size_t)(e0 + i));
+        if (binf) {
+            g1a_set_inf(R);
+        } else {
+            const bool dbl = (e0 + i == half - 1);
+            fp den, num, lam, dinv;
+            if (dbl) {
+                fp_dbl(den, Bp.y);
+                fp_sqr(num, Bp.x);
+                fp_dbl(lam, num);
+                fp_add(num, lam, num);  // 3 x^2
+            } else {
+                fp_sub(den, Bp.x, A.x);
+                fp_sub(num, Bp.y, A.y);
+            }
+            fp_mul(dinv, inv, prefix[i]);
+            fp_mul(inv, inv, den);
+            fp_mul(lam, num, dinv);
+            fp_sqr(R.x, lam);
+            fp_sub(R.x, R.x, A.x);
+            fp_sub(R.x, R.x, Bp.x);
+            fp_sub(R.y, A.x, R.x);
+            fp_mul(R.y, lam, R.y);
+            fp_sub(R.y, R.y, A.y);
+        }
+        g1a_store(T + 24 * (size_t)(half + e0 + i), R);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the MSM
+// Signed digit w of a canonical scalar k < 2^255: with k' = k + sum_{w < nw-1} 2^(c w + c - 1), digit_w = window_w(k') - 2^(c-1) in
+// [-2^(c-1), 2^(c-1)) for w < nw - 1 and the top digit = k' >> c(nw-1) in [0, 2^(c-1)]: sum_w digit_w 2^(c w) = k.
+__device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint32_t w, const fixed_kparams_t &kp) {
+    const uint4 a = reinterpret_cast<const uint4 *>(sp)[0], b = reinterpret_cast<const uint4 *>(sp)[1];
+    uint32_t k[9];
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(k[0]), "=r"(k[1]), "=r"(k[2]), "=r"(k[3]), "=r"(k[4]), "=r"(k[5]), "=r"(k[6]), "=r"(k[7]), "=r"(k[8])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w), "r"(kp.recode[0]), "r"(kp.recode[1]),
+          "r"(kp.recode[2]), "r"(kp.recode[3]), "r"(kp.recode[4]), "r"(kp.recode[5]), "r"(kp.recode[6]), "r"(kp.recode[7]));
+    const uint32_t bit = (uint32_t)kp.c * w, wi = bit >> 5, sh = bit & 31;
+    uint32_t lo = 0, hi = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < 9; t++) {
+        if (t == wi) lo = k[t];
+        if (t == wi + 1) hi = k[t];
+    }
+    const uint32_t v = __funnelshift_r(lo, hi, sh);
+    if (w + 1 < (uint32_t)kp.nw) return (int)(v & ((1u << kp.c) - 1u)) - (int)(kp.nd);
+    return (int)(v < kp.nd ? v : kp.nd);  // canonical scalars never exceed nd here; the clamp only keeps a non-canonical one in bounds
+}
+
+// One warp per segment.  Work item q = (pair i, window w) = (q / nw, q % nw); lane l takes items l, l + 32, ...; every item is one
+// gathered 96-byte table read and one mixed addition into the lane's Jacobian accumulator; the next item's point is fetched before the
+// current addition is issued, so the HBM gather latency (~1 us) hides behind ~3300 integer instructions.  The 32 partial sums are
+// folded with warp shuffles (5 full additions).
+__global__ void __launch_bounds__(128, 3) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
+                                                       const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
+                                                       uint32_t *__restrict__ out_jac) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    const fixed_seg_t seg = segs[warp];
+    const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
+    // returns true and the (un-negated) table point when item q has a non-zero digit
+    auto fetch = [&](uint32_t q, g1a &P, bool &neg) -> bool {
+        const uint32_t i = q / (uint32_t)kp.nw, w = q - i * (uint32_t)kp.nw;
+        uint32_t bidx, sidx;
+        if (i < seg.n) {
+            uint32_t j = i;
+            if (seg.sel_h) {
+                const uint32_t lo = i & (seg.sel_h - 1);
+                j = ((i - lo) << 1) | lo | seg.sel_val;
+            }
+            sidx = seg.scalars_off + j;
+            bidx = seg.base_off + j + (j >= seg.remap_from ? seg.remap_delta : 0u);
+        } else {
+            bidx = seg.extra_base - 1;
+            sidx = seg.scalars_off + seg.extra_scalar;
+        }
+        const int d = fixed_digit(scalars + 8 * (size_t)sidx, w, kp);
+        if (d == 0) return false;
+        neg = d < 0;
+        const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+        g1a_load(P, table + 24 * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1)));
+        return true;
+    };
+    g1j acc;
+    g1j_set_inf(acc);
+    g1a cur;
+    bool cur_neg = false, have = false;
+    uint32_t q = lane;
+    while (q < items && !have) {
+        have = fetch(q, cur, cur_neg);
+        q += 32;
+    }
+#pragma unroll 1
+    while (have) {
+        g1a nxt;
+        bool nxt_neg = false, hn = false;
+        while (q < items && !hn) {
+            hn = fetch(q, nxt, nxt_neg);
+            q += 32;
+        }
+        if (cur_neg) fp_neg(cur.y, cur.y);
+        g1j_add_mixed(acc, acc, cur);
+        cur = nxt;
+        cur_neg = nxt_neg;
+        have = hn;
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        g1j o;
+        shfl_down_g1j(o, acc, d, 32);
+        g1j_add(acc, acc, o);
+    }
+    if (lane == 0) g1j_store(out_jac + 36 * (size_t)seg.out_idx, acc);
+}
+
+cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint32_t n_bases, int c, int nw, uint32_t *jac_out) {
+    k_fixed_pow<<<(n_bases + 63) / 64, 64, 0, st>>>(bases_affine, n_bases, c, nw, jac_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t *table) {
+    k_fixed_seed<<<(chains * 6 + 255) / 256, 256, 0, st>>>(aff, chains, nd, table);
+    return cudaGetLastError();
+}
+cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half) {
+    const uint64_t parts = (half + FIXED_CH - 1) / FIXED_CH, threads = parts * chains;
+    k_fixed_level<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(table, chains, nd, half);
+    return cudaGetLastError();
+}
+cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
+                             const fixed_kparams_t &kp, uint32_t *out_jac) {
+    if (count == 0) return cudaSuccess;
+    k_fixed_msm<<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, out_jac);
+    return cudaGetLastError();
+}
+
+}  // namespace cdp

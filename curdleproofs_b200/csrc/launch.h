@@ -67,6 +67,32 @@ cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t
 cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out);
 cudaError_t launch_big_final(cudaStream_t st, const uint32_t *in, int nwin, int chunks, int c, uint32_t *out_jac);
 
+// fixed-base MSM over a precomputed digit table (k_fixed.cu).  Table layout: affine points, 96 B each,
+//   table[(base * nw + w) * nd + (d - 1)] = d * 2^(c w) * B_base      d = 1 .. nd = 2^(c-1),  w < nw = ceil(256 / c)
+struct fixed_seg_t {
+    uint32_t base_off;      // first base of the segment's range, in bases of the table
+    uint32_t scalars_off;   // first scalar of the range
+    uint32_t n;             // pairs the segment sums (without the extra one)
+    uint32_t sel_h;         // 0: the range is 0..n-1.  Power of two h: only range positions j with (j & h) == sel_val take part
+    uint32_t sel_val;       //    (n of them; position of the i-th one = i with bit h inserted) -- the L / R halves of a folded vector
+    uint32_t remap_from;    // range positions j >= remap_from use base j + remap_delta (a base list with a gap)
+    uint32_t remap_delta;
+    uint32_t extra_base;    // 0 = none, else 1 + table base index of one more pair ...
+    uint32_t extra_scalar;  // ... whose scalar is scalars[scalars_off + extra_scalar]
+    uint32_t out_idx;       // result goes to out_jac[out_idx]
+    uint32_t pad[2];
+};
+struct fixed_kparams_t {
+    int c, nw;
+    uint32_t nd;
+    uint32_t recode[8];  // sum over w < nw-1 of 2^(c w + c - 1): added to the scalar, turns unsigned windows into signed digits
+};
+cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint32_t n_bases, int c, int nw, uint32_t *jac_out);
+cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t *table);
+cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half);
+cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
+                             const fixed_kparams_t &kp, uint32_t *out_jac);
+
 // which: 0 = raw IMAD.WIDE chains (128 multiply-adds / thread / iteration), 1 = Fp mul chain, 2 = Fp sqr chain (1 / thread / iteration)
 cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, int threads, int iters);
 

@@ -18,6 +18,13 @@ class CdpError(RuntimeError):
     pass
 
 
+class FixedSeg(ctypes.Structure):
+    """cdp_fixed_seg (include/cdp_msm.h)."""
+    _fields_ = [("base_off", c_uint32), ("scalars_off", c_uint32), ("n", c_uint32), ("sel_h", c_uint32), ("sel_val", c_uint32),
+                ("remap_from", c_uint32), ("remap_delta", c_uint32), ("extra_base", c_uint32), ("extra_scalar", c_uint32),
+                ("out_idx", c_uint32), ("reserved", c_uint32 * 2)]
+
+
 class _MsmDesc(ctypes.Structure):
     _fields_ = [("affine_pts", c_void_p), ("scalars", c_void_p), ("n", c_size_t)]
 
@@ -45,6 +52,12 @@ _SIGS = {
     "cdp_msm_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_sum_jacobian_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    "cdp_fixed_table_create": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_void_p)]),
+    "cdp_fixed_table_destroy": (None, [c_void_p, c_void_p]),
+    "cdp_fixed_table_bytes": (c_size_t, [c_void_p]),
+    "cdp_fixed_table_bases": (c_size_t, [c_void_p]),
+    "cdp_msm_fixed": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "cdp_msm_fixed_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "cdp_profile_enable": (c_int, [c_void_p, c_int]),
     "cdp_profile_reset": (c_int, [c_void_p]),
     "cdp_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(c_uint64)]),
@@ -212,7 +225,43 @@ class Engine:
             self._check(rc, "cdp_decompress_batch")
         return bytes(out)[:n * AFFINE_BYTES], list(st)[:n]
 
-    PROFILE_KINDS = ("msm_buckets", "msm_combine", "smul", "normalize", "other")
+    # ---- fixed-base MSM over a digit table of CRS points ------------------------------------------------
+    def fixed_table_create(self, points: bytes, window_bits: int = 16) -> "FixedTable":
+        return FixedTable(self, points, window_bits)
+
+    def msm_fixed(self, table: "FixedTable", base_off: int, scalars: bytes) -> bytes:
+        """`util::msm(&crs_points[base_off .. base_off + n], scalars)` through the digit table."""
+        if len(scalars) % SCALAR_BYTES:
+            raise ValueError("malformed input length")
+        n = len(scalars) // SCALAR_BYTES
+        out = (ctypes.c_uint8 * JACOBIAN_BYTES)()
+        self._check(self._lib.cdp_msm_fixed(self._h, table.handle, base_off, _buf(scalars) if n else None, n, out), "cdp_msm_fixed")
+        return bytes(out)
+
+    def msm_fixed_batch(self, table: "FixedTable", scalars: bytes, segs: list) -> list[bytes]:
+        """A batch of cdp_fixed_seg segments over one scalar array (host convenience over cdp_msm_fixed_batch_dev)."""
+        lib, h = self._lib, self._h
+        n_out = max(s.out_idx for s in segs) + 1
+        arr = (FixedSeg * len(segs))(*segs)
+        d_sc = lib.cdp_dev_alloc(h, max(1, len(scalars)))
+        d_sg = lib.cdp_dev_alloc(h, ctypes.sizeof(arr))
+        d_out = lib.cdp_dev_alloc(h, n_out * JACOBIAN_BYTES)
+        try:
+            sb = _buf(scalars)
+            self._check(lib.cdp_h2d(h, d_sc, sb, len(scalars)), "cdp_h2d")
+            self._check(lib.cdp_h2d(h, d_sg, arr, ctypes.sizeof(arr)), "cdp_h2d")
+            self.sync()
+            self._check(lib.cdp_msm_fixed_batch_dev(h, table.handle, d_sc, d_sg, len(segs), 0, d_out), "cdp_msm_fixed_batch_dev")
+            out = (ctypes.c_uint8 * (n_out * JACOBIAN_BYTES))()
+            self._check(lib.cdp_d2h(h, out, d_out, n_out * JACOBIAN_BYTES), "cdp_d2h")
+            self.sync()
+        finally:
+            for d in (d_sc, d_sg, d_out):
+                lib.cdp_dev_free(h, d)
+        raw = bytes(out)
+        return [raw[i * JACOBIAN_BYTES:(i + 1) * JACOBIAN_BYTES] for i in range(n_out)]
+
+    PROFILE_KINDS = ("msm_buckets", "msm_combine", "smul", "normalize", "other", "msm_fixed")
 
     def profile_enable(self, on: bool = True):
         self._check(self._lib.cdp_profile_enable(self._h, int(on)), "cdp_profile_enable")
@@ -222,9 +271,9 @@ class Engine:
 
     def profile_read(self) -> dict:
         """{kind: {"ms": device time, "launches": count, "units": work items}} accumulated since the last reset."""
-        ms = (ctypes.c_double * 5)()
-        ln = (c_uint64 * 5)()
-        un = (c_uint64 * 5)()
+        ms = (ctypes.c_double * len(self.PROFILE_KINDS))()
+        ln = (c_uint64 * len(self.PROFILE_KINDS))()
+        un = (c_uint64 * len(self.PROFILE_KINDS))()
         self._check(self._lib.cdp_profile_read(self._h, ms, ln, un), "cdp_profile_read")
         return {k: {"ms": ms[i], "launches": int(ln[i]), "units": int(un[i])} for i, k in enumerate(self.PROFILE_KINDS)}
 
@@ -232,3 +281,35 @@ class Engine:
         ms = c_float()
         self._check(self._lib.cdp_bench_kernel(self._h, which, blocks, threads, iters, ctypes.byref(ms)), "cdp_bench_kernel")
         return float(ms.value)
+
+
+class FixedTable:
+    """Device-resident digit table of fixed bases (``cdp_fixed_table``): d * 2^(c w) * B for every base, window and digit."""
+
+    def __init__(self, engine: Engine, points: bytes, window_bits: int = 16):
+        if len(points) % AFFINE_BYTES or not points:
+            raise ValueError("malformed input length")
+        self._engine = engine
+        h = c_void_p()
+        engine._check(engine.lib.cdp_fixed_table_create(engine.handle, _buf(points), len(points) // AFFINE_BYTES, window_bits, ctypes.byref(h)),
+                      "cdp_fixed_table_create")
+        self._h = h
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def nbytes(self) -> int:
+        return int(self._engine.lib.cdp_fixed_table_bytes(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._engine.handle:
+            self._engine.lib.cdp_fixed_table_destroy(self._engine.handle, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -128,9 +128,9 @@ class BatchProver:
         """Per-kernel device time summed over lanes (lanes overlap on the GPU, so the sum can exceed the wall time)."""
         tot = {k: {"ms": 0.0, "launches": 0, "units": 0} for k in Engine.PROFILE_KINDS}
         for c in self._lane_ctx:
-            ms = (c_double * 5)()
-            ln = (c_uint64 * 5)()
-            un = (c_uint64 * 5)()
+            ms = (c_double * len(Engine.PROFILE_KINDS))()
+            ln = (c_uint64 * len(Engine.PROFILE_KINDS))()
+            un = (c_uint64 * len(Engine.PROFILE_KINDS))()
             self.engine.lib.cdp_profile_read(c, ms, ln, un)
             for i, k in enumerate(Engine.PROFILE_KINDS):
                 tot[k]["ms"] += ms[i]

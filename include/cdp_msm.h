@@ -132,6 +132,36 @@ typedef struct {
 int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, const cdp_msm_seg *d_segs, size_t count,
                       size_t max_n, size_t total_pairs, uint8_t *d_out_jac);
 
+/* ------------------------------------------------------------------ fixed-base MSM (CRS bases)
+ * `util::msm` (/root/reference/src/util.rs:19-22) for call sites whose `points` are CRS elements (crs.vec_G, vec_H, H, G_t, G_u,
+ * /root/reference/src/crs.rs:19-34): they are identical for every proof, so the engine keeps a digit table of them in HBM
+ *   table[base][w][d] = d * 2^(c w) * B_base,  d = 1 .. 2^(c-1),  w < ceil(256 / c)        (c = 16: 50 MB per base)
+ * and one (scalar, base) pair costs ceil(256 / c) gathered mixed additions.  Bases must be prime-order points or infinity;
+ * scalars canonical (< r).  Results are the same group elements as cdp_msm over the same points.
+ * A table is immutable after creation and may be used from any context of the same device concurrently. */
+typedef struct cdp_fixed_table cdp_fixed_table;
+int cdp_fixed_table_create(cdp_ctx *ctx, const uint8_t *affine_pts /* host */, size_t n_bases, int window_bits /* 2..16, 0 = default 16 */,
+                           cdp_fixed_table **out);
+void cdp_fixed_table_destroy(cdp_ctx *ctx, cdp_fixed_table *t);
+size_t cdp_fixed_table_bytes(const cdp_fixed_table *t);
+size_t cdp_fixed_table_bases(const cdp_fixed_table *t);
+/* sum_{j < n} scalars[j] * B[base_off + j] with host scalars: the drop-in for one `util::msm(&crs.vec_G[a..b], scalars)`. */
+int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base_off, const uint8_t *scalars, size_t n, uint8_t out_jac[CDP_JACOBIAN_BYTES]);
+/* A batch of fixed-base MSMs, device scalars.  Segment = the pairs (d_scalars[scalars_off + j], B[base_off + j + gap(j)]) over the
+ * range positions j it selects:
+ *   sel_h == 0: j = 0 .. n-1;   sel_h = power of two h: the n positions with (j & h) == sel_val (sel_val is 0 or h) -- the L / R
+ *   half pattern of a vector folded down to 2h entries, which is how the IPA / SameMSM round MSMs over *folded* bases
+ *   (src/inner_product_argument.rs:158-161, src/same_multiscalar_argument.rs:107-112) are written over the original ones;
+ *   gap(j) = remap_delta for j >= remap_from (a base list that skips some table entries), else 0;
+ *   extra_base != 0 adds the pair (d_scalars[scalars_off + extra_scalar], B[extra_base - 1]) -- the `+ ip * H` term.
+ * The result of segment i goes to d_out_jac[out_idx]. */
+typedef struct {
+    uint32_t base_off, scalars_off, n, sel_h, sel_val, remap_from, remap_delta, extra_base, extra_scalar, out_idx;
+    uint32_t reserved[2];
+} cdp_fixed_seg;
+int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                            size_t total_pairs, uint8_t *d_out_jac);
+
 /* Batched scalar multiplication / fold over device-resident points.  For every job j and element e < elems_per_job:
  *   d_pts[out_off + e] = ( (add_off != CDP_NONE ? d_pts[add_off + e] : O)
  *                          + d_scalars[scalar_off + e * scalar_stride] * d_pts[src_off + e] ).into_affine()
@@ -164,14 +194,15 @@ int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_o
 /* ------------------------------------------------------------------ per-kernel profiling
  * When enabled, every kernel launch of the context is bracketed by CUDA events on the context's stream and the elapsed
  * device time is accumulated per kernel kind.  `units` accumulates the work items each launch processed: (scalar, point)
- * pairs for the MSM bucket kernel, MSMs for the combine kernel, elements for smul / normalise.  bench.py derives the
+ * pairs for the MSM bucket and fixed-base kernels, MSMs for the combine kernel, elements for smul / normalise.  bench.py derives the
  * roofline figures from these. */
 #define CDP_PROFILE_MSM_BUCKETS 0
 #define CDP_PROFILE_MSM_COMBINE 1
 #define CDP_PROFILE_SMUL 2
 #define CDP_PROFILE_NORMALIZE 3
 #define CDP_PROFILE_OTHER 4
-#define CDP_PROFILE_KINDS 5
+#define CDP_PROFILE_MSM_FIXED 5
+#define CDP_PROFILE_KINDS 6
 int cdp_profile_enable(cdp_ctx *ctx, int on);
 int cdp_profile_reset(cdp_ctx *ctx);
 int cdp_profile_read(cdp_ctx *ctx, double ms[CDP_PROFILE_KINDS], uint64_t launches[CDP_PROFILE_KINDS], uint64_t units[CDP_PROFILE_KINDS]);
