@@ -12,8 +12,14 @@
 //     scalars -- e.g. B = A + alpha*M + beta*sum(G) is msm(G|H|M, (a+beta)|r_a|alpha); L_C = msm(G_R, c_L) + ip*H is one
 //     msm with H as an extra base.  The host therefore never touches a curve point: it receives 48-byte encodings.
 //   * all prover randomness is drawn up front in the reference's order (the draws do not depend on the transcript).
-//   * per round: one batched MSM launch over all proofs, one normalise+compress, one D2H, host transcripts in
-//     parallel over proofs, one batched fold launch.
+//   * every MSM whose bases are CRS points goes through the fixed-base digit table (cdp_fixed_table, 12 GiB in HBM at
+//     ell = 252).  That includes the IPA round MSMs over G and G' = u o G and the SameMSM round MSMs over G_with_blinders:
+//     the round-k folded base is G^(k)_i = sum_{j = i mod n_k} w_k(j) G_j with w_k(j) = prod_l gamma_l^{bit_l(j)} (the
+//     identity the reference's verifier uses, src/inner_product_argument.rs:202-250), so msm(G^(k)_R, c_L) is an MSM over
+//     the ORIGINAL bases with scalars c_L[j mod h] * w_k(j) -- the G, G' and G_with_blinders vectors are never folded
+//     (3(n-1) + n of the reference's 5(n-1) + n fold scalar-muls disappear); only T and U, which are per-proof, are.
+//   * per round: one batched MSM launch (+ one fixed-base launch) over all proofs, one normalise+compress, one D2H,
+//     host transcripts in parallel over proofs, one batched fold launch for T and U.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -43,6 +49,9 @@ struct SubLaunch {
     size_t pairs_per_proof = 0;
     std::vector<cdp_msm_seg> segs;  // max_batch * K, proof-major
     cdp_msm_seg *d_segs = nullptr;
+    bool fixed = false;               // segments over the CRS digit table
+    std::vector<cdp_fixed_seg> fsegs;
+    cdp_fixed_seg *d_fsegs = nullptr;
 };
 struct MsmStage {
     size_t scalars_per_proof = 0;
@@ -61,6 +70,7 @@ struct FoldStage {
 struct ProofState {
     std::unique_ptr<Transcript> tr;
     std::vector<Fr> vec_a, a_perm, factors, c, d, r_c, r_d, u, x, r_sm;
+    std::vector<Fr> wG, wGp, wS;  // fold weights of the original bases: G (gamma), G' (u, gamma^-1), G_with_blinders (gamma)
     Fr a_bl[2], c_bl[4], r_t, r_u, r_a, r_b, r_k, k, m_bl[4], b_bl[4], rb_alpha[4];
     Fr alpha_sp, beta_sp, gprod_result, alpha_g, beta_g, r_p, z, alpha_i, beta_i;
     Fr z_k, z_t, z_u, c_final, d_final, x_final;
@@ -85,6 +95,7 @@ enum XSlot { X_A = 0, X_M, X_GSUM, X_R, X_H1, X_S, X_H2, X_A2, X_GT, X_GU, X_B, 
 
 struct Lane {
     cdp_ctx *ctx = nullptr;
+    const cdp_fixed_table *table = nullptr;  // digit table of the CRS points (shared by all lanes of a prover)
     size_t ell = 0, n = 0, m = 0, max_batch = 0;
     int threads = 1;
     std::string err = "ok";
@@ -93,9 +104,10 @@ struct Lane {
 
     // device point array: [CRS block | per-proof working blocks]
     size_t crs_n = 0, PW = 0;
-    size_t o_GHM = 0, o_Gi = 0, o_Gp = 0, o_Gs = 0, o_T = 0, o_U = 0, o_R = 0, o_S = 0, o_X = 0;
-    size_t reg1 = 0, reg2 = 0;  // affine outputs of stage 1 / stage 2, proof-major (index pr * K + k), kept for the next stage
+    size_t o_T = 0, o_U = 0, o_R = 0, o_S = 0, o_X = 0;
+    size_t reg1 = 0, reg2 = 0;  // affine outputs of stage 1 / stage 2 (in launch order), kept for the next stage
     uint32_t *d_x1src = nullptr, *d_x1dst = nullptr, *d_x2src = nullptr, *d_x2dst = nullptr;
+    size_t xtab_B = 0;          // batch size the x1/x2 gather tables were built for
     uint8_t *d_pts = nullptr;
     uint8_t *d_in = nullptr;       // staging for the instance vectors of a batch (R,S,T,U: 4*ell per proof) + M affine
     uint8_t *d_Mjac = nullptr;
@@ -112,8 +124,7 @@ struct Lane {
 
     MsmStage st1, st2, st3, st4;
     std::vector<MsmStage> st_ipa, st_sm;
-    std::vector<FoldStage> f_ipa, f_sm;
-    FoldStage f_gp;  // G' = u o (G|H)
+    std::vector<FoldStage> f_sm;  // T, U folds
 
     std::vector<ProofState> ps;
 };
@@ -150,25 +161,50 @@ void put_fr(uint8_t *dst, const Fr &x) { x.to_bytes(dst); }
 
 // ---- stage table construction --------------------------------------------------------------------------------
 struct SegSpec {
-    size_t pts_rel;    // offset inside the proof block, or absolute when `absolute`
-    bool absolute;
-    size_t scal_rel;   // offset inside the proof's scalar block
-    size_t n;
-    long extra_abs;    // absolute index of the extra base, -1 none
+    size_t pts_rel = 0;    // variable-base: offset inside the proof block, or absolute when `absolute`
+    bool absolute = false;
+    size_t scal_rel = 0;   // offset inside the proof's scalar block
+    size_t n = 0;
+    long extra_abs = -1;   // variable-base: absolute index of the extra base, -1 none
+    // fixed-base (CRS digit table): pts_rel = first table base of the range; see cdp_fixed_seg for the rest
+    bool fixed = false;
+    size_t sel_h = 0, sel_val = 0, remap_from = 0xFFFFFFFFu, remap_delta = 0;
+    long fextra_base = -1;
+    size_t fextra_scalar = 0;
 };
+SegSpec fix_seg(size_t base_off, size_t scal_rel, size_t n) {
+    SegSpec s;
+    s.pts_rel = base_off; s.scal_rel = scal_rel; s.n = n; s.fixed = true;
+    return s;
+}
+// the positions j of a 0..2*cnt-1 range (every other run of h) with (j & h) == val
+SegSpec fix_half(size_t base_off, size_t scal_rel, size_t cnt, size_t h, size_t val) {
+    SegSpec s = fix_seg(base_off, scal_rel, cnt);
+    s.sel_h = h; s.sel_val = val;
+    return s;
+}
 void build_stage(Lane *p, MsmStage &st, const std::vector<SegSpec> &specs, size_t scalars_pp) {
     st.scalars_per_proof = scalars_pp;
-    // two size classes keep the tiny (1-3 point) MSMs out of the big-CTA launch
-    auto eff = [](const SegSpec &s) { return s.n + (s.extra_abs >= 0 ? 1 : 0); };
+    // variable-base: two size classes keep the tiny (1-3 point) MSMs out of the big-CTA launch; fixed-base: one more sub-launch
+    auto eff = [](const SegSpec &s) { return s.n + ((s.fixed ? s.fextra_base : s.extra_abs) >= 0 ? 1 : 0); };
     size_t big = 0;
-    for (auto &s : specs) big = std::max(big, eff(s));
+    bool any_var = false, any_fixed = false;
+    for (auto &s : specs) {
+        if (s.fixed) { any_fixed = true; continue; }
+        any_var = true;
+        big = std::max(big, eff(s));
+    }
     std::vector<int> cls(specs.size(), 0);
     bool split = false;
     if (big >= 12) {
         for (size_t i = 0; i < specs.size(); i++)
-            if (eff(specs[i]) * 8 <= big && eff(specs[i]) < 12) { cls[i] = 1; split = true; }
+            if (!specs[i].fixed && eff(specs[i]) * 8 <= big && eff(specs[i]) < 12) { cls[i] = 1; split = true; }
     }
-    st.subs.assign(split ? 2 : 1, SubLaunch());
+    const int n_var = any_var ? (split ? 2 : 1) : 0;
+    for (size_t i = 0; i < specs.size(); i++)
+        if (specs[i].fixed) cls[i] = n_var;
+    st.subs.assign(n_var + (any_fixed ? 1 : 0), SubLaunch());
+    if (any_fixed) st.subs[n_var].fixed = true;
     st.where.resize(specs.size());
     for (size_t i = 0; i < specs.size(); i++) {
         SubLaunch &sl = st.subs[cls[i]];
@@ -179,16 +215,32 @@ void build_stage(Lane *p, MsmStage &st, const std::vector<SegSpec> &specs, size_
     }
     for (size_t c = 0; c < st.subs.size(); c++) {
         SubLaunch &sl = st.subs[c];
-        sl.segs.resize(p->max_batch * sl.K);
+        if (sl.fixed) sl.fsegs.resize(p->max_batch * sl.K);
+        else sl.segs.resize(p->max_batch * sl.K);
         for (size_t pr = 0; pr < p->max_batch; pr++) {
             size_t bp = p->crs_n + pr * p->PW;
             for (size_t i = 0; i < specs.size(); i++) {
                 if (cls[i] != (int)c) continue;
-                cdp_msm_seg &sg = sl.segs[pr * sl.K + st.where[i].second];
-                sg.pts_off = (uint32_t)(specs[i].absolute ? specs[i].pts_rel : bp + specs[i].pts_rel);
-                sg.scalars_off = (uint32_t)(pr * scalars_pp + specs[i].scal_rel);
-                sg.n = (uint32_t)specs[i].n;
-                sg.extra = specs[i].extra_abs >= 0 ? (uint32_t)(specs[i].extra_abs + 1) : 0;
+                const SegSpec &sp = specs[i];
+                const size_t slot = pr * sl.K + st.where[i].second;
+                if (sl.fixed) {
+                    cdp_fixed_seg &fs = sl.fsegs[slot];
+                    memset(&fs, 0, sizeof fs);
+                    fs.base_off = (uint32_t)sp.pts_rel;
+                    fs.scalars_off = (uint32_t)(pr * scalars_pp + sp.scal_rel);
+                    fs.n = (uint32_t)sp.n;
+                    fs.sel_h = (uint32_t)sp.sel_h; fs.sel_val = (uint32_t)sp.sel_val;
+                    fs.remap_from = (uint32_t)sp.remap_from; fs.remap_delta = (uint32_t)sp.remap_delta;
+                    fs.extra_base = sp.fextra_base >= 0 ? (uint32_t)(sp.fextra_base + 1) : 0;
+                    fs.extra_scalar = (uint32_t)sp.fextra_scalar;
+                    fs.out_idx = (uint32_t)slot;
+                } else {
+                    cdp_msm_seg &sg = sl.segs[slot];
+                    sg.pts_off = (uint32_t)(sp.absolute ? sp.pts_rel : bp + sp.pts_rel);
+                    sg.scalars_off = (uint32_t)(pr * scalars_pp + sp.scal_rel);
+                    sg.n = (uint32_t)sp.n;
+                    sg.extra = sp.extra_abs >= 0 ? (uint32_t)(sp.extra_abs + 1) : 0;
+                }
             }
         }
     }
@@ -222,10 +274,13 @@ void build_fold(Lane *p, FoldStage &fs, const std::vector<JobSpec> &specs, size_
 int upload_tables(Lane *p) {
     auto up_stage = [&](MsmStage &st) -> int {
         for (auto &sl : st.subs) {
-            size_t bytes = sl.segs.size() * sizeof(cdp_msm_seg);
-            sl.d_segs = (cdp_msm_seg *)cdp_dev_alloc(p->ctx, bytes);
-            if (!sl.d_segs) return CDP_ERR_CUDA;
-            int rc = cdp_h2d(p->ctx, sl.d_segs, sl.segs.data(), bytes);
+            const void *src = sl.fixed ? (const void *)sl.fsegs.data() : (const void *)sl.segs.data();
+            size_t bytes = sl.fixed ? sl.fsegs.size() * sizeof(cdp_fixed_seg) : sl.segs.size() * sizeof(cdp_msm_seg);
+            void *d = cdp_dev_alloc(p->ctx, bytes);
+            if (!d) return CDP_ERR_CUDA;
+            if (sl.fixed) sl.d_fsegs = (cdp_fixed_seg *)d;
+            else sl.d_segs = (cdp_msm_seg *)d;
+            int rc = cdp_h2d(p->ctx, d, src, bytes);
             if (rc) return rc;
         }
         return CDP_OK;
@@ -239,9 +294,7 @@ int upload_tables(Lane *p) {
     PTRY(up_stage(p->st1)); PTRY(up_stage(p->st2)); PTRY(up_stage(p->st3)); PTRY(up_stage(p->st4));
     for (auto &s : p->st_ipa) PTRY(up_stage(s));
     for (auto &s : p->st_sm) PTRY(up_stage(s));
-    for (auto &f : p->f_ipa) PTRY(up_fold(f));
     for (auto &f : p->f_sm) PTRY(up_fold(f));
-    PTRY(up_fold(p->f_gp));
     PTRY(cdp_sync(p->ctx));  // the host vectors are pageable: make sure the copies are done before they can move
     return CDP_OK;
 }
@@ -254,7 +307,8 @@ int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_cop
     p->h2d_bytes += B * st.scalars_per_proof * 32;
     size_t out_off = 0;
     for (auto &sl : st.subs) {
-        PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
+        if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
+        else PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
         out_off += B * sl.K;
     }
     PTRY(cdp_normalize_dev(p->ctx, p->d_jac, out_off, st.aff_region != (size_t)-1 ? p->d_pts + st.aff_region * 96 : nullptr, p->d_comp));
@@ -274,6 +328,12 @@ const uint8_t *stage_out(const Lane *p, const MsmStage &st, size_t B, size_t pr,
     const SubLaunch &sl = st.subs[st.where[q].first];
     return p->h_comp + 48 * (base + pr * sl.K + st.where[q].second);
 }
+// index of output q of proof pr among the stage's outputs (launch order) for a batch of B
+size_t stage_out_index(const MsmStage &st, size_t B, size_t pr, size_t q) {
+    size_t base = 0;
+    for (int s = 0; s < st.where[q].first; s++) base += B * st.subs[s].K;
+    return base + pr * st.subs[st.where[q].first].K + st.where[q].second;
+}
 int run_fold_stage(Lane *p, FoldStage &fs, size_t B) {
     PTRY(cdp_h2d(p->ctx, p->d_fscal, p->h_fscal, B * fs.scalars_per_proof * 32));
     p->h2d_bytes += B * fs.scalars_per_proof * 32;
@@ -292,13 +352,11 @@ extern "C" size_t cdp_proof_size(size_t ell) {
 static void lane_destroy(Lane *p) {
     if (!p) return;
     cdp_ctx *c = p->ctx;
-    auto free_stage = [&](MsmStage &st) { for (auto &sl : st.subs) cdp_dev_free(c, sl.d_segs); };
+    auto free_stage = [&](MsmStage &st) { for (auto &sl : st.subs) { cdp_dev_free(c, sl.d_segs); cdp_dev_free(c, sl.d_fsegs); } };
     free_stage(p->st1); free_stage(p->st2); free_stage(p->st3); free_stage(p->st4);
     for (auto &s : p->st_ipa) free_stage(s);
     for (auto &s : p->st_sm) free_stage(s);
-    for (auto &f : p->f_ipa) cdp_dev_free(c, f.d_jobs);
     for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
-    cdp_dev_free(c, p->f_gp.d_jobs);
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
                     (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp})
         cdp_dev_free(c, d);
@@ -306,43 +364,47 @@ static void lane_destroy(Lane *p) {
     delete p;
 }
 
-static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
-    if (!out || !ctx || !crs_points || max_batch == 0 || ell < 4) return CDP_ERR_INVALID_ARG;
+static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t ell, const uint8_t *crs_points, size_t max_batch,
+                       int host_threads) {
+    if (!out || !ctx || !table || !crs_points || max_batch == 0 || ell < 4) return CDP_ERR_INVALID_ARG;
     *out = nullptr;
     size_t n = ell + NBL, m = 0;
     while (((size_t)1 << m) < n) m++;
     if (((size_t)1 << m) != n) return CDP_ERR_INVALID_ARG;  // n must be a power of two (src/inner_product_argument.rs:116)
     if (n + 1 > 2048) return CDP_ERR_TOO_LARGE;
     Lane *p = new Lane();
-    p->ctx = ctx; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch;
+    p->ctx = ctx; p->table = table; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch;
     p->threads = std::max(1, host_threads);
     // ---- device point layout
-    const size_t cG = 0, cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;  // CRS block: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec)
-    (void)cG;
+    // CRS block (also the base order of the digit table, whose first ell + 7 entries are crs_points): G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec)
+    const size_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
     p->crs_n = n + 5;
-    p->o_GHM = 0; p->o_Gi = n + 1; p->o_Gp = 2 * n + 1; p->o_Gs = 3 * n + 1; p->o_T = 4 * n + 1; p->o_U = 5 * n + 1;
-    p->o_R = 6 * n + 1; p->o_S = 6 * n + 1 + ell; p->o_X = 6 * n + 1 + 2 * ell;
-    p->PW = 6 * n + 1 + 2 * ell + X_COUNT;
+    // per-proof block: T_with_blinders | U_with_blinders (folded in place) | vec_R | vec_S | X (gathered short-MSM inputs)
+    p->o_T = 0; p->o_U = n; p->o_R = 2 * n; p->o_S = 2 * n + ell; p->o_X = 2 * n + 2 * ell;
+    p->PW = 2 * n + 2 * ell + X_COUNT;
     p->reg1 = p->crs_n + max_batch * p->PW;
     p->reg2 = p->reg1 + max_batch * S1_COUNT;
     size_t total_pts = p->reg2 + max_batch * S2_COUNT;
     if (total_pts >= ((size_t)1 << 31)) { delete p; return CDP_ERR_TOO_LARGE; }
+    // G_with_blinders = G | H_0 | H_1 | G_t | G_u (curdleproofs.rs:134-140) in table bases: positions >= ell + 2 skip H_2, H_3, H
+    const size_t gs_from = ell + 2, gs_delta = cGt - (ell + 2);
 
     // ---- stage tables
     {   // stage 1: everything that depends only on vec_a and the prover's own randomness
         // scalars: a_perm|r_a' (n) | vec_a (ell) | r_sm (n) | r_t | r_u | r_a | r_b
         const size_t sa = n, sR = n + ell, sx = 2 * n + ell;
         std::vector<SegSpec> v(S1_COUNT);
-        v[S1_A] = {p->o_GHM, false, 0, n, -1};         // A = msm(G|Hvec, a_perm | r_a')            curdleproofs.rs:93
+        v[S1_A] = fix_seg(0, 0, n);                    // A = msm(G|Hvec, a_perm | r_a')            curdleproofs.rs:93
         v[S1_R] = {p->o_R, false, sa, ell, -1};        // R = msm(vec_R, a)                         :112
         v[S1_S] = {p->o_S, false, sa, ell, -1};        // S = msm(vec_S, a)                         :113
-        v[S1_BA] = {p->o_Gs, false, sR, n, -1};        // B_a, B_t, B_u                              same_multiscalar_argument.rs:80-82
-        v[S1_BT] = {p->o_T, false, sR, n, -1};
+        v[S1_BA] = fix_seg(0, sR, n);                  // B_a = msm(G_with_blinders, r)             same_multiscalar_argument.rs:80
+        v[S1_BA].remap_from = gs_from; v[S1_BA].remap_delta = gs_delta;
+        v[S1_BT] = {p->o_T, false, sR, n, -1};         // B_t, B_u                                  :81-82
         v[S1_BU] = {p->o_U, false, sR, n, -1};
-        v[S1_T1] = {cGt, true, sx, 1, -1};             // cm_T.T_1 = r_t G_t                        :115 / commitments.rs:50
-        v[S1_U1] = {cGu, true, sx + 1, 1, -1};         // cm_U.T_1 = r_u G_u                        :116
-        v[S1_A1] = {cGt, true, sx + 2, 1, -1};         // cm_A.T_1 = r_a G_t                        same_scalar_argument.rs:60
-        v[S1_B1] = {cGu, true, sx + 3, 1, -1};         // cm_B.T_1 = r_b G_u                        :61
+        v[S1_T1] = fix_seg(cGt, sx, 1);                // cm_T.T_1 = r_t G_t                        :115 / commitments.rs:50
+        v[S1_U1] = fix_seg(cGu, sx + 1, 1);            // cm_U.T_1 = r_u G_u                        :116
+        v[S1_A1] = fix_seg(cGt, sx + 2, 1);            // cm_A.T_1 = r_a G_t                        same_scalar_argument.rs:60
+        v[S1_B1] = fix_seg(cGu, sx + 3, 1);            // cm_B.T_1 = r_b G_u                        :61
         build_stage(p, p->st1, v, sx + 4);
         p->st1.aff_region = p->reg1;
     }
@@ -357,30 +419,28 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
         build_stage(p, p->st2, v, 14);
         p->st2.aff_region = p->reg2;
     }
-    build_stage(p, p->st3, {{p->o_GHM, false, 0, n, -1}}, n);                      // C     grand_product_argument.rs:76
+    build_stage(p, p->st3, {fix_seg(0, 0, n)}, n);                                 // C     grand_product_argument.rs:76
     build_stage(p, p->st4, {{p->o_X + X_B, false, 0, 3, -1},                       // D = B - beta^-1 sum(G) + alpha sum(Hvec)   grand_product_argument.rs:132
-                            {p->o_GHM, false, 3, n, -1},                           // B_c   inner_product_argument.rs:126
-                            {p->o_GHM, false, 3 + n, n, -1}},                      // B_d = msm(G', r_d) = msm(G|H, r_d o u)   :127
+                            fix_seg(0, 3, n),                                      // B_c   inner_product_argument.rs:126
+                            fix_seg(0, 3 + n, n)},                                 // B_d = msm(G', r_d) = msm(G|Hvec, r_d o u)   :127
                 2 * n + 3);
-    build_fold(p, p->f_gp, {{p->o_GHM, 0, p->o_Gp, false, 0, 1}}, n, n);           // G' = u o (G|Hvec)   grand_product_argument.rs:92-102
-    p->st_ipa.resize(m); p->f_ipa.resize(m); p->st_sm.resize(m); p->f_sm.resize(m);
+    p->st_ipa.resize(m); p->st_sm.resize(m); p->f_sm.resize(m);
     for (size_t k = 0; k < m; k++) {
         size_t h = n >> (k + 1);
-        // inner_product_argument.rs:158-161; scalars: c_L | ipL | d_R | c_R | ipR | d_L
-        build_stage(p, p->st_ipa[k], {{p->o_Gi + h, false, 0, h, (long)cH},               // L_C = msm(G_R, c_L) + <c_L,d_R> H
-                                      {p->o_Gp, false, h + 1, h, -1},                      // L_D = msm(G'_L, d_R)
-                                      {p->o_Gi, false, 2 * h + 1, h, (long)cH},            // R_C = msm(G_L, c_R) + <c_R,d_L> H
-                                      {p->o_Gp + h, false, 3 * h + 2, h, -1}},             // R_D = msm(G'_R, d_L)
-                    4 * h + 2);
-        build_fold(p, p->f_ipa[k], {{p->o_Gi + h, p->o_Gi, p->o_Gi, true, 0, 0},           // G_L += gamma G_R       :177
-                                    {p->o_Gp + h, p->o_Gp, p->o_Gp, true, 1, 0}},          // G'_L += gamma^-1 G'_R  :178
-                   h, 2);
-        // same_multiscalar_argument.rs:107-112; scalars: x_L | x_R
-        build_stage(p, p->st_sm[k], {{p->o_Gs + h, false, 0, h, -1}, {p->o_T + h, false, 0, h, -1}, {p->o_U + h, false, 0, h, -1},
-                                     {p->o_Gs, false, h, h, -1}, {p->o_T, false, h, h, -1}, {p->o_U, false, h, h, -1}},
-                    2 * h);
-        build_fold(p, p->f_sm[k], {{p->o_T + h, p->o_T, p->o_T, true, 0, 0}, {p->o_U + h, p->o_U, p->o_U, true, 0, 0},
-                                   {p->o_Gs + h, p->o_Gs, p->o_Gs, true, 0, 0}},           // :128-130
+        // inner_product_argument.rs:158-161 over the original bases; scalars: cw (n) | ipL | ipR | dw (n)
+        //   cw[j] = w(j) c[j mod h] (bit h of j set) or w(j) c[h + j mod h] (clear);  dw[j] = w'(j) d[h + j mod h] (clear) or w'(j) d[j mod h] (set)
+        SegSpec LC = fix_half(0, 0, n / 2, h, h), LD = fix_half(0, n + 2, n / 2, h, 0), RC = fix_half(0, 0, n / 2, h, 0),
+                RD = fix_half(0, n + 2, n / 2, h, h);
+        LC.fextra_base = (long)cH; LC.fextra_scalar = n;          // L_C = msm(G_R, c_L) + <c_L,d_R> H
+        RC.fextra_base = (long)cH; RC.fextra_scalar = n + 1;      // R_C = msm(G_L, c_R) + <c_R,d_L> H
+        build_stage(p, p->st_ipa[k], {LC, LD, RC, RD}, 2 * n + 2);
+        // same_multiscalar_argument.rs:107-112; scalars: xw (n, G_with_blinders over the original bases) | x_L | x_R (folded T, U)
+        SegSpec LA = fix_half(0, 0, n / 2, h, h), RA = fix_half(0, 0, n / 2, h, 0);
+        LA.remap_from = RA.remap_from = gs_from; LA.remap_delta = RA.remap_delta = gs_delta;
+        build_stage(p, p->st_sm[k], {LA, {p->o_T + h, false, n, h, -1}, {p->o_U + h, false, n, h, -1},
+                                     RA, {p->o_T, false, n + h, h, -1}, {p->o_U, false, n + h, h, -1}},
+                    n + 2 * h);
+        build_fold(p, p->f_sm[k], {{p->o_T + h, p->o_T, p->o_T, true, 0, 0}, {p->o_U + h, p->o_U, p->o_U, true, 0, 0}},   // :128-129
                    h, 1);
     }
 
@@ -401,16 +461,11 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
     p->d_jac = (uint8_t *)dalloc(max_batch * p->max_out_pp * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * max_out * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * max_out * 48);
-    // gather tables.  From the CRS block: G|Hvec -> o_GHM and o_Gi ; G|H0|H1|G_t|G_u -> o_Gs ; T/U blinder slots (H) ;
+    // gather tables.  From the CRS block: the blinder slots of T / U (H) and the constant entries of the X block
     std::vector<uint32_t> gsrc, gdst, isrc, idst, cidx;
     const uint32_t INF_SRC = (uint32_t)(total_pts);  // one all-zero point appended after the array (the point at infinity)
     for (size_t pr = 0; pr < max_batch; pr++) {
         size_t bp = p->crs_n + pr * p->PW;
-        for (size_t i = 0; i < n; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + p->o_GHM + i)); }
-        for (size_t i = 0; i < n; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + p->o_Gi + i)); }
-        for (size_t i = 0; i < ell + 2; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + p->o_Gs + i)); }
-        gsrc.push_back((uint32_t)cGt); gdst.push_back((uint32_t)(bp + p->o_Gs + ell + 2));
-        gsrc.push_back((uint32_t)cGu); gdst.push_back((uint32_t)(bp + p->o_Gs + ell + 3));
         // vec_T_with_blinders = T | inf inf H inf ; vec_U_with_blinders = U | inf inf inf H   (curdleproofs.rs:142-155)
         const uint32_t tb[4] = {INF_SRC, INF_SRC, (uint32_t)cH, INF_SRC}, ub[4] = {INF_SRC, INF_SRC, INF_SRC, (uint32_t)cH};
         for (int i = 0; i < 4; i++) {
@@ -427,22 +482,12 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
         const size_t dsts[4] = {p->o_R, p->o_S, p->o_T, p->o_U};
         for (int v = 0; v < 4; v++)
             for (size_t i = 0; i < ell; i++) { isrc.push_back((uint32_t)(ib + v * ell + i)); idst.push_back((uint32_t)(bp + dsts[v] + i)); }
-        isrc.push_back((uint32_t)(max_batch * 4 * ell + pr)); idst.push_back((uint32_t)(bp + p->o_GHM + n));  // M behind G|Hvec (unused since stage 2 became short MSMs)
         isrc.push_back((uint32_t)(max_batch * 4 * ell + pr)); idst.push_back((uint32_t)(bp + p->o_X + X_M));
         if (pr == 0) p->i_count_per_proof = isrc.size();
     }
-    // after stage 1: A, R, S (affine) into the X block; after stage 2: B
-    std::vector<uint32_t> x1s, x1d, x2s, x2d;
-    for (size_t pr = 0; pr < max_batch; pr++) {
-        // stored outputs sit proof-major inside sub-launch 0 of their stage (index pr * K + k, independent of the batch size)
-        size_t bp = p->crs_n + pr * p->PW, r1 = p->reg1 + pr * p->st1.subs[0].K, r2 = p->reg2 + pr * p->st2.subs[0].K;
-        auto k1 = [&](int q) { return (size_t)p->st1.where[q].second; };
-        const std::pair<int, size_t> e1[] = {{X_A, r1 + k1(S1_A)}, {X_R, r1 + k1(S1_R)}, {X_S, r1 + k1(S1_S)}, {X_A2, r1 + k1(S1_A)}};
-        for (auto &e : e1) { x1s.push_back((uint32_t)e.second); x1d.push_back((uint32_t)(bp + p->o_X + e.first)); }
-        x2s.push_back((uint32_t)(r2 + p->st2.where[S2_B].second)); x2d.push_back((uint32_t)(bp + p->o_X + X_B));
-    }
-    p->d_x1src = (uint32_t *)dalloc(x1s.size() * 4); p->d_x1dst = (uint32_t *)dalloc(x1d.size() * 4);
-    p->d_x2src = (uint32_t *)dalloc(x2s.size() * 4); p->d_x2dst = (uint32_t *)dalloc(x2d.size() * 4);
+    // after stage 1: A, R, S (affine) into the X block; after stage 2: B.  The source indices depend on the batch size: built per call.
+    p->d_x1src = (uint32_t *)dalloc(max_batch * 4 * 4); p->d_x1dst = (uint32_t *)dalloc(max_batch * 4 * 4);
+    p->d_x2src = (uint32_t *)dalloc(max_batch * 4); p->d_x2dst = (uint32_t *)dalloc(max_batch * 4);
     p->d_gsrc = (uint32_t *)dalloc(gsrc.size() * 4); p->d_gdst = (uint32_t *)dalloc(gdst.size() * 4);
     p->d_isrc = (uint32_t *)dalloc(isrc.size() * 4); p->d_idst = (uint32_t *)dalloc(idst.size() * 4);
     if (!ok) { p->err = "allocation failed"; lane_destroy(p); return CDP_ERR_CUDA; }
@@ -460,10 +505,6 @@ static int lane_create(Lane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_
         rc |= cdp_h2d(ctx, p->d_pts + cGsum * 96, aff.data(), 2 * 96);
         rc |= cdp_sync(ctx);
     }
-    rc |= cdp_h2d(ctx, p->d_x1src, x1s.data(), x1s.size() * 4);
-    rc |= cdp_h2d(ctx, p->d_x1dst, x1d.data(), x1d.size() * 4);
-    rc |= cdp_h2d(ctx, p->d_x2src, x2s.data(), x2s.size() * 4);
-    rc |= cdp_h2d(ctx, p->d_x2dst, x2d.data(), x2d.size() * 4);
     rc |= cdp_h2d(ctx, p->d_gsrc, gsrc.data(), gsrc.size() * 4);
     rc |= cdp_h2d(ctx, p->d_gdst, gdst.data(), gdst.size() * 4);
     rc |= cdp_h2d(ctx, p->d_isrc, isrc.data(), isrc.size() * 4);
@@ -509,6 +550,23 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         p->h2d_bytes += B * (4 * ell * 96 + 144);
         PTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));  // M.into_affine()
         p->staged_batch = B;
+    }
+    if (p->xtab_B != B) {  // where stage 1 / stage 2 leave A, R, S / B (affine) depends on the batch size
+        std::vector<uint32_t> x1s, x1d, x2s, x2d;
+        for (size_t pr = 0; pr < B; pr++) {
+            size_t bp = p->crs_n + pr * p->PW;
+            const std::pair<int, int> e1[] = {{X_A, S1_A}, {X_R, S1_R}, {X_S, S1_S}, {X_A2, S1_A}};
+            for (auto &e : e1) {
+                x1s.push_back((uint32_t)(p->reg1 + stage_out_index(p->st1, B, pr, e.second)));
+                x1d.push_back((uint32_t)(bp + p->o_X + e.first));
+            }
+            x2s.push_back((uint32_t)(p->reg2 + stage_out_index(p->st2, B, pr, S2_B)));
+            x2d.push_back((uint32_t)(bp + p->o_X + X_B));
+        }
+        PTRY(cdp_h2d(p->ctx, p->d_x1src, x1s.data(), x1s.size() * 4)); PTRY(cdp_h2d(p->ctx, p->d_x1dst, x1d.data(), x1d.size() * 4));
+        PTRY(cdp_h2d(p->ctx, p->d_x2src, x2s.data(), x2s.size() * 4)); PTRY(cdp_h2d(p->ctx, p->d_x2dst, x2d.data(), x2d.size() * 4));
+        PTRY(cdp_sync(p->ctx));  // pageable sources
+        p->xtab_B = B;
     }
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_gsrc, p->d_gdst, B * p->g_count_per_proof));
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_count_per_proof));
@@ -669,13 +727,10 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         put_fr(sc, Fr::one()); put_fr(sc + 32, beta_inv.neg()); put_fr(sc + 64, s.alpha_g);
         for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + i), s.r_c[i]);                    // B_c = msm(G|Hvec, r_c)
         for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + n + i), s.r_d[i] * s.u[i]);       // B_d = msm(G', r_d)
-        uint8_t *fs = p->h_fscal + pr * n * 32;                                                // G'_i = u_i (G|Hvec)_i
-        for (size_t i = 0; i < n; i++) put_fr(fs + 32 * i, s.u[i]);
     });
     t_host += now_ms() - t0;
     t0 = now_ms();
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_x2src, p->d_x2dst, B));  // B (affine, from stage 2) -> X block
-    if (int rc = run_fold_stage(p, p->f_gp, B)) return rc;
     t_copy += now_ms() - t0;
     if (int rc = run_msm_stage(p, p->st4, B, t_wait, t_copy)) return rc;
 
@@ -697,6 +752,9 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             s.c[i] = s.r_c[i] + s.alpha_i * s.c[i];
             s.d[i] = s.r_d[i] + s.alpha_i * s.d[i];
         }
+        // fold weights of the original bases: G^(k)_i = sum_{j = i mod n_k} wG[j] G_j,  G'^(k)_i = sum wGp[j] G_j  (G' = u o G, :92-102 of gprod)
+        s.wG.assign(n, Fr::one());
+        s.wGp = s.u;
     });
     t_host += now_ms() - t0;
     for (size_t k = 0; k < m; k++) {
@@ -707,13 +765,15 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             ProofState &s = p->ps[pr];
             const Fr *cL = s.c.data(), *cR = s.c.data() + h, *dL = s.d.data(), *dR = s.d.data() + h;
             uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
-            size_t o = 0;
-            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), cL[i]);
-            put_fr(sc + 32 * (o++), s.beta_i * inner_product(cL, dR, h));   // H = beta crs_H ; L_C += <c_L,d_R> H
-            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), dR[i]);
-            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), cR[i]);
-            put_fr(sc + 32 * (o++), s.beta_i * inner_product(cR, dL, h));
-            for (size_t i = 0; i < h; i++) put_fr(sc + 32 * (o++), dL[i]);
+            // msm(G_R, c_L), msm(G_L, c_R), msm(G'_L, d_R), msm(G'_R, d_L) (:158-161) over the original bases
+            for (size_t j = 0; j < n; j++) {
+                const size_t i = j & (h - 1);
+                const bool hi = (j & h) != 0;
+                put_fr(sc + 32 * j, s.wG[j] * (hi ? cL[i] : cR[i]));
+                put_fr(sc + 32 * (n + 2 + j), s.wGp[j] * (hi ? dL[i] : dR[i]));
+            }
+            put_fr(sc + 32 * n, s.beta_i * inner_product(cL, dR, h));        // H = beta crs_H ; L_C += <c_L,d_R> H
+            put_fr(sc + 32 * (n + 1), s.beta_i * inner_product(cR, dL, h));  //                   R_C += <c_R,d_L> H
         });
         t_host += now_ms() - t0;
         if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
@@ -730,15 +790,12 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
                 s.c[i] += gamma_inv * s.c[h + i];
                 s.d[i] += gamma * s.d[h + i];
             }
-            put_fr(p->h_fscal + (pr * 2) * 32, gamma);
-            put_fr(p->h_fscal + (pr * 2 + 1) * 32, gamma_inv);
+            // G_L += gamma G_R, G'_L += gamma^-1 G'_R (:177-178), as weights on the original bases
+            if (h > 1)
+                for (size_t j = 0; j < n; j++)
+                    if (j & h) { s.wG[j] *= gamma; s.wGp[j] *= gamma_inv; }
         });
         t_host += now_ms() - t0;
-        if (h > 1) {  // after the last round the folded bases are never used again
-            t0 = now_ms();
-            if (int rc = run_fold_stage(p, p->f_ipa[k], B)) return rc;
-            t_copy += now_ms() - t0;
-        }
     }
 
     // ---- same_scalar (same_scalar_argument.rs:64-75) and same_msm step 1 (same_multiscalar_argument.rs:84-91)
@@ -767,6 +824,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         for (size_t i = 0; i < ell; i++) s.x[i] = s.r_sm[i] + a_sm * s.a_perm[i];
         const Fr tail[4] = {s.a_bl[0], s.a_bl[1], s.r_t, s.r_u};  // vec_a_with_blinders, curdleproofs.rs:157-160
         for (int i = 0; i < 4; i++) s.x[ell + i] = s.r_sm[ell + i] + a_sm * tail[i];
+        s.wS.assign(n, Fr::one());
     });
     t_host += now_ms() - t0;
     for (size_t k = 0; k < m; k++) {
@@ -776,7 +834,9 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         parallel_for(T, B, [&](size_t pr) {
             ProofState &s = p->ps[pr];
             uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
-            for (size_t i = 0; i < 2 * h; i++) put_fr(sc + 32 * i, s.x[i]);
+            // msm(G_R, x_L), msm(G_L, x_R) (:107,:110) over the original G_with_blinders; T, U use the folded vectors
+            for (size_t j = 0; j < n; j++) put_fr(sc + 32 * j, s.wS[j] * s.x[(j & h) ? (j & (h - 1)) : h + (j & (h - 1))]);
+            for (size_t i = 0; i < 2 * h; i++) put_fr(sc + 32 * (n + i), s.x[i]);
         });
         t_host += now_ms() - t0;
         if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
@@ -791,6 +851,9 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             Fr gamma = s.tr->challenge("same_msm_gamma"), gamma_inv = gamma.inverse();
             for (size_t i = 0; i < h; i++) s.x[i] += gamma_inv * s.x[h + i];
             put_fr(p->h_fscal + pr * 32, gamma);
+            if (h > 1)
+                for (size_t j = 0; j < n; j++)
+                    if (j & h) s.wS[j] *= gamma;   // G_L += gamma G_R (:130)
         });
         t_host += now_ms() - t0;
         if (h > 1) {
@@ -835,6 +898,8 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
 // own host thread: while one lane hashes transcripts on the host, or sits in a latency-bound tail of a small launch, the
 // others keep the SMs busy.
 struct cdp_prover {
+    cdp_fixed_table *table = nullptr;  // digit table of the CRS points, shared (read-only) by all lanes
+    cdp_ctx *table_ctx = nullptr;
     std::vector<Lane *> lanes;
     std::vector<cdp_ctx *> owned;
     std::vector<size_t> last_split;
@@ -855,6 +920,7 @@ extern "C" void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[
 extern "C" void cdp_prover_destroy(cdp_prover *p) {
     if (!p) return;
     for (Lane *l : p->lanes) lane_destroy(l);
+    if (p->table) cdp_fixed_table_destroy(p->table_ctx, p->table);
     for (cdp_ctx *c : p->owned) cdp_ctx_destroy(c);
     delete p;
 }
@@ -874,6 +940,13 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     p->max_batch = max_batch;
     size_t per_lane = (max_batch + lanes - 1) / lanes;
     int threads_per_lane = std::max(1, host_threads / lanes);
+    {   // CRS digit table: G | Hvec | H | G_t | G_u.  CDP_FIXED_BITS overrides the window width (default 16: 50 MB per base)
+        int bits = 0;
+        if (const char *e = getenv("CDP_FIXED_BITS")) bits = atoi(e);
+        int rc = cdp_fixed_table_create(ctx, crs_points, ell + 7, bits, &p->table);
+        if (rc != CDP_OK) { p->err = std::string("fixed table: ") + cdp_last_error(ctx); delete p; return rc; }
+        p->table_ctx = ctx;
+    }
     for (int i = 0; i < lanes; i++) {
         cdp_ctx *c = ctx;
         if (i > 0) {
@@ -881,7 +954,7 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
             p->owned.push_back(c);
         }
         Lane *l = nullptr;
-        int rc = lane_create(&l, c, ell, crs_points, per_lane, threads_per_lane);
+        int rc = lane_create(&l, c, p->table, ell, crs_points, per_lane, threads_per_lane);
         if (rc != CDP_OK) { cdp_prover_destroy(p); return rc; }
         p->lanes.push_back(l);
     }
