@@ -81,35 +81,31 @@ struct Fr {
         return r;
     }
     Fr neg() const { return zero() - *this; }
-    // separated operand scanning: 512-bit product, then four Montgomery reduction sweeps
+    // Montgomery product, coarsely integrated operand scanning without the extra carry word (r < 2^255: the top limb of the
+    // modulus has its high bit clear, so t never exceeds 2r - 1 between sweeps)
     Fr operator*(const Fr &o) const {
-        uint64_t t[9] = {0};
-        for (int i = 0; i < 4; i++) {
-            u128 c = 0;
-            for (int j = 0; j < 4; j++) {
-                c += (u128)v[i] * o.v[j] + t[i + j];
-                t[i + j] = (uint64_t)c;
-                c >>= 64;
-            }
-            t[i + 4] = (uint64_t)c;
-        }
-        for (int i = 0; i < 4; i++) {
-            uint64_t q = t[i] * NINV;
-            u128 c = 0;
-            for (int j = 0; j < 4; j++) {
-                c += (u128)q * MOD[j] + t[i + j];
-                t[i + j] = (uint64_t)c;
-                c >>= 64;
-            }
-            for (int j = i + 4; j < 9 && c; j++) {
-                c += t[j];
-                t[j] = (uint64_t)c;
-                c >>= 64;
-            }
-        }
+        uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define CDP_FR_SWEEP(bi)                                                                 \
+    {                                                                                    \
+        u128 A = (u128)v[0] * (bi) + t0;                                                 \
+        uint64_t m = (uint64_t)A * NINV;                                                 \
+        u128 C = (u128)m * MOD[0] + (uint64_t)A;                                         \
+        A = (u128)v[1] * (bi) + t1 + (uint64_t)(A >> 64);                                \
+        C = (u128)m * MOD[1] + (uint64_t)A + (uint64_t)(C >> 64);                        \
+        t0 = (uint64_t)C;                                                                \
+        A = (u128)v[2] * (bi) + t2 + (uint64_t)(A >> 64);                                \
+        C = (u128)m * MOD[2] + (uint64_t)A + (uint64_t)(C >> 64);                        \
+        t1 = (uint64_t)C;                                                                \
+        A = (u128)v[3] * (bi) + t3 + (uint64_t)(A >> 64);                                \
+        C = (u128)m * MOD[3] + (uint64_t)A + (uint64_t)(C >> 64);                        \
+        t2 = (uint64_t)C;                                                                \
+        t3 = (uint64_t)(C >> 64) + (uint64_t)(A >> 64);                                  \
+    }
+        CDP_FR_SWEEP(o.v[0]) CDP_FR_SWEEP(o.v[1]) CDP_FR_SWEEP(o.v[2]) CDP_FR_SWEEP(o.v[3])
+#undef CDP_FR_SWEEP
         Fr r;
-        memcpy(r.v, t + 4, 32);
-        if (t[8] || geq_mod(r.v)) r.sub_mod();
+        r.v[0] = t0; r.v[1] = t1; r.v[2] = t2; r.v[3] = t3;
+        if (geq_mod(r.v)) r.sub_mod();
         return r;
     }
     Fr &operator+=(const Fr &o) { return *this = *this + o; }

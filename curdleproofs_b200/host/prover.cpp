@@ -157,6 +157,35 @@ void parallel_for(int threads, size_t n, F f) {
     for (auto &th : pool) th.join();
 }
 
+// contiguous ranges, one per thread: lets a thread batch work (simultaneous inversion) over its own proofs
+template <class F>
+void parallel_chunks(int threads, size_t n, F f) {
+    size_t nt = std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, threads), n));
+    if (nt <= 1) {
+        f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (size_t t = 0; t < nt; t++)
+        pool.emplace_back([=]() { f(n * t / nt, n * (t + 1) / nt); });
+    for (auto &th : pool) th.join();
+}
+// xs[i] <- xs[i]^-1 for all i with one field inversion (Montgomery's trick); no element may be zero
+void batch_inverse(std::vector<Fr> &xs) {
+    const size_t n = xs.size();
+    if (n == 0) return;
+    std::vector<Fr> pre(n);
+    Fr acc = Fr::one();
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; acc *= xs[i]; }
+    Fr inv = acc.inverse();
+    for (size_t i = n; i-- > 0;) {
+        Fr t = inv * pre[i];
+        inv *= xs[i];
+        xs[i] = t;
+    }
+}
+
 void put_fr(uint8_t *dst, const Fr &x) { x.to_bytes(dst); }
 
 // ---- stage table construction --------------------------------------------------------------------------------
@@ -687,46 +716,62 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     t_host += now_ms() - t0;
     if (int rc = run_msm_stage(p, p->st3, B, t_wait, t_copy)) return rc;
 
-    // ---- gprod step 3-4 (grand_product_argument.rs:85-147) + IPA step 1 (inner_product_argument.rs:124-127) -> stage 4: D, B_c, B_d ; G'
+    // ---- gprod step 3-4 (grand_product_argument.rs:85-147) + IPA step 1 (inner_product_argument.rs:124-127) -> stage 4: D, B_c, B_d
     t0 = now_ms();
-    parallel_for(T, B, [&](size_t pr) {
-        ProofState &s = p->ps[pr];
-        memcpy(s.C, stage_out(p, p->st3, B, pr, 0), 48);
-        s.tr->append_point("gprod_step2", s.C);
-        s.tr->append_fr("gprod_step2", s.r_p);
-        s.beta_g = s.tr->challenge("gprod_beta");
-        const Fr beta = s.beta_g, beta_inv = beta.inverse();
-        s.u.resize(n);
-        Fr pw = beta_inv;
-        for (size_t i = 0; i < ell; i++) { s.u[i] = pw; pw *= beta_inv; }     // beta^-(i+1)
-        for (size_t i = 0; i < 4; i++) s.u[ell + i] = pw;                       // beta^-(ell+1)
-        s.d.assign(n, Fr::zero());
-        Fr pb = beta, p1 = Fr::one();
-        for (size_t i = 0; i < ell; i++) {                                      // d_i = b_i beta^(i+1) - beta^i
-            s.d[i] = s.factors[i] * pb - p1;
-            p1 = pb;
-            pb *= beta;
+    parallel_chunks(T, B, [&](size_t lo, size_t hi) {
+        // the field inversions of all proofs of the chunk share one exponentiation: {beta, c[n-2]} first, then the blinder denominator
+        std::vector<Fr> inv1(2 * (hi - lo)), inv2(hi - lo);
+        for (size_t pr = lo; pr < hi; pr++) {
+            ProofState &s = p->ps[pr];
+            memcpy(s.C, stage_out(p, p->st3, B, pr, 0), 48);
+            s.tr->append_point("gprod_step2", s.C);
+            s.tr->append_fr("gprod_step2", s.r_p);
+            s.beta_g = s.tr->challenge("gprod_beta");
+            inv1[2 * (pr - lo)] = s.beta_g;
+            inv1[2 * (pr - lo) + 1] = s.c[n - 2];
         }
-        const Fr beta_l = p1, beta_l1 = pb;                                     // beta^ell, beta^(ell+1)
-        for (int i = 0; i < 4; i++) s.d[ell + i] = beta_l1 * s.rb_alpha[i];
-        s.z = s.r_p * beta_l1 + s.gprod_result * beta_l - Fr::one();            // inner_prod
-        // generate_ipa_blinders: the two left-out blinders solve <r_c,d> + <r_d,c> = 0 and <r_c,r_d> = 0   (:53-77)
-        {
+        batch_inverse(inv1);
+        std::vector<Fr> omega(hi - lo), delta(hi - lo);
+        for (size_t pr = lo; pr < hi; pr++) {
+            ProofState &s = p->ps[pr];
+            const Fr beta = s.beta_g, beta_inv = inv1[2 * (pr - lo)], inv_c = inv1[2 * (pr - lo) + 1];
+            s.u.resize(n);
+            Fr pw = beta_inv;
+            for (size_t i = 0; i < ell; i++) { s.u[i] = pw; pw *= beta_inv; }     // beta^-(i+1)
+            for (size_t i = 0; i < 4; i++) s.u[ell + i] = pw;                       // beta^-(ell+1)
+            s.d.assign(n, Fr::zero());
+            Fr pb = beta, p1 = Fr::one();
+            for (size_t i = 0; i < ell; i++) {                                      // d_i = b_i beta^(i+1) - beta^i
+                s.d[i] = s.factors[i] * pb - p1;
+                p1 = pb;
+                pb *= beta;
+            }
+            const Fr beta_l = p1, beta_l1 = pb;                                     // beta^ell, beta^(ell+1)
+            for (int i = 0; i < 4; i++) s.d[ell + i] = beta_l1 * s.rb_alpha[i];
+            s.z = s.r_p * beta_l1 + s.gprod_result * beta_l - Fr::one();            // inner_prod
+            // generate_ipa_blinders: the two left-out blinders solve <r_c,d> + <r_d,c> = 0 and <r_c,r_d> = 0   (:53-77)
             const std::vector<Fr> &c = s.c, &d = s.d;
             std::vector<Fr> &r = s.r_c, &z = s.r_d;
-            Fr omega = inner_product(r.data(), d.data(), n) + inner_product(z.data(), c.data(), n - 2);
-            Fr delta = inner_product(r.data(), z.data(), n - 2);
-            Fr inv_c = c[n - 2].inverse();
-            Fr last_z = (r[n - 2] * inv_c * omega - delta) * (r[n - 2].neg() * inv_c * c[n - 1] + r[n - 1]).inverse();
-            Fr pen_z = inv_c.neg() * (last_z * c[n - 1] + omega);
+            omega[pr - lo] = inner_product(r.data(), d.data(), n) + inner_product(z.data(), c.data(), n - 2);
+            delta[pr - lo] = inner_product(r.data(), z.data(), n - 2);
+            inv2[pr - lo] = r[n - 2].neg() * inv_c * c[n - 1] + r[n - 1];
+        }
+        batch_inverse(inv2);
+        for (size_t pr = lo; pr < hi; pr++) {
+            ProofState &s = p->ps[pr];
+            const Fr beta_inv = inv1[2 * (pr - lo)], inv_c = inv1[2 * (pr - lo) + 1];
+            const std::vector<Fr> &c = s.c;
+            std::vector<Fr> &r = s.r_c, &z = s.r_d;
+            Fr last_z = (r[n - 2] * inv_c * omega[pr - lo] - delta[pr - lo]) * inv2[pr - lo];
+            Fr pen_z = inv_c.neg() * (last_z * c[n - 1] + omega[pr - lo]);
             z[n - 2] = pen_z;
             z[n - 1] = last_z;
+            uint8_t *sc = p->h_scal + pr * p->st4.scalars_per_proof * 32;
+            // D = 1 B - beta^-1 sum(G) + alpha_g sum(Hvec)   (the reference's verifier uses the same identity, grand_product_argument.rs:223)
+            put_fr(sc, Fr::one()); put_fr(sc + 32, beta_inv.neg()); put_fr(sc + 64, s.alpha_g);
+            for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + i), s.r_c[i]);                    // B_c = msm(G|Hvec, r_c)
+            for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + n + i), s.r_d[i] * s.u[i]);       // B_d = msm(G', r_d)
         }
-        uint8_t *sc = p->h_scal + pr * p->st4.scalars_per_proof * 32;
-        // D = 1 B - beta^-1 sum(G) + alpha_g sum(Hvec)   (the reference's verifier uses the same identity, grand_product_argument.rs:223)
-        put_fr(sc, Fr::one()); put_fr(sc + 32, beta_inv.neg()); put_fr(sc + 64, s.alpha_g);
-        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + i), s.r_c[i]);                    // B_c = msm(G|Hvec, r_c)
-        for (size_t i = 0; i < n; i++) put_fr(sc + 32 * (3 + n + i), s.r_d[i] * s.u[i]);       // B_d = msm(G', r_d)
     });
     t_host += now_ms() - t0;
     t0 = now_ms();
@@ -778,22 +823,31 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         t_host += now_ms() - t0;
         if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
         t0 = now_ms();
-        parallel_for(T, B, [&](size_t pr) {
-            ProofState &s = p->ps[pr];
-            uint8_t *rp = s.ipa_rounds.data() + k * 4 * 48;
-            for (int q = 0; q < 4; q++) {  // L_C, L_D, R_C, R_D
-                memcpy(rp + 48 * q, stage_out(p, st, B, pr, q), 48);
-                s.tr->append_point("ipa_loop", rp + 48 * q);
+        parallel_chunks(T, B, [&](size_t lo, size_t hi) {
+            std::vector<Fr> gam(hi - lo), ginv;
+            for (size_t pr = lo; pr < hi; pr++) {
+                ProofState &s = p->ps[pr];
+                uint8_t *rp = s.ipa_rounds.data() + k * 4 * 48;
+                for (int q = 0; q < 4; q++) {  // L_C, L_D, R_C, R_D
+                    memcpy(rp + 48 * q, stage_out(p, st, B, pr, q), 48);
+                    s.tr->append_point("ipa_loop", rp + 48 * q);
+                }
+                gam[pr - lo] = s.tr->challenge("ipa_gamma");
             }
-            Fr gamma = s.tr->challenge("ipa_gamma"), gamma_inv = gamma.inverse();
-            for (size_t i = 0; i < h; i++) {
-                s.c[i] += gamma_inv * s.c[h + i];
-                s.d[i] += gamma * s.d[h + i];
+            ginv = gam;
+            batch_inverse(ginv);  // one inversion for the chunk's gamma^-1 (:171)
+            for (size_t pr = lo; pr < hi; pr++) {
+                ProofState &s = p->ps[pr];
+                const Fr gamma = gam[pr - lo], gamma_inv = ginv[pr - lo];
+                for (size_t i = 0; i < h; i++) {
+                    s.c[i] += gamma_inv * s.c[h + i];
+                    s.d[i] += gamma * s.d[h + i];
+                }
+                // G_L += gamma G_R, G'_L += gamma^-1 G'_R (:177-178), as weights on the original bases
+                if (h > 1)
+                    for (size_t j = 0; j < n; j++)
+                        if (j & h) { s.wG[j] *= gamma; s.wGp[j] *= gamma_inv; }
             }
-            // G_L += gamma G_R, G'_L += gamma^-1 G'_R (:177-178), as weights on the original bases
-            if (h > 1)
-                for (size_t j = 0; j < n; j++)
-                    if (j & h) { s.wG[j] *= gamma; s.wGp[j] *= gamma_inv; }
         });
         t_host += now_ms() - t0;
     }
@@ -841,19 +895,28 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         t_host += now_ms() - t0;
         if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
         t0 = now_ms();
-        parallel_for(T, B, [&](size_t pr) {
-            ProofState &s = p->ps[pr];
-            uint8_t *rp = s.sm_rounds.data() + k * 6 * 48;
-            for (int q = 0; q < 6; q++) {  // L_A, L_T, L_U, R_A, R_T, R_U
-                memcpy(rp + 48 * q, stage_out(p, st, B, pr, q), 48);
-                s.tr->append_point("same_msm_loop", rp + 48 * q);
+        parallel_chunks(T, B, [&](size_t lo, size_t hi) {
+            std::vector<Fr> gam(hi - lo), ginv;
+            for (size_t pr = lo; pr < hi; pr++) {
+                ProofState &s = p->ps[pr];
+                uint8_t *rp = s.sm_rounds.data() + k * 6 * 48;
+                for (int q = 0; q < 6; q++) {  // L_A, L_T, L_U, R_A, R_T, R_U
+                    memcpy(rp + 48 * q, stage_out(p, st, B, pr, q), 48);
+                    s.tr->append_point("same_msm_loop", rp + 48 * q);
+                }
+                gam[pr - lo] = s.tr->challenge("same_msm_gamma");
             }
-            Fr gamma = s.tr->challenge("same_msm_gamma"), gamma_inv = gamma.inverse();
-            for (size_t i = 0; i < h; i++) s.x[i] += gamma_inv * s.x[h + i];
-            put_fr(p->h_fscal + pr * 32, gamma);
-            if (h > 1)
-                for (size_t j = 0; j < n; j++)
-                    if (j & h) s.wS[j] *= gamma;   // G_L += gamma G_R (:130)
+            ginv = gam;
+            batch_inverse(ginv);
+            for (size_t pr = lo; pr < hi; pr++) {
+                ProofState &s = p->ps[pr];
+                const Fr gamma = gam[pr - lo], gamma_inv = ginv[pr - lo];
+                for (size_t i = 0; i < h; i++) s.x[i] += gamma_inv * s.x[h + i];
+                put_fr(p->h_fscal + pr * 32, gamma);
+                if (h > 1)
+                    for (size_t j = 0; j < n; j++)
+                        if (j & h) s.wS[j] *= gamma;   // G_L += gamma G_R (:130)
+            }
         });
         t_host += now_ms() - t0;
         if (h > 1) {
