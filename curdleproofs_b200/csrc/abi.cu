@@ -139,9 +139,9 @@ msm_cfg pick_cfg(size_t max_n) {
     g.nwin = msm_nwin_for(g.c);
     return g;
 }
-constexpr size_t SMALL_MSM_MAX_N = 2048;  // C = 6, WPB = 11: 11 * 6 * 2048 = 135 KB of shared memory
+constexpr size_t SMALL_MSM_MAX_N = 2048;  // uint16 point ids with a sign bit (2n < 2^15); 4 warps x 12 KB of shared memory at c = 6
 
-// window sums for `count` segments -> d_win[count][nwin]
+// bucket sums for `count` segments -> d_win[count][nwin][2^(c-1)]
 int msm_buckets_dev(cdp_ctx *ctx, const msm_cfg &g, const uint8_t *d_pts, const uint8_t *d_scalars, const msm_seg_t *d_segs, size_t count,
                     size_t nmax, uint32_t *d_win, uint64_t pairs) {
     TRY(ensure_dev(ctx, ctx->d_dig, msm_dig_bytes(g.c, nmax, count)));
@@ -294,7 +294,7 @@ static int msm_batch_dev_c(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     msm_cfg g = pick_cfg(max_n);
     if (force_c) { g.c = force_c; g.nwin = msm_nwin_for(force_c); }
-    TRY(ensure_dev(ctx, ctx->d_win, count * g.nwin * CDP_JACOBIAN_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_win, msm_bucket_sums_bytes(g.c, count)));
     static_assert(sizeof(cdp_msm_seg) == sizeof(msm_seg_t), "segment layout");
     TRY(msm_buckets_dev(ctx, g, d_affine_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(d_segs), count, max_n,
                         reinterpret_cast<uint32_t *>(ctx->d_win.ptr), total_pairs));
@@ -379,14 +379,15 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer reuse
     memcpy(ctx->h_stage.ptr, segs.data(), nchunks * sizeof(msm_seg_t));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, ctx->h_stage.ptr, nchunks * sizeof(msm_seg_t), cudaMemcpyHostToDevice, ctx->stream));
-    TRY(ensure_dev(ctx, ctx->d_win, (nchunks + 1) * g.nwin * CDP_JACOBIAN_BYTES));
+    TRY(ensure_dev(ctx, ctx->d_win, msm_bucket_sums_bytes(g.c, nchunks + 1)));
     uint32_t *win = reinterpret_cast<uint32_t *>(ctx->d_win.ptr);
     TRY(msm_buckets_dev(ctx, g, d_pts, d_scalars, reinterpret_cast<const msm_seg_t *>(ctx->d_segs.ptr), nchunks, chunk, win, n));
     const uint32_t *win_final = win;
-    if (nchunks > 1) {
-        uint32_t *red = win + 36 * nchunks * g.nwin;
+    if (nchunks > 1) {  // bucket sums of the chunks are added slot by slot, then combined once
+        const uint32_t slots = (uint32_t)(g.nwin * msm_nb_for(g.c));
+        uint32_t *red = win + 36 * nchunks * (size_t)slots;
         launch_scope ls(ctx, CDP_PROFILE_OTHER, nchunks);
-        CUDA_TRY(ctx, launch_sum_groups(ctx->stream, win, red, (uint32_t)g.nwin, (uint32_t)nchunks, (uint32_t)g.nwin));
+        CUDA_TRY(ctx, launch_sum_groups(ctx->stream, win, red, slots, (uint32_t)nchunks, slots));
         win_final = red;
     }
     return combine_dev(ctx, g, win_final, 1, reinterpret_cast<uint32_t *>(d_out_jac));

@@ -3,22 +3,42 @@
 
 namespace cdp {
 
-// One thread per MSM: result = sum_w 2^(c*w) * W_w, Horner from the top window down.
-__global__ void __launch_bounds__(64) k_msm_combine(const uint32_t *__restrict__ win_sums, uint32_t *__restrict__ out_jac,
-                                                    uint32_t n_msm, int c, int nwin) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_msm) return;
+// Window combine of a batch of MSMs from their bucket sums [msm][window][bucket].  One thread per (MSM, bucket index b), the
+// nb = 2^(c-1) lanes of an MSM side by side in a warp:
+//   S_b = sum_w 2^(c w) B_{w,b}           Horner from the top window down, all lanes doubling in parallel
+//   out = sum_b (b + 1) S_b               suffix scan + tree sum with warp shuffles (2 (c-1) full additions deep), once per MSM
+// -- the same group element as reducing every window separately and combining the window sums, with nwin times fewer reductions.
+__global__ void __launch_bounds__(128) k_msm_combine(const uint32_t *__restrict__ bucket_sums, uint32_t *__restrict__ out_jac, uint32_t n_msm,
+                                                     int c, int nwin) {
+    const int nb = 1 << (c - 1);
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = gid / nb;
+    const int b = (int)(gid % nb);
+    const bool valid = i < n_msm;
     g1j acc;
-    g1j_load(acc, win_sums + 36 * ((size_t)i * nwin + (nwin - 1)));
+    g1j_set_inf(acc);
+    if (valid) {
+        const uint32_t *B = bucket_sums + 36 * ((size_t)i * nwin * nb + b);
+        g1j_load(acc, B + 36 * (size_t)(nwin - 1) * nb);
 #pragma unroll 1
-    for (int w = nwin - 2; w >= 0; w--) {
+        for (int w = nwin - 2; w >= 0; w--) {
 #pragma unroll 1
-        for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
-        g1j W;
-        g1j_load(W, win_sums + 36 * ((size_t)i * nwin + w));
-        g1j_add(acc, acc, W);
+            for (int k = 0; k < c; k++) g1j_dbl(acc, acc);
+            g1j W;
+            g1j_load(W, B + 36 * (size_t)w * nb);
+            g1j_add(acc, acc, W);
+        }
     }
-    g1j_store(out_jac + 36 * (size_t)i, acc);
+#pragma unroll 1
+    for (int step = 0; step < 2 * (c - 1); step++) {
+        const bool scan = step < c - 1;
+        const int d = scan ? (1 << step) : (nb >> (step - (c - 1) + 1));
+        const bool take = scan ? (b + d < nb) : (b < d);
+        g1j o;
+        shfl_down_g1j(o, acc, d, nb);
+        if (take) g1j_add(acc, acc, o);
+    }
+    if (valid && b == 0) g1j_store(out_jac + 36 * (size_t)i, acc);
 }
 
 
@@ -56,8 +76,9 @@ cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, cons
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *win_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin) {
-    k_msm_combine<<<(n_msm + 63) / 64, 64, 0, st>>>(win_sums, out_jac, n_msm, c, nwin);
+cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin) {
+    const uint64_t threads = (uint64_t)n_msm << (c - 1);
+    k_msm_combine<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(bucket_sums, out_jac, n_msm, c, nwin);
     return cudaGetLastError();
 }
 cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride) {

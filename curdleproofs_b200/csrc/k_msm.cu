@@ -8,19 +8,20 @@
 
 namespace cdp {
 
-// The small-MSM path -- `util::msm` (/root/reference/src/util.rs:19-22) for a batch of independent MSMs -- runs in two kernels:
+// The small-MSM path -- `util::msm` (/root/reference/src/util.rs:19-22) for a batch of independent MSMs -- runs in three kernels:
 //
 // k_msm_digits   one thread per (segment, pair): coalesced 128-bit scalar loads, GLV split (2n half-width "points": 2j -> P_j
 //                with k1, 2j+1 -> phi(P_j) with k2), signed radix-2^c recoding; digit rows (int8, one row per window) go to global
-//                memory once per MSM, so the bucket kernel can use as many small CTAs per MSM as it likes without redoing this.
-// k_msm_buckets  grid = (n_msm, ceil(NWIN / WPB)), CTAs of <= 128 threads (3 resident per SM at <= 168 registers).
-//                Lane (w, b) owns bucket b of window w:
-//   phase 0  the CTA's WPB digit rows are staged global -> shared memory with 16-byte loads
+//                memory once per MSM.
+// k_msm_buckets  one WARP per (MSM, group of 32 / 2^(c-1) windows); warps are independent (per-warp shared memory, __syncwarp only),
+//                so every MSM uses exactly ceil(NWIN / WPW) warps whatever the CTA shape.  Lane (w, b) owns bucket b of window w:
+//   phase 0  the warp's digit rows are staged global -> shared memory with 16-byte loads
 //   phase 1  each lane counts its bucket, a warp-shuffle scan over the nb lanes of the window gives list offsets
 //   phase 2  each lane writes its own index list (uint16 point id | sign bit) -- no atomics, no contention
 //   phase 3  each lane adds ITS OWN points (different lanes, different points => no serialisation); mixed adds
-//   phase 4  sum_b (b+1) B_b by a suffix scan + tree sum with warp shuffles (2*log2(nb) Jacobian adds deep)
-//   phase 5  lane b = 0 writes the window sum; k_msm_combine does the doublings
+//   phase 4  bucket sums go to global memory, [msm][window][bucket] (top window: the SP partial sums of a bucket are folded first)
+// k_msm_combine  (k_misc.cu) one thread per (MSM, bucket index): Horner over the windows FIRST (sum_w 2^(cw) B_{w,b}: the doublings run
+//                on 2^(c-1) lanes in parallel), THEN one weighted reduction sum_b (b+1) S_b per MSM -- instead of one reduction per window.
 // Handles infinity bases and zero scalars (digits 0) and all-equal scalars (one long list, still correct).
 template <int C>
 __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
@@ -71,45 +72,51 @@ __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__
     }
 }
 
-// dynamic shared memory: int8 digits[WPB][dstride] ; uint16 lists[WPB][2*nmax]
-template <int C, int WPB>
-__global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32, 3)
+// dynamic shared memory, per warp: int8 digits[WPW][dstride] ; uint16 lists[WPW][2*nmax]
+template <int C>
+__global__ void __launch_bounds__(128, 3)
     k_msm_buckets(const uint32_t *__restrict__ pts, const msm_seg_t *__restrict__ segs, const int8_t *__restrict__ dig, uint32_t rowstride,
-                  uint32_t *__restrict__ win_sums /* [msm][nwin] jacobian */, uint32_t nmax) {
+                  uint32_t *__restrict__ bucket_sums /* [msm][nwin][NB] jacobian */, uint32_t nmax, uint32_t n_msm) {
     constexpr int NB = 1 << (C - 1);
     constexpr int NWIN = (130 + C - 1) / C;
+    constexpr int WPW = 32 / NB;                    // windows per warp
+    constexpr int G = (NWIN + WPW - 1) / WPW;       // warps per MSM
     extern __shared__ __align__(16) uint8_t smem[];
-    const msm_seg_t seg = segs[blockIdx.x];
+    const int lane_id = threadIdx.x & 31;
+    const uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (unit >= n_msm * G) return;  // whole warps leave; nothing below synchronises across warps
+    const uint32_t msm = unit / G;
+    const int w0 = (int)(unit - msm * G) * WPW;
+    const msm_seg_t seg = segs[msm];
     const uint32_t n_plain = seg.n;
     const uint32_t n = seg.n + (seg.extra ? 1u : 0u), n2 = 2 * n;
     const uint32_t *PX = seg.extra ? pts + 24 * (size_t)(seg.extra - 1) : nullptr;
-    const int w0 = blockIdx.y * WPB;
     const uint32_t dstride = ((2 * nmax + 15) & ~15u) + 16;  // 16-byte aligned rows; the extra 16 bytes spread the rows over the banks
-    int8_t *digits = reinterpret_cast<int8_t *>(smem);
-    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + (size_t)WPB * dstride);
+    const size_t per_warp = msm_smem_per_warp(C, nmax);
+    int8_t *digits = reinterpret_cast<int8_t *>(smem + (threadIdx.x >> 5) * per_warp);
+    uint16_t *lists = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(digits) + (size_t)WPW * dstride);
     const uint32_t *P = pts + 24 * (size_t)seg.pts_off;
 
-    // ---- phase 0: stage this CTA's digit rows
+    // ---- phase 0: stage this warp's digit rows
     {
-        const int8_t *gd = dig + (size_t)blockIdx.x * NWIN * rowstride;
+        const int8_t *gd = dig + (size_t)msm * NWIN * rowstride;
         const uint32_t vec_per_row = (n2 + 15) / 16;
-        for (uint32_t t = threadIdx.x; t < WPB * vec_per_row; t += blockDim.x) {
+        for (uint32_t t = lane_id; t < WPW * vec_per_row; t += 32) {
             uint32_t wl = t / vec_per_row, v = t % vec_per_row;
             if (w0 + (int)wl < NWIN)
                 reinterpret_cast<uint4 *>(digits + (size_t)wl * dstride)[v] =
                     reinterpret_cast<const uint4 *>(gd + (size_t)(w0 + wl) * rowstride)[v];
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    const int lane_id = threadIdx.x;
     const int wl = lane_id / NB, b = lane_id % NB;
     const int w = w0 + wl;
-    const bool active = wl < WPB && w < NWIN;
+    const bool active = w < NWIN;
     // The top window only holds the few leftover bits (plus the recoding carry): NBT distinct non-zero digits.  Lane-per-
-    // bucket would leave NB - NBT lanes idle and put 2n/NBT points on each of the others, and that one slow warp would keep
-    // the whole CTA resident (measured: 10% warps active, profiles/r01_ncu_msm_buckets_v0.txt).  So in the top window every
-    // bucket is spread over SP = NB / NBT lanes (by point index); phase 4 first folds the SP partial sums of a bucket.
+    // bucket would leave NB - NBT lanes idle and put 2n/NBT points on each of the others (measured on the first version: 10% warps
+    // active, profiles/r01_ncu_msm_buckets_v0.txt).  So in the top window every bucket is spread over SP = NB / NBT lanes (by point
+    // index); phase 4 folds the SP partial sums of a bucket.
     constexpr int TB = 128 - C * (NWIN - 1);
     constexpr int NBT = TB > 0 ? (1 << TB) : 1;
     constexpr int SP = NB / NBT >= 1 ? NB / NBT : 1;
@@ -163,56 +170,48 @@ __global__ void __launch_bounds__(((WPB << (C - 1)) + 31) / 32 * 32, 3)
             g1j_add_mixed(acc, acc, q);
         }
     }
-    // ---- phase 4: window reduction  S = sum_b (b+1) * B_b = sum_j suffix_j, all with warp shuffles; one loop, one inlined
-    //      addition.  Ordinary window:  C-1 suffix-scan steps (distance 1, 2, 4, ...), then C-1 tree-sum steps.
-    //      Top window: log2(SP) steps fold the SP lanes of each bucket, then scan + tree over the NBT bucket leaders.
-    if (NB > 1) {
+    // ---- phase 4: top window only -- fold the SP lanes of each bucket (log2(SP) shuffle steps; other windows just pass through)
+    if (SP > 1 && w0 + WPW >= NWIN) {  // warp-uniform: only the MSM's last warp holds the top window
         constexpr int LS = SP >= 16 ? 4 : SP >= 8 ? 3 : SP >= 4 ? 2 : SP >= 2 ? 1 : 0;
-        constexpr int LN = NBT >= 16 ? 4 : NBT >= 8 ? 3 : NBT >= 4 ? 2 : NBT >= 2 ? 1 : 0;
-        static_assert(LS + 2 * LN <= 2 * (C - 1), "top-window schedule must fit the step count");
 #pragma unroll 1
-        for (int step = 0; step < 2 * (C - 1); step++) {
-            int d;
-            bool take;
-            if (!is_top) {
-                const bool scan = step < C - 1;
-                d = scan ? (1 << step) : (NB >> (step - (C - 1) + 1));
-                take = scan ? (b + d < NB) : (b < d);
-            } else {
-                const bool leader = (b & (SP - 1)) == 0;
-                if (step < LS) { d = SP >> (step + 1); take = (b & (SP - 1)) < d; }
-                else if (step < LS + LN) { d = SP << (step - LS); take = leader && (b + d < NB); }
-                else if (step < LS + 2 * LN) { d = NB >> (step - LS - LN + 1); take = leader && (b < d); }
-                else { d = 1; take = false; }
-            }
+        for (int step = 0; step < LS; step++) {
+            const int d = SP >> (step + 1);
+            const bool take = is_top && (b & (SP - 1)) < d;
             g1j o;
             shfl_down_g1j(o, acc, d, NB);
             if (take) g1j_add(acc, acc, o);
         }
     }
-    // ---- phase 5
-    if (active && b == 0) g1j_store(win_sums + 36 * ((size_t)blockIdx.x * NWIN + w), acc);
+    // ---- phase 5: bucket sums out.  Top window: leader lane k*SP holds bucket k; the other lanes fill the unused slots with infinity
+    if (active) {
+        int slot = b;
+        if (is_top && SP > 1) {
+            const bool leader = (b & (SP - 1)) == 0;
+            if (leader) slot = b / SP;
+            else { slot = NBT + b - b / SP - 1; g1j_set_inf(acc); }
+        }
+        g1j_store(bucket_sums + 36 * (((size_t)msm * NWIN + w) * NB + slot), acc);
+    }
 }
 
 #define CDP_CAT2(a, b) a##b
 #define CDP_CAT(a, b) CDP_CAT2(a, b)
 cudaError_t CDP_CAT(launch_msm_buckets_c, MSM_C)(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, const msm_seg_t *segs,
-                                                 uint32_t count, uint32_t nmax, int8_t *dig, uint32_t *win_sums) {
-    constexpr int C = MSM_C, WPB = msm_wpb_for(MSM_C), NWIN = msm_nwin_for(MSM_C);
-    constexpr int threads = ((WPB << (C - 1)) + 31) / 32 * 32;
+                                                 uint32_t count, uint32_t nmax, int8_t *dig, uint32_t *bucket_sums) {
+    constexpr int C = MSM_C;
     const uint32_t rowstride = msm_dig_rowstride(nmax);
     dim3 dgrid(count, nmax > 512 ? (nmax + 511) / 512 : 1);
     k_msm_digits<C><<<dgrid, 128, 0, st>>>(pts, scalars, segs, dig, rowstride);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     size_t smem = msm_smem_bytes(C, nmax);
-    auto kern = k_msm_buckets<C, WPB>;
+    auto kern = k_msm_buckets<C>;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(count, (NWIN + WPB - 1) / WPB);
-    kern<<<grid, threads, smem, st>>>(pts, segs, dig, rowstride, win_sums, nmax);
+    const uint64_t units = (uint64_t)count * msm_groups_for(C);
+    kern<<<(unsigned)((units + 3) / 4), 128, smem, st>>>(pts, segs, dig, rowstride, bucket_sums, nmax, count);
     return cudaGetLastError();
 }
 

@@ -49,7 +49,7 @@ cudaError_t launch_msm_buckets(cudaStream_t st, int c, const uint32_t *pts, cons
                                         uint32_t count, uint32_t nmax, int8_t *dig, uint32_t *win_sums);
 CDP_DECL_MSM(2) CDP_DECL_MSM(3) CDP_DECL_MSM(4) CDP_DECL_MSM(5) CDP_DECL_MSM(6)
 #undef CDP_DECL_MSM
-cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *win_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin);
+cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin);
 cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride);
 
 // large Pippenger MSM (k_bigmsm.cu)
@@ -98,13 +98,18 @@ cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, 
 
 // geometry shared by host and device
 constexpr int msm_nwin_for(int c) { return (130 + c - 1) / c; }
-// windows per CTA: CTAs of 96-128 threads (c = 6: 4 windows x 32 buckets, 5: 7 x 16, 4: 11 x 8, 3: 22 x 4, 2: 33 x 2)
-constexpr int msm_wpb_for(int c) { return c == 6 ? 4 : c == 5 ? 7 : c == 4 ? 11 : c == 3 ? 22 : 33; }
+// the bucket kernel gives every warp 32 / 2^(c-1) windows of one MSM; CTAs are 4 independent warps
+constexpr int msm_nb_for(int c) { return 1 << (c - 1); }
+constexpr int msm_wpw_for(int c) { return 32 / msm_nb_for(c); }
+constexpr int msm_groups_for(int c) { return (msm_nwin_for(c) + msm_wpw_for(c) - 1) / msm_wpw_for(c); }
 inline uint32_t msm_dig_rowstride(size_t nmax) { return (uint32_t)((2 * nmax + 15) & ~size_t(15)); }
 inline size_t msm_dig_bytes(int c, size_t nmax, size_t count) { return count * (size_t)msm_nwin_for(c) * msm_dig_rowstride(nmax); }
-inline size_t msm_smem_bytes(int c, size_t nmax) {
-    size_t wpb = msm_wpb_for(c), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
-    return wpb * dstride + wpb * 2 * nmax * sizeof(uint16_t);
+__host__ __device__ inline size_t msm_smem_per_warp(int c, size_t nmax) {
+    size_t wpw = 32 >> (c - 1), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
+    return (wpw * dstride + wpw * 2 * nmax * sizeof(uint16_t) + 15) & ~size_t(15);
 }
+inline size_t msm_smem_bytes(int c, size_t nmax) { return 4 * msm_smem_per_warp(c, nmax); }
+// bucket sums of `count` MSMs: [msm][window][bucket] Jacobian points
+inline size_t msm_bucket_sums_bytes(int c, size_t count) { return count * (size_t)msm_nwin_for(c) * msm_nb_for(c) * 144; }
 
 }  // namespace cdp
