@@ -467,6 +467,16 @@ extern "C" int cdp_sum_jacobian_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_
     return CDP_OK;
 }
 
+extern "C" int cdp_sum_groups_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t n_out, size_t per_out, size_t group_stride, uint8_t *d_out_jac) {
+    if (!ctx || !d_jac_in || !d_out_jac || per_out == 0) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_sum_groups_dev: bad argument");
+    if (n_out == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, n_out * per_out);
+    CUDA_TRY(ctx, launch_sum_groups(ctx->stream, reinterpret_cast<const uint32_t *>(d_jac_in), reinterpret_cast<uint32_t *>(d_out_jac), (uint32_t)n_out,
+                                    (uint32_t)per_out, (uint32_t)group_stride));
+    return CDP_OK;
+}
+
 extern "C" int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
     if (!ctx || !d_out_jac || (n && (!d_affine_pts || !d_scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: null argument");
     if (n == 0 || n >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: n out of range");
@@ -701,7 +711,7 @@ extern "C" size_t cdp_fixed_table_bytes(const cdp_fixed_table *t) { return t ? t
 extern "C" size_t cdp_fixed_table_bases(const cdp_fixed_table *t) { return t ? t->n_bases : 0; }
 
 extern "C" int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
-                                       size_t total_pairs, uint8_t *d_out_jac) {
+                                       size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac) {
     if (!ctx || !t || (count && (!d_scalars || !d_segs || !d_out_jac))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev: null argument");
     if (count == 0) return CDP_OK;
     if (t->device != ctx->device) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev: table lives on another device");
@@ -709,7 +719,7 @@ extern "C" int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, c
     static_assert(sizeof(cdp_fixed_seg) == sizeof(fixed_seg_t), "fixed segment layout");
     launch_scope ls(ctx, CDP_PROFILE_MSM_FIXED, total_pairs);
     CUDA_TRY(ctx, launch_fixed_msm(ctx->stream, t->d_table, reinterpret_cast<const uint32_t *>(d_scalars), reinterpret_cast<const fixed_seg_t *>(d_segs),
-                                   (uint32_t)count, t->kp, reinterpret_cast<uint32_t *>(d_out_jac)));
+                                   (uint32_t)count, t->kp, reinterpret_cast<const uint32_t *>(d_var_pts), reinterpret_cast<uint32_t *>(d_out_jac)));
     return CDP_OK;
 }
 
@@ -741,7 +751,7 @@ extern "C" int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_segs.ptr, hs, nseg * sizeof(fixed_seg_t), cudaMemcpyHostToDevice, ctx->stream));
     uint8_t *dj = (uint8_t *)ctx->d_jac.ptr;
-    TRY(cdp_msm_fixed_batch_dev(ctx, t, (const uint8_t *)ctx->d_scalars.ptr, (const cdp_fixed_seg *)ctx->d_segs.ptr, nseg, n, dj));
+    TRY(cdp_msm_fixed_batch_dev(ctx, t, (const uint8_t *)ctx->d_scalars.ptr, (const cdp_fixed_seg *)ctx->d_segs.ptr, nseg, n, nullptr, dj));
     const uint8_t *res = dj;
     if (nseg > 1) {
         TRY(cdp_sum_jacobian_dev(ctx, dj, nseg, dj + nseg * CDP_JACOBIAN_BYTES));

@@ -142,7 +142,7 @@ __device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint
 // folded with warp shuffles (5 full additions).
 __global__ void __launch_bounds__(128, 3) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
                                                        const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
-                                                       uint32_t *__restrict__ out_jac) {
+                                                       const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= count) return;
     const fixed_seg_t seg = segs[warp];
@@ -193,6 +193,10 @@ __global__ void __launch_bounds__(128, 3) k_fixed_msm(const uint32_t *__restrict
         cur_neg = nxt_neg;
         have = hn;
     }
+    if (lane < seg.addv_n) {  // plain (coefficient 1) device-resident points of the sum
+        g1a_load(cur, var_pts + 24 * ((size_t)seg.addv_off + lane));
+        g1j_add_mixed(acc, acc, cur);
+    }
 #pragma unroll 1
     for (int d = 16; d >= 1; d >>= 1) {
         g1j o;
@@ -216,9 +220,9 @@ cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains
     return cudaGetLastError();
 }
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
-                             const fixed_kparams_t &kp, uint32_t *out_jac) {
+                             const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac) {
     if (count == 0) return cudaSuccess;
-    k_fixed_msm<<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, out_jac);
+    k_fixed_msm<<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
     return cudaGetLastError();
 }
 

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__
     }
 }
 
-// dynamic shared memory, per warp: int8 digits[WPW][dstride] ; uint16 lists[WPW][2*nmax]
+// dynamic shared memory, per warp: int8 digits[WPW][dstride] ; uint16 lists[WPW][2*nmax] ; uint32 counters[32]
 template <int C>
 __global__ void __launch_bounds__(128, 3)
     k_msm_buckets(const uint32_t *__restrict__ pts, const msm_seg_t *__restrict__ segs, const int8_t *__restrict__ dig, uint32_t rowstride,
@@ -122,19 +122,25 @@ __global__ void __launch_bounds__(128, 3)
     constexpr int SP = NB / NBT >= 1 ? NB / NBT : 1;
     static_assert(NBT <= NB, "top-window digits must fit the lanes");
     const bool is_top = (w == NWIN - 1);
-    auto bucket_of = [&](int d, uint32_t pidx) -> int {
-        int ad = d < 0 ? -d : d;
-        if (ad == 0) return -1;
-        return is_top ? (ad - 1) * SP + (int)(pidx & (SP - 1)) : ad - 1;
-    };
-    // ---- phase 1: count
-    uint32_t cnt = 0;
-    if (active) {
-        const int8_t *row = digits + wl * dstride;
-        for (uint32_t p = 0; p < n2; p++) {
-            cnt += (bucket_of(row[p], p) == b);
+    // ---- phases 1-2: counting sort of the point ids by bucket, the whole warp working on one window row at a time: every lane takes
+    //      every 32nd digit (shared-memory atomics on the row's NB counters), so a row costs 2 * n2 / 32 steps per lane instead of
+    //      two full scans by every lane.  List order inside a bucket is arbitrary; the bucket SUM does not depend on it.
+    uint32_t *cnts = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(lists) + (size_t)WPW * 2 * nmax * sizeof(uint16_t));  // [WPW][NB] counts, then cursors
+    for (int t = lane_id; t < WPW * NB; t += 32) cnts[t] = 0;
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < WPW; r++) {
+        if (w0 + r >= NWIN) break;
+        const bool row_top = (w0 + r == NWIN - 1);
+        const int8_t *row = digits + r * dstride;
+        for (uint32_t p = lane_id; p < n2; p += 32) {
+            int d = row[p];
+            int ad = d < 0 ? -d : d;
+            if (ad) atomicAdd(&cnts[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
         }
     }
+    __syncwarp();
+    const uint32_t cnt = active ? cnts[wl * NB + b] : 0u;
     // exclusive scan of cnt over the NB lanes of this window (NB <= 32, windows are NB-aligned inside a warp)
     uint32_t off = cnt;
 #pragma unroll
@@ -143,14 +149,22 @@ __global__ void __launch_bounds__(128, 3)
         if (b >= d) off += o;
     }
     off -= cnt;
-    // ---- phase 2: lists
-    if (active) {
-        const int8_t *row = digits + wl * dstride;
-        uint16_t *lst = lists + (size_t)wl * (2 * nmax) + off;
-        uint32_t e = 0;
-        for (uint32_t p = 0; p < n2; p++) {
+    __syncwarp();
+    if (active) cnts[wl * NB + b] = off;  // becomes the bucket's write cursor
+    __syncwarp();
+#pragma unroll 1
+    for (int r = 0; r < WPW; r++) {
+        if (w0 + r >= NWIN) break;
+        const bool row_top = (w0 + r == NWIN - 1);
+        const int8_t *row = digits + r * dstride;
+        uint16_t *lst = lists + (size_t)r * (2 * nmax);
+        for (uint32_t p = lane_id; p < n2; p += 32) {
             int d = row[p];
-            if (bucket_of(d, p) == b) lst[e++] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
+            int ad = d < 0 ? -d : d;
+            if (ad) {
+                uint32_t pos = atomicAdd(&cnts[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
+                lst[pos] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
+            }
         }
     }
     __syncwarp();

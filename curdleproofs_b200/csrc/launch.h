@@ -80,7 +80,8 @@ struct fixed_seg_t {
     uint32_t extra_base;    // 0 = none, else 1 + table base index of one more pair ...
     uint32_t extra_scalar;  // ... whose scalar is scalars[scalars_off + extra_scalar]
     uint32_t out_idx;       // result goes to out_jac[out_idx]
-    uint32_t pad[2];
+    uint32_t addv_off;      // plus addv_n (<= 32) device-resident affine points var_pts[addv_off ..] added as they are: short sums such as
+    uint32_t addv_n;        // D = B - beta^-1 sum(G) + alpha sum(Hvec) or A' = A + T_1 + U_1 stay one launch
 };
 struct fixed_kparams_t {
     int c, nw;
@@ -91,7 +92,7 @@ cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint
 cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t *table);
 cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half);
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
-                             const fixed_kparams_t &kp, uint32_t *out_jac);
+                             const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac);
 
 // which: 0 = raw IMAD.WIDE chains (128 multiply-adds / thread / iteration), 1 = Fp mul chain, 2 = Fp sqr chain (1 / thread / iteration)
 cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, int threads, int iters);
@@ -106,7 +107,7 @@ inline uint32_t msm_dig_rowstride(size_t nmax) { return (uint32_t)((2 * nmax + 1
 inline size_t msm_dig_bytes(int c, size_t nmax, size_t count) { return count * (size_t)msm_nwin_for(c) * msm_dig_rowstride(nmax); }
 __host__ __device__ inline size_t msm_smem_per_warp(int c, size_t nmax) {
     size_t wpw = 32 >> (c - 1), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
-    return (wpw * dstride + wpw * 2 * nmax * sizeof(uint16_t) + 15) & ~size_t(15);
+    return (wpw * dstride + wpw * 2 * nmax * sizeof(uint16_t) + 32 * sizeof(uint32_t) + 15) & ~size_t(15);
 }
 inline size_t msm_smem_bytes(int c, size_t nmax) { return 4 * msm_smem_per_warp(c, nmax); }
 // bucket sums of `count` MSMs: [msm][window][bucket] Jacobian points

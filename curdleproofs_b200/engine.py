@@ -22,7 +22,7 @@ class FixedSeg(ctypes.Structure):
     """cdp_fixed_seg (include/cdp_msm.h)."""
     _fields_ = [("base_off", c_uint32), ("scalars_off", c_uint32), ("n", c_uint32), ("sel_h", c_uint32), ("sel_val", c_uint32),
                 ("remap_from", c_uint32), ("remap_delta", c_uint32), ("extra_base", c_uint32), ("extra_scalar", c_uint32),
-                ("out_idx", c_uint32), ("reserved", c_uint32 * 2)]
+                ("out_idx", c_uint32), ("addv_off", c_uint32), ("addv_n", c_uint32)]
 
 
 class _MsmDesc(ctypes.Structure):
@@ -51,13 +51,14 @@ _SIGS = {
     "cdp_host_free": (None, [c_void_p, c_void_p]),
     "cdp_msm_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_sum_jacobian_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_sum_groups_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "cdp_fixed_table_create": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_void_p)]),
     "cdp_fixed_table_destroy": (None, [c_void_p, c_void_p]),
     "cdp_fixed_table_bytes": (c_size_t, [c_void_p]),
     "cdp_fixed_table_bases": (c_size_t, [c_void_p]),
     "cdp_msm_fixed": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
-    "cdp_msm_fixed_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "cdp_msm_fixed_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cdp_profile_enable": (c_int, [c_void_p, c_int]),
     "cdp_profile_reset": (c_int, [c_void_p]),
     "cdp_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(c_uint64)]),
@@ -238,25 +239,29 @@ class Engine:
         self._check(self._lib.cdp_msm_fixed(self._h, table.handle, base_off, _buf(scalars) if n else None, n, out), "cdp_msm_fixed")
         return bytes(out)
 
-    def msm_fixed_batch(self, table: "FixedTable", scalars: bytes, segs: list) -> list[bytes]:
+    def msm_fixed_batch(self, table: "FixedTable", scalars: bytes, segs: list, var_pts: bytes = b"") -> list[bytes]:
         """A batch of cdp_fixed_seg segments over one scalar array (host convenience over cdp_msm_fixed_batch_dev)."""
         lib, h = self._lib, self._h
         n_out = max(s.out_idx for s in segs) + 1
         arr = (FixedSeg * len(segs))(*segs)
         d_sc = lib.cdp_dev_alloc(h, max(1, len(scalars)))
+        d_vp = lib.cdp_dev_alloc(h, max(1, len(var_pts)))
         d_sg = lib.cdp_dev_alloc(h, ctypes.sizeof(arr))
         d_out = lib.cdp_dev_alloc(h, n_out * JACOBIAN_BYTES)
         try:
             sb = _buf(scalars)
             self._check(lib.cdp_h2d(h, d_sc, sb, len(scalars)), "cdp_h2d")
             self._check(lib.cdp_h2d(h, d_sg, arr, ctypes.sizeof(arr)), "cdp_h2d")
+            if var_pts:
+                vb = _buf(var_pts)
+                self._check(lib.cdp_h2d(h, d_vp, vb, len(var_pts)), "cdp_h2d")
             self.sync()
-            self._check(lib.cdp_msm_fixed_batch_dev(h, table.handle, d_sc, d_sg, len(segs), 0, d_out), "cdp_msm_fixed_batch_dev")
+            self._check(lib.cdp_msm_fixed_batch_dev(h, table.handle, d_sc, d_sg, len(segs), 0, d_vp, d_out), "cdp_msm_fixed_batch_dev")
             out = (ctypes.c_uint8 * (n_out * JACOBIAN_BYTES))()
             self._check(lib.cdp_d2h(h, out, d_out, n_out * JACOBIAN_BYTES), "cdp_d2h")
             self.sync()
         finally:
-            for d in (d_sc, d_sg, d_out):
+            for d in (d_sc, d_sg, d_out, d_vp):
                 lib.cdp_dev_free(h, d)
         raw = bytes(out)
         return [raw[i * JACOBIAN_BYTES:(i + 1) * JACOBIAN_BYTES] for i in range(n_out)]

@@ -200,6 +200,7 @@ struct SegSpec {
     size_t sel_h = 0, sel_val = 0, remap_from = 0xFFFFFFFFu, remap_delta = 0;
     long fextra_base = -1;
     size_t fextra_scalar = 0;
+    size_t addv_rel = 0, addv_n = 0;  // device-resident points of the proof block added with coefficient 1
 };
 SegSpec fix_seg(size_t base_off, size_t scal_rel, size_t n) {
     SegSpec s;
@@ -263,6 +264,7 @@ void build_stage(Lane *p, MsmStage &st, const std::vector<SegSpec> &specs, size_
                     fs.extra_base = sp.fextra_base >= 0 ? (uint32_t)(sp.fextra_base + 1) : 0;
                     fs.extra_scalar = (uint32_t)sp.fextra_scalar;
                     fs.out_idx = (uint32_t)slot;
+                    fs.addv_off = (uint32_t)(bp + sp.addv_rel); fs.addv_n = (uint32_t)sp.addv_n;
                 } else {
                     cdp_msm_seg &sg = sl.segs[slot];
                     sg.pts_off = (uint32_t)(sp.absolute ? sp.pts_rel : bp + sp.pts_rel);
@@ -336,7 +338,7 @@ int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_cop
     p->h2d_bytes += B * st.scalars_per_proof * 32;
     size_t out_off = 0;
     for (auto &sl : st.subs) {
-        if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
+        if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144));
         else PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
         out_off += B * sl.K;
     }
@@ -444,12 +446,15 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
         v[S2_A2] = {p->o_X + X_R, false, 5, 2, -1};    // cm_A.T_2 = r_k R + r_a H                  same_scalar_argument.rs:60
         v[S2_U2] = {p->o_X + X_S, false, 7, 2, -1};    // cm_U.T_2 = k S + r_u H
         v[S2_B2] = {p->o_X + X_S, false, 9, 2, -1};    // cm_B.T_2 = r_k S + r_b H
-        v[S2_AP] = {p->o_X + X_A2, false, 11, 3, -1};  // A' = A + cm_T.T_1 + cm_U.T_1 = A + r_t G_t + r_u G_u   curdleproofs.rs:131
+        v[S2_AP] = fix_seg(cGt, 12, 2);                // A' = A + cm_T.T_1 + cm_U.T_1 = A + r_t G_t + r_u G_u   curdleproofs.rs:131
+        v[S2_AP].addv_rel = p->o_X + X_A2; v[S2_AP].addv_n = 1;
         build_stage(p, p->st2, v, 14);
         p->st2.aff_region = p->reg2;
     }
     build_stage(p, p->st3, {fix_seg(0, 0, n)}, n);                                 // C     grand_product_argument.rs:76
-    build_stage(p, p->st4, {{p->o_X + X_B, false, 0, 3, -1},                       // D = B - beta^-1 sum(G) + alpha sum(Hvec)   grand_product_argument.rs:132
+    SegSpec segD = fix_seg(cGsum, 1, 2);                                           // D = B - beta^-1 sum(G) + alpha sum(Hvec)   grand_product_argument.rs:132
+    segD.addv_rel = p->o_X + X_B; segD.addv_n = 1;
+    build_stage(p, p->st4, {segD,
                             fix_seg(0, 3, n),                                      // B_c   inner_product_argument.rs:126
                             fix_seg(0, 3 + n, n)},                                 // B_d = msm(G', r_d) = msm(G|Hvec, r_d o u)   :127
                 2 * n + 3);
@@ -523,17 +528,8 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     int rc = CDP_OK;
     // CRS block + the trailing all-zero point
     std::vector<uint8_t> zero(96, 0);
-    rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 7) * 96);
+    rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 9) * 96);  // crs_points here = the CRS followed by sum(G), sum(Hvec) (cdp_prover_create_lanes)
     rc |= cdp_h2d(ctx, p->d_pts + total_pts * 96, zero.data(), 96);
-    {   // sum(G), sum(Hvec): CRS constants (the reference keeps them as crs.G_sum / crs.H_sum, src/crs.rs:46-47)
-        std::vector<uint8_t> ones(32 * ell, 0), sums(2 * 144), aff(2 * 96);
-        for (size_t i = 0; i < ell; i++) ones[32 * i] = 1;
-        rc |= cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
-        rc |= cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
-        rc |= cdp_normalize_batch(ctx, sums.data(), 2, aff.data());
-        rc |= cdp_h2d(ctx, p->d_pts + cGsum * 96, aff.data(), 2 * 96);
-        rc |= cdp_sync(ctx);
-    }
     rc |= cdp_h2d(ctx, p->d_gsrc, gsrc.data(), gsrc.size() * 4);
     rc |= cdp_h2d(ctx, p->d_gdst, gdst.data(), gdst.size() * 4);
     rc |= cdp_h2d(ctx, p->d_isrc, isrc.data(), isrc.size() * 4);
@@ -566,13 +562,13 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     // ---- stage 0: instance to the device, working vectors assembled, transcript openings compressed
     t0 = now_ms();
     if (!resident) {
-        for (size_t pr = 0; pr < B; pr++) {
+        parallel_for(T, B, [&](size_t pr) {
             uint8_t *dst = p->h_in + pr * 4 * ell * 96;
             memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
             memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
             memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
             memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
-        }
+        });
         memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
         PTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
         PTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
@@ -1003,11 +999,20 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     p->max_batch = max_batch;
     size_t per_lane = (max_batch + lanes - 1) / lanes;
     int threads_per_lane = std::max(1, host_threads / lanes);
-    {   // CRS digit table: G | Hvec | H | G_t | G_u.  CDP_FIXED_BITS overrides the window width (default 16: 50 MB per base)
+    // CRS digit table: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec) (the last two are the reference's crs.G_sum / crs.H_sum,
+    // src/crs.rs:46-47).  CDP_FIXED_BITS overrides the window width (default 16: 50 MB per base)
+    std::vector<uint8_t> crs_ext((ell + 9) * 96);
+    {
+        memcpy(crs_ext.data(), crs_points, (ell + 7) * 96);
+        std::vector<uint8_t> ones(32 * ell, 0), sums(2 * 144);
+        for (size_t i = 0; i < ell; i++) ones[32 * i] = 1;
+        int rc = cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
+        if (rc == CDP_OK) rc = cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
+        if (rc == CDP_OK) rc = cdp_normalize_batch(ctx, sums.data(), 2, crs_ext.data() + (ell + 7) * 96);
         int bits = 0;
         if (const char *e = getenv("CDP_FIXED_BITS")) bits = atoi(e);
-        int rc = cdp_fixed_table_create(ctx, crs_points, ell + 7, bits, &p->table);
-        if (rc != CDP_OK) { p->err = std::string("fixed table: ") + cdp_last_error(ctx); delete p; return rc; }
+        if (rc == CDP_OK) rc = cdp_fixed_table_create(ctx, crs_ext.data(), ell + 9, bits, &p->table);
+        if (rc != CDP_OK) { delete p; return rc; }
         p->table_ctx = ctx;
     }
     for (int i = 0; i < lanes; i++) {
@@ -1017,7 +1022,7 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
             p->owned.push_back(c);
         }
         Lane *l = nullptr;
-        int rc = lane_create(&l, c, p->table, ell, crs_points, per_lane, threads_per_lane);
+        int rc = lane_create(&l, c, p->table, ell, crs_ext.data(), per_lane, threads_per_lane);
         if (rc != CDP_OK) { cdp_prover_destroy(p); return rc; }
         p->lanes.push_back(l);
     }

@@ -12,7 +12,9 @@
 //   * every left-hand side the reference builds with scalar-muls and size-m MSMs (`point_lhs`, C_a, D_a, ...) is linear in
 //     points that are already in HBM, so the eight `accumulate_check`s of a proof collapse into ONE msm over
 //     [CRS | R | S | T | U | M | proof points] with host-computed scalars, compared with the identity -- the reference's own
-//     MsmAccumulator idea (random factor per check, src/msm_accumulator.rs:44) taken to its end: no HashMap, a fixed slot table;
+//     MsmAccumulator idea (random factor per check, src/msm_accumulator.rs:44) taken to its end: no HashMap, a fixed slot table.
+//     The CRS part of that msm (G | Hvec | H | G_t | G_u, n + 3 bases shared by every proof) goes through the fixed-base digit
+//     table; the per-proof part (4 ell + 1 + proof points) through the variable-base kernel; the two partial sums are added;
 //   * the four point equalities of SameScalar are checked exactly as four short MSMs that must be the identity;
 //   * only two values have to come back mid-transcript: D (grand_product_argument.rs:223) and A' (curdleproofs.rs:255).
 #include <algorithm>
@@ -50,6 +52,19 @@ void parallel_for(int threads, size_t n, F f) {
     for (auto &th : pool) th.join();
 }
 void put_fr(uint8_t *dst, const Fr &x) { x.to_bytes(dst); }
+// xs[i] <- xs[i]^-1 with one field inversion (Montgomery's trick); no element may be zero (challenges never are)
+void batch_inverse(Fr *xs, size_t n) {
+    if (n == 0) return;
+    std::vector<Fr> pre(n);
+    Fr acc = Fr::one();
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; acc *= xs[i]; }
+    Fr inv = acc.inverse();
+    for (size_t i = n; i-- > 0;) {
+        Fr t = inv * pre[i];
+        inv *= xs[i];
+        xs[i] = t;
+    }
+}
 
 // indices of the proof's points in serialisation order (curdleproofs.rs:300-310 and the per-argument serialisers)
 struct ProofLayout {
@@ -79,14 +94,17 @@ struct VState {
 
 struct VLane {
     cdp_ctx *ctx = nullptr;
+    const cdp_fixed_table *table = nullptr;  // digit table of the CRS points (shared by the lanes)
+    cdp_fixed_seg *d_segF = nullptr, *d_segAf = nullptr;
     size_t ell = 0, n = 0, m = 0, max_batch = 0, np = 0;
     int threads = 1;
     std::string err = "ok";
+    double timing[3] = {0, 0, 0};  // last call: total, host compute, waiting for the GPU (ms)
     size_t crs_n = 0, VW = 0, o_R = 0, o_S = 0, o_T = 0, o_U = 0, o_M = 0, o_P = 0, o_X = 0, big_n = 0, reg = 0, chunks = 1;
     uint8_t *d_pts = nullptr, *d_in = nullptr, *d_Mjac = nullptr, *d_pcomp = nullptr, *d_status = nullptr;
     uint32_t *d_gsrc = nullptr, *d_gdst = nullptr, *d_isrc = nullptr, *d_idst = nullptr, *d_pdst = nullptr, *d_xsrc = nullptr, *d_xdst = nullptr;
     size_t g_pp = 0, i_pp = 0, x_pp = 0;
-    cdp_msm_seg *d_segA = nullptr, *d_segBig = nullptr, *d_segE = nullptr, *d_segSum = nullptr;
+    cdp_msm_seg *d_segBig = nullptr, *d_segE = nullptr;
     uint8_t *d_scal = nullptr, *h_scal = nullptr, *d_jac = nullptr, *d_comp = nullptr, *h_comp = nullptr, *h_in = nullptr, *h_pcomp = nullptr,
             *h_status = nullptr;
     uint8_t H_comp[48];
@@ -108,31 +126,33 @@ void vlane_destroy(VLane *p) {
     cdp_ctx *c = p->ctx;
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_pcomp, (void *)p->d_status, (void *)p->d_gsrc,
                     (void *)p->d_gdst, (void *)p->d_isrc, (void *)p->d_idst, (void *)p->d_pdst, (void *)p->d_xsrc, (void *)p->d_xdst,
-                    (void *)p->d_segA, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_segSum, (void *)p->d_scal, (void *)p->d_jac,
+                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_scal, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
     for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status}) cdp_host_free(c, h);
     delete p;
 }
 
-int vlane_create(VLane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
+int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads) {
     size_t n = ell + NBL, m = 0;
     while (((size_t)1 << m) < n) m++;
     if (((size_t)1 << m) != n) return CDP_ERR_INVALID_ARG;
     VLane *p = new VLane();
-    p->ctx = ctx; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch; p->threads = std::max(1, host_threads);
+    p->ctx = ctx; p->table = table; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch; p->threads = std::max(1, host_threads);
     ProofLayout L(m);
     p->np = L.np;
     const size_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
     p->crs_n = n + 5;
-    // per-proof block: [CRS copy (n+5) | R | S | T | U | M | proof points | X]; the first big_n points are the accumulated MSM's bases
+    // coefficient slots of one proof's accumulated check: [CRS (n+5, incl. sum(G), sum(Hvec)) | R | S | T | U | M | proof points].
+    // On the device only the per-proof part exists per proof: block = [R | S | T | U | M | proof points | X], slot o lives at bp + o - crs_n.
     p->o_R = p->crs_n; p->o_S = p->o_R + ell; p->o_T = p->o_S + ell; p->o_U = p->o_T + ell; p->o_M = p->o_U + ell; p->o_P = p->o_M + 1;
     p->big_n = p->o_P + L.np;
     p->o_X = p->big_n;
-    p->VW = p->o_X + X_COUNT;
-    p->chunks = (p->big_n + 2047) / 2048;
-    p->reg = p->crs_n + max_batch * p->VW;  // affine partial sums when the accumulated MSM needs more than one 2048-point chunk
-    size_t total_pts = p->reg + max_batch * p->chunks;
+    p->VW = p->o_X + X_COUNT - p->crs_n;
+    const size_t var_n = p->big_n - p->crs_n;
+    p->chunks = (var_n + 2047) / 2048;
+    p->reg = p->crs_n + max_batch * p->VW;
+    size_t total_pts = p->reg;
     if (total_pts >= ((size_t)1 << 31)) { delete p; return CDP_ERR_TOO_LARGE; }
     bool ok = true;
     auto dalloc = [&](size_t bytes) { void *d = cdp_dev_alloc(ctx, bytes); ok = ok && d; return d; };
@@ -149,16 +169,15 @@ int vlane_create(VLane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_point
     p->d_scal = (uint8_t *)dalloc(max_batch * scal_pp * 32);
     p->h_scal = (uint8_t *)halloc(max_batch * scal_pp * 32);
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
-    p->d_jac = (uint8_t *)dalloc(max_batch * (p->chunks + 5) * 144);
+    p->d_jac = (uint8_t *)dalloc(max_batch * (p->chunks + 6) * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * out_pp * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * out_pp * 48);
     // tables
     std::vector<uint32_t> gsrc, gdst, isrc, idst, pdst, xsrc, xdst;
-    std::vector<cdp_msm_seg> segA, segBig, segE, segSum;
+    std::vector<cdp_msm_seg> segBig(max_batch * p->chunks), segE;
+    std::vector<cdp_fixed_seg> segF(max_batch), segAf(2 * max_batch);
     for (size_t pr = 0; pr < max_batch; pr++) {
-        size_t bp = p->crs_n + pr * p->VW;
-        for (size_t i = 0; i < p->crs_n; i++) { gsrc.push_back((uint32_t)i); gdst.push_back((uint32_t)(bp + i)); }
-        if (pr == 0) p->g_pp = gsrc.size();
+        size_t bp = p->crs_n + pr * p->VW - p->crs_n;  // device index of coefficient slot o of this proof = bp + o   (o >= crs_n)
         const size_t dsts[4] = {p->o_R, p->o_S, p->o_T, p->o_U};
         for (int v = 0; v < 4; v++)
             for (size_t i = 0; i < ell; i++) { isrc.push_back((uint32_t)(pr * 4 * ell + v * ell + i)); idst.push_back((uint32_t)(bp + dsts[v] + i)); }
@@ -174,35 +193,46 @@ int vlane_create(VLane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_point
             {X_E4, P(L.B2)}, {X_E4 + 1, P(L.U2)}, {X_E4 + 2, P(L.S)}, {X_E4 + 3, (uint32_t)cH}};
         for (auto &e : xs) { xsrc.push_back(e.second); xdst.push_back((uint32_t)(bp + p->o_X + e.first)); }
         if (pr == 0) p->x_pp = xsrc.size();
-        // stage A: D, A'  (scalars: 6 per proof)
-        segA.push_back({(uint32_t)(bp + p->o_X + X_B), (uint32_t)(pr * 6), 3, 0});
-        segA.push_back({(uint32_t)(bp + p->o_X + X_A), (uint32_t)(pr * 6 + 3), 3, 0});
-        // final stage: accumulated MSM in <= 2048-point chunks, then the four SameScalar equalities
+        // stage A: D = B + (-beta^-1) sum(G) + alpha sum(Hvec) (two table pairs + one plain point), A' = A + T_1 + U_1 (three plain points)
+        {
+            cdp_fixed_seg &d = segAf[2 * pr], &a = segAf[2 * pr + 1];
+            memset(&d, 0, sizeof d); memset(&a, 0, sizeof a);
+            d.base_off = (uint32_t)cGsum; d.scalars_off = (uint32_t)(pr * 6 + 1); d.n = 2; d.remap_from = 0xFFFFFFFFu; d.out_idx = (uint32_t)(2 * pr);
+            d.addv_off = (uint32_t)(bp + p->o_X + X_B); d.addv_n = 1;
+            a.remap_from = 0xFFFFFFFFu; a.out_idx = (uint32_t)(2 * pr + 1);
+            a.addv_off = (uint32_t)(bp + p->o_X + X_A); a.addv_n = 3;
+        }
+        // final stage: the per-proof part of the accumulated MSM in <= 2048-point chunks (chunk-major tables: one launch per chunk
+        // leaves the partial sums as [chunk][proof]), its CRS part through the digit table, then the four SameScalar equalities
         for (size_t c = 0; c < p->chunks; c++) {
-            size_t lo = c * 2048, cnt = std::min<size_t>(2048, p->big_n - lo);
-            segBig.push_back({(uint32_t)(bp + lo), (uint32_t)(pr * scal_pp + lo), (uint32_t)cnt, 0});
+            size_t lo = p->crs_n + c * 2048, cnt = std::min<size_t>(2048, p->big_n - lo);
+            segBig[c * max_batch + pr] = {(uint32_t)(bp + lo), (uint32_t)(pr * scal_pp + lo), (uint32_t)cnt, 0};
+        }
+        {
+            cdp_fixed_seg &f = segF[pr];
+            memset(&f, 0, sizeof f);
+            f.base_off = 0; f.scalars_off = (uint32_t)(pr * scal_pp); f.n = (uint32_t)(n + 3); f.remap_from = 0xFFFFFFFFu; f.out_idx = (uint32_t)pr;
         }
         const size_t eoff[4] = {X_E1, X_E2, X_E3, X_E4}, elen[4] = {3, 4, 3, 4}, esc[4] = {0, 3, 7, 10};
         for (int e = 0; e < 4; e++)
             segE.push_back({(uint32_t)(bp + p->o_X + eoff[e]), (uint32_t)(pr * scal_pp + p->big_n + esc[e]), (uint32_t)elen[e], 0});
-        segSum.push_back({(uint32_t)(p->reg + pr * p->chunks), 0, (uint32_t)p->chunks, 0});  // all-ones scalars at offset 0 of a small buffer
     }
     auto up32 = [&](std::vector<uint32_t> &v, uint32_t *&d) { d = (uint32_t *)dalloc(v.size() * 4); return d ? cdp_h2d(ctx, d, v.data(), v.size() * 4) : CDP_ERR_CUDA; };
     auto upseg = [&](std::vector<cdp_msm_seg> &v, cdp_msm_seg *&d) { d = (cdp_msm_seg *)dalloc(v.size() * sizeof(cdp_msm_seg)); return d ? cdp_h2d(ctx, d, v.data(), v.size() * sizeof(cdp_msm_seg)) : CDP_ERR_CUDA; };
     int rc = CDP_OK;
     if (!ok) rc = CDP_ERR_CUDA;
-    if (!rc) rc |= up32(gsrc, p->d_gsrc) | up32(gdst, p->d_gdst) | up32(isrc, p->d_isrc) | up32(idst, p->d_idst) | up32(pdst, p->d_pdst) |
-                   up32(xsrc, p->d_xsrc) | up32(xdst, p->d_xdst) | upseg(segA, p->d_segA) | upseg(segBig, p->d_segBig) | upseg(segE, p->d_segE) |
-                   upseg(segSum, p->d_segSum);
+    if (!rc) rc |= up32(isrc, p->d_isrc) | up32(idst, p->d_idst) | up32(pdst, p->d_pdst) |
+                   up32(xsrc, p->d_xsrc) | up32(xdst, p->d_xdst) | upseg(segBig, p->d_segBig) | upseg(segE, p->d_segE);
     if (!rc) {
-        std::vector<uint8_t> zero(96, 0), ones(32 * std::max<size_t>(ell, 8), 0), sums(2 * 144), aff(2 * 96);
-        for (size_t i = 0; i < std::max<size_t>(ell, 8); i++) ones[32 * i] = 1;
-        rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 7) * 96);
+        p->d_segF = (cdp_fixed_seg *)dalloc(segF.size() * sizeof(cdp_fixed_seg));
+        rc |= p->d_segF ? cdp_h2d(ctx, p->d_segF, segF.data(), segF.size() * sizeof(cdp_fixed_seg)) : CDP_ERR_CUDA;
+        p->d_segAf = (cdp_fixed_seg *)dalloc(segAf.size() * sizeof(cdp_fixed_seg));
+        rc |= p->d_segAf ? cdp_h2d(ctx, p->d_segAf, segAf.data(), segAf.size() * sizeof(cdp_fixed_seg)) : CDP_ERR_CUDA;
+    }
+    if (!rc) {
+        std::vector<uint8_t> zero(96, 0);
+        rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 9) * 96);  // the CRS followed by sum(G), sum(Hvec) (cdp_verifier_create)
         rc |= cdp_h2d(ctx, p->d_pts + total_pts * 96, zero.data(), 96);
-        rc |= cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
-        rc |= cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
-        rc |= cdp_normalize_batch(ctx, sums.data(), 2, aff.data());
-        rc |= cdp_h2d(ctx, p->d_pts + cGsum * 96, aff.data(), 2 * 96);
         rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_comp);
         rc |= cdp_d2h(ctx, p->h_comp, p->d_comp, 48);
         rc |= cdp_sync(ctx);
@@ -214,34 +244,34 @@ int vlane_create(VLane **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_point
     return CDP_OK;
 }
 
-// s_i = prod_{j : bit (m-1-j) of i set} gamma_j  (get_verification_scalars_bitstring, src/util.rs:40-64), built by doubling
+// s_i = prod_{j : bit (m-1-j) of i set} gamma_j  (get_verification_scalars_bitstring, src/util.rs:40-64), built by doubling: n products
 void s_vector(std::vector<Fr> &s, const std::vector<Fr> &gam, size_t m) {
     size_t n = (size_t)1 << m;
-    s.assign(n, Fr::one());
-    for (size_t j = 0; j < m; j++) {          // challenge j controls bit m-1-j
+    s.resize(n);
+    s[0] = Fr::one();
+    for (size_t j = m; j-- > 0;) {            // challenge j controls bit m-1-j; low bits first
         size_t bit = (size_t)1 << (m - 1 - j);
-        for (size_t i = 0; i < n; i++)
-            if (i & bit) s[i] *= gam[j];
+        for (size_t i = 0; i < bit; i++) s[bit + i] = s[i] * gam[j];
     }
 }
 
 int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
     if (B == 0) return CDP_OK;
+    const double t_start = now_ms();
+    double t_host = 0, t_wait = 0, t0 = now_ms();
     const size_t ell = p->ell, n = p->n, m = p->m, NP = p->np;
     const int T = p->threads;
     const ProofLayout L(m);
     const size_t psz = cdp_proof_size(ell), scal_pp = p->big_n + 14, Moff = p->max_batch * 4 * ell;
     // ---- stage 0: instance + proof points to the device
-    for (size_t pr = 0; pr < B; pr++) {
+    memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
+    // instance vectors -> pinned staging; proof parsing: points -> h_pcomp (serialisation order), scalars -> state
+    parallel_for(T, B, [&](size_t pr) {
         uint8_t *dst = p->h_in + pr * 4 * ell * 96;
         memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
         memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
         memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
         memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
-    }
-    memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
-    // proof parsing: points -> h_pcomp (serialisation order), scalars -> state
-    parallel_for(T, B, [&](size_t pr) {
         VState &s = p->vs[pr];
         s.status = 1;
         const uint8_t *r = in->proofs + pr * psz;
@@ -251,11 +281,11 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         auto fr = [&](Fr &x) { if (!Fr::from_bytes(r, x)) s.status = 2; r += 32; };
         pts(9); fr(s.r_p); pts(2 + 4 * m); fr(s.c_final); fr(s.d_final); pts(4); fr(s.z_k); fr(s.z_t); fr(s.z_u); pts(3 + 6 * m); fr(s.x_final);
     });
+    t_host += now_ms() - t0;
     VTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
     VTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
     VTRY(cdp_h2d(p->ctx, p->d_pcomp, p->h_pcomp, B * NP * 48));
     VTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));
-    VTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_gsrc, p->d_gdst, B * p->g_pp));
     VTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_pp));
     VTRY(cdp_decompress_dev(p->ctx, p->d_pcomp, p->d_pdst, B * NP, p->d_pts, p->d_status));
     VTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_xsrc, p->d_xdst, B * p->x_pp));
@@ -263,7 +293,10 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     VTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp + B * 4 * ell * 48));
     VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * 4 * ell + B) * 48));
     VTRY(cdp_d2h(p->ctx, p->h_status, p->d_status, B * NP));
+    t0 = now_ms();
     VTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
+    t0 = now_ms();
 
     // ---- host part 1: transcript up to the GrandProduct beta; scalars of D and A'
     std::vector<uint8_t> tu_comp(B * 2 * n * 48);
@@ -309,11 +342,15 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         put_fr(sc + 96, Fr::one()); put_fr(sc + 128, Fr::one()); put_fr(sc + 160, Fr::one());     // A' = A + cm_T.T_1 + cm_U.T_1
     });
     // ---- stage A: D and A' come back as encodings
+    t_host += now_ms() - t0;
     VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * 6 * 32));
-    VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segA, 2 * B, 3, 6 * B, p->d_jac));
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segAf, 2 * B, 2 * B, p->d_pts, p->d_jac));
     VTRY(cdp_normalize_dev(p->ctx, p->d_jac, 2 * B, nullptr, p->d_comp));
     VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, 2 * B * 48));
+    t0 = now_ms();
     VTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
+    t0 = now_ms();
 
     // ---- host part 2: rest of the transcript; the coefficient of every base in the accumulated check
     parallel_for(T, B, [&](size_t pr) {
@@ -338,8 +375,9 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
             s.tr->append_point("ipa_loop", pc + 48 * (L.LC + k)); s.tr->append_point("ipa_loop", pc + 48 * (L.LD + k));
             s.tr->append_point("ipa_loop", pc + 48 * (L.RC + k)); s.tr->append_point("ipa_loop", pc + 48 * (L.RD + k));
             s.gam[k] = s.tr->challenge("ipa_gamma");
-            s.gam_inv[k] = s.gam[k].inverse();
         }
+        s.gam_inv = s.gam;
+        batch_inverse(s.gam_inv.data(), m);  // one field inversion for the m challenges (the reference: batch_inversion, :234)
         s_vector(s.s_ipa, s.gam, m);
         s_vector(s.sinv_ipa, s.gam_inv, m);  // 1/s_i: the same products over the inverted challenges
         // same_scalar (same_scalar_argument.rs:110-136)
@@ -362,8 +400,9 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
             const size_t o[6] = {L.LA, L.LT, L.LU, L.RA, L.RT, L.RU};
             for (int q = 0; q < 6; q++) s.tr->append_point("same_msm_loop", pc + 48 * (o[q] + k));
             s.gam2[k] = s.tr->challenge("same_msm_gamma");
-            s.gam2_inv[k] = s.gam2[k].inverse();
         }
+        s.gam2_inv = s.gam2;
+        batch_inverse(s.gam2_inv.data(), m);
         s_vector(s.s_sm, s.gam2, m);
         // ---- coefficients.  check j contributes rho_j * (lhs_j - <x_j, V_j>); the proof is accepted iff the total is the identity
         const Fr *rho = s.rho;
@@ -410,6 +449,10 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         // (7), (8): R == a x vec_R, S == a x vec_S                                   curdleproofs.rs:293-294
         cf[oP + L.R] += rho[6]; cf[oP + L.S] += rho[7];
         for (size_t i = 0; i < ell; i++) { cf[oR + i] -= rho[6] * s.vec_a[i]; cf[oS + i] -= rho[7] * s.vec_a[i]; }
+        // sum(G) and sum(Hvec) are not table bases: their coefficients go onto every G_i / Hvec_i
+        for (size_t i = 0; i < ell; i++) cf[cG + i] += cf[cGsum];
+        for (size_t i = ell; i < n; i++) cf[cG + i] += cf[cHsum];
+        cf[cGsum] = cf[cHsum] = Fr::zero();
         uint8_t *sc = p->h_scal + pr * scal_pp * 32;
         for (size_t i = 0; i < p->big_n; i++) put_fr(sc + 32 * i, cf[i]);
         // SameScalar equalities (same_scalar_argument.rs:127-136), each as "sum == identity":
@@ -419,24 +462,23 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         const Fr e[14] = {one, alpha_ss, s.z_t.neg(), one, alpha_ss, s.z_k.neg(), s.z_t.neg(), one, alpha_ss, s.z_u.neg(), one, alpha_ss, s.z_k.neg(), s.z_u.neg()};
         for (int i = 0; i < 14; i++) put_fr(se + 32 * i, e[i]);
     });
-    // ---- final stage
+    // ---- final stage: per-proof part (one launch per 2048-point chunk) + CRS part (digit table) -> added per proof; the equalities
+    const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + 1;
+    t_host += now_ms() - t0;
     VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * scal_pp * 32));
-    VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segBig, B * p->chunks, std::min<size_t>(2048, p->big_n), B * p->big_n, p->d_jac));
-    VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + B * p->chunks * 144));
-    if (p->chunks > 1) {
-        // partial sums -> affine -> one short all-ones MSM per proof
-        VTRY(cdp_normalize_dev(p->ctx, p->d_jac, B * p->chunks, p->d_pts + p->reg * 96, nullptr));
-        std::vector<uint8_t> ones(32 * p->chunks, 0);
-        for (size_t i = 0; i < p->chunks; i++) ones[32 * i] = 1;
-        VTRY(cdp_sync(p->ctx));  // the big scalar upload from h_scal must have finished before the staging buffer is reused
-        memcpy(p->h_scal, ones.data(), ones.size());
-        VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, ones.size()));
-        VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segSum, B, p->chunks, B * p->chunks, p->d_jac));
+    for (size_t c = 0; c < p->chunks; c++) {
+        size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
+        VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
     }
-    // results: [B accumulated (proof-major, first of each chunk group when chunks == 1)] [4B equalities]
-    VTRY(cdp_normalize_dev(p->ctx, p->d_jac, B * p->chunks + 4 * B, nullptr, p->d_comp));
-    VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * p->chunks + 4 * B) * 48));
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segF, B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
+    VTRY(cdp_sum_groups_dev(p->ctx, p->d_jac, B, NS, B, p->d_jac + NS * B * 144));
+    VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
+    // results: [B accumulated sums] [4B equalities]
+    VTRY(cdp_normalize_dev(p->ctx, p->d_jac + NS * B * 144, 5 * B, nullptr, p->d_comp));
+    VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, 5 * B * 48));
+    t0 = now_ms();
     VTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
     for (size_t pr = 0; pr < B; pr++) {
         VState &s = p->vs[pr];
         auto is_inf = [&](const uint8_t *c) {
@@ -444,17 +486,20 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
             for (int i = 1; i < 48; i++) if (c[i]) return false;
             return true;
         };
-        bool okk = is_inf(p->h_comp + (p->chunks > 1 ? pr : pr * p->chunks) * 48);
-        for (int e = 0; e < 4; e++) okk = okk && is_inf(p->h_comp + (B * p->chunks + 4 * pr + e) * 48);
+        bool okk = is_inf(p->h_comp + pr * 48);
+        for (int e = 0; e < 4; e++) okk = okk && is_inf(p->h_comp + (B + 4 * pr + e) * 48);
         if (s.status == 1 && !okk) s.status = 0;
         ok_out[pr] = (uint8_t)s.status;
     }
+    p->timing[0] = now_ms() - t_start; p->timing[1] = t_host; p->timing[2] = t_wait;
     return CDP_OK;
 }
 
 }  // namespace
 
 struct cdp_verifier {
+    cdp_fixed_table *table = nullptr;
+    cdp_ctx *table_ctx = nullptr;
     std::vector<VLane *> lanes;
     std::vector<cdp_ctx *> owned;
     size_t ell = 0, max_batch = 0;
@@ -464,21 +509,43 @@ struct cdp_verifier {
 extern "C" void cdp_verifier_destroy(cdp_verifier *v) {
     if (!v) return;
     for (VLane *l : v->lanes) vlane_destroy(l);
+    if (v->table) cdp_fixed_table_destroy(v->table_ctx, v->table);
     for (cdp_ctx *c : v->owned) cdp_ctx_destroy(c);
     delete v;
 }
 extern "C" const char *cdp_verifier_last_error(const cdp_verifier *v) { return v ? v->err.c_str() : "null verifier"; }
+extern "C" void cdp_verifier_last_timing(const cdp_verifier *v, double out_ms[3]) {
+    for (int k = 0; k < 3; k++) {
+        out_ms[k] = 0;
+        if (v) for (VLane *l : v->lanes) out_ms[k] = std::max(out_ms[k], l->timing[k]);
+    }
+}
 extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads,
                                    int lanes) {
     if (!out || !ctx || !crs_points || max_batch == 0 || ell < 4) return CDP_ERR_INVALID_ARG;
     *out = nullptr;
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (host_threads <= 0) host_threads = hw;
-    if (lanes <= 0) lanes = max_batch >= 512 ? 4 : max_batch >= 64 ? 2 : 1;
+    if (lanes <= 0) lanes = max_batch >= 512 ? 8 : max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
     lanes = (int)std::min<size_t>((size_t)lanes, max_batch);
     cdp_verifier *v = new cdp_verifier();
     v->ell = ell; v->max_batch = max_batch;
     size_t per_lane = (max_batch + lanes - 1) / lanes;
+    // CRS digit table: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec) (crs.G_sum / crs.H_sum, src/crs.rs:46-47); CDP_FIXED_BITS overrides the width
+    std::vector<uint8_t> crs_ext((ell + 9) * 96);
+    {
+        memcpy(crs_ext.data(), crs_points, (ell + 7) * 96);
+        std::vector<uint8_t> ones(32 * ell, 0), sums(2 * 144);
+        for (size_t i = 0; i < ell; i++) ones[32 * i] = 1;
+        int rc = cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
+        if (rc == CDP_OK) rc = cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
+        if (rc == CDP_OK) rc = cdp_normalize_batch(ctx, sums.data(), 2, crs_ext.data() + (ell + 7) * 96);
+        int bits = 0;
+        if (const char *e = getenv("CDP_FIXED_BITS")) bits = atoi(e);
+        if (rc == CDP_OK) rc = cdp_fixed_table_create(ctx, crs_ext.data(), ell + 9, bits, &v->table);
+        if (rc != CDP_OK) { delete v; return rc; }
+        v->table_ctx = ctx;
+    }
     for (int i = 0; i < lanes; i++) {
         cdp_ctx *c = ctx;
         if (i > 0) {
@@ -486,7 +553,7 @@ extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell,
             v->owned.push_back(c);
         }
         VLane *l = nullptr;
-        int rc = vlane_create(&l, c, ell, crs_points, per_lane, std::max(1, host_threads / lanes));
+        int rc = vlane_create(&l, c, v->table, ell, crs_ext.data(), per_lane, std::max(1, host_threads / lanes));
         if (rc != CDP_OK) { cdp_verifier_destroy(v); return rc; }
         v->lanes.push_back(l);
     }

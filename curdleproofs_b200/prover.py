@@ -165,6 +165,7 @@ class BatchVerifier:
         lib.cdp_verifier_destroy.argtypes = [c_void_p]
         lib.cdp_verifier_last_error.restype = c_char_p
         lib.cdp_verifier_last_error.argtypes = [c_void_p]
+        lib.cdp_verifier_last_timing.argtypes = [c_void_p, POINTER(c_double)]
         lib.cdp_verify_batch.restype = c_int
         lib.cdp_verify_batch.argtypes = [c_void_p, c_size_t, POINTER(_VerifyInputs), c_void_p]
         self.engine, self.ell, self.max_batch = engine, ell, max_batch
@@ -187,6 +188,11 @@ class BatchVerifier:
             self.close()
         except Exception:
             pass
+
+    def last_timing(self) -> dict:
+        t = (c_double * 3)()
+        self._lib.cdp_verifier_last_timing(self._h, t)
+        return {"total_ms": t[0], "host_ms": t[1], "gpu_wait_ms": t[2]}
 
     def verify_batch(self, instances, proofs, rng_seeds=None) -> list[int]:
         B = len(instances)

@@ -117,6 +117,9 @@ int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scal
 /* d_out_jac = sum of `count` Jacobian points.  The multi-GPU combine of a base-range-sharded MSM: every rank all-gathers the
  * 144-byte partial sums (NCCL has no elliptic-curve reduction op) and adds them locally. */
 int cdp_sum_jacobian_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t count, uint8_t *d_out_jac);
+/* d_out_jac[g] = sum_{s < per_out} d_jac_in[s * group_stride + g] for g < n_out: adds the partial sums of many MSMs at once (the
+ * chunk sums and the fixed-base part of each proof's accumulated check, /root/reference/src/msm_accumulator.rs:55-68). */
+int cdp_sum_groups_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t n_out, size_t per_out, size_t group_stride, uint8_t *d_out_jac);
 
 /* A batch of MSMs over device-resident bases and scalars.  Segment i computes
  *   sum_{j < n} d_scalars[scalars_off + j] * d_pts[pts_off + j]   (offsets in elements, not bytes). */
@@ -153,14 +156,16 @@ int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base_off, const
  *   half pattern of a vector folded down to 2h entries, which is how the IPA / SameMSM round MSMs over *folded* bases
  *   (src/inner_product_argument.rs:158-161, src/same_multiscalar_argument.rs:107-112) are written over the original ones;
  *   gap(j) = remap_delta for j >= remap_from (a base list that skips some table entries), else 0;
- *   extra_base != 0 adds the pair (d_scalars[scalars_off + extra_scalar], B[extra_base - 1]) -- the `+ ip * H` term.
- * The result of segment i goes to d_out_jac[out_idx]. */
+ *   extra_base != 0 adds the pair (d_scalars[scalars_off + extra_scalar], B[extra_base - 1]) -- the `+ ip * H` term;
+ *   addv_n (<= 32) != 0 adds the device-resident affine points d_var_pts[addv_off .. addv_off + addv_n) with coefficient 1, so
+ *   short sums like D = B - beta^-1 G_sum + alpha H_sum (src/grand_product_argument.rs:223) are one segment.
+ * The result of segment i goes to d_out_jac[out_idx].  d_var_pts may be NULL when no segment has addv_n. */
 typedef struct {
     uint32_t base_off, scalars_off, n, sel_h, sel_val, remap_from, remap_delta, extra_base, extra_scalar, out_idx;
-    uint32_t reserved[2];
+    uint32_t addv_off, addv_n;
 } cdp_fixed_seg;
 int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
-                            size_t total_pairs, uint8_t *d_out_jac);
+                            size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac);
 
 /* Batched scalar multiplication / fold over device-resident points.  For every job j and element e < elems_per_job:
  *   d_pts[out_off + e] = ( (add_off != CDP_NONE ? d_pts[add_off + e] : O)

@@ -74,6 +74,8 @@ typedef struct cdp_verifier cdp_verifier;
 int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads, int lanes);
 void cdp_verifier_destroy(cdp_verifier *v);
 const char *cdp_verifier_last_error(const cdp_verifier *v);
+/* Timing of the last cdp_verify_batch call, max over lanes, in ms: total, host compute (transcripts, coefficients), waiting for the GPU. */
+void cdp_verifier_last_timing(const cdp_verifier *v, double out_ms[3]);
 typedef struct {
     const uint8_t *vec_R;     /* batch * ell affine */
     const uint8_t *vec_S;

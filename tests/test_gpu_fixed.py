@@ -102,6 +102,16 @@ def test_fixed_segments_select_remap_extra(engine, oracle, bases, table):
                              extra_base=0, extra_scalar=0, out_idx=out))
         want.append(oracle.msm(pts_of([4 + j + (3 if j >= 10 else 0) for j in pos]), sc_of([3 + j for j in pos])))
         out += 1
-    got = engine.msm_fixed_batch(table, sc, segs)
+    # plain device-resident points added to the sum (D = B + fixed part; A' = A + T_1 + U_1 with no fixed pairs at all)
+    var = bases[96 * 20:96 * 25] + bytes(96)   # five points and one at infinity
+    segs.append(FixedSeg(base_off=1, scalars_off=0, n=2, sel_h=0, sel_val=0, remap_from=0xFFFFFFFF, remap_delta=0, extra_base=0, extra_scalar=0,
+                         out_idx=out, addv_off=1, addv_n=1))
+    want.append(oracle.msm(bases[96:96 * 3] + var[96:96 * 2], sc[:64] + pr.fr_to_bytes(1)))
+    out += 1
+    segs.append(FixedSeg(base_off=0, scalars_off=0, n=0, sel_h=0, sel_val=0, remap_from=0xFFFFFFFF, remap_delta=0, extra_base=0, extra_scalar=0,
+                         out_idx=out, addv_off=0, addv_n=6))
+    want.append(oracle.msm(var, pr.fr_to_bytes(1) * 6))
+    out += 1
+    got = engine.msm_fixed_batch(table, sc, segs, var)
     for i, (g, w) in enumerate(zip(got, want)):
         assert oracle.compress_jac(g) == oracle.compress_jac(w), i

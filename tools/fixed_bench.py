@@ -37,11 +37,11 @@ for (B, K, n) in ((1024, 4, 128), (128, 4, 128), (1024, 5, 256), (128, 5, 256), 
     buf = (ctypes.c_uint8 * len(scal)).from_buffer_copy(scal)
     lib.cdp_h2d(h, d_sc, buf, len(scal)); lib.cdp_h2d(h, d_sg, segs, ctypes.sizeof(segs)); eng.sync()
     for it in range(2):
-        lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, B * K, nsc, d_out)
+        lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, B * K, nsc, None, d_out)
     eng.sync()
     eng.profile_reset(); eng.profile_enable(True)
     for it in range(5):
-        lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, B * K, nsc, d_out)
+        lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, B * K, nsc, None, d_out)
     eng.sync()
     p = eng.profile_read()["msm_fixed"]
     eng.profile_enable(False)
