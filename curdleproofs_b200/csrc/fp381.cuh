@@ -170,6 +170,99 @@ __device__ __forceinline__ void fp_final_sub(fp &r) {
     fp_select(r, t, r, borrow != 0);
 }
 
+// ---- Montgomery product, row-wise with two interleaved 64-bit-aligned accumulator arrays ("even / odd" form).
+// The column-wise product further down funnels every partial product through ONE 96-bit accumulator: 300 multiply-adds in a single
+// carry chain, so a warp can issue one only every ~6 cycles and the kernels built on it (168 registers, 3 warps per scheduler) keep the
+// integer pipe ~40% busy (profiles/r01_ncu_msm_buckets_v3.txt: issue active 39%, stall_wait 3.5).  Here the running value is
+//   T = sum_k X[k] 2^(32k) + sum_k Y[k] 2^(32(k+1))
+// and the partial products a_j * b_i of one row fall into X (even j) or Y (odd j) at 64-bit aligned positions, so a row is four
+// independent carry chains of six multiply-adds each (a_even*b_i, a_odd*b_i, p_even*m, p_odd*m), and consecutive rows overlap word by
+// word.  Dividing by 2^32 after each row swaps the roles of the arrays: the old Y is the new X, and the old X (whose word 0 is now zero),
+// moved down two words in place, is the new Y.
+#define CDP_MAD6(acc, m0, m1, m2, m3, m4, m5, s, top)                                                                                  \
+    asm("mad.lo.cc.u32 %0, %13, %19, %0;\n\t"                                                                                           \
+        "madc.hi.cc.u32 %1, %13, %19, %1;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %2, %14, %19, %2;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %3, %14, %19, %3;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %4, %15, %19, %4;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %5, %15, %19, %5;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %6, %16, %19, %6;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %7, %16, %19, %7;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %8, %17, %19, %8;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %9, %17, %19, %9;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %10, %18, %19, %10;\n\t"                                                                                        \
+        "madc.hi.cc.u32 %11, %18, %19, %11;\n\t"                                                                                        \
+        "addc.u32 %12, %12, 0;"                                                                                                         \
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), \
+          "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11]), "+r"(top)                                                                         \
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(s))
+// Y[0] += X[1]; then X <- (X >> 64) + a_odd * bi (in place, ascending: every word is read before it is overwritten), carry-in from the add
+#define CDP_MAD6_RSHIFT(X, y0, m0, m1, m2, m3, m4, m5, s)                                                                              \
+    asm("add.cc.u32 %12, %12, %1;\n\t"                                                                                                 \
+        "madc.lo.cc.u32 %0, %13, %19, %2;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %1, %13, %19, %3;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %2, %14, %19, %4;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %3, %14, %19, %5;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %4, %15, %19, %6;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %5, %15, %19, %7;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %6, %16, %19, %8;\n\t"                                                                                          \
+        "madc.hi.cc.u32 %7, %16, %19, %9;\n\t"                                                                                          \
+        "madc.lo.cc.u32 %8, %17, %19, %10;\n\t"                                                                                         \
+        "madc.hi.cc.u32 %9, %17, %19, %11;\n\t"                                                                                         \
+        "madc.lo.cc.u32 %10, %18, %19, 0;\n\t"                                                                                          \
+        "madc.hi.u32 %11, %18, %19, 0;"                                                                                                 \
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]), "+r"(X[9]),       \
+          "+r"(X[10]), "+r"(X[11]), "+r"(y0)                                                                                            \
+        : "r"(m0), "r"(m1), "r"(m2), "r"(m3), "r"(m4), "r"(m5), "r"(s))
+// one Montgomery step on (X aligned, Y offset): m = X[0] * (-p^-1); Y += p_odd * m; X += p_even * m (X[0] becomes 0), carry into Y[11]
+#define CDP_REDC_ROW(X, Y)                                                                                                   \
+    {                                                                                                                        \
+        const uint32_t mm = X[0] * FP_INV32;                                                                                 \
+        uint32_t drop = 0;                                                                                                   \
+        CDP_MAD6(Y, CDP_P(1), CDP_P(3), CDP_P(5), CDP_P(7), CDP_P(9), CDP_P(11), mm, drop);                                  \
+        CDP_MAD6(X, CDP_P(0), CDP_P(2), CDP_P(4), CDP_P(6), CDP_P(8), CDP_P(10), mm, Y[11]);                                 \
+    }
+// row i >= 1: X / Y are the aligned / offset arrays left by the previous row
+#define CDP_MUL_ROW(X, Y, bi)                                                                                                \
+    {                                                                                                                        \
+        CDP_MAD6_RSHIFT(X, Y[0], a.v[1], a.v[3], a.v[5], a.v[7], a.v[9], a.v[11], bi);                                       \
+        CDP_MAD6(Y, a.v[0], a.v[2], a.v[4], a.v[6], a.v[8], a.v[10], bi, X[11]);                                             \
+        CDP_REDC_ROW(Y, X)                                                                                                   \
+    }
+__device__ __forceinline__ void fp_mul_eo(fp &r, const fp &a, const fp &b) {
+    uint32_t E[12], O[12];
+#pragma unroll
+    for (int j = 0; j < 12; j += 2) {
+        uint64_t pe = (uint64_t)a.v[j] * b.v[0], po = (uint64_t)a.v[j + 1] * b.v[0];
+        E[j] = (uint32_t)pe; E[j + 1] = (uint32_t)(pe >> 32);
+        O[j] = (uint32_t)po; O[j + 1] = (uint32_t)(po >> 32);
+    }
+    CDP_REDC_ROW(E, O)
+    CDP_MUL_ROW(E, O, b.v[1]) CDP_MUL_ROW(O, E, b.v[2]) CDP_MUL_ROW(E, O, b.v[3]) CDP_MUL_ROW(O, E, b.v[4])
+    CDP_MUL_ROW(E, O, b.v[5]) CDP_MUL_ROW(O, E, b.v[6]) CDP_MUL_ROW(E, O, b.v[7]) CDP_MUL_ROW(O, E, b.v[8])
+    CDP_MUL_ROW(E, O, b.v[9]) CDP_MUL_ROW(O, E, b.v[10]) CDP_MUL_ROW(E, O, b.v[11])
+    // after row 11 the aligned array is O (its word 0 is zero) and the offset array is E: result = E + (O >> 32)
+    fp out;
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, %33;\n\t"
+        "addc.cc.u32 %10, %22, %34;\n\t"
+        "addc.u32 %11, %23, 0;"
+        : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(out.v[3]), "=r"(out.v[4]), "=r"(out.v[5]), "=r"(out.v[6]), "=r"(out.v[7]),
+          "=r"(out.v[8]), "=r"(out.v[9]), "=r"(out.v[10]), "=r"(out.v[11])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]),
+          "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]));
+    fp_final_sub(out);
+    r = out;
+}
+
 __device__ __forceinline__ void fp_mul_inl(fp &r, const fp &a, const fp &b) {
     uint32_t m[12];
     fp out;
@@ -237,12 +330,20 @@ __device__ __forceinline__ void fp_sqr_inl(fp &r, const fp &a) {
 #ifndef CDP_INLINE_FP_MUL
 static __device__ __noinline__ fp fp_mul_fn(const fp a, const fp b) {
     fp r;
+#ifdef CDP_FP_MUL_COLUMNWISE
     fp_mul_inl(r, a, b);
+#else
+    fp_mul_eo(r, a, b);
+#endif
     return r;
 }
 static __device__ __noinline__ fp fp_sqr_fn(const fp a) {
     fp r;
+#ifdef CDP_FP_SQR_VIA_MUL
+    fp_mul_eo(r, a, a);
+#else
     fp_sqr_inl(r, a);
+#endif
     return r;
 }
 __device__ __forceinline__ void fp_mul(fp &r, const fp &a, const fp &b) { r = fp_mul_fn(a, b); }

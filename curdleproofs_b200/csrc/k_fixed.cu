@@ -140,7 +140,8 @@ __device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint
 // gathered 96-byte table read and one mixed addition into the lane's Jacobian accumulator; the next item's point is fetched before the
 // current addition is issued, so the HBM gather latency (~1 us) hides behind ~3300 integer instructions.  The 32 partial sums are
 // folded with warp shuffles (5 full additions).
-__global__ void __launch_bounds__(128, 3) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
+template <int OCC>
+__global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
                                                        const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
                                                        const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -222,7 +223,10 @@ cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
                              const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac) {
     if (count == 0) return cudaSuccess;
-    k_fixed_msm<<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+    const int occ = tuned_occupancy("CDP_OCC_FIXED", 3);
+    if (occ == 5) k_fixed_msm<5><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+    else if (occ == 4) k_fixed_msm<4><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+    else k_fixed_msm<3><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
     return cudaGetLastError();
 }
 

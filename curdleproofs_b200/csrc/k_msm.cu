@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__
 }
 
 // dynamic shared memory, per warp: int8 digits[WPW][dstride] ; uint16 lists[WPW][2*nmax] ; uint32 counters[32]
-template <int C>
-__global__ void __launch_bounds__(128, 3)
+template <int C, int OCC>
+__global__ void __launch_bounds__(128, OCC)
     k_msm_buckets(const uint32_t *__restrict__ pts, const msm_seg_t *__restrict__ segs, const int8_t *__restrict__ dig, uint32_t rowstride,
                   uint32_t *__restrict__ bucket_sums /* [msm][nwin][NB] jacobian */, uint32_t nmax, uint32_t n_msm) {
     constexpr int NB = 1 << (C - 1);
@@ -219,7 +219,8 @@ cudaError_t CDP_CAT(launch_msm_buckets_c, MSM_C)(cudaStream_t st, const uint32_t
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     size_t smem = msm_smem_bytes(C, nmax);
-    auto kern = k_msm_buckets<C>;
+    const int occ = tuned_occupancy("CDP_OCC_BUCKETS", 3);
+    auto kern = occ == 5 ? k_msm_buckets<C, 5> : occ == 4 ? k_msm_buckets<C, 4> : k_msm_buckets<C, 3>;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -14,7 +14,8 @@ namespace cdp {
 //   (1,0) -> P = (x, y)      (0,1) -> phi(P) = (beta x, y)      (1,1) -> P + phi(P) = -phi^2(P) = (beta^2 x, -y)
 // so each step is one doubling plus at most one mixed addition.  Within one fold job all threads share the scalar, so
 // the add/skip pattern is warp-uniform whenever a job spans whole warps.
-__global__ void __launch_bounds__(128, 3) k_smul_jobs(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
+template <int OCC>
+__global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
                                                    const smul_job_t *__restrict__ jobs, uint32_t elems_per_job, uint32_t total,
                                                    uint32_t *__restrict__ out_jac) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,7 +67,10 @@ cudaError_t launch_smul_jobs(cudaStream_t st, const uint32_t *pts, const uint32_
                              uint32_t elems_per_job, uint32_t *out_jac) {
     uint32_t total = n_jobs * elems_per_job;
     if (total == 0) return cudaSuccess;
-    k_smul_jobs<<<(total + 127) / 128, 128, 0, st>>>(pts, scalars, jobs, elems_per_job, total, out_jac);
+    const int occ = tuned_occupancy("CDP_OCC_SMUL", 3);
+    if (occ == 5) k_smul_jobs<5><<<(total + 127) / 128, 128, 0, st>>>(pts, scalars, jobs, elems_per_job, total, out_jac);
+    else if (occ == 4) k_smul_jobs<4><<<(total + 127) / 128, 128, 0, st>>>(pts, scalars, jobs, elems_per_job, total, out_jac);
+    else k_smul_jobs<3><<<(total + 127) / 128, 128, 0, st>>>(pts, scalars, jobs, elems_per_job, total, out_jac);
     return cudaGetLastError();
 }
 

@@ -14,8 +14,17 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace cdp {
+
+// resident CTAs per SM a kernel is compiled for (register budget 65536 / (128 * occ)); env override for tuning runs
+inline int tuned_occupancy(const char *env, int dflt) {
+    const char *e = getenv(env);
+    int v = e ? atoi(e) : dflt;
+    return v >= 3 && v <= 5 ? v : dflt;
+}
+
 
 struct msm_seg_t {
     uint32_t pts_off;      // first base, in points, into the launch's base array
