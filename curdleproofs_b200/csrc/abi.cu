@@ -123,14 +123,14 @@ struct launch_scope {
 struct msm_cfg {
     int c, nwin;
 };
-// Window width by MSM size.  Cost model (lane-steps per MSM, GLV doubles the point count):
-//   accumulate  nwin(c) * 2n / 2^(c-1) mixed additions per lane (+ imbalance), reduce  nwin(c) * 2(c-1) full additions per lane.
-// For the in-proof sizes the reduction dominates at c = 6, so narrow windows win until n reaches the thousands.
+// Window width by MSM size.  Cost model per MSM in mixed-addition equivalents (GLV doubles the point count):
+//   accumulate  2n * nwin(c)     combine  2^(c-1) * (0.58 * 128 + 1.55 * nwin(c))   (Horner per bucket index, one reduction)
+// c = 6 from n ~ 400, c = 5 from n ~ 50 (e.g. n = 256: 15.1k at c = 5, 14.7k at c = 6; n = 128: 8.5k at c = 5, 9.4k at c = 4).
 // Override for tuning: CDP_MSM_THRESH="T6,T5,T4,T3" (smallest n that uses c = 6, 5, 4, 3).
 msm_cfg pick_cfg(size_t max_n) {
     static size_t T[4] = {0, 0, 0, 0};
     if (T[3] == 0) {
-        size_t d[4] = {1536, 160, 40, 10};
+        size_t d[4] = {384, 48, 12, 4};
         if (const char *e = getenv("CDP_MSM_THRESH")) sscanf(e, "%zu,%zu,%zu,%zu", &d[0], &d[1], &d[2], &d[3]);
         for (int i = 0; i < 4; i++) T[i] = d[i] ? d[i] : 1;
     }

@@ -19,7 +19,18 @@ __global__ void __launch_bounds__(128) k_msm_combine(const uint32_t *__restrict_
     g1j_set_inf(acc);
     if (valid) {
         const uint32_t *B = bucket_sums + 36 * ((size_t)i * nwin * nb + b);
-        g1j_load(acc, B + 36 * (size_t)(nwin - 1) * nb);
+        // top window: bucket b < nbt is spread over sp slots b*sp .. b*sp + sp - 1 (k_msm_buckets); the other lanes start from infinity
+        const int tb = 128 - c * (nwin - 1), nbt = tb > 0 ? (1 << tb) : 1, sp = nb / nbt >= 1 ? nb / nbt : 1;
+        if (b < nbt) {
+            const uint32_t *T = bucket_sums + 36 * (((size_t)i * nwin + (nwin - 1)) * nb + (size_t)b * sp);
+            g1j_load(acc, T);
+#pragma unroll 1
+            for (int s = 1; s < sp; s++) {
+                g1j W;
+                g1j_load(W, T + 36 * (size_t)s);
+                g1j_add(acc, acc, W);
+            }
+        }
 #pragma unroll 1
         for (int w = nwin - 2; w >= 0; w--) {
 #pragma unroll 1

@@ -13,13 +13,12 @@ namespace cdp {
 // k_msm_digits   one thread per (segment, pair): coalesced 128-bit scalar loads, GLV split (2n half-width "points": 2j -> P_j
 //                with k1, 2j+1 -> phi(P_j) with k2), signed radix-2^c recoding; digit rows (int8, one row per window) go to global
 //                memory once per MSM.
-// k_msm_buckets  one WARP per (MSM, group of 32 / 2^(c-1) windows); warps are independent (per-warp shared memory, __syncwarp only),
+// k_msm_buckets  one WARP per (MSM, group of 64 / 2^(c-1) windows); warps are independent (per-warp shared memory, __syncwarp only),
 //                so every MSM uses exactly ceil(NWIN / WPW) warps whatever the CTA shape.  Lane (w, b) owns bucket b of window w:
 //   phase 0  the warp's digit rows are staged global -> shared memory with 16-byte loads
-//   phase 1  each lane counts its bucket, a warp-shuffle scan over the nb lanes of the window gives list offsets
-//   phase 2  each lane writes its own index list (uint16 point id | sign bit) -- no atomics, no contention
-//   phase 3  each lane adds ITS OWN points (different lanes, different points => no serialisation); mixed adds
-//   phase 4  bucket sums go to global memory, [msm][window][bucket] (top window: the SP partial sums of a bucket are folded first)
+//   phase 1-2  counting sort of the point ids (uint16 id | sign bit) into one list per (window, bucket) slot, 64 slots per warp
+//   phase 3  the slots are ranked by load; lane l takes the l-th largest and the l-th smallest
+//   phase 4  each lane adds the points of its two slots (mixed adds) and writes the sums to [msm][window][slot]
 // k_msm_combine  (k_misc.cu) one thread per (MSM, bucket index): Horner over the windows FIRST (sum_w 2^(cw) B_{w,b}: the doublings run
 //                on 2^(c-1) lanes in parallel), THEN one weighted reduction sum_b (b+1) S_b per MSM -- instead of one reduction per window.
 // Handles infinity bases and zero scalars (digits 0) and all-equal scalars (one long list, still correct).
@@ -72,14 +71,15 @@ __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__
     }
 }
 
-// dynamic shared memory, per warp: int8 digits[WPW][dstride] ; uint16 lists[WPW][2*nmax] ; uint32 counters[32]
+// dynamic shared memory, per warp: int8 digits[WPW][dstride] ; uint16 lists[WPW][2*nmax] ; uint32 cnt[64], cur[64] ; uint8 order[64]
 template <int C, int OCC>
 __global__ void __launch_bounds__(128, OCC)
     k_msm_buckets(const uint32_t *__restrict__ pts, const msm_seg_t *__restrict__ segs, const int8_t *__restrict__ dig, uint32_t rowstride,
                   uint32_t *__restrict__ bucket_sums /* [msm][nwin][NB] jacobian */, uint32_t nmax, uint32_t n_msm) {
     constexpr int NB = 1 << (C - 1);
     constexpr int NWIN = (130 + C - 1) / C;
-    constexpr int WPW = 32 / NB;                    // windows per warp
+    constexpr int SLOTS = 64;                       // (window, bucket) slots per warp: two per lane
+    constexpr int WPW = SLOTS / NB;                 // windows per warp
     constexpr int G = (NWIN + WPW - 1) / WPW;       // warps per MSM
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane_id = threadIdx.x & 31;
@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(128, OCC)
     const size_t per_warp = msm_smem_per_warp(C, nmax);
     int8_t *digits = reinterpret_cast<int8_t *>(smem + (threadIdx.x >> 5) * per_warp);
     uint16_t *lists = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(digits) + (size_t)WPW * dstride);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(lists) + (size_t)WPW * 2 * nmax * sizeof(uint16_t));
+    uint32_t *cur = cnt + SLOTS;
+    uint8_t *order = reinterpret_cast<uint8_t *>(cur + SLOTS);
     const uint32_t *P = pts + 24 * (size_t)seg.pts_off;
 
     // ---- phase 0: stage this warp's digit rows
@@ -107,27 +110,20 @@ __global__ void __launch_bounds__(128, OCC)
                 reinterpret_cast<uint4 *>(digits + (size_t)wl * dstride)[v] =
                     reinterpret_cast<const uint4 *>(gd + (size_t)(w0 + wl) * rowstride)[v];
         }
+        cnt[lane_id] = 0;
+        cnt[lane_id + 32] = 0;
     }
     __syncwarp();
-
-    const int wl = lane_id / NB, b = lane_id % NB;
-    const int w = w0 + wl;
-    const bool active = w < NWIN;
-    // The top window only holds the few leftover bits (plus the recoding carry): NBT distinct non-zero digits.  Lane-per-
-    // bucket would leave NB - NBT lanes idle and put 2n/NBT points on each of the others (measured on the first version: 10% warps
-    // active, profiles/r01_ncu_msm_buckets_v0.txt).  So in the top window every bucket is spread over SP = NB / NBT lanes (by point
-    // index); phase 4 folds the SP partial sums of a bucket.
+    // The top window only holds the few leftover bits (plus the recoding carry): NBT distinct non-zero digits.  One list per digit
+    // would leave NB - NBT slots empty and put 2n/NBT points into each of the others, so in the top window every bucket is spread over
+    // SP = NB / NBT slots (by point index); k_msm_combine adds the SP partial sums of a bucket before it starts.
     constexpr int TB = 128 - C * (NWIN - 1);
     constexpr int NBT = TB > 0 ? (1 << TB) : 1;
     constexpr int SP = NB / NBT >= 1 ? NB / NBT : 1;
-    static_assert(NBT <= NB, "top-window digits must fit the lanes");
-    const bool is_top = (w == NWIN - 1);
-    // ---- phases 1-2: counting sort of the point ids by bucket, the whole warp working on one window row at a time: every lane takes
-    //      every 32nd digit (shared-memory atomics on the row's NB counters), so a row costs 2 * n2 / 32 steps per lane instead of
-    //      two full scans by every lane.  List order inside a bucket is arbitrary; the bucket SUM does not depend on it.
-    uint32_t *cnts = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(lists) + (size_t)WPW * 2 * nmax * sizeof(uint16_t));  // [WPW][NB] counts, then cursors
-    for (int t = lane_id; t < WPW * NB; t += 32) cnts[t] = 0;
-    __syncwarp();
+    static_assert(NBT <= NB, "top-window digits must fit the slots");
+    // ---- phases 1-2: counting sort of the point ids by slot, the whole warp working on one window row at a time: every lane takes
+    //      every 32nd digit (shared-memory atomics on the row's NB counters).  List order inside a slot is arbitrary; its SUM does not
+    //      depend on it.
 #pragma unroll 1
     for (int r = 0; r < WPW; r++) {
         if (w0 + r >= NWIN) break;
@@ -136,21 +132,23 @@ __global__ void __launch_bounds__(128, OCC)
         for (uint32_t p = lane_id; p < n2; p += 32) {
             int d = row[p];
             int ad = d < 0 ? -d : d;
-            if (ad) atomicAdd(&cnts[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
+            if (ad) atomicAdd(&cnt[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
         }
     }
     __syncwarp();
-    const uint32_t cnt = active ? cnts[wl * NB + b] : 0u;
-    // exclusive scan of cnt over the NB lanes of this window (NB <= 32, windows are NB-aligned inside a warp)
-    uint32_t off = cnt;
+    // list offsets: exclusive scan of the counts inside every window row (rows are NB-aligned groups of slots; NB <= 32)
 #pragma unroll
-    for (int d = 1; d < NB; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, off, d, NB);
-        if (b >= d) off += o;
+    for (int half = 0; half < 2; half++) {
+        const int sl = lane_id + 32 * half;
+        const uint32_t c0 = cnt[sl];
+        uint32_t off = c0;
+#pragma unroll
+        for (int d = 1; d < NB; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, off, d, NB);
+            if ((sl & (NB - 1)) >= d) off += o;
+        }
+        cur[sl] = off - c0;
     }
-    off -= cnt;
-    __syncwarp();
-    if (active) cnts[wl * NB + b] = off;  // becomes the bucket's write cursor
     __syncwarp();
 #pragma unroll 1
     for (int r = 0; r < WPW; r++) {
@@ -162,19 +160,40 @@ __global__ void __launch_bounds__(128, OCC)
             int d = row[p];
             int ad = d < 0 ? -d : d;
             if (ad) {
-                uint32_t pos = atomicAdd(&cnts[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
+                uint32_t pos = atomicAdd(&cur[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
                 lst[pos] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
             }
         }
     }
+    // ---- phase 3: balance.  Slot loads are binomial (+-35% around the mean at these sizes) and a warp runs as long as its busiest lane,
+    //      so the 64 slots are ranked by load and lane l takes the l-th largest and the l-th smallest: every lane ends up within a few
+    //      points of two mean loads (measured before: 21 of 32 lanes active on average, profiles/r01_ncu_msm_buckets_v3.txt).
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int sl = lane_id + 32 * half;
+        const uint32_t c0 = cnt[sl];
+        int rank = 0;
+#pragma unroll 8
+        for (int t = 0; t < SLOTS; t++) {
+            const uint32_t ct = cnt[t];
+            rank += (ct > c0 || (ct == c0 && t < sl)) ? 1 : 0;
+        }
+        order[rank] = (uint8_t)sl;
+    }
     __syncwarp();
-    // ---- phase 3: accumulate own bucket
-    g1j acc;
-    g1j_set_inf(acc);
-    if (active) {
-        const uint16_t *lst = lists + (size_t)wl * (2 * nmax) + off;
+    // ---- phase 4: every lane sums its two slots (different lanes, different points => no serialisation; mixed additions) and writes
+    //      each sum to its place in [msm][window][slot]
 #pragma unroll 1
-        for (uint32_t e = 0; e < cnt; e++) {
+    for (int pass = 0; pass < 2; pass++) {
+        const int sl = order[pass == 0 ? lane_id : SLOTS - 1 - lane_id];
+        const int r = sl / NB, w = w0 + r;
+        if (w >= NWIN) continue;
+        const uint32_t c1 = cnt[sl];
+        const uint16_t *lst = lists + (size_t)r * (2 * nmax) + (cur[sl] - c1);
+        g1j acc;
+        g1j_set_inf(acc);
+#pragma unroll 1
+        for (uint32_t e = 0; e < c1; e++) {
             uint32_t id = lst[e];
             uint32_t p = id & 0x7FFFu;
             g1a q;
@@ -183,28 +202,7 @@ __global__ void __launch_bounds__(128, OCC)
             if (id & 0x8000u) fp_neg(q.y, q.y);
             g1j_add_mixed(acc, acc, q);
         }
-    }
-    // ---- phase 4: top window only -- fold the SP lanes of each bucket (log2(SP) shuffle steps; other windows just pass through)
-    if (SP > 1 && w0 + WPW >= NWIN) {  // warp-uniform: only the MSM's last warp holds the top window
-        constexpr int LS = SP >= 16 ? 4 : SP >= 8 ? 3 : SP >= 4 ? 2 : SP >= 2 ? 1 : 0;
-#pragma unroll 1
-        for (int step = 0; step < LS; step++) {
-            const int d = SP >> (step + 1);
-            const bool take = is_top && (b & (SP - 1)) < d;
-            g1j o;
-            shfl_down_g1j(o, acc, d, NB);
-            if (take) g1j_add(acc, acc, o);
-        }
-    }
-    // ---- phase 5: bucket sums out.  Top window: leader lane k*SP holds bucket k; the other lanes fill the unused slots with infinity
-    if (active) {
-        int slot = b;
-        if (is_top && SP > 1) {
-            const bool leader = (b & (SP - 1)) == 0;
-            if (leader) slot = b / SP;
-            else { slot = NBT + b - b / SP - 1; g1j_set_inf(acc); }
-        }
-        g1j_store(bucket_sums + 36 * (((size_t)msm * NWIN + w) * NB + slot), acc);
+        g1j_store(bucket_sums + 36 * (((size_t)msm * NWIN + w) * NB + (sl & (NB - 1))), acc);
     }
 }
 

@@ -108,15 +108,15 @@ cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, 
 
 // geometry shared by host and device
 constexpr int msm_nwin_for(int c) { return (130 + c - 1) / c; }
-// the bucket kernel gives every warp 32 / 2^(c-1) windows of one MSM; CTAs are 4 independent warps
+// the bucket kernel gives every warp 64 / 2^(c-1) windows of one MSM (64 slots, two per lane); CTAs are 4 independent warps
 constexpr int msm_nb_for(int c) { return 1 << (c - 1); }
-constexpr int msm_wpw_for(int c) { return 32 / msm_nb_for(c); }
+constexpr int msm_wpw_for(int c) { return 64 / msm_nb_for(c); }
 constexpr int msm_groups_for(int c) { return (msm_nwin_for(c) + msm_wpw_for(c) - 1) / msm_wpw_for(c); }
 inline uint32_t msm_dig_rowstride(size_t nmax) { return (uint32_t)((2 * nmax + 15) & ~size_t(15)); }
 inline size_t msm_dig_bytes(int c, size_t nmax, size_t count) { return count * (size_t)msm_nwin_for(c) * msm_dig_rowstride(nmax); }
 __host__ __device__ inline size_t msm_smem_per_warp(int c, size_t nmax) {
-    size_t wpw = 32 >> (c - 1), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
-    return (wpw * dstride + wpw * 2 * nmax * sizeof(uint16_t) + 32 * sizeof(uint32_t) + 15) & ~size_t(15);
+    size_t wpw = 64 >> (c - 1), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
+    return (wpw * dstride + wpw * 2 * nmax * sizeof(uint16_t) + 128 * sizeof(uint32_t) + 64 + 15) & ~size_t(15);
 }
 inline size_t msm_smem_bytes(int c, size_t nmax) { return 4 * msm_smem_per_warp(c, nmax); }
 // bucket sums of `count` MSMs: [msm][window][bucket] Jacobian points
