@@ -328,6 +328,16 @@ extern "C" int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const
     return CDP_OK;
 }
 
+extern "C" int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs, const uint8_t *d_comp_M, size_t ell, size_t batch, uint8_t *d_vec_a,
+                                       uint8_t *d_state) {
+    if (!ctx || (batch && (!d_comp_vecs || !d_comp_M || !d_vec_a || !d_state)) || ell == 0) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_transcript_open_dev: bad argument");
+    if (batch == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
+    CUDA_TRY(ctx, launch_transcript_open(ctx->stream, d_comp_vecs, d_comp_M, (uint32_t)ell, (uint32_t)batch, d_vec_a, reinterpret_cast<uint64_t *>(d_state)));
+    return CDP_OK;
+}
+
 extern "C" int cdp_decompress_dev(cdp_ctx *ctx, const uint8_t *d_compressed, const uint32_t *d_dst_index, size_t n, uint8_t *d_out_affine,
                                   uint8_t *d_status) {
     if (!ctx || (n && (!d_compressed || !d_out_affine || !d_status))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_decompress_dev: null argument");

@@ -66,6 +66,7 @@ _SIGS = {
     "cdp_gather_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "cdp_decompress_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_decompress_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "cdp_transcript_open_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
@@ -225,6 +226,29 @@ class Engine:
         if rc not in (0, 4):
             self._check(rc, "cdp_decompress_batch")
         return bytes(out)[:n * AFFINE_BYTES], list(st)[:n]
+
+    def transcript_open(self, comp_vecs: bytes, comp_M: bytes, ell: int):
+        """Device-side transcript opening (cdp_transcript_open_dev): comp_vecs = batch x 4 x ell encodings (R | S | T | U per proof),
+        comp_M = batch encodings.  Returns (vec_a bytes: batch x ell x 32, states: batch x 208 bytes)."""
+        B = len(comp_M) // COMPRESSED_BYTES
+        if len(comp_vecs) != B * 4 * ell * COMPRESSED_BYTES:
+            raise ValueError("malformed input length")
+        lib, h = self._lib, self._h
+        d_v, d_m = lib.cdp_dev_alloc(h, len(comp_vecs)), lib.cdp_dev_alloc(h, len(comp_M))
+        d_a, d_s = lib.cdp_dev_alloc(h, B * ell * 32), lib.cdp_dev_alloc(h, B * 208)
+        try:
+            bv, bm = _buf(comp_vecs), _buf(comp_M)
+            self._check(lib.cdp_h2d(h, d_v, bv, len(comp_vecs)), "cdp_h2d")
+            self._check(lib.cdp_h2d(h, d_m, bm, len(comp_M)), "cdp_h2d")
+            self._check(lib.cdp_transcript_open_dev(h, d_v, d_m, ell, B, d_a, d_s), "cdp_transcript_open_dev")
+            oa, os_ = (ctypes.c_uint8 * (B * ell * 32))(), (ctypes.c_uint8 * (B * 208))()
+            self._check(lib.cdp_d2h(h, oa, d_a, B * ell * 32), "cdp_d2h")
+            self._check(lib.cdp_d2h(h, os_, d_s, B * 208), "cdp_d2h")
+            self.sync()
+        finally:
+            for d in (d_v, d_m, d_a, d_s):
+                lib.cdp_dev_free(h, d)
+        return bytes(oa), bytes(os_)
 
     # ---- fixed-base MSM over a digit table of CRS points ------------------------------------------------
     def fixed_table_create(self, points: bytes, window_bits: int = 16) -> "FixedTable":

@@ -116,6 +116,7 @@ struct Lane {
     size_t g_count_per_proof = 0, i_count_per_proof = 0;
     uint32_t *d_cidx = nullptr;                         // indices of the points compressed for the transcript opening
     uint8_t *d_scal = nullptr, *d_fscal = nullptr;
+    uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
     uint8_t *d_jac = nullptr, *d_comp = nullptr;
     uint8_t *h_scal = nullptr, *h_fscal = nullptr, *h_comp = nullptr, *h_in = nullptr;
     size_t max_scalars_pp = 0, max_out_pp = 0;
@@ -389,9 +390,9 @@ static void lane_destroy(Lane *p) {
     for (auto &s : p->st_sm) free_stage(s);
     for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
-                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp})
+                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_comp, (void *)p->h_in}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -492,6 +493,8 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     p->h_scal = (uint8_t *)halloc(max_batch * p->max_scalars_pp * 32);
     p->d_fscal = (uint8_t *)dalloc(max_batch * n * 32);
     p->h_fscal = (uint8_t *)halloc(max_batch * n * 32);
+    p->d_veca = (uint8_t *)dalloc(max_batch * ell * 32); p->h_veca = (uint8_t *)halloc(max_batch * ell * 32);
+    p->d_tstate = (uint8_t *)dalloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES); p->h_tstate = (uint8_t *)halloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES);
     p->d_jac = (uint8_t *)dalloc(max_batch * p->max_out_pp * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * max_out * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * max_out * 48);
@@ -597,8 +600,12 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_count_per_proof));
     PTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp));
     PTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp + B * 4 * ell * 48));
+    // transcript opening (R, S, T, U, M -> vec_a) hashed on the device; the host continues from the returned STROBE states
+    PTRY(cdp_transcript_open_dev(p->ctx, p->d_comp, p->d_comp + B * 4 * ell * 48, ell, B, p->d_veca, p->d_tstate));
     PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * 4 * ell + B) * 48));
-    p->d2h_bytes += (B * 4 * ell + B) * 48;
+    PTRY(cdp_d2h(p->ctx, p->h_veca, p->d_veca, B * ell * 32));
+    PTRY(cdp_d2h(p->ctx, p->h_tstate, p->d_tstate, B * CDP_TRANSCRIPT_STATE_BYTES));
+    p->d2h_bytes += (B * 4 * ell + B) * 48 + B * ell * 32 + B * CDP_TRANSCRIPT_STATE_BYTES;
     t_copy += now_ms() - t0;
     t0 = now_ms();
     PTRY(cdp_sync(p->ctx));
@@ -612,9 +619,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         ProofState &s = p->ps[pr];
         const uint8_t *cmp = p->h_comp + pr * 4 * ell * 48;
         memcpy(s.M_comp, p->h_comp + (B * 4 * ell + pr) * 48, 48);
-        s.tr.reset(new Transcript("curdleproofs"));
-        for (int v = 0; v < 4; v++) s.tr->append_point_vec("curdleproofs_step1", cmp + v * ell * 48, ell);
-        s.tr->append_point("curdleproofs_step1", s.M_comp);
+        s.tr.reset(new Transcript(reinterpret_cast<const uint64_t *>(p->h_tstate + pr * CDP_TRANSCRIPT_STATE_BYTES)));
         uint8_t *tu = tu_comp.data() + pr * 2 * n * 48;
         uint8_t inf[48] = {0xC0};
         memcpy(tu, cmp + 2 * ell * 48, ell * 48);
@@ -623,7 +628,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         memcpy(uu, cmp + 3 * ell * 48, ell * 48);
         memcpy(uu + ell * 48, inf, 48); memcpy(uu + (ell + 1) * 48, inf, 48); memcpy(uu + (ell + 2) * 48, inf, 48); memcpy(uu + (ell + 3) * 48, p->H_comp, 48);
         s.vec_a.resize(ell);
-        for (size_t i = 0; i < ell; i++) s.vec_a[i] = s.tr->challenge("curdleproofs_vec_a");
+        for (size_t i = 0; i < ell; i++) Fr::from_bytes(p->h_veca + (pr * ell + i) * 32, s.vec_a[i]);
         // witnesses
         s.perm.assign(in->permutation + pr * ell, in->permutation + (pr + 1) * ell);
         Fr::from_bytes(in->k + 32 * pr, s.k);

@@ -102,6 +102,7 @@ struct VLane {
     double timing[3] = {0, 0, 0};  // last call: total, host compute, waiting for the GPU (ms)
     size_t crs_n = 0, VW = 0, o_R = 0, o_S = 0, o_T = 0, o_U = 0, o_M = 0, o_P = 0, o_X = 0, big_n = 0, reg = 0, chunks = 1;
     uint8_t *d_pts = nullptr, *d_in = nullptr, *d_Mjac = nullptr, *d_pcomp = nullptr, *d_status = nullptr;
+    uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
     uint32_t *d_gsrc = nullptr, *d_gdst = nullptr, *d_isrc = nullptr, *d_idst = nullptr, *d_pdst = nullptr, *d_xsrc = nullptr, *d_xdst = nullptr;
     size_t g_pp = 0, i_pp = 0, x_pp = 0;
     cdp_msm_seg *d_segBig = nullptr, *d_segE = nullptr;
@@ -126,10 +127,10 @@ void vlane_destroy(VLane *p) {
     cdp_ctx *c = p->ctx;
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_pcomp, (void *)p->d_status, (void *)p->d_gsrc,
                     (void *)p->d_gdst, (void *)p->d_isrc, (void *)p->d_idst, (void *)p->d_pdst, (void *)p->d_xsrc, (void *)p->d_xdst,
-                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_scal, (void *)p->d_jac,
+                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_scal, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -165,6 +166,8 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->h_in = (uint8_t *)halloc(max_batch * (4 * ell * 96 + 144));
     p->h_pcomp = (uint8_t *)halloc(max_batch * L.np * 48);
     p->h_status = (uint8_t *)halloc(max_batch * L.np);
+    p->d_veca = (uint8_t *)dalloc(max_batch * ell * 32); p->h_veca = (uint8_t *)halloc(max_batch * ell * 32);
+    p->d_tstate = (uint8_t *)dalloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES); p->h_tstate = (uint8_t *)halloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES);
     size_t scal_pp = p->big_n + 14;
     p->d_scal = (uint8_t *)dalloc(max_batch * scal_pp * 32);
     p->h_scal = (uint8_t *)halloc(max_batch * scal_pp * 32);
@@ -291,7 +294,11 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     VTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_xsrc, p->d_xdst, B * p->x_pp));
     VTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp));
     VTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp + B * 4 * ell * 48));
+    // transcript opening (R, S, T, U, M -> vec_a) hashed on the device; the host continues from the returned STROBE states
+    VTRY(cdp_transcript_open_dev(p->ctx, p->d_comp, p->d_comp + B * 4 * ell * 48, ell, B, p->d_veca, p->d_tstate));
     VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * 4 * ell + B) * 48));
+    VTRY(cdp_d2h(p->ctx, p->h_veca, p->d_veca, B * ell * 32));
+    VTRY(cdp_d2h(p->ctx, p->h_tstate, p->d_tstate, B * CDP_TRANSCRIPT_STATE_BYTES));
     VTRY(cdp_d2h(p->ctx, p->h_status, p->d_status, B * NP));
     t0 = now_ms();
     VTRY(cdp_sync(p->ctx));
@@ -307,11 +314,9 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         const uint8_t *cmp = p->h_comp + pr * 4 * ell * 48, *pc = p->h_pcomp + pr * NP * 48;
         memcpy(s.M_comp, p->h_comp + (B * 4 * ell + pr) * 48, 48);
         if ((cmp[2 * ell * 48] & 0x40) && s.status == 1) s.status = 0;  // vec_T[0] is infinity -> Err (curdleproofs.rs:218-220)
-        s.tr.reset(new Transcript("curdleproofs"));
-        for (int v = 0; v < 4; v++) s.tr->append_point_vec("curdleproofs_step1", cmp + v * ell * 48, ell);
-        s.tr->append_point("curdleproofs_step1", s.M_comp);
+        s.tr.reset(new Transcript(reinterpret_cast<const uint64_t *>(p->h_tstate + pr * CDP_TRANSCRIPT_STATE_BYTES)));
         s.vec_a.resize(ell);
-        for (size_t i = 0; i < ell; i++) s.vec_a[i] = s.tr->challenge("curdleproofs_vec_a");
+        for (size_t i = 0; i < ell; i++) Fr::from_bytes(p->h_veca + (pr * ell + i) * 32, s.vec_a[i]);
         uint8_t *tu = tu_comp.data() + pr * 2 * n * 48;
         uint8_t inf[48] = {0xC0};
         memcpy(tu, cmp + 2 * ell * 48, ell * 48);

@@ -193,6 +193,16 @@ int cdp_decompress_dev(cdp_ctx *ctx, const uint8_t *d_compressed, const uint32_t
  * instance vectors, src/curdleproofs.rs:81). */
 int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint32_t *d_index, size_t n, uint8_t *d_out_compressed);
 
+/* Opening of the Fiat-Shamir transcript on the device, one thread per proof (merlin 3.0.0 / STROBE-128 / Keccak-f[1600]):
+ *   Transcript::new(b"curdleproofs"); append_list(b"curdleproofs_step1", [vec_R, vec_S, vec_T, vec_U]); append(.., M);
+ *   vec_a = get_and_append_challenges(b"curdleproofs_vec_a", ell)          /root/reference/src/curdleproofs.rs:78-83, :213-225
+ * d_comp_vecs: batch x 4 x ell 48-byte encodings (proof-major: R | S | T | U), d_comp_M: batch encodings.
+ * Outputs: d_vec_a = batch x ell canonical 32-byte scalars; d_state = batch x 208 bytes: the 200-byte STROBE state, then pos, pos_begin
+ * (one byte each, then zero padding) -- the host continues the same transcript from it. */
+#define CDP_TRANSCRIPT_STATE_BYTES 208
+int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs, const uint8_t *d_comp_M, size_t ell, size_t batch, uint8_t *d_vec_a,
+                            uint8_t *d_state);
+
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);
 

@@ -18,3 +18,19 @@ def test_host_transcript_and_fr_match_oracle():
         b = subprocess.run([orc], check=True, capture_output=True).stdout
     assert len(a.splitlines()) == 330
     assert a == b
+
+
+def _build_transcript_harness(d):
+    exe = os.path.join(d, "tdc")
+    subprocess.run(["g++", "-O1", "-march=x86-64-v3", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/transcript_dev_check.cpp")], check=True)
+    return exe
+
+
+def test_device_transcript_code_matches_host_transcript_on_cpu():
+    """The device transcript-opening code (csrc/k_transcript.cu, compiled as plain C++) against the host merlin implementation:
+    vec_a and the continued transcript agree for ell = 4 ... 252, aligned and misaligned inputs."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = _build_transcript_harness(d)
+        out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "MISMATCH" not in out.stdout
