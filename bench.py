@@ -10,7 +10,8 @@ one batch of independent proofs per step per GPU.  One JSON line on stdout (rank
 
 `value`  : proofs/s with the instance vectors already resident in HBM when the timed region starts.
 `e2e`    : the same through the host-buffer C ABI (cdp_prove_batch): instance H2D + proofs D2H inside the timed region.
-Both include the per-round scalar uploads / 48-byte point downloads that the host-side Fiat-Shamir transcript needs.
+Both include the per-round scalar uploads / 48-byte point downloads that the host side of the Fiat-Shamir transcript needs
+(its opening -- the bulk of the hashing -- runs on the GPU).  The CRS digit table (fixed-base MSM) is built once at prover creation.
 """
 import argparse
 import json
@@ -284,7 +285,12 @@ def main():
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    bytes_per_unit = {"msm_buckets": 128, "smul": 288, "normalize": 240, "msm_combine": 0, "other": 144}
+    # algorithmic bytes per unit: variable-base pair = 32 B scalar + 96 B base; fixed-base pair = 32 B scalar +
+    # 16 gathered 96-byte table points (c = 16); fold element = 192 B in + 96 B out; normalised point = 144 B in + 96 B out
+    bytes_per_unit = {"msm_buckets": 128, "msm_fixed": 32 + 16 * 96, "smul": 288, "normalize": 240, "msm_combine": 144, "other": 144}
+    # measured DRAM bytes per unit of the same kernels from the committed `ncu --set full` captures (dram__bytes_read + write per launch /
+    # units of that launch): profiles/r01_ncu_fixed_msm_v1.txt (407.5 MB / 131,584 pairs), profiles/r01_ncu_msm_buckets_v3.txt (157.3 MB / 520,192 pairs)
+    ncu_traffic_per_unit = {"msm_fixed": 3097.0, "msm_buckets": 302.0}
     dom = max(prof, key=lambda k: prof[k]["ms"])
     d = prof[dom]
     avg_ms = d["ms"] / max(1, d["launches"])
@@ -295,7 +301,8 @@ def main():
     imad_peak = 148 * 4 * 256 * 2000 * 128 / (imad_ms * 1e-3)
     total_kernel_ms = sum(v["ms"] for v in prof.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                "traffic": ncu_traffic_per_unit[dom] * d["units"] / max(1, d["launches"]) if dom in ncu_traffic_per_unit else None,
+                "traffic_source": "ncu dram bytes per unit (profiles/r01_ncu_*) x units per launch", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                 "share_of_kernel_time": d["ms"] / total_kernel_ms if total_kernel_ms else None,
                 "note": "381-bit modular arithmetic: the binding roofline is the integer multiply pipe, not HBM (see int_pipe)",
                 "int_pipe": {"peak_imad_wide_per_s": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad)"},
