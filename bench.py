@@ -291,7 +291,10 @@ def main():
     # measured DRAM bytes per unit of the same kernels from the committed `ncu --set full` captures (dram__bytes_read + write per launch /
     # units of that launch): profiles/r01_ncu_fixed_msm_v1.txt (407.5 MB / 131,584 pairs), profiles/r01_ncu_msm_buckets_v3.txt (157.3 MB / 520,192 pairs)
     ncu_traffic_per_unit = {"msm_fixed": 3097.0, "msm_buckets": 302.0}
-    dom = max(prof, key=lambda k: prof[k]["ms"])
+    # dominant = the throughput kernel with the most device time; the latency-bound launches (combine: 130 dependent doublings per
+    # thread, normalise: one Fp inversion per thread) run a handful of warps each, and with 8 lanes in flight their summed durations
+    # mostly measure waiting for SM time, not work
+    dom = max(("msm_fixed", "msm_buckets", "smul"), key=lambda k: prof[k]["ms"])
     d = prof[dom]
     avg_ms = d["ms"] / max(1, d["launches"])
     alg_bytes = bytes_per_unit[dom] * d["units"] / max(1, d["launches"])
@@ -307,6 +310,47 @@ def main():
                 "note": "381-bit modular arithmetic: the binding roofline is the integer multiply pipe, not HBM (see int_pipe)",
                 "int_pipe": {"peak_imad_wide_per_s": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad)"},
                 "kernel_ms": {k: v["ms"] / args.steps for k, v in prof.items()}}
+    # ---- the same kernel timed ALONE (nothing else on the GPU): one fixed-base launch of the IPA-round shape for the whole batch
+    try:
+        from curdleproofs_b200 import FixedSeg
+        n_ = ell + 4
+        tab = eng.fixed_table_create(crs, 16)
+        nseg = B * 4
+        segs = (FixedSeg * nseg)()
+        for i in range(nseg):
+            segs[i].base_off = 0; segs[i].scalars_off = (i // 4) * (2 * n_ + 2) + (n_ + 2) * ((i % 4) // 2); segs[i].n = n_ // 2
+            segs[i].sel_h = n_ // 2; segs[i].sel_val = (n_ // 2) * (i % 2); segs[i].remap_from = 0xFFFFFFFF
+            if i % 4 < 2:  # L_C / R_C carry the extra `+ ip * H` pair (scalars n_, n_ + 1 of the proof's block)
+                segs[i].extra_base = n_ + 1; segs[i].extra_scalar = n_ + (i % 2)
+            segs[i].out_idx = i
+        sc = bytearray(os.urandom(32 * B * (2 * n_ + 2)))
+        sc[31::32] = bytes(x & 0x3F for x in sc[31::32])
+        lib, h = eng.lib, eng.handle
+        d_sc, d_sg, d_out = lib.cdp_dev_alloc(h, len(sc)), lib.cdp_dev_alloc(h, ctypes.sizeof(segs)), lib.cdp_dev_alloc(h, nseg * 144)
+        lib.cdp_h2d(h, d_sc, arr(bytes(sc)), len(sc)); lib.cdp_h2d(h, d_sg, segs, ctypes.sizeof(segs)); eng.sync()
+        for _ in range(3):
+            lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, nseg, B * (2 * n_ + 2), None, d_out)
+        eng.sync(); eng.profile_reset(); eng.profile_enable(True)
+        for _ in range(5):
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+            lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, nseg, B * (2 * n_ + 2), None, d_out)
+        eng.sync()
+        pf = eng.profile_read()["msm_fixed"]
+        eng.profile_enable(False)
+        iso_ms = pf["ms"] / pf["launches"]
+        pairs = B * (2 * n_ + 2)
+        madds = pairs * 16 / (iso_ms * 1e-3)
+        roofline["isolated"] = {"kernel": "k_fixed_msm, IPA-round shape, whole batch in one launch, nothing else running", "ms": iso_ms,
+                                "pairs_per_s": pairs / (iso_ms * 1e-3), "achieved_GBps": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9,
+                                "hbm_frac": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9 / hbm_peak,
+                                "mixed_adds_per_s": madds, "imad_wide_per_mixed_add": 7 * 288 + 4 * 234,
+                                "int_pipe_frac": madds * (7 * 288 + 4 * 234) / imad_peak}
+        for dd in (d_sc, d_sg, d_out):
+            lib.cdp_dev_free(h, dd)
+        tab.close()
+    except Exception as e:  # diagnostics only: never lose the headline line
+        roofline["isolated"] = {"error": repr(e)}
     line = {"metric": f"shuffle_proofs_per_sec_ell{ell}", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / README_PROOFS_PER_S if ell == 252 else None, "dtype": "u32", "data": "synthetic",
