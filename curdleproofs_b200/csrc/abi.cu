@@ -487,6 +487,18 @@ extern "C" int cdp_sum_groups_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t 
     return CDP_OK;
 }
 
+extern "C" int cdp_sum_groups2_dev(cdp_ctx *ctx, const uint8_t *d_a, size_t per_a, size_t sa, size_t ga, const uint8_t *d_b, size_t per_b, size_t sb,
+                                   size_t gb, size_t n_out, uint8_t *d_out_jac) {
+    if (!ctx || !d_out_jac || (per_a && !d_a) || (per_b && !d_b) || per_a + per_b == 0) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_sum_groups2_dev: bad argument");
+    if (n_out == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, n_out * (per_a + per_b));
+    CUDA_TRY(ctx, launch_sum_groups2(ctx->stream, reinterpret_cast<const uint32_t *>(d_a), (uint32_t)per_a, (uint32_t)sa, (uint32_t)ga,
+                                     reinterpret_cast<const uint32_t *>(d_b), (uint32_t)per_b, (uint32_t)sb, (uint32_t)gb,
+                                     reinterpret_cast<uint32_t *>(d_out_jac), (uint32_t)n_out));
+    return CDP_OK;
+}
+
 extern "C" int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
     if (!ctx || !d_out_jac || (n && (!d_affine_pts || !d_scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: null argument");
     if (n == 0 || n >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: n out of range");

@@ -53,18 +53,21 @@ __global__ void __launch_bounds__(128) k_msm_combine(const uint32_t *__restrict_
 }
 
 
-// out[g] = sum_{s < per_out} in[s * group_stride + g]   -- one warp per output point
-__global__ void __launch_bounds__(128) k_sum_groups(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n_out,
-                                                    uint32_t per_out, uint32_t group_stride) {
+// out[g] = sum_{s < per_a} A[s * sa + g * ga]  (+ sum_{s < per_b} B[s * sb + g * gb])   -- one warp per output point
+__global__ void __launch_bounds__(128) k_sum_groups(const uint32_t *__restrict__ A, uint32_t per_a, uint32_t sa, uint32_t ga,
+                                                    const uint32_t *__restrict__ Bsrc, uint32_t per_b, uint32_t sb, uint32_t gb,
+                                                    uint32_t *__restrict__ out, uint32_t n_out) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_out) return;
     g1j acc;
     g1j_set_inf(acc);
+    const uint32_t total = per_a + per_b;
 #pragma unroll 1
-    for (uint32_t s = lane; s < ((per_out + 31) & ~31u); s += 32) {
+    for (uint32_t s = lane; s < ((total + 31) & ~31u); s += 32) {
         g1j q;
         g1j_set_inf(q);
-        if (s < per_out) g1j_load(q, in + 36 * ((size_t)s * group_stride + warp));
+        if (s < per_a) g1j_load(q, A + 36 * ((size_t)s * sa + (size_t)warp * ga));
+        else if (s < total) g1j_load(q, Bsrc + 36 * ((size_t)(s - per_a) * sb + (size_t)warp * gb));
         g1j_add(acc, acc, q);
     }
 #pragma unroll 1
@@ -93,7 +96,12 @@ cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *bucket_sums, uin
     return cudaGetLastError();
 }
 cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride) {
-    k_sum_groups<<<(n_out * 32 + 127) / 128, 128, 0, st>>>(in, out, n_out, per_out, group_stride);
+    k_sum_groups<<<(n_out * 32 + 127) / 128, 128, 0, st>>>(in, per_out, group_stride, 1, nullptr, 0, 0, 0, out, n_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_groups2(cudaStream_t st, const uint32_t *A, uint32_t per_a, uint32_t sa, uint32_t ga, const uint32_t *B, uint32_t per_b,
+                               uint32_t sb, uint32_t gb, uint32_t *out, uint32_t n_out) {
+    k_sum_groups<<<(n_out * 32 + 127) / 128, 128, 0, st>>>(A, per_a, sa, ga, B, per_b, sb, gb, out, n_out);
     return cudaGetLastError();
 }
 

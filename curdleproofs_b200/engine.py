@@ -52,6 +52,7 @@ _SIGS = {
     "cdp_msm_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_sum_jacobian_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_sum_groups_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    "cdp_sum_groups2_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_void_p]),
     "cdp_msm_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     "cdp_fixed_table_create": (c_int, [c_void_p, c_void_p, c_size_t, c_int, POINTER(c_void_p)]),
     "cdp_fixed_table_destroy": (None, [c_void_p, c_void_p]),

@@ -36,6 +36,7 @@ using namespace cdp_host;
 namespace {
 
 constexpr size_t NBL = 4;
+constexpr size_t FSPLIT = 4;  // warps per proof for the CRS part of the accumulated check
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 template <class F>
 void parallel_for(int threads, size_t n, F f) {
@@ -87,7 +88,7 @@ struct VState {
     std::unique_ptr<Transcript> tr;
     std::vector<Fr> vec_a, s_ipa, sinv_ipa, u, s_sm, gam, gam_inv, gam2, gam2_inv;
     Fr r_p, c_final, d_final, z_k, z_t, z_u, x_final;
-    Fr alpha_sp, beta_sp, alpha_g, beta_g, beta_g_inv, gprod_result, z, rho[8];
+    Fr alpha_sp, beta_sp, alpha_g, beta_g, beta_g_inv, gprod_result, z, rho[12];
     uint8_t M_comp[48];
     int status = 1;  // 1 ok so far, 0 verification failure, 2 malformed
 };
@@ -100,6 +101,7 @@ struct VLane {
     int threads = 1;
     std::string err = "ok";
     double timing[3] = {0, 0, 0};  // last call: total, host compute, waiting for the GPU (ms)
+    bool exact_eq = false;         // CDP_VERIFY_EXACT_EQ=1: check the four SameScalar equalities as separate exact MSMs
     size_t crs_n = 0, VW = 0, o_R = 0, o_S = 0, o_T = 0, o_U = 0, o_M = 0, o_P = 0, o_X = 0, big_n = 0, reg = 0, chunks = 1;
     uint8_t *d_pts = nullptr, *d_in = nullptr, *d_Mjac = nullptr, *d_pcomp = nullptr, *d_status = nullptr;
     uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
@@ -140,6 +142,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     if (((size_t)1 << m) != n) return CDP_ERR_INVALID_ARG;
     VLane *p = new VLane();
     p->ctx = ctx; p->table = table; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch; p->threads = std::max(1, host_threads);
+    if (const char *e = getenv("CDP_VERIFY_EXACT_EQ")) p->exact_eq = atoi(e) != 0;
     ProofLayout L(m);
     p->np = L.np;
     const size_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
@@ -172,13 +175,13 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->d_scal = (uint8_t *)dalloc(max_batch * scal_pp * 32);
     p->h_scal = (uint8_t *)halloc(max_batch * scal_pp * 32);
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
-    p->d_jac = (uint8_t *)dalloc(max_batch * (p->chunks + 6) * 144);
+    p->d_jac = (uint8_t *)dalloc(max_batch * (p->chunks + FSPLIT + 5) * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * out_pp * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * out_pp * 48);
     // tables
     std::vector<uint32_t> gsrc, gdst, isrc, idst, pdst, xsrc, xdst;
     std::vector<cdp_msm_seg> segBig(max_batch * p->chunks), segE;
-    std::vector<cdp_fixed_seg> segF(max_batch), segAf(2 * max_batch);
+    std::vector<cdp_fixed_seg> segF(FSPLIT * max_batch), segAf(2 * max_batch);
     for (size_t pr = 0; pr < max_batch; pr++) {
         size_t bp = p->crs_n + pr * p->VW - p->crs_n;  // device index of coefficient slot o of this proof = bp + o   (o >= crs_n)
         const size_t dsts[4] = {p->o_R, p->o_S, p->o_T, p->o_U};
@@ -211,10 +214,12 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
             size_t lo = p->crs_n + c * 2048, cnt = std::min<size_t>(2048, p->big_n - lo);
             segBig[c * max_batch + pr] = {(uint32_t)(bp + lo), (uint32_t)(pr * scal_pp + lo), (uint32_t)cnt, 0};
         }
-        {
-            cdp_fixed_seg &f = segF[pr];
+        for (size_t q = 0; q < FSPLIT; q++) {  // the n + 3 CRS pairs in FSPLIT warps (one warp per segment): partial sums [proof][part]
+            const size_t lo = (n + 3) * q / FSPLIT, hi = (n + 3) * (q + 1) / FSPLIT;
+            cdp_fixed_seg &f = segF[pr * FSPLIT + q];
             memset(&f, 0, sizeof f);
-            f.base_off = 0; f.scalars_off = (uint32_t)(pr * scal_pp); f.n = (uint32_t)(n + 3); f.remap_from = 0xFFFFFFFFu; f.out_idx = (uint32_t)pr;
+            f.base_off = (uint32_t)lo; f.scalars_off = (uint32_t)(pr * scal_pp + lo); f.n = (uint32_t)(hi - lo); f.remap_from = 0xFFFFFFFFu;
+            f.out_idx = (uint32_t)(pr * FSPLIT + q);
         }
         const size_t eoff[4] = {X_E1, X_E2, X_E3, X_E4}, elen[4] = {3, 4, 3, 4}, esc[4] = {0, 3, 7, 10};
         for (int e = 0; e < 4; e++)
@@ -325,7 +330,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         memcpy(uu, cmp + 3 * ell * 48, ell * 48);
         memcpy(uu + ell * 48, inf, 48); memcpy(uu + (ell + 1) * 48, inf, 48); memcpy(uu + (ell + 2) * 48, inf, 48); memcpy(uu + (ell + 3) * 48, p->H_comp, 48);
         StdRng rng(in->rng_seed ? in->rng_seed[pr] : 0x9e3779b97f4a7c15ULL + pr);
-        for (int i = 0; i < 8; i++) s.rho[i] = rng.fr_rand();  // one per accumulate_check (msm_accumulator.rs:44), in call order
+        for (int i = 0; i < 12; i++) s.rho[i] = rng.fr_rand();  // one per accumulate_check (msm_accumulator.rs:44), in call order; 8..11: SameScalar
         // same_perm (same_permutation_argument.rs:134-145)
         s.tr->append_point("same_perm_step1", pc + 48 * L.A);
         s.tr->append_point("same_perm_step1", s.M_comp);
@@ -454,33 +459,45 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         // (7), (8): R == a x vec_R, S == a x vec_S                                   curdleproofs.rs:293-294
         cf[oP + L.R] += rho[6]; cf[oP + L.S] += rho[7];
         for (size_t i = 0; i < ell; i++) { cf[oR + i] -= rho[6] * s.vec_a[i]; cf[oS + i] -= rho[7] * s.vec_a[i]; }
+        // SameScalar (same_scalar_argument.rs:127-136): four point equalities, each "sum == identity":
+        //   cm_A.T_1 + alpha cm_T.T_1 - z_t G_t ;  cm_A.T_2 + alpha cm_T.T_2 - z_k R - z_t H ;  the same for B / U / S / z_u.
+        // All their bases already sit in the accumulated check, so by default they join it with their own random factors (the
+        // MsmAccumulator construction applied to four more checks: a false equality survives with probability 2^-254);
+        // CDP_VERIFY_EXACT_EQ=1 evaluates them as four separate exact MSMs instead.
+        if (!p->exact_eq) {
+            const Fr r8 = rho[8], r9 = rho[9], r10 = rho[10], r11 = rho[11];
+            cf[oP + L.A1] += r8; cf[oP + L.T1] += r8 * alpha_ss; cf[cGt] -= r8 * s.z_t;
+            cf[oP + L.A2] += r9; cf[oP + L.T2] += r9 * alpha_ss; cf[oP + L.R] -= r9 * s.z_k; cf[cH] -= r9 * s.z_t;
+            cf[oP + L.B1] += r10; cf[oP + L.U1] += r10 * alpha_ss; cf[cGu] -= r10 * s.z_u;
+            cf[oP + L.B2] += r11; cf[oP + L.U2] += r11 * alpha_ss; cf[oP + L.S] -= r11 * s.z_k; cf[cH] -= r11 * s.z_u;
+        }
         // sum(G) and sum(Hvec) are not table bases: their coefficients go onto every G_i / Hvec_i
         for (size_t i = 0; i < ell; i++) cf[cG + i] += cf[cGsum];
         for (size_t i = ell; i < n; i++) cf[cG + i] += cf[cHsum];
         cf[cGsum] = cf[cHsum] = Fr::zero();
         uint8_t *sc = p->h_scal + pr * scal_pp * 32;
         for (size_t i = 0; i < p->big_n; i++) put_fr(sc + 32 * i, cf[i]);
-        // SameScalar equalities (same_scalar_argument.rs:127-136), each as "sum == identity":
-        //   cm_A.T_1 + alpha cm_T.T_1 - z_t G_t ;  cm_A.T_2 + alpha cm_T.T_2 - z_k R - z_t H ;  the same for B / U / S / z_u
-        uint8_t *se = sc + 32 * p->big_n;
+        uint8_t *se = sc + 32 * p->big_n;  // scalars of the exact form of the SameScalar equalities
         const Fr one = Fr::one();
         const Fr e[14] = {one, alpha_ss, s.z_t.neg(), one, alpha_ss, s.z_k.neg(), s.z_t.neg(), one, alpha_ss, s.z_u.neg(), one, alpha_ss, s.z_k.neg(), s.z_u.neg()};
         for (int i = 0; i < 14; i++) put_fr(se + 32 * i, e[i]);
     });
     // ---- final stage: per-proof part (one launch per 2048-point chunk) + CRS part (digit table) -> added per proof; the equalities
-    const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + 1;
+    const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + FSPLIT;
     t_host += now_ms() - t0;
     VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * scal_pp * 32));
     for (size_t c = 0; c < p->chunks; c++) {
         size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
         VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
     }
-    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segF, B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
-    VTRY(cdp_sum_groups_dev(p->ctx, p->d_jac, B, NS, B, p->d_jac + NS * B * 144));
-    VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
-    // results: [B accumulated sums] [4B equalities]
-    VTRY(cdp_normalize_dev(p->ctx, p->d_jac + NS * B * 144, 5 * B, nullptr, p->d_comp));
-    VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, 5 * B * 48));
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
+    // accumulated sum of proof pr = its chunk sums [chunk][pr] + its CRS parts [pr][part]
+    VTRY(cdp_sum_groups2_dev(p->ctx, p->d_jac, p->chunks, B, 1, p->d_jac + p->chunks * B * 144, FSPLIT, 1, FSPLIT, B, p->d_jac + NS * B * 144));
+    const size_t n_res = p->exact_eq ? 5 * B : B;
+    if (p->exact_eq) VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
+    // results: [B accumulated sums] ([4B equalities])
+    VTRY(cdp_normalize_dev(p->ctx, p->d_jac + NS * B * 144, n_res, nullptr, p->d_comp));
+    VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, n_res * 48));
     t0 = now_ms();
     VTRY(cdp_sync(p->ctx));
     t_wait += now_ms() - t0;
@@ -492,7 +509,8 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
             return true;
         };
         bool okk = is_inf(p->h_comp + pr * 48);
-        for (int e = 0; e < 4; e++) okk = okk && is_inf(p->h_comp + (B + 4 * pr + e) * 48);
+        if (p->exact_eq)
+            for (int e = 0; e < 4; e++) okk = okk && is_inf(p->h_comp + (B + 4 * pr + e) * 48);
         if (s.status == 1 && !okk) s.status = 0;
         ok_out[pr] = (uint8_t)s.status;
     }

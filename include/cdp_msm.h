@@ -120,6 +120,10 @@ int cdp_sum_jacobian_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t count, ui
 /* d_out_jac[g] = sum_{s < per_out} d_jac_in[s * group_stride + g] for g < n_out: adds the partial sums of many MSMs at once (the
  * chunk sums and the fixed-base part of each proof's accumulated check, /root/reference/src/msm_accumulator.rs:55-68). */
 int cdp_sum_groups_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t n_out, size_t per_out, size_t group_stride, uint8_t *d_out_jac);
+/* Two sources with their own strides: d_out_jac[g] = sum_{s < per_a} d_a[s * sa + g * ga] + sum_{s < per_b} d_b[s * sb + g * gb]
+ * (indices in points).  d_out_jac must not overlap the inputs. */
+int cdp_sum_groups2_dev(cdp_ctx *ctx, const uint8_t *d_a, size_t per_a, size_t sa, size_t ga, const uint8_t *d_b, size_t per_b, size_t sb,
+                        size_t gb, size_t n_out, uint8_t *d_out_jac);
 
 /* A batch of MSMs over device-resident bases and scalars.  Segment i computes
  *   sum_{j < n} d_scalars[scalars_off + j] * d_pts[pts_off + j]   (offsets in elements, not bytes). */

@@ -104,6 +104,28 @@ def test_verifier_rejects_like_the_reference(engine, oracle, proved):
     bv.close()
 
 
+@pytest.mark.parametrize("exact", [0, 1])
+def test_verifier_same_scalar_checks(engine, oracle, proved, exact, monkeypatch):
+    """The SameScalar equalities (same_scalar_argument.rs:127-136): tampered z_k / z_t / z_u and swapped commitment points must be
+    rejected, both when the equalities join the accumulated check (default) and as four exact MSMs (CDP_VERIFY_EXACT_EQ=1)."""
+    from curdleproofs_b200 import BatchVerifier
+    monkeypatch.setenv("CDP_VERIFY_EXACT_EQ", str(exact))
+    ell, crs, insts, proofs = proved
+    inst, proof = insts[0], proofs[0]
+    m = 5
+    o_pts = 9 * 48 + 32 + (2 + 4 * m) * 48 + 64        # A1 | A2 | B1 | B2
+    o_z = o_pts + 4 * 48                                # z_k | z_t | z_u
+    bump = lambda b, o: b[:o] + pr.fr_to_bytes((int.from_bytes(b[o:o + 32], "little") + 1) % pr.R_ORDER) + b[o + 32:]  # noqa: E731
+    swap = lambda b, o: b[:o] + proofs[1][o:o + 48] + b[o + 48:]  # noqa: E731
+    cases = [bump(proof, o_z), bump(proof, o_z + 32), bump(proof, o_z + 64)] + [swap(proof, o_pts + 48 * i) for i in range(4)] + [proof]
+    bv = BatchVerifier(engine, ell, crs, max_batch=len(cases))
+    got = bv.verify_batch([inst] * len(cases), cases)
+    want = [oracle.verify(inst, c) for c in cases]
+    assert want == [0] * 7 + [1]
+    assert got == want
+    bv.close()
+
+
 def test_verifier_chunked_accumulated_msm(engine, oracle):
     """ell = 508: 5*ell + 8 + proof points > 2048 bases, so the accumulated MSM runs in chunks (the ell = 1020 config path)."""
     from curdleproofs_b200 import BatchProver, BatchVerifier
