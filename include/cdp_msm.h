@@ -142,12 +142,13 @@ int cdp_msm_batch_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *
 /* ------------------------------------------------------------------ fixed-base MSM (CRS bases)
  * `util::msm` (/root/reference/src/util.rs:19-22) for call sites whose `points` are CRS elements (crs.vec_G, vec_H, H, G_t, G_u,
  * /root/reference/src/crs.rs:19-34): they are identical for every proof, so the engine keeps a digit table of them in HBM
- *   table[base][w][d] = d * 2^(c w) * B_base,  d = 1 .. 2^(c-1),  w < ceil(256 / c)        (c = 16: 50 MB per base)
+ *   table[base][w][d] = d * 2^(c w) * B_base,  d = 1 .. 2^(c-1),  w < ceil(256 / c)        (c = 16: 50 MB per base, c = 19: 352 MB)
  * and one (scalar, base) pair costs ceil(256 / c) gathered mixed additions.  Bases must be prime-order points or infinity;
  * scalars canonical (< r).  Results are the same group elements as cdp_msm over the same points.
  * A table is immutable after creation and may be used from any context of the same device concurrently. */
 typedef struct cdp_fixed_table cdp_fixed_table;
-int cdp_fixed_table_create(cdp_ctx *ctx, const uint8_t *affine_pts /* host */, size_t n_bases, int window_bits /* 2..16, 0 = default 16 */,
+int cdp_fixed_table_create(cdp_ctx *ctx, const uint8_t *affine_pts /* host */, size_t n_bases,
+                           int window_bits /* 2..20; 0 = default 16 */,
                            cdp_fixed_table **out);
 void cdp_fixed_table_destroy(cdp_ctx *ctx, cdp_fixed_table *t);
 size_t cdp_fixed_table_bytes(const cdp_fixed_table *t);

@@ -26,7 +26,7 @@ def bases(oracle):
     return bytes(pts)
 
 
-@pytest.fixture(scope="module", params=[16, 8, 5])
+@pytest.fixture(scope="module", params=[19, 16, 8, 5])
 def table(request, engine, bases):
     t = engine.fixed_table_create(bases, request.param)
     yield t
