@@ -182,27 +182,38 @@ __global__ void __launch_bounds__(128, OCC)
     }
     __syncwarp();
     // ---- phase 4: every lane sums its two slots (different lanes, different points => no serialisation; mixed additions) and writes
-    //      each sum to its place in [msm][window][slot]
+    //      each sum to its place in [msm][window][slot].  ONE loop over both lists -- the warp runs max_l (load_A + load_B) steps, not
+    //      max_l load_A + max_l load_B -- with the accumulator flushed where the first list ends.
+    const int slA = order[lane_id], slB = order[SLOTS - 1 - lane_id];
+    const int rA = slA / NB, rB = slB / NB;
+    const bool okA = w0 + rA < NWIN, okB = w0 + rB < NWIN;
+    const uint32_t cA = okA ? cnt[slA] : 0u, cB = okB ? cnt[slB] : 0u;
+    const uint16_t *lstA = lists + (size_t)rA * (2 * nmax) + (cur[slA] - cnt[slA]);
+    const uint16_t *lstB = lists + (size_t)rB * (2 * nmax) + (cur[slB] - cnt[slB]);
+    uint32_t *outA = bucket_sums + 36 * (((size_t)msm * NWIN + (w0 + rA)) * NB + (slA & (NB - 1)));
+    uint32_t *outB = bucket_sums + 36 * (((size_t)msm * NWIN + (w0 + rB)) * NB + (slB & (NB - 1)));
+    g1j acc;
+    g1j_set_inf(acc);
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const int sl = order[pass == 0 ? lane_id : SLOTS - 1 - lane_id];
-        const int r = sl / NB, w = w0 + r;
-        if (w >= NWIN) continue;
-        const uint32_t c1 = cnt[sl];
-        const uint16_t *lst = lists + (size_t)r * (2 * nmax) + (cur[sl] - c1);
-        g1j acc;
-        g1j_set_inf(acc);
-#pragma unroll 1
-        for (uint32_t e = 0; e < c1; e++) {
-            uint32_t id = lst[e];
-            uint32_t p = id & 0x7FFFu;
-            g1a q;
-            g1a_load(q, (p >> 1) < n_plain ? P + 24 * (size_t)(p >> 1) : PX);
-            if (p & 1) fp_mul_beta(q.x, q.x);
-            if (id & 0x8000u) fp_neg(q.y, q.y);
-            g1j_add_mixed(acc, acc, q);
+    for (uint32_t e = 0; e < cA + cB; e++) {
+        if (e == cA) {  // first list done (an empty slot A is written here too, at e = 0, as infinity)
+            if (okA) g1j_store(outA, acc);
+            g1j_set_inf(acc);
         }
-        g1j_store(bucket_sums + 36 * (((size_t)msm * NWIN + w) * NB + (sl & (NB - 1))), acc);
+        const uint32_t id = e < cA ? lstA[e] : lstB[e - cA];
+        const uint32_t p = id & 0x7FFFu;
+        g1a q;
+        g1a_load(q, (p >> 1) < n_plain ? P + 24 * (size_t)(p >> 1) : PX);
+        if (p & 1) fp_mul_beta(q.x, q.x);
+        if (id & 0x8000u) fp_neg(q.y, q.y);
+        g1j_add_mixed(acc, acc, q);
+    }
+    if (cB == 0) {  // the loop never crossed into list B: acc is still slot A's sum (or infinity), slot B is empty
+        if (okA) g1j_store(outA, acc);
+        g1j_set_inf(acc);
+        if (okB) g1j_store(outB, acc);
+    } else if (okB) {
+        g1j_store(outB, acc);
     }
 }
 
