@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(128, OCC)
         for (uint32_t p = lane_id; p < n2; p += 32) {
             int d = row[p];
             int ad = d < 0 ? -d : d;
-            if (ad) atomicAdd(&cnt[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
+            if (ad) atomicAdd(&cnt[r * NB + (row_top ? (ad - 1) * SP + (int)((p >> 1) & (SP - 1)) : ad - 1)], 1u);
         }
     }
     __syncwarp();
@@ -156,13 +156,19 @@ __global__ void __launch_bounds__(128, OCC)
         const bool row_top = (w0 + r == NWIN - 1);
         const int8_t *row = digits + r * dstride;
         uint16_t *lst = lists + (size_t)r * (2 * nmax);
-        for (uint32_t p = lane_id; p < n2; p += 32) {
-            int d = row[p];
-            int ad = d < 0 ? -d : d;
-            if (ad) {
-                uint32_t pos = atomicAdd(&cur[r * NB + (row_top ? (ad - 1) * SP + (int)(p & (SP - 1)) : ad - 1)], 1u);
-                lst[pos] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
+        // plain points (even ids) first, phi-points (odd ids) second: in phase 4 the lanes of a warp then reach the extra
+        // multiplication by beta at about the same step instead of diverging on it at every step
+#pragma unroll 1
+        for (uint32_t par = 0; par < 2; par++) {
+            for (uint32_t p = 2 * lane_id + par; p < n2; p += 64) {
+                int d = row[p];
+                int ad = d < 0 ? -d : d;
+                if (ad) {
+                    uint32_t pos = atomicAdd(&cur[r * NB + (row_top ? (ad - 1) * SP + (int)((p >> 1) & (SP - 1)) : ad - 1)], 1u);
+                    lst[pos] = (uint16_t)(p | (d < 0 ? 0x8000u : 0u));
+                }
             }
+            __syncwarp();
         }
     }
     // ---- phase 3: balance.  Slot loads are binomial (+-35% around the mean at these sizes) and a warp runs as long as its busiest lane,
