@@ -252,7 +252,7 @@ def main():
     proof0 = bytes(out[:bp.proof_size])
     # ---- secondary metric: verifies/s on the proofs just produced (CurdleproofsProof::deserialize + verify through cdp_verify_batch)
     bp.close()
-    VB = min(B, 512)
+    VB = B
     bv = BatchVerifier(eng, ell, crs, max_batch=VB, host_threads=host_threads)
     vout = (ctypes.c_uint8 * VB)()
 
