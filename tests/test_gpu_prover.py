@@ -47,3 +47,28 @@ def test_prover_rejects_bad_sizes(engine, oracle):
     crs = oracle.crs_points(4)
     with pytest.raises(CdpError):
         BatchProver(engine, 5, crs + bytes(96), max_batch=1)  # ell + 4 not a power of two (inner_product_argument.rs:116)
+
+
+def test_full_size_ell252_multi_lane_round_trip(engine, oracle):
+    """BASELINE config 2 at its full size: ell = 252 (n = 256), a batch large enough for several prover / verifier lanes.
+    Two proofs are compared byte for byte with the oracle; the whole batch goes through prove -> verify (size-independent
+    property: everything the prover emits is accepted, the same proofs attached to other instances are rejected)."""
+    from curdleproofs_b200 import BatchProver, BatchVerifier
+    ell, batch = 252, 72
+    crs = oracle.crs_points(ell)
+    base = [oracle.random_instance(ell, crs, seed=500 + i, threads=8) for i in range(3)]
+    insts = [base[i % 3] for i in range(batch)]
+    seeds = [9000 + i for i in range(batch)]
+    bp = BatchProver(engine, ell, crs, max_batch=batch)
+    assert bp.lanes >= 2
+    proofs = bp.prove_batch(insts, seeds)
+    bp.close()
+    for i in (0, batch - 1):
+        assert proofs[i] == oracle.prove(insts[i], rng_seed=seeds[i], threads=8)
+        assert oracle.verify(insts[i], proofs[i], threads=8) == 1
+    assert len(set(proofs)) == batch  # different RNG streams: all proofs distinct
+    bv = BatchVerifier(engine, ell, crs, max_batch=batch)
+    assert bv.verify_batch(insts, proofs) == [1] * batch
+    shifted = insts[1:] + insts[:1]   # every proof now sits on a different instance
+    assert bv.verify_batch(shifted, proofs) == [0] * batch
+    bv.close()
