@@ -962,6 +962,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
 // own host thread: while one lane hashes transcripts on the host, or sits in a latency-bound tail of a small launch, the
 // others keep the SMs busy.
 struct cdp_prover {
+    cdp_ctx *ctx0 = nullptr;  // the caller's context (lane 0): used by the whisk wrappers for their own launches
     cdp_fixed_table *table = nullptr;  // digit table of the CRS points, shared (read-only) by all lanes
     cdp_ctx *table_ctx = nullptr;
     std::vector<Lane *> lanes;
@@ -1000,6 +1001,7 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     if (lanes <= 0) lanes = max_batch >= 512 ? 8 : max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
     lanes = (int)std::min<size_t>((size_t)lanes, max_batch);
     cdp_prover *p = new cdp_prover();
+    p->ctx0 = ctx;
     p->ell = ell;
     p->max_batch = max_batch;
     size_t per_lane = (max_batch + lanes - 1) / lanes;
@@ -1080,6 +1082,97 @@ extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *
         for (int k = 1; k < 4; k++) p->timing[k] = std::max(p->timing[k], p->lanes[i]->timing[k]);
         p->traffic[0] += p->lanes[i]->h2d_bytes;
         p->traffic[1] += p->lanes[i]->d2h_bytes;
+    }
+    return CDP_OK;
+}
+
+// =================================================================================================== whisk byte-level API
+// generate_whisk_shuffle_proof (/root/reference/src/whisk.rs:144-179) for a batch: witnesses from the caller's rng stream, shuffled
+// trackers and the permutation commitment on the GPU (decompression, k * R / k * S, M through the CRS digit table), the proof through
+// cdp_prove_batch with the same stream handed on.
+namespace {
+// Montgomery one (R mod p): Z of an affine point lifted to Jacobian
+const uint64_t FP_ONE_MONT[6] = {0x760900000002fffdULL, 0xebf4000bc40c0002ULL, 0x5f48985753c758baULL, 0x77ce585370525745ULL,
+                                 0x5c071a97a256ec6dULL, 0x15f65ec3fa80e493ULL};
+void affine_to_jac(uint8_t out[144], const uint8_t aff[96]) {
+    bool inf = true;
+    for (int i = 0; i < 96; i++) inf = inf && aff[i] == 0;
+    memcpy(out, aff, 96);
+    if (inf) memset(out + 96, 0, 48);
+    else memcpy(out + 96, FP_ONE_MONT, 48);
+}
+}  // namespace
+
+extern "C" size_t cdp_whisk_shuffle_proof_size(size_t ell) { return 48 + cdp_proof_size(ell); }
+
+extern "C" int cdp_whisk_generate_shuffle_proofs(cdp_prover *p, size_t B, const uint8_t *pre_trackers, const uint64_t *rng_seed,
+                                                 const uint64_t *rng_skip_words, uint8_t *post_out, uint8_t *proofs_out) {
+    if (!p) return CDP_ERR_INVALID_ARG;
+    if (!pre_trackers || !rng_seed || !post_out || !proofs_out || B == 0 || B > p->max_batch) { p->err = "cdp_whisk_generate_shuffle_proofs: bad argument"; return CDP_ERR_INVALID_ARG; }
+    cdp_ctx *ctx = p->ctx0;
+    const size_t ell = p->ell, n = ell + NBL, psz = cdp_proof_size(ell), np = B * ell;
+    auto fail = [&](int rc, const char *what) { p->err = std::string(what) + ": " + cdp_last_error(ctx); return rc; };
+    // witnesses, in the reference's draw order (whisk.rs:153-154, util.rs:102)
+    std::vector<uint32_t> perm(np);
+    std::vector<uint8_t> kk(32 * B), mbl(128 * B);
+    std::vector<uint64_t> skip(B);
+    for (size_t b = 0; b < B; b++) {
+        StdRng rng(rng_seed[b]);
+        if (rng_skip_words) rng.skip_words(rng_skip_words[b]);
+        uint32_t *pm = perm.data() + b * ell;
+        for (size_t i = 0; i < ell; i++) pm[i] = (uint32_t)i;
+        rng.shuffle_u32(pm, ell);
+        rng.fr_rand().to_bytes(kk.data() + 32 * b);
+        for (int i = 0; i < 4; i++) rng.fr_rand().to_bytes(mbl.data() + 128 * b + 32 * i);
+        skip[b] = rng.words_consumed();  // CurdleproofsProof::new continues the same stream
+    }
+    // unzip_trackers: 2 * ell encodings per shuffle, r_G / k_r_G interleaved (whisk.rs:265-277)
+    std::vector<uint8_t> aff(2 * np * 96), status(2 * np);
+    int rc = cdp_decompress_batch(ctx, pre_trackers, 2 * np, aff.data(), status.data());
+    if (rc != CDP_OK) return fail(rc, "unzip_trackers");
+    // vec_T = sigma(k * vec_R), vec_U = sigma(k * vec_S)   (util.rs:94-97)
+    std::vector<uint8_t> ks(2 * np * 32), kaff(2 * np * 96);
+    for (size_t b = 0; b < B; b++)
+        for (size_t i = 0; i < 2 * ell; i++) memcpy(ks.data() + (b * 2 * ell + i) * 32, kk.data() + 32 * b, 32);
+    rc = cdp_scalar_mul_batch(ctx, aff.data(), ks.data(), 2 * np, kaff.data());
+    if (rc != CDP_OK) return fail(rc, "k * trackers");
+    std::vector<uint8_t> R(np * 96), S(np * 96), T(np * 96), U(np * 96), M(B * 144);
+    for (size_t b = 0; b < B; b++)
+        for (size_t i = 0; i < ell; i++) {
+            const size_t o = b * ell + i, src = b * ell + perm[o];
+            memcpy(R.data() + 96 * o, aff.data() + 96 * (2 * o), 96);
+            memcpy(S.data() + 96 * o, aff.data() + 96 * (2 * o + 1), 96);
+            memcpy(T.data() + 96 * o, kaff.data() + 96 * (2 * src), 96);
+            memcpy(U.data() + 96 * o, kaff.data() + 96 * (2 * src + 1), 96);
+        }
+    // M = msm(vec_G, sigma as field elements) + msm(vec_H, m_blinders)   (util.rs:99-103): one MSM over the first n table bases
+    std::vector<uint8_t> msc(32 * n);
+    for (size_t b = 0; b < B; b++) {
+        memset(msc.data(), 0, msc.size());
+        for (size_t i = 0; i < ell; i++) memcpy(msc.data() + 32 * i, &perm[b * ell + i], 4);
+        memcpy(msc.data() + 32 * ell, mbl.data() + 128 * b, 128);
+        rc = cdp_msm_fixed(ctx, p->table, 0, msc.data(), n, M.data() + 144 * b);
+        if (rc != CDP_OK) return fail(rc, "permutation commitment");
+    }
+    std::vector<uint8_t> proofs(B * psz);
+    cdp_prove_inputs in;
+    in.vec_R = R.data(); in.vec_S = S.data(); in.vec_T = T.data(); in.vec_U = U.data(); in.M = M.data();
+    in.permutation = perm.data(); in.k = kk.data(); in.vec_m_blinders = mbl.data(); in.rng_seed = rng_seed; in.rng_skip_words = skip.data();
+    rc = cdp_prove_batch(p, B, &in, proofs.data());
+    if (rc != CDP_OK) return rc;
+    // zip_trackers + serialisation: compress T, U (interleaved) and M
+    std::vector<uint8_t> jac((2 * np + B) * 144), comp((2 * np + B) * 48);
+    for (size_t o = 0; o < np; o++) {
+        affine_to_jac(jac.data() + 144 * (2 * o), T.data() + 96 * o);
+        affine_to_jac(jac.data() + 144 * (2 * o + 1), U.data() + 96 * o);
+    }
+    memcpy(jac.data() + 144 * 2 * np, M.data(), 144 * B);
+    rc = cdp_compress_batch(ctx, jac.data(), 2 * np + B, comp.data());
+    if (rc != CDP_OK) return fail(rc, "zip_trackers");
+    memcpy(post_out, comp.data(), 2 * np * 48);
+    for (size_t b = 0; b < B; b++) {
+        memcpy(proofs_out + b * (48 + psz), comp.data() + 48 * (2 * np + b), 48);
+        memcpy(proofs_out + b * (48 + psz) + 48, proofs.data() + b * psz, psz);
     }
     return CDP_OK;
 }

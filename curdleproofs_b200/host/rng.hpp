@@ -21,10 +21,29 @@ class StdRng {
         }
     }
     uint32_t next_u32() {
+        consumed_++;
         if (idx_ >= 64) { refill(); idx_ = 0; }
         return buf_[idx_++];
     }
+    // 32-bit words produced so far (what a caller hands over as `rng_skip_words` when it passes the same stream on)
+    uint64_t words_consumed() const { return consumed_; }
+    // rand 0.8 `gen_range(0..range)` on u32 (widening multiply, rejection zone) and `SliceRandom::shuffle` (Fisher-Yates from the
+    // top) -- `permutation.shuffle(rng)`, /root/reference/src/whisk.rs:153
+    uint32_t gen_range_u32(uint32_t range) {
+        const uint32_t zone = (range << __builtin_clz(range)) - 1;
+        for (;;) {
+            uint64_t m = (uint64_t)next_u32() * range;
+            if ((uint32_t)m <= zone) return (uint32_t)(m >> 32);
+        }
+    }
+    void shuffle_u32(uint32_t *v, size_t n) {
+        for (size_t i = n; i-- > 1;) {
+            uint32_t j = gen_range_u32((uint32_t)(i + 1));
+            uint32_t t = v[i]; v[i] = v[j]; v[j] = t;
+        }
+    }
     uint64_t next_u64() {
+        consumed_ += 2;
         if (idx_ < 63) {
             uint64_t r = ((uint64_t)buf_[idx_ + 1] << 32) | buf_[idx_];
             idx_ += 2;
@@ -56,7 +75,7 @@ class StdRng {
 
    private:
     uint32_t key_[8];
-    uint64_t counter_ = 0;
+    uint64_t counter_ = 0, consumed_ = 0;
     uint32_t buf_[64];
     int idx_ = 64;
 

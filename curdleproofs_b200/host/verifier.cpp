@@ -521,6 +521,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
 }  // namespace
 
 struct cdp_verifier {
+    cdp_ctx *ctx0 = nullptr;
     cdp_fixed_table *table = nullptr;
     cdp_ctx *table_ctx = nullptr;
     std::vector<VLane *> lanes;
@@ -552,6 +553,7 @@ extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell,
     if (lanes <= 0) lanes = max_batch >= 512 ? 8 : max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
     lanes = (int)std::min<size_t>((size_t)lanes, max_batch);
     cdp_verifier *v = new cdp_verifier();
+    v->ctx0 = ctx;
     v->ell = ell; v->max_batch = max_batch;
     size_t per_lane = (max_batch + lanes - 1) / lanes;
     // CRS digit table: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec) (crs.G_sum / crs.H_sum, src/crs.rs:46-47); CDP_FIXED_BITS overrides the width
@@ -609,5 +611,49 @@ extern "C" int cdp_verify_batch(cdp_verifier *v, size_t B, const cdp_verify_inpu
     }
     for (size_t i = 0; i < Ln; i++)
         if (rcs[i] != CDP_OK) { v->err = "lane " + std::to_string(i) + ": " + v->lanes[i]->err; return rcs[i]; }
+    return CDP_OK;
+}
+
+// is_valid_whisk_shuffle_proof (/root/reference/src/whisk.rs:106-130) for a batch: trackers and M decompressed on the GPU, then cdp_verify_batch
+extern "C" int cdp_whisk_verify_shuffle_proofs(cdp_verifier *v, size_t B, const uint8_t *pre_trackers, const uint8_t *post_trackers,
+                                               const uint8_t *proofs, const uint64_t *rng_seed, uint8_t *result) {
+    if (!v) return CDP_ERR_INVALID_ARG;
+    if (!pre_trackers || !post_trackers || !proofs || !result || B == 0 || B > v->max_batch) { v->err = "cdp_whisk_verify_shuffle_proofs: bad argument"; return CDP_ERR_INVALID_ARG; }
+    static const uint64_t FP_ONE_MONT[6] = {0x760900000002fffdULL, 0xebf4000bc40c0002ULL, 0x5f48985753c758baULL, 0x77ce585370525745ULL,
+                                            0x5c071a97a256ec6dULL, 0x15f65ec3fa80e493ULL};
+    cdp_ctx *ctx = v->ctx0;
+    const size_t ell = v->ell, psz = cdp_proof_size(ell), np = B * ell, wsz = 48 + psz;
+    // all encodings in one decompression: pre (2 np), post (2 np), M (B)
+    std::vector<uint8_t> comp((4 * np + B) * 48), aff((4 * np + B) * 96), status(4 * np + B);
+    memcpy(comp.data(), pre_trackers, 2 * np * 48);
+    memcpy(comp.data() + 2 * np * 48, post_trackers, 2 * np * 48);
+    for (size_t b = 0; b < B; b++) memcpy(comp.data() + (4 * np + b) * 48, proofs + b * wsz, 48);
+    int rc = cdp_decompress_batch(ctx, comp.data(), 4 * np + B, aff.data(), status.data());
+    if (rc != CDP_OK && rc != CDP_ERR_NOT_ON_CURVE) { v->err = std::string("decompression: ") + cdp_last_error(ctx); return rc; }
+    std::vector<uint8_t> R(np * 96), S(np * 96), T(np * 96), U(np * 96), M(B * 144), body(B * psz), bad(B, 0);
+    for (size_t b = 0; b < B; b++) {
+        for (size_t i = 0; i < ell; i++) {
+            const size_t o = b * ell + i;
+            memcpy(R.data() + 96 * o, aff.data() + 96 * (2 * o), 96);
+            memcpy(S.data() + 96 * o, aff.data() + 96 * (2 * o + 1), 96);
+            memcpy(T.data() + 96 * o, aff.data() + 96 * (2 * np + 2 * o), 96);
+            memcpy(U.data() + 96 * o, aff.data() + 96 * (2 * np + 2 * o + 1), 96);
+            bad[b] |= status[2 * o] | status[2 * o + 1] | status[2 * np + 2 * o] | status[2 * np + 2 * o + 1];
+        }
+        bad[b] |= status[4 * np + b];
+        const uint8_t *ma = aff.data() + 96 * (4 * np + b);
+        bool inf = true;
+        for (int i = 0; i < 96; i++) inf = inf && ma[i] == 0;
+        memcpy(M.data() + 144 * b, ma, 96);
+        if (inf) memset(M.data() + 144 * b + 96, 0, 48);
+        else memcpy(M.data() + 144 * b + 96, FP_ONE_MONT, 48);
+        memcpy(body.data() + b * psz, proofs + b * wsz + 48, psz);
+    }
+    cdp_verify_inputs in;
+    in.vec_R = R.data(); in.vec_S = S.data(); in.vec_T = T.data(); in.vec_U = U.data(); in.M = M.data(); in.proofs = body.data(); in.rng_seed = rng_seed;
+    rc = cdp_verify_batch(v, B, &in, result);
+    if (rc != CDP_OK) return rc;
+    for (size_t b = 0; b < B; b++)
+        if (bad[b]) result[b] = 2;
     return CDP_OK;
 }

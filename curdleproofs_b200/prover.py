@@ -42,6 +42,12 @@ def load_prover_library() -> ctypes.CDLL:
         lib.cdp_prove_batch.restype = c_int
         lib.cdp_prove_batch.argtypes = [c_void_p, c_size_t, POINTER(_ProveInputs), c_void_p]
         lib.cdp_prover_last_timing.argtypes = [c_void_p, POINTER(c_double)]
+        lib.cdp_whisk_shuffle_proof_size.restype = c_size_t
+        lib.cdp_whisk_shuffle_proof_size.argtypes = [c_size_t]
+        lib.cdp_whisk_generate_shuffle_proofs.restype = c_int
+        lib.cdp_whisk_generate_shuffle_proofs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.cdp_whisk_verify_shuffle_proofs.restype = c_int
+        lib.cdp_whisk_verify_shuffle_proofs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         lib.cdp_prover_last_traffic.argtypes = [c_void_p, POINTER(c_uint64)]
         _PLIB = lib
     return _PLIB
@@ -110,6 +116,22 @@ class BatchProver:
             return out
         raw = bytes(out)
         return [raw[i * self.proof_size:(i + 1) * self.proof_size] for i in range(B)]
+
+    def whisk_generate_shuffle_proofs(self, pre_trackers: list, rng_seeds, rng_skip_words=None):
+        """`generate_whisk_shuffle_proof` (/root/reference/src/whisk.rs:144-179) for a batch.  pre_trackers[b] = ell * 96 bytes
+        (r_G || k_r_G per tracker).  Returns (post_trackers, whisk_shuffle_proof_bytes) per shuffle."""
+        B, ell = len(pre_trackers), self.ell
+        wsz = int(self._lib.cdp_whisk_shuffle_proof_size(ell))
+        pre = _arr(b"".join(pre_trackers))
+        seeds = (c_uint64 * B)(*rng_seeds)
+        skips = (c_uint64 * B)(*rng_skip_words) if rng_skip_words is not None else None
+        post = (ctypes.c_uint8 * (B * ell * 96))()
+        out = (ctypes.c_uint8 * (B * wsz))()
+        rc = self._lib.cdp_whisk_generate_shuffle_proofs(self._h, B, pre, seeds, skips, post, out)
+        if rc != 0:
+            raise CdpError(f"cdp_whisk_generate_shuffle_proofs failed (code {rc}): {self._lib.cdp_prover_last_error(self._h).decode()}")
+        post, out = bytes(post), bytes(out)
+        return [(post[b * ell * 96:(b + 1) * ell * 96], out[b * wsz:(b + 1) * wsz]) for b in range(B)]
 
     # ---- accounting across the lanes' contexts (lane 0 is the caller's Engine) ----
     @property
@@ -201,6 +223,17 @@ class BatchVerifier:
         P = _arr(b"".join(proofs))
         seeds = (c_uint64 * B)(*rng_seeds) if rng_seeds is not None else None
         return list(self.verify_raw(B, R, S, T, U, M, P, seeds))
+
+    def whisk_verify_shuffle_proofs(self, pre_trackers: list, post_trackers: list, proofs: list, rng_seeds=None) -> list:
+        """`is_valid_whisk_shuffle_proof` (/root/reference/src/whisk.rs:106-130) for a batch: 1 valid, 0 invalid, 2 does not deserialise."""
+        B = len(proofs)
+        seeds = (c_uint64 * B)(*rng_seeds) if rng_seeds is not None else None
+        out = (ctypes.c_uint8 * B)()
+        rc = self._lib.cdp_whisk_verify_shuffle_proofs(self._h, B, _arr(b"".join(pre_trackers)), _arr(b"".join(post_trackers)),
+                                                       _arr(b"".join(proofs)), seeds, out)
+        if rc != 0:
+            raise CdpError(f"cdp_whisk_verify_shuffle_proofs failed (code {rc}): {self._lib.cdp_verifier_last_error(self._h).decode()}")
+        return list(out)
 
     def verify_raw(self, B, R, S, T, U, M, proofs, seeds=None, out=None):
         vp = lambda x: ctypes.cast(x, c_void_p) if x is not None else None  # noqa: E731

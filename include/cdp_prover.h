@@ -88,6 +88,24 @@ typedef struct {
 /* result[i]: 1 = Ok(()), 0 = Err(VerificationError), 2 = the proof does not deserialise (bad encoding / not in the subgroup) */
 int cdp_verify_batch(cdp_verifier *v, size_t batch, const cdp_verify_inputs *in, uint8_t *result);
 
+/* ------------------------------------------------------------------ Whisk byte-level API
+ * `generate_whisk_shuffle_proof` / `is_valid_whisk_shuffle_proof` (/root/reference/src/whisk.rs:106-179) for a batch of shuffles.
+ * A tracker is 96 bytes: r_G || k_r_G, two 48-byte compressed points (src/whisk.rs:38-44); a whisk shuffle proof is
+ * compress(M) || CurdleproofsProof::serialize = 48 + cdp_proof_size(ell) bytes (4496 at ell = 124, src/whisk.rs:23).
+ * The reference fixes ell = 124 at compile time (src/whisk.rs:28-29); here ell is the prover's / verifier's.
+ *
+ * generate: for shuffle b, with rng = StdRng::seed_from_u64(rng_seed[b]) advanced by rng_skip_words[b] 32-bit words (NULL = 0):
+ *   permutation.shuffle(rng); k = Fr::rand(rng); (vec_R, vec_S) = unzip(pre_trackers);
+ *   (vec_T, vec_U, M, m_blinders) = shuffle_permute_and_commit_input(..)  (src/util.rs:83-106);  proof = CurdleproofsProof::new(.., rng)
+ * post_trackers_out: batch * ell trackers (vec_T[i] || vec_U[i]); proofs_out: batch * cdp_whisk_shuffle_proof_size(ell) bytes.
+ * Returns CDP_ERR_NOT_ON_CURVE when a tracker does not deserialise (the reference's SerializationError). */
+size_t cdp_whisk_shuffle_proof_size(size_t ell);
+int cdp_whisk_generate_shuffle_proofs(cdp_prover *p, size_t batch, const uint8_t *pre_trackers, const uint64_t *rng_seed,
+                                      const uint64_t *rng_skip_words, uint8_t *post_trackers_out, uint8_t *proofs_out);
+/* verify: result[b] = 1 valid, 0 invalid, 2 a tracker or the proof does not deserialise (the reference returns Err there). */
+int cdp_whisk_verify_shuffle_proofs(cdp_verifier *v, size_t batch, const uint8_t *pre_trackers, const uint8_t *post_trackers,
+                                    const uint8_t *proofs, const uint64_t *rng_seed, uint8_t *result);
+
 /* Host<->device bytes moved by the last cdp_prove_batch call: [0] host-to-device, [1] device-to-host. */
 void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]);
 

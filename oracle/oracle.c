@@ -112,7 +112,8 @@ EXPORT int oracle_whisk_tracker_proof_seed0(uint8_t out[128]) {
  *   proof_out : 48 (M) + curdle_proof_size(m) bytes              (the 4496-byte golden string at ell=124)
  *   inst_out  : optional, 4*ell affine points R,S,T,U (96 B each), M (144 B jacobian), permutation (ell x u32), k (32 B),
  *               vec_m_blinders (4 x 32 B) and, as a u64, the number of u32 words the rng had produced when
- *               CurdleproofsProof::new was entered (so that a prover can be handed the same stream)
+ *               CurdleproofsProof::new was entered (so that a prover can be handed the same stream), then the same count
+ *               at the entry of generate_whisk_shuffle_proof
  *   verified  : result of is_valid_whisk_shuffle_proof on the serialised proof with the same rng */
 EXPORT int oracle_whisk_shuffle_proof_seed0(size_t ell, uint8_t *proof_out, uint8_t *inst_out, int *verified, int threads) {
     stdrng_t rng; stdrng_seed_from_u64(&rng, 0);
@@ -125,6 +126,7 @@ EXPORT int oracle_whisk_shuffle_proof_seed0(size_t ell, uint8_t *proof_out, uint
         fr_t k, r; fr_rand(&k, &rng); fr_rand(&r, &rng);
         g1j_t t; g1a_mul_fr(&t, &G, &r); g1j_to_affine(&vR[i], &t); g1a_mul_fr(&t, &vR[i], &k); g1j_to_affine(&vS[i], &t);
     }
+    uint64_t words_at_entry = (rng.counter / 4 - 1) * 64 + (uint64_t)rng.index;   /* rng position when generate_whisk_shuffle_proof is entered */
     uint32_t *perm = (uint32_t *)malloc(4 * ell);
     for (size_t i = 0; i < ell; i++) perm[i] = (uint32_t)i;
     stdrng_shuffle_u32(perm, ell, &rng);                                   /* :153 */
@@ -143,6 +145,7 @@ EXPORT int oracle_whisk_shuffle_proof_seed0(size_t ell, uint8_t *proof_out, uint
         fr_to_bytes(w, &k); w += 32;
         for (int i = 0; i < N_BLINDERS; i++) { fr_to_bytes(w, &m_bl[i]); w += 32; }
         memcpy(w, &words_before, 8);
+        memcpy(w + 8, &words_at_entry, 8);
     }
     if (verified) { /* is_valid_whisk_shuffle_proof :106-130 */
         curdle_proof_t pf2; g1j_t M2; const uint8_t *rd = proof_out;

@@ -151,7 +151,7 @@ class Oracle:
     def whisk_shuffle_proof_seed0(self, ell=124, threads=1, want_instance=False):
         size = 48 + self.L.oracle_proof_size(ell)
         out = _u8(size)
-        inst = _u8(384 * ell + 144 + 4 * ell + 32 + 128 + 8) if want_instance else None
+        inst = _u8(384 * ell + 144 + 4 * ell + 32 + 128 + 16) if want_instance else None
         ok = c_int(-1)
         n = self.L.oracle_whisk_shuffle_proof_seed0(ell, out, inst, ctypes.byref(ok), threads)
         assert n == size
@@ -163,7 +163,8 @@ class Oracle:
                      U=raw[288 * ell:o], M=raw[o:o + 144],
                      perm=[int.from_bytes(raw[o + 144 + 4 * i:o + 148 + 4 * i], "little") for i in range(ell)],
                      k=raw[o + 144 + 4 * ell:o + 176 + 4 * ell], m_blinders=raw[o + 176 + 4 * ell:o + 304 + 4 * ell],
-                     rng_words=int.from_bytes(raw[o + 304 + 4 * ell:o + 312 + 4 * ell], "little"))
+                     rng_words=int.from_bytes(raw[o + 304 + 4 * ell:o + 312 + 4 * ell], "little"),
+                     whisk_entry_words=int.from_bytes(raw[o + 312 + 4 * ell:o + 320 + 4 * ell], "little"))
         return bytes(out), bool(ok.value), d
 
     def whisk_tracker_proof_seed0(self):
