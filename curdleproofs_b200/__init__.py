@@ -17,6 +17,8 @@ There is no CPU fallback: constructing an ``Engine`` without the built extension
 device raises.
 """
 from .engine import Engine, CdpError, FixedSeg, FixedTable, lib_path, load_library  # noqa: F401
-from .prover import BatchProver, BatchVerifier, load_prover_library  # noqa: F401
+from .prover import (BatchProver, BatchVerifier, load_prover_library, whisk_generate_tracker_proofs,  # noqa: F401
+                     whisk_verify_tracker_proofs)
 
-__all__ = ["Engine", "CdpError", "FixedSeg", "FixedTable", "lib_path", "load_library", "BatchProver", "BatchVerifier", "load_prover_library"]
+__all__ = ["Engine", "CdpError", "FixedSeg", "FixedTable", "lib_path", "load_library", "BatchProver", "BatchVerifier", "load_prover_library",
+           "whisk_generate_tracker_proofs", "whisk_verify_tracker_proofs"]

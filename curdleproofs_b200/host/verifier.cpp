@@ -19,6 +19,8 @@
 //   * only two values have to come back mid-transcript: D (grand_product_argument.rs:223) and A' (curdleproofs.rs:255).
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -290,6 +292,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         pts(9); fr(s.r_p); pts(2 + 4 * m); fr(s.c_final); fr(s.d_final); pts(4); fr(s.z_k); fr(s.z_t); fr(s.z_u); pts(3 + 6 * m); fr(s.x_final);
     });
     t_host += now_ms() - t0;
+    if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host part 1: %.2f ms (B=%zu)\n", now_ms() - t0, B);
     VTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
     VTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
     VTRY(cdp_h2d(p->ctx, p->d_pcomp, p->h_pcomp, B * NP * 48));
@@ -353,6 +356,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     });
     // ---- stage A: D and A' come back as encodings
     t_host += now_ms() - t0;
+    if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host part 2: %.2f ms (B=%zu)\n", now_ms() - t0, B);
     VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * 6 * 32));
     VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segAf, 2 * B, 2 * B, p->d_pts, p->d_jac));
     VTRY(cdp_normalize_dev(p->ctx, p->d_jac, 2 * B, nullptr, p->d_comp));
@@ -485,6 +489,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     // ---- final stage: per-proof part (one launch per 2048-point chunk) + CRS part (digit table) -> added per proof; the equalities
     const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + FSPLIT;
     t_host += now_ms() - t0;
+    if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host part 3: %.2f ms (B=%zu)\n", now_ms() - t0, B);
     VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * scal_pp * 32));
     for (size_t c = 0; c < p->chunks; c++) {
         size_t cnt = std::min<size_t>(2048, var_n - c * 2048);

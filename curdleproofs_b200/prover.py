@@ -171,6 +171,35 @@ class BatchProver:
         return {"total_ms": t[0], "host_ms": t[1], "gpu_wait_ms": t[2], "copy_issue_ms": t[3]}
 
 
+def whisk_generate_tracker_proofs(engine: Engine, trackers: list, ks: list, rng_seeds, rng_skip_words=None) -> list:
+    """`generate_whisk_tracker_proof` (/root/reference/src/whisk.rs:231-263) for a batch: 128-byte proofs A || B || s."""
+    lib = load_prover_library()
+    lib.cdp_whisk_generate_tracker_proofs.restype = c_int
+    lib.cdp_whisk_generate_tracker_proofs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    B = len(trackers)
+    out = (ctypes.c_uint8 * (128 * B))()
+    seeds = (c_uint64 * B)(*rng_seeds)
+    skips = (c_uint64 * B)(*rng_skip_words) if rng_skip_words is not None else None
+    rc = lib.cdp_whisk_generate_tracker_proofs(engine.handle, B, _arr(b"".join(trackers)), _arr(b"".join(ks)), seeds, skips, out)
+    if rc != 0:
+        raise CdpError(f"cdp_whisk_generate_tracker_proofs failed (code {rc})")
+    raw = bytes(out)
+    return [raw[128 * i:128 * i + 128] for i in range(B)]
+
+
+def whisk_verify_tracker_proofs(engine: Engine, trackers: list, k_commitments: list, proofs: list) -> list:
+    """`is_valid_whisk_tracker_proof` (/root/reference/src/whisk.rs:183-229) for a batch: 1 valid, 0 invalid, 2 does not deserialise."""
+    lib = load_prover_library()
+    lib.cdp_whisk_verify_tracker_proofs.restype = c_int
+    lib.cdp_whisk_verify_tracker_proofs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]
+    B = len(proofs)
+    out = (ctypes.c_uint8 * B)()
+    rc = lib.cdp_whisk_verify_tracker_proofs(engine.handle, B, _arr(b"".join(trackers)), _arr(b"".join(k_commitments)), _arr(b"".join(proofs)), out)
+    if rc != 0:
+        raise CdpError(f"cdp_whisk_verify_tracker_proofs failed (code {rc})")
+    return list(out)
+
+
 class _VerifyInputs(ctypes.Structure):
     _fields_ = [("vec_R", c_void_p), ("vec_S", c_void_p), ("vec_T", c_void_p), ("vec_U", c_void_p), ("M", c_void_p), ("proofs", c_void_p),
                 ("rng_seed", c_void_p)]

@@ -106,6 +106,15 @@ int cdp_whisk_generate_shuffle_proofs(cdp_prover *p, size_t batch, const uint8_t
 int cdp_whisk_verify_shuffle_proofs(cdp_verifier *v, size_t batch, const uint8_t *pre_trackers, const uint8_t *post_trackers,
                                     const uint8_t *proofs, const uint64_t *rng_seed, uint8_t *result);
 
+/* Tracker opening proofs (src/whisk.rs:183-263): knowledge of k with k_r_G = k * r_G and k_commitment = k * G.
+ * trackers: batch * 96 bytes; k: batch canonical 32-byte scalars; proofs: batch * 128 bytes (A || B || s, src/whisk.rs:24-25).
+ * generate: blinder = Fr::rand(StdRng::seed_from_u64(rng_seed[b]) advanced by rng_skip_words[b] words); verify: result[b] = 1 / 0 / 2
+ * (valid / invalid / an encoding does not deserialise). */
+int cdp_whisk_generate_tracker_proofs(cdp_ctx *ctx, size_t batch, const uint8_t *trackers, const uint8_t *k, const uint64_t *rng_seed,
+                                      const uint64_t *rng_skip_words, uint8_t *proofs_out);
+int cdp_whisk_verify_tracker_proofs(cdp_ctx *ctx, size_t batch, const uint8_t *trackers, const uint8_t *k_commitments, const uint8_t *proofs,
+                                    uint8_t *result);
+
 /* Host<->device bytes moved by the last cdp_prove_batch call: [0] host-to-device, [1] device-to-host. */
 void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[2]);
 

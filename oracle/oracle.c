@@ -89,6 +89,18 @@ EXPORT void oracle_stdrng_seed_bytes(uint64_t seed, uint8_t out[32]) { stdrng_t 
 
 /* ---- whisk golden vectors ---- */
 /* whisk_tracker_proof test, src/whisk.rs:381-402 (uses :50-67, :231-263) */
+/* inputs of the same test for a caller that runs the product API: k (32) | tracker r_G, k_r_G (96) | k_commitment (48) | u64 rng words consumed before generate_whisk_tracker_proof */
+EXPORT int oracle_whisk_tracker_inputs_seed0(uint8_t out[184]) {
+    stdrng_t rng; stdrng_seed_from_u64(&rng, 0);
+    fr_t k, r; fr_rand(&k, &rng); fr_rand(&r, &rng);
+    g1a_t G; g1a_generator(&G);
+    g1j_t r_G, k_r_G, k_G; g1a_mul_fr(&r_G, &G, &r);
+    g1a_t r_Ga; g1j_to_affine(&r_Ga, &r_G); g1a_mul_fr(&k_r_G, &r_Ga, &k); g1a_mul_fr(&k_G, &G, &k);
+    fr_to_bytes(out, &k); g1j_compress(out + 32, &r_G); g1j_compress(out + 80, &k_r_G); g1j_compress(out + 128, &k_G);
+    uint64_t words = (rng.counter / 4 - 1) * 64 + (uint64_t)rng.index;
+    memcpy(out + 176, &words, 8);
+    return 0;
+}
 EXPORT int oracle_whisk_tracker_proof_seed0(uint8_t out[128]) {
     stdrng_t rng; stdrng_seed_from_u64(&rng, 0);
     fr_t k, r, blinder; fr_rand(&k, &rng); fr_rand(&r, &rng);

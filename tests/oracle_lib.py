@@ -167,6 +167,12 @@ class Oracle:
                      whisk_entry_words=int.from_bytes(raw[o + 312 + 4 * ell:o + 320 + 4 * ell], "little"))
         return bytes(out), bool(ok.value), d
 
+    def whisk_tracker_inputs_seed0(self):
+        out = _u8(184)
+        self.L.oracle_whisk_tracker_inputs_seed0(out)
+        raw = bytes(out)
+        return dict(k=raw[:32], tracker=raw[32:128], k_commitment=raw[128:176], rng_words=int.from_bytes(raw[176:184], "little"))
+
     def whisk_tracker_proof_seed0(self):
         out = _u8(128)
         self.L.oracle_whisk_tracker_proof_seed0(out)

@@ -41,3 +41,17 @@ def test_whisk_api_reproduces_the_golden_vector(engine, oracle):
     assert got[:5] == [1, 1, 0, 0, 0]
     assert got[5] in (0, 2)
     bv.close()
+
+
+def test_whisk_tracker_proof_golden(engine, oracle):
+    """`whisk_tracker_proof` (src/whisk.rs:381-402): the 128-byte seed-0 proof through the product API, and its validity check."""
+    from curdleproofs_b200 import whisk_generate_tracker_proofs, whisk_verify_tracker_proofs
+    golden = bytes.fromhex(open(os.path.join(HERE, "golden", "whisk_tracker_proof_seed0.hex")).read().strip())
+    t = oracle.whisk_tracker_inputs_seed0()
+    proofs = whisk_generate_tracker_proofs(engine, [t["tracker"]] * 2, [t["k"]] * 2, [0, 7], rng_skip_words=[t["rng_words"], 0])
+    assert proofs[0] == golden
+    assert proofs[1] != golden
+    bad_s = proofs[0][:96] + bytes([proofs[0][96] ^ 1]) + proofs[0][97:]
+    wrong_commitment = t["tracker"][:48]  # r_G instead of k_G
+    got = whisk_verify_tracker_proofs(engine, [t["tracker"]] * 4, [t["k_commitment"]] * 3 + [wrong_commitment], [proofs[0], proofs[1], bad_s, proofs[0]])
+    assert got == [1, 1, 0, 0]
