@@ -70,7 +70,10 @@ struct FoldStage {
 struct ProofState {
     std::unique_ptr<Transcript> tr;
     std::vector<Fr> vec_a, a_perm, factors, c, d, r_c, r_d, u, x, r_sm;
-    std::vector<Fr> wG, wGp, wS;  // fold weights of the original bases: G (gamma), G' (u, gamma^-1), G_with_blinders (gamma)
+    // fold weights of the original bases: G (gamma), G' (u, gamma^-1), G_with_blinders (gamma).  Kept as CANONICAL integers in the Fr
+    // container: a Montgomery product of a canonical value and a Montgomery-form value is the canonical product, so `weight * scalar`
+    // is already the byte form the MSM wants (no separate conversion), and `weight * gamma` stays canonical.
+    std::vector<Fr> wG, wGp, wS;
     Fr a_bl[2], c_bl[4], r_t, r_u, r_a, r_b, r_k, k, m_bl[4], b_bl[4], rb_alpha[4];
     Fr alpha_sp, beta_sp, gprod_result, alpha_g, beta_g, r_p, z, alpha_i, beta_i;
     Fr z_k, z_t, z_u, c_final, d_final, x_final;
@@ -188,6 +191,10 @@ void batch_inverse(std::vector<Fr> &xs) {
 }
 
 void put_fr(uint8_t *dst, const Fr &x) { x.to_bytes(dst); }
+// values held as canonical integers inside the Fr container (the fold weights): see ProofState
+void put_canonical(uint8_t *dst, const Fr &x) { memcpy(dst, x.v, 32); }
+Fr fr_canonical_one() { uint64_t one[4] = {1, 0, 0, 0}; return Fr::raw(one); }
+Fr fr_to_canonical_value(const Fr &x) { uint64_t c[4]; x.to_canonical(c); return Fr::raw(c); }
 
 // ---- stage table construction --------------------------------------------------------------------------------
 struct SegSpec {
@@ -799,8 +806,9 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             s.d[i] = s.r_d[i] + s.alpha_i * s.d[i];
         }
         // fold weights of the original bases: G^(k)_i = sum_{j = i mod n_k} wG[j] G_j,  G'^(k)_i = sum wGp[j] G_j  (G' = u o G, :92-102 of gprod)
-        s.wG.assign(n, Fr::one());
-        s.wGp = s.u;
+        s.wG.assign(n, fr_canonical_one());
+        s.wGp.resize(n);
+        for (size_t j = 0; j < n; j++) s.wGp[j] = fr_to_canonical_value(s.u[j]);
     });
     t_host += now_ms() - t0;
     for (size_t k = 0; k < m; k++) {
@@ -815,8 +823,8 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             for (size_t j = 0; j < n; j++) {
                 const size_t i = j & (h - 1);
                 const bool hi = (j & h) != 0;
-                put_fr(sc + 32 * j, s.wG[j] * (hi ? cL[i] : cR[i]));
-                put_fr(sc + 32 * (n + 2 + j), s.wGp[j] * (hi ? dL[i] : dR[i]));
+                put_canonical(sc + 32 * j, s.wG[j] * (hi ? cL[i] : cR[i]));
+                put_canonical(sc + 32 * (n + 2 + j), s.wGp[j] * (hi ? dL[i] : dR[i]));
             }
             put_fr(sc + 32 * n, s.beta_i * inner_product(cL, dR, h));        // H = beta crs_H ; L_C += <c_L,d_R> H
             put_fr(sc + 32 * (n + 1), s.beta_i * inner_product(cR, dL, h));  //                   R_C += <c_R,d_L> H
@@ -879,7 +887,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         for (size_t i = 0; i < ell; i++) s.x[i] = s.r_sm[i] + a_sm * s.a_perm[i];
         const Fr tail[4] = {s.a_bl[0], s.a_bl[1], s.r_t, s.r_u};  // vec_a_with_blinders, curdleproofs.rs:157-160
         for (int i = 0; i < 4; i++) s.x[ell + i] = s.r_sm[ell + i] + a_sm * tail[i];
-        s.wS.assign(n, Fr::one());
+        s.wS.assign(n, fr_canonical_one());
     });
     t_host += now_ms() - t0;
     for (size_t k = 0; k < m; k++) {
@@ -890,7 +898,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             ProofState &s = p->ps[pr];
             uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
             // msm(G_R, x_L), msm(G_L, x_R) (:107,:110) over the original G_with_blinders; T, U use the folded vectors
-            for (size_t j = 0; j < n; j++) put_fr(sc + 32 * j, s.wS[j] * s.x[(j & h) ? (j & (h - 1)) : h + (j & (h - 1))]);
+            for (size_t j = 0; j < n; j++) put_canonical(sc + 32 * j, s.wS[j] * s.x[(j & h) ? (j & (h - 1)) : h + (j & (h - 1))]);
             for (size_t i = 0; i < 2 * h; i++) put_fr(sc + 32 * (n + i), s.x[i]);
         });
         t_host += now_ms() - t0;
