@@ -24,7 +24,8 @@ namespace cdp {
 // Handles infinity bases and zero scalars (digits 0) and all-equal scalars (one long list, still correct).
 template <int C>
 __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
-                                                    const msm_seg_t *__restrict__ segs, int8_t *__restrict__ dig, uint32_t rowstride) {
+                                                    const msm_seg_t *__restrict__ segs, int8_t *__restrict__ dig, uint32_t rowstride,
+                                                    uint32_t *__restrict__ bx, uint32_t nmax) {
     constexpr int NB = 1 << (C - 1);
     constexpr int NWIN = (130 + C - 1) / C;
     const msm_seg_t seg = segs[blockIdx.x];
@@ -46,6 +47,12 @@ __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__
         for (int q = 0; q < 6; q++) {
             uint4 v = pp[q];
             nz |= v.x | v.y | v.z | v.w;
+        }
+        {   // x-coordinate of phi(P) = (beta x, y), once per base instead of once per bucket addition
+            fp x;
+            fp_load(x, reinterpret_cast<const uint32_t *>(pp));
+            fp_mul_beta(x, x);
+            fp_store(bx + 12 * ((size_t)blockIdx.x * nmax + j), x);
         }
         glv_t g;
         glv_split(g, k);
@@ -75,7 +82,8 @@ __global__ void __launch_bounds__(128) k_msm_digits(const uint32_t *__restrict__
 template <int C, int OCC>
 __global__ void __launch_bounds__(128, OCC)
     k_msm_buckets(const uint32_t *__restrict__ pts, const msm_seg_t *__restrict__ segs, const int8_t *__restrict__ dig, uint32_t rowstride,
-                  uint32_t *__restrict__ bucket_sums /* [msm][nwin][NB] jacobian */, uint32_t nmax, uint32_t n_msm) {
+                  uint32_t *__restrict__ bucket_sums /* [msm][nwin][NB] jacobian */, uint32_t nmax, uint32_t n_msm,
+                  const uint32_t *__restrict__ bx /* [msm][nmax] beta * x */) {
     constexpr int NB = 1 << (C - 1);
     constexpr int NWIN = (130 + C - 1) / C;
     constexpr int SLOTS = 64;                       // (window, bucket) slots per warp: two per lane
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(128, OCC)
         const uint32_t p = id & 0x7FFFu;
         g1a q;
         g1a_load(q, (p >> 1) < n_plain ? P + 24 * (size_t)(p >> 1) : PX);
-        if (p & 1) fp_mul_beta(q.x, q.x);
+        if (p & 1) fp_load(q.x, bx + 12 * ((size_t)msm * nmax + (p >> 1)));  // phi(P): beta * x from the digit kernel
         if (id & 0x8000u) fp_neg(q.y, q.y);
         g1j_add_mixed(acc, acc, q);
     }
@@ -230,7 +238,8 @@ cudaError_t CDP_CAT(launch_msm_buckets_c, MSM_C)(cudaStream_t st, const uint32_t
     constexpr int C = MSM_C;
     const uint32_t rowstride = msm_dig_rowstride(nmax);
     dim3 dgrid(count, nmax > 512 ? (nmax + 511) / 512 : 1);
-    k_msm_digits<C><<<dgrid, 128, 0, st>>>(pts, scalars, segs, dig, rowstride);
+    uint32_t *bx = reinterpret_cast<uint32_t *>(dig + msm_dig_rows_bytes(C, nmax, count));
+    k_msm_digits<C><<<dgrid, 128, 0, st>>>(pts, scalars, segs, dig, rowstride, bx, nmax);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     size_t smem = msm_smem_bytes(C, nmax);
@@ -241,7 +250,7 @@ cudaError_t CDP_CAT(launch_msm_buckets_c, MSM_C)(cudaStream_t st, const uint32_t
         if (e != cudaSuccess) return e;
     }
     const uint64_t units = (uint64_t)count * msm_groups_for(C);
-    kern<<<(unsigned)((units + 3) / 4), 128, smem, st>>>(pts, segs, dig, rowstride, bucket_sums, nmax, count);
+    kern<<<(unsigned)((units + 3) / 4), 128, smem, st>>>(pts, segs, dig, rowstride, bucket_sums, nmax, count, bx);
     return cudaGetLastError();
 }
 

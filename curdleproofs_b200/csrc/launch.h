@@ -117,7 +117,9 @@ constexpr int msm_nb_for(int c) { return 1 << (c - 1); }
 constexpr int msm_wpw_for(int c) { return 64 / msm_nb_for(c); }
 constexpr int msm_groups_for(int c) { return (msm_nwin_for(c) + msm_wpw_for(c) - 1) / msm_wpw_for(c); }
 inline uint32_t msm_dig_rowstride(size_t nmax) { return (uint32_t)((2 * nmax + 15) & ~size_t(15)); }
-inline size_t msm_dig_bytes(int c, size_t nmax, size_t count) { return count * (size_t)msm_nwin_for(c) * msm_dig_rowstride(nmax); }
+// scratch of one small-MSM launch: the digit rows, then beta * x of every base (48 B each)
+inline size_t msm_dig_rows_bytes(int c, size_t nmax, size_t count) { return (count * (size_t)msm_nwin_for(c) * msm_dig_rowstride(nmax) + 255) & ~size_t(255); }
+inline size_t msm_dig_bytes(int c, size_t nmax, size_t count) { return msm_dig_rows_bytes(c, nmax, count) + count * nmax * 48; }
 __host__ __device__ inline size_t msm_smem_per_warp(int c, size_t nmax) {
     size_t wpw = 64 >> (c - 1), dstride = ((2 * nmax + 15) & ~size_t(15)) + 16;
     return (wpw * dstride + wpw * 2 * nmax * sizeof(uint16_t) + 128 * sizeof(uint32_t) + 64 + 15) & ~size_t(15);
