@@ -10,10 +10,12 @@
 
 namespace cdp {
 
-// One thread per element.  Joint double-and-add over the two 128-bit GLV halves; the three possible addends per step:
-//   (1,0) -> P = (x, y)      (0,1) -> phi(P) = (beta x, y)      (1,1) -> P + phi(P) = -phi^2(P) = (beta^2 x, -y)
-// so each step is one doubling plus at most one mixed addition.  Within one fold job all threads share the scalar, so
-// the add/skip pattern is warp-uniform whenever a job spans whole warps.
+// One thread per element.  The two 128-bit GLV halves (k1, k2) are recoded into the joint sparse form (Solinas): digits in {0, +-1},
+// on average only every second column non-zero (plain binary: three out of four).  The addends of a column:
+//   (+-1, 0) -> +-P = (x, +-y)      (0, +-1) -> +-phi(P) = (beta x, +-y)      +-(1, 1) -> +-(P + phi(P)) = -+phi^2(P) = (beta^2 x, -+y)
+// are affine and free; +-(1, -1) -> +-(P - phi(P)) is computed once per element (Jacobian) and added with a full addition.
+// So: 128 doublings, ~48 mixed and ~16 full additions per element instead of 128 doublings and ~96 mixed additions.  Within one fold
+// job all threads share the scalar, so the column pattern is warp-uniform whenever a job spans whole warps.
 template <int OCC>
 __global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
                                                    const smul_job_t *__restrict__ jobs, uint32_t elems_per_job, uint32_t total,
@@ -30,35 +32,83 @@ __global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restri
     }
     glv_t g;
     glv_split(g, k);
+    // ---- joint sparse form, least significant column first; kept as four bit masks (non-zero / negative, per half), 130 columns
+    uint32_t nz0[5] = {0, 0, 0, 0, 0}, sg0[5] = {0, 0, 0, 0, 0}, nz1[5] = {0, 0, 0, 0, 0}, sg1[5] = {0, 0, 0, 0, 0};
+    int top = -1;
+    {
+        uint32_t a0 = g.k1[0], a1 = g.k1[1], a2 = g.k1[2], a3 = g.k1[3], b0 = g.k2[0], b1 = g.k2[1], b2 = g.k2[2], b3 = g.k2[3];
+        uint32_t d0 = 0, d1 = 0;
+#pragma unroll 1
+        for (int col = 0; col < 130; col++) {
+            if ((a0 | a1 | a2 | a3 | b0 | b1 | b2 | b3 | d0 | d1) == 0) break;
+            const uint32_t l0 = (a0 + d0) & 7, l1 = (b0 + d1) & 7;   // only the three low bits of k + d matter
+            int u0 = 0, u1 = 0;
+            if (l0 & 1) {
+                u0 = 2 - (int)(l0 & 3);                                // l0 mods 4: 1 -> 1, 3 -> -1
+                if ((l0 == 3 || l0 == 5) && (l1 & 3) == 2) u0 = -u0;
+            }
+            if (l1 & 1) {
+                u1 = 2 - (int)(l1 & 3);
+                if ((l1 == 3 || l1 == 5) && (l0 & 3) == 2) u1 = -u1;
+            }
+            if (2 * (int)d0 == 1 + u0) d0 = 1 - d0;
+            if (2 * (int)d1 == 1 + u1) d1 = 1 - d1;
+            const uint32_t bit = 1u << (col & 31);
+            if (u0) { nz0[col >> 5] |= bit; if (u0 < 0) sg0[col >> 5] |= bit; }
+            if (u1) { nz1[col >> 5] |= bit; if (u1 < 0) sg1[col >> 5] |= bit; }
+            if (u0 | u1) top = col;
+            a0 = (a0 >> 1) | (a1 << 31); a1 = (a1 >> 1) | (a2 << 31); a2 = (a2 >> 1) | (a3 << 31); a3 >>= 1;
+            b0 = (b0 >> 1) | (b1 << 31); b1 = (b1 >> 1) | (b2 << 31); b2 = (b2 >> 1) | (b3 << 31); b3 >>= 1;
+        }
+    }
     g1a P;
     g1a_load(P, pts + 24 * ((size_t)job.src_off + e));
     fp bx, bbx, ny;
     fp_mul_beta(bx, P.x);
     fp_mul_beta(bbx, bx);
     fp_neg(ny, P.y);
+    // D = P - phi(P), Jacobian (P + (beta x, -y)); infinity stays infinity
+    g1j D;
+    {
+        g1j Pj;
+        g1j_from_affine(Pj, P);
+        g1a nphi;
+        nphi.x = bx; nphi.y = ny;
+        if (g1a_is_inf(P)) g1a_set_inf(nphi);
+        g1j_add_mixed(D, Pj, nphi);
+    }
     g1j acc;
     g1j_set_inf(acc);
-    // iteration 128 is the optional final "+ L" (one inlined addition serves both uses)
+    // column -1 is the optional final "+ L" (one inlined mixed addition serves both uses)
 #pragma unroll 1
-    for (int bit = 127; bit >= -1; bit--) {
+    for (int col = top; col >= -1; col--) {
         g1a q;
-        bool do_add;
-        if (bit >= 0) {
+        bool do_madd = false, do_jadd = false, neg_d = false;
+        if (col >= 0) {
             g1j_dbl(acc, acc);
-            uint32_t b1 = g.k1[3] >> 31, b2 = g.k2[3] >> 31;
-            g.k1[3] = (g.k1[3] << 1) | (g.k1[2] >> 31); g.k1[2] = (g.k1[2] << 1) | (g.k1[1] >> 31);
-            g.k1[1] = (g.k1[1] << 1) | (g.k1[0] >> 31); g.k1[0] <<= 1;
-            g.k2[3] = (g.k2[3] << 1) | (g.k2[2] >> 31); g.k2[2] = (g.k2[2] << 1) | (g.k2[1] >> 31);
-            g.k2[1] = (g.k2[1] << 1) | (g.k2[0] >> 31); g.k2[0] <<= 1;
-            do_add = (b1 | b2) != 0;
-            fp_select(q.x, P.x, bx, b2 != 0);
-            fp_select(q.x, q.x, bbx, (b1 & b2) != 0);
-            fp_select(q.y, P.y, ny, (b1 & b2) != 0);
+            const uint32_t w = (uint32_t)col >> 5, bit = 1u << (col & 31);
+            const bool z0 = (nz0[w] & bit) != 0, z1 = (nz1[w] & bit) != 0, n0 = (sg0[w] & bit) != 0, n1 = (sg1[w] & bit) != 0;
+            if (z0 && z1 && n0 != n1) {
+                do_jadd = true;
+                neg_d = n0;                                            // (-1, +1) = -(P - phi P)
+            } else if (z0 || z1) {
+                do_madd = true;
+                const bool both = z0 && z1;                            // same signs: +-(P + phi P) = (beta^2 x, -+y)
+                const bool neg = z0 ? n0 : n1;
+                fp_select(q.x, P.x, bx, !z0);
+                fp_select(q.x, q.x, bbx, both);
+                fp_select(q.y, P.y, ny, neg != both);
+            }
         } else {
-            do_add = job.add_off != 0xFFFFFFFFu;
-            if (do_add) g1a_load(q, pts + 24 * ((size_t)job.add_off + e));
+            do_madd = job.add_off != 0xFFFFFFFFu;
+            if (do_madd) g1a_load(q, pts + 24 * ((size_t)job.add_off + e));
         }
-        if (do_add) g1j_add_mixed(acc, acc, q);
+        if (do_madd) g1j_add_mixed(acc, acc, q);
+        if (do_jadd) {
+            g1j t = D;
+            if (neg_d) fp_neg(t.Y, t.Y);
+            g1j_add(acc, acc, t);
+        }
     }
     g1j_store(out_jac + 36 * (size_t)i, acc);
 }
