@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ell", type=int, default=252)
-    ap.add_argument("--batch", type=int, default=1024, help="proofs per step per GPU")
+    ap.add_argument("--batch", type=int, default=4096, help="proofs per step per GPU")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batch pipelines per GPU (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
