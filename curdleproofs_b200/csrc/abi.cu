@@ -408,7 +408,7 @@ constexpr size_t BIG_MSM_MIN_N = size_t(1) << 13;  // CDP_BIG_MIN_LOG2 overrides
 static int big_c_for(size_t n) {
     static int forced = -1;
     if (forced < 0) { const char *e = getenv("CDP_BIG_C"); forced = e ? atoi(e) : 0; }
-    if (forced >= 12 && forced <= 16) return forced;
+    if (forced >= 12 && forced <= 18) return forced;
     return n < (size_t(1) << 15) ? 12 : n < (size_t(1) << 17) ? 13 : n < (size_t(1) << 19) ? 14 : n < (size_t(1) << 20) ? 15 : 16;
 }
 static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {

@@ -25,6 +25,15 @@ for which, key in [(1, "fpmul"), (2, "fpsqr")]:
         ops = blocks * threads * iters
         out[key].append({"threads": threads, "blocks_per_sm": bps, "warps_per_sm": threads * bps // 32, "ms": ms,
                          "fp_ops_per_s": ops / (ms * 1e-3), "ns_per_op_per_thread": ms * 1e6 / iters})
+# FP64 pipe: DFMA alone, DFMA + IMAD.WIDE in one loop, DFMA + 64-bit integer adds in one loop (128 of each per iteration)
+out["dfma"] = []
+for which, key in [(3, "dfma"), (4, "dfma+imad_wide"), (5, "dfma+iadd64")]:
+    for threads, bps in [(256, 1), (256, 2), (256, 4)]:
+        blocks = SM * bps
+        iters = 2000
+        ms = min(eng.bench_kernel(which, blocks, threads, iters) for _ in range(3))
+        ops = blocks * threads * iters * 128
+        out["dfma"].append({"kernel": key, "threads": threads, "blocks_per_sm": bps, "ms": ms, "dfma_per_s": ops / (ms * 1e-3)})
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/microbench.json", "w"), indent=1)
 for k, v in out.items():
