@@ -263,6 +263,58 @@ __device__ __forceinline__ void fp_mul_eo(fp &r, const fp &a, const fp &b) {
     r = out;
 }
 
+// ---- Montgomery squaring, row-wise (generated: tools/gen_fp_sqr.py, which also checks the exact instruction sequence on a register /
+// carry-flag model).  The 24-word square is built from the 66 off-diagonal products in even / odd arrays (plain IMAD.WIDE carry
+// chains), doubled with funnel shifts, the 12 diagonal squares added in one chain; then twelve even / odd reduction rows on the low
+// half and the high half added at the end: 222 wide multiply-adds and ~130 other instructions.  The column-wise squaring below
+// (fp_sqr_inl) pays one IADD3.X per product for its third accumulator word -- 234 + ~380 instructions, a quarter of all instructions
+// of a mixed addition (profiles/r01_ncu_fixed_msm_v2.txt).
+// one reduction row: aligned array X (X[0] == 0 after the previous row), offset array Y; m = new lowest word * (-p^-1)
+#define CDP_SQR_RED_ROW(X, Y)                                                                                                \
+    {                                                                                                                        \
+        const uint32_t mr = (Y[0] + X[1]) * FP_INV32;                                                                        \
+        CDP_MAD6_RSHIFT(X, Y[0], CDP_P(1), CDP_P(3), CDP_P(5), CDP_P(7), CDP_P(9), CDP_P(11), mr);                           \
+        CDP_MAD6(Y, CDP_P(0), CDP_P(2), CDP_P(4), CDP_P(6), CDP_P(8), CDP_P(10), mr, X[11]);                                 \
+    }
+__device__ __forceinline__ void fp_sqr_rw(fp &r, const fp &a) {
+#include "fp_sqr_rows.inc"
+    fp out;
+    asm("add.cc.u32 %0, %12, %24;\n\t"
+        "addc.cc.u32 %1, %13, %25;\n\t"
+        "addc.cc.u32 %2, %14, %26;\n\t"
+        "addc.cc.u32 %3, %15, %27;\n\t"
+        "addc.cc.u32 %4, %16, %28;\n\t"
+        "addc.cc.u32 %5, %17, %29;\n\t"
+        "addc.cc.u32 %6, %18, %30;\n\t"
+        "addc.cc.u32 %7, %19, %31;\n\t"
+        "addc.cc.u32 %8, %20, %32;\n\t"
+        "addc.cc.u32 %9, %21, %33;\n\t"
+        "addc.cc.u32 %10, %22, %34;\n\t"
+        "addc.u32 %11, %23, 0;"
+        : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(out.v[3]), "=r"(out.v[4]), "=r"(out.v[5]), "=r"(out.v[6]), "=r"(out.v[7]),
+          "=r"(out.v[8]), "=r"(out.v[9]), "=r"(out.v[10]), "=r"(out.v[11])
+        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]),
+          "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]), "r"(Y[8]), "r"(Y[9]), "r"(Y[10]), "r"(Y[11]));
+    asm("add.cc.u32 %0, %0, %12;\n\t"
+        "addc.cc.u32 %1, %1, %13;\n\t"
+        "addc.cc.u32 %2, %2, %14;\n\t"
+        "addc.cc.u32 %3, %3, %15;\n\t"
+        "addc.cc.u32 %4, %4, %16;\n\t"
+        "addc.cc.u32 %5, %5, %17;\n\t"
+        "addc.cc.u32 %6, %6, %18;\n\t"
+        "addc.cc.u32 %7, %7, %19;\n\t"
+        "addc.cc.u32 %8, %8, %20;\n\t"
+        "addc.cc.u32 %9, %9, %21;\n\t"
+        "addc.cc.u32 %10, %10, %22;\n\t"
+        "addc.u32 %11, %11, %23;"
+        : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2]), "+r"(out.v[3]), "+r"(out.v[4]), "+r"(out.v[5]), "+r"(out.v[6]), "+r"(out.v[7]),
+          "+r"(out.v[8]), "+r"(out.v[9]), "+r"(out.v[10]), "+r"(out.v[11])
+        : "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(E[16]), "r"(E[17]), "r"(E[18]), "r"(E[19]), "r"(E[20]), "r"(E[21]), "r"(E[22]),
+          "r"(E[23]));
+    fp_final_sub(out);
+    r = out;
+}
+
 __device__ __forceinline__ void fp_mul_inl(fp &r, const fp &a, const fp &b) {
     uint32_t m[12];
     fp out;
@@ -339,10 +391,12 @@ static __device__ __noinline__ fp fp_mul_fn(const fp a, const fp b) {
 }
 static __device__ __noinline__ fp fp_sqr_fn(const fp a) {
     fp r;
-#ifdef CDP_FP_SQR_VIA_MUL
+#if defined(CDP_FP_SQR_VIA_MUL)
     fp_mul_eo(r, a, a);
-#else
+#elif defined(CDP_FP_SQR_COLUMNWISE)
     fp_sqr_inl(r, a);
+#else
+    fp_sqr_rw(r, a);
 #endif
     return r;
 }
