@@ -157,8 +157,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": f"shuffle_proofs_per_sec_ell{ell}", "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": value / README_PROOFS_PER_S if ell == 252 else None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"ell={ell} CurdleproofsProof::new on host cores (C port of the reference path; arkworks not buildable here)",
-                       "ell": ell, "proofs_per_step": count},
+            "config": {"workload": f"ell={ell} CurdleproofsProof::new, {args.batch} independent proofs per step per GPU, bit-exact vs reference CPU path",
+                       "ell": ell, "batch_per_gpu": args.batch, "proofs_per_step": count,
+                       "reference_arm": "the same workload on the host cores, bounded sample per step (C port of the reference path under oracle/, "
+                                        "pinned to the reference's golden proofs; arkworks itself is not buildable here: no Rust toolchain)"},
             "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port",
                              "sample": f"{count} proofs per step, one per host thread, {args.steps} steps"},
             "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
