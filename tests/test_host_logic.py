@@ -34,3 +34,31 @@ def test_device_transcript_code_matches_host_transcript_on_cpu():
         out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "MISMATCH" not in out.stdout
+
+
+def test_generated_squaring_schedule_is_model_checked_and_current():
+    """curdleproofs_b200/csrc/fp_sqr_rows.inc is generated: tools/gen_fp_sqr.py runs the exact instruction sequence of the row-wise
+    Montgomery squaring on a 32-bit register / carry-flag model against big integers (any dropped carry asserts) before it writes the
+    file.  Re-run the generator and require the committed file to be what it produces."""
+    path = os.path.join(ROOT, "curdleproofs_b200", "csrc", "fp_sqr_rows.inc")
+    before = open(path).read()
+    out = subprocess.run(["python", os.path.join(ROOT, "tools", "gen_fp_sqr.py")], check=True, capture_output=True, text=True).stdout
+    assert "model ok" in out and "222 wide multiply-adds" in out
+    assert open(path).read() == before
+
+
+def test_crs_text_format_errors_need_no_device():
+    """`from_hex_g1affine` (/root/reference/src/crs.rs:128-139): prefix, hex digits and length are checked before any point decoding;
+    `from_points` refuses too few points (src/crs.rs:40-42)."""
+    import pytest
+    from curdleproofs_b200.crs import CrsError, CurdleproofsCrs
+    for bad in ("97f1" * 24, "0x" + "zz" * 48, "0x" + "00" * 47, "0x" + "00" * 49, 7, None):
+        with pytest.raises(CrsError):
+            CurdleproofsCrs._parse_hex_point(bad)
+    assert CurdleproofsCrs._parse_hex_point("0x" + "c0" + "00" * 47) == bytes([0xC0]) + bytes(47)
+    with pytest.raises(CrsError):
+        CurdleproofsCrs.from_points(None, 4, bytes(96 * 10))  # needs 4 + 4 + 3 points
+    with pytest.raises(CrsError):
+        CurdleproofsCrs.from_json(None, "[1, 2]")
+    with pytest.raises(CrsError):
+        CurdleproofsCrs.from_hex(None, {"vec_G": []})
