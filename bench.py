@@ -348,8 +348,8 @@ def main():
         roofline["isolated"] = {"kernel": "k_fixed_msm, IPA-round shape, whole batch in one launch, nothing else running", "ms": iso_ms,
                                 "pairs_per_s": pairs / (iso_ms * 1e-3), "achieved_GBps": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9,
                                 "hbm_frac": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9 / hbm_peak,
-                                "mixed_adds_per_s": madds, "imad_wide_per_mixed_add": 7 * 288 + 4 * 234,
-                                "int_pipe_frac": madds * (7 * 288 + 4 * 234) / imad_peak}
+                                "mixed_adds_per_s": madds, "imad_wide_per_mixed_add": 7 * 288 + 4 * 222,
+                                "int_pipe_frac": madds * (7 * 288 + 4 * 222) / imad_peak}
         for dd in (d_sc, d_sg, d_out):
             lib.cdp_dev_free(h, dd)
         tab.close()
