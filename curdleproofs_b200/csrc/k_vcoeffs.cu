@@ -1,0 +1,287 @@
+// Verifier scalar preparation on the device -- SURVEY.md section 8(f) rank 3.  For every proof of a batch the coefficient of EVERY
+// base of its accumulated check is computed here from the O(log n) Fiat-Shamir challenges, instead of on the host:
+//   * the verification scalars s_i = prod_{j : bit (m-1-j) of i set} gamma_j and their inverses
+//     (`get_verification_scalars_bitstring`, /root/reference/src/util.rs:40-64; used at src/inner_product_argument.rs:202-250 and
+//     src/same_multiscalar_argument.rs:242-259), the GrandProduct rescaling u_i = beta^-(i+1) (src/grand_product_argument.rs:92-102);
+//   * the `a * x_i` products of the eight `MsmAccumulator::accumulate_check` calls (src/msm_accumulator.rs:37-52) with the
+//     accumulator's HashMap replaced by the verifier's fixed slot table, plus the four SameScalar equalities
+//     (src/same_scalar_argument.rs:127-136) with their own random factors.
+// Input per proof: 27 + 4 m Montgomery scalars (random factors, challenges, the proof's seven scalars) and vec_a; output: the
+// 5 ell + 8 + (proof points) canonical 32-byte scalars the two MSM kernels read.  The host keeps the transcript (hashing) only.
+// One CTA per proof, one thread per vector index; Fr in 8 x 32-bit limbs with 64-bit products (a few thousand products per proof:
+// nothing here is throughput-critical).  Integer work only.
+#ifndef CDP_VCOEFFS_HOST_HARNESS  // tests/host/vcoeffs_check.cpp compiles this file with g++ to check it on the CPU
+#include "launch.h"
+#endif
+
+namespace cdp {
+
+namespace vcoef {
+
+struct fr_t {
+    uint32_t v[8];
+};
+// r, R mod r, -r^-1 mod 2^32 (the same constants as host/fr.hpp and constants.cuh, as literals so that the CPU harness sees them too)
+__device__ __forceinline__ uint32_t fr_mod(int i) {
+    const uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return t[i];
+}
+__device__ __forceinline__ uint32_t fr_r2(int i) {
+    const uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+    return t[i];
+}
+__device__ __forceinline__ uint32_t fr_r1(int i) {
+    const uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+    return t[i];
+}
+constexpr uint32_t FR_NINV = 0xffffffffu;
+
+__device__ __forceinline__ fr_t fr_zero() {
+    fr_t r;
+    for (int i = 0; i < 8; i++) r.v[i] = 0;
+    return r;
+}
+__device__ __forceinline__ fr_t fr_one() {
+    fr_t r;
+    for (int i = 0; i < 8; i++) r.v[i] = fr_r1(i);
+    return r;
+}
+__device__ __forceinline__ bool fr_geq_mod(const uint32_t *a) {
+    for (int i = 7; i >= 0; i--) {
+        if (a[i] > fr_mod(i)) return true;
+        if (a[i] < fr_mod(i)) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ void fr_sub_mod(uint32_t *a) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a[i] - fr_mod(i) - borrow;
+        a[i] = (uint32_t)d;
+        borrow = (d >> 32) & 1;
+    }
+}
+__device__ __forceinline__ fr_t fr_add(const fr_t &a, const fr_t &b) {
+    fr_t r;
+    uint64_t c = 0;
+    for (int i = 0; i < 8; i++) {
+        c += (uint64_t)a.v[i] + b.v[i];
+        r.v[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    if (c || fr_geq_mod(r.v)) fr_sub_mod(r.v);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_sub(const fr_t &a, const fr_t &b) {
+    fr_t r;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a.v[i] - b.v[i] - borrow;
+        r.v[i] = (uint32_t)d;
+        borrow = (d >> 32) & 1;
+    }
+    if (borrow) {
+        uint64_t c = 0;
+        for (int i = 0; i < 8; i++) {
+            c += (uint64_t)r.v[i] + fr_mod(i);
+            r.v[i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    return r;
+}
+__device__ __forceinline__ fr_t fr_neg(const fr_t &a) { return fr_sub(fr_zero(), a); }
+// Montgomery product (R = 2^256), coarsely integrated operand scanning
+__device__ __noinline__ fr_t fr_mul(const fr_t &a, const fr_t &b) {
+    uint32_t t[10];
+    for (int i = 0; i < 10; i++) t[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)a.v[j] * b.v[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[8] = (uint32_t)c;
+        t[9] = (uint32_t)(c >> 32);
+        const uint32_t m = t[0] * FR_NINV;
+        c = (uint64_t)m * fr_mod(0) + t[0];
+        c >>= 32;
+        for (int j = 1; j < 8; j++) {
+            c += (uint64_t)m * fr_mod(j) + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[7] = (uint32_t)c;
+        t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    fr_t r;
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+    if (t[8] || fr_geq_mod(r.v)) fr_sub_mod(r.v);
+    return r;
+}
+__device__ __forceinline__ fr_t fr_load(const uint32_t *p) {
+    fr_t r;
+    for (int i = 0; i < 8; i++) r.v[i] = p[i];
+    return r;
+}
+// canonical little-endian value -> Montgomery form
+__device__ __forceinline__ fr_t fr_to_mont(const fr_t &a) {
+    fr_t r2;
+    for (int i = 0; i < 8; i++) r2.v[i] = fr_r2(i);
+    return fr_mul(a, r2);
+}
+// Montgomery form -> canonical value, stored as 8 words
+__device__ __forceinline__ void fr_store_canonical(uint32_t *dst, const fr_t &a) {
+    fr_t one = fr_zero();
+    one.v[0] = 1;
+    const fr_t c = fr_mul(a, one);
+    for (int i = 0; i < 8; i++) dst[i] = c.v[i];
+}
+// x^e for a small exponent
+__device__ __forceinline__ fr_t fr_pow_u32(const fr_t &x, uint32_t e) {
+    fr_t acc = fr_one();
+    bool started = false;
+    for (int i = 31; i >= 0; i--) {
+        if (started) acc = fr_mul(acc, acc);
+        if ((e >> i) & 1) {
+            acc = started ? fr_mul(acc, x) : x;
+            started = true;
+        }
+    }
+    return acc;
+}
+// s_i = prod_{j : bit (m-1-j) of i set} g_j
+__device__ __forceinline__ fr_t s_value(const uint32_t *g, uint32_t m, uint32_t i) {
+    fr_t acc = fr_one();
+    bool started = false;
+    for (uint32_t j = 0; j < m; j++)
+        if ((i >> (m - 1 - j)) & 1) {
+            const fr_t gj = fr_load(g + 8 * j);
+            acc = started ? fr_mul(acc, gj) : gj;
+            started = true;
+        }
+    return acc;
+}
+
+}  // namespace vcoef
+
+// positions inside a proof's challenge block (Montgomery scalars, 8 words each); the four challenge vectors follow at CH_VEC
+enum {
+    CH_RHO = 0, CH_ALPHA_SP = 12, CH_BETA_SP, CH_ALPHA_G, CH_BETA_INV, CH_ALPHA_I, CH_BETA_I, CH_Z, CH_C, CH_D, CH_X, CH_ALPHA_SM,
+    CH_ALPHA_SS, CH_ZK, CH_ZT, CH_ZU, CH_VEC = 27
+};
+
+// One thread of the CTA that serves proof `pr`.  chal: [B][vch][8], vec_a: [B][ell][8] canonical, out: [B][scal_pp][8] canonical.
+__device__ __forceinline__ void vcoef_thread(uint32_t pr, uint32_t tid, uint32_t nthreads, const uint32_t *chal, const uint32_t *vec_a,
+                                             const vcoef_params_t P, uint32_t *out) {
+    using namespace vcoef;
+    const uint32_t ell = P.ell, n = P.n, m = P.m;
+    const uint32_t *ch = chal + 8 * (size_t)pr * P.vch;
+    uint32_t *sc = out + 8 * (size_t)pr * P.scal_pp;
+    auto C = [&](uint32_t k) { return fr_load(ch + 8 * k); };
+    const uint32_t *gam = ch + 8 * CH_VEC, *gam_inv = gam + 8 * m, *gam2 = gam_inv + 8 * m, *gam2_inv = gam2 + 8 * m;
+    const uint32_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
+    // proof point indices in serialisation order (host/verifier.cpp ProofLayout)
+    const uint32_t L_A = 0, L_T1 = 1, L_T2 = 2, L_U1 = 3, L_U2 = 4, L_R = 5, L_S = 6, L_B = 7, L_C = 8, L_Bc = 9, L_Bd = 10;
+    const uint32_t L_LC = 11, L_RC = L_LC + m, L_LD = L_RC + m, L_RD = L_LD + m, L_A1 = L_RD + m, L_A2 = L_A1 + 1, L_B1 = L_A2 + 1,
+                   L_B2 = L_B1 + 1, L_Ba = L_B2 + 1, L_Bt = L_Ba + 1, L_Bu = L_Bt + 1, L_LA = L_Bu + 1, L_LT = L_LA + m, L_LU = L_LT + m,
+                   L_RA = L_LU + m, L_RT = L_RA + m, L_RU = L_RT + m;
+    const bool joint = P.exact_eq == 0;  // the SameScalar equalities join the accumulated check with rho[8..11]
+    auto put = [&](uint32_t slot, const fr_t &x) { fr_store_canonical(sc + 8 * slot, x); };
+    const fr_t xf = C(CH_X);
+    const fr_t x4 = fr_mul(C(CH_RHO + 3), xf), x5 = fr_mul(C(CH_RHO + 4), xf), x6 = fr_mul(C(CH_RHO + 5), xf);
+    const fr_t t2 = fr_mul(C(CH_RHO + 2), C(CH_ALPHA_I));
+
+    // ---- per-index part: CRS bases G | Hvec (slot i), R_i, S_i, T_i, U_i
+    {
+        const fr_t t0 = fr_mul(C(CH_RHO + 0), C(CH_BETA_SP)), t1 = fr_mul(C(CH_RHO + 1), C(CH_C)), t3 = fr_mul(C(CH_RHO + 2), C(CH_D));
+        const fr_t binv = C(CH_BETA_INV);
+        const fr_t g_sum = fr_neg(fr_mul(t2, binv)), h_sum = fr_mul(t2, C(CH_ALPHA_G));  // coefficients of sum(G), sum(Hvec): onto every G_i / Hvec_i
+        const fr_t r6 = C(CH_RHO + 6), r7 = C(CH_RHO + 7);
+        for (uint32_t i = tid; i < n; i += nthreads) {
+            const fr_t s_ipa = s_value(gam, m, i), sinv_ipa = s_value(gam_inv, m, i), s_sm = s_value(gam2, m, i);
+            const fr_t u = fr_pow_u32(binv, (i < ell ? i : ell) + 1);
+            fr_t cf = i < ell ? fr_sub(g_sum, t0) : h_sum;
+            cf = fr_sub(cf, fr_mul(t1, s_ipa));
+            cf = fr_sub(cf, fr_mul(fr_mul(t3, sinv_ipa), u));
+            if (i < ell + 2) cf = fr_sub(cf, fr_mul(x4, s_sm));
+            put(i, cf);
+            if (i < ell) {
+                const fr_t a = fr_to_mont(fr_load(vec_a + 8 * ((size_t)pr * ell + i)));
+                put(P.o_R + i, fr_neg(fr_mul(r6, a)));
+                put(P.o_S + i, fr_neg(fr_mul(r7, a)));
+                put(P.o_T + i, fr_neg(fr_mul(x5, s_sm)));
+                put(P.o_U + i, fr_neg(fr_mul(x6, s_sm)));
+            }
+        }
+    }
+    // ---- the 10 m round points: thread k takes L/R number k of every argument
+    for (uint32_t k = tid; k < m; k += nthreads) {
+        const fr_t g = fr_load(gam + 8 * k), gi = fr_load(gam_inv + 8 * k), g2 = fr_load(gam2 + 8 * k), g2i = fr_load(gam2_inv + 8 * k);
+        const fr_t r1 = C(CH_RHO + 1), r2 = C(CH_RHO + 2), r3 = C(CH_RHO + 3), r4 = C(CH_RHO + 4), r5 = C(CH_RHO + 5);
+        put(P.o_P + L_LC + k, fr_mul(r1, g)); put(P.o_P + L_RC + k, fr_mul(r1, gi));
+        put(P.o_P + L_LD + k, fr_mul(r2, g)); put(P.o_P + L_RD + k, fr_mul(r2, gi));
+        put(P.o_P + L_LA + k, fr_mul(r3, g2)); put(P.o_P + L_RA + k, fr_mul(r3, g2i));
+        put(P.o_P + L_LT + k, fr_mul(r4, g2)); put(P.o_P + L_RT + k, fr_mul(r4, g2i));
+        put(P.o_P + L_LU + k, fr_mul(r5, g2)); put(P.o_P + L_RU + k, fr_mul(r5, g2i));
+    }
+    // ---- the remaining single slots (one thread)
+    if (tid == (m < nthreads ? m : 0)) {
+        const fr_t r0 = C(CH_RHO + 0), r1 = C(CH_RHO + 1), r2 = C(CH_RHO + 2), r3 = C(CH_RHO + 3), r4 = C(CH_RHO + 4), r5 = C(CH_RHO + 5),
+                   r6 = C(CH_RHO + 6), r7 = C(CH_RHO + 7), r8 = C(CH_RHO + 8), r9 = C(CH_RHO + 9), r10 = C(CH_RHO + 10), r11 = C(CH_RHO + 11);
+        const fr_t alpha_i = C(CH_ALPHA_I), beta_i = C(CH_BETA_I), alpha_sm = C(CH_ALPHA_SM), alpha_ss = C(CH_ALPHA_SS);
+        const fr_t zk = C(CH_ZK), zt = C(CH_ZT), zu = C(CH_ZU);
+        const fr_t s2 = s_value(gam2, m, ell + 2), s3 = s_value(gam2, m, ell + 3);
+        const fr_t a4 = fr_mul(r3, alpha_sm);
+        // H: IPA first check, the blinder slots of T (ell + 2) and U (ell + 3), SameScalar
+        fr_t h = fr_sub(fr_mul(fr_mul(fr_mul(alpha_i, alpha_i), C(CH_Z)), beta_i), fr_mul(fr_mul(C(CH_C), C(CH_D)), beta_i));
+        h = fr_mul(r1, h);
+        h = fr_sub(h, fr_mul(x5, s2));
+        h = fr_sub(h, fr_mul(x6, s3));
+        fr_t gt = fr_neg(fr_mul(x4, s2)), gu = fr_neg(fr_mul(x4, s3));
+        fr_t cT1 = a4, cU1 = a4, cT2 = fr_mul(r4, alpha_sm), cU2 = fr_mul(r5, alpha_sm), cR = r6, cS = r7;
+        fr_t cA1 = fr_zero(), cA2 = fr_zero(), cB1 = fr_zero(), cB2 = fr_zero();
+        if (joint) {
+            h = fr_sub(h, fr_mul(r9, zt));
+            h = fr_sub(h, fr_mul(r11, zu));
+            gt = fr_sub(gt, fr_mul(r8, zt));
+            gu = fr_sub(gu, fr_mul(r10, zu));
+            cA1 = r8; cT1 = fr_add(cT1, fr_mul(r8, alpha_ss));
+            cA2 = r9; cT2 = fr_add(cT2, fr_mul(r9, alpha_ss)); cR = fr_sub(cR, fr_mul(r9, zk));
+            cB1 = r10; cU1 = fr_add(cU1, fr_mul(r10, alpha_ss));
+            cB2 = r11; cU2 = fr_add(cU2, fr_mul(r11, alpha_ss)); cS = fr_sub(cS, fr_mul(r11, zk));
+        }
+        put(cH, h); put(cGt, gt); put(cGu, gu);
+        put(cGsum, fr_zero()); put(cHsum, fr_zero());
+        put(P.o_M, fr_neg(fr_mul(r0, C(CH_ALPHA_SP))));
+        put(P.o_P + L_B, fr_add(r0, t2));
+        put(P.o_P + L_A, fr_sub(a4, r0));
+        put(P.o_P + L_Bc, r1); put(P.o_P + L_C, fr_mul(r1, alpha_i)); put(P.o_P + L_Bd, r2);
+        put(P.o_P + L_Ba, r3); put(P.o_P + L_Bt, r4); put(P.o_P + L_Bu, r5);
+        put(P.o_P + L_T1, cT1); put(P.o_P + L_U1, cU1); put(P.o_P + L_T2, cT2); put(P.o_P + L_U2, cU2);
+        put(P.o_P + L_R, cR); put(P.o_P + L_S, cS);
+        put(P.o_P + L_A1, cA1); put(P.o_P + L_A2, cA2); put(P.o_P + L_B1, cB1); put(P.o_P + L_B2, cB2);
+        // scalars of the exact form of the SameScalar equalities (CDP_VERIFY_EXACT_EQ=1)
+        const fr_t one = fr_one(), nzt = fr_neg(zt), nzk = fr_neg(zk), nzu = fr_neg(zu);
+        const fr_t e[14] = {one, alpha_ss, nzt, one, alpha_ss, nzk, nzt, one, alpha_ss, nzu, one, alpha_ss, nzk, nzu};
+        for (uint32_t k = 0; k < 14; k++) put(P.big_n + k, e[k]);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_verify_coeffs(const uint32_t *__restrict__ chal, const uint32_t *__restrict__ vec_a,
+                                                       const vcoef_params_t P, uint32_t *__restrict__ out) {
+    vcoef_thread(blockIdx.x, threadIdx.x, blockDim.x, chal, vec_a, P, out);
+}
+
+#ifndef CDP_VCOEFFS_HOST_HARNESS
+cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch,
+                                 uint32_t *out) {
+    k_verify_coeffs<<<batch, 256, 0, st>>>(chal, vec_a, P, out);
+    return cudaGetLastError();
+}
+#endif
+
+}  // namespace cdp

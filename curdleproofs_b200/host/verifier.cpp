@@ -88,7 +88,7 @@ enum XSlot { X_B = 0, X_GSUM, X_HSUM, X_A, X_T1, X_U1,                 // D = B 
 
 struct VState {
     std::unique_ptr<Transcript> tr;
-    std::vector<Fr> vec_a, s_ipa, sinv_ipa, u, s_sm, gam, gam_inv, gam2, gam2_inv;
+    std::vector<Fr> vec_a, gam, gam_inv, gam2, gam2_inv;
     Fr r_p, c_final, d_final, z_k, z_t, z_u, x_final;
     Fr alpha_sp, beta_sp, alpha_g, beta_g, beta_g_inv, gprod_result, z, rho[12];
     uint8_t M_comp[48];
@@ -107,6 +107,8 @@ struct VLane {
     size_t crs_n = 0, VW = 0, o_R = 0, o_S = 0, o_T = 0, o_U = 0, o_M = 0, o_P = 0, o_X = 0, big_n = 0, reg = 0, chunks = 1;
     uint8_t *d_pts = nullptr, *d_in = nullptr, *d_Mjac = nullptr, *d_pcomp = nullptr, *d_status = nullptr;
     uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
+    uint8_t *d_chal = nullptr, *h_chal = nullptr;  // per-proof challenge blocks for the device-side scalar preparation (cdp_verify_coeffs_dev)
+    size_t vch = 0;
     uint32_t *d_gsrc = nullptr, *d_gdst = nullptr, *d_isrc = nullptr, *d_idst = nullptr, *d_pdst = nullptr, *d_xsrc = nullptr, *d_xdst = nullptr;
     size_t g_pp = 0, i_pp = 0, x_pp = 0;
     cdp_msm_seg *d_segBig = nullptr, *d_segE = nullptr;
@@ -131,10 +133,10 @@ void vlane_destroy(VLane *p) {
     cdp_ctx *c = p->ctx;
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_pcomp, (void *)p->d_status, (void *)p->d_gsrc,
                     (void *)p->d_gdst, (void *)p->d_isrc, (void *)p->d_idst, (void *)p->d_pdst, (void *)p->d_xsrc, (void *)p->d_xdst,
-                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_scal, (void *)p->d_jac,
+                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_chal}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -174,8 +176,10 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->d_veca = (uint8_t *)dalloc(max_batch * ell * 32); p->h_veca = (uint8_t *)halloc(max_batch * ell * 32);
     p->d_tstate = (uint8_t *)dalloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES); p->h_tstate = (uint8_t *)halloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES);
     size_t scal_pp = p->big_n + 14;
+    p->vch = 27 + 4 * m;
+    p->d_chal = (uint8_t *)dalloc(max_batch * p->vch * 32); p->h_chal = (uint8_t *)halloc(max_batch * p->vch * 32);
     p->d_scal = (uint8_t *)dalloc(max_batch * scal_pp * 32);
-    p->h_scal = (uint8_t *)halloc(max_batch * scal_pp * 32);
+    p->h_scal = (uint8_t *)halloc(max_batch * 6 * 32);  // stage A only: the coefficients of the accumulated check are computed on the device
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
     p->d_jac = (uint8_t *)dalloc(max_batch * (p->chunks + FSPLIT + 5) * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * out_pp * 48);
@@ -254,17 +258,6 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     return CDP_OK;
 }
 
-// s_i = prod_{j : bit (m-1-j) of i set} gamma_j  (get_verification_scalars_bitstring, src/util.rs:40-64), built by doubling: n products
-void s_vector(std::vector<Fr> &s, const std::vector<Fr> &gam, size_t m) {
-    size_t n = (size_t)1 << m;
-    s.resize(n);
-    s[0] = Fr::one();
-    for (size_t j = m; j-- > 0;) {            // challenge j controls bit m-1-j; low bits first
-        size_t bit = (size_t)1 << (m - 1 - j);
-        for (size_t i = 0; i < bit; i++) s[bit + i] = s[i] * gam[j];
-    }
-}
-
 int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
     if (B == 0) return CDP_OK;
     const double t_start = now_ms();
@@ -337,11 +330,12 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         // same_perm (same_permutation_argument.rs:134-145)
         s.tr->append_point("same_perm_step1", pc + 48 * L.A);
         s.tr->append_point("same_perm_step1", s.M_comp);
-        s.tr->append_fr_vec("same_perm_step1", s.vec_a.data(), ell);
+        s.tr->append_fr_vec_canonical("same_perm_step1", p->h_veca + pr * ell * 32, ell);  // the device left vec_a as canonical bytes
         s.alpha_sp = s.tr->challenge("same_perm_alpha");
         s.beta_sp = s.tr->challenge("same_perm_beta");
         s.gprod_result = Fr::one();
-        for (size_t i = 0; i < ell; i++) s.gprod_result *= s.vec_a[i] + Fr::from_u64(i) * s.alpha_sp + s.beta_sp;
+        Fr i_alpha = s.beta_sp;  // i * alpha + beta, advanced by addition
+        for (size_t i = 0; i < ell; i++) { s.gprod_result *= s.vec_a[i] + i_alpha; i_alpha += s.alpha_sp; }
         // gprod (grand_product_argument.rs:202-223)
         s.tr->append_point("gprod_step1", pc + 48 * L.B);
         s.tr->append_fr("gprod_step1", s.gprod_result);
@@ -371,10 +365,6 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         VState &s = p->vs[pr];
         const uint8_t *pc = p->h_pcomp + pr * NP * 48, *D_comp = p->h_comp + (2 * pr) * 48, *AP_comp = p->h_comp + (2 * pr + 1) * 48;
         const Fr beta = s.beta_g, beta_inv = s.beta_g_inv;
-        s.u.resize(n);
-        Fr pw = beta_inv;
-        for (size_t i = 0; i < ell; i++) { s.u[i] = pw; pw *= beta_inv; }
-        for (size_t i = 0; i < 4; i++) s.u[ell + i] = pw;
         Fr beta_l = beta.pow_u64(ell), beta_l1 = beta_l * beta;
         s.z = s.r_p * beta_l1 + s.gprod_result * beta_l - Fr::one();
         // IPA (inner_product_argument.rs:282-323)
@@ -392,8 +382,6 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         }
         s.gam_inv = s.gam;
         batch_inverse(s.gam_inv.data(), m);  // one field inversion for the m challenges (the reference: batch_inversion, :234)
-        s_vector(s.s_ipa, s.gam, m);
-        s_vector(s.sinv_ipa, s.gam_inv, m);  // 1/s_i: the same products over the inverted challenges
         // same_scalar (same_scalar_argument.rs:110-136)
         const size_t ss[10] = {L.R, L.S, L.T1, L.T2, L.U1, L.U2, L.A1, L.A2, L.B1, L.B2};
         for (int q = 0; q < 10; q++) s.tr->append_point("sameexp_points", pc + 48 * ss[q]);
@@ -417,80 +405,24 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         }
         s.gam2_inv = s.gam2;
         batch_inverse(s.gam2_inv.data(), m);
-        s_vector(s.s_sm, s.gam2, m);
-        // ---- coefficients.  check j contributes rho_j * (lhs_j - <x_j, V_j>); the proof is accepted iff the total is the identity
-        const Fr *rho = s.rho;
-        std::vector<Fr> cf(p->big_n, Fr::zero());
-        const size_t cG = 0, cHv = ell, cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
-        const size_t oR = p->o_R, oS = p->o_S, oT = p->o_T, oU = p->o_U, oM = p->o_M, oP = p->o_P;
-        const Fr cf_c = s.c_final, cf_d = s.d_final, xf = s.x_final;
-        // (1) same_perm: B - A - alpha M == beta * sum(G)                         same_permutation_argument.rs:149-154
-        cf[oP + L.B] += rho[0]; cf[oP + L.A] -= rho[0]; cf[oM] -= rho[0] * s.alpha_sp;
-        Fr t0 = rho[0] * s.beta_sp;
-        for (size_t i = 0; i < ell; i++) cf[cG + i] -= t0;
-        // (2) IPA first check: gamma x L_C + (B_c + alpha C + alpha^2 z beta H) + gamma^-1 x R_C == c s x G + c d beta H      :289-309
-        cf[oP + L.Bc] += rho[1]; cf[oP + L.C] += rho[1] * alpha_i;
-        cf[cH] += rho[1] * (alpha_i * alpha_i * s.z * beta_i - cf_c * cf_d * beta_i);
-        for (size_t k = 0; k < m; k++) { cf[oP + L.LC + k] += rho[1] * s.gam[k]; cf[oP + L.RC + k] += rho[1] * s.gam_inv[k]; }
-        Fr t1 = rho[1] * cf_c;
-        for (size_t i = 0; i < n; i++) cf[cG + i] -= t1 * s.s_ipa[i];   // G | Hvec are contiguous: indices 0..n-1
-        // (3) IPA second check: gamma x L_D + (B_d + alpha D) + gamma^-1 x R_D == d (u o 1/s) x G,   D = B - beta^-1 G_sum + alpha_g H_sum   :311-323
-        cf[oP + L.Bd] += rho[2];
-        Fr t2 = rho[2] * alpha_i;
-        cf[oP + L.B] += t2; cf[cGsum] -= t2 * beta_inv; cf[cHsum] += t2 * s.alpha_g;
-        for (size_t k = 0; k < m; k++) { cf[oP + L.LD + k] += rho[2] * s.gam[k]; cf[oP + L.RD + k] += rho[2] * s.gam_inv[k]; }
-        Fr t3 = rho[2] * cf_d;
-        for (size_t i = 0; i < n; i++) cf[cG + i] -= t3 * s.sinv_ipa[i] * s.u[i];
-        // (4)-(6) same_msm: gamma x L_X + (B_x + alpha X) + gamma^-1 x R_X == x s x V_X            same_multiscalar_argument.rs:242-259
-        //   X = A' = A + T_1 + U_1 over G|H0|H1|G_t|G_u ;  X = cm_T.T_2 over T|inf inf H inf ;  X = cm_U.T_2 over U|inf inf inf H
-        const size_t Bx[3] = {L.Ba, L.Bt, L.Bu}, Lx[3] = {L.LA, L.LT, L.LU}, Rx[3] = {L.RA, L.RT, L.RU};
-        for (int c = 0; c < 3; c++) {
-            const Fr &r = rho[3 + c];
-            cf[oP + Bx[c]] += r;
-            for (size_t k = 0; k < m; k++) { cf[oP + Lx[c] + k] += r * s.gam2[k]; cf[oP + Rx[c] + k] += r * s.gam2_inv[k]; }
-        }
-        Fr a4 = rho[3] * alpha_sm;
-        cf[oP + L.A] += a4; cf[oP + L.T1] += a4; cf[oP + L.U1] += a4;
-        cf[oP + L.T2] += rho[4] * alpha_sm;
-        cf[oP + L.U2] += rho[5] * alpha_sm;
-        Fr x4 = rho[3] * xf, x5 = rho[4] * xf, x6 = rho[5] * xf;
-        for (size_t i = 0; i < ell + 2; i++) cf[cG + i] -= x4 * s.s_sm[i];          // G | H0 | H1
-        cf[cGt] -= x4 * s.s_sm[ell + 2]; cf[cGu] -= x4 * s.s_sm[ell + 3];
-        for (size_t i = 0; i < ell; i++) { cf[oT + i] -= x5 * s.s_sm[i]; cf[oU + i] -= x6 * s.s_sm[i]; }
-        cf[cH] -= x5 * s.s_sm[ell + 2];                                              // T slot ell+2 holds H
-        cf[cH] -= x6 * s.s_sm[ell + 3];                                              // U slot ell+3 holds H
-        (void)cHv;
-        // (7), (8): R == a x vec_R, S == a x vec_S                                   curdleproofs.rs:293-294
-        cf[oP + L.R] += rho[6]; cf[oP + L.S] += rho[7];
-        for (size_t i = 0; i < ell; i++) { cf[oR + i] -= rho[6] * s.vec_a[i]; cf[oS + i] -= rho[7] * s.vec_a[i]; }
-        // SameScalar (same_scalar_argument.rs:127-136): four point equalities, each "sum == identity":
-        //   cm_A.T_1 + alpha cm_T.T_1 - z_t G_t ;  cm_A.T_2 + alpha cm_T.T_2 - z_k R - z_t H ;  the same for B / U / S / z_u.
-        // All their bases already sit in the accumulated check, so by default they join it with their own random factors (the
-        // MsmAccumulator construction applied to four more checks: a false equality survives with probability 2^-254);
-        // CDP_VERIFY_EXACT_EQ=1 evaluates them as four separate exact MSMs instead.
-        if (!p->exact_eq) {
-            const Fr r8 = rho[8], r9 = rho[9], r10 = rho[10], r11 = rho[11];
-            cf[oP + L.A1] += r8; cf[oP + L.T1] += r8 * alpha_ss; cf[cGt] -= r8 * s.z_t;
-            cf[oP + L.A2] += r9; cf[oP + L.T2] += r9 * alpha_ss; cf[oP + L.R] -= r9 * s.z_k; cf[cH] -= r9 * s.z_t;
-            cf[oP + L.B1] += r10; cf[oP + L.U1] += r10 * alpha_ss; cf[cGu] -= r10 * s.z_u;
-            cf[oP + L.B2] += r11; cf[oP + L.U2] += r11 * alpha_ss; cf[oP + L.S] -= r11 * s.z_k; cf[cH] -= r11 * s.z_u;
-        }
-        // sum(G) and sum(Hvec) are not table bases: their coefficients go onto every G_i / Hvec_i
-        for (size_t i = 0; i < ell; i++) cf[cG + i] += cf[cGsum];
-        for (size_t i = ell; i < n; i++) cf[cG + i] += cf[cHsum];
-        cf[cGsum] = cf[cHsum] = Fr::zero();
-        uint8_t *sc = p->h_scal + pr * scal_pp * 32;
-        for (size_t i = 0; i < p->big_n; i++) put_fr(sc + 32 * i, cf[i]);
-        uint8_t *se = sc + 32 * p->big_n;  // scalars of the exact form of the SameScalar equalities
-        const Fr one = Fr::one();
-        const Fr e[14] = {one, alpha_ss, s.z_t.neg(), one, alpha_ss, s.z_k.neg(), s.z_t.neg(), one, alpha_ss, s.z_u.neg(), one, alpha_ss, s.z_k.neg(), s.z_u.neg()};
-        for (int i = 0; i < 14; i++) put_fr(se + 32 * i, e[i]);
+        // ---- the coefficient of every base of the accumulated check (check j contributes rho_j * (lhs_j - <x_j, V_j>); the proof is accepted
+        //      iff the total is the identity) is computed on the device from this block: cdp_verify_coeffs_dev / csrc/k_vcoeffs.cu
+        Fr *ch = reinterpret_cast<Fr *>(p->h_chal + pr * p->vch * 32);
+        for (int i = 0; i < 12; i++) ch[i] = s.rho[i];
+        ch[12] = s.alpha_sp; ch[13] = s.beta_sp; ch[14] = s.alpha_g; ch[15] = beta_inv; ch[16] = alpha_i; ch[17] = beta_i; ch[18] = s.z;
+        ch[19] = s.c_final; ch[20] = s.d_final; ch[21] = s.x_final; ch[22] = alpha_sm; ch[23] = alpha_ss; ch[24] = s.z_k; ch[25] = s.z_t; ch[26] = s.z_u;
+        for (size_t k = 0; k < m; k++) { ch[27 + k] = s.gam[k]; ch[27 + m + k] = s.gam_inv[k]; ch[27 + 2 * m + k] = s.gam2[k]; ch[27 + 3 * m + k] = s.gam2_inv[k]; }
     });
     // ---- final stage: per-proof part (one launch per 2048-point chunk) + CRS part (digit table) -> added per proof; the equalities
     const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + FSPLIT;
     t_host += now_ms() - t0;
     if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host part 3: %.2f ms (B=%zu)\n", now_ms() - t0, B);
-    VTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * scal_pp * 32));
+    VTRY(cdp_h2d(p->ctx, p->d_chal, p->h_chal, B * p->vch * 32));
+    {
+        cdp_vcoef_params vp = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)p->big_n, (uint32_t)scal_pp, (uint32_t)p->o_R, (uint32_t)p->o_S,
+                               (uint32_t)p->o_T, (uint32_t)p->o_U, (uint32_t)p->o_M, (uint32_t)p->o_P, p->exact_eq ? 1u : 0u, (uint32_t)p->vch};
+        VTRY(cdp_verify_coeffs_dev(p->ctx, p->d_chal, p->d_veca, &vp, B, p->d_scal));
+    }
     for (size_t c = 0; c < p->chunks; c++) {
         size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
         VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));

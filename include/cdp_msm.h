@@ -208,6 +208,25 @@ int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint32_t *
 int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs, const uint8_t *d_comp_M, size_t ell, size_t batch, uint8_t *d_vec_a,
                             uint8_t *d_state);
 
+/* Verifier scalar preparation on the device: from a proof's Fiat-Shamir challenges to the coefficient of every
+ * base of its accumulated check -- the verification scalars s_i / 1/s_i of `get_verification_scalars_bitstring`
+ * (/root/reference/src/util.rs:40-64, used at src/inner_product_argument.rs:202-250 and src/same_multiscalar_argument.rs:242-259),
+ * the GrandProduct rescaling beta^-(i+1) (src/grand_product_argument.rs:92-102) and the `a * x_i` products of the
+ * `MsmAccumulator::accumulate_check` calls (src/msm_accumulator.rs:37-52), with the accumulator's HashMap replaced by fixed slots.
+ * d_challenges: batch x vch scalars, 4 x u64 MONTGOMERY form (R = 2^256) as the host's Fr keeps them:
+ *   [0..11] the random factors of the 8 checks + 4 SameScalar equalities, [12] same_perm alpha, [13] same_perm beta, [14] gprod alpha,
+ *   [15] gprod beta^-1, [16] ipa alpha, [17] ipa beta, [18] z, [19] c_final, [20] d_final, [21] x_final, [22] same_msm alpha,
+ *   [23] same_scalar alpha, [24] z_k, [25] z_t, [26] z_u, then ipa gamma[m], ipa gamma^-1[m], same_msm gamma[m], same_msm gamma^-1[m].
+ * d_vec_a: batch x ell canonical scalars (as cdp_transcript_open_dev leaves them).
+ * d_scalars_out: batch x scal_pp canonical scalars: slots [0, n+5) = G | Hvec | H | G_t | G_u | (sum(G), sum(Hvec): zero, folded into the
+ *   G_i / Hvec_i), then R, S, T, U (ell each) at o_R .. o_U, M at o_M, the proof's points in serialisation order at o_P, and at big_n the 14
+ *   scalars of the exact form of the SameScalar equalities.  exact_eq != 0 keeps those four equalities out of the accumulated check. */
+typedef struct {
+    uint32_t ell, n, m, big_n, scal_pp, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch /* = 27 + 4 m */;
+} cdp_vcoef_params;
+int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8_t *d_vec_a, const cdp_vcoef_params *params, size_t batch,
+                          uint8_t *d_scalars_out);
+
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);
 

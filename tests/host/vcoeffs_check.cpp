@@ -1,0 +1,145 @@
+// Test helper (CPU): compiles the DEVICE verifier-scalar code (curdleproofs_b200/csrc/k_vcoeffs.cu) as plain C++ and compares every
+// output scalar with a straightforward host restatement of the same algebra -- the eight `accumulate_check` calls of
+// `CurdleproofsProof::verify` (/root/reference/src/curdleproofs.rs:283-296 and the argument verifiers they reach) plus the four
+// SameScalar equalities -- written with the product's host Fr (host/fr.hpp) in the vector-at-a-time style the host driver used before
+// this step moved to the GPU.  Random challenges; ell = 4, 12, 124, 252; both SameScalar modes.
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CDP_VCOEFFS_HOST_HARNESS
+#define __device__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(x)
+struct dim3_t { unsigned x; };
+static dim3_t blockIdx{0}, blockDim{1}, threadIdx{0};
+namespace cdp {
+struct vcoef_params_t { uint32_t ell, n, m, big_n, scal_pp, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch; };
+}
+#include "../../curdleproofs_b200/csrc/k_vcoeffs.cu"
+#include "../../curdleproofs_b200/host/fr.hpp"
+
+using namespace cdp_host;
+
+static uint64_t rng_state = 0x243F6A8885A308D3ULL;
+static uint64_t next64() { rng_state ^= rng_state << 13; rng_state ^= rng_state >> 7; rng_state ^= rng_state << 17; return rng_state; }
+static Fr rand_fr() {
+    uint64_t a[4] = {next64(), next64(), next64(), next64() >> 2};
+    return Fr::raw(a) * Fr::raw(Fr::R2);  // some field element, Montgomery form
+}
+static void s_vector(std::vector<Fr> &s, const Fr *gam, size_t m) {
+    size_t n = (size_t)1 << m;
+    s.resize(n);
+    s[0] = Fr::one();
+    for (size_t j = m; j-- > 0;) {
+        size_t bit = (size_t)1 << (m - 1 - j);
+        for (size_t i = 0; i < bit; i++) s[bit + i] = s[i] * gam[j];
+    }
+}
+
+static int run(size_t ell, bool exact_eq) {
+    const size_t n = ell + 4;
+    size_t m = 0;
+    while (((size_t)1 << m) < n) m++;
+    const size_t LC = 11, RC = LC + m, LD = RC + m, RD = LD + m, A1 = RD + m, A2 = A1 + 1, B1 = A2 + 1, B2 = B1 + 1, Ba = B2 + 1, Bt = Ba + 1,
+                 Bu = Bt + 1, LA = Bu + 1, LT = LA + m, LU = LT + m, RA = LU + m, RT = RA + m, RU = RT + m, np = RU + m;
+    const size_t LA_ = 0, T1 = 1, T2 = 2, U1 = 3, U2 = 4, R = 5, S = 6, Bp = 7, Cp = 8, Bc = 9, Bd = 10;
+    const size_t crs_n = n + 5, oR = crs_n, oS = oR + ell, oT = oS + ell, oU = oT + ell, oM = oU + ell, oP = oM + 1, big_n = oP + np, scal_pp = big_n + 14;
+    const size_t vch = 27 + 4 * m;
+    const size_t B = 3;
+    std::vector<Fr> ch(B * vch), va(B * ell);
+    for (auto &x : ch) x = rand_fr();
+    for (auto &x : va) x = rand_fr();
+    std::vector<uint8_t> va_bytes(B * ell * 32), want(B * scal_pp * 32, 0), got(B * scal_pp * 32, 0xEE);
+    for (size_t i = 0; i < B * ell; i++) va[i].to_bytes(&va_bytes[32 * i]);
+    // ---- reference
+    for (size_t pr = 0; pr < B; pr++) {
+        const Fr *c = &ch[pr * vch], *rho = c;
+        const Fr alpha_sp = c[12], beta_sp = c[13], alpha_g = c[14], beta_inv = c[15], alpha_i = c[16], beta_i = c[17], z = c[18], cf_c = c[19],
+                 cf_d = c[20], xf = c[21], alpha_sm = c[22], alpha_ss = c[23], z_k = c[24], z_t = c[25], z_u = c[26];
+        const Fr *gam = c + 27, *gam_inv = gam + m, *gam2 = gam_inv + m, *gam2_inv = gam2 + m;
+        std::vector<Fr> s_ipa, sinv_ipa, s_sm, u(n);
+        s_vector(s_ipa, gam, m); s_vector(sinv_ipa, gam_inv, m); s_vector(s_sm, gam2, m);
+        Fr pw = beta_inv;
+        for (size_t i = 0; i < ell; i++) { u[i] = pw; pw *= beta_inv; }
+        for (size_t i = 0; i < 4; i++) u[ell + i] = pw;
+        std::vector<Fr> cf(big_n, Fr::zero());
+        const size_t cG = 0, cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
+        cf[oP + Bp] += rho[0]; cf[oP + LA_] -= rho[0]; cf[oM] -= rho[0] * alpha_sp;
+        Fr t0 = rho[0] * beta_sp;
+        for (size_t i = 0; i < ell; i++) cf[cG + i] -= t0;
+        cf[oP + Bc] += rho[1]; cf[oP + Cp] += rho[1] * alpha_i;
+        cf[cH] += rho[1] * (alpha_i * alpha_i * z * beta_i - cf_c * cf_d * beta_i);
+        for (size_t k = 0; k < m; k++) { cf[oP + LC + k] += rho[1] * gam[k]; cf[oP + RC + k] += rho[1] * gam_inv[k]; }
+        Fr t1 = rho[1] * cf_c;
+        for (size_t i = 0; i < n; i++) cf[cG + i] -= t1 * s_ipa[i];
+        cf[oP + Bd] += rho[2];
+        Fr t2 = rho[2] * alpha_i;
+        cf[oP + Bp] += t2; cf[cGsum] -= t2 * beta_inv; cf[cHsum] += t2 * alpha_g;
+        for (size_t k = 0; k < m; k++) { cf[oP + LD + k] += rho[2] * gam[k]; cf[oP + RD + k] += rho[2] * gam_inv[k]; }
+        Fr t3 = rho[2] * cf_d;
+        for (size_t i = 0; i < n; i++) cf[cG + i] -= t3 * sinv_ipa[i] * u[i];
+        const size_t Bx[3] = {Ba, Bt, Bu}, Lx[3] = {LA, LT, LU}, Rx[3] = {RA, RT, RU};
+        for (int q = 0; q < 3; q++) {
+            const Fr &r = rho[3 + q];
+            cf[oP + Bx[q]] += r;
+            for (size_t k = 0; k < m; k++) { cf[oP + Lx[q] + k] += r * gam2[k]; cf[oP + Rx[q] + k] += r * gam2_inv[k]; }
+        }
+        Fr a4 = rho[3] * alpha_sm;
+        cf[oP + LA_] += a4; cf[oP + T1] += a4; cf[oP + U1] += a4;
+        cf[oP + T2] += rho[4] * alpha_sm;
+        cf[oP + U2] += rho[5] * alpha_sm;
+        Fr x4 = rho[3] * xf, x5 = rho[4] * xf, x6 = rho[5] * xf;
+        for (size_t i = 0; i < ell + 2; i++) cf[cG + i] -= x4 * s_sm[i];
+        cf[cGt] -= x4 * s_sm[ell + 2]; cf[cGu] -= x4 * s_sm[ell + 3];
+        for (size_t i = 0; i < ell; i++) { cf[oT + i] -= x5 * s_sm[i]; cf[oU + i] -= x6 * s_sm[i]; }
+        cf[cH] -= x5 * s_sm[ell + 2];
+        cf[cH] -= x6 * s_sm[ell + 3];
+        cf[oP + R] += rho[6]; cf[oP + S] += rho[7];
+        for (size_t i = 0; i < ell; i++) { cf[oR + i] -= rho[6] * va[pr * ell + i]; cf[oS + i] -= rho[7] * va[pr * ell + i]; }
+        if (!exact_eq) {
+            const Fr r8 = rho[8], r9 = rho[9], r10 = rho[10], r11 = rho[11];
+            cf[oP + A1] += r8; cf[oP + T1] += r8 * alpha_ss; cf[cGt] -= r8 * z_t;
+            cf[oP + A2] += r9; cf[oP + T2] += r9 * alpha_ss; cf[oP + R] -= r9 * z_k; cf[cH] -= r9 * z_t;
+            cf[oP + B1] += r10; cf[oP + U1] += r10 * alpha_ss; cf[cGu] -= r10 * z_u;
+            cf[oP + B2] += r11; cf[oP + U2] += r11 * alpha_ss; cf[oP + S] -= r11 * z_k; cf[cH] -= r11 * z_u;
+        }
+        for (size_t i = 0; i < ell; i++) cf[cG + i] += cf[cGsum];
+        for (size_t i = ell; i < n; i++) cf[cG + i] += cf[cHsum];
+        cf[cGsum] = cf[cHsum] = Fr::zero();
+        uint8_t *sc = &want[pr * scal_pp * 32];
+        for (size_t i = 0; i < big_n; i++) cf[i].to_bytes(sc + 32 * i);
+        const Fr one = Fr::one();
+        const Fr e[14] = {one, alpha_ss, z_t.neg(), one, alpha_ss, z_k.neg(), z_t.neg(), one, alpha_ss, z_u.neg(), one, alpha_ss, z_k.neg(), z_u.neg()};
+        for (int i = 0; i < 14; i++) e[i].to_bytes(sc + 32 * (big_n + i));
+    }
+    // ---- device code on the CPU: 7 "threads" per proof (so that the strided loops and the single-slot thread are both exercised)
+    cdp::vcoef_params_t P = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)big_n, (uint32_t)scal_pp, (uint32_t)oR, (uint32_t)oS, (uint32_t)oT,
+                             (uint32_t)oU, (uint32_t)oM, (uint32_t)oP, exact_eq ? 1u : 0u, (uint32_t)vch};
+    for (uint32_t nthreads : {1u, 7u, 300u}) {
+        std::fill(got.begin(), got.end(), 0xEE);
+        for (uint32_t pr = 0; pr < B; pr++)
+            for (uint32_t t = 0; t < nthreads; t++)
+                cdp::vcoef_thread(pr, t, nthreads, reinterpret_cast<const uint32_t *>(ch.data()), reinterpret_cast<const uint32_t *>(va_bytes.data()), P,
+                                  reinterpret_cast<uint32_t *>(got.data()));
+        if (got != want) {
+            for (size_t i = 0; i < got.size() / 32; i++)
+                if (memcmp(&got[32 * i], &want[32 * i], 32)) { printf("ell=%zu exact=%d threads=%u: first mismatch at scalar %zu (slot %zu of proof %zu)\n", ell, (int)exact_eq, nthreads, i, i % scal_pp, i / scal_pp); break; }
+            return 1;
+        }
+    }
+    printf("ell=%zu exact_eq=%d ok (%zu scalars per proof)\n", ell, (int)exact_eq, scal_pp);
+    return 0;
+}
+
+int main() {
+    int rc = 0;
+    for (size_t ell : {4, 12, 124, 252})
+        for (bool ex : {false, true}) rc |= run(ell, ex);
+    return rc;
+}

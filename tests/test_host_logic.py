@@ -62,3 +62,16 @@ def test_crs_text_format_errors_need_no_device():
         CurdleproofsCrs.from_json(None, "[1, 2]")
     with pytest.raises(CrsError):
         CurdleproofsCrs.from_hex(None, {"vec_G": []})
+
+
+def test_device_verifier_scalar_code_matches_host_restatement_on_cpu():
+    """The device-side verifier scalar preparation (csrc/k_vcoeffs.cu, compiled as plain C++): every coefficient of the accumulated check
+    -- verification scalars s_i / 1/s_i (/root/reference/src/util.rs:40-64), beta^-(i+1) rescaling, the `a * x_i` products of the eight
+    accumulate_check calls (src/msm_accumulator.rs:37-52) and the four SameScalar equalities -- against a vector-at-a-time host restatement
+    with the product's host Fr, on random challenges, ell = 4 / 12 / 124 / 252, both SameScalar modes, three thread counts."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "vcc")
+        subprocess.run(["g++", "-O1", "-march=x86-64-v3", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/vcoeffs_check.cpp")], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count(" ok ") == 8
