@@ -339,17 +339,26 @@ extern "C" int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs,
 }
 
 extern "C" int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8_t *d_vec_a, const cdp_vcoef_params *params, size_t batch,
-                                     uint8_t *d_scalars_out) {
-    if (!ctx || !params || (batch && (!d_challenges || !d_vec_a || !d_scalars_out))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_coeffs_dev: bad argument");
+                                     uint8_t *d_crs_scalars, uint8_t *d_var_scalars, uint8_t *d_exact_scalars) {
+    if (!ctx || !params || (batch && (!d_challenges || !d_vec_a || !d_crs_scalars || !d_var_scalars || !d_exact_scalars)))
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_coeffs_dev: bad argument");
     if (batch == 0) return CDP_OK;
     const cdp_vcoef_params &q = *params;
-    if (q.m == 0 || q.m > 16 || q.n != (1u << q.m) || q.ell + 4 != q.n || q.vch != 27 + 4 * q.m || q.scal_pp < q.big_n + 14)
+    if (q.m == 0 || q.m > 16 || q.n != (1u << q.m) || q.ell + 4 != q.n || q.vch != 27 + 4 * q.m || q.vw < q.big_n - (q.n + 5))
         return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_coeffs_dev: inconsistent layout");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
-    vcoef_params_t P = {q.ell, q.n, q.m, q.big_n, q.scal_pp, q.o_R, q.o_S, q.o_T, q.o_U, q.o_M, q.o_P, q.exact_eq, q.vch};
+    vcoef_params_t P = {q.ell, q.n, q.m, q.big_n, q.vw, q.o_R, q.o_S, q.o_T, q.o_U, q.o_M, q.o_P, q.exact_eq, q.vch};
     CUDA_TRY(ctx, launch_verify_coeffs(ctx->stream, reinterpret_cast<const uint32_t *>(d_challenges), reinterpret_cast<const uint32_t *>(d_vec_a), P,
-                                       (uint32_t)batch, reinterpret_cast<uint32_t *>(d_scalars_out)));
+                                       (uint32_t)batch, reinterpret_cast<uint32_t *>(d_crs_scalars), reinterpret_cast<uint32_t *>(d_var_scalars),
+                                       reinterpret_cast<uint32_t *>(d_exact_scalars)));
+    return CDP_OK;
+}
+
+extern "C" int cdp_dev_zero(cdp_ctx *ctx, void *d_ptr, size_t bytes) {
+    if (!ctx || (bytes && !d_ptr)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_dev_zero: bad argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_ptr, 0, bytes, ctx->stream));
     return CDP_OK;
 }
 

@@ -7,7 +7,7 @@
 //     accumulator's HashMap replaced by the verifier's fixed slot table, plus the four SameScalar equalities
 //     (src/same_scalar_argument.rs:127-136) with their own random factors.
 // Input per proof: 27 + 4 m Montgomery scalars (random factors, challenges, the proof's seven scalars) and vec_a; output: the
-// 5 ell + 8 + (proof points) canonical 32-byte scalars the two MSM kernels read.  The host keeps the transcript (hashing) only.
+// 5 ell + 8 + (proof points) canonical 32-byte scalars the MSM kernels read.  The host keeps the transcript (hashing) only.
 // One CTA per proof, one thread per vector index; Fr in 8 x 32-bit limbs with 64-bit products (a few thousand products per proof:
 // nothing here is throughput-critical).  Integer work only.
 #ifndef CDP_VCOEFFS_HOST_HARNESS  // tests/host/vcoeffs_check.cpp compiles this file with g++ to check it on the CPU
@@ -174,13 +174,15 @@ enum {
     CH_ALPHA_SS, CH_ZK, CH_ZT, CH_ZU, CH_VEC = 27
 };
 
-// One thread of the CTA that serves proof `pr`.  chal: [B][vch][8], vec_a: [B][ell][8] canonical, out: [B][scal_pp][8] canonical.
+// One thread of the CTA that serves proof `pr`.  chal: [B][vch][8], vec_a: [B][ell][8] canonical.  Outputs, canonical: the CRS slots
+// (< n + 5) go to out_crs[pr][n + 5], the per-proof slots (R, S, T, U, M, proof points) to out_var[pr * vw + slot] -- the same index the
+// point of that slot has in the verifier's per-lane base array, so that ONE msm over the whole array is the merged check of the batch --
+// and the 14 scalars of the exact SameScalar form to out_ex[pr][14].
 __device__ __forceinline__ void vcoef_thread(uint32_t pr, uint32_t tid, uint32_t nthreads, const uint32_t *chal, const uint32_t *vec_a,
-                                             const vcoef_params_t P, uint32_t *out) {
+                                             const vcoef_params_t P, uint32_t *out_crs, uint32_t *out_var, uint32_t *out_ex) {
     using namespace vcoef;
     const uint32_t ell = P.ell, n = P.n, m = P.m;
     const uint32_t *ch = chal + 8 * (size_t)pr * P.vch;
-    uint32_t *sc = out + 8 * (size_t)pr * P.scal_pp;
     auto C = [&](uint32_t k) { return fr_load(ch + 8 * k); };
     const uint32_t *gam = ch + 8 * CH_VEC, *gam_inv = gam + 8 * m, *gam2 = gam_inv + 8 * m, *gam2_inv = gam2 + 8 * m;
     const uint32_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
@@ -190,7 +192,12 @@ __device__ __forceinline__ void vcoef_thread(uint32_t pr, uint32_t tid, uint32_t
                    L_B2 = L_B1 + 1, L_Ba = L_B2 + 1, L_Bt = L_Ba + 1, L_Bu = L_Bt + 1, L_LA = L_Bu + 1, L_LT = L_LA + m, L_LU = L_LT + m,
                    L_RA = L_LU + m, L_RT = L_RA + m, L_RU = L_RT + m;
     const bool joint = P.exact_eq == 0;  // the SameScalar equalities join the accumulated check with rho[8..11]
-    auto put = [&](uint32_t slot, const fr_t &x) { fr_store_canonical(sc + 8 * slot, x); };
+    const uint32_t crs_n = n + 5;
+    auto put = [&](uint32_t slot, const fr_t &x) {
+        uint32_t *d = slot < crs_n ? out_crs + 8 * ((size_t)pr * crs_n + slot)
+                                   : slot < P.big_n ? out_var + 8 * ((size_t)pr * P.vw + slot) : out_ex + 8 * ((size_t)pr * 14 + (slot - P.big_n));
+        fr_store_canonical(d, x);
+    };
     const fr_t xf = C(CH_X);
     const fr_t x4 = fr_mul(C(CH_RHO + 3), xf), x5 = fr_mul(C(CH_RHO + 4), xf), x6 = fr_mul(C(CH_RHO + 5), xf);
     const fr_t t2 = fr_mul(C(CH_RHO + 2), C(CH_ALPHA_I));
@@ -272,14 +279,15 @@ __device__ __forceinline__ void vcoef_thread(uint32_t pr, uint32_t tid, uint32_t
 }
 
 __global__ void __launch_bounds__(256) k_verify_coeffs(const uint32_t *__restrict__ chal, const uint32_t *__restrict__ vec_a,
-                                                       const vcoef_params_t P, uint32_t *__restrict__ out) {
-    vcoef_thread(blockIdx.x, threadIdx.x, blockDim.x, chal, vec_a, P, out);
+                                                       const vcoef_params_t P, uint32_t *__restrict__ out_crs, uint32_t *__restrict__ out_var,
+                                                       uint32_t *__restrict__ out_ex) {
+    vcoef_thread(blockIdx.x, threadIdx.x, blockDim.x, chal, vec_a, P, out_crs, out_var, out_ex);
 }
 
 #ifndef CDP_VCOEFFS_HOST_HARNESS
 cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch,
-                                 uint32_t *out) {
-    k_verify_coeffs<<<batch, 256, 0, st>>>(chal, vec_a, P, out);
+                                 uint32_t *out_crs, uint32_t *out_var, uint32_t *out_ex) {
+    k_verify_coeffs<<<batch, 256, 0, st>>>(chal, vec_a, P, out_crs, out_var, out_ex);
     return cudaGetLastError();
 }
 #endif

@@ -50,9 +50,10 @@ cudaError_t launch_compress_affine(cudaStream_t st, const uint32_t *pts, const u
 cudaError_t launch_decompress(cudaStream_t st, const uint8_t *comp, const uint32_t *dst_idx, uint32_t *out_affine, uint8_t *status, uint32_t n);
 // k_vcoeffs.cu: the verifier's scalar preparation (slot layout of one proof's accumulated check; host/verifier.cpp builds it)
 struct vcoef_params_t {
-    uint32_t ell, n, m, big_n, scal_pp, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch;
+    uint32_t ell, n, m, big_n, vw, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch;
 };
-cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch, uint32_t *out);
+cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch, uint32_t *out_crs,
+                                 uint32_t *out_var, uint32_t *out_ex);
 cudaError_t launch_transcript_open(cudaStream_t st, const uint8_t *comp_vecs, const uint8_t *comp_M, uint32_t ell, uint32_t B, uint8_t *vec_a_out,
                                    uint64_t *state_out);
 cudaError_t launch_gather_points(cudaStream_t st, uint32_t *pts, const uint32_t *src, const uint32_t *src_idx, const uint32_t *dst_idx, uint32_t n);

@@ -109,6 +109,12 @@ struct VLane {
     uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
     uint8_t *d_chal = nullptr, *h_chal = nullptr;  // per-proof challenge blocks for the device-side scalar preparation (cdp_verify_coeffs_dev)
     size_t vch = 0;
+    // scalars of the accumulated check: CRS slots [proof][crs_n]; per-proof slots in the SAME indexing as d_pts (zero wherever d_pts holds
+    // something that is not a base of the check: the CRS block, the gathered copies), so that msm(d_pts, d_vscal) over the whole array is
+    // the merged check of the lane's batch; the 14 scalars of the exact SameScalar form [proof][14]
+    uint8_t *d_cscal = nullptr, *d_vscal = nullptr, *d_escal = nullptr;
+    bool merged = true;   // CDP_VERIFY_MERGE=0: always one accumulated MSM per proof
+    size_t n_merged = 0, n_fallback = 0;  // lane batches accepted by the merged check / re-checked proof by proof
     uint32_t *d_gsrc = nullptr, *d_gdst = nullptr, *d_isrc = nullptr, *d_idst = nullptr, *d_pdst = nullptr, *d_xsrc = nullptr, *d_xdst = nullptr;
     size_t g_pp = 0, i_pp = 0, x_pp = 0;
     cdp_msm_seg *d_segBig = nullptr, *d_segE = nullptr;
@@ -133,7 +139,7 @@ void vlane_destroy(VLane *p) {
     cdp_ctx *c = p->ctx;
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_pcomp, (void *)p->d_status, (void *)p->d_gsrc,
                     (void *)p->d_gdst, (void *)p->d_isrc, (void *)p->d_idst, (void *)p->d_pdst, (void *)p->d_xsrc, (void *)p->d_xdst,
-                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_jac,
+                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_cscal, (void *)p->d_vscal, (void *)p->d_escal, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
     for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_chal}) cdp_host_free(c, h);
@@ -147,6 +153,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     VLane *p = new VLane();
     p->ctx = ctx; p->table = table; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch; p->threads = std::max(1, host_threads);
     if (const char *e = getenv("CDP_VERIFY_EXACT_EQ")) p->exact_eq = atoi(e) != 0;
+    if (const char *e = getenv("CDP_VERIFY_MERGE")) p->merged = atoi(e) != 0;
     ProofLayout L(m);
     p->np = L.np;
     const size_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
@@ -175,13 +182,15 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->h_status = (uint8_t *)halloc(max_batch * L.np);
     p->d_veca = (uint8_t *)dalloc(max_batch * ell * 32); p->h_veca = (uint8_t *)halloc(max_batch * ell * 32);
     p->d_tstate = (uint8_t *)dalloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES); p->h_tstate = (uint8_t *)halloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES);
-    size_t scal_pp = p->big_n + 14;
     p->vch = 27 + 4 * m;
     p->d_chal = (uint8_t *)dalloc(max_batch * p->vch * 32); p->h_chal = (uint8_t *)halloc(max_batch * p->vch * 32);
-    p->d_scal = (uint8_t *)dalloc(max_batch * scal_pp * 32);
+    p->d_scal = (uint8_t *)dalloc(max_batch * 6 * 32);  // stage A (D, A')
+    p->d_cscal = (uint8_t *)dalloc(max_batch * p->crs_n * 32);
+    p->d_vscal = (uint8_t *)dalloc((total_pts + 1) * 32);
+    p->d_escal = (uint8_t *)dalloc(max_batch * 14 * 32);
     p->h_scal = (uint8_t *)halloc(max_batch * 6 * 32);  // stage A only: the coefficients of the accumulated check are computed on the device
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
-    p->d_jac = (uint8_t *)dalloc(max_batch * (p->chunks + FSPLIT + 5) * 144);
+    p->d_jac = (uint8_t *)dalloc((max_batch * (p->chunks + FSPLIT + 5) + 4) * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * out_pp * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * out_pp * 48);
     // tables
@@ -218,18 +227,18 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
         // leaves the partial sums as [chunk][proof]), its CRS part through the digit table, then the four SameScalar equalities
         for (size_t c = 0; c < p->chunks; c++) {
             size_t lo = p->crs_n + c * 2048, cnt = std::min<size_t>(2048, p->big_n - lo);
-            segBig[c * max_batch + pr] = {(uint32_t)(bp + lo), (uint32_t)(pr * scal_pp + lo), (uint32_t)cnt, 0};
+            segBig[c * max_batch + pr] = {(uint32_t)(bp + lo), (uint32_t)(bp + lo), (uint32_t)cnt, 0};  // d_vscal is indexed like d_pts
         }
         for (size_t q = 0; q < FSPLIT; q++) {  // the n + 3 CRS pairs in FSPLIT warps (one warp per segment): partial sums [proof][part]
             const size_t lo = (n + 3) * q / FSPLIT, hi = (n + 3) * (q + 1) / FSPLIT;
             cdp_fixed_seg &f = segF[pr * FSPLIT + q];
             memset(&f, 0, sizeof f);
-            f.base_off = (uint32_t)lo; f.scalars_off = (uint32_t)(pr * scal_pp + lo); f.n = (uint32_t)(hi - lo); f.remap_from = 0xFFFFFFFFu;
+            f.base_off = (uint32_t)lo; f.scalars_off = (uint32_t)(pr * p->crs_n + lo); f.n = (uint32_t)(hi - lo); f.remap_from = 0xFFFFFFFFu;
             f.out_idx = (uint32_t)(pr * FSPLIT + q);
         }
         const size_t eoff[4] = {X_E1, X_E2, X_E3, X_E4}, elen[4] = {3, 4, 3, 4}, esc[4] = {0, 3, 7, 10};
         for (int e = 0; e < 4; e++)
-            segE.push_back({(uint32_t)(bp + p->o_X + eoff[e]), (uint32_t)(pr * scal_pp + p->big_n + esc[e]), (uint32_t)elen[e], 0});
+            segE.push_back({(uint32_t)(bp + p->o_X + eoff[e]), (uint32_t)(pr * 14 + esc[e]), (uint32_t)elen[e], 0});
     }
     auto up32 = [&](std::vector<uint32_t> &v, uint32_t *&d) { d = (uint32_t *)dalloc(v.size() * 4); return d ? cdp_h2d(ctx, d, v.data(), v.size() * 4) : CDP_ERR_CUDA; };
     auto upseg = [&](std::vector<cdp_msm_seg> &v, cdp_msm_seg *&d) { d = (cdp_msm_seg *)dalloc(v.size() * sizeof(cdp_msm_seg)); return d ? cdp_h2d(ctx, d, v.data(), v.size() * sizeof(cdp_msm_seg)) : CDP_ERR_CUDA; };
@@ -247,6 +256,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
         std::vector<uint8_t> zero(96, 0);
         rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 9) * 96);  // the CRS followed by sum(G), sum(Hvec) (cdp_verifier_create)
         rc |= cdp_h2d(ctx, p->d_pts + total_pts * 96, zero.data(), 96);
+        rc |= cdp_dev_zero(ctx, p->d_vscal, (total_pts + 1) * 32);
         rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_comp);
         rc |= cdp_d2h(ctx, p->h_comp, p->d_comp, 48);
         rc |= cdp_sync(ctx);
@@ -265,7 +275,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     const size_t ell = p->ell, n = p->n, m = p->m, NP = p->np;
     const int T = p->threads;
     const ProofLayout L(m);
-    const size_t psz = cdp_proof_size(ell), scal_pp = p->big_n + 14, Moff = p->max_batch * 4 * ell;
+    const size_t psz = cdp_proof_size(ell), Moff = p->max_batch * 4 * ell;
     // ---- stage 0: instance + proof points to the device
     memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
     // instance vectors -> pinned staging; proof parsing: points -> h_pcomp (serialisation order), scalars -> state
@@ -419,19 +429,53 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host part 3: %.2f ms (B=%zu)\n", now_ms() - t0, B);
     VTRY(cdp_h2d(p->ctx, p->d_chal, p->h_chal, B * p->vch * 32));
     {
-        cdp_vcoef_params vp = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)p->big_n, (uint32_t)scal_pp, (uint32_t)p->o_R, (uint32_t)p->o_S,
+        cdp_vcoef_params vp = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)p->big_n, (uint32_t)p->VW, (uint32_t)p->o_R, (uint32_t)p->o_S,
                                (uint32_t)p->o_T, (uint32_t)p->o_U, (uint32_t)p->o_M, (uint32_t)p->o_P, p->exact_eq ? 1u : 0u, (uint32_t)p->vch};
-        VTRY(cdp_verify_coeffs_dev(p->ctx, p->d_chal, p->d_veca, &vp, B, p->d_scal));
+        VTRY(cdp_verify_coeffs_dev(p->ctx, p->d_chal, p->d_veca, &vp, B, p->d_cscal, p->d_vscal, p->d_escal));
     }
+    // CRS part of every proof's check through the digit table: partial sums [proof][part]
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
+    auto is_inf = [](const uint8_t *c) {
+        if (c[0] != 0xC0) return false;
+        for (int i = 1; i < 48; i++) if (c[i]) return false;
+        return true;
+    };
+    // ---- merged check of the lane's batch (SURVEY.md 8(f) rank 3 / BASELINE config 3): every check of every proof already carries its own
+    //      independent random factor, so the sum over the batch is again one random linear combination -- the MsmAccumulator argument
+    //      (msm_accumulator.rs:55-68) applied to 12 B checks instead of 12.  d_vscal is indexed like d_pts, so the per-proof bases of the
+    //      whole batch are ONE large MSM (cdp_msm_dev: sort-based Pippenger, ~16 additions per point instead of ~44 in B small ones); the CRS
+    //      parts are summed.  Identity => every proof of the batch is accepted.  Otherwise (or when a proof is already rejected / malformed,
+    //      whose points must not enter the sum) the per-proof path below decides each proof on its own: verdicts are the same either way.
+    bool decided = false;
+    bool clean = true;
+    for (size_t pr = 0; pr < B; pr++) clean = clean && p->vs[pr].status == 1;
+    if (p->merged && !p->exact_eq && clean && B >= 2) {
+        uint8_t *d_m = p->d_jac + (p->max_batch * (p->chunks + FSPLIT + 5)) * 144;  // 4 spare points
+        VTRY(cdp_msm_dev(p->ctx, p->d_pts + p->crs_n * 96, p->d_vscal + p->crs_n * 32, B * p->VW, d_m));
+        VTRY(cdp_sum_jacobian_dev(p->ctx, p->d_jac + p->chunks * B * 144, FSPLIT * B, d_m + 144));
+        VTRY(cdp_sum_jacobian_dev(p->ctx, d_m, 2, d_m + 288));
+        VTRY(cdp_normalize_dev(p->ctx, d_m + 288, 1, nullptr, p->d_comp));
+        VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, 48));
+        t0 = now_ms();
+        VTRY(cdp_sync(p->ctx));
+        t_wait += now_ms() - t0;
+        decided = is_inf(p->h_comp);
+        if (decided) p->n_merged++; else p->n_fallback++;
+    }
+    if (decided) {
+        for (size_t pr = 0; pr < B; pr++) ok_out[pr] = (uint8_t)p->vs[pr].status;
+        p->timing[0] = now_ms() - t_start; p->timing[1] = t_host; p->timing[2] = t_wait;
+        return CDP_OK;
+    }
+    // ---- per-proof path: the per-proof part (one launch per 2048-point chunk) added to the proof's CRS part; the exact equalities
     for (size_t c = 0; c < p->chunks; c++) {
         size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
-        VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
+        VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_vscal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
     }
-    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
     // accumulated sum of proof pr = its chunk sums [chunk][pr] + its CRS parts [pr][part]
     VTRY(cdp_sum_groups2_dev(p->ctx, p->d_jac, p->chunks, B, 1, p->d_jac + p->chunks * B * 144, FSPLIT, 1, FSPLIT, B, p->d_jac + NS * B * 144));
     const size_t n_res = p->exact_eq ? 5 * B : B;
-    if (p->exact_eq) VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
+    if (p->exact_eq) VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_escal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
     // results: [B accumulated sums] ([4B equalities])
     VTRY(cdp_normalize_dev(p->ctx, p->d_jac + NS * B * 144, n_res, nullptr, p->d_comp));
     VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, n_res * 48));
@@ -440,11 +484,6 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     t_wait += now_ms() - t0;
     for (size_t pr = 0; pr < B; pr++) {
         VState &s = p->vs[pr];
-        auto is_inf = [&](const uint8_t *c) {
-            if (c[0] != 0xC0) return false;
-            for (int i = 1; i < 48; i++) if (c[i]) return false;
-            return true;
-        };
         bool okk = is_inf(p->h_comp + pr * 48);
         if (p->exact_eq)
             for (int e = 0; e < 4; e++) okk = okk && is_inf(p->h_comp + (B + 4 * pr + e) * 48);
@@ -475,6 +514,11 @@ extern "C" void cdp_verifier_destroy(cdp_verifier *v) {
     delete v;
 }
 extern "C" const char *cdp_verifier_last_error(const cdp_verifier *v) { return v ? v->err.c_str() : "null verifier"; }
+extern "C" void cdp_verifier_merge_stats(const cdp_verifier *v, uint64_t out[2]) {
+    out[0] = out[1] = 0;
+    if (!v) return;
+    for (VLane *l : v->lanes) { out[0] += l->n_merged; out[1] += l->n_fallback; }
+}
 extern "C" void cdp_verifier_last_timing(const cdp_verifier *v, double out_ms[3]) {
     for (int k = 0; k < 3; k++) {
         out_ms[k] = 0;

@@ -240,6 +240,14 @@ class BatchVerifier:
         except Exception:
             pass
 
+    def merge_stats(self) -> dict:
+        """Lane sub-batches accepted by the merged accumulated check / re-checked proof by proof, since creation."""
+        out = (c_uint64 * 2)()
+        self._lib.cdp_verifier_merge_stats.argtypes = [c_void_p, POINTER(c_uint64)]
+        self._lib.cdp_verifier_merge_stats.restype = None
+        self._lib.cdp_verifier_merge_stats(self._h, out)
+        return {"merged": int(out[0]), "fallback": int(out[1])}
+
     def last_timing(self) -> dict:
         t = (c_double * 3)()
         self._lib.cdp_verifier_last_timing(self._h, t)

@@ -107,6 +107,7 @@ void *cdp_dev_alloc(cdp_ctx *ctx, size_t bytes);
 void cdp_dev_free(cdp_ctx *ctx, void *d_ptr);
 int cdp_h2d(cdp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int cdp_dev_zero(cdp_ctx *ctx, void *d_ptr, size_t bytes); /* asynchronous memset(0) on the context's stream */
 /* Pinned host memory for the asynchronous copies above. */
 void *cdp_host_alloc(cdp_ctx *ctx, size_t bytes);
 void cdp_host_free(cdp_ctx *ctx, void *h_ptr);
@@ -218,14 +219,16 @@ int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs, const uint
  *   [15] gprod beta^-1, [16] ipa alpha, [17] ipa beta, [18] z, [19] c_final, [20] d_final, [21] x_final, [22] same_msm alpha,
  *   [23] same_scalar alpha, [24] z_k, [25] z_t, [26] z_u, then ipa gamma[m], ipa gamma^-1[m], same_msm gamma[m], same_msm gamma^-1[m].
  * d_vec_a: batch x ell canonical scalars (as cdp_transcript_open_dev leaves them).
- * d_scalars_out: batch x scal_pp canonical scalars: slots [0, n+5) = G | Hvec | H | G_t | G_u | (sum(G), sum(Hvec): zero, folded into the
- *   G_i / Hvec_i), then R, S, T, U (ell each) at o_R .. o_U, M at o_M, the proof's points in serialisation order at o_P, and at big_n the 14
- *   scalars of the exact form of the SameScalar equalities.  exact_eq != 0 keeps those four equalities out of the accumulated check. */
+ * Outputs (canonical scalars): d_crs_scalars[batch][n + 5] = G | Hvec | H | G_t | G_u | (sum(G), sum(Hvec): zero, folded into the G_i /
+ *   Hvec_i); d_var_scalars[pr * vw + slot] for the per-proof slots n + 5 <= slot < big_n: R, S, T, U (ell each) at o_R .. o_U, M at o_M, the
+ *   proof's points in serialisation order at o_P -- the index the point of that slot has in the verifier's base array, so that one MSM
+ *   over the whole array is the merged check of a batch; d_exact_scalars[batch][14] = the exact form of the SameScalar equalities.
+ *   exact_eq != 0 keeps those four equalities out of the accumulated check. */
 typedef struct {
-    uint32_t ell, n, m, big_n, scal_pp, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch /* = 27 + 4 m */;
+    uint32_t ell, n, m, big_n, vw, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch /* = 27 + 4 m */;
 } cdp_vcoef_params;
 int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8_t *d_vec_a, const cdp_vcoef_params *params, size_t batch,
-                          uint8_t *d_scalars_out);
+                          uint8_t *d_crs_scalars, uint8_t *d_var_scalars, uint8_t *d_exact_scalars);
 
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);

@@ -69,13 +69,19 @@ void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]);
  * `CurdleproofsProof::deserialize` + `verify` (src/curdleproofs.rs:197-323) for `batch` independent proofs.
  * Proof points are decompressed and subgroup-checked on the GPU; the eight accumulated checks of a proof become one MSM
  * over [CRS | R | S | T | U | M | proof points] compared with the identity (the reference's MsmAccumulator, without the
- * HashMap); SameScalar's four point equalities are checked exactly. */
+ * HashMap); SameScalar's four point equalities join that check with their own random factors (CDP_VERIFY_EXACT_EQ=1: four exact MSMs).
+ * The coefficients are computed on the device (cdp_verify_coeffs_dev).  By default a lane first runs the MERGED check of its whole
+ * sub-batch -- the per-proof bases of all its proofs in ONE large MSM plus the summed CRS parts, every check already carrying its own
+ * random factor -- and accepts all of them when that is the identity; otherwise (or when a proof of the sub-batch is malformed) every
+ * proof is decided by its own accumulated MSM, so the verdicts never depend on the mode.  CDP_VERIFY_MERGE=0 disables the merged check. */
 typedef struct cdp_verifier cdp_verifier;
 int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads, int lanes);
 void cdp_verifier_destroy(cdp_verifier *v);
 const char *cdp_verifier_last_error(const cdp_verifier *v);
 /* Timing of the last cdp_verify_batch call, max over lanes, in ms: total, host compute (transcripts, coefficients), waiting for the GPU. */
 void cdp_verifier_last_timing(const cdp_verifier *v, double out_ms[3]);
+/* Since creation: [0] lane sub-batches accepted by the merged check, [1] lane sub-batches that fell back to proof-by-proof checks. */
+void cdp_verifier_merge_stats(const cdp_verifier *v, uint64_t out[2]);
 typedef struct {
     const uint8_t *vec_R;     /* batch * ell affine */
     const uint8_t *vec_S;

@@ -19,7 +19,7 @@
 struct dim3_t { unsigned x; };
 static dim3_t blockIdx{0}, blockDim{1}, threadIdx{0};
 namespace cdp {
-struct vcoef_params_t { uint32_t ell, n, m, big_n, scal_pp, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch; };
+struct vcoef_params_t { uint32_t ell, n, m, big_n, vw, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch; };
 }
 #include "../../curdleproofs_b200/csrc/k_vcoeffs.cu"
 #include "../../curdleproofs_b200/host/fr.hpp"
@@ -50,12 +50,14 @@ static int run(size_t ell, bool exact_eq) {
                  Bu = Bt + 1, LA = Bu + 1, LT = LA + m, LU = LT + m, RA = LU + m, RT = RA + m, RU = RT + m, np = RU + m;
     const size_t LA_ = 0, T1 = 1, T2 = 2, U1 = 3, U2 = 4, R = 5, S = 6, Bp = 7, Cp = 8, Bc = 9, Bd = 10;
     const size_t crs_n = n + 5, oR = crs_n, oS = oR + ell, oT = oS + ell, oU = oT + ell, oM = oU + ell, oP = oM + 1, big_n = oP + np, scal_pp = big_n + 14;
+    const size_t vw = big_n - crs_n + 20;  // the verifier's per-proof block width: per-proof slots + 20 gathered copies
     const size_t vch = 27 + 4 * m;
     const size_t B = 3;
     std::vector<Fr> ch(B * vch), va(B * ell);
     for (auto &x : ch) x = rand_fr();
     for (auto &x : va) x = rand_fr();
     std::vector<uint8_t> va_bytes(B * ell * 32), want(B * scal_pp * 32, 0), got(B * scal_pp * 32, 0xEE);
+    std::vector<uint8_t> g_crs(B * crs_n * 32), g_var((B * vw + crs_n) * 32), g_ex(B * 14 * 32);
     for (size_t i = 0; i < B * ell; i++) va[i].to_bytes(&va_bytes[32 * i]);
     // ---- reference
     for (size_t pr = 0; pr < B; pr++) {
@@ -119,14 +121,24 @@ static int run(size_t ell, bool exact_eq) {
         for (int i = 0; i < 14; i++) e[i].to_bytes(sc + 32 * (big_n + i));
     }
     // ---- device code on the CPU: 7 "threads" per proof (so that the strided loops and the single-slot thread are both exercised)
-    cdp::vcoef_params_t P = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)big_n, (uint32_t)scal_pp, (uint32_t)oR, (uint32_t)oS, (uint32_t)oT,
+    cdp::vcoef_params_t P = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)big_n, (uint32_t)vw, (uint32_t)oR, (uint32_t)oS, (uint32_t)oT,
                              (uint32_t)oU, (uint32_t)oM, (uint32_t)oP, exact_eq ? 1u : 0u, (uint32_t)vch};
     for (uint32_t nthreads : {1u, 7u, 300u}) {
-        std::fill(got.begin(), got.end(), 0xEE);
+        std::fill(g_crs.begin(), g_crs.end(), 0xEE); std::fill(g_var.begin(), g_var.end(), 0xEE); std::fill(g_ex.begin(), g_ex.end(), 0xEE);
         for (uint32_t pr = 0; pr < B; pr++)
             for (uint32_t t = 0; t < nthreads; t++)
                 cdp::vcoef_thread(pr, t, nthreads, reinterpret_cast<const uint32_t *>(ch.data()), reinterpret_cast<const uint32_t *>(va_bytes.data()), P,
-                                  reinterpret_cast<uint32_t *>(got.data()));
+                                  reinterpret_cast<uint32_t *>(g_crs.data()), reinterpret_cast<uint32_t *>(g_var.data()), reinterpret_cast<uint32_t *>(g_ex.data()));
+        // back into one row per proof; every byte of the per-proof window outside [crs_n, big_n) must be untouched
+        for (size_t pr = 0; pr < B; pr++) {
+            uint8_t *row = &got[pr * scal_pp * 32];
+            memcpy(row, &g_crs[pr * crs_n * 32], crs_n * 32);
+            memcpy(row + crs_n * 32, &g_var[(pr * vw + crs_n) * 32], (big_n - crs_n) * 32);
+            memcpy(row + big_n * 32, &g_ex[pr * 14 * 32], 14 * 32);
+            for (size_t k = big_n; k < crs_n + vw; k++)
+                for (int q = 0; q < 32; q++)
+                    if (g_var[(pr * vw + k) * 32 + q] != 0xEE) { printf("ell=%zu: gathered-copy slot %zu of proof %zu was written\n", ell, k, pr); return 1; }
+        }
         if (got != want) {
             for (size_t i = 0; i < got.size() / 32; i++)
                 if (memcmp(&got[32 * i], &want[32 * i], 32)) { printf("ell=%zu exact=%d threads=%u: first mismatch at scalar %zu (slot %zu of proof %zu)\n", ell, (int)exact_eq, nthreads, i, i % scal_pp, i / scal_pp); break; }

@@ -140,3 +140,43 @@ def test_verifier_chunked_accumulated_msm(engine, oracle):
     assert bv.verify_batch([inst, bad], proofs) == [1, 0]
     assert oracle.verify(inst, proofs[0], threads=8) == 1
     bv.close()
+
+
+def test_verifier_merged_check_and_fallback(engine, oracle, proved, monkeypatch):
+    """The merged accumulated check of a lane's sub-batch (one large MSM over the per-proof bases of all its proofs + the summed CRS
+    parts; SURVEY.md 8(f) rank 3, BASELINE config 3) accepts a batch of valid proofs in one go, and a batch with a bad proof falls back
+    to proof-by-proof checks with exactly the oracle's verdicts.  64 proofs x 191 slots is past the large-Pippenger threshold (2^13)."""
+    from curdleproofs_b200 import BatchVerifier
+    ell, crs, insts, proofs = proved
+    B = 64
+    bi, bp_ = [insts[i % 4] for i in range(B)], [proofs[i % 4] for i in range(B)]
+    bv = BatchVerifier(engine, ell, crs, max_batch=B, lanes=1)
+    assert bv.verify_batch(bi, bp_, rng_seeds=list(range(100, 100 + B))) == [1] * B
+    assert bv.merge_stats() == {"merged": 1, "fallback": 0}
+    # one proof attached to the wrong instance, one with a tampered scalar: the merged check must fail and the fallback must find exactly them
+    bad_i, bad_p = list(bi), list(bp_)
+    bad_i[17] = insts[(17 + 1) % 4]
+    bad_p[40] = bad_p[40][:-32] + pr.fr_to_bytes((int.from_bytes(bad_p[40][-32:], "little") + 1) % pr.R_ORDER)
+    want = [1] * B
+    want[17] = want[40] = 0
+    assert [oracle.verify(bad_i[k], bad_p[k]) for k in (16, 17, 40)] == [1, 0, 0]
+    assert bv.verify_batch(bad_i, bad_p) == want
+    assert bv.merge_stats() == {"merged": 1, "fallback": 1}
+    # a malformed proof keeps the whole sub-batch off the merged path (its points must not enter the sum)
+    broken = bytearray(bp_[5]); broken[48 * 5 + 20] ^= 0x55
+    mal_p = list(bp_); mal_p[5] = bytes(broken)
+    got = bv.verify_batch(bi, mal_p)
+    assert got[5] in (0, 2) and got[:5] + got[6:] == [1] * (B - 1)
+    assert bv.merge_stats() == {"merged": 1, "fallback": 1}
+    # two valid proofs whose errors would cancel in a naive (unweighted) sum cannot exist here, but two INVALID ones must not cancel either:
+    # swap the proofs of two different instances
+    sw_p = list(bp_); sw_p[0], sw_p[1] = bp_[1], bp_[0]
+    got = bv.verify_batch(bi, sw_p)
+    assert got[:2] == [0, 0] and got[2:] == [1] * (B - 2)
+    bv.close()
+    monkeypatch.setenv("CDP_VERIFY_MERGE", "0")
+    bv = BatchVerifier(engine, ell, crs, max_batch=B, lanes=2)
+    assert bv.verify_batch(bad_i, bad_p) == want
+    assert bv.verify_batch(bi, bp_) == [1] * B
+    assert bv.merge_stats() == {"merged": 0, "fallback": 0}
+    bv.close()
