@@ -338,6 +338,41 @@ extern "C" int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs,
     return CDP_OK;
 }
 
+extern "C" int cdp_verify_transcript_a_dev(cdp_ctx *ctx, const uint8_t *d_proof_points, const uint8_t *d_proof_scalars, const uint8_t *d_comp_vecs,
+                                          const uint8_t *d_comp_M, const uint8_t *d_vec_a, size_t ell, size_t batch, uint8_t *d_state,
+                                          uint8_t *d_challenges, uint8_t *d_tmp, uint8_t *d_stage_scalars, uint8_t *d_flags) {
+    if (!ctx || ell == 0 || (batch && (!d_proof_points || !d_proof_scalars || !d_comp_vecs || !d_comp_M || !d_vec_a || !d_state || !d_challenges || !d_tmp ||
+                                       !d_stage_scalars || !d_flags)))
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_transcript_a_dev: bad argument");
+    if (batch == 0) return CDP_OK;
+    size_t n = ell + 4, m = 0;
+    while ((size_t(1) << m) < n) m++;
+    if ((size_t(1) << m) != n || m > 16) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_transcript_a_dev: ell + 4 must be a power of two");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
+    CUDA_TRY(ctx, launch_verify_transcript_a(ctx->stream, d_proof_points, d_proof_scalars, d_comp_M, d_vec_a, (uint32_t)ell, (uint32_t)(18 + 10 * m),
+                                             (uint32_t)(27 + 4 * m), (uint32_t)batch, reinterpret_cast<uint64_t *>(d_state),
+                                             reinterpret_cast<uint32_t *>(d_challenges), reinterpret_cast<uint32_t *>(d_tmp),
+                                             reinterpret_cast<uint32_t *>(d_stage_scalars), d_comp_vecs, d_flags));
+    return CDP_OK;
+}
+extern "C" int cdp_verify_transcript_b_dev(cdp_ctx *ctx, const uint8_t *d_proof_points, const uint8_t *d_proof_scalars, const uint8_t *d_comp_vecs,
+                                          const uint8_t *d_comp_DA, const uint8_t *d_comp_H, size_t ell, size_t batch, uint8_t *d_state,
+                                          uint8_t *d_challenges, const uint8_t *d_tmp) {
+    if (!ctx || ell == 0 || (batch && (!d_proof_points || !d_proof_scalars || !d_comp_vecs || !d_comp_DA || !d_comp_H || !d_state || !d_challenges || !d_tmp)))
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_transcript_b_dev: bad argument");
+    if (batch == 0) return CDP_OK;
+    size_t n = ell + 4, m = 0;
+    while ((size_t(1) << m) < n) m++;
+    if ((size_t(1) << m) != n || m > 16) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_transcript_b_dev: ell + 4 must be a power of two");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
+    CUDA_TRY(ctx, launch_verify_transcript_b(ctx->stream, d_proof_points, d_proof_scalars, d_comp_DA, d_comp_vecs, d_comp_H, (uint32_t)ell, (uint32_t)m,
+                                             (uint32_t)(18 + 10 * m), (uint32_t)(27 + 4 * m), (uint32_t)batch, reinterpret_cast<uint64_t *>(d_state),
+                                             reinterpret_cast<uint32_t *>(d_challenges), reinterpret_cast<const uint32_t *>(d_tmp)));
+    return CDP_OK;
+}
+
 extern "C" int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8_t *d_vec_a, const cdp_vcoef_params *params, size_t batch,
                                      uint8_t *d_crs_scalars, uint8_t *d_var_scalars, uint8_t *d_exact_scalars) {
     if (!ctx || !params || (batch && (!d_challenges || !d_vec_a || !d_crs_scalars || !d_var_scalars || !d_exact_scalars)))

@@ -11,6 +11,7 @@
 #include "launch.h"
 #include "constants.cuh"
 #endif
+#include "fr256.cuh"
 
 namespace cdp {
 
@@ -202,11 +203,250 @@ __global__ void __launch_bounds__(32) k_transcript_open(const uint8_t *__restric
     so[25] = (uint64_t)s.pos | ((uint64_t)s.pos_begin << 8);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// The REST of the verifier's transcript on the device (verifier side): `CurdleproofsProof::verify`
+// (/root/reference/src/curdleproofs.rs:226-296) reaches SamePerm / GrandProduct / IPA / SameScalar / SameMSM `verify`, each of which only
+// appends proof points and scalars and draws challenges.  One thread per proof continues the STROBE state k_transcript_open left, in two
+// kernels because the transcript needs two points computed on the GPU in between (D and A', a fixed-base launch):
+//   k_verify_transcript_a   same_perm (src/same_permutation_argument.rs:134-145) and gprod (src/grand_product_argument.rs:202-223) up to
+//                           the gprod beta: alpha, beta of same_perm, the grand product of (a_i + i alpha + beta), alpha_g, beta_g and
+//                           beta_g^-1; writes the six scalars of D = B - beta^-1 sum(G) + alpha_g sum(Hvec) and A' = A + T_1 + U_1
+//   k_verify_transcript_b   z, then IPA (src/inner_product_argument.rs:282-304), SameScalar (src/same_scalar_argument.rs:110-125) and
+//                           SameMSM (src/same_multiscalar_argument.rs:231-241); inverts the 2m round challenges with one inversion each
+//                           (the reference's batch_inversion, inner_product_argument.rs:234); completes the proof's challenge block for
+//                           k_verify_coeffs (entries 12..26 and the four challenge vectors; 0..11, the random factors, come from the host)
+// Proof points are read as the 48-byte encodings of the serialised proof, proof scalars as canonical 32-byte values.
+namespace {
+
+__device__ const uint8_t L_SP1[] = "same_perm_step1";
+__device__ const uint8_t L_SPA[] = "same_perm_alpha";
+__device__ const uint8_t L_SPB[] = "same_perm_beta";
+__device__ const uint8_t L_GP1[] = "gprod_step1";
+__device__ const uint8_t L_GPA[] = "gprod_alpha";
+__device__ const uint8_t L_GP2[] = "gprod_step2";
+__device__ const uint8_t L_GPB[] = "gprod_beta";
+__device__ const uint8_t L_IP1[] = "ipa_step1";
+__device__ const uint8_t L_IPA[] = "ipa_alpha";
+__device__ const uint8_t L_IPB[] = "ipa_beta";
+__device__ const uint8_t L_IPL[] = "ipa_loop";
+__device__ const uint8_t L_IPG[] = "ipa_gamma";
+__device__ const uint8_t L_SEP[] = "sameexp_points";
+__device__ const uint8_t L_SSA[] = "same_scalar_alpha";
+__device__ const uint8_t L_SM1[] = "same_msm_step1";
+__device__ const uint8_t L_SMA[] = "same_msm_alpha";
+__device__ const uint8_t L_SML[] = "same_msm_loop";
+__device__ const uint8_t L_SMG[] = "same_msm_gamma";
+
+__device__ __forceinline__ void state_load(strobe_t &s, const uint64_t *src) {
+#pragma unroll 1
+    for (int i = 0; i < 25; i++) s.st[i] = src[i];
+    s.pos = (uint32_t)(src[25] & 0xFF);
+    s.pos_begin = (uint32_t)((src[25] >> 8) & 0xFF);
+}
+__device__ __forceinline__ void state_store(uint64_t *dst, const strobe_t &s) {
+#pragma unroll 1
+    for (int i = 0; i < 25; i++) dst[i] = s.st[i];
+    dst[25] = (uint64_t)s.pos | ((uint64_t)s.pos_begin << 8);
+}
+__device__ __forceinline__ void append_point(strobe_t &s, const uint8_t *label, uint32_t llen, const uint8_t *comp) {
+    merlin_append(s, label, llen, 0, 0, comp, 48);
+}
+// `append(label, &Fr)`: the canonical 32-byte little-endian value (src/transcript.rs:29-33)
+__device__ void append_fr(strobe_t &s, const uint8_t *label, uint32_t llen, const vcoef::fr_t &x_mont) {
+    uint32_t w[8];
+    vcoef::fr_store_canonical(w, x_mont);
+    strobe_meta_ad(s, label, llen, false);
+    strobe_absorb_value(s, 32, 4);
+    strobe_begin(s, FLAG_A, false);
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) strobe_absorb_value(s, w[k], 4);
+}
+// get_and_append_challenge (src/transcript.rs:41-54); returns the challenge in Montgomery form
+__device__ vcoef::fr_t draw_challenge(strobe_t &s, const uint8_t *label, uint32_t llen) {
+    uint8_t buf[64];
+    vcoef::fr_t c;
+    for (;;) {
+        merlin_challenge(s, label, llen, buf, 64);
+        buf[31] &= 0x7F;
+        uint32_t nz = 0;
+        for (int k = 0; k < 8; k++) {
+            c.v[k] = (uint32_t)buf[4 * k] | ((uint32_t)buf[4 * k + 1] << 8) | ((uint32_t)buf[4 * k + 2] << 16) | ((uint32_t)buf[4 * k + 3] << 24);
+            nz |= c.v[k];
+        }
+        if (nz && !vcoef::fr_geq_mod(c.v)) break;
+    }
+    merlin_append(s, label, llen, 0, 0, buf, 32);
+    return vcoef::fr_to_mont(c);
+}
+__device__ __forceinline__ void chal_store(uint32_t *dst, const vcoef::fr_t &x) {
+    for (int k = 0; k < 8; k++) dst[k] = x.v[k];
+}
+
+}  // namespace
+
+// pcomp: B x np encodings (the proof's points in serialisation order), pscal: B x 7 canonical scalars (r_p, c_final, d_final, z_k, z_t,
+// z_u, x_final), comp_M: B encodings, vec_a: B x ell canonical, state: B x 26 u64 (in/out).  Outputs: chal[pr][12..15] (Montgomery),
+// tmp[pr][0..1] = grand product, beta_g (Montgomery), stage_scal[pr][6] canonical = {1, -beta_g^-1, alpha_g, 1, 1, 1}, flags[pr] = 1 when
+// vec_T[0] (first encoding of the T block of comp_vecs, B x 4 x ell encodings) is the identity.
+__global__ void __launch_bounds__(32) k_verify_transcript_a(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                            const uint8_t *__restrict__ comp_M, const uint8_t *__restrict__ vec_a, uint32_t ell,
+                                                            uint32_t np, uint32_t vch, uint32_t B, uint64_t *__restrict__ state,
+                                                            uint32_t *__restrict__ chal, uint32_t *__restrict__ tmp, uint32_t *__restrict__ stage_scal,
+                                                            const uint8_t *__restrict__ comp_vecs, uint8_t *__restrict__ flags) {
+    using namespace vcoef;
+    const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pr >= B) return;
+    strobe_t s;
+    state_load(s, state + (size_t)pr * 26);
+    const uint8_t *pc = pcomp + (size_t)pr * np * 48;
+    const uint8_t *va = vec_a + (size_t)pr * ell * 32;
+    // same_perm: A, M, vec_a -> alpha, beta
+    append_point(s, L_SP1, 15, pc + 48 * 0);
+    append_point(s, L_SP1, 15, comp_M + (size_t)pr * 48);
+    merlin_append(s, L_SP1, 15, (uint64_t)ell, 8, va, ell * 32);
+    const fr_t alpha_sp = draw_challenge(s, L_SPA, 15), beta_sp = draw_challenge(s, L_SPB, 14);
+    fr_t gprod = fr_one(), i_alpha = beta_sp;  // i * alpha + beta, advanced by addition
+#pragma unroll 1
+    for (uint32_t i = 0; i < ell; i++) {
+        const fr_t a = fr_to_mont(fr_load(reinterpret_cast<const uint32_t *>(va + 32 * i)));
+        gprod = fr_mul(gprod, fr_add(a, i_alpha));
+        i_alpha = fr_add(i_alpha, alpha_sp);
+    }
+    // gprod: B, grand product -> alpha; C, r_p -> beta
+    append_point(s, L_GP1, 11, pc + 48 * 7);
+    append_fr(s, L_GP1, 11, gprod);
+    const fr_t alpha_g = draw_challenge(s, L_GPA, 11);
+    append_point(s, L_GP2, 11, pc + 48 * 8);
+    const fr_t r_p = fr_to_mont(fr_load(reinterpret_cast<const uint32_t *>(pscal + ((size_t)pr * 7 + 0) * 32)));
+    append_fr(s, L_GP2, 11, r_p);
+    const fr_t beta_g = draw_challenge(s, L_GPB, 10);
+    const fr_t beta_inv = fr_inverse(beta_g);
+    state_store(state + (size_t)pr * 26, s);
+    uint32_t *ch = chal + 8 * (size_t)pr * vch;
+    chal_store(ch + 8 * CH_ALPHA_SP, alpha_sp); chal_store(ch + 8 * CH_BETA_SP, beta_sp);
+    chal_store(ch + 8 * CH_ALPHA_G, alpha_g); chal_store(ch + 8 * CH_BETA_INV, beta_inv);
+    chal_store(tmp + 8 * ((size_t)pr * 2 + 0), gprod); chal_store(tmp + 8 * ((size_t)pr * 2 + 1), beta_g);
+    uint32_t *sc = stage_scal + 8 * (size_t)pr * 6;
+    const fr_t one = fr_one();
+    fr_store_canonical(sc + 0, one); fr_store_canonical(sc + 8, fr_neg(beta_inv)); fr_store_canonical(sc + 16, alpha_g);
+    fr_store_canonical(sc + 24, one); fr_store_canonical(sc + 32, one); fr_store_canonical(sc + 40, one);
+    // vec_T[0] is the identity -> Err(VerificationError) (curdleproofs.rs:218-220): bit 6 of the first byte of its encoding
+    if (flags) flags[pr] = (comp_vecs[(((size_t)pr * 4 + 2) * ell) * 48] & 0x40) ? 1 : 0;
+}
+
+// da_comp: B x 2 encodings (D, A'), comp_T / comp_U: the instance's vec_T / vec_U encodings of proof pr at comp_vecs + ((pr * 4 + 2 | 3) * ell) * 48,
+// H_comp: the encoding of crs.H.  Completes chal[pr][16..26] and the four challenge vectors.
+__global__ void __launch_bounds__(32) k_verify_transcript_b(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                            const uint8_t *__restrict__ da_comp, const uint8_t *__restrict__ comp_vecs,
+                                                            const uint8_t *__restrict__ H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch,
+                                                            uint32_t B, uint64_t *__restrict__ state, uint32_t *__restrict__ chal,
+                                                            const uint32_t *__restrict__ tmp) {
+    using namespace vcoef;
+    const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pr >= B) return;
+    strobe_t s;
+    state_load(s, state + (size_t)pr * 26);
+    const uint8_t *pc = pcomp + (size_t)pr * np * 48;
+    const uint32_t n = ell + 4;
+    // proof point indices in serialisation order (host/verifier.cpp ProofLayout)
+    const uint32_t L_T1 = 1, L_T2 = 2, L_U1 = 3, L_U2 = 4, L_R = 5, L_S = 6, L_C = 8, L_Bc = 9, L_Bd = 10;
+    const uint32_t L_LC = 11, L_RC = L_LC + m, L_LD = L_RC + m, L_RD = L_LD + m, L_A1 = L_RD + m, L_A2 = L_A1 + 1, L_B1 = L_A2 + 1,
+                   L_B2 = L_B1 + 1, L_Ba = L_B2 + 1, L_Bt = L_Ba + 1, L_Bu = L_Bt + 1, L_LA = L_Bu + 1, L_LT = L_LA + m, L_LU = L_LT + m,
+                   L_RA = L_LU + m, L_RT = L_RA + m, L_RU = L_RT + m;
+    auto PS = [&](uint32_t k) { return fr_to_mont(fr_load(reinterpret_cast<const uint32_t *>(pscal + ((size_t)pr * 7 + k) * 32))); };
+    const fr_t r_p = PS(0);
+    const fr_t gprod = fr_load(tmp + 8 * ((size_t)pr * 2 + 0)), beta = fr_load(tmp + 8 * ((size_t)pr * 2 + 1));
+    // z = r_p beta^(ell+1) + gprod beta^ell - 1   (grand_product_argument.rs:225-229)
+    const fr_t beta_l = fr_pow_u32(beta, ell);
+    const fr_t z = fr_sub(fr_add(fr_mul(r_p, fr_mul(beta_l, beta)), fr_mul(gprod, beta_l)), fr_one());
+    // IPA
+    append_point(s, L_IP1, 9, pc + 48 * L_C);
+    append_point(s, L_IP1, 9, da_comp + ((size_t)pr * 2 + 0) * 48);
+    append_fr(s, L_IP1, 9, z);
+    append_point(s, L_IP1, 9, pc + 48 * L_Bc);
+    append_point(s, L_IP1, 9, pc + 48 * L_Bd);
+    const fr_t alpha_i = draw_challenge(s, L_IPA, 9), beta_i = draw_challenge(s, L_IPB, 8);
+    uint32_t *ch = chal + 8 * (size_t)pr * vch;
+    fr_t g[16];
+#pragma unroll 1
+    for (uint32_t k = 0; k < m; k++) {
+        append_point(s, L_IPL, 8, pc + 48 * (L_LC + k)); append_point(s, L_IPL, 8, pc + 48 * (L_LD + k));
+        append_point(s, L_IPL, 8, pc + 48 * (L_RC + k)); append_point(s, L_IPL, 8, pc + 48 * (L_RD + k));
+        g[k] = draw_challenge(s, L_IPG, 9);
+        chal_store(ch + 8 * (CH_VEC + k), g[k]);
+    }
+    fr_batch_inverse(g, m);
+    for (uint32_t k = 0; k < m; k++) chal_store(ch + 8 * (CH_VEC + m + k), g[k]);
+    // SameScalar
+    {
+        const uint32_t ss[10] = {L_R, L_S, L_T1, L_T2, L_U1, L_U2, L_A1, L_A2, L_B1, L_B2};
+#pragma unroll 1
+        for (int q = 0; q < 10; q++) append_point(s, L_SEP, 14, pc + 48 * ss[q]);
+    }
+    const fr_t alpha_ss = draw_challenge(s, L_SSA, 17);
+    // SameMSM: A', cm_T.T_2, cm_U.T_2, vec_T | inf inf H inf, vec_U | inf inf inf H, B_a, B_t, B_u
+    append_point(s, L_SM1, 14, da_comp + ((size_t)pr * 2 + 1) * 48);
+    append_point(s, L_SM1, 14, pc + 48 * L_T2);
+    append_point(s, L_SM1, 14, pc + 48 * L_U2);
+#pragma unroll 1
+    for (int v = 0; v < 2; v++) {  // a Vec<G1Affine> of n elements: u64-LE count, the ell instance points, the four blinder slots
+        strobe_meta_ad(s, L_SM1, 14, false);
+        strobe_absorb_value(s, 8 + n * 48, 4);
+        strobe_begin(s, FLAG_A, false);
+        strobe_absorb_value(s, (uint64_t)n, 8);
+        strobe_absorb(s, comp_vecs + (((size_t)pr * 4 + 2 + v) * ell) * 48, ell * 48);
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            if (q == 2 + v) {
+                strobe_absorb(s, H_comp, 48);
+            } else {
+                strobe_absorb_byte(s, 0xC0);
+#pragma unroll 1
+                for (int k = 1; k < 48; k++) strobe_absorb_byte(s, 0);
+            }
+        }
+    }
+    append_point(s, L_SM1, 14, pc + 48 * L_Ba);
+    append_point(s, L_SM1, 14, pc + 48 * L_Bt);
+    append_point(s, L_SM1, 14, pc + 48 * L_Bu);
+    const fr_t alpha_sm = draw_challenge(s, L_SMA, 14);
+#pragma unroll 1
+    for (uint32_t k = 0; k < m; k++) {
+        const uint32_t o[6] = {L_LA, L_LT, L_LU, L_RA, L_RT, L_RU};
+#pragma unroll 1
+        for (int q = 0; q < 6; q++) append_point(s, L_SML, 13, pc + 48 * (o[q] + k));
+        g[k] = draw_challenge(s, L_SMG, 14);
+        chal_store(ch + 8 * (CH_VEC + 2 * m + k), g[k]);
+    }
+    fr_batch_inverse(g, m);
+    for (uint32_t k = 0; k < m; k++) chal_store(ch + 8 * (CH_VEC + 3 * m + k), g[k]);
+    state_store(state + (size_t)pr * 26, s);
+    chal_store(ch + 8 * CH_ALPHA_I, alpha_i); chal_store(ch + 8 * CH_BETA_I, beta_i); chal_store(ch + 8 * CH_Z, z);
+    chal_store(ch + 8 * CH_C, PS(1)); chal_store(ch + 8 * CH_D, PS(2)); chal_store(ch + 8 * CH_X, PS(6));
+    chal_store(ch + 8 * CH_ALPHA_SM, alpha_sm); chal_store(ch + 8 * CH_ALPHA_SS, alpha_ss);
+    chal_store(ch + 8 * CH_ZK, PS(3)); chal_store(ch + 8 * CH_ZT, PS(4)); chal_store(ch + 8 * CH_ZU, PS(5));
+}
+
 #ifndef CDP_TRANSCRIPT_HOST_HARNESS
 cudaError_t launch_transcript_open(cudaStream_t st, const uint8_t *comp_vecs, const uint8_t *comp_M, uint32_t ell, uint32_t B, uint8_t *vec_a_out,
                                    uint64_t *state_out) {
     if (B == 0) return cudaSuccess;
     k_transcript_open<<<(B + 31) / 32, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_transcript_a(cudaStream_t st, const uint8_t *pcomp, const uint8_t *pscal, const uint8_t *comp_M, const uint8_t *vec_a,
+                                       uint32_t ell, uint32_t np, uint32_t vch, uint32_t B, uint64_t *state, uint32_t *chal, uint32_t *tmp,
+                                       uint32_t *stage_scal, const uint8_t *comp_vecs, uint8_t *flags) {
+    if (B == 0) return cudaSuccess;
+    k_verify_transcript_a<<<(B + 31) / 32, 32, 0, st>>>(pcomp, pscal, comp_M, vec_a, ell, np, vch, B, state, chal, tmp, stage_scal, comp_vecs, flags);
+    return cudaGetLastError();
+}
+cudaError_t launch_verify_transcript_b(cudaStream_t st, const uint8_t *pcomp, const uint8_t *pscal, const uint8_t *da_comp, const uint8_t *comp_vecs,
+                                       const uint8_t *H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch, uint32_t B, uint64_t *state,
+                                       uint32_t *chal, const uint32_t *tmp) {
+    if (B == 0) return cudaSuccess;
+    k_verify_transcript_b<<<(B + 31) / 32, 32, 0, st>>>(pcomp, pscal, da_comp, comp_vecs, H_comp, ell, m, np, vch, B, state, chal, tmp);
     return cudaGetLastError();
 }
 #endif

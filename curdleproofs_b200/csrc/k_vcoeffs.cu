@@ -13,166 +13,11 @@
 #ifndef CDP_VCOEFFS_HOST_HARNESS  // tests/host/vcoeffs_check.cpp compiles this file with g++ to check it on the CPU
 #include "launch.h"
 #endif
+#include "fr256.cuh"
 
 namespace cdp {
 
-namespace vcoef {
 
-struct fr_t {
-    uint32_t v[8];
-};
-// r, R mod r, -r^-1 mod 2^32 (the same constants as host/fr.hpp and constants.cuh, as literals so that the CPU harness sees them too)
-__device__ __forceinline__ uint32_t fr_mod(int i) {
-    const uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
-    return t[i];
-}
-__device__ __forceinline__ uint32_t fr_r2(int i) {
-    const uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
-    return t[i];
-}
-__device__ __forceinline__ uint32_t fr_r1(int i) {
-    const uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
-    return t[i];
-}
-constexpr uint32_t FR_NINV = 0xffffffffu;
-
-__device__ __forceinline__ fr_t fr_zero() {
-    fr_t r;
-    for (int i = 0; i < 8; i++) r.v[i] = 0;
-    return r;
-}
-__device__ __forceinline__ fr_t fr_one() {
-    fr_t r;
-    for (int i = 0; i < 8; i++) r.v[i] = fr_r1(i);
-    return r;
-}
-__device__ __forceinline__ bool fr_geq_mod(const uint32_t *a) {
-    for (int i = 7; i >= 0; i--) {
-        if (a[i] > fr_mod(i)) return true;
-        if (a[i] < fr_mod(i)) return false;
-    }
-    return true;
-}
-__device__ __forceinline__ void fr_sub_mod(uint32_t *a) {
-    uint64_t borrow = 0;
-    for (int i = 0; i < 8; i++) {
-        uint64_t d = (uint64_t)a[i] - fr_mod(i) - borrow;
-        a[i] = (uint32_t)d;
-        borrow = (d >> 32) & 1;
-    }
-}
-__device__ __forceinline__ fr_t fr_add(const fr_t &a, const fr_t &b) {
-    fr_t r;
-    uint64_t c = 0;
-    for (int i = 0; i < 8; i++) {
-        c += (uint64_t)a.v[i] + b.v[i];
-        r.v[i] = (uint32_t)c;
-        c >>= 32;
-    }
-    if (c || fr_geq_mod(r.v)) fr_sub_mod(r.v);
-    return r;
-}
-__device__ __forceinline__ fr_t fr_sub(const fr_t &a, const fr_t &b) {
-    fr_t r;
-    uint64_t borrow = 0;
-    for (int i = 0; i < 8; i++) {
-        uint64_t d = (uint64_t)a.v[i] - b.v[i] - borrow;
-        r.v[i] = (uint32_t)d;
-        borrow = (d >> 32) & 1;
-    }
-    if (borrow) {
-        uint64_t c = 0;
-        for (int i = 0; i < 8; i++) {
-            c += (uint64_t)r.v[i] + fr_mod(i);
-            r.v[i] = (uint32_t)c;
-            c >>= 32;
-        }
-    }
-    return r;
-}
-__device__ __forceinline__ fr_t fr_neg(const fr_t &a) { return fr_sub(fr_zero(), a); }
-// Montgomery product (R = 2^256), coarsely integrated operand scanning
-__device__ __noinline__ fr_t fr_mul(const fr_t &a, const fr_t &b) {
-    uint32_t t[10];
-    for (int i = 0; i < 10; i++) t[i] = 0;
-    for (int i = 0; i < 8; i++) {
-        uint64_t c = 0;
-        for (int j = 0; j < 8; j++) {
-            c += (uint64_t)a.v[j] * b.v[i] + t[j];
-            t[j] = (uint32_t)c;
-            c >>= 32;
-        }
-        c += t[8];
-        t[8] = (uint32_t)c;
-        t[9] = (uint32_t)(c >> 32);
-        const uint32_t m = t[0] * FR_NINV;
-        c = (uint64_t)m * fr_mod(0) + t[0];
-        c >>= 32;
-        for (int j = 1; j < 8; j++) {
-            c += (uint64_t)m * fr_mod(j) + t[j];
-            t[j - 1] = (uint32_t)c;
-            c >>= 32;
-        }
-        c += t[8];
-        t[7] = (uint32_t)c;
-        t[8] = t[9] + (uint32_t)(c >> 32);
-    }
-    fr_t r;
-    for (int i = 0; i < 8; i++) r.v[i] = t[i];
-    if (t[8] || fr_geq_mod(r.v)) fr_sub_mod(r.v);
-    return r;
-}
-__device__ __forceinline__ fr_t fr_load(const uint32_t *p) {
-    fr_t r;
-    for (int i = 0; i < 8; i++) r.v[i] = p[i];
-    return r;
-}
-// canonical little-endian value -> Montgomery form
-__device__ __forceinline__ fr_t fr_to_mont(const fr_t &a) {
-    fr_t r2;
-    for (int i = 0; i < 8; i++) r2.v[i] = fr_r2(i);
-    return fr_mul(a, r2);
-}
-// Montgomery form -> canonical value, stored as 8 words
-__device__ __forceinline__ void fr_store_canonical(uint32_t *dst, const fr_t &a) {
-    fr_t one = fr_zero();
-    one.v[0] = 1;
-    const fr_t c = fr_mul(a, one);
-    for (int i = 0; i < 8; i++) dst[i] = c.v[i];
-}
-// x^e for a small exponent
-__device__ __forceinline__ fr_t fr_pow_u32(const fr_t &x, uint32_t e) {
-    fr_t acc = fr_one();
-    bool started = false;
-    for (int i = 31; i >= 0; i--) {
-        if (started) acc = fr_mul(acc, acc);
-        if ((e >> i) & 1) {
-            acc = started ? fr_mul(acc, x) : x;
-            started = true;
-        }
-    }
-    return acc;
-}
-// s_i = prod_{j : bit (m-1-j) of i set} g_j
-__device__ __forceinline__ fr_t s_value(const uint32_t *g, uint32_t m, uint32_t i) {
-    fr_t acc = fr_one();
-    bool started = false;
-    for (uint32_t j = 0; j < m; j++)
-        if ((i >> (m - 1 - j)) & 1) {
-            const fr_t gj = fr_load(g + 8 * j);
-            acc = started ? fr_mul(acc, gj) : gj;
-            started = true;
-        }
-    return acc;
-}
-
-}  // namespace vcoef
-
-// positions inside a proof's challenge block (Montgomery scalars, 8 words each); the four challenge vectors follow at CH_VEC
-enum {
-    CH_RHO = 0, CH_ALPHA_SP = 12, CH_BETA_SP, CH_ALPHA_G, CH_BETA_INV, CH_ALPHA_I, CH_BETA_I, CH_Z, CH_C, CH_D, CH_X, CH_ALPHA_SM,
-    CH_ALPHA_SS, CH_ZK, CH_ZT, CH_ZU, CH_VEC = 27
-};
 
 // One thread of the CTA that serves proof `pr`.  chal: [B][vch][8], vec_a: [B][ell][8] canonical.  Outputs, canonical: the CRS slots
 // (< n + 5) go to out_crs[pr][n + 5], the per-proof slots (R, S, T, U, M, proof points) to out_var[pr * vw + slot] -- the same index the

@@ -113,6 +113,11 @@ struct VLane {
     // something that is not a base of the check: the CRS block, the gathered copies), so that msm(d_pts, d_vscal) over the whole array is
     // the merged check of the lane's batch; the 14 scalars of the exact SameScalar form [proof][14]
     uint8_t *d_cscal = nullptr, *d_vscal = nullptr, *d_escal = nullptr;
+    // device-side transcript (cdp_verify_transcript_{a,b}_dev): the proof's 7 scalars, scratch, D / A' encodings, identity flags, crs.H encoding,
+    // the merged check's result
+    uint8_t *d_pscal = nullptr, *h_pscal = nullptr, *d_vtmp = nullptr, *d_da = nullptr, *d_vflag = nullptr, *h_vflag = nullptr, *d_Hcomp = nullptr,
+            *d_mres = nullptr, *h_mres = nullptr;
+    bool dev_transcript = true;  // CDP_VERIFY_HOST_TRANSCRIPT=1: the per-round transcript and the challenges on the host (the older path)
     bool merged = true;   // CDP_VERIFY_MERGE=0: always one accumulated MSM per proof
     size_t n_merged = 0, n_fallback = 0;  // lane batches accepted by the merged check / re-checked proof by proof
     uint32_t *d_gsrc = nullptr, *d_gdst = nullptr, *d_isrc = nullptr, *d_idst = nullptr, *d_pdst = nullptr, *d_xsrc = nullptr, *d_xdst = nullptr;
@@ -139,10 +144,11 @@ void vlane_destroy(VLane *p) {
     cdp_ctx *c = p->ctx;
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_pcomp, (void *)p->d_status, (void *)p->d_gsrc,
                     (void *)p->d_gdst, (void *)p->d_isrc, (void *)p->d_idst, (void *)p->d_pdst, (void *)p->d_xsrc, (void *)p->d_xdst,
-                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_cscal, (void *)p->d_vscal, (void *)p->d_escal, (void *)p->d_jac,
+                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_cscal, (void *)p->d_vscal, (void *)p->d_escal, (void *)p->d_pscal, (void *)p->d_vtmp,
+                    (void *)p->d_da, (void *)p->d_vflag, (void *)p->d_Hcomp, (void *)p->d_mres, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_chal}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_chal, (void *)p->h_pscal, (void *)p->h_vflag, (void *)p->h_mres}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -154,6 +160,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->ctx = ctx; p->table = table; p->ell = ell; p->n = n; p->m = m; p->max_batch = max_batch; p->threads = std::max(1, host_threads);
     if (const char *e = getenv("CDP_VERIFY_EXACT_EQ")) p->exact_eq = atoi(e) != 0;
     if (const char *e = getenv("CDP_VERIFY_MERGE")) p->merged = atoi(e) != 0;
+    if (const char *e = getenv("CDP_VERIFY_HOST_TRANSCRIPT")) p->dev_transcript = atoi(e) == 0;
     ProofLayout L(m);
     p->np = L.np;
     const size_t cH = n, cGt = n + 1, cGu = n + 2, cGsum = n + 3, cHsum = n + 4;
@@ -188,6 +195,12 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->d_cscal = (uint8_t *)dalloc(max_batch * p->crs_n * 32);
     p->d_vscal = (uint8_t *)dalloc((total_pts + 1) * 32);
     p->d_escal = (uint8_t *)dalloc(max_batch * 14 * 32);
+    p->d_pscal = (uint8_t *)dalloc(max_batch * 7 * 32); p->h_pscal = (uint8_t *)halloc(max_batch * 7 * 32);
+    p->d_vtmp = (uint8_t *)dalloc(max_batch * 2 * 32);
+    p->d_da = (uint8_t *)dalloc(max_batch * 2 * 48);
+    p->d_vflag = (uint8_t *)dalloc(max_batch); p->h_vflag = (uint8_t *)halloc(max_batch);
+    p->d_Hcomp = (uint8_t *)dalloc(48);
+    p->d_mres = (uint8_t *)dalloc(48); p->h_mres = (uint8_t *)halloc(48);
     p->h_scal = (uint8_t *)halloc(max_batch * 6 * 32);  // stage A only: the coefficients of the accumulated check are computed on the device
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
     p->d_jac = (uint8_t *)dalloc((max_batch * (p->chunks + FSPLIT + 5) + 4) * 144);
@@ -257,6 +270,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
         rc |= cdp_h2d(ctx, p->d_pts, crs_points, (ell + 9) * 96);  // the CRS followed by sum(G), sum(Hvec) (cdp_verifier_create)
         rc |= cdp_h2d(ctx, p->d_pts + total_pts * 96, zero.data(), 96);
         rc |= cdp_dev_zero(ctx, p->d_vscal, (total_pts + 1) * 32);
+        rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_Hcomp);
         rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_comp);
         rc |= cdp_d2h(ctx, p->h_comp, p->d_comp, 48);
         rc |= cdp_sync(ctx);
@@ -268,8 +282,136 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     return CDP_OK;
 }
 
+// The per-proof decision: every proof's own accumulated sum = its per-proof part (one launch per 2048-point chunk) + its CRS part (already in
+// d_jac, [proof][part]); with CDP_VERIFY_EXACT_EQ the four SameScalar equalities as exact MSMs.  Leaves the encodings in h_comp after a sync.
+int per_proof_stage(VLane *p, size_t B, double &t_wait) {
+    const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + FSPLIT;
+    for (size_t c = 0; c < p->chunks; c++) {
+        size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
+        VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_vscal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
+    }
+    // accumulated sum of proof pr = its chunk sums [chunk][pr] + its CRS parts [pr][part]
+    VTRY(cdp_sum_groups2_dev(p->ctx, p->d_jac, p->chunks, B, 1, p->d_jac + p->chunks * B * 144, FSPLIT, 1, FSPLIT, B, p->d_jac + NS * B * 144));
+    const size_t n_res = p->exact_eq ? 5 * B : B;
+    if (p->exact_eq) VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_escal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
+    // results: [B accumulated sums] ([4B equalities])
+    VTRY(cdp_normalize_dev(p->ctx, p->d_jac + NS * B * 144, n_res, nullptr, p->d_comp));
+    VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, n_res * 48));
+    double t0 = now_ms();
+    VTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
+    return CDP_OK;
+}
+bool enc_is_inf(const uint8_t *c) {
+    if (c[0] != 0xC0) return false;
+    for (int i = 1; i < 48; i++) if (c[i]) return false;
+    return true;
+}
+// the merged check of a sub-batch: per-proof bases of all proofs in one MSM + the summed CRS parts -> one encoding in d_mres (no sync)
+int merged_stage(VLane *p, size_t B) {
+    uint8_t *d_m = p->d_jac + (p->max_batch * (p->chunks + FSPLIT + 5)) * 144;  // 4 spare points
+    VTRY(cdp_msm_dev(p->ctx, p->d_pts + p->crs_n * 96, p->d_vscal + p->crs_n * 32, B * p->VW, d_m));
+    VTRY(cdp_sum_jacobian_dev(p->ctx, p->d_jac + p->chunks * B * 144, FSPLIT * B, d_m + 144));
+    VTRY(cdp_sum_jacobian_dev(p->ctx, d_m, 2, d_m + 288));
+    VTRY(cdp_normalize_dev(p->ctx, d_m + 288, 1, nullptr, p->d_mres));
+    VTRY(cdp_d2h(p->ctx, p->h_mres, p->d_mres, 48));
+    return CDP_OK;
+}
+
+// `deserialize` + `verify` with the whole transcript and all scalar algebra on the device: the host parses and stages the inputs and
+// draws the random factors; ONE synchronisation at the end (a second one only when the merged check does not accept the sub-batch).
+int vlane_verify_dev(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
+    const double t_start = now_ms();
+    double t_host = 0, t_wait = 0, t0 = now_ms();
+    const size_t ell = p->ell, n = p->n, m = p->m, NP = p->np;
+    const int T = p->threads;
+    const size_t psz = cdp_proof_size(ell), Moff = p->max_batch * 4 * ell;
+    memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
+    parallel_for(T, B, [&](size_t pr) {
+        uint8_t *dst = p->h_in + pr * 4 * ell * 96;
+        memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
+        memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
+        memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
+        memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
+        VState &s = p->vs[pr];
+        s.status = 1;
+        // proof parsing (curdleproofs.rs:311-323 and the per-argument deserialisers): points -> h_pcomp in serialisation order, the seven
+        // scalars -> h_pscal (r_p, c_final, d_final, z_k, z_t, z_u, x_final); a scalar >= r does not deserialise
+        const uint8_t *r = in->proofs + pr * psz;
+        uint8_t *pc = p->h_pcomp + pr * NP * 48, *ps = p->h_pscal + pr * 7 * 32;
+        size_t k = 0, q = 0;
+        auto pts = [&](size_t cnt) { memcpy(pc + 48 * k, r, 48 * cnt); k += cnt; r += 48 * cnt; };
+        auto fr = [&]() { Fr x; if (!Fr::from_bytes(r, x)) s.status = 2; memcpy(ps + 32 * q, r, 32); q++; r += 32; };
+        pts(9); fr(); pts(2 + 4 * m); fr(); fr(); pts(4); fr(); fr(); fr(); pts(3 + 6 * m); fr();
+        // one random factor per accumulate_check (msm_accumulator.rs:44), in call order; 8..11: the SameScalar equalities
+        StdRng rng(in->rng_seed ? in->rng_seed[pr] : 0x9e3779b97f4a7c15ULL + pr);
+        Fr *ch = reinterpret_cast<Fr *>(p->h_chal + pr * p->vch * 32);
+        for (int i = 0; i < 12; i++) ch[i] = rng.fr_rand();
+    });
+    t_host += now_ms() - t0;
+    if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host staging: %.2f ms (B=%zu)\n", now_ms() - t0, B);
+    VTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+    VTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
+    VTRY(cdp_h2d(p->ctx, p->d_pcomp, p->h_pcomp, B * NP * 48));
+    VTRY(cdp_h2d(p->ctx, p->d_pscal, p->h_pscal, B * 7 * 32));
+    VTRY(cdp_h2d(p->ctx, p->d_chal, p->h_chal, B * p->vch * 32));
+    VTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));
+    VTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_pp));
+    VTRY(cdp_decompress_dev(p->ctx, p->d_pcomp, p->d_pdst, B * NP, p->d_pts, p->d_status));
+    VTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_xsrc, p->d_xdst, B * p->x_pp));
+    VTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp));
+    uint8_t *d_Mcomp = p->d_comp + B * 4 * ell * 48;
+    VTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, d_Mcomp));
+    // the transcript: opening -> same_perm / gprod -> (D, A' on the GPU) -> IPA / SameScalar / SameMSM -> the coefficients
+    VTRY(cdp_transcript_open_dev(p->ctx, p->d_comp, d_Mcomp, ell, B, p->d_veca, p->d_tstate));
+    VTRY(cdp_verify_transcript_a_dev(p->ctx, p->d_pcomp, p->d_pscal, p->d_comp, d_Mcomp, p->d_veca, ell, B, p->d_tstate, p->d_chal, p->d_vtmp, p->d_scal,
+                                     p->d_vflag));
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, p->d_segAf, 2 * B, 2 * B, p->d_pts, p->d_jac));
+    VTRY(cdp_normalize_dev(p->ctx, p->d_jac, 2 * B, nullptr, p->d_da));
+    VTRY(cdp_verify_transcript_b_dev(p->ctx, p->d_pcomp, p->d_pscal, p->d_comp, p->d_da, p->d_Hcomp, ell, B, p->d_tstate, p->d_chal, p->d_vtmp));
+    {
+        cdp_vcoef_params vp = {(uint32_t)ell, (uint32_t)n, (uint32_t)m, (uint32_t)p->big_n, (uint32_t)p->VW, (uint32_t)p->o_R, (uint32_t)p->o_S,
+                               (uint32_t)p->o_T, (uint32_t)p->o_U, (uint32_t)p->o_M, (uint32_t)p->o_P, p->exact_eq ? 1u : 0u, (uint32_t)p->vch};
+        VTRY(cdp_verify_coeffs_dev(p->ctx, p->d_chal, p->d_veca, &vp, B, p->d_cscal, p->d_vscal, p->d_escal));
+    }
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
+    // the merged check is launched before the decompression statuses are known; its result only counts for a sub-batch without a
+    // malformed or already rejected proof (such a proof's points must not enter the sum)
+    const bool try_merged = p->merged && !p->exact_eq && B >= 2;
+    if (try_merged) VTRY(merged_stage(p, B));
+    VTRY(cdp_d2h(p->ctx, p->h_status, p->d_status, B * NP));
+    VTRY(cdp_d2h(p->ctx, p->h_vflag, p->d_vflag, B));
+    t0 = now_ms();
+    VTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
+    bool clean = true;
+    for (size_t pr = 0; pr < B; pr++) {
+        VState &s = p->vs[pr];
+        const uint8_t *st = p->h_status + pr * NP;
+        for (size_t i = 0; i < NP; i++) if (st[i]) s.status = 2;  // a proof point failed `deserialize_compressed`
+        if (p->h_vflag[pr] && s.status == 1) s.status = 0;       // vec_T[0] is the identity -> Err (curdleproofs.rs:218-220)
+        clean = clean && s.status == 1;
+    }
+    bool decided = try_merged && clean && enc_is_inf(p->h_mres);
+    if (try_merged && clean) { if (decided) p->n_merged++; else p->n_fallback++; }  // a sub-batch with a malformed proof never counted on the merged result
+    if (!decided) {
+        VTRY(per_proof_stage(p, B, t_wait));
+        for (size_t pr = 0; pr < B; pr++) {
+            VState &s = p->vs[pr];
+            bool okk = enc_is_inf(p->h_comp + pr * 48);
+            if (p->exact_eq)
+                for (int e = 0; e < 4; e++) okk = okk && enc_is_inf(p->h_comp + (B + 4 * pr + e) * 48);
+            if (s.status == 1 && !okk) s.status = 0;
+        }
+    }
+    for (size_t pr = 0; pr < B; pr++) ok_out[pr] = (uint8_t)p->vs[pr].status;
+    p->timing[0] = now_ms() - t_start; p->timing[1] = t_host; p->timing[2] = t_wait;
+    return CDP_OK;
+}
+
 int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
     if (B == 0) return CDP_OK;
+    if (p->dev_transcript) return vlane_verify_dev(p, B, in, ok_out);
     const double t_start = now_ms();
     double t_host = 0, t_wait = 0, t0 = now_ms();
     const size_t ell = p->ell, n = p->n, m = p->m, NP = p->np;
@@ -423,8 +565,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         ch[19] = s.c_final; ch[20] = s.d_final; ch[21] = s.x_final; ch[22] = alpha_sm; ch[23] = alpha_ss; ch[24] = s.z_k; ch[25] = s.z_t; ch[26] = s.z_u;
         for (size_t k = 0; k < m; k++) { ch[27 + k] = s.gam[k]; ch[27 + m + k] = s.gam_inv[k]; ch[27 + 2 * m + k] = s.gam2[k]; ch[27 + 3 * m + k] = s.gam2_inv[k]; }
     });
-    // ---- final stage: per-proof part (one launch per 2048-point chunk) + CRS part (digit table) -> added per proof; the equalities
-    const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + FSPLIT;
+    // ---- final stage
     t_host += now_ms() - t0;
     if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host part 3: %.2f ms (B=%zu)\n", now_ms() - t0, B);
     VTRY(cdp_h2d(p->ctx, p->d_chal, p->h_chal, B * p->vch * 32));
@@ -435,11 +576,6 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     }
     // CRS part of every proof's check through the digit table: partial sums [proof][part]
     VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
-    auto is_inf = [](const uint8_t *c) {
-        if (c[0] != 0xC0) return false;
-        for (int i = 1; i < 48; i++) if (c[i]) return false;
-        return true;
-    };
     // ---- merged check of the lane's batch (SURVEY.md 8(f) rank 3 / BASELINE config 3): every check of every proof already carries its own
     //      independent random factor, so the sum over the batch is again one random linear combination -- the MsmAccumulator argument
     //      (msm_accumulator.rs:55-68) applied to 12 B checks instead of 12.  d_vscal is indexed like d_pts, so the per-proof bases of the
@@ -450,16 +586,11 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
     bool clean = true;
     for (size_t pr = 0; pr < B; pr++) clean = clean && p->vs[pr].status == 1;
     if (p->merged && !p->exact_eq && clean && B >= 2) {
-        uint8_t *d_m = p->d_jac + (p->max_batch * (p->chunks + FSPLIT + 5)) * 144;  // 4 spare points
-        VTRY(cdp_msm_dev(p->ctx, p->d_pts + p->crs_n * 96, p->d_vscal + p->crs_n * 32, B * p->VW, d_m));
-        VTRY(cdp_sum_jacobian_dev(p->ctx, p->d_jac + p->chunks * B * 144, FSPLIT * B, d_m + 144));
-        VTRY(cdp_sum_jacobian_dev(p->ctx, d_m, 2, d_m + 288));
-        VTRY(cdp_normalize_dev(p->ctx, d_m + 288, 1, nullptr, p->d_comp));
-        VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, 48));
+        VTRY(merged_stage(p, B));
         t0 = now_ms();
         VTRY(cdp_sync(p->ctx));
         t_wait += now_ms() - t0;
-        decided = is_inf(p->h_comp);
+        decided = enc_is_inf(p->h_mres);
         if (decided) p->n_merged++; else p->n_fallback++;
     }
     if (decided) {
@@ -467,26 +598,12 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         p->timing[0] = now_ms() - t_start; p->timing[1] = t_host; p->timing[2] = t_wait;
         return CDP_OK;
     }
-    // ---- per-proof path: the per-proof part (one launch per 2048-point chunk) added to the proof's CRS part; the exact equalities
-    for (size_t c = 0; c < p->chunks; c++) {
-        size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
-        VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_vscal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
-    }
-    // accumulated sum of proof pr = its chunk sums [chunk][pr] + its CRS parts [pr][part]
-    VTRY(cdp_sum_groups2_dev(p->ctx, p->d_jac, p->chunks, B, 1, p->d_jac + p->chunks * B * 144, FSPLIT, 1, FSPLIT, B, p->d_jac + NS * B * 144));
-    const size_t n_res = p->exact_eq ? 5 * B : B;
-    if (p->exact_eq) VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_escal, p->d_segE, 4 * B, 4, 14 * B, p->d_jac + (NS + 1) * B * 144));
-    // results: [B accumulated sums] ([4B equalities])
-    VTRY(cdp_normalize_dev(p->ctx, p->d_jac + NS * B * 144, n_res, nullptr, p->d_comp));
-    VTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, n_res * 48));
-    t0 = now_ms();
-    VTRY(cdp_sync(p->ctx));
-    t_wait += now_ms() - t0;
+    VTRY(per_proof_stage(p, B, t_wait));
     for (size_t pr = 0; pr < B; pr++) {
         VState &s = p->vs[pr];
-        bool okk = is_inf(p->h_comp + pr * 48);
+        bool okk = enc_is_inf(p->h_comp + pr * 48);
         if (p->exact_eq)
-            for (int e = 0; e < 4; e++) okk = okk && is_inf(p->h_comp + (B + 4 * pr + e) * 48);
+            for (int e = 0; e < 4; e++) okk = okk && enc_is_inf(p->h_comp + (B + 4 * pr + e) * 48);
         if (s.status == 1 && !okk) s.status = 0;
         ok_out[pr] = (uint8_t)s.status;
     }

@@ -209,6 +209,23 @@ int cdp_compress_affine_dev(cdp_ctx *ctx, const uint8_t *d_pts, const uint32_t *
 int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs, const uint8_t *d_comp_M, size_t ell, size_t batch, uint8_t *d_vec_a,
                             uint8_t *d_state);
 
+/* The rest of the VERIFIER's transcript on the device, one thread per proof, continuing the state cdp_transcript_open_dev left
+ * (`CurdleproofsProof::verify`, /root/reference/src/curdleproofs.rs:226-296, and the `verify` of the five arguments it calls: they only append
+ * proof points / scalars and draw challenges).  Two steps, because the transcript needs D and A' from the GPU in between:
+ *   _a: same_perm and gprod up to the gprod beta; writes challenge-block entries 12..15 (cdp_verify_coeffs_dev), d_tmp (batch x 2 scalars: the
+ *       grand product and beta, for _b), d_stage_scalars (batch x 6 canonical: {1, -beta^-1, alpha_g, 1, 1, 1}, the scalars of
+ *       D = B - beta^-1 sum(G) + alpha_g sum(Hvec) and A' = A + T_1 + U_1) and d_flags (batch bytes: 1 when vec_T[0] is the identity);
+ *   _b: z, IPA, SameScalar, SameMSM; inverts the round challenges; completes entries 16..26 and the four challenge vectors.
+ * d_proof_points: batch x (18 + 10 m) encodings, the proof's points in serialisation order; d_proof_scalars: batch x 7 canonical scalars
+ * (r_p, c_final, d_final, z_k, z_t, z_u, x_final); d_comp_vecs / d_comp_M / d_vec_a: as in cdp_transcript_open_dev; d_comp_DA: batch x 2
+ * encodings (D, A'); d_comp_H: the encoding of crs.H; d_state: batch x 208 bytes, in/out. */
+int cdp_verify_transcript_a_dev(cdp_ctx *ctx, const uint8_t *d_proof_points, const uint8_t *d_proof_scalars, const uint8_t *d_comp_vecs,
+                                const uint8_t *d_comp_M, const uint8_t *d_vec_a, size_t ell, size_t batch, uint8_t *d_state, uint8_t *d_challenges,
+                                uint8_t *d_tmp, uint8_t *d_stage_scalars, uint8_t *d_flags);
+int cdp_verify_transcript_b_dev(cdp_ctx *ctx, const uint8_t *d_proof_points, const uint8_t *d_proof_scalars, const uint8_t *d_comp_vecs,
+                                const uint8_t *d_comp_DA, const uint8_t *d_comp_H, size_t ell, size_t batch, uint8_t *d_state, uint8_t *d_challenges,
+                                const uint8_t *d_tmp);
+
 /* Verifier scalar preparation on the device: from a proof's Fiat-Shamir challenges to the coefficient of every
  * base of its accumulated check -- the verification scalars s_i / 1/s_i of `get_verification_scalars_bitstring`
  * (/root/reference/src/util.rs:40-64, used at src/inner_product_argument.rs:202-250 and src/same_multiscalar_argument.rs:242-259),

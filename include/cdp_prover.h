@@ -70,7 +70,8 @@ void cdp_prover_last_timing(const cdp_prover *p, double out_ms[4]);
  * Proof points are decompressed and subgroup-checked on the GPU; the eight accumulated checks of a proof become one MSM
  * over [CRS | R | S | T | U | M | proof points] compared with the identity (the reference's MsmAccumulator, without the
  * HashMap); SameScalar's four point equalities join that check with their own random factors (CDP_VERIFY_EXACT_EQ=1: four exact MSMs).
- * The coefficients are computed on the device (cdp_verify_coeffs_dev).  By default a lane first runs the MERGED check of its whole
+ * The transcript (cdp_transcript_open_dev, cdp_verify_transcript_{a,b}_dev; CDP_VERIFY_HOST_TRANSCRIPT=1 keeps the per-round part on the
+ * host) and the coefficients (cdp_verify_coeffs_dev) are computed on the device.  By default a lane first runs the MERGED check of its whole
  * sub-batch -- the per-proof bases of all its proofs in ONE large MSM plus the summed CRS parts, every check already carrying its own
  * random factor -- and accepts all of them when that is the identity; otherwise (or when a proof of the sub-batch is malformed) every
  * proof is decided by its own accumulated MSM, so the verdicts never depend on the mode.  CDP_VERIFY_MERGE=0 disables the merged check. */

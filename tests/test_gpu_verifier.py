@@ -180,3 +180,25 @@ def test_verifier_merged_check_and_fallback(engine, oracle, proved, monkeypatch)
     assert bv.verify_batch(bi, bp_) == [1] * B
     assert bv.merge_stats() == {"merged": 0, "fallback": 0}
     bv.close()
+
+
+def test_verifier_host_transcript_path_agrees(engine, oracle, proved, monkeypatch):
+    """CDP_VERIFY_HOST_TRANSCRIPT=1 keeps the per-round transcript and the challenges on the host (the older path): same verdicts as the
+    default device-side transcript on valid, tampered and malformed proofs."""
+    from curdleproofs_b200 import BatchVerifier
+    ell, crs, insts, proofs = proved
+    bad = proofs[1][:-32] + pr.fr_to_bytes((int.from_bytes(proofs[1][-32:], "little") + 1) % pr.R_ORDER)
+    too_big = proofs[2][:-32] + (pr.R_ORDER + 5).to_bytes(32, "little")          # x_final >= r: does not deserialise
+    broken = bytearray(proofs[3]); broken[48 * 5 + 20] ^= 0x55
+    inf_T = dict(insts[0], T=bytes(96) + insts[0]["T"][96:])
+    cases_i = [insts[0], insts[1], insts[2], insts[3], inf_T, insts[1]]
+    cases_p = [proofs[0], bad, too_big, bytes(broken), proofs[0], proofs[1]]
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CDP_VERIFY_HOST_TRANSCRIPT", mode)
+        bv = BatchVerifier(engine, ell, crs, max_batch=8, lanes=1)
+        res[mode] = bv.verify_batch(cases_i, cases_p, rng_seeds=[11, 12, 13, 14, 15, 16])
+        assert bv.verify_batch(insts, proofs) == [1, 1, 1, 1]
+        bv.close()
+    assert res["0"] == res["1"]
+    assert res["0"][0] == 1 and res["0"][1] == 0 and res["0"][2] == 2 and res["0"][3] in (0, 2) and res["0"][4] == 0 and res["0"][5] == 1

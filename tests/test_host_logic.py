@@ -75,3 +75,15 @@ def test_device_verifier_scalar_code_matches_host_restatement_on_cpu():
         out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count(" ok ") == 8
+
+
+def test_device_verifier_transcript_code_matches_host_transcript_on_cpu():
+    """The device verifier-transcript kernels (k_verify_transcript_a / _b in csrc/k_transcript.cu, compiled as plain C++) against the
+    product's host merlin / Fr following `CurdleproofsProof::verify` (/root/reference/src/curdleproofs.rs:226-296): every challenge, the
+    inverted round challenges, z, the stage scalars, the identity flag of vec_T[0] and the final STROBE state; ell = 12 / 124 / 252."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "vtc")
+        subprocess.run(["g++", "-O1", "-march=x86-64-v3", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/vtranscript_check.cpp")], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count(" ok ") == 3
