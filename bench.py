@@ -193,7 +193,7 @@ def main():
     rnd.seed(7777 + rank)  # rank-specific instances, shared CRS
     insts = build_batch(eng, crs, ell, B, rnd, g, fr, rs)
     # host threads: the box's cores are shared by the ranks of this node (one process per GPU)
-    host_threads = max(8, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    host_threads = max(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))  # >= 2 per lane
     bp = BatchProver(eng, ell, crs, max_batch=B, lanes=args.lanes, host_threads=host_threads)
 
     import ctypes

@@ -676,7 +676,7 @@ extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell,
             v->owned.push_back(c);
         }
         VLane *l = nullptr;
-        int rc = vlane_create(&l, c, v->table, ell, crs_ext.data(), per_lane, std::max(1, host_threads / lanes));
+        int rc = vlane_create(&l, c, v->table, ell, crs_ext.data(), per_lane, std::max(1, (host_threads + lanes - 1) / lanes));
         if (rc != CDP_OK) { cdp_verifier_destroy(v); return rc; }
         v->lanes.push_back(l);
     }

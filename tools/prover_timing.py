@@ -9,12 +9,13 @@ from curdleproofs_b200 import Engine, BatchProver
 ell = int(sys.argv[1]) if len(sys.argv) > 1 else 252
 batches = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [16, 64, 256]
 lanes = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+host_threads = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 oracle = oracle_lib.Oracle()
 crs = oracle.crs_points(ell)
 inst = oracle.random_instance(ell, crs, seed=1, threads=8)
 eng = Engine(0)
 for B in batches:
-    bp = BatchProver(eng, ell, crs, max_batch=B, lanes=lanes)
+    bp = BatchProver(eng, ell, crs, max_batch=B, lanes=lanes, host_threads=host_threads)
     insts = [inst] * B
     seeds = list(range(B))
     proofs = bp.prove_batch(insts, seeds)  # warm-up
