@@ -484,7 +484,7 @@ static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d
     size_t o_keys = 0, o_vals = o_keys + al(items * 4), o_keys2 = o_vals + al(items * 4), o_vals2 = o_keys2 + al(items * 4),
            o_start = o_vals2 + al(items * 4), o_bjac = o_start + al((size_t)nwin * (nb + 1) * 4), o_top = o_bjac + al(slots * 144),
            o_A0 = o_top + al((size_t)nb * 144), o_B0 = o_A0 + al(lvl * 144), o_A1 = o_B0 + al(lvl * 144), o_B1 = o_A1 + al(lvl * 144),
-           o_tmp = o_B1 + al(lvl * 144), total = o_tmp + al(sort_tmp);
+           o_tmp = o_B1 + al(lvl * 144), o_heavy = o_tmp + al(sort_tmp), total = o_heavy + al(big_heavy_bytes(n2, nwin));
     TRY(ensure_dev(ctx, ctx->d_big, total));
     uint8_t *ws = (uint8_t *)ctx->d_big.ptr;
     uint32_t *keys = (uint32_t *)(ws + o_keys), *vals = (uint32_t *)(ws + o_vals), *keys2 = (uint32_t *)(ws + o_keys2), *vals2 = (uint32_t *)(ws + o_vals2);
@@ -493,7 +493,7 @@ static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, n); CUDA_TRY(ctx, launch_big_digits(ctx->stream, P, S, (uint32_t)n, c, nwin, keys, vals)); }
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_sort(ctx->stream, ws + o_tmp, sort_tmp, keys, keys2, vals, vals2, n2, nwin, c, nullptr)); }
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_offsets(ctx->stream, keys2, n2, nwin, nb, c, start)); }
-    { launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, (uint64_t)n); CUDA_TRY(ctx, launch_big_accumulate(ctx->stream, P, vals2, start, n2, nwin, nb, sp_top, 1, bjac)); }
+    { launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, (uint64_t)n); CUDA_TRY(ctx, launch_big_accumulate(ctx->stream, P, vals2, start, n2, nwin, nb, sp_top, 1, bjac, ws + o_heavy)); }
     // top window: fold the sp_top partial sums of each bucket (two steps when a bucket has many), back into the window's slot array
     {
         uint32_t *top_slots = bjac + 36 * (size_t)(nwin - 1) * nb, *tmp = (uint32_t *)(ws + o_top);

@@ -86,9 +86,18 @@ __global__ void __launch_bounds__(256) k_big_offsets(const uint32_t *__restrict_
 // Every window owns nb slots (threads).  In an ordinary window slot = bucket.  The top window only sees the few leftover
 // bits (plus the recoding carry), i.e. a handful of very long buckets: there slot = (bucket, s) and the sp_top threads of a
 // bucket take every sp_top-th point, producing sp_top partial sums that all carry the bucket's weight.
+// A bucket with more than BIG_HEAVY points (skewed scalars: all-equal scalars put ALL points of a window into one bucket, 32-bit scalars put
+// half of them into the carry bucket of the third window) is not run by its one thread -- that would be seconds of sequential additions --
+// but cut into chunks of BIG_CHUNK points, appended to a device-side work list and summed by k_big_heavy (one CTA per chunk) and
+// k_big_heavy_fold (one warp per heavy bucket).  Uniform scalars never take this path: buckets hold ~2n / 2^(c-1) <= 256 points.
+constexpr uint32_t BIG_HEAVY = 2048, BIG_CHUNK = 4096;
+struct big_heavy_item_t {
+    uint32_t slot, lo, hi, first;  // bucket slot (index into buckets_jac), range in the window's sorted array, first item of this bucket in the list
+};
 __global__ void __launch_bounds__(128) k_big_accumulate(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted,
                                                         const uint32_t *__restrict__ start, uint32_t n2, int nwin, uint32_t nb, uint32_t sp_top,
-                                                        uint32_t chunks, uint32_t *__restrict__ buckets_jac) {
+                                                        uint32_t chunks, uint32_t *__restrict__ buckets_jac, uint32_t *__restrict__ heavy_count,
+                                                        big_heavy_item_t *__restrict__ heavy_items, uint32_t heavy_cap) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)nwin * nb) return;
     uint32_t w = (uint32_t)(t / nb), slot = (uint32_t)(t % nb);
@@ -100,6 +109,26 @@ __global__ void __launch_bounds__(128) k_big_accumulate(const uint32_t *__restri
     const uint32_t *v = vals_sorted + (size_t)w * n2;
     g1j acc;
     g1j_set_inf(acc);
+    // heavy bucket (per-thread share above BIG_HEAVY; in the top window a bucket is already spread over sp_top threads): the thread of
+    // its first slot appends the bucket's chunks to the work list, every thread of the bucket leaves infinity in its slot
+    const uint32_t blo = st[b], cnt = hi > blo ? hi - blo : 0u;
+    if (cnt / stride > BIG_HEAVY) {
+        const uint32_t nch = (cnt + BIG_CHUNK - 1) / BIG_CHUNK;
+        bool listed = true;
+        if (first == 0) {
+            const uint32_t base = atomicAdd(heavy_count, nch);
+            listed = base + nch <= heavy_cap;  // always true: the list is sized for the worst case
+            if (listed)
+                for (uint32_t j = 0; j < nch; j++) {
+                    const uint32_t clo = blo + j * BIG_CHUNK, chi = clo + BIG_CHUNK < hi ? clo + BIG_CHUNK : hi;
+                    heavy_items[base + j] = {(uint32_t)t, clo, chi, j == 0 ? 0x80000000u : 0u};
+                }
+        }
+        if (listed) {
+            g1j_store(buckets_jac + 36 * t, acc);  // infinity; k_big_heavy_fold writes the bucket's sum into its first slot
+            return;
+        }
+    }
 #pragma unroll 1
     for (uint32_t e = lo; e < hi; e += stride) {
         uint32_t id = v[e];
@@ -112,6 +141,83 @@ __global__ void __launch_bounds__(128) k_big_accumulate(const uint32_t *__restri
     }
     (void)chunks;
     g1j_store(buckets_jac + 36 * t, acc);
+}
+
+// One CTA per work item (a chunk of <= BIG_CHUNK points of one heavy bucket): the 128 threads stride over the chunk with mixed additions,
+// then a shuffle / shared-memory reduction; partial sum to heavy_partial[item].  The grid is sized for the worst case; CTAs beyond the
+// list's length leave at once.
+__global__ void __launch_bounds__(128) k_big_heavy(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted, uint32_t n2,
+                                                   uint32_t nb, const uint32_t *__restrict__ heavy_count,
+                                                   const big_heavy_item_t *__restrict__ heavy_items, uint32_t heavy_cap,
+                                                   uint32_t *__restrict__ heavy_partial) {
+    const uint32_t count = *heavy_count < heavy_cap ? *heavy_count : heavy_cap;
+    __shared__ uint32_t sm[4 * 36];
+    for (uint32_t item = blockIdx.x; item < count; item += gridDim.x) {
+        const big_heavy_item_t it = heavy_items[item];
+        const uint32_t w = it.slot / nb;
+        const uint32_t *v = vals_sorted + (size_t)w * n2;
+        g1j acc;
+        g1j_set_inf(acc);
+#pragma unroll 1
+        for (uint32_t e = it.lo + threadIdx.x; e < it.hi; e += blockDim.x) {
+            const uint32_t id = v[e], p = id & 0x7FFFFFFFu;
+            g1a q;
+            g1a_load(q, pts + 24 * (size_t)(p >> 1));
+            if (p & 1) fp_mul_beta(q.x, q.x);
+            if (id & 0x80000000u) fp_neg(q.y, q.y);
+            g1j_add_mixed(acc, acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            g1j o;
+            shfl_down_g1j(o, acc, d, 32);
+            g1j_add(acc, acc, o);
+        }
+        __syncthreads();  // the previous item's readers are done with sm
+        if ((threadIdx.x & 31) == 0) g1j_store(sm + 36 * (threadIdx.x >> 5), acc);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            g1j_load(acc, sm);
+#pragma unroll 1
+            for (int k = 1; k < 4; k++) {
+                g1j o;
+                g1j_load(o, sm + 36 * k);
+                g1j_add(acc, acc, o);
+            }
+            g1j_store(heavy_partial + 36 * (size_t)item, acc);
+        }
+    }
+}
+// One warp per work item that is the FIRST chunk of its bucket: sums the bucket's partial sums (its items are contiguous in the list: the
+// bucket's chunk count follows from its point range) into the bucket's slot.
+__global__ void __launch_bounds__(128) k_big_heavy_fold(const uint32_t *__restrict__ heavy_count, const big_heavy_item_t *__restrict__ heavy_items,
+                                                        uint32_t heavy_cap, const uint32_t *__restrict__ start, uint32_t nb,
+                                                        const uint32_t *__restrict__ heavy_partial, uint32_t *__restrict__ buckets_jac) {
+    const uint32_t count = *heavy_count < heavy_cap ? *heavy_count : heavy_cap;
+    const uint32_t lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (uint32_t item = blockIdx.x * wpb + (threadIdx.x >> 5); item < count; item += gridDim.x * wpb) {
+        const big_heavy_item_t it = heavy_items[item];
+        if (!(it.first & 0x80000000u)) continue;  // warp-uniform
+        const uint32_t w = it.slot / nb, b = it.slot % nb;
+        const uint32_t *st = start + (size_t)w * (nb + 1);
+        const uint32_t nch = (st[b + 1] - st[b] + BIG_CHUNK - 1) / BIG_CHUNK;
+        g1j acc;
+        g1j_set_inf(acc);
+#pragma unroll 1
+        for (uint32_t j = lane; j < ((nch + 31) & ~31u); j += 32) {
+            g1j q;
+            g1j_set_inf(q);
+            if (j < nch) g1j_load(q, heavy_partial + 36 * (size_t)(item + j));
+            g1j_add(acc, acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) {
+            g1j o;
+            shfl_down_g1j(o, acc, d, 32);
+            g1j_add(acc, acc, o);
+        }
+        if (lane == 0) g1j_store(buckets_jac + 36 * (size_t)it.slot, acc);
+    }
 }
 
 // One level of the hierarchical bucket reduction.  Every node carries A = sum of its buckets and Bv = sum of (local index) * bucket.
@@ -265,10 +371,29 @@ cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uin
     k_big_offsets<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys_sorted, n2, nwin, nb, c, start);
     return cudaGetLastError();
 }
+size_t big_heavy_capacity(uint32_t n2, int nwin) {  // worst case: every bucket's last chunk is partial, at most items / BIG_HEAVY heavy buckets
+    const size_t items = (size_t)n2 * nwin;
+    return items / BIG_CHUNK + items / BIG_HEAVY + 16;
+}
+size_t big_heavy_bytes(uint32_t n2, int nwin) {  // counter (256 B) + work list + partial sums
+    const size_t cap = big_heavy_capacity(n2, nwin);
+    return 256 + ((cap * sizeof(big_heavy_item_t) + 255) & ~size_t(255)) + cap * 144;
+}
 cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
-                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac) {
+                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac, void *heavy_ws) {
     size_t total = (size_t)nwin * nb;
-    k_big_accumulate<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pts, vals_sorted, start, n2, nwin, nb, sp_top, chunks, buckets_jac);
+    const size_t cap = big_heavy_capacity(n2, nwin);
+    uint32_t *count = reinterpret_cast<uint32_t *>(heavy_ws);
+    big_heavy_item_t *items = reinterpret_cast<big_heavy_item_t *>(reinterpret_cast<uint8_t *>(heavy_ws) + 256);
+    uint32_t *partial = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(heavy_ws) + 256 + ((cap * sizeof(big_heavy_item_t) + 255) & ~size_t(255)));
+    cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    k_big_accumulate<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pts, vals_sorted, start, n2, nwin, nb, sp_top, chunks, buckets_jac, count, items,
+                                                                      (uint32_t)cap);
+    // skewed inputs only: with uniform scalars the list is empty and both kernels return at once (grid-stride over the list)
+    const unsigned grid = (unsigned)(cap < 148 * 12 ? cap : 148 * 12);
+    k_big_heavy<<<grid, 128, 0, st>>>(pts, vals_sorted, n2, nb, count, items, (uint32_t)cap, partial);
+    k_big_heavy_fold<<<148, 128, 0, st>>>(count, items, (uint32_t)cap, start, nb, partial, buckets_jac);
     return cudaGetLastError();
 }
 cudaError_t launch_big_weights(cudaStream_t st, uint32_t *w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks) {

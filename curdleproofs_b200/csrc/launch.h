@@ -83,8 +83,9 @@ cudaError_t launch_big_digits(cudaStream_t st, const uint32_t *pts, const uint32
 cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, const uint32_t *keys, uint32_t *keys_out, const uint32_t *vals,
                             uint32_t *vals_out, uint32_t n2, int nwin, int c, const uint32_t *seg_offsets);
 cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c, uint32_t *start);
+size_t big_heavy_bytes(uint32_t n2, int nwin);
 cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
-                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac);
+                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac, void *heavy_ws);
 cudaError_t launch_big_weights(cudaStream_t st, uint32_t *w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks);
 cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
                                     uint32_t *Bout);

@@ -201,3 +201,24 @@ def test_msm_large_pippenger(engine, oracle, pool, n):
     sc[32 * 50:32 * 51] = pr.fr_to_bytes(pr.R_ORDER - 1)
     pts, sc = bytes(pts), bytes(sc)
     assert oracle.compress_jac(engine.msm(pts, sc)) == oracle.compress_jac(oracle.msm(pts, sc, threads=8))
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "small32", "half_shared", "two_values"])
+def test_msm_large_pippenger_skewed_scalars(engine, oracle, pool, kind):
+    """Skewed scalar distributions on the large-Pippenger path (BASELINE config 5's extra distributions; the all-equal case is the
+    SamePerm MSM shape, /root/reference/src/same_permutation_argument.rs:75-76): whole windows collapse into one bucket, which goes
+    through the heavy-bucket work list (k_big_heavy / k_big_heavy_fold, also for the top window).  Bit-exact vs the oracle."""
+    n = 16384 + 123
+    rnd = random.Random(hash(kind) & 0xFFFF)
+    pts = (pool * (n // 2100 + 1))[:96 * n]
+    one = pr.fr_to_bytes(rnd.randrange(1, pr.R_ORDER))
+    if kind == "all_equal":
+        sc = one * n
+    elif kind == "small32":
+        sc = b"".join(pr.fr_to_bytes(rnd.randrange(1 << 32)) for _ in range(n))
+    elif kind == "half_shared":
+        sc = b"".join(one if i % 2 else pr.fr_to_bytes(rnd.randrange(pr.R_ORDER)) for i in range(n))
+    else:
+        two = pr.fr_to_bytes(pr.R_ORDER - 2)
+        sc = b"".join(one if rnd.random() < 0.7 else two for _ in range(n))
+    assert oracle.compress_jac(engine.msm(pts, sc)) == oracle.compress_jac(oracle.msm(pts, sc, threads=8))
