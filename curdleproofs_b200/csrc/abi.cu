@@ -390,6 +390,16 @@ extern "C" int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, 
     return CDP_OK;
 }
 
+extern "C" int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_stride, size_t cols, size_t rows, uint8_t *d_out) {
+    if (!ctx || (cols && rows && (!d_scalars || !d_out)) || row_stride < cols) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_sum_scalars_dev: bad argument");
+    if (cols == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, cols * rows);
+    CUDA_TRY(ctx, launch_sum_scalars(ctx->stream, reinterpret_cast<const uint32_t *>(d_scalars), (uint32_t)row_stride, (uint32_t)cols, (uint32_t)rows,
+                                     reinterpret_cast<uint32_t *>(d_out)));
+    return CDP_OK;
+}
+
 extern "C" int cdp_dev_zero(cdp_ctx *ctx, void *d_ptr, size_t bytes) {
     if (!ctx || (bytes && !d_ptr)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_dev_zero: bad argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -129,10 +129,26 @@ __global__ void __launch_bounds__(256) k_verify_coeffs(const uint32_t *__restric
     vcoef_thread(blockIdx.x, threadIdx.x, blockDim.x, chal, vec_a, P, out_crs, out_var, out_ex);
 }
 
+// out[i] = sum over rows of in[row * stride + i] (mod r), canonical scalars in and out: the CRS coefficients of all proofs of a sub-batch
+// added up for the merged check (the accumulator's `entry(base) += a * x_i` of msm_accumulator.rs:47-51 across proofs).  One thread per column.
+__global__ void __launch_bounds__(128) k_sum_scalars(const uint32_t *__restrict__ in, uint32_t stride, uint32_t cols, uint32_t rows,
+                                                     uint32_t *__restrict__ out) {
+    using namespace vcoef;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cols) return;
+    fr_t acc = fr_zero();
+    for (uint32_t r = 0; r < rows; r++) acc = fr_add(acc, fr_load(in + 8 * ((size_t)r * stride + i)));
+    for (int k = 0; k < 8; k++) out[8 * (size_t)i + k] = acc.v[k];
+}
+
 #ifndef CDP_VCOEFFS_HOST_HARNESS
 cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch,
                                  uint32_t *out_crs, uint32_t *out_var, uint32_t *out_ex) {
     k_verify_coeffs<<<batch, 256, 0, st>>>(chal, vec_a, P, out_crs, out_var, out_ex);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_scalars(cudaStream_t st, const uint32_t *in, uint32_t stride, uint32_t cols, uint32_t rows, uint32_t *out) {
+    k_sum_scalars<<<(cols + 127) / 128, 128, 0, st>>>(in, stride, cols, rows, out);
     return cudaGetLastError();
 }
 #endif

@@ -98,7 +98,7 @@ struct VState {
 struct VLane {
     cdp_ctx *ctx = nullptr;
     const cdp_fixed_table *table = nullptr;  // digit table of the CRS points (shared by the lanes)
-    cdp_fixed_seg *d_segF = nullptr, *d_segAf = nullptr;
+    cdp_fixed_seg *d_segF = nullptr, *d_segAf = nullptr, *d_segFsum = nullptr;  // d_segFsum: the CRS part of the merged check (summed scalars)
     size_t ell = 0, n = 0, m = 0, max_batch = 0, np = 0;
     int threads = 1;
     std::string err = "ok";
@@ -144,7 +144,7 @@ void vlane_destroy(VLane *p) {
     cdp_ctx *c = p->ctx;
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_pcomp, (void *)p->d_status, (void *)p->d_gsrc,
                     (void *)p->d_gdst, (void *)p->d_isrc, (void *)p->d_idst, (void *)p->d_pdst, (void *)p->d_xsrc, (void *)p->d_xdst,
-                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_cscal, (void *)p->d_vscal, (void *)p->d_escal, (void *)p->d_pscal, (void *)p->d_vtmp,
+                    (void *)p->d_segF, (void *)p->d_segAf, (void *)p->d_segFsum, (void *)p->d_segBig, (void *)p->d_segE, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_chal, (void *)p->d_scal, (void *)p->d_cscal, (void *)p->d_vscal, (void *)p->d_escal, (void *)p->d_pscal, (void *)p->d_vtmp,
                     (void *)p->d_da, (void *)p->d_vflag, (void *)p->d_Hcomp, (void *)p->d_mres, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
@@ -192,7 +192,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->vch = 27 + 4 * m;
     p->d_chal = (uint8_t *)dalloc(max_batch * p->vch * 32); p->h_chal = (uint8_t *)halloc(max_batch * p->vch * 32);
     p->d_scal = (uint8_t *)dalloc(max_batch * 6 * 32);  // stage A (D, A')
-    p->d_cscal = (uint8_t *)dalloc(max_batch * p->crs_n * 32);
+    p->d_cscal = (uint8_t *)dalloc((max_batch + 1) * p->crs_n * 32);  // last row: the column sums of the merged check
     p->d_vscal = (uint8_t *)dalloc((total_pts + 1) * 32);
     p->d_escal = (uint8_t *)dalloc(max_batch * 14 * 32);
     p->d_pscal = (uint8_t *)dalloc(max_batch * 7 * 32); p->h_pscal = (uint8_t *)halloc(max_batch * 7 * 32);
@@ -203,7 +203,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->d_mres = (uint8_t *)dalloc(48); p->h_mres = (uint8_t *)halloc(48);
     p->h_scal = (uint8_t *)halloc(max_batch * 6 * 32);  // stage A only: the coefficients of the accumulated check are computed on the device
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
-    p->d_jac = (uint8_t *)dalloc((max_batch * (p->chunks + FSPLIT + 5) + 4) * 144);
+    p->d_jac = (uint8_t *)dalloc((max_batch * (p->chunks + FSPLIT + 5) + 2 * FSPLIT + 4) * 144);
     p->d_comp = (uint8_t *)dalloc(max_batch * out_pp * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * out_pp * 48);
     // tables
@@ -262,6 +262,17 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     if (!rc) {
         p->d_segF = (cdp_fixed_seg *)dalloc(segF.size() * sizeof(cdp_fixed_seg));
         rc |= p->d_segF ? cdp_h2d(ctx, p->d_segF, segF.data(), segF.size() * sizeof(cdp_fixed_seg)) : CDP_ERR_CUDA;
+        std::vector<cdp_fixed_seg> segFsum(FSPLIT);
+        for (size_t q = 0; q < FSPLIT; q++) {
+            const size_t lo = (n + 3) * q / FSPLIT, hi = (n + 3) * (q + 1) / FSPLIT;
+            cdp_fixed_seg &f = segFsum[q];
+            memset(&f, 0, sizeof f);
+            f.base_off = (uint32_t)lo; f.scalars_off = (uint32_t)(max_batch * p->crs_n + lo); f.n = (uint32_t)(hi - lo); f.remap_from = 0xFFFFFFFFu;
+            f.out_idx = (uint32_t)q;
+        }
+        p->d_segFsum = (cdp_fixed_seg *)dalloc(segFsum.size() * sizeof(cdp_fixed_seg));
+        rc |= p->d_segFsum ? cdp_h2d(ctx, p->d_segFsum, segFsum.data(), segFsum.size() * sizeof(cdp_fixed_seg)) : CDP_ERR_CUDA;
+        rc |= cdp_sync(ctx);  // segFsum is a local
         p->d_segAf = (cdp_fixed_seg *)dalloc(segAf.size() * sizeof(cdp_fixed_seg));
         rc |= p->d_segAf ? cdp_h2d(ctx, p->d_segAf, segAf.data(), segAf.size() * sizeof(cdp_fixed_seg)) : CDP_ERR_CUDA;
     }
@@ -286,6 +297,8 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
 // d_jac, [proof][part]); with CDP_VERIFY_EXACT_EQ the four SameScalar equalities as exact MSMs.  Leaves the encodings in h_comp after a sync.
 int per_proof_stage(VLane *p, size_t B, double &t_wait) {
     const size_t var_n = p->big_n - p->crs_n, NS = p->chunks + FSPLIT;
+    // CRS part of every proof's check through the digit table: partial sums [proof][part]
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segF, FSPLIT * B, B * (p->n + 3), nullptr, p->d_jac + p->chunks * B * 144));
     for (size_t c = 0; c < p->chunks; c++) {
         size_t cnt = std::min<size_t>(2048, var_n - c * 2048);
         VTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_vscal, p->d_segBig + c * p->max_batch, B, cnt, B * cnt, p->d_jac + c * B * 144));
@@ -309,11 +322,14 @@ bool enc_is_inf(const uint8_t *c) {
 }
 // the merged check of a sub-batch: per-proof bases of all proofs in one MSM + the summed CRS parts -> one encoding in d_mres (no sync)
 int merged_stage(VLane *p, size_t B) {
-    uint8_t *d_m = p->d_jac + (p->max_batch * (p->chunks + FSPLIT + 5)) * 144;  // 4 spare points
+    uint8_t *d_m = p->d_jac + (p->max_batch * (p->chunks + FSPLIT + 5)) * 144;  // spare points: [0] per-proof bases, [1 .. FSPLIT] CRS parts, then the total
     VTRY(cdp_msm_dev(p->ctx, p->d_pts + p->crs_n * 96, p->d_vscal + p->crs_n * 32, B * p->VW, d_m));
-    VTRY(cdp_sum_jacobian_dev(p->ctx, p->d_jac + p->chunks * B * 144, FSPLIT * B, d_m + 144));
-    VTRY(cdp_sum_jacobian_dev(p->ctx, d_m, 2, d_m + 288));
-    VTRY(cdp_normalize_dev(p->ctx, d_m + 288, 1, nullptr, p->d_mres));
+    // the coefficients all proofs put on the same CRS base are added first (the accumulator's `entry += a * x_i` across proofs): ONE pass
+    // through the digit table instead of B
+    VTRY(cdp_sum_scalars_dev(p->ctx, p->d_cscal, p->crs_n, p->n + 3, B, p->d_cscal + p->max_batch * p->crs_n * 32));
+    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segFsum, FSPLIT, p->n + 3, nullptr, d_m + 144));
+    VTRY(cdp_sum_jacobian_dev(p->ctx, d_m, FSPLIT + 1, d_m + (FSPLIT + 1) * 144));
+    VTRY(cdp_normalize_dev(p->ctx, d_m + (FSPLIT + 1) * 144, 1, nullptr, p->d_mres));
     VTRY(cdp_d2h(p->ctx, p->h_mres, p->d_mres, 48));
     return CDP_OK;
 }
@@ -374,7 +390,6 @@ int vlane_verify_dev(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *o
                                (uint32_t)p->o_T, (uint32_t)p->o_U, (uint32_t)p->o_M, (uint32_t)p->o_P, p->exact_eq ? 1u : 0u, (uint32_t)p->vch};
         VTRY(cdp_verify_coeffs_dev(p->ctx, p->d_chal, p->d_veca, &vp, B, p->d_cscal, p->d_vscal, p->d_escal));
     }
-    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
     // the merged check is launched before the decompression statuses are known; its result only counts for a sub-batch without a
     // malformed or already rejected proof (such a proof's points must not enter the sum)
     const bool try_merged = p->merged && !p->exact_eq && B >= 2;
@@ -574,8 +589,6 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
                                (uint32_t)p->o_T, (uint32_t)p->o_U, (uint32_t)p->o_M, (uint32_t)p->o_P, p->exact_eq ? 1u : 0u, (uint32_t)p->vch};
         VTRY(cdp_verify_coeffs_dev(p->ctx, p->d_chal, p->d_veca, &vp, B, p->d_cscal, p->d_vscal, p->d_escal));
     }
-    // CRS part of every proof's check through the digit table: partial sums [proof][part]
-    VTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_cscal, p->d_segF, FSPLIT * B, B * (n + 3), nullptr, p->d_jac + p->chunks * B * 144));
     // ---- merged check of the lane's batch (SURVEY.md 8(f) rank 3 / BASELINE config 3): every check of every proof already carries its own
     //      independent random factor, so the sum over the batch is again one random linear combination -- the MsmAccumulator argument
     //      (msm_accumulator.rs:55-68) applied to 12 B checks instead of 12.  d_vscal is indexed like d_pts, so the per-proof bases of the

@@ -246,6 +246,9 @@ typedef struct {
 } cdp_vcoef_params;
 int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8_t *d_vec_a, const cdp_vcoef_params *params, size_t batch,
                           uint8_t *d_crs_scalars, uint8_t *d_var_scalars, uint8_t *d_exact_scalars);
+/* d_out[i] = sum over r < rows of d_scalars[r * row_stride + i] (mod r), canonical 32-byte scalars, i < cols: the coefficients that several
+ * proofs put on the same CRS base, added up for the merged check (`*entry += a * x_i`, /root/reference/src/msm_accumulator.rs:47-51). */
+int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_stride, size_t cols, size_t rows, uint8_t *d_out);
 
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);
