@@ -85,9 +85,12 @@ __device__ __forceinline__ fr_t fr_neg(const fr_t &a) { return fr_sub(fr_zero(),
 // Montgomery product (R = 2^256), coarsely integrated operand scanning
 static __device__ __noinline__ fr_t fr_mul(const fr_t &a, const fr_t &b) {
     uint32_t t[10];
+#pragma unroll
     for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
     for (int i = 0; i < 8; i++) {
         uint64_t c = 0;
+#pragma unroll
         for (int j = 0; j < 8; j++) {
             c += (uint64_t)a.v[j] * b.v[i] + t[j];
             t[j] = (uint32_t)c;
@@ -99,6 +102,7 @@ static __device__ __noinline__ fr_t fr_mul(const fr_t &a, const fr_t &b) {
         const uint32_t m = t[0] * FR_NINV;
         c = (uint64_t)m * fr_mod(0) + t[0];
         c >>= 32;
+#pragma unroll
         for (int j = 1; j < 8; j++) {
             c += (uint64_t)m * fr_mod(j) + t[j];
             t[j - 1] = (uint32_t)c;

@@ -123,23 +123,32 @@ __device__ __forceinline__ void vcoef_thread(uint32_t pr, uint32_t tid, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(256) k_verify_coeffs(const uint32_t *__restrict__ chal, const uint32_t *__restrict__ vec_a,
+__global__ void __launch_bounds__(256, 2) k_verify_coeffs(const uint32_t *__restrict__ chal, const uint32_t *__restrict__ vec_a,
                                                        const vcoef_params_t P, uint32_t *__restrict__ out_crs, uint32_t *__restrict__ out_var,
                                                        uint32_t *__restrict__ out_ex) {
     vcoef_thread(blockIdx.x, threadIdx.x, blockDim.x, chal, vec_a, P, out_crs, out_var, out_ex);
 }
 
 // out[i] = sum over rows of in[row * stride + i] (mod r), canonical scalars in and out: the CRS coefficients of all proofs of a sub-batch
-// added up for the merged check (the accumulator's `entry(base) += a * x_i` of msm_accumulator.rs:47-51 across proofs).  One thread per column.
+// added up for the merged check (the accumulator's `entry(base) += a * x_i` of msm_accumulator.rs:47-51 across proofs).  One warp per column:
+// the lanes take every 32nd row, then a shuffle reduction.
+#ifndef CDP_VCOEFFS_HOST_HARNESS
 __global__ void __launch_bounds__(128) k_sum_scalars(const uint32_t *__restrict__ in, uint32_t stride, uint32_t cols, uint32_t rows,
                                                      uint32_t *__restrict__ out) {
     using namespace vcoef;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= cols) return;
     fr_t acc = fr_zero();
-    for (uint32_t r = 0; r < rows; r++) acc = fr_add(acc, fr_load(in + 8 * ((size_t)r * stride + i)));
-    for (int k = 0; k < 8; k++) out[8 * (size_t)i + k] = acc.v[k];
+    for (uint32_t r = lane; r < rows; r += 32) acc = fr_add(acc, fr_load(in + 8 * ((size_t)r * stride + i)));
+    for (int d = 16; d >= 1; d >>= 1) {
+        fr_t o;
+        for (int k = 0; k < 8; k++) o.v[k] = __shfl_down_sync(0xffffffffu, acc.v[k], d);
+        acc = fr_add(acc, o);
+    }
+    if (lane == 0)
+        for (int k = 0; k < 8; k++) out[8 * (size_t)i + k] = acc.v[k];
 }
+#endif
 
 #ifndef CDP_VCOEFFS_HOST_HARNESS
 cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch,
@@ -148,7 +157,7 @@ cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const ui
     return cudaGetLastError();
 }
 cudaError_t launch_sum_scalars(cudaStream_t st, const uint32_t *in, uint32_t stride, uint32_t cols, uint32_t rows, uint32_t *out) {
-    k_sum_scalars<<<(cols + 127) / 128, 128, 0, st>>>(in, stride, cols, rows, out);
+    k_sum_scalars<<<(cols * 32 + 127) / 128, 128, 0, st>>>(in, stride, cols, rows, out);
     return cudaGetLastError();
 }
 #endif
