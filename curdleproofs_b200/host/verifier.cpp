@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <random>
 #include <string>
 #include <thread>
 #include <vector>
@@ -360,7 +361,7 @@ int vlane_verify_dev(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *o
         auto fr = [&]() { Fr x; if (!Fr::from_bytes(r, x)) s.status = 2; memcpy(ps + 32 * q, r, 32); q++; r += 32; };
         pts(9); fr(); pts(2 + 4 * m); fr(); fr(); pts(4); fr(); fr(); fr(); pts(3 + 6 * m); fr();
         // one random factor per accumulate_check (msm_accumulator.rs:44), in call order; 8..11: the SameScalar equalities
-        StdRng rng(in->rng_seed ? in->rng_seed[pr] : 0x9e3779b97f4a7c15ULL + pr);
+        StdRng rng(in->rng_seed[pr]);  // cdp_verify_batch always supplies seeds (the caller's, or fresh ones from the OS)
         Fr *ch = reinterpret_cast<Fr *>(p->h_chal + pr * p->vch * 32);
         for (int i = 0; i < 12; i++) ch[i] = rng.fr_rand();
     });
@@ -492,7 +493,7 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
         uint8_t *uu = tu + n * 48;
         memcpy(uu, cmp + 3 * ell * 48, ell * 48);
         memcpy(uu + ell * 48, inf, 48); memcpy(uu + (ell + 1) * 48, inf, 48); memcpy(uu + (ell + 2) * 48, inf, 48); memcpy(uu + (ell + 3) * 48, p->H_comp, 48);
-        StdRng rng(in->rng_seed ? in->rng_seed[pr] : 0x9e3779b97f4a7c15ULL + pr);
+        StdRng rng(in->rng_seed[pr]);  // cdp_verify_batch always supplies seeds (the caller's, or fresh ones from the OS)
         for (int i = 0; i < 12; i++) s.rho[i] = rng.fr_rand();  // one per accumulate_check (msm_accumulator.rs:44), in call order; 8..11: SameScalar
         // same_perm (same_permutation_argument.rs:134-145)
         s.tr->append_point("same_perm_step1", pc + 48 * L.A);
@@ -700,6 +701,24 @@ extern "C" int cdp_verify_batch(cdp_verifier *v, size_t B, const cdp_verify_inpu
     if (!v) return CDP_ERR_INVALID_ARG;
     if (!in || !ok_out || B == 0 || B > v->max_batch || !in->vec_R || !in->proofs) { v->err = "cdp_verify_batch: bad argument"; return CDP_ERR_INVALID_ARG; }
     const size_t Ln = v->lanes.size(), ell = v->ell, psz = cdp_proof_size(ell);
+    // The random factors of the accumulated checks must be unpredictable to whoever made the proofs (msm_accumulator.rs:44 draws them from
+    // the verifier's rng).  Without caller-supplied seeds they come from the OS entropy source: 128 bits per call, expanded per proof.
+    std::vector<uint64_t> own_seeds;
+    cdp_verify_inputs with_seeds = *in;
+    if (!in->rng_seed) {
+        std::random_device rd;
+        uint64_t a = ((uint64_t)rd() << 32) | rd(), b = ((uint64_t)rd() << 32) | rd();
+        own_seeds.resize(B);
+        for (size_t i = 0; i < B; i++) {  // splitmix64 over two independent 64-bit states
+            a += 0x9e3779b97f4a7c15ULL; b += 0xd1342543de82ef95ULL;
+            uint64_t x = a, y = b;
+            x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ULL; x = (x ^ (x >> 27)) * 0x94d049bb133111ebULL; x ^= x >> 31;
+            y = (y ^ (y >> 30)) * 0xbf58476d1ce4e5b9ULL; y = (y ^ (y >> 27)) * 0x94d049bb133111ebULL; y ^= y >> 31;
+            own_seeds[i] = x ^ (y << 1);
+        }
+        with_seeds.rng_seed = own_seeds.data();
+        in = &with_seeds;
+    }
     std::vector<size_t> off(Ln + 1, 0);
     for (size_t i = 0; i < Ln; i++) off[i + 1] = off[i] + (B / Ln + (i < B % Ln ? 1 : 0));
     std::vector<int> rcs(Ln, CDP_OK);

@@ -90,7 +90,8 @@ typedef struct {
     const uint8_t *vec_U;
     const uint8_t *M;         /* batch jacobian */
     const uint8_t *proofs;    /* batch * cdp_proof_size(ell) bytes, `CurdleproofsProof::serialize` format */
-    const uint64_t *rng_seed; /* batch, or NULL: seeds the random factors of the accumulated checks (msm_accumulator.rs:44) */
+    const uint64_t *rng_seed; /* batch: seeds of the random factors of the accumulated checks (msm_accumulator.rs:44; the `rng` argument of
+                                 `verify`), or NULL: fresh seeds from the OS entropy source.  They must be unpredictable to the prover. */
 } cdp_verify_inputs;
 /* result[i]: 1 = Ok(()), 0 = Err(VerificationError), 2 = the proof does not deserialise (bad encoding / not in the subgroup) */
 int cdp_verify_batch(cdp_verifier *v, size_t batch, const cdp_verify_inputs *in, uint8_t *result);
