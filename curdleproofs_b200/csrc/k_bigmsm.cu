@@ -94,7 +94,7 @@ constexpr uint32_t BIG_HEAVY = 2048, BIG_CHUNK = 4096;
 struct big_heavy_item_t {
     uint32_t slot, lo, hi, first;  // bucket slot (index into buckets_jac), range in the window's sorted array, first item of this bucket in the list
 };
-__global__ void __launch_bounds__(128) k_big_accumulate(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted,
+__global__ void __launch_bounds__(128, 3) k_big_accumulate(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted,
                                                         const uint32_t *__restrict__ start, uint32_t n2, int nwin, uint32_t nb, uint32_t sp_top,
                                                         uint32_t chunks, uint32_t *__restrict__ buckets_jac, uint32_t *__restrict__ heavy_count,
                                                         big_heavy_item_t *__restrict__ heavy_items, uint32_t heavy_cap) {
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) k_big_accumulate(const uint32_t *__restri
 // One CTA per work item (a chunk of <= BIG_CHUNK points of one heavy bucket): the 128 threads stride over the chunk with mixed additions,
 // then a shuffle / shared-memory reduction; partial sum to heavy_partial[item].  The grid is sized for the worst case; CTAs beyond the
 // list's length leave at once.
-__global__ void __launch_bounds__(128) k_big_heavy(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted, uint32_t n2,
+__global__ void __launch_bounds__(128, 3) k_big_heavy(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted, uint32_t n2,
                                                    uint32_t nb, const uint32_t *__restrict__ heavy_count,
                                                    const big_heavy_item_t *__restrict__ heavy_items, uint32_t heavy_cap,
                                                    uint32_t *__restrict__ heavy_partial) {

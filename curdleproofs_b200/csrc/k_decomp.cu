@@ -24,7 +24,7 @@ __device__ __forceinline__ void mul_by_z(g1j &r, const g1j &p) {
 }
 
 // status: 0 ok, 1 malformed encoding / x >= p, 2 not on curve, 3 not in subgroup
-__global__ void __launch_bounds__(128) k_decompress(const uint8_t *__restrict__ comp, const uint32_t *__restrict__ dst_idx,
+__global__ void __launch_bounds__(128, 3) k_decompress(const uint8_t *__restrict__ comp, const uint32_t *__restrict__ dst_idx,
                                                     uint32_t *__restrict__ out_affine, uint8_t *__restrict__ status, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
