@@ -15,7 +15,7 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 struct dim3_t { unsigned x; };
 static dim3_t blockIdx{0}, blockDim{1}, threadIdx{0};
 namespace cdp {
