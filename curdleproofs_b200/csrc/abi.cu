@@ -390,6 +390,23 @@ extern "C" int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, 
     return CDP_OK;
 }
 
+extern "C" int cdp_round_expand_dev(cdp_ctx *ctx, const uint8_t *d_compact, const uint8_t *d_u_canonical, size_t n, size_t h, size_t scalars_per_proof,
+                                    size_t compact_per_proof, int mode, size_t batch, uint8_t *d_scalars_out) {
+    if (!ctx || (batch && (!d_compact || !d_scalars_out)) || (mode != 0 && mode != 1) || (mode == 0 && batch && !d_u_canonical) || h == 0 ||
+        (h & (h - 1)) || n < 2 * h || n % (2 * h))
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_round_expand_dev: bad argument");
+    const size_t Q = n / (2 * h);
+    if (compact_per_proof < (mode == 0 ? 2 * Q + 4 * h + 2 : Q + 2 * h) || scalars_per_proof < (mode == 0 ? 2 * n + 2 : n + 2 * h))
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_round_expand_dev: inconsistent layout");
+    if (batch == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch * n);
+    round_expand_params_t P = {(uint32_t)n, (uint32_t)h, (uint32_t)scalars_per_proof, (uint32_t)compact_per_proof, (uint32_t)mode};
+    CUDA_TRY(ctx, launch_round_expand(ctx->stream, reinterpret_cast<const uint32_t *>(d_compact), reinterpret_cast<const uint32_t *>(d_u_canonical), P,
+                                      (uint32_t)batch, reinterpret_cast<uint32_t *>(d_scalars_out)));
+    return CDP_OK;
+}
+
 extern "C" int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_stride, size_t cols, size_t rows, uint8_t *d_out) {
     if (!ctx || (cols && rows && (!d_scalars || !d_out)) || row_stride < cols) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_sum_scalars_dev: bad argument");
     if (cols == 0) return CDP_OK;

@@ -129,6 +129,48 @@ __global__ void __launch_bounds__(256, 2) k_verify_coeffs(const uint32_t *__rest
     vcoef_thread(blockIdx.x, threadIdx.x, blockDim.x, chal, vec_a, P, out_crs, out_var, out_ex);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Prover side: the scalars of one folding round, expanded on the device.  The batched prover writes the round MSMs of the IPA / SameMSM
+// arguments over the ORIGINAL bases (/root/reference/src/inner_product_argument.rs:158-161, src/same_multiscalar_argument.rs:107-112 with
+// the folded bases G^(k)_i = sum_{j = i mod n_k} w(j) G_j): scalar j is   w(prefix of j) * v[side of j],
+// where w depends only on the bits of j above the round's split h (the product of the earlier rounds' challenges on those bits) and v is
+// the current folded vector of 2h entries.  The host therefore only sends Q = n / 2h prefix weights and the 2h vector entries; this kernel
+// forms the n (or 2n) products -- the host used to do these n products per vector per round itself, which was the bulk of its field work.
+//   mode 0 (IPA):     compact = Wc[Q] canonical | c[2h] Montgomery | Wd[Q] Montgomery | d[2h] Montgomery | ipL | ipR (canonical)
+//                     out[j] = Wc[q] c[sel j],  out[n] = ipL, out[n+1] = ipR,  out[n+2+j] = Wd[q] u[j] d[sel j]   (u canonical, per proof: G' = u o G)
+//   mode 1 (SameMSM): compact = Ws[Q] canonical | x[2h] Montgomery;   out[j] = Ws[q] x[sel j],  out[n + i] = x[i] (canonical), i < 2h
+//   q = j / 2h,  sel j = (j mod h) when bit h of j is set, h + (j mod h) otherwise.   A Montgomery product of a canonical and a
+//   Montgomery-form value is the canonical product, so every output is already the byte form the MSM kernels read.
+__device__ __forceinline__ void round_expand_thread(uint32_t pr, uint32_t tid, uint32_t nthreads, const uint32_t *compact, const uint32_t *ucan,
+                                                    const round_expand_params_t P, uint32_t *out) {
+    using namespace vcoef;
+    const uint32_t n = P.n, h = P.h, Q = n / (2 * h);
+    const uint32_t *cb = compact + 8 * (size_t)pr * P.cpp;
+    uint32_t *sc = out + 8 * (size_t)pr * P.spp;
+    auto put_raw = [&](uint32_t slot, const fr_t &x) { for (int k = 0; k < 8; k++) sc[8 * slot + k] = x.v[k]; };
+    if (P.mode == 0) {
+        const uint32_t *Wc = cb, *cv = cb + 8 * Q, *Wd = cv + 8 * 2 * h, *dv = Wd + 8 * Q, *ip = dv + 8 * 2 * h;
+        const uint32_t *u = ucan + 8 * (size_t)pr * n;
+        for (uint32_t j = tid; j < n; j += nthreads) {
+            const uint32_t q = j / (2 * h), i = j & (h - 1), sel = (j & h) ? i : h + i;
+            put_raw(j, fr_mul(fr_load(Wc + 8 * q), fr_load(cv + 8 * sel)));
+            put_raw(n + 2 + j, fr_mul(fr_mul(fr_load(Wd + 8 * q), fr_load(u + 8 * j)), fr_load(dv + 8 * sel)));
+        }
+        if (tid == 0) { put_raw(n, fr_load(ip)); put_raw(n + 1, fr_load(ip + 8)); }
+    } else {
+        const uint32_t *Ws = cb, *xv = cb + 8 * Q;
+        for (uint32_t j = tid; j < n; j += nthreads) {
+            const uint32_t q = j / (2 * h), i = j & (h - 1), sel = (j & h) ? i : h + i;
+            put_raw(j, fr_mul(fr_load(Ws + 8 * q), fr_load(xv + 8 * sel)));
+        }
+        for (uint32_t i = tid; i < 2 * h; i += nthreads) fr_store_canonical(sc + 8 * (n + i), fr_load(xv + 8 * i));
+    }
+}
+__global__ void __launch_bounds__(256, 2) k_round_expand(const uint32_t *__restrict__ compact, const uint32_t *__restrict__ ucan,
+                                                         const round_expand_params_t P, uint32_t *__restrict__ out) {
+    round_expand_thread(blockIdx.x, threadIdx.x, blockDim.x, compact, ucan, P, out);
+}
+
 // out[i] = sum over rows of in[row * stride + i] (mod r), canonical scalars in and out: the CRS coefficients of all proofs of a sub-batch
 // added up for the merged check (the accumulator's `entry(base) += a * x_i` of msm_accumulator.rs:47-51 across proofs).  One warp per column:
 // the lanes take every 32nd row, then a shuffle reduction.
@@ -154,6 +196,11 @@ __global__ void __launch_bounds__(128) k_sum_scalars(const uint32_t *__restrict_
 cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const uint32_t *vec_a, const vcoef_params_t &P, uint32_t batch,
                                  uint32_t *out_crs, uint32_t *out_var, uint32_t *out_ex) {
     k_verify_coeffs<<<batch, 256, 0, st>>>(chal, vec_a, P, out_crs, out_var, out_ex);
+    return cudaGetLastError();
+}
+cudaError_t launch_round_expand(cudaStream_t st, const uint32_t *compact, const uint32_t *ucan, const round_expand_params_t &P, uint32_t batch,
+                                uint32_t *out) {
+    k_round_expand<<<batch, 256, 0, st>>>(compact, ucan, P, out);
     return cudaGetLastError();
 }
 cudaError_t launch_sum_scalars(cudaStream_t st, const uint32_t *in, uint32_t stride, uint32_t cols, uint32_t rows, uint32_t *out) {

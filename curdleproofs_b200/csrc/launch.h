@@ -48,6 +48,11 @@ cudaError_t launch_normalize(cudaStream_t st, int chunk, const uint32_t *jac, ui
                              const smul_job_t *jobs, uint32_t elems_per_job);
 cudaError_t launch_compress_affine(cudaStream_t st, const uint32_t *pts, const uint32_t *idx, uint8_t *out_comp, uint32_t n);
 cudaError_t launch_decompress(cudaStream_t st, const uint8_t *comp, const uint32_t *dst_idx, uint32_t *out_affine, uint8_t *status, uint32_t n);
+struct round_expand_params_t {
+    uint32_t n, h, spp, cpp, mode;  // vector length, split of this round, scalars per proof in the output / in the compact block, 0 = IPA, 1 = SameMSM
+};
+cudaError_t launch_round_expand(cudaStream_t st, const uint32_t *compact, const uint32_t *ucan, const round_expand_params_t &P, uint32_t batch,
+                                uint32_t *out);
 cudaError_t launch_sum_scalars(cudaStream_t st, const uint32_t *in, uint32_t stride, uint32_t cols, uint32_t rows, uint32_t *out);
 cudaError_t launch_verify_transcript_a(cudaStream_t st, const uint8_t *pcomp, const uint8_t *pscal, const uint8_t *comp_M, const uint8_t *vec_a,
                                        uint32_t ell, uint32_t np, uint32_t vch, uint32_t B, uint64_t *state, uint32_t *chal, uint32_t *tmp,

@@ -74,6 +74,8 @@ struct ProofState {
     // container: a Montgomery product of a canonical value and a Montgomery-form value is the canonical product, so `weight * scalar`
     // is already the byte form the MSM wants (no separate conversion), and `weight * gamma` stays canonical.
     std::vector<Fr> wG, wGp, wS;
+    // the same weights per PREFIX of the index (the bits above the current split), for the device-side expansion: WcP, WsP canonical, WdP Montgomery
+    std::vector<Fr> WcP, WdP, WsP;
     Fr a_bl[2], c_bl[4], r_t, r_u, r_a, r_b, r_k, k, m_bl[4], b_bl[4], rb_alpha[4];
     Fr alpha_sp, beta_sp, gprod_result, alpha_g, beta_g, r_p, z, alpha_i, beta_i;
     Fr z_k, z_t, z_u, c_final, d_final, x_final;
@@ -119,6 +121,9 @@ struct Lane {
     size_t g_count_per_proof = 0, i_count_per_proof = 0;
     uint32_t *d_cidx = nullptr;                         // indices of the points compressed for the transcript opening
     uint8_t *d_scal = nullptr, *d_fscal = nullptr;
+    // device-side expansion of the round scalars (cdp_round_expand_dev): compact per-proof blocks (prefix weights + folded vectors), u canonical
+    uint8_t *d_cmp = nullptr, *h_cmp = nullptr, *d_ucan = nullptr, *h_ucan = nullptr;
+    bool dev_expand = true;  // CDP_PROVE_HOST_EXPAND=1: the n products per vector per round on the host (the older path)
     uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
     uint8_t *d_jac = nullptr, *d_comp = nullptr;
     uint8_t *h_scal = nullptr, *h_fscal = nullptr, *h_comp = nullptr, *h_in = nullptr;
@@ -340,10 +345,20 @@ int upload_tables(Lane *p) {
 
 // ---- running a stage -----------------------------------------------------------------------------------------
 // scalars for all proofs are already in p->h_scal (proof-major, st.scalars_per_proof each)
-int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_copy) {
+struct ExpandSpec {
+    int mode;            // 0 = IPA round (c and d scalars), 1 = SameMSM round (x scalars + the folded vector)
+    size_t n, h, cpp;    // vector length, split, compact scalars per proof (in p->h_cmp)
+};
+int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_copy, const ExpandSpec *ex = nullptr) {
     double t0 = now_ms();
-    PTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * st.scalars_per_proof * 32));
-    p->h2d_bytes += B * st.scalars_per_proof * 32;
+    if (ex) {  // the stage's scalars are formed on the device from the compact blocks in p->h_cmp
+        PTRY(cdp_h2d(p->ctx, p->d_cmp, p->h_cmp, B * ex->cpp * 32));
+        p->h2d_bytes += B * ex->cpp * 32;
+        PTRY(cdp_round_expand_dev(p->ctx, p->d_cmp, p->d_ucan, ex->n, ex->h, st.scalars_per_proof, ex->cpp, ex->mode, B, p->d_scal));
+    } else {
+        PTRY(cdp_h2d(p->ctx, p->d_scal, p->h_scal, B * st.scalars_per_proof * 32));
+        p->h2d_bytes += B * st.scalars_per_proof * 32;
+    }
     size_t out_off = 0;
     for (auto &sl : st.subs) {
         if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144));
@@ -397,9 +412,9 @@ static void lane_destroy(Lane *p) {
     for (auto &s : p->st_sm) free_stage(s);
     for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
-                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate})
+                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_cmp, (void *)p->d_ucan, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_cmp, (void *)p->h_ucan, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -500,6 +515,9 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     p->h_scal = (uint8_t *)halloc(max_batch * p->max_scalars_pp * 32);
     p->d_fscal = (uint8_t *)dalloc(max_batch * n * 32);
     p->h_fscal = (uint8_t *)halloc(max_batch * n * 32);
+    p->d_cmp = (uint8_t *)dalloc(max_batch * (2 * n + 4) * 32); p->h_cmp = (uint8_t *)halloc(max_batch * (2 * n + 4) * 32);
+    p->d_ucan = (uint8_t *)dalloc(max_batch * n * 32); p->h_ucan = (uint8_t *)halloc(max_batch * n * 32);
+    if (const char *e = getenv("CDP_PROVE_HOST_EXPAND")) p->dev_expand = atoi(e) == 0;
     p->d_veca = (uint8_t *)dalloc(max_batch * ell * 32); p->h_veca = (uint8_t *)halloc(max_batch * ell * 32);
     p->d_tstate = (uint8_t *)dalloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES); p->h_tstate = (uint8_t *)halloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES);
     p->d_jac = (uint8_t *)dalloc(max_batch * p->max_out_pp * 144);
@@ -806,11 +824,22 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             s.d[i] = s.r_d[i] + s.alpha_i * s.d[i];
         }
         // fold weights of the original bases: G^(k)_i = sum_{j = i mod n_k} wG[j] G_j,  G'^(k)_i = sum wGp[j] G_j  (G' = u o G, :92-102 of gprod)
-        s.wG.assign(n, fr_canonical_one());
-        s.wGp.resize(n);
-        for (size_t j = 0; j < n; j++) s.wGp[j] = fr_to_canonical_value(s.u[j]);
+        if (p->dev_expand) {
+            s.WcP.assign(1, fr_canonical_one());
+            s.WdP.assign(1, Fr::one());
+            uint8_t *uc = p->h_ucan + pr * n * 32;
+            for (size_t j = 0; j < n; j++) s.u[j].to_bytes(uc + 32 * j);  // u canonical, resident on the device for all rounds
+        } else {
+            s.wG.assign(n, fr_canonical_one());
+            s.wGp.resize(n);
+            for (size_t j = 0; j < n; j++) s.wGp[j] = fr_to_canonical_value(s.u[j]);
+        }
     });
     t_host += now_ms() - t0;
+    if (p->dev_expand) {
+        PTRY(cdp_h2d(p->ctx, p->d_ucan, p->h_ucan, B * n * 32));
+        p->h2d_bytes += B * n * 32;
+    }
     for (size_t k = 0; k < m; k++) {
         const size_t h = n >> (k + 1);
         MsmStage &st = p->st_ipa[k];
@@ -818,6 +847,17 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         parallel_for(T, B, [&](size_t pr) {
             ProofState &s = p->ps[pr];
             const Fr *cL = s.c.data(), *cR = s.c.data() + h, *dL = s.d.data(), *dR = s.d.data() + h;
+            if (p->dev_expand) {  // compact block: Wc[Q] | c[2h] | Wd[Q] | d[2h] | ipL | ipR  (cdp_round_expand_dev, mode 0)
+                const size_t Q = n / (2 * h);
+                uint8_t *w = p->h_cmp + pr * (2 * Q + 4 * h + 2) * 32;
+                memcpy(w, s.WcP.data(), Q * 32); w += Q * 32;
+                memcpy(w, s.c.data(), 2 * h * 32); w += 2 * h * 32;
+                memcpy(w, s.WdP.data(), Q * 32); w += Q * 32;
+                memcpy(w, s.d.data(), 2 * h * 32); w += 2 * h * 32;
+                put_fr(w, s.beta_i * inner_product(cL, dR, h));
+                put_fr(w + 32, s.beta_i * inner_product(cR, dL, h));
+                return;
+            }
             uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
             // msm(G_R, c_L), msm(G_L, c_R), msm(G'_L, d_R), msm(G'_R, d_L) (:158-161) over the original bases
             for (size_t j = 0; j < n; j++) {
@@ -830,7 +870,10 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             put_fr(sc + 32 * (n + 1), s.beta_i * inner_product(cR, dL, h));  //                   R_C += <c_R,d_L> H
         });
         t_host += now_ms() - t0;
-        if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
+        {
+            const ExpandSpec ex = {0, n, h, 2 * (n / (2 * h)) + 4 * h + 2};
+            if (int rc = run_msm_stage(p, st, B, t_wait, t_copy, p->dev_expand ? &ex : nullptr)) return rc;
+        }
         t0 = now_ms();
         parallel_chunks(T, B, [&](size_t lo, size_t hi) {
             std::vector<Fr> gam(hi - lo), ginv;
@@ -853,7 +896,15 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
                     s.d[i] += gamma * s.d[h + i];
                 }
                 // G_L += gamma G_R, G'_L += gamma^-1 G'_R (:177-178), as weights on the original bases
-                if (h > 1)
+                if (h > 1 && p->dev_expand) {  // per prefix: the new low bit of the prefix is bit h of the index
+                    const size_t Q = n / (2 * h);
+                    std::vector<Fr> wc(2 * Q), wd(2 * Q);
+                    for (size_t q = 0; q < Q; q++) {
+                        wc[2 * q] = s.WcP[q]; wc[2 * q + 1] = s.WcP[q] * gamma;
+                        wd[2 * q] = s.WdP[q]; wd[2 * q + 1] = s.WdP[q] * gamma_inv;
+                    }
+                    s.WcP.swap(wc); s.WdP.swap(wd);
+                } else if (h > 1)
                     for (size_t j = 0; j < n; j++)
                         if (j & h) { s.wG[j] *= gamma; s.wGp[j] *= gamma_inv; }
             }
@@ -887,7 +938,8 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         for (size_t i = 0; i < ell; i++) s.x[i] = s.r_sm[i] + a_sm * s.a_perm[i];
         const Fr tail[4] = {s.a_bl[0], s.a_bl[1], s.r_t, s.r_u};  // vec_a_with_blinders, curdleproofs.rs:157-160
         for (int i = 0; i < 4; i++) s.x[ell + i] = s.r_sm[ell + i] + a_sm * tail[i];
-        s.wS.assign(n, fr_canonical_one());
+        if (p->dev_expand) s.WsP.assign(1, fr_canonical_one());
+        else s.wS.assign(n, fr_canonical_one());
     });
     t_host += now_ms() - t0;
     for (size_t k = 0; k < m; k++) {
@@ -898,11 +950,21 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
             ProofState &s = p->ps[pr];
             uint8_t *sc = p->h_scal + pr * st.scalars_per_proof * 32;
             // msm(G_R, x_L), msm(G_L, x_R) (:107,:110) over the original G_with_blinders; T, U use the folded vectors
+            if (p->dev_expand) {  // compact block: Ws[Q] | x[2h]  (cdp_round_expand_dev, mode 1)
+                const size_t Q = n / (2 * h);
+                uint8_t *w = p->h_cmp + pr * (Q + 2 * h) * 32;
+                memcpy(w, s.WsP.data(), Q * 32);
+                memcpy(w + Q * 32, s.x.data(), 2 * h * 32);
+                return;
+            }
             for (size_t j = 0; j < n; j++) put_canonical(sc + 32 * j, s.wS[j] * s.x[(j & h) ? (j & (h - 1)) : h + (j & (h - 1))]);
             for (size_t i = 0; i < 2 * h; i++) put_fr(sc + 32 * (n + i), s.x[i]);
         });
         t_host += now_ms() - t0;
-        if (int rc = run_msm_stage(p, st, B, t_wait, t_copy)) return rc;
+        {
+            const ExpandSpec ex = {1, n, h, n / (2 * h) + 2 * h};
+            if (int rc = run_msm_stage(p, st, B, t_wait, t_copy, p->dev_expand ? &ex : nullptr)) return rc;
+        }
         t0 = now_ms();
         parallel_chunks(T, B, [&](size_t lo, size_t hi) {
             std::vector<Fr> gam(hi - lo), ginv;
@@ -922,7 +984,12 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
                 const Fr gamma = gam[pr - lo], gamma_inv = ginv[pr - lo];
                 for (size_t i = 0; i < h; i++) s.x[i] += gamma_inv * s.x[h + i];
                 put_fr(p->h_fscal + pr * 32, gamma);
-                if (h > 1)
+                if (h > 1 && p->dev_expand) {
+                    const size_t Q = n / (2 * h);
+                    std::vector<Fr> ws(2 * Q);
+                    for (size_t q = 0; q < Q; q++) { ws[2 * q] = s.WsP[q]; ws[2 * q + 1] = s.WsP[q] * gamma; }
+                    s.WsP.swap(ws);
+                } else if (h > 1)
                     for (size_t j = 0; j < n; j++)
                         if (j & h) s.wS[j] *= gamma;   // G_L += gamma G_R (:130)
             }

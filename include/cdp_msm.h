@@ -246,6 +246,16 @@ typedef struct {
 } cdp_vcoef_params;
 int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8_t *d_vec_a, const cdp_vcoef_params *params, size_t batch,
                           uint8_t *d_crs_scalars, uint8_t *d_var_scalars, uint8_t *d_exact_scalars);
+/* Prover: the scalars of one folding round expanded on the device.  The batched prover writes the round MSMs of the IPA / SameMSM arguments
+ * (/root/reference/src/inner_product_argument.rs:158-161, src/same_multiscalar_argument.rs:107-112) over the ORIGINAL bases, so scalar j of a
+ * round with split h is  w(j / 2h) * v[j mod h (+ h when bit h of j is clear)]: the host sends the n / 2h prefix weights and the 2h entries of
+ * the folded vector, this forms the products.  mode 0 (IPA): compact = Wc[Q] canonical | c[2h] Montgomery | Wd[Q] Montgomery | d[2h] Montgomery
+ * | ipL | ipR canonical; out = c-scalars[n] | ipL | ipR | d-scalars[n] with d-scalar j = Wd[q] u[j] d[..] (d_u_canonical: batch x n, the
+ * GrandProduct rescaling beta^-(j+1) of src/grand_product_argument.rs:92-102).  mode 1 (SameMSM): compact = Ws[Q] canonical | x[2h]
+ * Montgomery; out = x-scalars[n] | x[2h] canonical.  All outputs are canonical 32-byte scalars. */
+int cdp_round_expand_dev(cdp_ctx *ctx, const uint8_t *d_compact, const uint8_t *d_u_canonical, size_t n, size_t h, size_t scalars_per_proof,
+                         size_t compact_per_proof, int mode, size_t batch, uint8_t *d_scalars_out);
+
 /* d_out[i] = sum over r < rows of d_scalars[r * row_stride + i] (mod r), canonical 32-byte scalars, i < cols: the coefficients that several
  * proofs put on the same CRS base, added up for the merged check (`*entry += a * x_i`, /root/reference/src/msm_accumulator.rs:47-51). */
 int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_stride, size_t cols, size_t rows, uint8_t *d_out);

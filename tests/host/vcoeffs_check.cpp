@@ -20,6 +20,7 @@ struct dim3_t { unsigned x; };
 static dim3_t blockIdx{0}, blockDim{1}, threadIdx{0};
 namespace cdp {
 struct vcoef_params_t { uint32_t ell, n, m, big_n, vw, o_R, o_S, o_T, o_U, o_M, o_P, exact_eq, vch; };
+struct round_expand_params_t { uint32_t n, h, spp, cpp, mode; };
 }
 #include "../../curdleproofs_b200/csrc/k_vcoeffs.cu"
 #include "../../curdleproofs_b200/host/fr.hpp"
@@ -149,7 +150,73 @@ static int run(size_t ell, bool exact_eq) {
     return 0;
 }
 
+// The prover's round scalars: the host loop the batched prover used (per-index fold weights, n products per vector per round) against the
+// device expansion from prefix weights (k_round_expand / round_expand_thread), over all log2(n) rounds of both arguments.
+static Fr canonical_value(const Fr &x) { uint64_t c[4]; x.to_canonical(c); return Fr::raw(c); }
+static int run_expand(size_t n) {
+    size_t m = 0;
+    while (((size_t)1 << m) < n) m++;
+    const uint64_t one_c[4] = {1, 0, 0, 0};
+    std::vector<Fr> c(n), d(n), x(n), u(n), wG(n, Fr::raw(one_c)), wGp(n), wS(n, Fr::raw(one_c));
+    for (size_t i = 0; i < n; i++) { c[i] = rand_fr(); d[i] = rand_fr(); x[i] = rand_fr(); u[i] = rand_fr(); wGp[i] = canonical_value(u[i]); }
+    std::vector<uint8_t> ucan(n * 32);
+    for (size_t i = 0; i < n; i++) memcpy(&ucan[32 * i], wGp[i].v, 32);
+    std::vector<Fr> Wc(1, Fr::raw(one_c)), Wd(1, Fr::one()), Ws(1, Fr::raw(one_c));
+    for (size_t k = 0; k < m; k++) {
+        const size_t h = n >> (k + 1), Q = n / (2 * h);
+        // ---- reference: the per-index loops (prover.cpp before this step moved to the device)
+        std::vector<uint8_t> want_ipa((2 * n + 2) * 32), want_sm((n + 2 * h) * 32);
+        Fr ipL = rand_fr(), ipR = rand_fr();
+        const Fr *cL = c.data(), *cR = c.data() + h, *dL = d.data(), *dR = d.data() + h;
+        for (size_t j = 0; j < n; j++) {
+            const size_t i = j & (h - 1);
+            const bool hi = (j & h) != 0;
+            Fr a = wG[j] * (hi ? cL[i] : cR[i]), b = wGp[j] * (hi ? dL[i] : dR[i]);
+            memcpy(&want_ipa[32 * j], a.v, 32); memcpy(&want_ipa[32 * (n + 2 + j)], b.v, 32);
+            Fr e = wS[j] * x[(j & h) ? (j & (h - 1)) : h + (j & (h - 1))];
+            memcpy(&want_sm[32 * j], e.v, 32);
+        }
+        ipL.to_bytes(&want_ipa[32 * n]); ipR.to_bytes(&want_ipa[32 * (n + 1)]);
+        for (size_t i = 0; i < 2 * h; i++) x[i].to_bytes(&want_sm[32 * (n + i)]);
+        // ---- device expansion from the compact blocks
+        std::vector<uint8_t> cmp_ipa((2 * Q + 4 * h + 2) * 32), cmp_sm((Q + 2 * h) * 32), got_ipa((2 * n + 2) * 32, 0xEE), got_sm((n + 2 * h) * 32, 0xEE);
+        uint8_t *w = cmp_ipa.data();
+        for (size_t q = 0; q < Q; q++, w += 32) memcpy(w, Wc[q].v, 32);
+        for (size_t i = 0; i < 2 * h; i++, w += 32) memcpy(w, c[i].v, 32);
+        for (size_t q = 0; q < Q; q++, w += 32) memcpy(w, Wd[q].v, 32);
+        for (size_t i = 0; i < 2 * h; i++, w += 32) memcpy(w, d[i].v, 32);
+        ipL.to_bytes(w); ipR.to_bytes(w + 32);
+        w = cmp_sm.data();
+        for (size_t q = 0; q < Q; q++, w += 32) memcpy(w, Ws[q].v, 32);
+        for (size_t i = 0; i < 2 * h; i++, w += 32) memcpy(w, x[i].v, 32);
+        cdp::round_expand_params_t P0 = {(uint32_t)n, (uint32_t)h, (uint32_t)(2 * n + 2), (uint32_t)(2 * Q + 4 * h + 2), 0};
+        cdp::round_expand_params_t P1 = {(uint32_t)n, (uint32_t)h, (uint32_t)(n + 2 * h), (uint32_t)(Q + 2 * h), 1};
+        for (uint32_t t = 0; t < 5; t++) {
+            cdp::round_expand_thread(0, t, 5, reinterpret_cast<const uint32_t *>(cmp_ipa.data()), reinterpret_cast<const uint32_t *>(ucan.data()), P0,
+                                     reinterpret_cast<uint32_t *>(got_ipa.data()));
+            cdp::round_expand_thread(0, t, 5, reinterpret_cast<const uint32_t *>(cmp_sm.data()), nullptr, P1, reinterpret_cast<uint32_t *>(got_sm.data()));
+        }
+        if (got_ipa != want_ipa || got_sm != want_sm) { printf("expand n=%zu round %zu: mismatch (ipa %d, sm %d)\n", n, k, (int)(got_ipa != want_ipa), (int)(got_sm != want_sm)); return 1; }
+        // ---- the folds: vectors, per-index weights (reference) and prefix weights (new)
+        Fr gamma = rand_fr(), gamma_inv = gamma.inverse(), g2 = rand_fr(), g2_inv = g2.inverse();
+        for (size_t i = 0; i < h; i++) { c[i] += gamma_inv * c[h + i]; d[i] += gamma * d[h + i]; x[i] += g2_inv * x[h + i]; }
+        for (size_t j = 0; j < n; j++)
+            if (j & h) { wG[j] *= gamma; wGp[j] *= gamma_inv; wS[j] *= g2; }
+        std::vector<Fr> Wc2(2 * Q), Wd2(2 * Q), Ws2(2 * Q);
+        for (size_t q = 0; q < Q; q++) {
+            Wc2[2 * q] = Wc[q]; Wc2[2 * q + 1] = Wc[q] * gamma;
+            Wd2[2 * q] = Wd[q]; Wd2[2 * q + 1] = Wd[q] * gamma_inv;
+            Ws2[2 * q] = Ws[q]; Ws2[2 * q + 1] = Ws[q] * g2;
+        }
+        Wc.swap(Wc2); Wd.swap(Wd2); Ws.swap(Ws2);
+    }
+    printf("expand n=%zu ok (%zu rounds)\n", n, m);
+    return 0;
+}
+
 int main() {
+    if (run_expand(8) | run_expand(16) | run_expand(256)) return 1;
+
     int rc = 0;
     for (size_t ell : {4, 12, 124, 252})
         for (bool ex : {false, true}) rc |= run(ell, ex);

@@ -68,13 +68,15 @@ def test_device_verifier_scalar_code_matches_host_restatement_on_cpu():
     """The device-side verifier scalar preparation (csrc/k_vcoeffs.cu, compiled as plain C++): every coefficient of the accumulated check
     -- verification scalars s_i / 1/s_i (/root/reference/src/util.rs:40-64), beta^-(i+1) rescaling, the `a * x_i` products of the eight
     accumulate_check calls (src/msm_accumulator.rs:37-52) and the four SameScalar equalities -- against a vector-at-a-time host restatement
-    with the product's host Fr, on random challenges, ell = 4 / 12 / 124 / 252, both SameScalar modes, three thread counts."""
+    with the product's host Fr, on random challenges, ell = 4 / 12 / 124 / 252, both SameScalar modes, three thread counts.  The same
+    harness checks the prover's device-side round expansion (k_round_expand: prefix weights x folded vector) against the per-index host loops
+    it replaces (/root/reference/src/inner_product_argument.rs:158-179, src/same_multiscalar_argument.rs:107-131)."""
     with tempfile.TemporaryDirectory() as d:
         exe = os.path.join(d, "vcc")
         subprocess.run(["g++", "-O1", "-march=x86-64-v3", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/vcoeffs_check.cpp")], check=True)
         out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
-    assert out.stdout.count(" ok ") == 8
+    assert out.stdout.count(" ok ") == 8 + 3  # 8 coefficient cases + the prover's round expansion for n = 8 / 16 / 256 (all rounds, both arguments)
 
 
 def test_device_verifier_transcript_code_matches_host_transcript_on_cpu():
