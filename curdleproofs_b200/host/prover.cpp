@@ -18,6 +18,8 @@
 //     identity the reference's verifier uses, src/inner_product_argument.rs:202-250), so msm(G^(k)_R, c_L) is an MSM over
 //     the ORIGINAL bases with scalars c_L[j mod h] * w_k(j) -- the G, G' and G_with_blinders vectors are never folded
 //     (3(n-1) + n of the reference's 5(n-1) + n fold scalar-muls disappear); only T and U, which are per-proof, are.
+//     Those n scalars per vector are an outer product (prefix weight x folded vector entry): the host uploads the factors and
+//     cdp_round_expand_dev forms the products on the device (CDP_PROVE_HOST_EXPAND=1: on the host).
 //   * per round: one batched MSM launch (+ one fixed-base launch) over all proofs, one normalise+compress, one D2H,
 //     host transcripts in parallel over proofs, one batched fold launch for T and U.
 #include <algorithm>

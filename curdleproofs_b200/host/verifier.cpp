@@ -11,12 +11,18 @@
 //   * all proof points are decompressed and subgroup-checked on the GPU in one launch;
 //   * every left-hand side the reference builds with scalar-muls and size-m MSMs (`point_lhs`, C_a, D_a, ...) is linear in
 //     points that are already in HBM, so the eight `accumulate_check`s of a proof collapse into ONE msm over
-//     [CRS | R | S | T | U | M | proof points] with host-computed scalars, compared with the identity -- the reference's own
-//     MsmAccumulator idea (random factor per check, src/msm_accumulator.rs:44) taken to its end: no HashMap, a fixed slot table.
-//     The CRS part of that msm (G | Hvec | H | G_t | G_u, n + 3 bases shared by every proof) goes through the fixed-base digit
-//     table; the per-proof part (4 ell + 1 + proof points) through the variable-base kernel; the two partial sums are added;
-//   * the four point equalities of SameScalar are checked exactly as four short MSMs that must be the identity;
-//   * only two values have to come back mid-transcript: D (grand_product_argument.rs:223) and A' (curdleproofs.rs:255).
+//     [CRS | R | S | T | U | M | proof points], compared with the identity -- the reference's own MsmAccumulator idea (random factor
+//     per check, src/msm_accumulator.rs:44) taken to its end: no HashMap, a fixed slot table.  The CRS part of that msm (G | Hvec | H |
+//     G_t | G_u, n + 3 bases shared by every proof) goes through the fixed-base digit table, the per-proof part (4 ell + 1 + proof
+//     points) through the variable-base kernels;
+//   * the four point equalities of SameScalar join that check with their own random factors (CDP_VERIFY_EXACT_EQ=1: four exact MSMs);
+//   * the transcript runs on the device as well (vlane_verify_dev: cdp_transcript_open_dev, cdp_verify_transcript_{a,b}_dev around the
+//     fixed-base launch for the two points the transcript needs, D (grand_product_argument.rs:223) and A' (curdleproofs.rs:255)), and so
+//     does the scalar algebra (cdp_verify_coeffs_dev); the host parses, stages and draws the random factors.  vlane_verify keeps the
+//     older flow with the per-round transcript on the host (CDP_VERIFY_HOST_TRANSCRIPT=1);
+//   * by default a lane first runs the MERGED check of its sub-batch (merged_stage: all per-proof bases in one large MSM, the CRS
+//     coefficients summed across proofs) and only falls back to one accumulated MSM per proof (per_proof_stage) when that is not the
+//     identity or a proof of the sub-batch is malformed: same verdicts either way.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
