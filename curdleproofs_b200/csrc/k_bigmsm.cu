@@ -7,10 +7,12 @@
 //                    so window w is the slice [w * 2n, (w+1) * 2n) of the sorted array)
 //   k_big_offsets    bucket boundaries from the sorted keys
 //   k_big_accumulate one thread per (window, bucket): mixed additions over the bucket's points (gathered 96-byte loads, the
-//                    base array is L2-resident up to ~2^20 points)
-//   bucket reduction: sum_b (b+1) B_b per window.  The buckets are normalised to affine and handed to the batched small-MSM
-//                    kernel with the constant weights 1..2^(c-1) as (15/16-bit) scalars -- a segmented weighted sum -- followed by
-//   k_big_final      per-window chunk sums + Horner over the windows.
+//                    base array is L2-resident up to ~2^20 points); the top window's few long buckets are spread over sp_top threads
+//                    (k_big_fold_top adds their partial sums); a bucket whose per-thread share exceeds BIG_HEAVY points (skewed
+//                    scalars) goes to a device-side work list instead: k_big_heavy (one CTA per 4096-point chunk), k_big_heavy_fold
+//   k_big_reduce_level   sum_b (b+1) B_b per window as a hierarchy of 16-ary running sums (A = plain sum, Bv = index-weighted sum per node)
+//   k_big_horner     Horner over the windows.
+// (k_big_weights / k_big_final belong to an earlier reduction through the small-MSM kernel and are kept for experiments.)
 #include <cub/device/device_radix_sort.cuh>
 
 #include "launch.h"
