@@ -407,6 +407,22 @@ extern "C" int cdp_round_expand_dev(cdp_ctx *ctx, const uint8_t *d_compact, cons
     return CDP_OK;
 }
 
+extern "C" size_t cdp_prove_work_scalars(size_t ell) { return 11 * (ell + 4) + 64; }
+extern "C" size_t cdp_prove_random_scalars(size_t ell) { return 3 * (ell + 4) + 11; }
+extern "C" int cdp_prove_stage_dev(cdp_ctx *ctx, const cdp_prove_dev *P, int stage, unsigned round) {
+    if (!ctx || !P || stage < CDP_PS_S1 || stage > CDP_PS_SM_ROUND) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_stage_dev: bad argument");
+    if (P->batch == 0) return CDP_OK;
+    const size_t n = (size_t)P->ell + 4;
+    if (P->ell < 4 || ((size_t)1 << P->m) != n || round >= P->m || !P->d_state || !P->d_vec_a || !P->d_perm || !P->d_witness || !P->d_random ||
+        !P->d_work || !P->d_comp0_vecs || !P->d_comp0_M || !P->d_comp_H || !P->d_comp || !P->d_side || !P->d_proofs || !P->d_scalars ||
+        !P->d_fold_scalars)
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_stage_dev: inconsistent parameters");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_OTHER, P->batch);
+    CUDA_TRY(ctx, launch_prove_stage(ctx->stream, *P, stage, round));
+    return CDP_OK;
+}
+
 extern "C" int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_stride, size_t cols, size_t rows, uint8_t *d_out) {
     if (!ctx || (cols && rows && (!d_scalars || !d_out)) || row_stride < cols) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_sum_scalars_dev: bad argument");
     if (cols == 0) return CDP_OK;

@@ -23,6 +23,7 @@
 //   * per round: one batched MSM launch (+ one fixed-base launch) over all proofs, one normalise+compress, one D2H,
 //     host transcripts in parallel over proofs, one batched fold launch for T and U.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -128,6 +129,14 @@ struct Lane {
     bool dev_expand = true;  // CDP_PROVE_HOST_EXPAND=1: the n products per vector per round on the host (the older path)
     uint8_t *d_veca = nullptr, *d_tstate = nullptr, *h_veca = nullptr, *h_tstate = nullptr;  // device-side transcript opening
     uint8_t *d_jac = nullptr, *d_comp = nullptr;
+    // device-side prover (cdp_prove_stage_dev): the transcript and the Fr algebra of every step run on the GPU, the host only stages inputs
+    // and draws the randomness.  CDP_PROVE_HOST_TRANSCRIPT=1 keeps the older host path (same proofs).
+    bool dev_prove = true;
+    uint8_t *d_comp0 = nullptr;    // encodings of the instance (4 ell per proof, then one M per proof): read again by same_msm_step1
+    uint8_t *d_compH = nullptr;    // encoding of crs.H
+    uint32_t *d_perm = nullptr, *h_perm = nullptr;
+    uint8_t *d_wit = nullptr, *h_wit = nullptr, *d_rnd = nullptr, *h_rnd = nullptr, *d_work = nullptr, *d_side = nullptr, *d_proofs = nullptr,
+            *h_proofs = nullptr;
     uint8_t *h_scal = nullptr, *h_fscal = nullptr, *h_comp = nullptr, *h_in = nullptr;
     size_t max_scalars_pp = 0, max_out_pp = 0;
     size_t staged_batch = 0;
@@ -414,9 +423,10 @@ static void lane_destroy(Lane *p) {
     for (auto &s : p->st_sm) free_stage(s);
     for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
-                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_cmp, (void *)p->d_ucan, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate})
+                    (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_cmp, (void *)p->d_ucan, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_comp0, (void *)p->d_compH,
+                    (void *)p->d_perm, (void *)p->d_wit, (void *)p->d_rnd, (void *)p->d_work, (void *)p->d_side, (void *)p->d_proofs})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_cmp, (void *)p->h_ucan, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_cmp, (void *)p->h_ucan, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_perm, (void *)p->h_wit, (void *)p->h_rnd, (void *)p->h_proofs}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -523,6 +533,18 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     p->d_veca = (uint8_t *)dalloc(max_batch * ell * 32); p->h_veca = (uint8_t *)halloc(max_batch * ell * 32);
     p->d_tstate = (uint8_t *)dalloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES); p->h_tstate = (uint8_t *)halloc(max_batch * CDP_TRANSCRIPT_STATE_BYTES);
     p->d_jac = (uint8_t *)dalloc(max_batch * p->max_out_pp * 144);
+    if (const char *e = getenv("CDP_PROVE_HOST_TRANSCRIPT")) p->dev_prove = atoi(e) == 0;
+    p->d_comp0 = (uint8_t *)dalloc(max_batch * in_pp * 48);
+    p->d_compH = (uint8_t *)dalloc(48);
+    if (p->dev_prove) {
+        const size_t psz = cdp_proof_size(ell), nrnd = cdp_prove_random_scalars(ell);
+        p->d_perm = (uint32_t *)dalloc(max_batch * ell * 4); p->h_perm = (uint32_t *)halloc(max_batch * ell * 4);
+        p->d_wit = (uint8_t *)dalloc(max_batch * 5 * 32); p->h_wit = (uint8_t *)halloc(max_batch * 5 * 32);
+        p->d_rnd = (uint8_t *)dalloc(max_batch * nrnd * 32); p->h_rnd = (uint8_t *)halloc(max_batch * nrnd * 32);
+        p->d_work = (uint8_t *)dalloc(max_batch * cdp_prove_work_scalars(ell) * 32);
+        p->d_side = (uint8_t *)dalloc(max_batch * 96);
+        p->d_proofs = (uint8_t *)dalloc(max_batch * psz); p->h_proofs = (uint8_t *)halloc(max_batch * psz);
+    }
     p->d_comp = (uint8_t *)dalloc(max_batch * max_out * 48);
     p->h_comp = (uint8_t *)halloc(max_batch * max_out * 48);
     // gather tables.  From the CRS block: the blinder slots of T / U (H) and the constant entries of the X block
@@ -565,14 +587,134 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     rc |= cdp_h2d(ctx, p->d_isrc, isrc.data(), isrc.size() * 4);
     rc |= cdp_h2d(ctx, p->d_idst, idst.data(), idst.size() * 4);
     // compressed H for the blinder slots of the same_msm transcript message
-    rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_comp);
-    rc |= cdp_d2h(ctx, p->h_comp, p->d_comp, 48);
+    rc |= cdp_compress_affine_dev(ctx, p->d_pts + cH * 96, nullptr, 1, p->d_compH);
+    rc |= cdp_d2h(ctx, p->h_comp, p->d_compH, 48);
     rc |= cdp_sync(ctx);
     if (rc) { p->err = std::string("setup: ") + cdp_last_error(ctx); lane_destroy(p); return CDP_ERR_CUDA; }
     memcpy(p->H_comp, p->h_comp, 48);
     if (upload_tables(p) != CDP_OK) { lane_destroy(p); return CDP_ERR_CUDA; }
     p->ps.resize(max_batch);
     *out = p;
+    return CDP_OK;
+}
+
+// the prover's `rng` for proof pr (cdp_prove_inputs): a 32-byte ChaCha12 key, the reference's test-vector u64 seed, or a fresh key from the OS
+static bool make_rng(const cdp_prove_inputs *in, size_t pr, StdRng &rng) {
+    if (in->rng_key) rng = StdRng(StdRng::from_key_t{}, in->rng_key + 32 * pr);
+    else if (in->rng_seed) rng = StdRng(in->rng_seed[pr]);
+    else {
+        uint8_t key[32];
+        if (!StdRng::os_key(key)) return false;
+        rng = StdRng(StdRng::from_key_t{}, key);
+    }
+    if (in->rng_skip_words) rng.skip_words(in->rng_skip_words[pr]);
+    return true;
+}
+
+namespace {
+uint32_t out_map_entry(const MsmStage &st, size_t q) {
+    size_t base = 0;
+    for (int s = 0; s < st.where[q].first; s++) base += st.subs[s].K;
+    return (uint32_t)((base << 16) | (st.subs[st.where[q].first].K << 8) | (size_t)st.where[q].second);
+}
+// every launch of one MSM stage (its scalars are already in d_scal), then normalise + compress into d_comp; nothing returns to the host
+int enqueue_msm_stage(Lane *p, MsmStage &st, size_t B) {
+    size_t out_off = 0;
+    for (auto &sl : st.subs) {
+        if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144));
+        else PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
+        out_off += B * sl.K;
+    }
+    PTRY(cdp_normalize_dev(p->ctx, p->d_jac, out_off, st.aff_region != (size_t)-1 ? p->d_pts + st.aff_region * 96 : nullptr, p->d_comp));
+    return CDP_OK;
+}
+// one step of the device-side transcript + scalar algebra: reads the outputs of `consumed`, writes the scalars of the next stage
+int enqueue_prove_stage(Lane *p, cdp_prove_dev &P, int stage, unsigned round, const MsmStage *consumed, size_t emitted_spp) {
+    memset(P.out_map, 0, sizeof P.out_map);
+    if (consumed)
+        for (size_t q = 0; q < consumed->outputs(); q++) P.out_map[q] = out_map_entry(*consumed, q);
+    P.scalars_per_proof = (uint32_t)emitted_spp;
+    PTRY(cdp_prove_stage_dev(p->ctx, &P, stage, round));
+    return CDP_OK;
+}
+}  // namespace
+
+// `CurdleproofsProof::new` for a sub-batch with the whole protocol on the device: after the instance, the witnesses and the prover's
+// randomness are in HBM, the lane is ONE stream of kernels (MSM launches alternating with cdp_prove_stage_dev steps) and one
+// synchronisation; the host's only arithmetic is the ChaCha12 stream of the randomness.
+static int lane_prove_device(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *proofs_out, double t_start, double t_copy) {
+    const size_t ell = p->ell, n = p->n, m = p->m;
+    const int T = p->threads;
+    const size_t proof_size = cdp_proof_size(ell), nrnd = cdp_prove_random_scalars(ell);
+    double t0 = now_ms(), t_host = 0, t_wait = 0;
+    // witnesses and randomness (all draws in the reference's order; they do not depend on the transcript)
+    std::vector<int> rng_ok(B, 1);
+    parallel_for(T, B, [&](size_t pr) {
+        memcpy(p->h_perm + pr * ell, in->permutation + pr * ell, ell * 4);
+        memcpy(p->h_wit + pr * 160, in->k + 32 * pr, 32);
+        memcpy(p->h_wit + pr * 160 + 32, in->vec_m_blinders + 128 * pr, 128);
+        StdRng rng(0);
+        if (!make_rng(in, pr, rng)) { rng_ok[pr] = 0; return; }
+        uint64_t *w = reinterpret_cast<uint64_t *>(p->h_rnd + pr * nrnd * 32);
+        auto draw = [&](size_t slot) { Fr x = rng.fr_rand(); memcpy(w + 4 * slot, x.v, 32); };
+        for (size_t i = 0; i < 6; i++) draw(i);                       // r_a[2] (curdleproofs.rs:86), r_c[4] (grand_product_argument.rs:75)
+        for (size_t i = 0; i < n; i++) draw(6 + i);                   // inner_product_argument.rs:46
+        for (size_t i = 0; i + 2 < n; i++) draw(6 + n + i);           // :47
+        memset(w + 4 * (6 + 2 * n - 2), 0, 64);                       // the two entries solved for on the device (:53-77)
+        for (size_t i = 0; i < 5; i++) draw(6 + 2 * n + i);           // r_t r_u (curdleproofs.rs:110-111), r_a r_b r_k (same_scalar_argument.rs:56-58)
+        for (size_t i = 0; i < n; i++) draw(11 + 2 * n + i);          // same_multiscalar_argument.rs:78
+    });
+    for (size_t pr = 0; pr < B; pr++)
+        if (!rng_ok[pr]) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: no entropy source for the prover's randomness");
+    t_host += now_ms() - t0;
+    t0 = now_ms();
+    PTRY(cdp_h2d(p->ctx, p->d_perm, p->h_perm, B * ell * 4));
+    PTRY(cdp_h2d(p->ctx, p->d_wit, p->h_wit, B * 160));
+    PTRY(cdp_h2d(p->ctx, p->d_rnd, p->h_rnd, B * nrnd * 32));
+    p->h2d_bytes += B * (ell * 4 + 160 + nrnd * 32);
+
+    cdp_prove_dev P;
+    memset(&P, 0, sizeof P);
+    P.ell = (uint32_t)ell; P.m = (uint32_t)m; P.batch = (uint32_t)B; P.proof_bytes = (uint32_t)proof_size;
+    P.d_state = p->d_tstate; P.d_vec_a = p->d_veca; P.d_perm = p->d_perm; P.d_witness = p->d_wit; P.d_random = p->d_rnd; P.d_work = p->d_work;
+    P.d_comp0_vecs = p->d_comp0; P.d_comp0_M = p->d_comp0 + B * 4 * ell * 48; P.d_comp_H = p->d_compH; P.d_comp = p->d_comp;
+    P.d_side = p->d_side; P.d_proofs = p->d_proofs; P.d_scalars = p->d_scal; P.d_fold_scalars = p->d_fscal;
+
+    if (int rc = enqueue_prove_stage(p, P, CDP_PS_S1, 0, nullptr, p->st1.scalars_per_proof)) return rc;
+    if (int rc = enqueue_msm_stage(p, p->st1, B)) return rc;
+    if (int rc = enqueue_prove_stage(p, P, CDP_PS_SAMEPERM, 0, &p->st1, p->st2.scalars_per_proof)) return rc;
+    PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_x1src, p->d_x1dst, B * 4));  // A, R, S (affine, from stage 1) -> X block
+    if (int rc = enqueue_msm_stage(p, p->st2, B)) return rc;
+    if (int rc = enqueue_prove_stage(p, P, CDP_PS_GPROD1, 0, &p->st2, p->st3.scalars_per_proof)) return rc;
+    if (int rc = enqueue_msm_stage(p, p->st3, B)) return rc;
+    if (int rc = enqueue_prove_stage(p, P, CDP_PS_GPROD2, 0, &p->st3, p->st4.scalars_per_proof)) return rc;
+    PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_x2src, p->d_x2dst, B));      // B (affine, from stage 2) -> X block
+    if (int rc = enqueue_msm_stage(p, p->st4, B)) return rc;
+    if (int rc = enqueue_prove_stage(p, P, CDP_PS_IPA0, 0, &p->st4, p->st_ipa[0].scalars_per_proof)) return rc;
+    for (size_t k = 0; k < m; k++) {
+        if (int rc = enqueue_msm_stage(p, p->st_ipa[k], B)) return rc;
+        const size_t next_spp = k + 1 < m ? p->st_ipa[k + 1].scalars_per_proof : p->st_sm[0].scalars_per_proof;
+        if (int rc = enqueue_prove_stage(p, P, CDP_PS_IPA_ROUND, (unsigned)k, &p->st_ipa[k], next_spp)) return rc;
+    }
+    for (size_t k = 0; k < m; k++) {
+        if (int rc = enqueue_msm_stage(p, p->st_sm[k], B)) return rc;
+        const size_t next_spp = p->st_sm[k + 1 < m ? k + 1 : k].scalars_per_proof;
+        if (int rc = enqueue_prove_stage(p, P, CDP_PS_SM_ROUND, (unsigned)k, &p->st_sm[k], next_spp)) return rc;
+        if ((n >> (k + 1)) > 1) PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, p->f_sm[k].d_jobs, B * p->f_sm[k].J, p->f_sm[k].epj));  // T, U folds (:128-129)
+    }
+    PTRY(cdp_d2h(p->ctx, p->h_proofs, p->d_proofs, B * proof_size));
+    p->d2h_bytes += B * proof_size;
+    t_copy += now_ms() - t0;
+    t0 = now_ms();
+    PTRY(cdp_sync(p->ctx));
+    t_wait += now_ms() - t0;
+    t0 = now_ms();
+    memcpy(proofs_out, p->h_proofs, B * proof_size);
+    t_host += now_ms() - t0;
+    p->timing[0] = now_ms() - t_start;
+    p->timing[1] = t_host;
+    p->timing[2] = t_wait;
+    p->timing[3] = t_copy;
     return CDP_OK;
 }
 
@@ -625,11 +767,13 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     }
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_gsrc, p->d_gdst, B * p->g_count_per_proof));
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_in, p->d_isrc, p->d_idst, B * p->i_count_per_proof));
-    PTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp));
-    PTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp + B * 4 * ell * 48));
-    // transcript opening (R, S, T, U, M -> vec_a) hashed on the device; the host continues from the returned STROBE states
-    PTRY(cdp_transcript_open_dev(p->ctx, p->d_comp, p->d_comp + B * 4 * ell * 48, ell, B, p->d_veca, p->d_tstate));
-    PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp, (B * 4 * ell + B) * 48));
+    PTRY(cdp_compress_affine_dev(p->ctx, p->d_in, nullptr, B * 4 * ell, p->d_comp0));
+    PTRY(cdp_compress_affine_dev(p->ctx, p->d_in + Moff * 96, nullptr, B, p->d_comp0 + B * 4 * ell * 48));
+    // transcript opening (R, S, T, U, M -> vec_a) hashed on the device
+    PTRY(cdp_transcript_open_dev(p->ctx, p->d_comp0, p->d_comp0 + B * 4 * ell * 48, ell, B, p->d_veca, p->d_tstate));
+    if (p->dev_prove) return lane_prove_device(p, B, in, proofs_out, t_start, t_copy + now_ms() - t0);
+    // older path: the host continues the transcripts from the returned STROBE states
+    PTRY(cdp_d2h(p->ctx, p->h_comp, p->d_comp0, (B * 4 * ell + B) * 48));
     PTRY(cdp_d2h(p->ctx, p->h_veca, p->d_veca, B * ell * 32));
     PTRY(cdp_d2h(p->ctx, p->h_tstate, p->d_tstate, B * CDP_TRANSCRIPT_STATE_BYTES));
     p->d2h_bytes += (B * 4 * ell + B) * 48 + B * ell * 32 + B * CDP_TRANSCRIPT_STATE_BYTES;
@@ -642,6 +786,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     //      same_multiscalar_argument.rs:78-82)
     t0 = now_ms();
     std::vector<uint8_t> tu_comp(B * 2 * n * 48);  // vec_T_with_blinders | vec_U_with_blinders encodings, kept for same_msm_step1
+    std::atomic<bool> rng_fail{false};
     parallel_for(T, B, [&](size_t pr) {
         ProofState &s = p->ps[pr];
         const uint8_t *cmp = p->h_comp + pr * 4 * ell * 48;
@@ -661,8 +806,8 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         Fr::from_bytes(in->k + 32 * pr, s.k);
         for (int i = 0; i < 4; i++) Fr::from_bytes(in->vec_m_blinders + 32 * (4 * pr + i), s.m_bl[i]);
         // all prover randomness, in the reference's draw order
-        StdRng rng(in->rng_seed[pr]);
-        if (in->rng_skip_words) rng.skip_words(in->rng_skip_words[pr]);
+        StdRng rng(0);
+        if (!make_rng(in, pr, rng)) { rng_fail = true; return; }
         s.a_bl[0] = rng.fr_rand(); s.a_bl[1] = rng.fr_rand();                 // curdleproofs.rs:86
         for (int i = 0; i < 4; i++) s.c_bl[i] = rng.fr_rand();                  // grand_product_argument.rs:75
         s.r_c.resize(n); s.r_d.resize(n);
@@ -688,6 +833,7 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
         s.sm_rounds.resize(m * 6 * 48);
     });
     t_host += now_ms() - t0;
+    if (rng_fail) return perr(p, CDP_ERR_INVALID_ARG, "cdp_prove_batch: no entropy source for the prover's randomness");
     if (int rc = run_msm_stage(p, p->st1, B, t_wait, t_copy)) return rc;
 
     // ---- same_perm (same_permutation_argument.rs:60-82) -> stage 2: B
@@ -1073,6 +1219,11 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
                                        int lanes) {
     if (!out || !ctx || !crs_points || max_batch == 0) return CDP_ERR_INVALID_ARG;
     *out = nullptr;
+    {   // checked before the (multi-GiB) digit table is built: ell >= N_BLINDERS, ell + 4 a power of two (src/inner_product_argument.rs:116)
+        const size_t n = ell + NBL;
+        if (ell < 4 || (n & (n - 1)) != 0) return CDP_ERR_INVALID_ARG;
+        if (n + 1 > 2048) return CDP_ERR_TOO_LARGE;
+    }
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (host_threads <= 0) host_threads = hw;
     if (lanes <= 0) lanes = max_batch >= 512 ? 8 : max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
@@ -1090,8 +1241,8 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     std::vector<uint8_t> crs_ext((ell + 9) * 96);
     {
         memcpy(crs_ext.data(), crs_points, (ell + 7) * 96);
-        std::vector<uint8_t> ones(32 * ell, 0), sums(2 * 144);
-        for (size_t i = 0; i < ell; i++) ones[32 * i] = 1;
+        std::vector<uint8_t> ones(32 * std::max(ell, NBL), 0), sums(2 * 144);
+        for (size_t i = 0; i < std::max(ell, NBL); i++) ones[32 * i] = 1;
         int rc = cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
         if (rc == CDP_OK) rc = cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
         if (rc == CDP_OK) rc = cdp_normalize_batch(ctx, sums.data(), 2, crs_ext.data() + (ell + 7) * 96);
@@ -1124,6 +1275,24 @@ extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *
     if (!p) return CDP_ERR_INVALID_ARG;
     if (!in || !proofs_out || B == 0 || B > p->max_batch) { p->err = "cdp_prove_batch: bad argument"; return CDP_ERR_INVALID_ARG; }
     const size_t L = p->lanes.size(), ell = p->ell, psz = cdp_proof_size(ell);
+    if (!in->permutation || !in->k || !in->vec_m_blinders) { p->err = "cdp_prove_batch: missing witness"; return CDP_ERR_INVALID_ARG; }
+    if (in->vec_R && (!in->vec_S || !in->vec_T || !in->vec_U || !in->M)) { p->err = "cdp_prove_batch: missing instance vector"; return CDP_ERR_INVALID_ARG; }
+    {   // witnesses: every permutation a bijection of 0..ell-1 (the reference indexes with it and panics out of range), scalars canonical
+        std::vector<uint8_t> seen(ell);
+        for (size_t pr = 0; pr < B; pr++) {
+            std::fill(seen.begin(), seen.end(), 0);
+            for (size_t i = 0; i < ell; i++) {
+                const uint32_t v = in->permutation[pr * ell + i];
+                if (v >= ell || seen[v]) { p->err = "cdp_prove_batch: permutation " + std::to_string(pr) + " is not a bijection of 0..ell-1"; return CDP_ERR_INVALID_ARG; }
+                seen[v] = 1;
+            }
+            uint64_t w[4];
+            for (int j = 0; j < 5; j++) {
+                memcpy(w, j == 0 ? in->k + 32 * pr : in->vec_m_blinders + 128 * pr + 32 * (j - 1), 32);
+                if (Fr::geq_mod(w)) { p->err = "cdp_prove_batch: witness scalar of proof " + std::to_string(pr) + " is not canonical"; return CDP_ERR_INVALID_ARG; }
+            }
+        }
+    }
     // contiguous split, as even as possible
     std::vector<size_t> off(L + 1, 0);
     for (size_t i = 0; i < L; i++) off[i + 1] = off[i] + (B / L + (i < B % L ? 1 : 0));
@@ -1143,8 +1312,9 @@ extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *
         sub.permutation = in->permutation + o * ell;
         sub.k = in->k + o * 32;
         sub.vec_m_blinders = in->vec_m_blinders + o * 128;
-        sub.rng_seed = in->rng_seed + o;
+        sub.rng_seed = in->rng_seed ? in->rng_seed + o : nullptr;
         sub.rng_skip_words = in->rng_skip_words ? in->rng_skip_words + o : nullptr;
+        sub.rng_key = in->rng_key ? in->rng_key + 32 * o : nullptr;
         rcs[i] = lane_prove(p->lanes[i], cnt, &sub, proofs_out + o * psz);
     };
     if (L == 1) run(0);
@@ -1187,7 +1357,15 @@ extern "C" size_t cdp_whisk_shuffle_proof_size(size_t ell) { return 48 + cdp_pro
 extern "C" int cdp_whisk_generate_shuffle_proofs(cdp_prover *p, size_t B, const uint8_t *pre_trackers, const uint64_t *rng_seed,
                                                  const uint64_t *rng_skip_words, uint8_t *post_out, uint8_t *proofs_out) {
     if (!p) return CDP_ERR_INVALID_ARG;
-    if (!pre_trackers || !rng_seed || !post_out || !proofs_out || B == 0 || B > p->max_batch) { p->err = "cdp_whisk_generate_shuffle_proofs: bad argument"; return CDP_ERR_INVALID_ARG; }
+    if (!pre_trackers || !post_out || !proofs_out || B == 0 || B > p->max_batch) { p->err = "cdp_whisk_generate_shuffle_proofs: bad argument"; return CDP_ERR_INVALID_ARG; }
+    // rng_seed == NULL: every shuffle gets a fresh 256-bit ChaCha12 key from the operating system (what a production caller wants; the
+    // u64 seeds reproduce the reference's test vectors and carry 64 bits of entropy at most)
+    std::vector<uint8_t> keys;
+    if (!rng_seed) {
+        keys.resize(32 * B);
+        for (size_t b = 0; b < B; b++)
+            if (!StdRng::os_key(keys.data() + 32 * b)) { p->err = "cdp_whisk_generate_shuffle_proofs: no entropy source"; return CDP_ERR_INVALID_ARG; }
+    }
     cdp_ctx *ctx = p->ctx0;
     const size_t ell = p->ell, n = ell + NBL, psz = cdp_proof_size(ell), np = B * ell;
     auto fail = [&](int rc, const char *what) { p->err = std::string(what) + ": " + cdp_last_error(ctx); return rc; };
@@ -1196,7 +1374,7 @@ extern "C" int cdp_whisk_generate_shuffle_proofs(cdp_prover *p, size_t B, const 
     std::vector<uint8_t> kk(32 * B), mbl(128 * B);
     std::vector<uint64_t> skip(B);
     for (size_t b = 0; b < B; b++) {
-        StdRng rng(rng_seed[b]);
+        StdRng rng = rng_seed ? StdRng(rng_seed[b]) : StdRng(StdRng::from_key_t{}, keys.data() + 32 * b);
         if (rng_skip_words) rng.skip_words(rng_skip_words[b]);
         uint32_t *pm = perm.data() + b * ell;
         for (size_t i = 0; i < ell; i++) pm[i] = (uint32_t)i;
@@ -1237,6 +1415,7 @@ extern "C" int cdp_whisk_generate_shuffle_proofs(cdp_prover *p, size_t B, const 
     cdp_prove_inputs in;
     in.vec_R = R.data(); in.vec_S = S.data(); in.vec_T = T.data(); in.vec_U = U.data(); in.M = M.data();
     in.permutation = perm.data(); in.k = kk.data(); in.vec_m_blinders = mbl.data(); in.rng_seed = rng_seed; in.rng_skip_words = skip.data();
+    in.rng_key = rng_seed ? nullptr : keys.data();
     rc = cdp_prove_batch(p, B, &in, proofs.data());
     if (rc != CDP_OK) return rc;
     // zip_trackers + serialisation: compress T, U (interleaved) and M

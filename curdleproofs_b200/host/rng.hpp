@@ -5,6 +5,8 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <sys/random.h>
+#include <sys/types.h>
 
 #include "fr.hpp"
 
@@ -20,6 +22,12 @@ class StdRng {
             key_[i] = (x >> rot) | (x << ((32 - rot) & 31));
         }
     }
+    // `StdRng::from_seed`: the 32 bytes are the ChaCha12 key itself.  What a production caller uses (a key from its own CSPRNG); the 64-bit
+    // seed_from_u64 form above exists for the reference's test vectors and carries at most 64 bits of entropy.
+    struct from_key_t {};
+    StdRng(from_key_t, const uint8_t key[32]) { memcpy(key_, key, 32); }
+    // 32 fresh bytes from the operating system (getrandom); false when the entropy source is unavailable
+    static bool os_key(uint8_t key[32]);
     uint32_t next_u32() {
         consumed_++;
         if (idx_ >= 64) { refill(); idx_ = 0; }
@@ -102,5 +110,15 @@ class StdRng {
         counter_ += 4;
     }
 };
+
+inline bool StdRng::os_key(uint8_t key[32]) {
+    size_t got = 0;
+    while (got < 32) {
+        ssize_t r = getrandom(key + got, 32 - got, 0);
+        if (r <= 0) return false;
+        got += (size_t)r;
+    }
+    return true;
+}
 
 }  // namespace cdp_host

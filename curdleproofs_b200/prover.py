@@ -12,7 +12,7 @@ from .engine import AFFINE_BYTES, JACOBIAN_BYTES, SCALAR_BYTES, CdpError, Engine
 class _ProveInputs(ctypes.Structure):
     _fields_ = [("vec_R", c_void_p), ("vec_S", c_void_p), ("vec_T", c_void_p), ("vec_U", c_void_p), ("M", c_void_p),
                 ("permutation", c_void_p), ("k", c_void_p), ("vec_m_blinders", c_void_p), ("rng_seed", c_void_p),
-                ("rng_skip_words", c_void_p)]
+                ("rng_skip_words", c_void_p), ("rng_key", c_void_p)]
 
 
 _PLIB = None
@@ -89,24 +89,26 @@ class BatchProver:
         except Exception:
             pass
 
-    def prove_batch(self, instances, rng_seeds, rng_skip_words=None) -> list[bytes]:
+    def prove_batch(self, instances, rng_seeds=None, rng_skip_words=None, rng_keys=None) -> list[bytes]:
         """instances: list of dicts with R, S, T, U (ell affine each), M (jacobian), perm (list of int), k, m_blinders.
-        rng_seeds[i] seeds the prover's StdRng for proof i (the reference's `rng` argument)."""
+        The reference's `rng` argument, per proof: rng_keys[i] (32 bytes, `StdRng::from_seed`) or rng_seeds[i] (`seed_from_u64`: test vectors
+        only, 64 bits of entropy); with neither, every proof draws a fresh key from the operating system."""
         B = len(instances)
         ell = self.ell
         cat = lambda key: b"".join(i[key] for i in instances)  # noqa: E731
         bufs = dict(R=_arr(cat("R")), S=_arr(cat("S")), T=_arr(cat("T")), U=_arr(cat("U")), M=_arr(cat("M")), k=_arr(cat("k")),
                     mb=_arr(cat("m_blinders")))
         perm = (c_uint32 * (B * ell))(*[x for i in instances for x in i["perm"]])
-        seeds = (c_uint64 * B)(*rng_seeds)
+        seeds = (c_uint64 * B)(*rng_seeds) if rng_seeds is not None else None
         skips = (c_uint64 * B)(*rng_skip_words) if rng_skip_words is not None else None
-        return self.prove_raw(B, bufs["R"], bufs["S"], bufs["T"], bufs["U"], bufs["M"], perm, bufs["k"], bufs["mb"], seeds, skips)
+        keys = _arr(b"".join(rng_keys)) if rng_keys is not None else None
+        return self.prove_raw(B, bufs["R"], bufs["S"], bufs["T"], bufs["U"], bufs["M"], perm, bufs["k"], bufs["mb"], seeds, skips, keys=keys)
 
-    def prove_raw(self, B, R, S, T, U, M, perm, k, mb, seeds, skips=None, out=None, split=True):
+    def prove_raw(self, B, R, S, T, U, M, perm, k, mb, seeds, skips=None, out=None, split=True, keys=None):
         # R is None: reuse the instance batch staged in HBM by the previous call ("inputs already resident" mode)
         vp = lambda x: ctypes.cast(x, c_void_p) if x is not None else None  # noqa: E731
         inp = _ProveInputs(vp(R), vp(S), vp(T), vp(U), vp(M), ctypes.cast(perm, c_void_p), ctypes.cast(k, c_void_p), ctypes.cast(mb, c_void_p),
-                           ctypes.cast(seeds, c_void_p), ctypes.cast(skips, c_void_p) if skips is not None else None)
+                           vp(seeds), vp(skips), vp(keys))
         if out is None:
             out = (ctypes.c_uint8 * (B * self.proof_size))()
         rc = self._lib.cdp_prove_batch(self._h, B, ctypes.byref(inp), out)

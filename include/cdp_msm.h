@@ -256,6 +256,50 @@ int cdp_verify_coeffs_dev(cdp_ctx *ctx, const uint8_t *d_challenges, const uint8
 int cdp_round_expand_dev(cdp_ctx *ctx, const uint8_t *d_compact, const uint8_t *d_u_canonical, size_t n, size_t h, size_t scalars_per_proof,
                          size_t compact_per_proof, int mode, size_t batch, uint8_t *d_scalars_out);
 
+/* ------------------------------------------------------------------ the prover's transcript + scalar algebra on the device
+ * SURVEY.md 8(f) rank 1, prover half.  Between two group launches `CurdleproofsProof::new` (/root/reference/src/curdleproofs.rs:59-184) appends
+ * the new points to the merlin transcript, draws challenges (/root/reference/src/transcript.rs:28-61) and does O(n) arithmetic in Fr to form
+ * the next launch's scalars.  cdp_prove_stage_dev runs one such step for a whole batch, one CTA per proof (csrc/k_prove.cu), so that a batch
+ * goes from cdp_transcript_open_dev to the serialised proof bytes without a host round trip:
+ *   CDP_PS_S1         witness vectors and blinders (curdleproofs.rs:86-116)                 -> scalars of A, R, S, B_a, B_t, B_u, T_1, U_1, A_1, B_1
+ *   CDP_PS_SAMEPERM   same_permutation_argument.rs:60-82                                    -> scalars of B, T_2, A_2, U_2, B_2, A'
+ *   CDP_PS_GPROD1     grand_product_argument.rs:63-83                                       -> scalars of C
+ *   CDP_PS_GPROD2     grand_product_argument.rs:85-147, inner_product_argument.rs:53-77     -> scalars of D, B_c, B_d
+ *   CDP_PS_IPA0       inner_product_argument.rs:129-140                                     -> scalars of IPA round 0
+ *   CDP_PS_IPA_ROUND  inner_product_argument.rs:150-186 for `round`; the last round goes on through same_scalar_argument.rs:64-75 and
+ *                     same_multiscalar_argument.rs:84-91                                    -> scalars of IPA round + 1 / SameMSM round 0
+ *   CDP_PS_SM_ROUND   same_multiscalar_argument.rs:99-136 for `round`                       -> fold scalar gamma + scalars of SameMSM round + 1
+ * Scalar layouts per stage are those of host/prover.cpp's stage tables (round MSMs over the ORIGINAL CRS bases).  Every stage also writes
+ * the points it consumed, and the proof's scalars, into d_proofs (`CurdleproofsProof::serialize` layout). */
+enum { CDP_PS_S1 = 0, CDP_PS_SAMEPERM, CDP_PS_GPROD1, CDP_PS_GPROD2, CDP_PS_IPA0, CDP_PS_IPA_ROUND, CDP_PS_SM_ROUND };
+typedef struct {
+    uint32_t ell, m, batch;          /* m = log2(ell + 4) */
+    uint32_t proof_bytes;            /* cdp_proof_size(ell): stride of d_proofs */
+    uint32_t scalars_per_proof;      /* stride (in scalars) of d_scalars for the stage being EMITTED */
+    uint32_t out_map[12];            /* where output q of the CONSUMED stage sits in d_comp, per proof pr: encoding index
+                                        batch * (e >> 16) + pr * ((e >> 8) & 255) + (e & 255) */
+    uint8_t *d_state;                /* batch x 208 B, the STROBE states cdp_transcript_open_dev left; in/out */
+    const uint8_t *d_vec_a;          /* batch x ell canonical scalars (cdp_transcript_open_dev) */
+    const uint32_t *d_perm;          /* batch x ell: the permutation witness */
+    const uint8_t *d_witness;        /* batch x 5 canonical scalars: k, vec_m_blinders[4] */
+    uint8_t *d_random;               /* batch x cdp_prove_random_scalars(ell) raw `Fr::rand` outputs (Montgomery representations), draw order:
+                                        r_a[2] (curdleproofs.rs:86), r_c[4] (grand_product_argument.rs:75), ipa r_c[n], r_d[n] (the last two
+                                        are solved for on the device, inner_product_argument.rs:46-77), r_t, r_u (curdleproofs.rs:110-111),
+                                        r_a, r_b, r_k (same_scalar_argument.rs:56-58), same_msm r[n] (same_multiscalar_argument.rs:78) */
+    uint8_t *d_work;                 /* batch x cdp_prove_work_scalars(ell) x 32 B of per-proof state, opaque */
+    const uint8_t *d_comp0_vecs;     /* batch x 4 x ell encodings of the instance (R | S | T | U), d_comp0_M: batch encodings of M */
+    const uint8_t *d_comp0_M;
+    const uint8_t *d_comp_H;         /* the encoding of crs.H */
+    const uint8_t *d_comp;           /* the consumed stage's output encodings (cdp_normalize_dev) */
+    uint8_t *d_side;                 /* batch x 2 encodings kept for later transcript messages: A', D */
+    uint8_t *d_proofs;               /* batch x proof_bytes */
+    uint8_t *d_scalars;              /* out: batch x scalars_per_proof canonical scalars */
+    uint8_t *d_fold_scalars;         /* out (CDP_PS_SM_ROUND): batch canonical scalars, gamma of the T / U fold */
+} cdp_prove_dev;
+size_t cdp_prove_work_scalars(size_t ell);
+size_t cdp_prove_random_scalars(size_t ell);
+int cdp_prove_stage_dev(cdp_ctx *ctx, const cdp_prove_dev *params, int stage, unsigned round);
+
 /* d_out[i] = sum over r < rows of d_scalars[r * row_stride + i] (mod r), canonical 32-byte scalars, i < cols: the coefficients that several
  * proofs put on the same CRS base, added up for the merged check (`*entry += a * x_i`, /root/reference/src/msm_accumulator.rs:47-51). */
 int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_stride, size_t cols, size_t rows, uint8_t *d_out);

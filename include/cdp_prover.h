@@ -54,11 +54,18 @@ typedef struct {
     const uint64_t *rng_seed;      /* batch: the prover's `rng` is StdRng::seed_from_u64(rng_seed[i]) ...            */
     const uint64_t *rng_skip_words;/* ... advanced by this many u32 outputs first (NULL = 0): lets a caller that already
                                       consumed part of the stream (src/whisk.rs:153-154, src/util.rs:102) hand it over. */
+    const uint8_t *rng_key;        /* batch * 32 bytes, or NULL.  When set it replaces rng_seed: the prover's `rng` is
+                                      StdRng::from_seed(rng_key[i]) (a full 256-bit ChaCha12 key, e.g. from the caller's OsRng).
+                                      rng_seed carries only 64 bits of entropy -- a proof made from a guessable seed leaks its witness to
+                                      anyone who replays the seed -- and is meant for reproducing test vectors.  With rng_seed == NULL and
+                                      rng_key == NULL every proof draws a fresh key from the operating system's entropy source. */
 } cdp_prove_inputs;
 
 /* proofs_out: batch * cdp_proof_size(ell) bytes.  Host buffers in, host buffers out (copies are inside the call).
  * If in->vec_R is NULL the instance vectors (R, S, T, U, M) staged in HBM by the previous call are reused -- the
- * "inputs already resident" mode; witnesses and rng fields are still read from `in`. */
+ * "inputs already resident" mode; witnesses and rng fields are still read from `in`.
+ * Witnesses are validated before any work starts: every permutation must be a bijection of 0..ell-1 and k / vec_m_blinders canonical
+ * (< r); otherwise CDP_ERR_INVALID_ARG (the reference panics on an out-of-range index). */
 int cdp_prove_batch(cdp_prover *p, size_t batch, const cdp_prove_inputs *in, uint8_t *proofs_out);
 
 /* Timing breakdown of the last cdp_prove_batch call, milliseconds: [0] total, [1] host transcript/scalar work,
