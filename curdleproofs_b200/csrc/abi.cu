@@ -1,11 +1,14 @@
 // C ABI (include/cdp_msm.h) over the sm_100a kernels.  Host-side glue only: buffer management, launch geometry,
 // chunking of large MSMs.  No arithmetic happens on the host and there is no CPU fallback.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -333,7 +336,7 @@ extern "C" int cdp_transcript_open_dev(cdp_ctx *ctx, const uint8_t *d_comp_vecs,
     if (!ctx || (batch && (!d_comp_vecs || !d_comp_M || !d_vec_a || !d_state)) || ell == 0) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_transcript_open_dev: bad argument");
     if (batch == 0) return CDP_OK;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
+    launch_scope ls(ctx, CDP_PROFILE_TRANSCRIPT, batch);
     CUDA_TRY(ctx, launch_transcript_open(ctx->stream, d_comp_vecs, d_comp_M, (uint32_t)ell, (uint32_t)batch, d_vec_a, reinterpret_cast<uint64_t *>(d_state)));
     return CDP_OK;
 }
@@ -349,7 +352,7 @@ extern "C" int cdp_verify_transcript_a_dev(cdp_ctx *ctx, const uint8_t *d_proof_
     while ((size_t(1) << m) < n) m++;
     if ((size_t(1) << m) != n || m > 16) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_transcript_a_dev: ell + 4 must be a power of two");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
+    launch_scope ls(ctx, CDP_PROFILE_TRANSCRIPT, batch);
     CUDA_TRY(ctx, launch_verify_transcript_a(ctx->stream, d_proof_points, d_proof_scalars, d_comp_M, d_vec_a, (uint32_t)ell, (uint32_t)(18 + 10 * m),
                                              (uint32_t)(27 + 4 * m), (uint32_t)batch, reinterpret_cast<uint64_t *>(d_state),
                                              reinterpret_cast<uint32_t *>(d_challenges), reinterpret_cast<uint32_t *>(d_tmp),
@@ -366,7 +369,7 @@ extern "C" int cdp_verify_transcript_b_dev(cdp_ctx *ctx, const uint8_t *d_proof_
     while ((size_t(1) << m) < n) m++;
     if ((size_t(1) << m) != n || m > 16) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_verify_transcript_b_dev: ell + 4 must be a power of two");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    launch_scope ls(ctx, CDP_PROFILE_OTHER, batch);
+    launch_scope ls(ctx, CDP_PROFILE_TRANSCRIPT, batch);
     CUDA_TRY(ctx, launch_verify_transcript_b(ctx->stream, d_proof_points, d_proof_scalars, d_comp_DA, d_comp_vecs, d_comp_H, (uint32_t)ell, (uint32_t)m,
                                              (uint32_t)(18 + 10 * m), (uint32_t)(27 + 4 * m), (uint32_t)batch, reinterpret_cast<uint64_t *>(d_state),
                                              reinterpret_cast<uint32_t *>(d_challenges), reinterpret_cast<const uint32_t *>(d_tmp)));
@@ -418,7 +421,7 @@ extern "C" int cdp_prove_stage_dev(cdp_ctx *ctx, const cdp_prove_dev *P, int sta
         !P->d_fold_scalars)
         return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_stage_dev: inconsistent parameters");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    launch_scope ls(ctx, CDP_PROFILE_OTHER, P->batch);
+    launch_scope ls(ctx, CDP_PROFILE_PROVE_STAGE, P->batch);
     CUDA_TRY(ctx, launch_prove_stage(ctx->stream, *P, stage, round));
     return CDP_OK;
 }
@@ -890,6 +893,181 @@ extern "C" int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base
 }
 
 // =================================================================================================== profiling
+// =================================================================================================== multi-GPU (NCCL)
+// NCCL is resolved at run time: the library stays loadable (and single-GPU use unaffected) where NCCL is absent, and inside a PyTorch
+// process dlopen by soname returns the copy torch already loaded.
+namespace {
+struct nccl_api {
+    void *handle = nullptr;
+    std::string err;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+nccl_api *nccl() {
+    static nccl_api api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("CDP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+            api.err = dlerror();
+        }
+        if (!api.handle) return;
+        bool ok = true;
+        auto sym = [&](const char *nm) { void *p = dlsym(api.handle, nm); if (!p) { ok = false; api.err = std::string("missing symbol ") + nm; } return p; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+        api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+        if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+    });
+    return &api;
+}
+}  // namespace
+
+struct cdp_comm {
+    cdp_ctx *ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    uint8_t *d_mine = nullptr, *d_all = nullptr;  // this rank's partial sum; the gathered n_ranks partial sums
+    std::string err = "ok";
+};
+namespace {
+int comm_fail(cdp_comm *c, int code, const std::string &msg) {
+    if (c) { c->err = msg; if (c->ctx) c->ctx->err = msg; }
+    return code;
+}
+#define NCCL_TRY(c, expr)                                                                                                   \
+    do {                                                                                                                    \
+        ncclResult_t r__ = (expr);                                                                                          \
+        if (r__ != ncclSuccess) return comm_fail(c, CDP_ERR_NCCL, std::string(#expr) + ": " + nccl()->GetErrorString(r__)); \
+    } while (0)
+int comm_alloc(cdp_comm *c) {
+    if (cudaSetDevice(c->ctx->device) != cudaSuccess || cudaMalloc(&c->d_mine, 144) != cudaSuccess ||
+        cudaMalloc(&c->d_all, 144 * (size_t)c->n_ranks) != cudaSuccess)
+        return comm_fail(c, CDP_ERR_CUDA, "cdp_comm: allocation failed");
+    return CDP_OK;
+}
+// the local part: this rank's Pippenger over its shard (or the point at infinity for an empty shard) into d_mine
+int sharded_local(cdp_comm *c, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n_local) {
+    cdp_ctx *ctx = c->ctx;
+    if (n_local == 0) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx, cudaMemsetAsync(c->d_mine, 0, 144, ctx->stream));  // Z = 0
+        return CDP_OK;
+    }
+    return cdp_msm_dev(ctx, d_pts, d_scalars, n_local, c->d_mine);
+}
+int sharded_gather(cdp_comm *c, const uint8_t *d_partial) {
+    CUDA_TRY(c->ctx, cudaSetDevice(c->ctx->device));
+    NCCL_TRY(c, nccl()->AllGather(d_partial, c->d_all, 144, ncclUint8, c->comm, c->ctx->stream));
+    return CDP_OK;
+}
+}  // namespace
+
+extern "C" int cdp_comm_unique_id(uint8_t out_id[CDP_COMM_ID_BYTES]) {
+    static_assert(sizeof(ncclUniqueId) == CDP_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!out_id) return CDP_ERR_INVALID_ARG;
+    if (!nccl()->handle) return CDP_ERR_NCCL;
+    ncclUniqueId id;
+    if (nccl()->GetUniqueId(&id) != ncclSuccess) return CDP_ERR_NCCL;
+    memcpy(out_id, &id, sizeof id);
+    return CDP_OK;
+}
+extern "C" int cdp_comm_create(cdp_comm **out, cdp_ctx *ctx, const uint8_t id[CDP_COMM_ID_BYTES], int n_ranks, int rank) {
+    if (!out || !ctx || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_comm_create: bad argument");
+    *out = nullptr;
+    if (!nccl()->handle) return fail(ctx, CDP_ERR_NCCL, "cdp_comm_create: NCCL not available: " + nccl()->err);
+    cdp_comm *c = new cdp_comm();
+    c->ctx = ctx; c->n_ranks = n_ranks; c->rank = rank;
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    ncclResult_t r = cudaSetDevice(ctx->device) == cudaSuccess ? nccl()->CommInitRank(&c->comm, n_ranks, uid, rank) : ncclUnhandledCudaError;
+    if (r != ncclSuccess) {
+        fail(ctx, CDP_ERR_NCCL, std::string("ncclCommInitRank: ") + nccl()->GetErrorString(r));
+        delete c;
+        return CDP_ERR_NCCL;
+    }
+    if (int rc = comm_alloc(c)) { cdp_comm_destroy(c); return rc; }
+    *out = c;
+    return CDP_OK;
+}
+extern "C" int cdp_comm_create_all(cdp_comm **out, cdp_ctx *const *ctxs, int n) {
+    if (!out || !ctxs || n < 1) return CDP_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++) { out[i] = nullptr; if (!ctxs[i]) return CDP_ERR_INVALID_ARG; }
+    if (!nccl()->handle) return fail(ctxs[0], CDP_ERR_NCCL, "cdp_comm_create_all: NCCL not available: " + nccl()->err);
+    std::vector<int> devs(n);
+    std::vector<ncclComm_t> comms(n, nullptr);
+    for (int i = 0; i < n; i++) devs[i] = ctxs[i]->device;
+    ncclResult_t r = nccl()->CommInitAll(comms.data(), n, devs.data());
+    if (r != ncclSuccess) return fail(ctxs[0], CDP_ERR_NCCL, std::string("ncclCommInitAll: ") + nccl()->GetErrorString(r));
+    for (int i = 0; i < n; i++) {
+        cdp_comm *c = new cdp_comm();
+        c->ctx = ctxs[i]; c->comm = comms[i]; c->n_ranks = n; c->rank = i;
+        out[i] = c;
+    }
+    for (int i = 0; i < n; i++)
+        if (int rc = comm_alloc(out[i])) {
+            for (int j = 0; j < n; j++) { cdp_comm_destroy(out[j]); out[j] = nullptr; }
+            return rc;
+        }
+    return CDP_OK;
+}
+extern "C" void cdp_comm_destroy(cdp_comm *c) {
+    if (!c) return;
+    if (c->ctx) { cudaSetDevice(c->ctx->device); cudaStreamSynchronize(c->ctx->stream); }
+    if (c->comm && nccl()->handle) nccl()->CommDestroy(c->comm);
+    if (c->d_mine) cudaFree(c->d_mine);
+    if (c->d_all) cudaFree(c->d_all);
+    delete c;
+}
+extern "C" int cdp_comm_rank(const cdp_comm *c) { return c ? c->rank : -1; }
+extern "C" int cdp_comm_size(const cdp_comm *c) { return c ? c->n_ranks : 0; }
+extern "C" const char *cdp_comm_last_error(const cdp_comm *c) { return c ? c->err.c_str() : "null communicator"; }
+extern "C" void cdp_shard_range(size_t n, int rank, int n_ranks, size_t *lo, size_t *hi) {
+    const size_t w = (size_t)(n_ranks > 0 ? n_ranks : 1), r = (size_t)(rank > 0 ? rank : 0), base = n / w, rem = n % w;
+    const size_t l = r * base + std::min(r, rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (r < rem ? 1 : 0);
+}
+extern "C" int cdp_allreduce_jacobian_dev(cdp_comm *c, const uint8_t *d_partial_jac, uint8_t *d_out_jac) {
+    if (!c || !d_partial_jac || !d_out_jac) return comm_fail(c, CDP_ERR_INVALID_ARG, "cdp_allreduce_jacobian_dev: bad argument");
+    TRY(sharded_gather(c, d_partial_jac));
+    return cdp_sum_jacobian_dev(c->ctx, c->d_all, (size_t)c->n_ranks, d_out_jac);
+}
+extern "C" int cdp_msm_sharded_dev(cdp_comm *c, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n_local, uint8_t *d_out_jac) {
+    if (!c || !d_out_jac || (n_local && (!d_pts || !d_scalars))) return comm_fail(c, CDP_ERR_INVALID_ARG, "cdp_msm_sharded_dev: bad argument");
+    TRY(sharded_local(c, d_pts, d_scalars, n_local));
+    return cdp_allreduce_jacobian_dev(c, c->d_mine, d_out_jac);
+}
+extern "C" int cdp_msm_sharded_group(cdp_comm *const *comms, int n, const uint8_t *const *d_pts, const uint8_t *const *d_scalars, const size_t *n_local,
+                                     uint8_t *const *d_out_jac) {
+    if (!comms || n < 1 || !d_pts || !d_scalars || !n_local || !d_out_jac) return CDP_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++)
+        if (!comms[i] || comms[i]->n_ranks != n || !d_out_jac[i]) return CDP_ERR_INVALID_ARG;
+    for (int i = 0; i < n; i++) TRY(sharded_local(comms[i], d_pts[i], d_scalars[i], n_local[i]));
+    NCCL_TRY(comms[0], nccl()->GroupStart());
+    for (int i = 0; i < n; i++) {
+        const int rc = sharded_gather(comms[i], comms[i]->d_mine);
+        if (rc != CDP_OK) { nccl()->GroupEnd(); return rc; }
+    }
+    NCCL_TRY(comms[0], nccl()->GroupEnd());
+    for (int i = 0; i < n; i++) TRY(cdp_sum_jacobian_dev(comms[i]->ctx, comms[i]->d_all, (size_t)n, d_out_jac[i]));
+    return CDP_OK;
+}
+
 static void prof_drain(cdp_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     static const char *dump = getenv("CDP_PROFILE_DUMP");  // optional per-launch log: "kind units ms" per line

@@ -292,7 +292,7 @@ __device__ void cta_reduce_add(fr_t *arr, uint32_t cnt) {
 }
 // x^-1 computed by the leader and handed to every thread through `slot`
 __device__ fr_t cta_inverse(const fr_t &x, fr_t *slot) {
-    if (CTA_LEADER) *slot = fr_inverse(x);
+    if (CTA_LEADER) *slot = fr_inverse_euclid(x);
     CTA_SYNC();
     const fr_t r = *slot;
     CTA_SYNC();
@@ -459,7 +459,7 @@ __device__ void stage_gprod2(pctx &c) {
     // 1 / (r_c[n-1] - r_c[n-2] c[n-1] / c[n-2]) = c[n-2] / E
     if (CTA_LEADER) {
         const fr_t c2 = c.w.c[n - 2], E = fr_sub(fr_mul(rc[n - 1], c2), fr_mul(rc[n - 2], c.w.c[n - 1]));
-        const fr_t p01 = fr_mul(beta, c2), inv = fr_inverse(fr_mul(p01, E));
+        const fr_t p01 = fr_mul(beta, c2), inv = fr_inverse_euclid(fr_mul(p01, E));
         const fr_t invE = fr_mul(inv, p01), inv01 = fr_mul(inv, E);
         c.w.sm[SM_T0] = fr_mul(inv01, c2);      // beta^-1
         c.w.sm[SM_T1] = fr_mul(inv01, beta);    // c[n-2]^-1
@@ -693,7 +693,10 @@ __global__ void __launch_bounds__(256) k_prove_stage(const __grid_constant__ cdp
 #ifndef CDP_PROVE_HOST_HARNESS
 cudaError_t launch_prove_stage(cudaStream_t st, const cdp_prove_dev &P, int stage, uint32_t round) {
     if (P.batch == 0) return cudaSuccess;
-    k_prove_stage<<<P.batch, 256, 0, st>>>(P, stage, round);
+    // one warp per proof by default: the steps are latency-bound (one thread hashes), so a CTA should hold as little of an SM as possible
+    // while the throughput kernels of the other lanes run beside it; CDP_PROVE_THREADS (32 .. 256) for tuning runs
+    static const int threads = [] { const char *e = getenv("CDP_PROVE_THREADS"); int v = e ? atoi(e) : 32; return v >= 32 && v <= 256 && v % 32 == 0 ? v : 32; }();
+    k_prove_stage<<<P.batch, threads, 0, st>>>(P, stage, round);
     return cudaGetLastError();
 }
 #endif

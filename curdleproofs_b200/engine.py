@@ -71,6 +71,17 @@ _SIGS = {
     "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
+    "cdp_comm_unique_id": (c_int, [c_void_p]),
+    "cdp_comm_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int]),
+    "cdp_comm_create_all": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int]),
+    "cdp_comm_destroy": (None, [c_void_p]),
+    "cdp_comm_rank": (c_int, [c_void_p]),
+    "cdp_comm_size": (c_int, [c_void_p]),
+    "cdp_comm_last_error": (c_char_p, [c_void_p]),
+    "cdp_shard_range": (None, [c_size_t, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
+    "cdp_msm_sharded_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "cdp_msm_sharded_group": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_size_t), POINTER(c_void_p)]),
+    "cdp_allreduce_jacobian_dev": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 _LIB = None
@@ -291,7 +302,7 @@ class Engine:
         raw = bytes(out)
         return [raw[i * JACOBIAN_BYTES:(i + 1) * JACOBIAN_BYTES] for i in range(n_out)]
 
-    PROFILE_KINDS = ("msm_buckets", "msm_combine", "smul", "normalize", "other", "msm_fixed")
+    PROFILE_KINDS = ("msm_buckets", "msm_combine", "smul", "normalize", "other", "msm_fixed", "prove_stage", "transcript")
 
     def profile_enable(self, on: bool = True):
         self._check(self._lib.cdp_profile_enable(self._h, int(on)), "cdp_profile_enable")

@@ -35,6 +35,7 @@
 #pragma GCC visibility push(default)
 #include "../../include/cdp_prover.h"
 #pragma GCC visibility pop
+#include "crs_table.hpp"
 #include "merlin.hpp"
 #include "rng.hpp"
 
@@ -1186,12 +1187,13 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
 // others keep the SMs busy.
 struct cdp_prover {
     cdp_ctx *ctx0 = nullptr;  // the caller's context (lane 0): used by the whisk wrappers for their own launches
-    cdp_fixed_table *table = nullptr;  // digit table of the CRS points, shared (read-only) by all lanes
-    cdp_ctx *table_ctx = nullptr;
+    SharedCrsTable *shared = nullptr;  // digit table of the CRS points: shared (read-only) by all lanes and by every prover / verifier of the process over the same CRS
+    const cdp_fixed_table *table = nullptr;
     std::vector<Lane *> lanes;
     std::vector<cdp_ctx *> owned;
     std::vector<size_t> last_split;
     size_t ell = 0, max_batch = 0;
+    bool serial = false;  // run the lanes one after the other (cdp_prover_set_serial): per-kernel device times without overlap
     std::string err = "ok";
     double timing[4] = {0, 0, 0, 0};
     uint64_t traffic[2] = {0, 0};
@@ -1208,7 +1210,7 @@ extern "C" void cdp_prover_last_traffic(const cdp_prover *p, uint64_t out_bytes[
 extern "C" void cdp_prover_destroy(cdp_prover *p) {
     if (!p) return;
     for (Lane *l : p->lanes) lane_destroy(l);
-    if (p->table) cdp_fixed_table_destroy(p->table_ctx, p->table);
+    crs_table_release(p->shared);
     for (cdp_ctx *c : p->owned) cdp_ctx_destroy(c);
     delete p;
 }
@@ -1237,21 +1239,10 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     // thread per lane does (measured: 8 / 16 / 32 / 64 threads for 8 lanes on 16 cores: 875 / 767 / 767 / 797 ms per 4096 proofs)
     int threads_per_lane = std::max(1, (host_threads + lanes - 1) / lanes);
     // CRS digit table: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec) (the last two are the reference's crs.G_sum / crs.H_sum,
-    // src/crs.rs:46-47).  CDP_FIXED_BITS overrides the window width (default 16: 50 MB per base)
-    std::vector<uint8_t> crs_ext((ell + 9) * 96);
-    {
-        memcpy(crs_ext.data(), crs_points, (ell + 7) * 96);
-        std::vector<uint8_t> ones(32 * std::max(ell, NBL), 0), sums(2 * 144);
-        for (size_t i = 0; i < std::max(ell, NBL); i++) ones[32 * i] = 1;
-        int rc = cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
-        if (rc == CDP_OK) rc = cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
-        if (rc == CDP_OK) rc = cdp_normalize_batch(ctx, sums.data(), 2, crs_ext.data() + (ell + 7) * 96);
-        int bits = 0;
-        if (const char *e = getenv("CDP_FIXED_BITS")) bits = atoi(e);
-        if (rc == CDP_OK) rc = cdp_fixed_table_create(ctx, crs_ext.data(), ell + 9, bits, &p->table);
-        if (rc != CDP_OK) { delete p; return rc; }
-        p->table_ctx = ctx;
-    }
+    // src/crs.rs:46-47), one per (device, CRS) in the process (crs_table.hpp).  CDP_FIXED_BITS overrides the window width (default 16: 50 MB per base)
+    if (int rc = crs_table_acquire(ctx, ell, crs_points, &p->shared)) { delete p; return rc; }
+    p->table = p->shared->table;
+    const std::vector<uint8_t> &crs_ext = p->shared->crs_ext;
     for (int i = 0; i < lanes; i++) {
         cdp_ctx *c = ctx;
         if (i > 0) {
@@ -1267,6 +1258,8 @@ extern "C" int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t el
     return CDP_OK;
 }
 extern "C" int cdp_prover_lane_count(const cdp_prover *p) { return p ? (int)p->lanes.size() : 0; }
+extern "C" void cdp_prover_set_serial(cdp_prover *p, int on) { if (p) p->serial = on != 0; }
+extern "C" size_t cdp_prover_table_bytes(const cdp_prover *p) { return p && p->table ? cdp_fixed_table_bytes(p->table) : 0; }
 extern "C" cdp_ctx *cdp_prover_lane_ctx(const cdp_prover *p, int lane) {
     return (p && lane >= 0 && lane < (int)p->lanes.size()) ? p->lanes[lane]->ctx : nullptr;
 }
@@ -1317,8 +1310,9 @@ extern "C" int cdp_prove_batch(cdp_prover *p, size_t B, const cdp_prove_inputs *
         sub.rng_key = in->rng_key ? in->rng_key + 32 * o : nullptr;
         rcs[i] = lane_prove(p->lanes[i], cnt, &sub, proofs_out + o * psz);
     };
-    if (L == 1) run(0);
-    else {
+    if (L == 1 || p->serial) {
+        for (size_t i = 0; i < L; i++) run(i);
+    } else {
         std::vector<std::thread> th;
         for (size_t i = 0; i < L; i++) th.emplace_back(run, i);
         for (auto &t : th) t.join();

@@ -37,6 +37,7 @@
 #pragma GCC visibility push(default)
 #include "../../include/cdp_prover.h"
 #pragma GCC visibility pop
+#include "crs_table.hpp"
 #include "merlin.hpp"
 #include "rng.hpp"
 
@@ -635,8 +636,8 @@ int vlane_verify(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *ok_ou
 
 struct cdp_verifier {
     cdp_ctx *ctx0 = nullptr;
-    cdp_fixed_table *table = nullptr;
-    cdp_ctx *table_ctx = nullptr;
+    SharedCrsTable *shared = nullptr;  // the CRS digit table, shared with every prover / verifier of the process over the same CRS (crs_table.hpp)
+    const cdp_fixed_table *table = nullptr;
     std::vector<VLane *> lanes;
     std::vector<cdp_ctx *> owned;
     size_t ell = 0, max_batch = 0;
@@ -646,7 +647,7 @@ struct cdp_verifier {
 extern "C" void cdp_verifier_destroy(cdp_verifier *v) {
     if (!v) return;
     for (VLane *l : v->lanes) vlane_destroy(l);
-    if (v->table) cdp_fixed_table_destroy(v->table_ctx, v->table);
+    crs_table_release(v->shared);
     for (cdp_ctx *c : v->owned) cdp_ctx_destroy(c);
     delete v;
 }
@@ -666,6 +667,8 @@ extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell,
                                    int lanes) {
     if (!out || !ctx || !crs_points || max_batch == 0 || ell < 4) return CDP_ERR_INVALID_ARG;
     *out = nullptr;
+    if (((ell + NBL) & (ell + NBL - 1)) != 0) return CDP_ERR_INVALID_ARG;  // ell + 4 must be a power of two; checked before the table is built
+    if (ell + NBL + 1 > 2048) return CDP_ERR_TOO_LARGE;
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (host_threads <= 0) host_threads = hw;
     if (lanes <= 0) lanes = max_batch >= 512 ? 8 : max_batch >= 128 ? 4 : max_batch >= 32 ? 2 : 1;
@@ -675,20 +678,9 @@ extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell,
     v->ell = ell; v->max_batch = max_batch;
     size_t per_lane = (max_batch + lanes - 1) / lanes;
     // CRS digit table: G | Hvec | H | G_t | G_u | sum(G) | sum(Hvec) (crs.G_sum / crs.H_sum, src/crs.rs:46-47); CDP_FIXED_BITS overrides the width
-    std::vector<uint8_t> crs_ext((ell + 9) * 96);
-    {
-        memcpy(crs_ext.data(), crs_points, (ell + 7) * 96);
-        std::vector<uint8_t> ones(32 * ell, 0), sums(2 * 144);
-        for (size_t i = 0; i < ell; i++) ones[32 * i] = 1;
-        int rc = cdp_msm(ctx, crs_points, ones.data(), ell, sums.data());
-        if (rc == CDP_OK) rc = cdp_msm(ctx, crs_points + ell * 96, ones.data(), NBL, sums.data() + 144);
-        if (rc == CDP_OK) rc = cdp_normalize_batch(ctx, sums.data(), 2, crs_ext.data() + (ell + 7) * 96);
-        int bits = 0;
-        if (const char *e = getenv("CDP_FIXED_BITS")) bits = atoi(e);
-        if (rc == CDP_OK) rc = cdp_fixed_table_create(ctx, crs_ext.data(), ell + 9, bits, &v->table);
-        if (rc != CDP_OK) { delete v; return rc; }
-        v->table_ctx = ctx;
-    }
+    if (int rc = crs_table_acquire(ctx, ell, crs_points, &v->shared)) { delete v; return rc; }
+    v->table = v->shared->table;
+    const std::vector<uint8_t> &crs_ext = v->shared->crs_ext;
     for (int i = 0; i < lanes; i++) {
         cdp_ctx *c = ctx;
         if (i > 0) {

@@ -34,6 +34,7 @@ extern "C" {
 #define CDP_ERR_CUDA 2
 #define CDP_ERR_TOO_LARGE 3
 #define CDP_ERR_NOT_ON_CURVE 4
+#define CDP_ERR_NCCL 5
 
 #define CDP_FP_BYTES 48
 #define CDP_SCALAR_BYTES 32
@@ -307,6 +308,38 @@ int cdp_sum_scalars_dev(cdp_ctx *ctx, const uint8_t *d_scalars, size_t row_strid
 /* Jacobian -> affine and/or compressed (either output may be NULL). d_out_affine may alias nothing in d_jac. */
 int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_out_affine, uint8_t *d_out_compressed);
 
+/* ------------------------------------------------------------------ multi-GPU: one large MSM sharded by base range
+ * `util::msm` (/root/reference/src/util.rs:19-22) over N = sum of n_local pairs, rank r holding a contiguous range of the
+ * bases and their scalars.  Every rank runs the large Pippenger on its shard; the only collective is ONE ncclAllGather of the 144-byte
+ * partial sums (NCCL has no elliptic-curve reduction op, so the "allreduce" of partial G1 sums is all-gather + local add); every rank ends
+ * with the full sum.  NCCL (>= 2.x, `libnccl.so.2`, or the path in $CDP_NCCL_LIB) is loaded at the first use, so single-GPU callers do not
+ * depend on it; every NCCL failure is reported as CDP_ERR_NCCL with ncclGetErrorString in cdp_last_error.
+ *
+ * One process per GPU (the layout bench.py and `torch.distributed.run` use): rank 0 calls cdp_comm_unique_id and distributes the 128 bytes
+ * out of band (exactly like ncclGetUniqueId), then every rank calls cdp_comm_create with its own context.
+ * One process driving several GPUs: cdp_comm_create_all over one context per device, and cdp_msm_sharded_group to issue the collective
+ * for all of them (ncclGroupStart / End around the per-device calls). */
+typedef struct cdp_comm cdp_comm;
+#define CDP_COMM_ID_BYTES 128
+int cdp_comm_unique_id(uint8_t out_id[CDP_COMM_ID_BYTES]);
+int cdp_comm_create(cdp_comm **out, cdp_ctx *ctx, const uint8_t id[CDP_COMM_ID_BYTES], int n_ranks, int rank);
+int cdp_comm_create_all(cdp_comm **out /* n */, cdp_ctx *const *ctxs, int n);
+void cdp_comm_destroy(cdp_comm *comm);
+int cdp_comm_rank(const cdp_comm *comm);
+int cdp_comm_size(const cdp_comm *comm);
+const char *cdp_comm_last_error(const cdp_comm *comm);
+/* The contiguous base range [lo, hi) of `rank` for an MSM of n pairs, as even as possible (the partition every caller should use). */
+void cdp_shard_range(size_t n, int rank, int n_ranks, size_t *lo, size_t *hi);
+/* d_out_jac (144 B, on every rank) = sum over all ranks of msm(shard).  n_local may be 0.  Asynchronous on the context's stream: the local
+ * MSM, the all-gather and the final addition are ordered on that one stream. */
+int cdp_msm_sharded_dev(cdp_comm *comm, const uint8_t *d_affine_pts_shard, const uint8_t *d_scalars_shard, size_t n_local, uint8_t *d_out_jac);
+/* The same for the n communicators of cdp_comm_create_all (arrays of n device pointers, one per communicator / device). */
+int cdp_msm_sharded_group(cdp_comm *const *comms, int n, const uint8_t *const *d_affine_pts_shard, const uint8_t *const *d_scalars_shard,
+                          const size_t *n_local, uint8_t *const *d_out_jac);
+/* Partial sums that were computed elsewhere (the merged accumulated check of a verifier's sub-batches, /root/reference/src/msm_accumulator.rs:55-68):
+ * d_out_jac = sum over ranks of d_partial_jac (one Jacobian point per rank).  d_partial_jac and d_out_jac may alias. */
+int cdp_allreduce_jacobian_dev(cdp_comm *comm, const uint8_t *d_partial_jac, uint8_t *d_out_jac);
+
 /* ------------------------------------------------------------------ per-kernel profiling
  * When enabled, every kernel launch of the context is bracketed by CUDA events on the context's stream and the elapsed
  * device time is accumulated per kernel kind.  `units` accumulates the work items each launch processed: (scalar, point)
@@ -318,7 +351,9 @@ int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, uint8_t *d_o
 #define CDP_PROFILE_NORMALIZE 3
 #define CDP_PROFILE_OTHER 4
 #define CDP_PROFILE_MSM_FIXED 5
-#define CDP_PROFILE_KINDS 6
+#define CDP_PROFILE_PROVE_STAGE 6 /* cdp_prove_stage_dev: transcript + Fr algebra of the prover */
+#define CDP_PROFILE_TRANSCRIPT 7  /* transcript opening / verifier transcript kernels */
+#define CDP_PROFILE_KINDS 8
 int cdp_profile_enable(cdp_ctx *ctx, int on);
 int cdp_profile_reset(cdp_ctx *ctx);
 int cdp_profile_read(cdp_ctx *ctx, double ms[CDP_PROFILE_KINDS], uint64_t launches[CDP_PROFILE_KINDS], uint64_t units[CDP_PROFILE_KINDS]);

@@ -36,6 +36,12 @@ int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t 
 int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads,
                             int lanes);
 int cdp_prover_lane_count(const cdp_prover *p);
+/* Diagnostics: run the lanes of the following cdp_prove_batch calls one after the other instead of concurrently, so that the per-kernel
+ * device times of cdp_profile_* are those of kernels running alone (bench.py's roofline pass). */
+void cdp_prover_set_serial(cdp_prover *p, int on);
+/* Size of the CRS digit table the prover uses.  The table is shared by every prover / verifier of the process created over the same CRS
+ * on the same device (reference-counted), so a verifier next to a prover costs no second table. */
+size_t cdp_prover_table_bytes(const cdp_prover *p);
 /* The cdp_ctx a lane runs on (for cdp_profile_* / cdp_launch_count accounting across lanes). */
 cdp_ctx *cdp_prover_lane_ctx(const cdp_prover *p, int lane);
 void cdp_prover_destroy(cdp_prover *p);

@@ -201,4 +201,31 @@ int cdp_prove_stage_dev(cdp_ctx *c, const cdp_prove_dev *P, int stage, unsigned 
     return CDP_OK;
 }
 
+// the single-thread Euclidean inversion of csrc/fr256.cuh against the Fermat ladder: edge values and `count` pseudo-random ones; returns the number of mismatches
+int mock_check_fr_inverse(int count) {
+    using namespace cdp::vcoef;
+    int bad = 0;
+    uint64_t s = 0x9E3779B97F4A7C15ULL;
+    auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 16); };
+    for (int t = 0; t < count + 6; t++) {
+        fr_t x = fr_zero();
+        if (t == 0) x.v[0] = 1;
+        else if (t == 1) x.v[0] = 2;
+        else if (t == 2) { for (int i = 0; i < 8; i++) x.v[i] = fr_mod(i); x.v[0] -= 1; }
+        else if (t == 3) x = fr_one();
+        else if (t == 4) x.v[7] = 0x40000000u;
+        else if (t == 5) { /* zero */ }
+        else { for (int i = 0; i < 8; i++) x.v[i] = next(); x.v[7] &= 0x3FFFFFFFu; }
+        const fr_t a = fr_inverse(x), b = fr_inverse_euclid(x);
+        bool same = true;
+        for (int i = 0; i < 8; i++) same = same && a.v[i] == b.v[i];
+        if (t != 5) {
+            const fr_t one = fr_mul(x, b), want = fr_one();
+            for (int i = 0; i < 8; i++) same = same && one.v[i] == want.v[i];
+        }
+        bad += !same;
+    }
+    return bad;
+}
+
 }  // extern "C"

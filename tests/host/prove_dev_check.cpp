@@ -5,6 +5,7 @@
 //   prove_dev_check random <ell> <batch> <lanes>   random instances, seeds 1.., both rng forms; device path AND the host-transcript path
 //   prove_dev_check golden                        the reference's seed-0 whisk shuffle (ell = 124, src/whisk.rs:416-456): the proof part of
 //                                                 the 4496-byte golden vector (src/whisk.rs:455), which tests/test_oracle_golden.py pins
+//   prove_dev_check inverse                       the device code's single-thread Euclidean Fr inversion against the Fermat ladder
 //   prove_dev_check badinput                      witness validation: out-of-range / repeated permutation entries, non-canonical scalars
 #include <cstdint>
 #include <cstdio>
@@ -23,6 +24,7 @@ int oracle_prove(size_t ell, const uint8_t *crs_pts, const uint8_t *vec_R, const
                  uint8_t *proof_out, int threads);
 int oracle_whisk_shuffle_proof_seed0(size_t ell, uint8_t *proof_out, uint8_t *inst_out, int *verified, int threads);
 void oracle_stdrng_seed_bytes(uint64_t seed, uint8_t out[32]);
+int mock_check_fr_inverse(int count);  // tests/host/cpu_engine_mock.cpp
 }
 
 struct Batch {
@@ -142,6 +144,11 @@ int main(int argc, char **argv) {
         if (prove(b, 1, false, false, out) != CDP_OK) { printf("MISMATCH badinput: the untouched batch was rejected\n"); bad = 1; }
         if (!bad) printf("badinput ok : malformed witnesses are refused with CDP_ERR_INVALID_ARG before any work\n");
         return bad;
+    }
+    if (!strcmp(mode, "inverse")) {
+        const int bad = mock_check_fr_inverse(2000);
+        printf(bad ? "MISMATCH inverse: %d values\n" : "inverse ok : Euclidean and Fermat inversions agree on edge values and 2000 random ones (%d mismatches)\n", bad);
+        return bad != 0;
     }
     printf("unknown mode %s\n", mode);
     return 2;

@@ -1,0 +1,136 @@
+"""GPU: one large MSM sharded by base range across the ranks of a node through the engine's own communicator (`cdp_comm_*`,
+`cdp_msm_sharded_dev`, include/cdp_msm.h; SURVEY.md 8(e), `util::msm` /root/reference/src/util.rs:19-22): every rank's result must be the
+oracle's MSM over ALL bases.  World size 1 runs on any box (NCCL with one rank); the two-rank forms (one process per GPU, and one
+process driving two GPUs) need a 2-GPU lease and are skipped with that reason otherwise."""
+import os
+import random
+import socket
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(n, seed=5):
+    import oracle_lib
+    import py_ref as pr
+    o = oracle_lib.Oracle()
+    rnd = random.Random(seed)
+    k = min(n, 512)  # distinct base points; repeated beyond that (the MSM does not care)
+    base = o.scalar_mul_batch(o.generator() * k, b"".join(pr.fr_to_bytes(rnd.randrange(1, pr.R_ORDER)) for _ in range(k)))
+    pts = (base * ((n + k - 1) // k))[:96 * n]
+    sc = b"".join(pr.fr_to_bytes(rnd.randrange(pr.R_ORDER)) for _ in range(n))
+    return o, pts, sc
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n", [1, 300, 20000])
+def test_sharded_msm_world1(n):
+    from curdleproofs_b200 import Engine
+    from curdleproofs_b200.sharded import Comm
+    o, pts, sc = _inputs(n)
+    eng = Engine(0)
+    comm = Comm(eng, Comm.unique_id(eng), 1, 0)
+    got = comm.msm_sharded(pts, sc)
+    assert o.compress_jac(got) == o.compress_jac(o.msm(pts, sc))
+    comm.close()
+    eng.close()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_worker(rank, world, port, sizes, q):
+    import torch
+    import torch.distributed as dist
+    from curdleproofs_b200 import Engine
+    from curdleproofs_b200.sharded import Comm, shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # only carries the 128-byte communicator id
+    eng = Engine(rank)
+    comm = Comm.from_torch_distributed(eng, rank, world)
+    res = []
+    for n in sizes:
+        o, pts, sc = _inputs(n)
+        lo, hi = shard_range(n, rank, world)
+        got = comm.msm_sharded(pts[96 * lo:96 * hi], sc[32 * lo:32 * hi])
+        res.append(o.compress_jac(got) == o.compress_jac(o.msm(pts, sc)))
+    q.put((rank, res))
+    dist.barrier()
+    comm.close()
+    eng.close()
+    dist.destroy_process_group()
+
+
+def test_sharded_msm_two_ranks_one_process_per_gpu():
+    if _gpu_count() < 2:
+        pytest.skip("needs a 2-GPU lease (this box has %d GPU): run under `gpurun --gpus 2`" % _gpu_count())
+    import torch.multiprocessing as mp
+    world, sizes = 2, [1, 37, 9001, 40000]  # n = 1: rank 1 holds an empty shard
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, ok in res:
+        assert all(ok), (rank, ok)
+
+
+def test_sharded_msm_group_one_process_two_gpus():
+    if _gpu_count() < 2:
+        pytest.skip("needs a 2-GPU lease (this box has %d GPU): run under `gpurun --gpus 2`" % _gpu_count())
+    import ctypes
+    from ctypes import c_size_t, c_void_p
+    from curdleproofs_b200 import Engine
+    from curdleproofs_b200.sharded import shard_range
+    n, world = 30011, 2
+    o, pts, sc = _inputs(n)
+    engs = [Engine(r) for r in range(world)]
+    lib = engs[0].lib
+    comms = (c_void_p * world)()
+    ctxs = (c_void_p * world)(*[e.handle for e in engs])
+    assert lib.cdp_comm_create_all(comms, ctxs, world) == 0
+    d_p, d_s, d_o, nl = (c_void_p * world)(), (c_void_p * world)(), (c_void_p * world)(), (c_size_t * world)()
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        nl[r] = hi - lo
+        h = engs[r].handle
+        d_p[r], d_s[r], d_o[r] = lib.cdp_dev_alloc(h, 96 * (hi - lo)), lib.cdp_dev_alloc(h, 32 * (hi - lo)), lib.cdp_dev_alloc(h, 144)
+        lib.cdp_h2d(h, d_p[r], (ctypes.c_uint8 * (96 * (hi - lo))).from_buffer_copy(pts[96 * lo:96 * hi]), 96 * (hi - lo))
+        lib.cdp_h2d(h, d_s[r], (ctypes.c_uint8 * (32 * (hi - lo))).from_buffer_copy(sc[32 * lo:32 * hi]), 32 * (hi - lo))
+        engs[r].sync()
+    assert lib.cdp_msm_sharded_group(comms, world, d_p, d_s, nl, d_o) == 0
+    want = o.compress_jac(o.msm(pts, sc))
+    for r in range(world):
+        out = (ctypes.c_uint8 * 144)()
+        lib.cdp_d2h(engs[r].handle, out, d_o[r], 144)
+        engs[r].sync()
+        assert o.compress_jac(bytes(out)) == want
+    for r in range(world):
+        lib.cdp_comm_destroy(comms[r])
+        for d in (d_p[r], d_s[r], d_o[r]):
+            lib.cdp_dev_free(engs[r].handle, d)
+        engs[r].close()

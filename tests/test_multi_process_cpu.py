@@ -1,5 +1,7 @@
-"""CPU, world_size = 2, gloo: the N > 1 host logic -- base-range sharding of one MSM, all-gather of the 144-byte partial sums,
-local addition -- with the oracle standing in for the GPU kernel (no GPU in this container)."""
+"""CPU, world_size = 2, gloo: the N > 1 host logic -- base-range sharding of one MSM, the hand-over of the communicator id from rank 0
+(curdleproofs_b200.sharded.exchange_unique_id), all-gather of the 144-byte partial sums, local addition -- with the oracle standing in
+for the GPU kernel and a gloo all-gather for the engine's NCCL one (no GPU in this container; the real collective is cdp_msm_sharded_dev,
+tests/test_gpu_sharded.py)."""
 import os
 import random
 import socket
@@ -28,10 +30,13 @@ def _free_port():
 def _worker(rank, world, port, n, q):
     import oracle_lib
     import py_ref as pr
-    from curdleproofs_b200.sharded import allgather_partials, shard_range
+    from curdleproofs_b200.sharded import COMM_ID_BYTES, exchange_unique_id, shard_range
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the communicator id travels from rank 0 to everyone (a 128-byte opaque blob, like ncclGetUniqueId's)
+    uid = exchange_unique_id(lambda: bytes((7 * i + 3) % 256 for i in range(COMM_ID_BYTES)), rank, world)
+    assert uid == bytes((7 * i + 3) % 256 for i in range(COMM_ID_BYTES))
     o = oracle_lib.Oracle()
     rnd = random.Random(42)  # identical inputs on every rank
     sc0 = b"".join(pr.fr_to_bytes(rnd.randrange(pr.R_ORDER)) for _ in range(n))
@@ -40,7 +45,8 @@ def _worker(rank, world, port, n, q):
     lo, hi = shard_range(n, rank, world)
     partial = o.msm(pts[96 * lo:96 * hi], sc[32 * lo:32 * hi])          # this rank's base range
     t = torch.frombuffer(bytearray(partial), dtype=torch.uint8)
-    allp = allgather_partials(t, world)                                  # [world, 144], same on every rank
+    allp = torch.empty((world, 144), dtype=torch.uint8)
+    dist.all_gather_into_tensor(allp.view(-1), t)                        # [world, 144], same on every rank
     acc = pr.INF
     for r in range(world):
         acc = pr.add(acc, pr.jacobian_from_bytes(bytes(allp[r].numpy().tobytes())))

@@ -42,3 +42,9 @@ def test_prover_rejects_malformed_witnesses(harness):
     """cdp_prove_batch validates the witnesses before any work (the reference panics on an out-of-range permutation index)."""
     out = subprocess.run([harness, "badinput"], capture_output=True, text=True)
     assert out.returncode == 0 and "badinput ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_device_fr_inversion_euclid_matches_fermat(harness):
+    """csrc/fr256.cuh fr_inverse_euclid (one thread inverts each round challenge on the prover's critical path) against the Fermat ladder."""
+    out = subprocess.run([harness, "inverse"], capture_output=True, text=True)
+    assert out.returncode == 0 and "inverse ok" in out.stdout, out.stdout + out.stderr
