@@ -1,17 +1,19 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark of the B200 Curdleproofs engine.
 
-Metric (BASELINE.json): shuffle proofs/s at ell = 252 (`CurdleproofsProof::new`, /root/reference/src/curdleproofs.rs:59-184),
-one batch of independent proofs per step per GPU.  One JSON line on stdout (rank 0).
+Metric (BASELINE.json): shuffle proofs/s at ell = 252 (`CurdleproofsProof::new`, /root/reference/src/curdleproofs.rs:59-184), one batch of
+independent proofs per step per GPU; beside it verifies/s and the standalone G1 MSM sweep (pairs/s, sharded by base range over the ranks).
+One JSON line on stdout (rank 0).
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...      # the reference's CPU path (oracle port; arkworks is not buildable here)
 
 `value`  : proofs/s with the instance vectors already resident in HBM when the timed region starts.
-`e2e`    : the same through the host-buffer C ABI (cdp_prove_batch): instance H2D + proofs D2H inside the timed region.
-Both include the per-round scalar uploads / 48-byte point downloads that the host side of the Fiat-Shamir transcript needs
-(its opening -- the bulk of the hashing -- runs on the GPU).  The CRS digit table (fixed-base MSM) is built once at prover creation.
+`e2e`    : the same through the host-buffer C ABI (cdp_prove_batch): instance + witnesses + randomness H2D, proofs D2H inside the timed region.
+The whole protocol (Fiat-Shamir transcript and scalar algebra included) runs on the GPU; the host draws the prover's randomness (ChaCha12).
+`roofline`: the dominant kernel timed in a SERIALISED pass of the same step (lanes one after the other, so CUDA-event durations are
+device time of that kernel alone), against the measured HBM copy bandwidth (MEASURED_PEAKS.json) and the measured IMAD.WIDE rate.
 """
 import argparse
 import json
@@ -30,6 +32,7 @@ R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 GX = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
 GY = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
 README_PROOFS_PER_S = 1.0 / 0.560  # reference README.md:49, ell = 252 proving on an i7-8550U
+IMAD_PER_MIXED_ADD = 7 * 288 + 4 * 222  # Jacobian + affine: 7 products, 4 squarings
 
 
 def mont(v):
@@ -46,7 +49,16 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="proofs per step per GPU")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batch pipelines per GPU (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--msm-sizes", default="14,18,22", help="log2 sizes of the MSM sweep ('' = skip)")
+    ap.add_argument("--no-extras", action="store_true", help="skip config 4 (small batches gathered to rank 0) and the worst-case verifier step")
     return ap.parse_args()
+
+
+def common_config(args):
+    """The workload both arms run, key for key (arm-specific remarks live outside `config`)."""
+    return {"workload": f"ell={args.ell} CurdleproofsProof::new, {args.batch} independent proofs per step per GPU, bit-exact vs reference CPU path",
+            "ell": args.ell, "batch_per_gpu": args.batch, "l2_flush": "256 MiB memset between steps",
+            "parallelism": "proofs sharded over the GPUs of the node, no data-path collective"}
 
 
 # ---------------------------------------------------------------------------------------------- synthetic workload
@@ -127,11 +139,28 @@ class ClockSampler:
         return out
 
 
+# ---------------------------------------------------------------------------------------------- CPU port: unit costs
+def port_unit_costs(o):
+    """Single-thread unit costs of the CPU port, so that its speed can be judged next to arkworks' published figures."""
+    import ctypes
+    L = o.L
+    L.oracle_time_fp_mul_ns.restype = ctypes.c_double
+    L.oracle_time_mixed_add_ns.restype = ctypes.c_double
+    g = o.generator()
+    k = (R_MOD - 12345).to_bytes(32, "little")
+    n = 64
+    t = time.perf_counter()
+    o.scalar_mul_batch(g * n, k * n)
+    smul_us = (time.perf_counter() - t) / n * 1e6
+    return {"fp_mul_ns": L.oracle_time_fp_mul_ns(2000000), "mixed_add_ns": L.oracle_time_mixed_add_ns(200000), "scalar_mul_255bit_us": smul_us,
+            "note": "one thread; Fp product = six-limb CIOS in C (no assembly), scalar multiplication = double-and-add without GLV, as arkworks' Mul<Fr>"}
+
+
 # ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path on the host cores.  arkworks cannot be built in this image
     (no Rust), so this is the C port under oracle/ (pinned bit-exact to the reference's golden proofs), one proof per
-    host thread, all threads busy."""
+    host thread, all threads busy.  A step = a bounded sample of the workload (one proof per host thread)."""
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -147,24 +176,111 @@ def run_reference(args, rank, world):
     a = [buf(inst[k]) for k in ("crs", "R", "S", "T", "U", "M")]
     kk, mb = buf(inst["k"]), buf(inst["m_blinders"])
     count = cores  # bounded sample per step: one proof per host thread
+
     def step():
         return o.L.oracle_time_prove(ell, *a, perm, kk, mb, count, cores, None)
-    for _ in range(min(args.warmup, 1)):
+
+    for _ in range(args.warmup):
         step()
     times = [step() for _ in range(args.steps)]
     t = sum(times)
     value = count * args.steps / t
     line = {"impl": "reference", "metric": f"shuffle_proofs_per_sec_ell{ell}", "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": value / README_PROOFS_PER_S if ell == 252 else None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"ell={ell} CurdleproofsProof::new, {args.batch} independent proofs per step per GPU, bit-exact vs reference CPU path",
-                       "ell": ell, "batch_per_gpu": args.batch, "proofs_per_step": count,
-                       "reference_arm": "the same workload on the host cores, bounded sample per step (C port of the reference path under oracle/, "
-                                        "pinned to the reference's golden proofs; arkworks itself is not buildable here: no Rust toolchain)"},
+            "config": common_config(args),
+            "reference_arm": "the same workload on the host cores, a bounded sample per step (C port of the reference path under oracle/, pinned to "
+                             "the reference's golden proofs; arkworks itself is not buildable here: no Rust toolchain)",
             "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port",
-                             "sample": f"{count} proofs per step, one per host thread, {args.steps} steps"},
+                             "sample": f"{count} proofs per step, one per host thread, {args.steps} steps after {args.warmup} warm-up steps",
+                             "unit_costs": port_unit_costs(o)},
             "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- MSM sweep (metric 2)
+def msm_sweep(args, eng, stream, rank, world, flush_buf, with_cpu):
+    """Standalone G1 MSM (`util::msm`, /root/reference/src/util.rs:19-22) of 2^k pairs, device-resident, sharded by base range over the ranks
+    through the engine's communicator: the only collective is one all-gather of the 144-byte partial sums.  Inputs depend on the global
+    index only, so the result (`checksum`: its 48-byte encoding) is the same for every N."""
+    import ctypes
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from curdleproofs_b200.sharded import Comm, shard_range
+    sizes = [int(x) for x in args.msm_sizes.split(",") if x.strip()]
+    if not sizes:
+        return None
+    lib, h = eng.lib, eng.handle
+    comm = Comm.from_torch_distributed(eng, rank, world)
+    g = mont(GX) + mont(GY)
+    out = {"metric": "g1_msm_pairs_per_sec", "unit": "pairs/s", "collective": "one ncclAllGather of the 144-byte partial sums per MSM (cdp_msm_sharded_dev)",
+           "scalars": "uniform 254-bit (< r)", "bases": "t_i * G, t_i uniform 254-bit, seeded by the global index", "points": []}
+    o = None
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib
+        o = oracle_lib.Oracle()
+        o.L.oracle_msm.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int]
+    for lg in sizes:
+        n = 1 << lg
+        lo, hi = shard_range(n, rank, world)
+        nl = hi - lo
+        rng = np.random.Generator(np.random.Philox(key=7000 + lg))
+        t_all = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+        s_all = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+        t_all[:, 3] &= np.uint64((1 << 62) - 1)
+        s_all[:, 3] &= np.uint64((1 << 62) - 1)
+        sc = s_all[lo:hi].tobytes()
+        pts = eng.scalar_mul_batch(g * nl, t_all[lo:hi].tobytes()) if nl else b""
+        d_p, d_s, d_o = lib.cdp_dev_alloc(h, max(96 * nl, 96)), lib.cdp_dev_alloc(h, max(32 * nl, 32)), lib.cdp_dev_alloc(h, 144)
+        if nl:
+            lib.cdp_h2d(h, d_p, (ctypes.c_uint8 * len(pts)).from_buffer_copy(pts), len(pts))
+            lib.cdp_h2d(h, d_s, (ctypes.c_uint8 * len(sc)).from_buffer_copy(sc), len(sc))
+        eng.sync()
+        reps = 3 if lg >= 20 else 10
+        for _ in range(2):
+            comm.msm_sharded_dev(d_p, d_s, nl, d_o)
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms_list = []
+        for _ in range(reps):
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            comm.msm_sharded_dev(d_p, d_s, nl, d_o)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_list.append(e0.elapsed_time(e1))
+        ms = statistics.median(ms_list)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        res = (ctypes.c_uint8 * 144)()
+        lib.cdp_d2h(h, res, d_o, 144)
+        eng.sync()
+        checksum = eng.compress_batch(bytes(res)).hex()
+        pt = {"log2_n": lg, "pairs_per_s": n / (ms * 1e-3), "ms": ms, "reps": reps, "checksum": checksum,
+              "achieved_GBps_128B_per_pair": 128 * n / (ms * 1e-3) / 1e9}
+        if o is not None and world == 1:
+            cores = os.cpu_count() or 1
+            cj = (ctypes.c_uint8 * 144)()
+            t0 = time.perf_counter()
+            o.L.oracle_msm(pts, sc, n, cj, cores)
+            dt = time.perf_counter() - t0
+            pt["cpu"] = {"pairs_per_s": n / dt, "seconds": dt, "cores": cores, "kind": "port",
+                         "result_matches_gpu": o.compress_jac(bytes(cj)).hex() == checksum}
+        out["points"].append(pt)
+        for d in (d_p, d_s, d_o):
+            lib.cdp_dev_free(h, d)
+        del t_all, s_all, pts, sc
+    comm.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- main arm
@@ -175,6 +291,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+
+    import ctypes
 
     import torch
     import torch.distributed as dist
@@ -192,11 +310,11 @@ def main():
     crs, rnd, g, fr, rs = make_instances(eng, ell, B, seed=2024)
     rnd.seed(7777 + rank)  # rank-specific instances, shared CRS
     insts = build_batch(eng, crs, ell, B, rnd, g, fr, rs)
-    # host threads: the box's cores are shared by the ranks of this node (one process per GPU)
-    host_threads = max(16, (os.cpu_count() or 8) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))  # >= 2 per lane
+    # host threads: the box's cores are shared by the ranks of this node (one process per GPU); the host only stages buffers and draws randomness
+    cores = os.cpu_count() or 8
+    host_threads = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     bp = BatchProver(eng, ell, crs, max_batch=B, lanes=args.lanes, host_threads=host_threads)
 
-    import ctypes
     cat = lambda key: b"".join(i[key] for i in insts)  # noqa: E731
     arr = lambda b: (ctypes.c_uint8 * len(b)).from_buffer_copy(b)  # noqa: E731
     R, S, T, U, M, K, MB = (arr(cat(k)) for k in ("R", "S", "T", "U", "M", "k", "m_blinders"))
@@ -205,116 +323,178 @@ def main():
     out = (ctypes.c_uint8 * (B * bp.proof_size))()
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
-    def step(resident):
+    def step(resident, prover=None, n=B, outbuf=None):
+        prover = prover or bp
         with torch.cuda.stream(stream):
             flush_buf.zero_()  # L2 flush between steps (256 MiB > 126 MB L2)
         if resident:
-            bp.prove_raw(B, None, None, None, None, None, perm, K, MB, seeds, out=out, split=False)
+            prover.prove_raw(n, None, None, None, None, None, perm, K, MB, seeds, out=outbuf or out, split=False)
         else:
-            bp.prove_raw(B, R, S, T, U, M, perm, K, MB, seeds, out=out, split=False)
+            prover.prove_raw(n, R, S, T, U, M, perm, K, MB, seeds, out=outbuf or out, split=False)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(resident, steps):
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = bp.launch_count
         with torch.cuda.stream(stream):
             e0.record(stream)
         for _ in range(steps):
-            step(resident)
+            fn()
         with torch.cuda.stream(stream):
             e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, bp.launch_count - l0
+        return max_over_ranks(e0.elapsed_time(e1)), bp.launch_count - l0
 
     step(False)  # stages the instance batch in HBM (and is the first warm-up step)
     for _ in range(max(0, args.warmup - 1)):
         step(True)
-    # ---- timed region 1: inputs resident in HBM, per-kernel profile on
-    bp.profile_reset()
-    bp.profile_enable(True)
+    # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_res, launches = timed(True, args.steps)
+    ms_res, launches = timed(lambda: step(True), args.steps)
     clocks = sampler.stop() if sampler else None
-    prof = bp.profile_read()
-    bp.profile_enable(False)
     timing = bp.last_timing()
     # ---- timed region 2: end to end through the host-buffer API
-    ms_e2e, _ = timed(False, args.steps)
+    ms_e2e, _ = timed(lambda: step(False), args.steps)
     traffic = bp.last_traffic()
     proof0 = bytes(out[:bp.proof_size])
+    # ---- per-kernel device time: one more step with the lanes SERIALISED (nothing overlaps, so event durations are device time of each kernel)
+    bp.set_serial(True)
+    bp.profile_reset()
+    bp.profile_enable(True)
+    t_ser = time.perf_counter()
+    step(True)
+    torch.cuda.synchronize()
+    t_ser = (time.perf_counter() - t_ser) * 1e3
+    prof = bp.profile_read()
+    bp.profile_enable(False)
+    bp.set_serial(False)
+    table_bytes = bp.table_bytes
+
     # ---- secondary metric: verifies/s on the proofs just produced (CurdleproofsProof::deserialize + verify through cdp_verify_batch)
-    bp.close()
     VB = B
-    bv = BatchVerifier(eng, ell, crs, max_batch=VB, host_threads=host_threads)
+    bv = BatchVerifier(eng, ell, crs, max_batch=VB, host_threads=host_threads)  # shares the prover's digit table
     vout = (ctypes.c_uint8 * VB)()
 
-    def vstep():
-        bv.verify_raw(VB, R, S, T, U, M, out, None, out=vout)
+    def vstep(proofs=out):
+        bv.verify_raw(VB, R, S, T, U, M, proofs, None, out=vout)
 
     vstep()
-    barrier()
-    ve0, ve1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ve0.record(stream)
-    for _ in range(args.steps):
-        vstep()
-    with torch.cuda.stream(stream):
-        ve1.record(stream)
-    barrier()
-    ms_ver = ve0.elapsed_time(ve1)
-    if world > 1:
-        t = torch.tensor([ms_ver], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_ver = float(t.item())
+    ms_ver, _ = timed(vstep, args.steps)
     all_ok = all(x == 1 for x in vout)
+    verify = {"metric": f"shuffle_verifies_per_sec_ell{ell}", "value": world * VB * args.steps / (ms_ver * 1e-3), "unit": "verifies/s",
+              "batch_per_gpu": VB, "ms_per_step": ms_ver / args.steps, "all_accepted": all_ok,
+              "note": "host buffers in (instance + serialised proofs), verdicts out; README.md:49 reference: 35 ms/verify on i7-8550U"}
+    extras = {}
+    if not args.no_extras:
+        # worst case for the merged check: one invalid proof in every lane's sub-batch -> every lane falls back to proof-by-proof MSMs
+        bad = (ctypes.c_uint8 * len(out)).from_buffer_copy(out)
+        nl = max(1, bv.lanes)
+        per = (VB + nl - 1) // nl
+        bad_idx = list(range(0, VB, per))
+        for i in bad_idx:
+            bad[i * bp.proof_size + bp.proof_size - 1] ^= 1  # x_final: still canonical with overwhelming probability, no longer valid
+        s0 = bv.merge_stats()
+        vstep(bad)
+        ms_bad, _ = timed(lambda: vstep(bad), 2)
+        s1 = bv.merge_stats()
+        verdicts_ok = all((vout[i] != 1) == (i in set(bad_idx)) for i in range(VB))
+        verify["worst_case"] = {"value": world * VB * 2 / (ms_bad * 1e-3), "unit": "verifies/s", "ms_per_step": ms_bad / 2,
+                                "what": f"{len(bad_idx)} invalid proofs per step, one in every lane sub-batch: the merged check rejects and every proof is decided by its own accumulated MSM",
+                                "fallback_sub_batches": s1["fallback"] - s0["fallback"], "verdicts_correct": verdicts_ok}
+    bv.close()
+
+    if not args.no_extras:
+        # config 4 of BASELINE.json: 1024 proofs over 8 GPUs = 128 per GPU per step, proofs gathered to rank 0 (end to end, host buffers)
+        B4 = min(128, B)
+        bp4 = BatchProver(eng, ell, crs, max_batch=B4, host_threads=host_threads)  # shares the digit table
+        out4 = (ctypes.c_uint8 * (B4 * bp.proof_size))()
+        d_gather = torch.empty(B4 * bp.proof_size, dtype=torch.uint8, device="cuda")
+        gathered = [torch.empty_like(d_gather) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+        def step4():
+            step(False, prover=bp4, n=B4, outbuf=out4)
+            if world > 1:
+                d_gather.copy_(torch.frombuffer(out4, dtype=torch.uint8), non_blocking=False)
+                dist.gather(d_gather, gathered, dst=0)
+
+        step4(); step4()
+        ms4, _ = timed(step4, args.steps)
+        extras["config4"] = {"what": f"{B4} proofs per GPU per step ({world * B4} per step over {world} GPU(s)), end to end from host buffers, proofs gathered to rank 0 (NCCL gather)",
+                             "value": world * B4 * args.steps / (ms4 * 1e-3), "unit": "proofs/s", "ms_per_step": ms4 / args.steps, "lanes": bp4.lanes}
+        bp4.close()
+
+    sweep = None
+    try:
+        sweep = msm_sweep(args, eng, stream, rank, world, flush_buf, with_cpu=(world == 1 and not args.no_cpu_baseline))
+    except Exception as e:  # never lose the headline line
+        sweep = {"error": repr(e)}
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     value = world * B * args.steps / (ms_res * 1e-3)
     e2e = world * B * args.steps / (ms_e2e * 1e-3)
-    # ---- roofline of the dominant kernel (by device time inside the timed region)
+    # ---- roofline of the dominant kernel, from the serialised pass
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    # algorithmic bytes per unit: variable-base pair = 32 B scalar + 96 B base; fixed-base pair = 32 B scalar +
-    # 16 gathered 96-byte table points (c = 16); fold element = 192 B in + 96 B out; normalised point = 144 B in + 96 B out
-    bytes_per_unit = {"msm_buckets": 128, "msm_fixed": 32 + 16 * 96, "smul": 288, "normalize": 240, "msm_combine": 144, "other": 144}
-    # measured DRAM bytes per unit of the same kernels from the committed `ncu --set full` captures (dram__bytes_read + write per launch /
-    # units of that launch): profiles/r01_ncu_fixed_msm_v1.txt (407.5 MB / 131,584 pairs), profiles/r01_ncu_msm_buckets_v3.txt (157.3 MB / 520,192 pairs)
-    ncu_traffic_per_unit = {"msm_fixed": 3097.0, "msm_buckets": 302.0}
-    # dominant = the throughput kernel with the most device time; the latency-bound launches (combine: 130 dependent doublings per
-    # thread, normalise: one Fp inversion per thread) run a handful of warps each, and with 8 lanes in flight their summed durations
-    # mostly measure waiting for SM time, not work
-    dom = max(("msm_fixed", "msm_buckets", "smul"), key=lambda k: prof[k]["ms"])
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (burst)") if "hbm_gbs" in peaks else (6650.0, "fallback of B200_PROFILING.md")
+    # ncu DRAM bytes per unit of the FINAL kernels (profiles/r02_ncu_traffic.json, written from this round's `ncu --set full` captures)
+    ncu_traffic = {}
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+    except Exception:
+        pass
+    throughput_kinds = ("msm_fixed", "msm_buckets", "smul")
+    dom = max(throughput_kinds, key=lambda k: prof[k]["ms"])
     d = prof[dom]
     avg_ms = d["ms"] / max(1, d["launches"])
-    alg_bytes = bytes_per_unit[dom] * d["units"] / max(1, d["launches"])
-    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    # integer-pipe view: Fp multiplications are 300 IMAD.WIDE.U32 each; peak measured live with a register-only kernel
+    units_per_launch = d["units"] / max(1, d["launches"])
+    # an MSM pair is 128 algorithmic bytes (32-byte scalar + 96-byte base), a fold element 288
+    contract_bytes = {"msm_fixed": 128, "msm_buckets": 128, "smul": 288}[dom]
+    achieved = contract_bytes * units_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     imad_ms = min(eng.bench_kernel(0, 148 * 4, 256, 2000) for _ in range(3))
     imad_peak = 148 * 4 * 256 * 2000 * 128 / (imad_ms * 1e-3)
     total_kernel_ms = sum(v["ms"] for v in prof.values())
+    tr = ncu_traffic.get(dom, {})
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": ncu_traffic_per_unit[dom] * d["units"] / max(1, d["launches"]) if dom in ncu_traffic_per_unit else None,
-                "traffic_source": "ncu dram bytes per unit (profiles/r01_ncu_*) x units per launch", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                "traffic": tr.get("dram_bytes_per_unit") * units_per_launch if tr.get("dram_bytes_per_unit") else None,
+                "traffic_source": tr.get("source"), "peak_source": peak_src,
+                "algorithmic_bytes_per_unit": contract_bytes, "units_per_launch": units_per_launch, "avg_launch_ms": avg_ms,
+                "timing": "CUDA events around every launch of ONE extra step with the prover's lanes serialised (cdp_prover_set_serial): kernels run alone",
                 "share_of_kernel_time": d["ms"] / total_kernel_ms if total_kernel_ms else None,
-                "note": "381-bit modular arithmetic: the binding roofline is the integer multiply pipe, not HBM (see int_pipe)",
-                "int_pipe": {"peak_imad_wide_per_s": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad)"},
-                "kernel_ms": {k: v["ms"] / args.steps for k, v in prof.items()}}
-    # ---- the same kernel timed ALONE (nothing else on the GPU): one fixed-base launch of the IPA-round shape for the whole batch
+                "serialised_step_ms": t_ser, "serialised_kernel_ms_sum": total_kernel_ms,
+                "kernel_ms": {k: v["ms"] for k, v in prof.items()}, "kernel_launches": {k: v["launches"] for k, v in prof.items()},
+                "note": "381-bit modular arithmetic: the binding roofline is the integer multiply pipe, not HBM (int_pipe); fixed-base pairs also gather "
+                        "16 table entries of 96 B each (table_gather_*), which the 128-byte contract figure does not count"}
+    if dom == "msm_fixed":
+        gather_bytes = 32 + 16 * 96
+        adds_per_s = 16 * units_per_launch / (avg_ms * 1e-3)
+        roofline["table_gather_bytes_per_pair"] = gather_bytes
+        roofline["table_gather_achieved_GBps"] = gather_bytes * units_per_launch / (avg_ms * 1e-3) / 1e9
+        roofline["table_gather_frac"] = roofline["table_gather_achieved_GBps"] / hbm_peak
+        roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)",
+                                "achieved": adds_per_s * IMAD_PER_MIXED_ADD, "frac": adds_per_s * IMAD_PER_MIXED_ADD / imad_peak,
+                                "mixed_adds_per_s": adds_per_s, "imad_wide_per_mixed_add": IMAD_PER_MIXED_ADD}
+    else:
+        roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)"}
+    # ---- the same kernel timed ALONE on synthetic scalars (nothing else on the GPU): one fixed-base launch of the IPA-round shape for the whole batch
     try:
         from curdleproofs_b200 import FixedSeg
         n_ = ell + 4
@@ -346,10 +526,12 @@ def main():
         pairs = B * (2 * n_ + 2)
         madds = pairs * 16 / (iso_ms * 1e-3)
         roofline["isolated"] = {"kernel": "k_fixed_msm, IPA-round shape, whole batch in one launch, nothing else running", "ms": iso_ms,
-                                "pairs_per_s": pairs / (iso_ms * 1e-3), "achieved_GBps": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9,
-                                "hbm_frac": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9 / hbm_peak,
-                                "mixed_adds_per_s": madds, "imad_wide_per_mixed_add": 7 * 288 + 4 * 222,
-                                "int_pipe_frac": madds * (7 * 288 + 4 * 222) / imad_peak}
+                                "pairs_per_s": pairs / (iso_ms * 1e-3),
+                                "achieved_GBps_128B_per_pair": pairs * 128 / (iso_ms * 1e-3) / 1e9, "hbm_frac_128B_per_pair": pairs * 128 / (iso_ms * 1e-3) / 1e9 / hbm_peak,
+                                "achieved_GBps_table_gather": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9,
+                                "hbm_frac_table_gather": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9 / hbm_peak,
+                                "mixed_adds_per_s": madds, "imad_wide_per_mixed_add": IMAD_PER_MIXED_ADD,
+                                "int_pipe_frac": madds * IMAD_PER_MIXED_ADD / imad_peak}
         for dd in (d_sc, d_sg, d_out):
             lib.cdp_dev_free(h, dd)
         tab.close()
@@ -358,22 +540,20 @@ def main():
     line = {"metric": f"shuffle_proofs_per_sec_ell{ell}", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": value / README_PROOFS_PER_S if ell == 252 else None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"ell={ell} CurdleproofsProof::new, {B} independent proofs per step per GPU, bit-exact vs reference CPU path",
-                       "ell": ell, "batch_per_gpu": B, "l2_flush": "256 MiB memset between steps", "parallelism": f"proofs sharded over {world} GPU(s), no collective",
-                       "baseline": "README.md:49 560 ms/proof on i7-8550U (other hardware)", "host_threads": host_threads, "lanes": bp.lanes},
+            "config": common_config(args),
+            "run": {"host_threads": host_threads, "host_cores": cores, "lanes": bp.lanes, "table_bytes": table_bytes,
+                    "baseline": "README.md:49 560 ms/proof on i7-8550U (other hardware)",
+                    "transcript": "device (cdp_prove_stage_dev)" if os.environ.get("CDP_PROVE_HOST_TRANSCRIPT", "0") in ("", "0") else "host"},
             "e2e": {"value": e2e, "unit": "proofs/s", "h2d_bytes_per_step": traffic["h2d_bytes"], "d2h_bytes_per_step": traffic["d2h_bytes"],
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
-            "verify": {"metric": f"shuffle_verifies_per_sec_ell{ell}", "value": world * VB * args.steps / (ms_ver * 1e-3), "unit": "verifies/s",
-                       "batch_per_gpu": VB, "ms_per_step": ms_ver / args.steps, "all_accepted": all_ok,
-                       "note": "host buffers in (instance + serialised proofs), verdicts out; README.md:49 reference: 35 ms/verify on i7-8550U"},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks, "verify": verify, "msm_sweep": sweep, "extra": extras,
             "host_breakdown_last_step_ms": timing}
+    bp.close()
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on a bounded sample, and a parity check of proof 0
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib
         o = oracle_lib.Oracle()
-        cores = os.cpu_count() or 1
         inst = insts[0]
         pc = (ctypes.c_uint32 * ell)(*inst["perm"])
         a = [arr(inst[k]) for k in ("crs", "R", "S", "T", "U", "M")]
@@ -386,9 +566,11 @@ def main():
         line["verify"]["cpu_baseline"] = {"value": 4 * cores / tv, "unit": "verifies/s", "cores": cores, "kind": "port", "all_accepted": bool(allok.value)}
         line["cpu_baseline"] = {"value": count / t, "unit": "proofs/s", "cores": cores, "kind": "port",
                                 "sample": f"{count} ell={ell} proofs, one per host thread ({cores} threads), oracle C port",
-                                "parity_proof0_bit_exact": bool(want0 == proof0), "oracle_verifies_gpu_proof": o.verify(inst, proof0) == 1}
+                                "parity_proof0_bit_exact": bool(want0 == proof0), "oracle_verifies_gpu_proof": o.verify(inst, proof0) == 1,
+                                "unit_costs": port_unit_costs(o)}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -652,6 +652,7 @@ extern "C" void cdp_verifier_destroy(cdp_verifier *v) {
     delete v;
 }
 extern "C" const char *cdp_verifier_last_error(const cdp_verifier *v) { return v ? v->err.c_str() : "null verifier"; }
+extern "C" int cdp_verifier_lane_count(const cdp_verifier *v) { return v ? (int)v->lanes.size() : 0; }
 extern "C" void cdp_verifier_merge_stats(const cdp_verifier *v, uint64_t out[2]) {
     out[0] = out[1] = 0;
     if (!v) return;

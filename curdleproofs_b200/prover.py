@@ -49,6 +49,9 @@ def load_prover_library() -> ctypes.CDLL:
         lib.cdp_whisk_verify_shuffle_proofs.restype = c_int
         lib.cdp_whisk_verify_shuffle_proofs.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
         lib.cdp_prover_last_traffic.argtypes = [c_void_p, POINTER(c_uint64)]
+        lib.cdp_prover_set_serial.argtypes = [c_void_p, c_int]
+        lib.cdp_prover_table_bytes.restype = c_size_t
+        lib.cdp_prover_table_bytes.argtypes = [c_void_p]
         _PLIB = lib
     return _PLIB
 
@@ -140,6 +143,14 @@ class BatchProver:
     def launch_count(self) -> int:
         return sum(int(self.engine.lib.cdp_launch_count(c)) for c in self._lane_ctx)
 
+    def set_serial(self, on: bool):
+        """Diagnostics: run the lanes one after the other, so that per-kernel profile times are those of kernels running alone."""
+        self._lib.cdp_prover_set_serial(self._h, int(on))
+
+    @property
+    def table_bytes(self) -> int:
+        return int(self._lib.cdp_prover_table_bytes(self._h))
+
     def profile_enable(self, on: bool = True):
         for c in self._lane_ctx:
             self.engine.lib.cdp_profile_enable(c, int(on))
@@ -230,6 +241,9 @@ class BatchVerifier:
         if rc != 0:
             raise CdpError(f"cdp_verifier_create failed (code {rc})")
         self._h = h
+        lib.cdp_verifier_lane_count.restype = c_int
+        lib.cdp_verifier_lane_count.argtypes = [c_void_p]
+        self.lanes = int(lib.cdp_verifier_lane_count(h))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -92,6 +92,8 @@ typedef struct cdp_verifier cdp_verifier;
 int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads, int lanes);
 void cdp_verifier_destroy(cdp_verifier *v);
 const char *cdp_verifier_last_error(const cdp_verifier *v);
+/* Lanes (concurrent sub-batch pipelines; a batch is split over them contiguously, as evenly as possible). */
+int cdp_verifier_lane_count(const cdp_verifier *v);
 /* Timing of the last cdp_verify_batch call, max over lanes, in ms: total, host compute (transcripts, coefficients), waiting for the GPU. */
 void cdp_verifier_last_timing(const cdp_verifier *v, double out_ms[3]);
 /* Since creation: [0] lane sub-batches accepted by the merged check, [1] lane sub-batches that fell back to proof-by-proof checks. */

@@ -272,6 +272,23 @@ EXPORT double oracle_time_msm(const uint8_t *pts, const uint8_t *scalars, size_t
     for (int i = 0; i < reps; i++) oracle_msm(pts, scalars, n, out_jac, threads);
     return now_s() - t0;
 }
+/* single-thread unit costs of this port (bench.py prints them next to the baseline so that its speed can be judged) */
+EXPORT double oracle_time_fp_mul_ns(int reps) {
+    fp_t a, b; memcpy(a.l, FP_GX_MONT, 48); memcpy(b.l, FP_GY_MONT, 48);
+    double t0 = now_s();
+    for (int i = 0; i < reps; i++) fp_mul(&a, &a, &b);   /* dependent chain */
+    double dt = now_s() - t0;
+    volatile uint64_t sink = a.l[0]; (void)sink;
+    return dt / reps * 1e9;
+}
+EXPORT double oracle_time_mixed_add_ns(int reps) {
+    g1a_t G; g1a_generator(&G); g1j_t J; g1j_from_affine(&J, &G); g1j_dbl(&J, &J);
+    double t0 = now_s();
+    for (int i = 0; i < reps; i++) g1j_add_affine(&J, &J, &G);
+    double dt = now_s() - t0;
+    volatile uint64_t sink = J.X.l[0]; (void)sink;
+    return dt / reps * 1e9;
+}
 EXPORT int oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

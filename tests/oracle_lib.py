@@ -114,6 +114,13 @@ class Oracle:
         return bytes(out)
 
     # ---- protocol ----
+    def stdrng_seed_bytes(self, seed):
+        """The 32-byte ChaCha12 key `StdRng::seed_from_u64(seed)` expands to (rand_core's PCG32 fill): the same stream through `from_seed`."""
+        out = _u8(32)
+        self.L.oracle_stdrng_seed_bytes.argtypes = [c_uint64, c_void_p]
+        self.L.oracle_stdrng_seed_bytes(seed, out)
+        return bytes(out)
+
     def crs_points(self, ell):
         out = _u8(96 * (ell + 7))
         self.L.oracle_generate_crs_points(ell, out)

@@ -72,3 +72,47 @@ def test_full_size_ell252_multi_lane_round_trip(engine, oracle):
     shifted = insts[1:] + insts[:1]   # every proof now sits on a different instance
     assert bv.verify_batch(shifted, proofs) == [0] * batch
     bv.close()
+
+
+def test_ell252_sixteen_proofs_across_all_lanes_byte_identical(engine, oracle):
+    """BASELINE config 2 (ell = 252): 64 proofs over 8 lanes; the first and the last proof of EVERY lane's sub-batch (16 proofs) are
+    compared byte for byte with the oracle's `CurdleproofsProof::new` (/root/reference/src/curdleproofs.rs:59-184), half of them with the
+    rng given as a 32-byte key instead of the u64 test seed."""
+    from curdleproofs_b200 import BatchProver
+    ell, batch, lanes = 252, 64, 8
+    crs = oracle.crs_points(ell)
+    base = [oracle.random_instance(ell, crs, seed=700 + i, threads=8) for i in range(4)]
+    insts = [base[(3 * i) % 4] for i in range(batch)]
+    seeds = [31000 + 7 * i for i in range(batch)]
+    bp = BatchProver(engine, ell, crs, max_batch=batch, lanes=lanes)
+    assert bp.lanes == lanes
+    proofs = bp.prove_batch(insts, seeds)
+    keys = [oracle.stdrng_seed_bytes(s) for s in seeds]
+    proofs_k = bp.prove_batch(insts, rng_keys=keys)
+    bp.close()
+    per = batch // lanes
+    picked = [l * per for l in range(lanes)] + [l * per + per - 1 for l in range(lanes)]
+    assert len(picked) == 16
+    for j, i in enumerate(picked):
+        want = oracle.prove(insts[i], rng_seed=seeds[i], threads=8)
+        assert (proofs if j % 2 == 0 else proofs_k)[i] == want, f"proof {i} (lane {i // per}) differs from the oracle"
+    assert proofs == proofs_k
+
+
+def test_ell1020_proof_and_verdict_parity(engine, oracle):
+    """BASELINE config 3 (ell = 1020, n = 1024): one proof byte-identical to the oracle's, accepted by the oracle's verifier and by the
+    batched GPU verifier; a proof attached to a permuted instance is rejected by both."""
+    from curdleproofs_b200 import BatchProver, BatchVerifier
+    ell = 1020
+    crs = oracle.crs_points(ell)
+    inst = oracle.random_instance(ell, crs, seed=4242, threads=8)
+    bp = BatchProver(engine, ell, crs, max_batch=2)
+    proofs = bp.prove_batch([inst, inst], [5, 6])
+    bp.close()
+    assert proofs[0] == oracle.prove(inst, rng_seed=5, threads=8)
+    assert oracle.verify(inst, proofs[1], threads=8) == 1
+    bad = dict(inst, T=inst["U"], U=inst["T"])
+    bv = BatchVerifier(engine, ell, crs, max_batch=2)
+    assert bv.verify_batch([inst, bad], proofs) == [1, 0]
+    assert oracle.verify(bad, proofs[1], threads=8) == 0
+    bv.close()
