@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #pragma GCC visibility push(default)
@@ -189,6 +190,42 @@ int smul_jobs_dev(cdp_ctx *ctx, uint8_t *d_pts, const uint8_t *d_scalars, const 
 }
 
 const uint8_t INF_JAC_ZERO[CDP_JACOBIAN_BYTES] = {0};
+
+// Host-to-device copy of a caller's (pageable) buffer, queued on the context's stream.  A cudaMemcpyAsync from pageable memory is staged by
+// the driver at ~1-3 GB/s; large inputs of the host-buffer drop-ins (cdp_msm at 2^20+ pairs: 128 B per pair) go through two pinned
+// 8 MiB buffers instead, filled by a few host threads while the previous chunk is on the wire.
+int h2d_pipelined(cdp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    constexpr size_t CH = size_t(8) << 20;
+    if (bytes <= (size_t(1) << 20)) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return CDP_OK;
+    }
+    TRY(ensure_host(ctx, ctx->h_stage, 2 * CH));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // earlier users of the staging buffer are done
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    for (auto &e : ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min<size_t>(4, std::max(1u, hw / 2));
+    uint8_t *stage = (uint8_t *)ctx->h_stage.ptr;
+    const uint8_t *src = (const uint8_t *)h_src;
+    int rc = CDP_OK;
+    size_t k = 0;
+    for (size_t off = 0; off < bytes && rc == CDP_OK; off += CH, k++) {
+        const size_t b = k & 1, len = std::min(CH, bytes - off);
+        if (k >= 2 && cudaEventSynchronize(ev[b]) != cudaSuccess) { rc = fail(ctx, CDP_ERR_CUDA, "h2d_pipelined: event"); break; }
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++)
+            th.emplace_back([=] { memcpy(stage + b * CH + len * t / nt, src + off + len * t / nt, len * (t + 1) / nt - len * t / nt); });
+        memcpy(stage + b * CH, src + off, len / nt);
+        for (auto &x : th) x.join();
+        if (cudaMemcpyAsync((uint8_t *)d_dst + off, stage + b * CH, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaEventRecord(ev[b], ctx->stream) != cudaSuccess)
+            rc = fail(ctx, CDP_ERR_CUDA, "h2d_pipelined: copy");
+    }
+    if (rc == CDP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, CDP_ERR_CUDA, "h2d_pipelined: sync");  // the staging buffer is free again
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
 
 }  // namespace
 
@@ -479,7 +516,12 @@ extern "C" int cdp_normalize_dev(cdp_ctx *ctx, const uint8_t *d_jac, size_t n, u
 // =================================================================================================== host-buffer drop-ins
 // One MSM of any size: chunks of <= 2048 points (one CTA pair each), window sums reduced across chunks, one Horner pass.
 static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
-    size_t chunk = std::min<size_t>(SMALL_MSM_MAX_N, n);
+    // A lone MSM is latency-bound: a lane of the bucket kernel adds its ~m / 4 points (chunk of m points, c = 5) one after the other, ~8 us
+    // per mixed addition for a warp running alone, and only 7 warps work on a chunk.  So a single MSM is cut into chunks of <= 64 points
+    // (16 sequential additions per lane, n / 64 * 7 warps in flight); their bucket sums are added slot by slot and combined once -- the
+    // ~130 dependent doublings of that one Horner pass (~0.7 ms) are what is left.  CDP_MSM_SINGLE_CHUNK overrides the chunk size.
+    static const size_t single_chunk = [] { const char *e = getenv("CDP_MSM_SINGLE_CHUNK"); size_t v = e ? (size_t)atoll(e) : 64; return std::min<size_t>(SMALL_MSM_MAX_N, std::max<size_t>(v, 16)); }();
+    size_t chunk = std::min<size_t>(single_chunk, n);
     size_t nchunks = (n + chunk - 1) / chunk;
     msm_cfg g = pick_cfg(chunk);
     std::vector<msm_seg_t> segs(nchunks);
@@ -509,7 +551,9 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
 }
 
 // ---- large Pippenger (k_bigmsm.cu) ---------------------------------------------------------------------------
-constexpr size_t BIG_MSM_MIN_N = size_t(1) << 13;  // CDP_BIG_MIN_LOG2 overrides (tuning)
+// below this size the chunked small-MSM path (more additions per pair, but no sort and a much shorter launch chain) is faster;
+// CDP_BIG_MIN_LOG2 overrides (tuning)
+static const size_t BIG_MSM_MIN_N = [] { const char *e = getenv("CDP_BIG_MIN_LOG2"); int v = e ? atoi(e) : 16; return size_t(1) << (v >= 11 && v <= 24 ? v : 16); }();
 static int big_c_for(size_t n) {
     static int forced = -1;
     if (forced < 0) { const char *e = getenv("CDP_BIG_C"); forced = e ? atoi(e) : 0; }
@@ -623,8 +667,8 @@ extern "C" int cdp_msm(cdp_ctx *ctx, const uint8_t *affine_pts, const uint8_t *s
     TRY(ensure_dev(ctx, ctx->d_pts, n * CDP_AFFINE_BYTES));
     TRY(ensure_dev(ctx, ctx->d_scalars, n * CDP_SCALAR_BYTES));
     TRY(ensure_dev(ctx, ctx->d_out, CDP_JACOBIAN_BYTES));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pts.ptr, affine_pts, n * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(h2d_pipelined(ctx, ctx->d_pts.ptr, affine_pts, n * CDP_AFFINE_BYTES));
+    TRY(h2d_pipelined(ctx, ctx->d_scalars.ptr, scalars, n * CDP_SCALAR_BYTES));
     if (n >= BIG_MSM_MIN_N) TRY(msm_big_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
     else TRY(msm_single_resident(ctx, (const uint8_t *)ctx->d_pts.ptr, (const uint8_t *)ctx->d_scalars.ptr, n, (uint8_t *)ctx->d_out.ptr));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_jac, ctx->d_out.ptr, CDP_JACOBIAN_BYTES, cudaMemcpyDeviceToHost, ctx->stream));

@@ -6,9 +6,11 @@
 // `util::msm` (/root/reference/src/util.rs:19-22) and the fold loops
 // (/root/reference/src/inner_product_argument.rs:174-179, src/same_multiscalar_argument.rs:126-131).
 //
-// Multiplication is a column-wise (product-scanning) Montgomery product: every 32x32->64 partial product is one
-// `mad.lo.cc / madc.hi.cc` pair, which ptxas fuses into a single IMAD.WIDE.U32 with carry-out, plus one IADD3.X
-// for the third accumulator word.  300 IMAD-pipe instructions per product, 48 live registers, no local memory.
+// Multiplication is a ROW-wise Montgomery product with two interleaved accumulator arrays (even / odd limbs of the multiplicand): every
+// row is four independent carry chains of six IMAD.WIDE.U32(.X), carries in the condition-code register, p folded in as immediates --
+// 288 wide multiply-adds per product and enough instruction-level parallelism for one warp per scheduler to keep the pipe 63 % busy.
+// Squaring is row-wise too (fp_sqr_rows.inc, generated and model-checked by tools/gen_fp_sqr.py): 222 wide multiply-adds.  Both are
+// called (register ABI), not inlined, so that the hot set of every kernel fits the instruction cache.
 // No tensor cores: 381-bit modular integer arithmetic is not a dense contraction.
 #pragma once
 #include <stdint.h>

@@ -12,7 +12,6 @@
 //                    scalars) goes to a device-side work list instead: k_big_heavy (one CTA per 4096-point chunk), k_big_heavy_fold
 //   k_big_reduce_level   sum_b (b+1) B_b per window as a hierarchy of 16-ary running sums (A = plain sum, Bv = index-weighted sum per node)
 //   k_big_horner     Horner over the windows.
-// (k_big_weights / k_big_final belong to an earlier reduction through the small-MSM kernel and are kept for experiments.)
 #include <cub/device/device_radix_sort.cuh>
 
 #include "launch.h"
@@ -306,51 +305,6 @@ __global__ void __launch_bounds__(128) k_big_fold_top(const uint32_t *__restrict
     if (lane == 0) g1j_store(out + 36 * (size_t)warp, acc);
 }
 
-// weight of slot i as a 32-byte scalar: bucket index + 1 (the constant scalars of the bucket reduction)
-__global__ void k_big_weights(uint32_t *__restrict__ w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const uint32_t slot = i % nb;
-    (void)chunks;
-    uint32_t bucket = ((int)(i / nb) == nwin - 1) ? slot / sp_top : slot;
-    uint4 *d = reinterpret_cast<uint4 *>(w + 8 * (size_t)i);
-    d[0] = make_uint4(bucket + 1, 0, 0, 0);
-    d[1] = make_uint4(0, 0, 0, 0);
-}
-
-// in: [nwin][chunks] Jacobian partial weighted sums; out = sum_w 2^(c w) * sum_chunk in[w][chunk].  One warp.
-__global__ void __launch_bounds__(32) k_big_final(const uint32_t *__restrict__ in, int nwin, int chunks, int c, uint32_t *__restrict__ out_jac) {
-    const int lane = threadIdx.x;
-    g1j total;
-    g1j_set_inf(total);
-#pragma unroll 1
-    for (int w = nwin - 1; w >= 0; w--) {
-        // lanes sum the chunk results of window w
-        g1j acc;
-        g1j_set_inf(acc);
-        for (int s = lane; s < ((chunks + 31) & ~31); s += 32) {
-            g1j q;
-            g1j_set_inf(q);
-            if (s < chunks) g1j_load(q, in + 36 * ((size_t)w * chunks + s));
-            g1j_add(acc, acc, q);
-        }
-#pragma unroll 1
-        for (int d = 16; d >= 1; d >>= 1) {
-            g1j o;
-            shfl_down_g1j(o, acc, d, 32);
-            g1j_add(acc, acc, o);
-        }
-        if (lane == 0) {
-            if (w != nwin - 1) {
-#pragma unroll 1
-                for (int k = 0; k < c; k++) g1j_dbl(total, total);
-            }
-            g1j_add(total, total, acc);
-        }
-    }
-    if (lane == 0) g1j_store(out_jac, total);
-}
-
 size_t big_msm_sort_temp_bytes(uint32_t n2, int nwin, int c) {
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
@@ -398,10 +352,6 @@ cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const ui
     k_big_heavy_fold<<<148, 128, 0, st>>>(count, items, (uint32_t)cap, start, nb, partial, buckets_jac);
     return cudaGetLastError();
 }
-cudaError_t launch_big_weights(cudaStream_t st, uint32_t *w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks) {
-    k_big_weights<<<(total + 255) / 256, 256, 0, st>>>(w, total, nb, nwin, sp_top, chunks);
-    return cudaGetLastError();
-}
 cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
                                     uint32_t *Bout) {
     k_big_reduce_level<<<(n_out + 127) / 128, 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
@@ -416,9 +366,4 @@ cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nb
     k_big_fold_top<<<(n_warps * 32 + 127) / 128, 128, 0, st>>>(in, nbt, sp, nw, pad_to, out);
     return cudaGetLastError();
 }
-cudaError_t launch_big_final(cudaStream_t st, const uint32_t *in, int nwin, int chunks, int c, uint32_t *out_jac) {
-    k_big_final<<<1, 32, 0, st>>>(in, nwin, chunks, c, out_jac);
-    return cudaGetLastError();
-}
-
 }  // namespace cdp

@@ -207,6 +207,122 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
     if (lane == 0) g1j_store(out_jac + 36 * (size_t)seg.out_idx, acc);
 }
 
+// ---- the same kernel with the table points staged through shared memory by the bulk-copy engine (cp.async.bulk, SASS: UBLKCP) ----
+// Every thread owns two 96-byte slots and two mbarriers: the copy of the NEXT item's table entry is issued (one instruction, no destination
+// registers) before the current addition starts and is waited for only when its addition begins, so the gathered point does not occupy 24
+// registers across a ~3300-instruction addition as the register-prefetch version above does.  Slots are 112 bytes apart (conflict-free
+// 16-byte shared loads for 8 consecutive lanes).
+constexpr uint32_t FIXED_SLOT_BYTES = 112;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_issue(uint32_t dst, const void *src, uint32_t mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(96u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(96u), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+        if (!ok && ++spins > (1u << 26)) __trap();  // a lost copy must not hang the GPU
+    } while (!ok);
+}
+template <int OCC>
+__global__ void __launch_bounds__(128, OCC) k_fixed_msm_bulk(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
+                                                            const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
+                                                            const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac) {
+    extern __shared__ __align__(16) uint8_t fixed_smem[];
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    // per thread: slots [2][112 B] then, behind all slots, mbarriers [2]
+    uint8_t *slot0 = fixed_smem + (size_t)threadIdx.x * 2 * FIXED_SLOT_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fixed_smem + (size_t)blockDim.x * 2 * FIXED_SLOT_BYTES) + 2 * threadIdx.x;
+    const uint32_t s_slot = smem_u32(slot0), s_bar = smem_u32(bars);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_bar + 8));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp >= count) return;
+    const fixed_seg_t seg = segs[warp];
+    const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
+    // address of the table entry of item q (nullptr: zero digit) and the sign of its digit
+    auto locate = [&](uint32_t q, bool &neg) -> const uint32_t * {
+        const uint32_t i = q / (uint32_t)kp.nw, w = q - i * (uint32_t)kp.nw;
+        uint32_t bidx, sidx;
+        if (i < seg.n) {
+            uint32_t j = i;
+            if (seg.sel_h) {
+                const uint32_t lo = i & (seg.sel_h - 1);
+                j = ((i - lo) << 1) | lo | seg.sel_val;
+            }
+            sidx = seg.scalars_off + j;
+            bidx = seg.base_off + j + (j >= seg.remap_from ? seg.remap_delta : 0u);
+        } else {
+            bidx = seg.extra_base - 1;
+            sidx = seg.scalars_off + seg.extra_scalar;
+        }
+        const int d = fixed_digit(scalars + 8 * (size_t)sidx, w, kp);
+        if (d == 0) return nullptr;
+        neg = d < 0;
+        const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+        return table + 24 * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1));
+    };
+    g1j acc;
+    g1j_set_inf(acc);
+    bool cur_neg = false, have = false;
+    uint32_t q = lane, buf = 0, parity = 0;  // parity bit b = phase of buffer b's barrier
+    while (q < items && !have) {
+        const uint32_t *src = locate(q, cur_neg);
+        q += 32;
+        if (src) {
+            bulk_issue(s_slot, src, s_bar);
+            have = true;
+        }
+    }
+#pragma unroll 1
+    while (have) {
+        bool nxt_neg = false, hn = false;
+        while (q < items && !hn) {
+            const uint32_t *src = locate(q, nxt_neg);
+            q += 32;
+            if (src) {
+                bulk_issue(s_slot + (buf ^ 1) * FIXED_SLOT_BYTES, src, s_bar + (buf ^ 1) * 8);
+                hn = true;
+            }
+        }
+        bulk_wait(s_bar + buf * 8, (parity >> buf) & 1);
+        parity ^= 1u << buf;
+        g1a cur;
+        {
+            const uint4 *sp = reinterpret_cast<const uint4 *>(slot0 + buf * FIXED_SLOT_BYTES);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const uint4 a = sp[k], b = sp[3 + k];
+                cur.x.v[4 * k] = a.x; cur.x.v[4 * k + 1] = a.y; cur.x.v[4 * k + 2] = a.z; cur.x.v[4 * k + 3] = a.w;
+                cur.y.v[4 * k] = b.x; cur.y.v[4 * k + 1] = b.y; cur.y.v[4 * k + 2] = b.z; cur.y.v[4 * k + 3] = b.w;
+            }
+        }
+        if (cur_neg) fp_neg(cur.y, cur.y);
+        g1j_add_mixed(acc, acc, cur);
+        buf ^= 1;
+        cur_neg = nxt_neg;
+        have = hn;
+    }
+    if (lane < seg.addv_n) {  // plain (coefficient 1) device-resident points of the sum
+        g1a cur;
+        g1a_load(cur, var_pts + 24 * ((size_t)seg.addv_off + lane));
+        g1j_add_mixed(acc, acc, cur);
+    }
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) {
+        g1j o;
+        shfl_down_g1j(o, acc, d, 32);
+        g1j_add(acc, acc, o);
+    }
+    if (lane == 0) g1j_store(out_jac + 36 * (size_t)seg.out_idx, acc);
+}
+
 cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint32_t n_bases, int c, int nw, uint32_t *jac_out) {
     k_fixed_pow<<<(n_bases + 63) / 64, 64, 0, st>>>(bases_affine, n_bases, c, nw, jac_out);
     return cudaGetLastError();
@@ -224,6 +340,14 @@ cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint3
                              const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac) {
     if (count == 0) return cudaSuccess;
     const int occ = tuned_occupancy("CDP_OCC_FIXED", 3);
+    static const int bulk = [] { const char *e = getenv("CDP_FIXED_BULK"); return e ? atoi(e) : 0; }();
+    if (bulk) {  // table points staged through shared memory by cp.async.bulk (see k_fixed_msm_bulk)
+        const size_t smem = 128 * 2 * FIXED_SLOT_BYTES + 128 * 2 * 8;
+        if (occ == 5) k_fixed_msm_bulk<5><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+        else if (occ == 4) k_fixed_msm_bulk<4><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+        else k_fixed_msm_bulk<3><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+        return cudaGetLastError();
+    }
     if (occ == 5) k_fixed_msm<5><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
     else if (occ == 4) k_fixed_msm<4><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
     else k_fixed_msm<3><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);

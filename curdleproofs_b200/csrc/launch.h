@@ -98,12 +98,10 @@ cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uin
 size_t big_heavy_bytes(uint32_t n2, int nwin);
 cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
                                   uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac, void *heavy_ws);
-cudaError_t launch_big_weights(cudaStream_t st, uint32_t *w, uint32_t total, uint32_t nb, int nwin, uint32_t sp_top, uint32_t chunks);
 cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
                                     uint32_t *Bout);
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac);
 cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out);
-cudaError_t launch_big_final(cudaStream_t st, const uint32_t *in, int nwin, int chunks, int c, uint32_t *out_jac);
 
 // fixed-base MSM over a precomputed digit table (k_fixed.cu).  Table layout: affine points, 96 B each,
 //   table[(base * nw + w) * nd + (d - 1)] = d * 2^(c w) * B_base      d = 1 .. nd = 2^(c-1),  w < nw = ceil(256 / c)
