@@ -553,7 +553,7 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
 // ---- large Pippenger (k_bigmsm.cu) ---------------------------------------------------------------------------
 // below this size the chunked small-MSM path (more additions per pair, but no sort and a much shorter launch chain) is faster;
 // CDP_BIG_MIN_LOG2 overrides (tuning)
-static const size_t BIG_MSM_MIN_N = [] { const char *e = getenv("CDP_BIG_MIN_LOG2"); int v = e ? atoi(e) : 16; return size_t(1) << (v >= 11 && v <= 24 ? v : 16); }();
+static const size_t BIG_MSM_MIN_N = [] { const char *e = getenv("CDP_BIG_MIN_LOG2"); int v = e ? atoi(e) : 17; return size_t(1) << (v >= 11 && v <= 24 ? v : 17); }();
 static int big_c_for(size_t n) {
     static int forced = -1;
     if (forced < 0) { const char *e = getenv("CDP_BIG_C"); forced = e ? atoi(e) : 0; }
@@ -851,7 +851,12 @@ extern "C" int cdp_fixed_table_create(cdp_ctx *ctx, const uint8_t *affine_pts, s
         int bit = c * w + c - 1;
         t->kp.recode[bit >> 5] |= 1u << (bit & 31);
     }
-    t->bytes = chains * nd * CDP_AFFINE_BYTES;
+    // entry stride: 128 bytes -- one DRAM line per gathered entry (ncu: 2.1 KB of DRAM traffic per pair for 1.5 KB of entries; packed at
+    // 96 bytes an entry straddles two lines half of the time: 3.1 KB per pair, profiles/r02_fixed_stride.txt).  Same kernel time either
+    // way (the gather is latency-hidden, not bandwidth-bound); CDP_FIXED_STRIDE=96 selects the packed table (3/4 of the memory).
+    static const uint32_t stride_bytes = [] { const char *e = getenv("CDP_FIXED_STRIDE"); return e && atoi(e) == 96 ? 96u : 128u; }();
+    t->kp.es = stride_bytes / 4;
+    t->bytes = chains * nd * (size_t)stride_bytes;
     if (cudaMalloc(&t->d_table, t->bytes) != cudaSuccess) {
         delete t;
         return fail(ctx, CDP_ERR_CUDA, "cdp_fixed_table_create: cudaMalloc of the digit table failed");
@@ -864,10 +869,10 @@ extern "C" int cdp_fixed_table_create(cdp_ctx *ctx, const uint8_t *affine_pts, s
     cudaError_t e = cudaMemcpyAsync(ctx->d_pts.ptr, affine_pts, n_bases * CDP_AFFINE_BYTES, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_fixed_pow(ctx->stream, (const uint32_t *)ctx->d_pts.ptr, (uint32_t)n_bases, c, nw, (uint32_t *)ctx->d_jac.ptr);
     if (e == cudaSuccess) e = launch_normalize(ctx->stream, 1, (const uint32_t *)ctx->d_jac.ptr, (uint32_t *)ctx->d_out.ptr, nullptr, (uint32_t)chains, nullptr, 1);
-    if (e == cudaSuccess) e = launch_fixed_seed(ctx->stream, (const uint32_t *)ctx->d_out.ptr, (uint32_t)chains, nd, t->d_table);
+    if (e == cudaSuccess) e = launch_fixed_seed(ctx->stream, (const uint32_t *)ctx->d_out.ptr, (uint32_t)chains, nd, t->kp.es, t->d_table);
     ctx->launches += 3;
     for (uint32_t half = 1; half < nd && e == cudaSuccess; half <<= 1) {
-        e = launch_fixed_level(ctx->stream, t->d_table, (uint32_t)chains, nd, half);
+        e = launch_fixed_level(ctx->stream, t->d_table, (uint32_t)chains, nd, half, t->kp.es);
         ctx->launches++;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

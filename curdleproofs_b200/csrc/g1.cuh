@@ -145,6 +145,61 @@ __device__ __forceinline__ void g1j_add_mixed(g1j &r, const g1j &p, const g1a &q
     r.Z = Z3;
 }
 
+// The same mixed addition with the field products expanded in place (fp_mul_eo / fp_sqr_rw inlined) instead of called: ~55 KB of
+// straight-line SASS, but none of the ~36 register moves per call that the by-value ABI of fp_mul_fn / fp_sqr_fn costs -- ptxas emits those
+// as IMAD.MOV.U32, i.e. on the same fmaheavy pipe that the 2904 IMAD.WIDE of the addition already keep ~70 % busy
+// (profiles/r02_ncu_fixed_pipes.txt).  For the one hot loop of a kernel only; everything else keeps the compact called form.
+__device__ __forceinline__ void g1j_add_mixed_expanded(g1j &r, const g1j &p, const g1a &q) {
+    if (g1a_is_inf(q)) {
+        r = p;
+        return;
+    }
+    if (g1j_is_inf(p)) {
+        r.X = q.x;
+        r.Y = q.y;
+        fp_set_one(r.Z);
+        return;
+    }
+    fp Z1Z1, U2, S2, H, HH, I, J, rr, V, t;
+    fp_sqr_rw(Z1Z1, p.Z);
+    fp_mul_eo(U2, q.x, Z1Z1);
+    fp_mul_eo(S2, q.y, p.Z);
+    fp_mul_eo(S2, S2, Z1Z1);
+    fp_sub(H, U2, p.X);
+    fp_sub(rr, S2, p.Y);
+    if (fp_is_zero(H)) {
+        if (fp_is_zero(rr)) {
+            g1j_dbl_outlined(&r, &p);
+        } else {
+            g1j_set_inf(r);
+        }
+        return;
+    }
+    fp_dbl(rr, rr);
+    fp_sqr_rw(HH, H);
+    fp_dbl(I, HH);
+    fp_dbl(I, I);
+    fp_mul_eo(J, H, I);
+    fp_mul_eo(V, p.X, I);
+    fp X3, Y3, Z3;
+    fp_sqr_rw(X3, rr);
+    fp_sub(X3, X3, J);
+    fp_sub(X3, X3, V);
+    fp_sub(X3, X3, V);
+    fp_sub(t, V, X3);
+    fp_mul_eo(Y3, rr, t);
+    fp_mul_eo(t, p.Y, J);
+    fp_dbl(t, t);
+    fp_sub(Y3, Y3, t);
+    fp_add(Z3, p.Z, H);
+    fp_sqr_rw(Z3, Z3);
+    fp_sub(Z3, Z3, Z1Z1);
+    fp_sub(Z3, Z3, HH);
+    r.X = X3;
+    r.Y = Y3;
+    r.Z = Z3;
+}
+
 // r = p + q, both Jacobian (11M + 5S); all special cases handled
 __device__ __forceinline__ void g1j_add(g1j &r, const g1j &p, const g1j &q) {
     if (g1j_is_inf(q)) {

@@ -5,7 +5,8 @@
 //   src/inner_product_argument.rs:202-250) -- every L/R cross term over G, G' = u o G and G_with_blinders.
 //
 // B200-first layout: with 180 GB of HBM per GPU the whole digit table fits on the device,
-//   table[(base * nw + w) * nd + (d - 1)] = d * 2^(c w) * B_base   (affine, 96 B; c = 16: 16 windows x 32768 digits = 50 MB per base)
+//   table[(base * nw + w) * nd + (d - 1)] = d * 2^(c w) * B_base   (affine, 96 B; c = 16: 16 windows x 32768 digits = 50 MB per base;
+//   entries 96 bytes apart, or 128 -- one DRAM line per gathered entry -- with CDP_FIXED_STRIDE=128)
 // so one (scalar, base) pair costs nw = 16 mixed additions -- gathered 96-byte reads, no buckets, no doublings, no window
 // combine -- instead of ~52 bucket additions plus the bucket reduction of the variable-base kernel.
 #include "launch.h"
@@ -31,11 +32,11 @@ __global__ void __launch_bounds__(64) k_fixed_pow(const uint32_t *__restrict__ b
 }
 
 // table[chain * nd + 0] = aff[chain]   (digit 1 of every (base, window) chain)
-__global__ void __launch_bounds__(256) k_fixed_seed(const uint32_t *__restrict__ aff, uint32_t chains, uint32_t nd, uint32_t *__restrict__ table) {
+__global__ void __launch_bounds__(256) k_fixed_seed(const uint32_t *__restrict__ aff, uint32_t chains, uint32_t nd, uint32_t es, uint32_t *__restrict__ table) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t ch = t / 6, q = t % 6;
     if (ch >= chains) return;
-    reinterpret_cast<uint4 *>(table + 24 * (size_t)ch * nd)[q] = reinterpret_cast<const uint4 *>(aff + 24 * (size_t)ch)[q];
+    reinterpret_cast<uint4 *>(table + (size_t)es * ch * nd)[q] = reinterpret_cast<const uint4 *>(aff + 24 * (size_t)ch)[q];
 }
 
 // One doubling level of every chain: entries [0, half) hold 1Q .. half*Q; this writes (half + e + 1) Q = (e + 1) Q + half Q for
@@ -43,16 +44,16 @@ __global__ void __launch_bounds__(256) k_fixed_seed(const uint32_t *__restrict__
 // e == half - 1 is the doubling (half Q + half Q).  Bases are prime-order points (or infinity: the whole chain stays all-zero), so no
 // other coincidence of x-coordinates can occur below the group order.
 constexpr int FIXED_CH = 16;
-__global__ void __launch_bounds__(128) k_fixed_level(uint32_t *__restrict__ table, uint32_t chains, uint32_t nd, uint32_t half) {
+__global__ void __launch_bounds__(128) k_fixed_level(uint32_t *__restrict__ table, uint32_t chains, uint32_t nd, uint32_t half, uint32_t es) {
     const uint32_t parts = (half + FIXED_CH - 1) / FIXED_CH;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t ch = t / parts, part = t - ch * parts;
     if (ch >= chains) return;
     const uint32_t e0 = part * FIXED_CH;
     const uint32_t cnt = half - e0 < (uint32_t)FIXED_CH ? half - e0 : (uint32_t)FIXED_CH;
-    uint32_t *T = table + 24 * (size_t)ch * nd;
+    uint32_t *T = table + (size_t)es * ch * nd;  // entries are es words apart (24, or 32: one 128-byte line each)
     g1a Bp;
-    g1a_load(Bp, T + 24 * (size_t)(half - 1));
+    g1a_load(Bp, T + (size_t)es * (half - 1));
     const bool binf = g1a_is_inf(Bp);
     fp prefix[FIXED_CH];
     fp run;
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(128) k_fixed_level(uint32_t *__restrict__ tabl
             fp_dbl(den, Bp.y);
         } else {
             fp ax;
-            fp_load(ax, T + 24 * (size_t)(e0 + i));
+            fp_load(ax, T + (size_t)es * (e0 + i));
             fp_sub(den, Bp.x, ax);
         }
         fp_mul(run, run, den);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(128) k_fixed_level(uint32_t *__restrict__ tabl
 #pragma unroll 1
     for (int i = (int)cnt - 1; i >= 0; i--) {
         g1a A, R;
-        g1a_load(A, T + 24 * (size_t)(e0 + i));
+        g1a_load(A, T + (size_t)es * (e0 + i));
         if (binf) {
             g1a_set_inf(R);
         } else {
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(128) k_fixed_level(uint32_t *__restrict__ tabl
             fp_mul(R.y, lam, R.y);
             fp_sub(R.y, R.y, A.y);
         }
-        g1a_store(T + 24 * (size_t)(half + e0 + i), R);
+        g1a_store(T + (size_t)es * (half + e0 + i), R);
     }
 }
 
@@ -140,7 +141,7 @@ __device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint
 // gathered 96-byte table read and one mixed addition into the lane's Jacobian accumulator; the next item's point is fetched before the
 // current addition is issued, so the HBM gather latency (~1 us) hides behind ~3300 integer instructions.  The 32 partial sums are
 // folded with warp shuffles (5 full additions).
-template <int OCC>
+template <int OCC, bool EXPANDED = false>
 __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
                                                        const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
                                                        const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac) {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
         if (d == 0) return false;
         neg = d < 0;
         const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-        g1a_load(P, table + 24 * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1)));
+        g1a_load(P, table + (size_t)kp.es * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1)));
         return true;
     };
     g1j acc;
@@ -189,7 +190,8 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
             q += 32;
         }
         if (cur_neg) fp_neg(cur.y, cur.y);
-        g1j_add_mixed(acc, acc, cur);
+        if (EXPANDED) g1j_add_mixed_expanded(acc, acc, cur);
+        else g1j_add_mixed(acc, acc, cur);
         cur = nxt;
         cur_neg = nxt_neg;
         have = hn;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm_bulk(const uint32_t *__r
         if (d == 0) return nullptr;
         neg = d < 0;
         const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-        return table + 24 * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1));
+        return table + (size_t)kp.es * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1));
     };
     g1j acc;
     g1j_set_inf(acc);
@@ -327,13 +329,13 @@ cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint
     k_fixed_pow<<<(n_bases + 63) / 64, 64, 0, st>>>(bases_affine, n_bases, c, nw, jac_out);
     return cudaGetLastError();
 }
-cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t *table) {
-    k_fixed_seed<<<(chains * 6 + 255) / 256, 256, 0, st>>>(aff, chains, nd, table);
+cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t es, uint32_t *table) {
+    k_fixed_seed<<<(chains * 6 + 255) / 256, 256, 0, st>>>(aff, chains, nd, es, table);
     return cudaGetLastError();
 }
-cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half) {
+cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half, uint32_t es) {
     const uint64_t parts = (half + FIXED_CH - 1) / FIXED_CH, threads = parts * chains;
-    k_fixed_level<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(table, chains, nd, half);
+    k_fixed_level<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(table, chains, nd, half, es);
     return cudaGetLastError();
 }
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
@@ -346,6 +348,12 @@ cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint3
         if (occ == 5) k_fixed_msm_bulk<5><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
         else if (occ == 4) k_fixed_msm_bulk<4><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
         else k_fixed_msm_bulk<3><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+        return cudaGetLastError();
+    }
+    static const int expanded = [] { const char *e = getenv("CDP_FIXED_EXPANDED"); return e ? atoi(e) : 0; }();
+    if (expanded) {  // the hot loop's mixed addition with its field products expanded in place (g1j_add_mixed_expanded)
+        if (occ == 4) k_fixed_msm<4, true><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+        else k_fixed_msm<3, true><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
         return cudaGetLastError();
     }
     if (occ == 5) k_fixed_msm<5><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);

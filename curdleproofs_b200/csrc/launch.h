@@ -122,11 +122,12 @@ struct fixed_seg_t {
 struct fixed_kparams_t {
     int c, nw;
     uint32_t nd;
+    uint32_t es;         // distance between table entries in 32-bit words: 24 (packed) or 32 (one 128-byte line per entry)
     uint32_t recode[8];  // sum over w < nw-1 of 2^(c w + c - 1): added to the scalar, turns unsigned windows into signed digits
 };
 cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint32_t n_bases, int c, int nw, uint32_t *jac_out);
-cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t *table);
-cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half);
+cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t chains, uint32_t nd, uint32_t es, uint32_t *table);
+cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half, uint32_t es);
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
                              const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac);
 

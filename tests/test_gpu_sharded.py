@@ -56,47 +56,17 @@ def _free_port():
     return p
 
 
-def _rank_worker(rank, world, port, sizes, q):
-    import torch
-    import torch.distributed as dist
-    from curdleproofs_b200 import Engine
-    from curdleproofs_b200.sharded import Comm, shard_range
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("gloo", rank=rank, world_size=world)  # only carries the 128-byte communicator id
-    eng = Engine(rank)
-    comm = Comm.from_torch_distributed(eng, rank, world)
-    res = []
-    for n in sizes:
-        o, pts, sc = _inputs(n)
-        lo, hi = shard_range(n, rank, world)
-        got = comm.msm_sharded(pts[96 * lo:96 * hi], sc[32 * lo:32 * hi])
-        res.append(o.compress_jac(got) == o.compress_jac(o.msm(pts, sc)))
-    q.put((rank, res))
-    dist.barrier()
-    comm.close()
-    eng.close()
-    dist.destroy_process_group()
-
-
 def test_sharded_msm_two_ranks_one_process_per_gpu():
+    """One process per GPU under torch.distributed.run (tests/mp/sharded_msm_ranks.py): n = 1 (an empty shard), uneven splits, and a size
+    that takes the sort-based large path on every shard."""
     if _gpu_count() < 2:
         pytest.skip("needs a 2-GPU lease (this box has %d GPU): run under `gpurun --gpus 2`" % _gpu_count())
-    import torch.multiprocessing as mp
-    world, sizes = 2, [1, 37, 9001, 40000]  # n = 1: rank 1 holds an empty shard
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_rank_worker, args=(r, world, port, sizes, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
-    for rank, ok in res:
-        assert all(ok), (rank, ok)
+    import subprocess
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(_free_port()), os.path.join(HERE, "mp", "sharded_msm_ranks.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "RANK 0 OK" in out.stdout and "RANK 1 OK" in out.stdout and "MISMATCH" not in out.stdout
 
 
 def test_sharded_msm_group_one_process_two_gpus():
