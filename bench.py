@@ -317,7 +317,9 @@ def main():
 
     cat = lambda key: b"".join(i[key] for i in insts)  # noqa: E731
     arr = lambda b: (ctypes.c_uint8 * len(b)).from_buffer_copy(b)  # noqa: E731
-    R, S, T, U, M, K, MB = (arr(cat(k)) for k in ("R", "S", "T", "U", "M", "k", "m_blinders"))
+    # the step's inputs live in page-locked host memory (cdp_host_alloc): the e2e copies are DMAs from the caller's own buffers
+    R, S, T, U = (eng.pinned_array(cat(k)) for k in ("R", "S", "T", "U"))
+    M, K, MB = (arr(cat(k)) for k in ("M", "k", "m_blinders"))
     perm = (ctypes.c_uint32 * (B * ell))(*[x for i in insts for x in i["perm"]])
     seeds = (ctypes.c_uint64 * B)(*range(1000 * rank, 1000 * rank + B))
     out = (ctypes.c_uint8 * (B * bp.proof_size))()

@@ -312,6 +312,19 @@ extern "C" int cdp_h2d(cdp_ctx *ctx, void *d_dst, const void *h_src, size_t byte
     CUDA_TRY(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return CDP_OK;
 }
+extern "C" int cdp_host_is_pinned(const void *h_ptr) {
+    if (!h_ptr) return 0;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h_ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+extern "C" int cdp_h2d_2d(cdp_ctx *ctx, void *d_dst, size_t dpitch, const void *h_src, size_t spitch, size_t width, size_t height) {
+    if (!ctx || !d_dst || !h_src) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_h2d_2d: null argument");
+    if (width == 0 || height == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_dst, dpitch, h_src, spitch, width, height, cudaMemcpyHostToDevice, ctx->stream));
+    return CDP_OK;
+}
 extern "C" int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!ctx) return CDP_ERR_INVALID_ARG;
     if (bytes == 0) return CDP_OK;
@@ -1084,6 +1097,7 @@ extern "C" void cdp_comm_destroy(cdp_comm *c) {
 }
 extern "C" int cdp_comm_rank(const cdp_comm *c) { return c ? c->rank : -1; }
 extern "C" int cdp_comm_size(const cdp_comm *c) { return c ? c->n_ranks : 0; }
+extern "C" cdp_ctx *cdp_comm_ctx(const cdp_comm *c) { return c ? c->ctx : nullptr; }
 extern "C" const char *cdp_comm_last_error(const cdp_comm *c) { return c ? c->err.c_str() : "null communicator"; }
 extern "C" void cdp_shard_range(size_t n, int rank, int n_ranks, size_t *lo, size_t *hi) {
     const size_t w = (size_t)(n_ranks > 0 ? n_ranks : 1), r = (size_t)(rank > 0 ? rank : 0), base = n / w, rem = n % w;

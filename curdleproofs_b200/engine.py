@@ -71,6 +71,8 @@ _SIGS = {
     "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
+    "cdp_host_is_pinned": (c_int, [c_void_p]),
+    "cdp_h2d_2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t]),
     "cdp_comm_unique_id": (c_int, [c_void_p]),
     "cdp_comm_create": (c_int, [POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int]),
     "cdp_comm_create_all": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int]),
@@ -123,6 +125,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.cdp_host_free(self._h, p)
+            self._pinned = []
             self._lib.cdp_ctx_destroy(self._h)
             self._h = None
 
@@ -147,6 +152,19 @@ class Engine:
     @property
     def launch_count(self) -> int:
         return int(self._lib.cdp_launch_count(self._h))
+
+    def pinned_array(self, data: bytes):
+        """A page-locked host buffer (cdp_host_alloc) holding `data`, as a ctypes array: inputs handed to the batched prover / verifier from
+        such buffers go to the device by direct DMA, without a staging pass.  Freed with the Engine (keep the Engine alive while in use)."""
+        n = max(1, len(data))
+        p = self._lib.cdp_host_alloc(self._h, n)
+        if not p:
+            raise CdpError("cdp_host_alloc failed")
+        arr = (ctypes.c_uint8 * n).from_address(p)
+        ctypes.memmove(arr, data, len(data))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return arr
 
     def sync(self):
         self._check(self._lib.cdp_sync(self._h), "cdp_sync")

@@ -735,15 +735,19 @@ static int lane_prove(Lane *p, size_t B, const cdp_prove_inputs *in, uint8_t *pr
     // ---- stage 0: instance to the device, working vectors assembled, transcript openings compressed
     t0 = now_ms();
     if (!resident) {
-        parallel_for(T, B, [&](size_t pr) {
-            uint8_t *dst = p->h_in + pr * 4 * ell * 96;
-            memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
-            memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
-            memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
-            memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
-        });
+        const uint8_t *vecs[4] = {in->vec_R, in->vec_S, in->vec_T, in->vec_U};
+        bool pinned = true;
+        for (const uint8_t *v : vecs) pinned = pinned && cdp_host_is_pinned(v);
         memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
-        PTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+        if (pinned) {  // page-locked caller buffers: four strided DMAs straight into the proof-major layout, no staging pass
+            for (int v = 0; v < 4; v++) PTRY(cdp_h2d_2d(p->ctx, p->d_in + v * ell * 96, 4 * ell * 96, vecs[v], ell * 96, ell * 96, B));
+        } else {
+            parallel_for(T, B, [&](size_t pr) {
+                uint8_t *dst = p->h_in + pr * 4 * ell * 96;
+                for (int v = 0; v < 4; v++) memcpy(dst + v * ell * 96, vecs[v] + pr * ell * 96, ell * 96);
+            });
+            PTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+        }
         PTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
         p->h2d_bytes += B * (4 * ell * 96 + 144);
         PTRY(cdp_normalize_dev(p->ctx, p->d_Mjac, B, p->d_in + Moff * 96, nullptr));  // M.into_affine()

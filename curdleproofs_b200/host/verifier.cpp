@@ -127,6 +127,12 @@ struct VLane {
             *d_mres = nullptr, *h_mres = nullptr;
     bool dev_transcript = true;  // CDP_VERIFY_HOST_TRANSCRIPT=1: the per-round transcript and the challenges on the host (the older path)
     bool merged = true;   // CDP_VERIFY_MERGE=0: always one accumulated MSM per proof
+    // cdp_verify_batch_sharded: the lane stops before deciding (`defer`), leaves its merged sum (Jacobian, h_msum) and what it knows about the
+    // sub-batch, and is finished by vlane_verify_finish once the cross-lane / cross-rank sum is known
+    bool defer = false, st_try = false, st_clean = false, st_pending = false;
+    size_t st_B = 0;
+    double st_t_start = 0, st_t_host = 0, st_t_wait = 0;
+    uint8_t *h_msum = nullptr;
     size_t n_merged = 0, n_fallback = 0;  // lane batches accepted by the merged check / re-checked proof by proof
     uint32_t *d_gsrc = nullptr, *d_gdst = nullptr, *d_isrc = nullptr, *d_idst = nullptr, *d_pdst = nullptr, *d_xsrc = nullptr, *d_xdst = nullptr;
     size_t g_pp = 0, i_pp = 0, x_pp = 0;
@@ -156,7 +162,7 @@ void vlane_destroy(VLane *p) {
                     (void *)p->d_da, (void *)p->d_vflag, (void *)p->d_Hcomp, (void *)p->d_mres, (void *)p->d_jac,
                     (void *)p->d_comp})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_chal, (void *)p->h_pscal, (void *)p->h_vflag, (void *)p->h_mres}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_pcomp, (void *)p->h_status, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_chal, (void *)p->h_pscal, (void *)p->h_vflag, (void *)p->h_mres, (void *)p->h_msum}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -209,6 +215,7 @@ int vlane_create(VLane **out, cdp_ctx *ctx, const cdp_fixed_table *table, size_t
     p->d_vflag = (uint8_t *)dalloc(max_batch); p->h_vflag = (uint8_t *)halloc(max_batch);
     p->d_Hcomp = (uint8_t *)dalloc(48);
     p->d_mres = (uint8_t *)dalloc(48); p->h_mres = (uint8_t *)halloc(48);
+    p->h_msum = (uint8_t *)halloc(144);
     p->h_scal = (uint8_t *)halloc(max_batch * 6 * 32);  // stage A only: the coefficients of the accumulated check are computed on the device
     size_t out_pp = std::max<size_t>(p->chunks + 5, 4 * ell + 1);
     p->d_jac = (uint8_t *)dalloc((max_batch * (p->chunks + FSPLIT + 5) + 2 * FSPLIT + 4) * 144);
@@ -339,8 +346,11 @@ int merged_stage(VLane *p, size_t B) {
     VTRY(cdp_sum_jacobian_dev(p->ctx, d_m, FSPLIT + 1, d_m + (FSPLIT + 1) * 144));
     VTRY(cdp_normalize_dev(p->ctx, d_m + (FSPLIT + 1) * 144, 1, nullptr, p->d_mres));
     VTRY(cdp_d2h(p->ctx, p->h_mres, p->d_mres, 48));
+    if (p->defer) VTRY(cdp_d2h(p->ctx, p->h_msum, d_m + (FSPLIT + 1) * 144, 144));  // the sum itself, for the cross-lane / cross-rank check
     return CDP_OK;
 }
+
+int vlane_verify_finish(VLane *p, uint8_t *ok_out, bool global_accept);
 
 // `deserialize` + `verify` with the whole transcript and all scalar algebra on the device: the host parses and stages the inputs and
 // draws the random factors; ONE synchronisation at the end (a second one only when the merged check does not accept the sub-batch).
@@ -351,12 +361,13 @@ int vlane_verify_dev(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *o
     const int T = p->threads;
     const size_t psz = cdp_proof_size(ell), Moff = p->max_batch * 4 * ell;
     memcpy(p->h_in + B * 4 * ell * 96, in->M, B * 144);
+    const uint8_t *vecs[4] = {in->vec_R, in->vec_S, in->vec_T, in->vec_U};
+    bool pinned = true;  // page-locked caller buffers go to the device by strided DMA, without the staging pass
+    for (const uint8_t *v : vecs) pinned = pinned && cdp_host_is_pinned(v);
     parallel_for(T, B, [&](size_t pr) {
         uint8_t *dst = p->h_in + pr * 4 * ell * 96;
-        memcpy(dst, in->vec_R + pr * ell * 96, ell * 96);
-        memcpy(dst + ell * 96, in->vec_S + pr * ell * 96, ell * 96);
-        memcpy(dst + 2 * ell * 96, in->vec_T + pr * ell * 96, ell * 96);
-        memcpy(dst + 3 * ell * 96, in->vec_U + pr * ell * 96, ell * 96);
+        if (!pinned)
+            for (int v = 0; v < 4; v++) memcpy(dst + v * ell * 96, vecs[v] + pr * ell * 96, ell * 96);
         VState &s = p->vs[pr];
         s.status = 1;
         // proof parsing (curdleproofs.rs:311-323 and the per-argument deserialisers): points -> h_pcomp in serialisation order, the seven
@@ -374,7 +385,11 @@ int vlane_verify_dev(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *o
     });
     t_host += now_ms() - t0;
     if (getenv("CDP_VERIFY_TRACE")) fprintf(stderr, "verify lane host staging: %.2f ms (B=%zu)\n", now_ms() - t0, B);
-    VTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+    if (pinned) {
+        for (int v = 0; v < 4; v++) VTRY(cdp_h2d_2d(p->ctx, p->d_in + v * ell * 96, 4 * ell * 96, vecs[v], ell * 96, ell * 96, B));
+    } else {
+        VTRY(cdp_h2d(p->ctx, p->d_in, p->h_in, B * 4 * ell * 96));
+    }
     VTRY(cdp_h2d(p->ctx, p->d_Mjac, p->h_in + B * 4 * ell * 96, B * 144));
     VTRY(cdp_h2d(p->ctx, p->d_pcomp, p->h_pcomp, B * NP * 48));
     VTRY(cdp_h2d(p->ctx, p->d_pscal, p->h_pscal, B * 7 * 32));
@@ -415,7 +430,23 @@ int vlane_verify_dev(VLane *p, size_t B, const cdp_verify_inputs *in, uint8_t *o
         if (p->h_vflag[pr] && s.status == 1) s.status = 0;       // vec_T[0] is the identity -> Err (curdleproofs.rs:218-220)
         clean = clean && s.status == 1;
     }
-    bool decided = try_merged && clean && enc_is_inf(p->h_mres);
+    p->st_try = try_merged; p->st_clean = clean; p->st_B = B;
+    p->st_t_start = t_start; p->st_t_host = t_host; p->st_t_wait = t_wait;
+    if (p->defer) {  // cdp_verify_batch_sharded decides with the sums of all lanes and ranks, then calls vlane_verify_finish
+        p->st_pending = true;
+        return CDP_OK;
+    }
+    return vlane_verify_finish(p, ok_out, false);
+}
+
+// second half of vlane_verify_dev: `global_accept` = the sum of the merged checks of ALL clean sub-batches (all lanes, all ranks) is the identity
+int vlane_verify_finish(VLane *p, uint8_t *ok_out, bool global_accept) {
+    const size_t B = p->st_B;
+    const bool try_merged = p->st_try, clean = p->st_clean;
+    const double t_start = p->st_t_start, t_host = p->st_t_host;
+    double t_wait = p->st_t_wait;
+    p->st_pending = false;
+    bool decided = try_merged && clean && (global_accept || enc_is_inf(p->h_mres));
     if (try_merged && clean) { if (decided) p->n_merged++; else p->n_fallback++; }  // a sub-batch with a malformed proof never counted on the merged result
     if (!decided) {
         VTRY(per_proof_stage(p, B, t_wait));
@@ -642,10 +673,13 @@ struct cdp_verifier {
     std::vector<cdp_ctx *> owned;
     size_t ell = 0, max_batch = 0;
     std::string err = "ok";
+    uint8_t *d_gsum = nullptr;                    // cdp_verify_batch_sharded: lane sums, the rank's partial sum, the total, its encoding
+    uint64_t n_global = 0, n_global_reject = 0;   // sharded calls decided by the cross-rank sum / that fell back to the local checks
 };
 
 extern "C" void cdp_verifier_destroy(cdp_verifier *v) {
     if (!v) return;
+    if (v->d_gsum) cdp_dev_free(v->ctx0, v->d_gsum);
     for (VLane *l : v->lanes) vlane_destroy(l);
     crs_table_release(v->shared);
     for (cdp_ctx *c : v->owned) cdp_ctx_destroy(c);
@@ -696,7 +730,7 @@ extern "C" int cdp_verifier_create(cdp_verifier **out, cdp_ctx *ctx, size_t ell,
     *out = v;
     return CDP_OK;
 }
-extern "C" int cdp_verify_batch(cdp_verifier *v, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
+static int verify_batch_impl(cdp_verifier *v, cdp_comm *comm, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
     if (!v) return CDP_ERR_INVALID_ARG;
     if (!in || !ok_out || B == 0 || B > v->max_batch || !in->vec_R || !in->proofs) { v->err = "cdp_verify_batch: bad argument"; return CDP_ERR_INVALID_ARG; }
     const size_t Ln = v->lanes.size(), ell = v->ell, psz = cdp_proof_size(ell);
@@ -730,7 +764,10 @@ extern "C" int cdp_verify_batch(cdp_verifier *v, size_t B, const cdp_verify_inpu
         sub.M = in->M + o * 144;
         sub.proofs = in->proofs + o * psz;
         sub.rng_seed = in->rng_seed ? in->rng_seed + o : nullptr;
+        v->lanes[i]->defer = comm != nullptr && v->lanes[i]->dev_transcript;
+        v->lanes[i]->st_pending = false;
         rcs[i] = vlane_verify(v->lanes[i], cnt, &sub, ok_out + o);
+        v->lanes[i]->defer = false;
     };
     if (Ln == 1) run(0);
     else {
@@ -738,9 +775,58 @@ extern "C" int cdp_verify_batch(cdp_verifier *v, size_t B, const cdp_verify_inpu
         for (size_t i = 0; i < Ln; i++) th.emplace_back(run, i);
         for (auto &t : th) t.join();
     }
+    int first_rc = CDP_OK;
+    for (size_t i = 0; i < Ln; i++)
+        if (rcs[i] != CDP_OK && first_rc == CDP_OK) { v->err = "lane " + std::to_string(i) + ": " + v->lanes[i]->err; first_rc = rcs[i]; }
+    if (!comm) return first_rc;
+    // ---- the sharded accumulated check: every clean sub-batch of every lane of every rank contributes its merged sum -- a random linear
+    // combination of all its checks (msm_accumulator.rs:37-68) -- and ONE all-gather + add of the per-rank partial sums decides them all:
+    // identity => every proof of every clean sub-batch on every rank is accepted.  Every rank takes part exactly once per call, whatever
+    // its local state (a rank with nothing to contribute sends the point at infinity).
+    cdp_ctx *ctx = v->ctx0;
+    std::vector<uint8_t> sums;
+    for (size_t i = 0; i < Ln; i++) {
+        VLane *l = v->lanes[i];
+        if (first_rc == CDP_OK && l->st_pending && l->st_try && l->st_clean) sums.insert(sums.end(), l->h_msum, l->h_msum + 144);
+    }
+    const size_t k = sums.size() / 144;
+    if (!v->d_gsum) v->d_gsum = (uint8_t *)cdp_dev_alloc(ctx, (Ln + 2) * 144 + 48);
+    if (!v->d_gsum) { v->err = "cdp_verify_batch_sharded: allocation failed"; return CDP_ERR_CUDA; }
+    uint8_t *d_part = v->d_gsum + Ln * 144, *d_tot = d_part + 144, *d_enc = d_tot + 144;
+    int rc = CDP_OK;
+    if (k) { rc = cdp_h2d(ctx, v->d_gsum, sums.data(), k * 144); if (rc == CDP_OK) rc = cdp_sum_jacobian_dev(ctx, v->d_gsum, k, d_part); }
+    else rc = cdp_dev_zero(ctx, d_part, 144);
+    if (rc == CDP_OK) rc = cdp_allreduce_jacobian_dev(comm, d_part, d_tot);
+    uint8_t enc[48];
+    if (rc == CDP_OK) rc = cdp_normalize_dev(ctx, d_tot, 1, nullptr, d_enc);
+    if (rc == CDP_OK) rc = cdp_d2h(ctx, enc, d_enc, 48);
+    if (rc == CDP_OK) rc = cdp_sync(ctx);
+    if (rc != CDP_OK) { v->err = std::string("cdp_verify_batch_sharded: ") + cdp_last_error(ctx); return rc; }
+    if (first_rc != CDP_OK) return first_rc;
+    const bool global_accept = enc_is_inf(enc);
+    if (global_accept) v->n_global++; else v->n_global_reject++;
+    auto fin = [&](size_t i) {
+        if (v->lanes[i]->st_pending) rcs[i] = vlane_verify_finish(v->lanes[i], ok_out + off[i], global_accept);
+    };
+    if (Ln == 1) fin(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < Ln; i++) th.emplace_back(fin, i);
+        for (auto &t : th) t.join();
+    }
     for (size_t i = 0; i < Ln; i++)
         if (rcs[i] != CDP_OK) { v->err = "lane " + std::to_string(i) + ": " + v->lanes[i]->err; return rcs[i]; }
     return CDP_OK;
+}
+extern "C" int cdp_verify_batch(cdp_verifier *v, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) { return verify_batch_impl(v, nullptr, B, in, ok_out); }
+extern "C" int cdp_verify_batch_sharded(cdp_verifier *v, cdp_comm *comm, size_t B, const cdp_verify_inputs *in, uint8_t *ok_out) {
+    if (!v) return CDP_ERR_INVALID_ARG;
+    if (!comm || cdp_comm_ctx(comm) != v->ctx0) { v->err = "cdp_verify_batch_sharded: the communicator must be bound to the verifier's context"; return CDP_ERR_INVALID_ARG; }
+    return verify_batch_impl(v, comm, B, in, ok_out);
+}
+extern "C" void cdp_verifier_global_stats(const cdp_verifier *v, uint64_t out[2]) {
+    out[0] = v ? v->n_global : 0;
+    out[1] = v ? v->n_global_reject : 0;
 }
 
 // is_valid_whisk_shuffle_proof (/root/reference/src/whisk.rs:106-130) for a batch: trackers and M decompressed on the GPU, then cdp_verify_batch

@@ -269,13 +269,13 @@ class BatchVerifier:
         self._lib.cdp_verifier_last_timing(self._h, t)
         return {"total_ms": t[0], "host_ms": t[1], "gpu_wait_ms": t[2]}
 
-    def verify_batch(self, instances, proofs, rng_seeds=None) -> list[int]:
+    def verify_batch(self, instances, proofs, rng_seeds=None, comm=None) -> list[int]:
         B = len(instances)
         cat = lambda key: b"".join(i[key] for i in instances)  # noqa: E731
         R, S, T, U, M = (_arr(cat(k)) for k in ("R", "S", "T", "U", "M"))
         P = _arr(b"".join(proofs))
         seeds = (c_uint64 * B)(*rng_seeds) if rng_seeds is not None else None
-        return list(self.verify_raw(B, R, S, T, U, M, P, seeds))
+        return list(self.verify_raw(B, R, S, T, U, M, P, seeds, comm=comm))
 
     def whisk_verify_shuffle_proofs(self, pre_trackers: list, post_trackers: list, proofs: list, rng_seeds=None) -> list:
         """`is_valid_whisk_shuffle_proof` (/root/reference/src/whisk.rs:106-130) for a batch: 1 valid, 0 invalid, 2 does not deserialise."""
@@ -288,11 +288,28 @@ class BatchVerifier:
             raise CdpError(f"cdp_whisk_verify_shuffle_proofs failed (code {rc}): {self._lib.cdp_verifier_last_error(self._h).decode()}")
         return list(out)
 
-    def verify_raw(self, B, R, S, T, U, M, proofs, seeds=None, out=None):
+    def global_stats(self) -> dict:
+        """Sharded calls accepted by the cross-rank accumulated sum / decided locally instead, since creation."""
+        out = (c_uint64 * 2)()
+        self._lib.cdp_verifier_global_stats.argtypes = [c_void_p, POINTER(c_uint64)]
+        self._lib.cdp_verifier_global_stats.restype = None
+        self._lib.cdp_verifier_global_stats(self._h, out)
+        return {"accepted": int(out[0]), "local": int(out[1])}
+
+    def verify_raw(self, B, R, S, T, U, M, proofs, seeds=None, out=None, comm=None):
+        """comm (curdleproofs_b200.sharded.Comm on this verifier's Engine): the accumulated check sharded over the ranks
+        (cdp_verify_batch_sharded): one all-gather of partial sums decides the proofs of all ranks; a collective call."""
         vp = lambda x: ctypes.cast(x, c_void_p) if x is not None else None  # noqa: E731
         inp = _VerifyInputs(vp(R), vp(S), vp(T), vp(U), vp(M), vp(proofs), vp(seeds))
         if out is None:
             out = (ctypes.c_uint8 * B)()
+        if comm is not None:
+            self._lib.cdp_verify_batch_sharded.restype = c_int
+            self._lib.cdp_verify_batch_sharded.argtypes = [c_void_p, c_void_p, c_size_t, POINTER(_VerifyInputs), c_void_p]
+            rc = self._lib.cdp_verify_batch_sharded(self._h, comm._h, B, ctypes.byref(inp), out)
+            if rc != 0:
+                raise CdpError(f"cdp_verify_batch_sharded failed (code {rc}): {self._lib.cdp_verifier_last_error(self._h).decode()}")
+            return out
         rc = self._lib.cdp_verify_batch(self._h, B, ctypes.byref(inp), out)
         if rc != 0:
             raise CdpError(f"cdp_verify_batch failed (code {rc}): {self._lib.cdp_verifier_last_error(self._h).decode()}")

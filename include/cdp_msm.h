@@ -109,6 +109,11 @@ void cdp_dev_free(cdp_ctx *ctx, void *d_ptr);
 int cdp_h2d(cdp_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int cdp_d2h(cdp_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 int cdp_dev_zero(cdp_ctx *ctx, void *d_ptr, size_t bytes); /* asynchronous memset(0) on the context's stream */
+/* Strided copy (cudaMemcpy2DAsync): `height` rows of `width` bytes, rows spitch / dpitch bytes apart.  With a page-locked source it is a
+ * direct DMA from the caller's buffer: the batched prover / verifier use it to lay the caller's vec_R | vec_S | vec_T | vec_U out proof-major
+ * in HBM without a staging pass when cdp_host_is_pinned says the buffers are page-locked (cdp_host_alloc, cudaHostRegister, ...). */
+int cdp_h2d_2d(cdp_ctx *ctx, void *d_dst, size_t dpitch, const void *h_src, size_t spitch, size_t width, size_t height);
+int cdp_host_is_pinned(const void *h_ptr);
 /* Pinned host memory for the asynchronous copies above. */
 void *cdp_host_alloc(cdp_ctx *ctx, size_t bytes);
 void cdp_host_free(cdp_ctx *ctx, void *h_ptr);
@@ -327,6 +332,7 @@ int cdp_comm_create_all(cdp_comm **out /* n */, cdp_ctx *const *ctxs, int n);
 void cdp_comm_destroy(cdp_comm *comm);
 int cdp_comm_rank(const cdp_comm *comm);
 int cdp_comm_size(const cdp_comm *comm);
+cdp_ctx *cdp_comm_ctx(const cdp_comm *comm); /* the context the communicator is bound to */
 const char *cdp_comm_last_error(const cdp_comm *comm);
 /* The contiguous base range [lo, hi) of `rank` for an MSM of n pairs, as even as possible (the partition every caller should use). */
 void cdp_shard_range(size_t n, int rank, int n_ranks, size_t *lo, size_t *hi);

@@ -110,6 +110,15 @@ typedef struct {
 } cdp_verify_inputs;
 /* result[i]: 1 = Ok(()), 0 = Err(VerificationError), 2 = the proof does not deserialise (bad encoding / not in the subgroup) */
 int cdp_verify_batch(cdp_verifier *v, size_t batch, const cdp_verify_inputs *in, uint8_t *result);
+/* The accumulated check of a batch that is spread over the GPUs of a node (`MsmAccumulator::verify`,
+ * /root/reference/src/msm_accumulator.rs:55-68): every rank verifies ITS proofs (its share of the bases of the one large accumulated MSM),
+ * the merged sums of all sub-batches of all ranks are added with ONE all-gather of the 144-byte partial sums (cdp_allreduce_jacobian_dev),
+ * and the identity accepts every proof of every rank at once; otherwise -- or for sub-batches holding a malformed proof -- each rank
+ * decides its own proofs exactly as cdp_verify_batch does, so the verdicts never depend on the mode.  Collective: every rank of `comm`
+ * must call it the same number of times.  `comm` must have been created on the verifier's context. */
+int cdp_verify_batch_sharded(cdp_verifier *v, cdp_comm *comm, size_t batch, const cdp_verify_inputs *in, uint8_t *result);
+/* Since creation: [0] sharded calls accepted by the cross-rank sum, [1] sharded calls that fell back to local decisions. */
+void cdp_verifier_global_stats(const cdp_verifier *v, uint64_t out[2]);
 
 /* ------------------------------------------------------------------ Whisk byte-level API
  * `generate_whisk_shuffle_proof` / `is_valid_whisk_shuffle_proof` (/root/reference/src/whisk.rs:106-179) for a batch of shuffles.

@@ -72,6 +72,11 @@ void cdp_host_free(cdp_ctx *, void *p) { free(p); }
 int cdp_h2d(cdp_ctx *, void *d, const void *h, size_t n) { memcpy(d, h, n); return CDP_OK; }
 int cdp_d2h(cdp_ctx *, void *h, const void *d, size_t n) { memcpy(h, d, n); return CDP_OK; }
 int cdp_dev_zero(cdp_ctx *, void *d, size_t n) { memset(d, 0, n); return CDP_OK; }
+int cdp_host_is_pinned(const void *) { return 0; }
+int cdp_h2d_2d(cdp_ctx *, void *d, size_t dp, const void *h, size_t sp, size_t w, size_t rows) {
+    for (size_t r = 0; r < rows; r++) memcpy((uint8_t *)d + r * dp, (const uint8_t *)h + r * sp, w);
+    return CDP_OK;
+}
 
 int cdp_msm(cdp_ctx *, const uint8_t *pts, const uint8_t *sc, size_t n, uint8_t out[144]) { return oracle_msm(pts, sc, n, out, 1); }
 int cdp_normalize_batch(cdp_ctx *, const uint8_t *jac, size_t n, uint8_t *out) { return oracle_normalize_batch(jac, n, out); }

@@ -31,6 +31,27 @@ def main():
         good = o.compress_jac(got) == o.compress_jac(o.msm(pts, sc, threads=4))
         print(f"rank {rank} n={n} shard=[{lo},{hi}) {'ok' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
+    # the accumulated check of a batch spread over the ranks (cdp_verify_batch_sharded): all valid -> the cross-rank sum accepts everything;
+    # one invalid proof on the last rank -> every rank decides locally, with the oracle's verdicts
+    from curdleproofs_b200 import BatchVerifier
+    from test_gpu_sharded import _proved_batch
+    import oracle_lib
+    o = oracle_lib.Oracle()
+    ell, batch = 12, 4
+    crs, insts, proofs = _proved_batch(o, eng, ell, batch, 500 + 10 * rank)
+    bv = BatchVerifier(eng, ell, crs, max_batch=batch, lanes=2)
+    r1 = bv.verify_batch(insts, proofs, comm=comm)
+    s1 = bv.global_stats()
+    bad = list(proofs)
+    if rank == world - 1:
+        bad[1] = bad[1][:-1] + bytes([bad[1][-1] ^ 1])
+    r2 = bv.verify_batch(insts, bad, comm=comm)
+    s2 = bv.global_stats()
+    want2 = [1, 0, 1, 1] if rank == world - 1 else [1] * batch
+    good = r1 == [1] * batch and s1 == {"accepted": 1, "local": 0} and r2 == want2 and s2 == {"accepted": 1, "local": 1}
+    print(f"rank {rank} sharded verify: {r1} {s1} {r2} {s2} {'ok' if good else 'MISMATCH'}", flush=True)
+    ok = ok and good
+    bv.close()
     dist.barrier()
     comm.close()
     eng.close()

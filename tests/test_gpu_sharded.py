@@ -48,6 +48,71 @@ def test_sharded_msm_world1(n):
     eng.close()
 
 
+def _proved_batch(oracle, eng, ell, batch, seed0):
+    from curdleproofs_b200 import BatchProver
+    crs = oracle.crs_points(ell)
+    insts = [oracle.random_instance(ell, crs, seed=seed0 + i) for i in range(batch)]
+    bp = BatchProver(eng, ell, crs, max_batch=batch, lanes=2)
+    proofs = bp.prove_batch(insts, [seed0 + 50 + i for i in range(batch)])
+    bp.close()
+    return crs, insts, proofs
+
+
+def test_sharded_accumulated_verify_world1():
+    """cdp_verify_batch_sharded with a one-rank communicator: the merged sums of the lanes are added, all-gathered (one rank) and decide the
+    whole batch; a batch with one invalid proof is rejected by the global sum and decided locally, with the same verdicts as cdp_verify_batch."""
+    import oracle_lib
+    from curdleproofs_b200 import BatchVerifier, Engine
+    from curdleproofs_b200.sharded import Comm
+    o = oracle_lib.Oracle()
+    eng = Engine(0)
+    comm = Comm(eng, Comm.unique_id(eng), 1, 0)
+    ell, batch = 12, 6
+    crs, insts, proofs = _proved_batch(o, eng, ell, batch, 300)
+    bv = BatchVerifier(eng, ell, crs, max_batch=batch, lanes=2)
+    assert bv.verify_batch(insts, proofs, comm=comm) == [1] * batch
+    assert bv.global_stats() == {"accepted": 1, "local": 0}
+    bad = list(proofs)
+    bad[4] = bad[4][:-1] + bytes([bad[4][-1] ^ 1])  # x_final
+    want = [o.verify(i, p) for i, p in zip(insts, bad)]
+    assert want == [1, 1, 1, 1, 0, 1]
+    assert bv.verify_batch(insts, bad, comm=comm) == want
+    assert bv.verify_batch(insts, bad) == want
+    assert bv.global_stats() == {"accepted": 1, "local": 1}
+    bv.close()
+    comm.close()
+    eng.close()
+
+
+def test_prover_reads_pinned_inputs_directly():
+    """Page-locked caller buffers (Engine.pinned_array) take the strided-DMA path of cdp_prove_batch / cdp_verify_batch: same proofs, same verdicts."""
+    import ctypes
+
+    import oracle_lib
+    from curdleproofs_b200 import BatchProver, BatchVerifier, Engine
+    o = oracle_lib.Oracle()
+    eng = Engine(0)
+    ell, batch = 12, 5
+    crs = o.crs_points(ell)
+    insts = [o.random_instance(ell, crs, seed=800 + i) for i in range(batch)]
+    seeds = [40 + i for i in range(batch)]
+    bp = BatchProver(eng, ell, crs, max_batch=batch, lanes=2)
+    want = bp.prove_batch(insts, seeds)
+    cat = lambda k: b"".join(i[k] for i in insts)  # noqa: E731
+    arr = lambda b: (ctypes.c_uint8 * len(b)).from_buffer_copy(b)  # noqa: E731
+    R, S, T, U = (eng.pinned_array(cat(k)) for k in ("R", "S", "T", "U"))
+    assert eng.lib.cdp_host_is_pinned(R) == 1 and eng.lib.cdp_host_is_pinned(arr(b"x" * 64)) == 0
+    perm = (ctypes.c_uint32 * (batch * ell))(*[x for i in insts for x in i["perm"]])
+    got = bp.prove_raw(batch, R, S, T, U, arr(cat("M")), perm, arr(cat("k")), arr(cat("m_blinders")), (ctypes.c_uint64 * batch)(*seeds))
+    assert got == want and got[0] == o.prove(insts[0], rng_seed=seeds[0])
+    bp.close()
+    bv = BatchVerifier(eng, ell, crs, max_batch=batch, lanes=2)
+    res = bv.verify_raw(batch, R, S, T, U, arr(cat("M")), arr(b"".join(got)))
+    assert list(res) == [1] * batch
+    bv.close()
+    eng.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
