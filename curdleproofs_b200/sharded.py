@@ -8,8 +8,31 @@ from __future__ import annotations
 import ctypes
 from ctypes import c_size_t, c_void_p
 
+import os
+
 CDP_ERR_NCCL = 5
 COMM_ID_BYTES = 128
+
+
+def _prefer_bundled_nccl():
+    """The engine loads NCCL at its first communicator call (`libnccl.so.2`, or $CDP_NCCL_LIB).  Inside a Python process that also uses
+    PyTorch the copy must be the one PyTorch was built against (the `nvidia-nccl` wheel): whichever `libnccl.so.2` is loaded first serves
+    both, and an older system NCCL lacks symbols libtorch_cuda needs.  So point the engine at the wheel's library when there is one."""
+    if os.environ.get("CDP_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CDP_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+_prefer_bundled_nccl()
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
