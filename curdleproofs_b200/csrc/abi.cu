@@ -42,6 +42,7 @@ struct cdp_ctx {
     // pinned host staging
     scratch_t h_stage;
     int sm_count = 148;
+    size_t big_msm_min = 0;  // cdp_set_big_msm_min: pairs from which one MSM takes the sort-based path (0 = the built-in threshold)
     // optional per-kernel profiling (cdp_profile_*): CUDA events around every launch on the context's stream
     bool profiling = false;
     struct prof_rec { int kind; cudaEvent_t e0, e1; uint64_t units; };
@@ -570,8 +571,10 @@ static const size_t BIG_MSM_MIN_N = [] { const char *e = getenv("CDP_BIG_MIN_LOG
 static int big_c_for(size_t n) {
     static int forced = -1;
     if (forced < 0) { const char *e = getenv("CDP_BIG_C"); forced = e ? atoi(e) : 0; }
-    if (forced >= 12 && forced <= 18) return forced;
-    return n < (size_t(1) << 15) ? 12 : n < (size_t(1) << 17) ? 13 : n < (size_t(1) << 19) ? 14 : n < (size_t(1) << 20) ? 15 : 16;
+    if (forced >= 12 && forced <= 20) return forced;
+    // measured with load-ordered slots (tools/msm_latency.py, round 2): 2^17..2^19: 15, 2^20: 16, 2^21: 17, 2^22: 19 (7 windows)
+    return n < (size_t(1) << 14) ? 12 : n < (size_t(1) << 16) ? 13 : n < (size_t(1) << 17) ? 14 : n < (size_t(1) << 20) ? 15 : n < (size_t(1) << 21) ? 16 :
+           n < (size_t(1) << 22) ? 17 : 19;
 }
 static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
     const int c = big_c_for(n), nwin = (130 + c - 1) / c;
@@ -587,7 +590,8 @@ static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d
     size_t o_keys = 0, o_vals = o_keys + al(items * 4), o_keys2 = o_vals + al(items * 4), o_vals2 = o_keys2 + al(items * 4),
            o_start = o_vals2 + al(items * 4), o_bjac = o_start + al((size_t)nwin * (nb + 1) * 4), o_top = o_bjac + al(slots * 144),
            o_A0 = o_top + al((size_t)nb * 144), o_B0 = o_A0 + al(lvl * 144), o_A1 = o_B0 + al(lvl * 144), o_B1 = o_A1 + al(lvl * 144),
-           o_tmp = o_B1 + al(lvl * 144), o_heavy = o_tmp + al(sort_tmp), total = o_heavy + al(big_heavy_bytes(n2, nwin));
+           o_tmp = o_B1 + al(lvl * 144), o_heavy = o_tmp + al(sort_tmp), o_order = o_heavy + al(big_heavy_bytes(n2, nwin)),
+           total = o_order + al(4 * slots * 4 + big_order_temp_bytes(slots));
     TRY(ensure_dev(ctx, ctx->d_big, total));
     uint8_t *ws = (uint8_t *)ctx->d_big.ptr;
     uint32_t *keys = (uint32_t *)(ws + o_keys), *vals = (uint32_t *)(ws + o_vals), *keys2 = (uint32_t *)(ws + o_keys2), *vals2 = (uint32_t *)(ws + o_vals2);
@@ -596,7 +600,9 @@ static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, n); CUDA_TRY(ctx, launch_big_digits(ctx->stream, P, S, (uint32_t)n, c, nwin, keys, vals)); }
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_sort(ctx->stream, ws + o_tmp, sort_tmp, keys, keys2, vals, vals2, n2, nwin, c, nullptr)); }
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_offsets(ctx->stream, keys2, n2, nwin, nb, c, start)); }
-    { launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, (uint64_t)n); CUDA_TRY(ctx, launch_big_accumulate(ctx->stream, P, vals2, start, n2, nwin, nb, sp_top, 1, bjac, ws + o_heavy)); }
+    uint32_t *order_ws = (uint32_t *)(ws + o_order);
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, slots); CUDA_TRY(ctx, launch_big_order(ctx->stream, start, nwin, nb, sp_top, order_ws, big_order_temp_bytes(slots))); }
+    { launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, (uint64_t)n); CUDA_TRY(ctx, launch_big_accumulate(ctx->stream, P, vals2, start, n2, nwin, nb, sp_top, order_ws + 3 * slots, bjac, ws + o_heavy)); }
     // top window: fold the sp_top partial sums of each bucket (two steps when a bucket has many), back into the window's slot array
     {
         uint32_t *top_slots = bjac + 36 * (size_t)(nwin - 1) * nb, *tmp = (uint32_t *)(ws + o_top);
@@ -661,11 +667,16 @@ extern "C" int cdp_sum_groups2_dev(cdp_ctx *ctx, const uint8_t *d_a, size_t per_
     return CDP_OK;
 }
 
+extern "C" int cdp_set_big_msm_min(cdp_ctx *ctx, size_t n_pairs) {
+    if (!ctx || (n_pairs && n_pairs < 2048)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_set_big_msm_min: the sort-based path needs at least 2048 pairs");
+    ctx->big_msm_min = n_pairs;
+    return CDP_OK;
+}
 extern "C" int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
     if (!ctx || !d_out_jac || (n && (!d_affine_pts || !d_scalars))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: null argument");
     if (n == 0 || n >= (size_t(1) << 31)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_dev: n out of range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (n >= BIG_MSM_MIN_N) return msm_big_resident(ctx, d_affine_pts, d_scalars, n, d_out_jac);
+    if (n >= (ctx->big_msm_min ? ctx->big_msm_min : BIG_MSM_MIN_N)) return msm_big_resident(ctx, d_affine_pts, d_scalars, n, d_out_jac);
     return msm_single_resident(ctx, d_affine_pts, d_scalars, n, d_out_jac);
 }
 

@@ -3,6 +3,7 @@
 //   k_bench_fpmul  dependent chain of Montgomery products per thread        -> achieved Fp multiplications per second
 #include "launch.h"
 #include "fp381.cuh"
+#include "g1.cuh"
 
 namespace cdp {
 
@@ -94,11 +95,83 @@ __global__ void __launch_bounds__(256) k_bench_dfma(uint32_t *out, uint32_t seed
                                                  e0 ^ e1 ^ f0 ^ f1 ^ g0 ^ g1 ^ h0 ^ h1 ^ (uint32_t)u ^ (uint32_t)(u >> 32);
 }
 
+// Mixed-addition chains (acc += P, `iters` times per thread) at the occupancy of the production kernels (128 threads, 3 CTAs / SM):
+//   which = 6  g1j_add_mixed as the kernels use it: field products called with by-value register arguments (ptxas marshals them with
+//              IMAD.MOV.U32, i.e. on the fmaheavy pipe that the products themselves saturate)
+//   which = 7  the same formula with the products called through POINTERS to local-memory operands: the marshalling becomes LDL / STL
+//              (load/store pipe) instead
+static __device__ __noinline__ void fp_mul_pfn(fp *r, const fp *a, const fp *b) {
+    fp z;
+    fp_mul_eo(z, *a, *b);
+    *r = z;
+}
+static __device__ __noinline__ void fp_sqr_pfn(fp *r, const fp *a) {
+    fp z;
+    fp_sqr_rw(z, *a);
+    *r = z;
+}
+__device__ __forceinline__ void g1j_add_mixed_ptr(g1j &r, const g1j &p, const g1a &q) {
+    fp Z1Z1, U2, S2, H, HH, I, J, rr, V, t, X3, Y3, Z3;
+    fp_sqr_pfn(&Z1Z1, &p.Z);
+    fp_mul_pfn(&U2, &q.x, &Z1Z1);
+    fp_mul_pfn(&S2, &q.y, &p.Z);
+    fp_mul_pfn(&S2, &S2, &Z1Z1);
+    fp_sub(H, U2, p.X);
+    fp_sub(rr, S2, p.Y);
+    fp_dbl(rr, rr);
+    fp_sqr_pfn(&HH, &H);
+    fp_dbl(I, HH);
+    fp_dbl(I, I);
+    fp_mul_pfn(&J, &H, &I);
+    fp_mul_pfn(&V, &p.X, &I);
+    fp_sqr_pfn(&X3, &rr);
+    fp_sub(X3, X3, J);
+    fp_sub(X3, X3, V);
+    fp_sub(X3, X3, V);
+    fp_sub(t, V, X3);
+    fp_mul_pfn(&Y3, &rr, &t);
+    fp_mul_pfn(&t, &p.Y, &J);
+    fp_dbl(t, t);
+    fp_sub(Y3, Y3, t);
+    fp_add(Z3, p.Z, H);
+    fp_sqr_pfn(&Z3, &Z3);
+    fp_sub(Z3, Z3, Z1Z1);
+    fp_sub(Z3, Z3, HH);
+    r.X = X3;
+    r.Y = Y3;
+    r.Z = Z3;
+}
+template <int MODE>
+__global__ void __launch_bounds__(128, 3) k_bench_madd(uint32_t *out, uint32_t seed, int iters) {
+    g1j acc;
+    g1a P;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        acc.X.v[i] = seed * (i + 1) + threadIdx.x;
+        acc.Y.v[i] = (seed ^ 0x9e3779b9u) * (i + 3) + blockIdx.x;
+        acc.Z.v[i] = seed + 77u * i + threadIdx.x * 3u;
+        P.x.v[i] = (seed ^ 0x85ebca6bu) * (i + 5) + threadIdx.x;
+        P.y.v[i] = (seed ^ 0xc2b2ae35u) * (i + 7) + blockIdx.x;
+    }
+    acc.X.v[11] &= 0x0fffffffu; acc.Y.v[11] &= 0x0fffffffu; acc.Z.v[11] &= 0x0fffffffu; P.x.v[11] &= 0x0fffffffu; P.y.v[11] &= 0x0fffffffu;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        if (MODE == 0) g1j_add_mixed(acc, acc, P);
+        else g1j_add_mixed_ptr(acc, acc, P);
+    }
+    uint32_t a = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) a ^= acc.X.v[i] ^ acc.Y.v[i] ^ acc.Z.v[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a;
+}
+
 cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, int threads, int iters) {
     if (which == 0) k_bench_imad<<<blocks, threads, 0, st>>>(out, 12345u, iters);
     else if (which == 3) k_bench_dfma<0><<<blocks, threads, 0, st>>>(out, 12345u, iters);
     else if (which == 4) k_bench_dfma<1><<<blocks, threads, 0, st>>>(out, 12345u, iters);
     else if (which == 5) k_bench_dfma<2><<<blocks, threads, 0, st>>>(out, 12345u, iters);
+    else if (which == 6) k_bench_madd<0><<<blocks, 128, 0, st>>>(out, 12345u, iters);
+    else if (which == 7) k_bench_madd<1><<<blocks, 128, 0, st>>>(out, 12345u, iters);
     else k_bench_fpmul<<<blocks, threads, 0, st>>>(out, 12345u, iters, which == 2);
     return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 //   one cub::DeviceRadixSort over (window | bucket) keys groups the point ids of each bucket (every window keeps exactly 2n items,
 //                    so window w is the slice [w * 2n, (w+1) * 2n) of the sorted array)
 //   k_big_offsets    bucket boundaries from the sorted keys
+//   k_big_loads      + a 12-bit radix sort: the accumulate slots in descending order of their load (balanced warps)
 //   k_big_accumulate one thread per (window, bucket): mixed additions over the bucket's points (gathered 96-byte loads, the
 //                    base array is L2-resident up to ~2^20 points); the top window's few long buckets are spread over sp_top threads
 //                    (k_big_fold_top adds their partial sums); a bucket whose per-thread share exceeds BIG_HEAVY points (skewed
@@ -97,10 +98,13 @@ struct big_heavy_item_t {
 };
 __global__ void __launch_bounds__(128, 3) k_big_accumulate(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ vals_sorted,
                                                         const uint32_t *__restrict__ start, uint32_t n2, int nwin, uint32_t nb, uint32_t sp_top,
-                                                        uint32_t chunks, uint32_t *__restrict__ buckets_jac, uint32_t *__restrict__ heavy_count,
+                                                        const uint32_t *__restrict__ order, uint32_t *__restrict__ buckets_jac, uint32_t *__restrict__ heavy_count,
                                                         big_heavy_item_t *__restrict__ heavy_items, uint32_t heavy_cap) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (size_t)nwin * nb) return;
+    // slots are handed out in descending order of their load (k_big_loads + a 12-bit radix sort): the 32 lanes of a warp then run the same
+    // number of additions (Poisson bucket sizes left 24 of 32 lanes active on average), and the longest buckets start first
+    t = order[t];
     uint32_t w = (uint32_t)(t / nb), slot = (uint32_t)(t % nb);
     const bool top = (int)w == nwin - 1;
     const uint32_t nbt = nb / sp_top;  // buckets of the top window; slot = r * nbt + b there (b fastest, so that the fold is a strided sum)
@@ -140,8 +144,24 @@ __global__ void __launch_bounds__(128, 3) k_big_accumulate(const uint32_t *__res
         if (id & 0x80000000u) fp_neg(q.y, q.y);
         g1j_add_mixed(acc, acc, q);
     }
-    (void)chunks;
     g1j_store(buckets_jac + 36 * t, acc);
+}
+
+// load of every accumulate slot (number of points its thread adds; 0 for a heavy bucket, which only lists its chunks), clamped to 12 bits
+__global__ void __launch_bounds__(256) k_big_loads(const uint32_t *__restrict__ start, int nwin, uint32_t nb, uint32_t sp_top, uint32_t *__restrict__ keys,
+                                                   uint32_t *__restrict__ vals) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nwin * nb) return;
+    const uint32_t w = (uint32_t)(t / nb), slot = (uint32_t)(t % nb);
+    const bool top = (int)w == nwin - 1;
+    const uint32_t nbt = nb / sp_top;
+    const uint32_t b = top ? slot % nbt : slot, stride = top ? sp_top : 1u, first = top ? slot / nbt : 0u;
+    const uint32_t *st = start + (size_t)w * (nb + 1);
+    const uint32_t cnt = st[b + 1] - st[b];
+    uint32_t load = cnt > first ? (cnt - first + stride - 1) / stride : 0u;
+    if (cnt / stride > BIG_HEAVY) load = 0;
+    keys[t] = load > 4095u ? 4095u : load;
+    vals[t] = (uint32_t)t;
 }
 
 // One CTA per work item (a chunk of <= BIG_CHUNK points of one heavy bucket): the 128 threads stride over the chunk with mixed additions,
@@ -327,6 +347,19 @@ cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uin
     k_big_offsets<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys_sorted, n2, nwin, nb, c, start);
     return cudaGetLastError();
 }
+size_t big_order_temp_bytes(size_t slots) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                              slots, 0, 12);
+    return bytes;
+}
+// order_ws: 4 arrays of `slots` words (keys, values, sorted keys, sorted values = the order), then the sort's temporary storage
+cudaError_t launch_big_order(cudaStream_t st, const uint32_t *start, int nwin, uint32_t nb, uint32_t sp_top, uint32_t *order_ws, size_t temp_bytes) {
+    const size_t slots = (size_t)nwin * nb;
+    uint32_t *keys = order_ws, *vals = order_ws + slots, *keys2 = order_ws + 2 * slots, *vals2 = order_ws + 3 * slots;
+    k_big_loads<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(start, nwin, nb, sp_top, keys, vals);
+    return cub::DeviceRadixSort::SortPairsDescending(order_ws + 4 * slots, temp_bytes, keys, keys2, vals, vals2, slots, 0, 12, st);
+}
 size_t big_heavy_capacity(uint32_t n2, int nwin) {  // worst case: every bucket's last chunk is partial, at most items / BIG_HEAVY heavy buckets
     const size_t items = (size_t)n2 * nwin;
     return items / BIG_CHUNK + items / BIG_HEAVY + 16;
@@ -336,7 +369,7 @@ size_t big_heavy_bytes(uint32_t n2, int nwin) {  // counter (256 B) + work list 
     return 256 + ((cap * sizeof(big_heavy_item_t) + 255) & ~size_t(255)) + cap * 144;
 }
 cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
-                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac, void *heavy_ws) {
+                                  uint32_t nb, uint32_t sp_top, const uint32_t *order, uint32_t *buckets_jac, void *heavy_ws) {
     size_t total = (size_t)nwin * nb;
     const size_t cap = big_heavy_capacity(n2, nwin);
     uint32_t *count = reinterpret_cast<uint32_t *>(heavy_ws);
@@ -344,7 +377,7 @@ cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const ui
     uint32_t *partial = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(heavy_ws) + 256 + ((cap * sizeof(big_heavy_item_t) + 255) & ~size_t(255)));
     cudaError_t e = cudaMemsetAsync(count, 0, 4, st);
     if (e != cudaSuccess) return e;
-    k_big_accumulate<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pts, vals_sorted, start, n2, nwin, nb, sp_top, chunks, buckets_jac, count, items,
+    k_big_accumulate<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(pts, vals_sorted, start, n2, nwin, nb, sp_top, order, buckets_jac, count, items,
                                                                       (uint32_t)cap);
     // skewed inputs only: with uniform scalars the list is empty and both kernels return at once (grid-stride over the list)
     const unsigned grid = (unsigned)(cap < 148 * 12 ? cap : 148 * 12);

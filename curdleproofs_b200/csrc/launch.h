@@ -96,8 +96,10 @@ cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, cons
                             uint32_t *vals_out, uint32_t n2, int nwin, int c, const uint32_t *seg_offsets);
 cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c, uint32_t *start);
 size_t big_heavy_bytes(uint32_t n2, int nwin);
+size_t big_order_temp_bytes(size_t slots);
+cudaError_t launch_big_order(cudaStream_t st, const uint32_t *start, int nwin, uint32_t nb, uint32_t sp_top, uint32_t *order_ws, size_t temp_bytes);
 cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const uint32_t *vals_sorted, const uint32_t *start, uint32_t n2, int nwin,
-                                  uint32_t nb, uint32_t sp_top, uint32_t chunks, uint32_t *buckets_jac, void *heavy_ws);
+                                  uint32_t nb, uint32_t sp_top, const uint32_t *order, uint32_t *buckets_jac, void *heavy_ws);
 cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
                                     uint32_t *Bout);
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac);

@@ -185,10 +185,18 @@ def test_generator_kat_through_gpu(engine, oracle):
     assert engine.compress_batch(jac).hex() == want
 
 
+@pytest.fixture(params=["large_path", "chunked_small_path"])
+def msm_path(request, engine):
+    """One MSM of 2^13 .. 2^17 pairs through BOTH implementations: the sort-based large Pippenger (k_bigmsm.cu; forced from 2^13 here, the
+    default crossover is 2^17) and the chunked small-MSM kernels (the default below 2^17)."""
+    engine.set_big_msm_min(8192 if request.param == "large_path" else 0)
+    yield request.param
+    engine.set_big_msm_min(0)
+
+
 @pytest.mark.parametrize("n", [8192, 8192 + 37, 20000])
-def test_msm_large_pippenger(engine, oracle, pool, n):
-    """n >= 2^13 takes the sort-based Pippenger path (k_bigmsm.cu); bit-exact vs the oracle, with infinity bases, zero scalars
-    and small scalars mixed in."""
+def test_msm_large_pippenger(engine, oracle, pool, n, msm_path):
+    """Bit-exact vs the oracle, with infinity bases, zero scalars and small scalars mixed in."""
     rnd = random.Random(n)
     pts = bytearray((pool * (n // 2100 + 1))[:96 * n])
     sc = bytearray(rand_scalars(rnd, n))
@@ -204,7 +212,7 @@ def test_msm_large_pippenger(engine, oracle, pool, n):
 
 
 @pytest.mark.parametrize("kind", ["all_equal", "small32", "half_shared", "two_values"])
-def test_msm_large_pippenger_skewed_scalars(engine, oracle, pool, kind):
+def test_msm_large_pippenger_skewed_scalars(engine, oracle, pool, kind, msm_path):
     """Skewed scalar distributions on the large-Pippenger path (BASELINE config 5's extra distributions; the all-equal case is the
     SamePerm MSM shape, /root/reference/src/same_permutation_argument.rs:75-76): whole windows collapse into one bucket, which goes
     through the heavy-bucket work list (k_big_heavy / k_big_heavy_fold, also for the top window).  Bit-exact vs the oracle."""
