@@ -913,17 +913,24 @@ extern "C" void cdp_fixed_table_destroy(cdp_ctx *ctx, cdp_fixed_table *t) {
 extern "C" size_t cdp_fixed_table_bytes(const cdp_fixed_table *t) { return t ? t->bytes : 0; }
 extern "C" size_t cdp_fixed_table_bases(const cdp_fixed_table *t) { return t ? t->n_bases : 0; }
 
-extern "C" int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
-                                       size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac) {
+extern "C" int cdp_msm_fixed_batch_dev_lanes(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                                             size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac, int lanes_per_segment) {
     if (!ctx || !t || (count && (!d_scalars || !d_segs || !d_out_jac))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev: null argument");
+    if (lanes_per_segment != 0 && lanes_per_segment != 8 && lanes_per_segment != 16 && lanes_per_segment != 32)
+        return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev_lanes: lanes_per_segment must be 0 (= 32), 8, 16 or 32");
     if (count == 0) return CDP_OK;
     if (t->device != ctx->device) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev: table lives on another device");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     static_assert(sizeof(cdp_fixed_seg) == sizeof(fixed_seg_t), "fixed segment layout");
     launch_scope ls(ctx, CDP_PROFILE_MSM_FIXED, total_pairs);
     CUDA_TRY(ctx, launch_fixed_msm(ctx->stream, t->d_table, reinterpret_cast<const uint32_t *>(d_scalars), reinterpret_cast<const fixed_seg_t *>(d_segs),
-                                   (uint32_t)count, t->kp, reinterpret_cast<const uint32_t *>(d_var_pts), reinterpret_cast<uint32_t *>(d_out_jac)));
+                                   (uint32_t)count, t->kp, reinterpret_cast<const uint32_t *>(d_var_pts), reinterpret_cast<uint32_t *>(d_out_jac),
+                                   lanes_per_segment ? lanes_per_segment : 32));
     return CDP_OK;
+}
+extern "C" int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                                       size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac) {
+    return cdp_msm_fixed_batch_dev_lanes(ctx, t, d_scalars, d_segs, count, total_pairs, d_var_pts, d_out_jac, 32);
 }
 
 extern "C" int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base_off, const uint8_t *scalars, size_t n,

@@ -144,28 +144,37 @@ __device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint
 template <int OCC, bool EXPANDED = false>
 __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
                                                        const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
-                                                       const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac) {
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= count) return;
-    const fixed_seg_t seg = segs[warp];
+                                                       const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac, uint32_t lg) {
+    // G = 2^lg lanes per segment (32: a warp per segment).  With many segments in flight fewer lanes per segment mean longer per-lane chains
+    // and fewer fold steps: the 5 full additions of a 32-lane fold are ~12 % of a 129-pair segment's work, the 3 of an 8-lane fold ~2 %.
+    const uint32_t G = 1u << lg, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sidx = gtid >> lg, lane = gtid & (G - 1);
+    const bool active = sidx < count;  // lanes of an idle group still take part in the warp-wide shuffles below
+    fixed_seg_t seg;
+    if (active) {
+        seg = segs[sidx];
+    } else {
+        seg.n = 0; seg.extra_base = 0; seg.addv_n = 0; seg.base_off = 0; seg.scalars_off = 0; seg.sel_h = 0; seg.sel_val = 0;
+        seg.remap_from = 0xFFFFFFFFu; seg.remap_delta = 0; seg.extra_scalar = 0; seg.out_idx = 0; seg.addv_off = 0;
+    }
     const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
     // returns true and the (un-negated) table point when item q has a non-zero digit
     auto fetch = [&](uint32_t q, g1a &P, bool &neg) -> bool {
         const uint32_t i = q / (uint32_t)kp.nw, w = q - i * (uint32_t)kp.nw;
-        uint32_t bidx, sidx;
+        uint32_t bidx, sidx2;
         if (i < seg.n) {
             uint32_t j = i;
             if (seg.sel_h) {
                 const uint32_t lo = i & (seg.sel_h - 1);
                 j = ((i - lo) << 1) | lo | seg.sel_val;
             }
-            sidx = seg.scalars_off + j;
+            sidx2 = seg.scalars_off + j;
             bidx = seg.base_off + j + (j >= seg.remap_from ? seg.remap_delta : 0u);
         } else {
             bidx = seg.extra_base - 1;
-            sidx = seg.scalars_off + seg.extra_scalar;
+            sidx2 = seg.scalars_off + seg.extra_scalar;
         }
-        const int d = fixed_digit(scalars + 8 * (size_t)sidx, w, kp);
+        const int d = fixed_digit(scalars + 8 * (size_t)sidx2, w, kp);
         if (d == 0) return false;
         neg = d < 0;
         const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
     uint32_t q = lane;
     while (q < items && !have) {
         have = fetch(q, cur, cur_neg);
-        q += 32;
+        q += G;
     }
 #pragma unroll 1
     while (have) {
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
         bool nxt_neg = false, hn = false;
         while (q < items && !hn) {
             hn = fetch(q, nxt, nxt_neg);
-            q += 32;
+            q += G;
         }
         if (cur_neg) fp_neg(cur.y, cur.y);
         if (EXPANDED) g1j_add_mixed_expanded(acc, acc, cur);
@@ -196,17 +205,18 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
         cur_neg = nxt_neg;
         have = hn;
     }
-    if (lane < seg.addv_n) {  // plain (coefficient 1) device-resident points of the sum
-        g1a_load(cur, var_pts + 24 * ((size_t)seg.addv_off + lane));
+#pragma unroll 1
+    for (uint32_t a = lane; a < seg.addv_n; a += G) {  // plain (coefficient 1) device-resident points of the sum
+        g1a_load(cur, var_pts + 24 * ((size_t)seg.addv_off + a));
         g1j_add_mixed(acc, acc, cur);
     }
 #pragma unroll 1
-    for (int d = 16; d >= 1; d >>= 1) {
+    for (int d = (int)(G >> 1); d >= 1; d >>= 1) {
         g1j o;
-        shfl_down_g1j(o, acc, d, 32);
+        shfl_down_g1j(o, acc, d, (int)G);
         g1j_add(acc, acc, o);
     }
-    if (lane == 0) g1j_store(out_jac + 36 * (size_t)seg.out_idx, acc);
+    if (active && lane == 0) g1j_store(out_jac + 36 * (size_t)seg.out_idx, acc);
 }
 
 // ---- the same kernel with the table points staged through shared memory by the bulk-copy engine (cp.async.bulk, SASS: UBLKCP) ----
@@ -339,26 +349,30 @@ cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains
     return cudaGetLastError();
 }
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
-                             const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac) {
+                             const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac, int lanes_per_seg) {
     if (count == 0) return cudaSuccess;
     const int occ = tuned_occupancy("CDP_OCC_FIXED", 3);
     static const int bulk = [] { const char *e = getenv("CDP_FIXED_BULK"); return e ? atoi(e) : 0; }();
-    if (bulk) {  // table points staged through shared memory by cp.async.bulk (see k_fixed_msm_bulk)
+    if (bulk) {  // table points staged through shared memory by cp.async.bulk (see k_fixed_msm_bulk); a warp per segment
         const size_t smem = 128 * 2 * FIXED_SLOT_BYTES + 128 * 2 * 8;
         if (occ == 5) k_fixed_msm_bulk<5><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
         else if (occ == 4) k_fixed_msm_bulk<4><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
         else k_fixed_msm_bulk<3><<<(count + 3) / 4, 128, smem, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
         return cudaGetLastError();
     }
+    static const int forced_lanes = [] { const char *e = getenv("CDP_FIXED_LANES"); return e ? atoi(e) : 0; }();
+    if (forced_lanes == 8 || forced_lanes == 16 || forced_lanes == 32) lanes_per_seg = forced_lanes;
+    const uint32_t lg = lanes_per_seg == 8 ? 3u : lanes_per_seg == 16 ? 4u : 5u;
+    const unsigned blocks = (unsigned)((((size_t)count << lg) + 127) / 128);
     static const int expanded = [] { const char *e = getenv("CDP_FIXED_EXPANDED"); return e ? atoi(e) : 0; }();
     if (expanded) {  // the hot loop's mixed addition with its field products expanded in place (g1j_add_mixed_expanded)
-        if (occ == 4) k_fixed_msm<4, true><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
-        else k_fixed_msm<3, true><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+        if (occ == 4) k_fixed_msm<4, true><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
+        else k_fixed_msm<3, true><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
         return cudaGetLastError();
     }
-    if (occ == 5) k_fixed_msm<5><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
-    else if (occ == 4) k_fixed_msm<4><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
-    else k_fixed_msm<3><<<(count + 3) / 4, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac);
+    if (occ == 5) k_fixed_msm<5><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
+    else if (occ == 4) k_fixed_msm<4><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
+    else k_fixed_msm<3><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
     return cudaGetLastError();
 }
 

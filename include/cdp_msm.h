@@ -183,6 +183,10 @@ typedef struct {
 } cdp_fixed_seg;
 int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
                             size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac);
+/* The same with 8, 16 or 32 (= the default of the call above) lanes of a warp working on one segment: fewer lanes per segment when many
+ * equally long segments are in flight (longer per-lane addition chains, fewer fold steps per segment). */
+int cdp_msm_fixed_batch_dev_lanes(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                                  size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac, int lanes_per_segment);
 
 /* Batched scalar multiplication / fold over device-resident points.  For every job j and element e < elems_per_job:
  *   d_pts[out_off + e] = ( (add_off != CDP_NONE ? d_pts[add_off + e] : O)
