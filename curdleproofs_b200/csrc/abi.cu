@@ -467,7 +467,7 @@ extern "C" int cdp_prove_stage_dev(cdp_ctx *ctx, const cdp_prove_dev *P, int sta
     if (!ctx || !P || stage < CDP_PS_S1 || stage > CDP_PS_SM_ROUND) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_stage_dev: bad argument");
     if (P->batch == 0) return CDP_OK;
     const size_t n = (size_t)P->ell + 4;
-    if (P->ell < 4 || ((size_t)1 << P->m) != n || round >= P->m || !P->d_state || !P->d_vec_a || !P->d_perm || !P->d_witness || !P->d_random ||
+    if (P->ell < 4 || ((size_t)1 << P->m) != n || round >= P->m || P->switch_round < 1 || P->switch_round > P->m || !P->d_state || !P->d_vec_a || !P->d_perm || !P->d_witness || !P->d_random ||
         !P->d_work || !P->d_comp0_vecs || !P->d_comp0_M || !P->d_comp_H || !P->d_comp || !P->d_side || !P->d_proofs || !P->d_scalars ||
         !P->d_fold_scalars)
         return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_stage_dev: inconsistent parameters");

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
         seg = segs[sidx];
     } else {
         seg.n = 0; seg.extra_base = 0; seg.addv_n = 0; seg.base_off = 0; seg.scalars_off = 0; seg.sel_h = 0; seg.sel_val = 0;
-        seg.remap_from = 0xFFFFFFFFu; seg.remap_delta = 0; seg.extra_scalar = 0; seg.out_idx = 0; seg.addv_off = 0;
+        seg.remap_from = 0xFFFFFFFFu; seg.remap_delta = 0; seg.extra_scalar = 0; seg.out_idx = 0; seg.addv_off = 0; seg.pos_off = 0; seg.pos_stride = 0;
     }
     const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
     // returns true and the (un-negated) table point when item q has a non-zero digit
@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
                 j = ((i - lo) << 1) | lo | seg.sel_val;
             }
             sidx2 = seg.scalars_off + j;
-            bidx = seg.base_off + j + (j >= seg.remap_from ? seg.remap_delta : 0u);
+            const uint32_t pj = seg.pos_off + j * (seg.pos_stride ? seg.pos_stride : 1u);
+            bidx = seg.base_off + pj + (pj >= seg.remap_from ? seg.remap_delta : 0u);
         } else {
             bidx = seg.extra_base - 1;
             sidx2 = seg.scalars_off + seg.extra_scalar;
@@ -269,7 +270,8 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm_bulk(const uint32_t *__r
                 j = ((i - lo) << 1) | lo | seg.sel_val;
             }
             sidx = seg.scalars_off + j;
-            bidx = seg.base_off + j + (j >= seg.remap_from ? seg.remap_delta : 0u);
+            const uint32_t pj = seg.pos_off + j * (seg.pos_stride ? seg.pos_stride : 1u);
+            bidx = seg.base_off + pj + (pj >= seg.remap_from ? seg.remap_delta : 0u);
         } else {
             bidx = seg.extra_base - 1;
             sidx = seg.scalars_off + seg.extra_scalar;

@@ -336,6 +336,51 @@ __device__ void emit_sm_round(pctx &c, uint32_t k) {
     }
     CTA_FOR(i, 2 * h) put_raw(c.scal + 8 * (n + i), fr_from_mont(c.w.x[i]));
 }
+// From the switch round k0 on (cdp_prove_dev::switch_round) the folded bases are MATERIALISED: G^(k0)_i = sum_q Wc[q] G_{i + q n'} (n' = n >> k0
+// entries, Q = 2^k0 original bases each: one strided fixed-base segment per entry), likewise G'^(k0) and G_with_blinders^(k0); the remaining rounds
+// then run like the reference's (inner_product_argument.rs:158-179): MSMs of h pairs over the folded vectors, which are folded with gamma.
+// Unfolded, every round costs n / 2 table pairs per cross term however short the vectors have become.
+//   materialisation scalars, entry (i, q) at i * Q + q:   IPA: m1 = Wc[q] | m2 = Wd[q] u_{i + q n'}  (n each);  SameMSM: ms = Ws[q]  (n)
+__device__ void emit_ipa_materialise(pctx &c, uint32_t k0) {
+    const uint32_t n = c.n, ns = n >> k0, Q = 1u << k0;
+    const fr_t *Wc = c.w.wc + (k0 & 1) * (n / 2), *Wd = c.w.wd + (k0 & 1) * (n / 2);
+    CTA_FOR(e, n) {
+        const uint32_t i = e / Q, q = e - i * Q;
+        put_raw(c.scal + 8 * e, Wc[q]);
+        put_raw(c.scal + 8 * (n + e), fr_mul(Wd[q], c.w.ucan[i + q * ns]));
+    }
+}
+__device__ void emit_sm_materialise(pctx &c, uint32_t k0) {
+    const uint32_t n = c.n, Q = 1u << k0;
+    const fr_t *Ws = c.w.ws + (k0 & 1) * (n / 2);
+    CTA_FOR(e, n) put_raw(c.scal + 8 * e, Ws[e & (Q - 1)]);
+}
+// IPA round k over the materialised vectors; scalars at offset 2n: c_L (h) | ipL | c_R (h) | ipR | d (2h), all canonical
+__device__ void emit_ipa_round_folded(pctx &c, uint32_t k) {
+    const uint32_t n = c.n, h = n >> (k + 1);
+    uint32_t *sc = c.scal + 8 * (2 * n);
+    CTA_FOR(i, h) {
+        put_raw(sc + 8 * i, fr_from_mont(c.w.c[i]));
+        put_raw(sc + 8 * (h + 1 + i), fr_from_mont(c.w.c[h + i]));
+        c.w.sa[i] = fr_mul(c.w.c[i], c.w.d[h + i]);
+        c.w.sb[i] = fr_mul(c.w.c[h + i], c.w.d[i]);
+    }
+    CTA_FOR(i, 2 * h) put_raw(sc + 8 * (2 * h + 2 + i), fr_from_mont(c.w.d[i]));
+    CTA_SYNC();
+    cta_reduce_add(c.w.sa, h);
+    cta_reduce_add(c.w.sb, h);
+    if (CTA_LEADER) {
+        const fr_t beta_i = c.w.sm[SM_BETA_I];
+        put_raw(sc + 8 * h, fr_from_mont(fr_mul(beta_i, c.w.sa[0])));
+        put_raw(sc + 8 * (2 * h + 1), fr_from_mont(fr_mul(beta_i, c.w.sb[0])));
+    }
+    CTA_SYNC();
+}
+// SameMSM round k over the materialised G_with_blinders: only x[0 .. 2h) is needed (at offset n, where the unfolded form keeps it too)
+__device__ void emit_sm_round_folded(pctx &c, uint32_t k) {
+    const uint32_t n = c.n, h = n >> (k + 1);
+    CTA_FOR(i, 2 * h) put_raw(c.scal + 8 * (n + i), fr_from_mont(c.w.x[i]));
+}
 // prefix weights of the next round: the new low bit of the prefix is bit h of the base index; set = R half = weight x g
 __device__ void grow_weights(fr_t *W, uint32_t half, uint32_t k, const fr_t &g) {
     const uint32_t Q = 1u << k;
@@ -609,11 +654,24 @@ __device__ void stage_ipa_round(pctx &c, uint32_t k) {
         c.w.c[i] = fr_add(c.w.c[i], fr_mul(gamma_inv, c.w.c[h + i]));
         c.w.d[i] = fr_add(c.w.d[i], fr_mul(gamma, c.w.d[h + i]));
     }
-    if (h > 1) {  // G = G_L + gamma G_R, G' = G'_L + gamma^-1 G'_R (:177-178) as weights on the original bases
-        grow_weights(c.w.wc, n / 2, k, gamma);
-        grow_weights(c.w.wd, n / 2, k, gamma_inv);
+    if (h > 1) {  // G = G_L + gamma G_R, G' = G'_L + gamma^-1 G'_R (:177-178): as weights on the original bases, or -- from the switch round on -- a fold launch
+        const uint32_t k0 = c.P->switch_round;
+        if (k + 1 <= k0) {
+            grow_weights(c.w.wc, n / 2, k, gamma);
+            grow_weights(c.w.wd, n / 2, k, gamma_inv);
+        }
+        if (k >= k0 && CTA_LEADER) {
+            uint32_t *fs = reinterpret_cast<uint32_t *>(c.P->d_fold_scalars) + 16 * (size_t)c.pr;
+            put_raw(fs, fr_from_mont(gamma));
+            put_raw(fs + 8, fr_from_mont(gamma_inv));
+        }
         CTA_SYNC();
-        emit_ipa_round(c, k + 1);
+        if (k + 1 < k0) {
+            emit_ipa_round(c, k + 1);
+        } else {
+            if (k + 1 == k0) emit_ipa_materialise(c, k0);
+            emit_ipa_round_folded(c, k + 1);
+        }
         return;
     }
     CTA_SYNC();
@@ -635,11 +693,17 @@ __device__ void stage_sm_round(pctx &c, uint32_t k) {
     const fr_t gamma_inv = cta_inverse(gamma, c.w.sm + SM_T0);
     CTA_FOR(i, h) c.w.x[i] = fr_add(c.w.x[i], fr_mul(gamma_inv, c.w.x[h + i]));  // x = x_L + gamma^-1 x_R   (:126)
     if (h > 1) {
-        // T = T_L + gamma T_R, U likewise: the fold launch reads gamma; G_with_blinders = G_L + gamma G_R as weights   (:128-130)
+        // T = T_L + gamma T_R, U likewise: the fold launch reads gamma; G_with_blinders = G_L + gamma G_R as weights, or folded too   (:128-130)
+        const uint32_t k0 = c.P->switch_round;
         if (CTA_LEADER) put_raw(reinterpret_cast<uint32_t *>(c.P->d_fold_scalars) + 8 * (size_t)c.pr, fr_from_mont(gamma));
-        grow_weights(c.w.ws, n / 2, k, gamma);
+        if (k + 1 <= k0) grow_weights(c.w.ws, n / 2, k, gamma);
         CTA_SYNC();
-        emit_sm_round(c, k + 1);
+        if (k + 1 < k0) {
+            emit_sm_round(c, k + 1);
+        } else {
+            if (k + 1 == k0) emit_sm_materialise(c, k0);
+            emit_sm_round_folded(c, k + 1);
+        }
         return;
     }
     CTA_SYNC();

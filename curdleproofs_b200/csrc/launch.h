@@ -120,6 +120,8 @@ struct fixed_seg_t {
     uint32_t out_idx;       // result goes to out_jac[out_idx]
     uint32_t addv_off;      // plus addv_n (<= 32) device-resident affine points var_pts[addv_off ..] added as they are: short sums such as
     uint32_t addv_n;        // D = B - beta^-1 sum(G) + alpha sum(Hvec) or A' = A + T_1 + U_1 stay one launch
+    uint32_t pos_off;       // range position j walks the bases at pos_off + j * pos_stride (0 = 1) instead of j; its scalar stays scalars[scalars_off + j]
+    uint32_t pos_stride;
 };
 struct fixed_kparams_t {
     int c, nw;

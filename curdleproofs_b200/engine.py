@@ -22,7 +22,7 @@ class FixedSeg(ctypes.Structure):
     """cdp_fixed_seg (include/cdp_msm.h)."""
     _fields_ = [("base_off", c_uint32), ("scalars_off", c_uint32), ("n", c_uint32), ("sel_h", c_uint32), ("sel_val", c_uint32),
                 ("remap_from", c_uint32), ("remap_delta", c_uint32), ("extra_base", c_uint32), ("extra_scalar", c_uint32),
-                ("out_idx", c_uint32), ("addv_off", c_uint32), ("addv_n", c_uint32)]
+                ("out_idx", c_uint32), ("addv_off", c_uint32), ("addv_n", c_uint32), ("pos_off", c_uint32), ("pos_stride", c_uint32)]
 
 
 class _MsmDesc(ctypes.Structure):

@@ -146,7 +146,12 @@ struct Lane {
 
     MsmStage st1, st2, st3, st4;
     std::vector<MsmStage> st_ipa, st_sm;
-    std::vector<FoldStage> f_sm;  // T, U folds
+    std::vector<FoldStage> f_sm;  // T, U folds (and, from the switch round on, the materialised G_with_blinders)
+    // switch round k0 (device-side prover only): rounds k >= k0 run over MATERIALISED folded bases (st_ipa_mat / st_sm_mat produce them, n >> k0
+    // points per vector, kept affine in regM / regS), see cdp_prove_dev::switch_round; k0 = m: never
+    size_t k0 = 0, regM = 0, regS = 0;
+    MsmStage st_ipa_mat, st_sm_mat;
+    std::vector<FoldStage> f_ipa;
 
     std::vector<ProofState> ps;
 };
@@ -227,6 +232,10 @@ struct SegSpec {
     long fextra_base = -1;
     size_t fextra_scalar = 0;
     size_t addv_rel = 0, addv_n = 0;  // device-resident points of the proof block added with coefficient 1
+    size_t pos_off = 0, pos_stride = 0;  // fixed-base: strided walk over the bases (cdp_fixed_seg)
+    // variable-base: points of a stage region (the affine outputs of an earlier stage, K_region per proof) instead of the proof block
+    long region_base = -1;
+    size_t region_stride = 0;
 };
 SegSpec fix_seg(size_t base_off, size_t scal_rel, size_t n) {
     SegSpec s;
@@ -297,9 +306,11 @@ void build_stage(Lane *p, MsmStage &st, const std::vector<SegSpec> &specs, size_
                     fs.extra_scalar = (uint32_t)sp.fextra_scalar;
                     fs.out_idx = (uint32_t)slot;
                     fs.addv_off = (uint32_t)(bp + sp.addv_rel); fs.addv_n = (uint32_t)sp.addv_n;
+                    fs.pos_off = (uint32_t)sp.pos_off; fs.pos_stride = (uint32_t)sp.pos_stride;
                 } else {
                     cdp_msm_seg &sg = sl.segs[slot];
-                    sg.pts_off = (uint32_t)(sp.absolute ? sp.pts_rel : bp + sp.pts_rel);
+                    sg.pts_off = (uint32_t)(sp.region_base >= 0 ? (size_t)sp.region_base + pr * sp.region_stride + sp.pts_rel
+                                            : sp.absolute ? sp.pts_rel : bp + sp.pts_rel);
                     sg.scalars_off = (uint32_t)(pr * scalars_pp + sp.scal_rel);
                     sg.n = (uint32_t)sp.n;
                     sg.extra = sp.extra_abs >= 0 ? (uint32_t)(sp.extra_abs + 1) : 0;
@@ -314,6 +325,8 @@ struct JobSpec {
     size_t src_rel, add_rel, out_rel;
     bool has_add;
     size_t scal_rel, stride;
+    long region_base = -1;      // offsets relative to a stage region (region_base + pr * region_stride) instead of the proof block
+    size_t region_stride = 0;
 };
 void build_fold(Lane *p, FoldStage &fs, const std::vector<JobSpec> &specs, size_t epj, size_t scalars_pp) {
     fs.J = specs.size();
@@ -321,8 +334,8 @@ void build_fold(Lane *p, FoldStage &fs, const std::vector<JobSpec> &specs, size_
     fs.scalars_per_proof = scalars_pp;
     fs.jobs.resize(p->max_batch * fs.J);
     for (size_t pr = 0; pr < p->max_batch; pr++) {
-        size_t bp = p->crs_n + pr * p->PW;
         for (size_t j = 0; j < fs.J; j++) {
+            const size_t bp = specs[j].region_base >= 0 ? (size_t)specs[j].region_base + pr * specs[j].region_stride : p->crs_n + pr * p->PW;
             cdp_smul_job &jb = fs.jobs[pr * fs.J + j];
             memset(&jb, 0, sizeof jb);
             jb.src_off = (uint32_t)(bp + specs[j].src_rel);
@@ -358,6 +371,11 @@ int upload_tables(Lane *p) {
     for (auto &s : p->st_ipa) PTRY(up_stage(s));
     for (auto &s : p->st_sm) PTRY(up_stage(s));
     for (auto &f : p->f_sm) PTRY(up_fold(f));
+    if (p->k0 < p->m) {
+        PTRY(up_stage(p->st_ipa_mat)); PTRY(up_stage(p->st_sm_mat));
+        for (auto &f : p->f_ipa)
+            if (f.J) PTRY(up_fold(f));
+    }
     PTRY(cdp_sync(p->ctx));  // the host vectors are pageable: make sure the copies are done before they can move
     return CDP_OK;
 }
@@ -434,6 +452,8 @@ static void lane_destroy(Lane *p) {
     for (auto &s : p->st_ipa) free_stage(s);
     for (auto &s : p->st_sm) free_stage(s);
     for (auto &f : p->f_sm) cdp_dev_free(c, f.d_jobs);
+    free_stage(p->st_ipa_mat); free_stage(p->st_sm_mat);
+    for (auto &f : p->f_ipa) cdp_dev_free(c, f.d_jobs);
     for (void *d : {(void *)p->d_pts, (void *)p->d_in, (void *)p->d_Mjac, (void *)p->d_gsrc, (void *)p->d_gdst, (void *)p->d_isrc,
                     (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_cmp, (void *)p->d_ucan, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_comp0, (void *)p->d_compH,
                     (void *)p->d_perm, (void *)p->d_wit, (void *)p->d_rnd, (void *)p->d_work, (void *)p->d_side, (void *)p->d_proofs})
@@ -462,7 +482,24 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     p->PW = 2 * n + 2 * ell + X_COUNT;
     p->reg1 = p->crs_n + max_batch * p->PW;
     p->reg2 = p->reg1 + max_batch * S1_COUNT;
-    size_t total_pts = p->reg2 + max_batch * S2_COUNT;
+    // switch round: by default the vectors are materialised when they are down to 16 entries (CDP_PROVE_SWITCH_LEN: that length; 0: never);
+    // only the device-side prover knows the folded form
+    {
+        bool dev_prove = true;
+        if (const char *e = getenv("CDP_PROVE_HOST_TRANSCRIPT")) dev_prove = atoi(e) == 0;
+        size_t sw_len = 16;
+        if (const char *e = getenv("CDP_PROVE_SWITCH_LEN")) sw_len = (size_t)atoll(e);
+        p->k0 = m;
+        if (dev_prove && sw_len >= 2 && (sw_len & (sw_len - 1)) == 0 && sw_len * 2 <= n) {
+            size_t k0 = 0;
+            while ((n >> k0) > sw_len) k0++;
+            if (k0 >= 1 && k0 < m) p->k0 = k0;
+        }
+    }
+    const size_t k0 = p->k0, ns = n >> std::min(k0, m);  // ns: entries of a materialised vector
+    p->regM = p->reg2 + max_batch * S2_COUNT;            // per proof: G^(k0) (ns) | G'^(k0) (ns)
+    p->regS = p->regM + max_batch * 2 * ns;              // per proof: G_with_blinders^(k0) (ns)
+    size_t total_pts = p->regS + max_batch * ns;
     if (total_pts >= ((size_t)1 << 31)) { delete p; return CDP_ERR_TOO_LARGE; }
     // G_with_blinders = G | H_0 | H_1 | G_t | G_u (curdleproofs.rs:134-140) in table bases: positions >= ell + 2 skip H_2, H_3, H
     const size_t gs_from = ell + 2, gs_delta = cGt - (ell + 2);
@@ -505,24 +542,65 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
                             fix_seg(0, 3, n),                                      // B_c   inner_product_argument.rs:126
                             fix_seg(0, 3 + n, n)},                                 // B_d = msm(G', r_d) = msm(G|Hvec, r_d o u)   :127
                 2 * n + 3);
-    p->st_ipa.resize(m); p->st_sm.resize(m); p->f_sm.resize(m);
+    p->st_ipa.resize(m); p->st_sm.resize(m); p->f_sm.resize(m); p->f_ipa.resize(m);
+    const size_t SPPF = 2 * n + 2 * ns + 2;  // scalars per proof of the IPA emissions from the switch on: materialisation (2n) | one folded round (<= 2 ns + 2)
+    if (k0 < m) {
+        // materialisation: entry i of the folded vector = the Q = 2^k0 original bases i, i + ns, i + 2 ns, ... with the prefix weights (k_prove.cu)
+        const size_t Q = (size_t)1 << k0;
+        std::vector<SegSpec> vi(2 * ns), vs(ns);
+        for (size_t i = 0; i < ns; i++) {
+            vi[i] = fix_seg(0, i * Q, Q); vi[i].pos_off = i; vi[i].pos_stride = ns;                    // G^(k0)_i
+            vi[ns + i] = fix_seg(0, n + i * Q, Q); vi[ns + i].pos_off = i; vi[ns + i].pos_stride = ns;  // G'^(k0)_i = sum Wd[q] u_j G_j
+            vs[i] = fix_seg(0, i * Q, Q); vs[i].pos_off = i; vs[i].pos_stride = ns;                    // G_with_blinders^(k0)_i
+            vs[i].remap_from = gs_from; vs[i].remap_delta = gs_delta;
+        }
+        build_stage(p, p->st_ipa_mat, vi, SPPF);
+        p->st_ipa_mat.aff_region = p->regM;
+        build_stage(p, p->st_sm_mat, vs, n + ns);
+        p->st_sm_mat.aff_region = p->regS;
+    }
     for (size_t k = 0; k < m; k++) {
         size_t h = n >> (k + 1);
-        // inner_product_argument.rs:158-161 over the original bases; scalars: cw (n) | ipL | ipR | dw (n)
-        //   cw[j] = w(j) c[j mod h] (bit h of j set) or w(j) c[h + j mod h] (clear);  dw[j] = w'(j) d[h + j mod h] (clear) or w'(j) d[j mod h] (set)
-        SegSpec LC = fix_half(0, 0, n / 2, h, h), LD = fix_half(0, n + 2, n / 2, h, 0), RC = fix_half(0, 0, n / 2, h, 0),
-                RD = fix_half(0, n + 2, n / 2, h, h);
-        LC.fextra_base = (long)cH; LC.fextra_scalar = n;          // L_C = msm(G_R, c_L) + <c_L,d_R> H
-        RC.fextra_base = (long)cH; RC.fextra_scalar = n + 1;      // R_C = msm(G_L, c_R) + <c_R,d_L> H
-        build_stage(p, p->st_ipa[k], {LC, LD, RC, RD}, 2 * n + 2);
-        // same_multiscalar_argument.rs:107-112; scalars: xw (n, G_with_blinders over the original bases) | x_L | x_R (folded T, U)
-        SegSpec LA = fix_half(0, 0, n / 2, h, h), RA = fix_half(0, 0, n / 2, h, 0);
-        LA.remap_from = RA.remap_from = gs_from; LA.remap_delta = RA.remap_delta = gs_delta;
-        build_stage(p, p->st_sm[k], {LA, {p->o_T + h, false, n, h, -1}, {p->o_U + h, false, n, h, -1},
-                                     RA, {p->o_T, false, n + h, h, -1}, {p->o_U, false, n + h, h, -1}},
-                    n + 2 * h);
-        build_fold(p, p->f_sm[k], {{p->o_T + h, p->o_T, p->o_T, true, 0, 0}, {p->o_U + h, p->o_U, p->o_U, true, 0, 0}},   // :128-129
-                   h, 1);
+        if (k < k0) {
+            // inner_product_argument.rs:158-161 over the original bases; scalars: cw (n) | ipL | ipR | dw (n)
+            //   cw[j] = w(j) c[j mod h] (bit h of j set) or w(j) c[h + j mod h] (clear);  dw[j] = w'(j) d[h + j mod h] (clear) or w'(j) d[j mod h] (set)
+            SegSpec LC = fix_half(0, 0, n / 2, h, h), LD = fix_half(0, n + 2, n / 2, h, 0), RC = fix_half(0, 0, n / 2, h, 0),
+                    RD = fix_half(0, n + 2, n / 2, h, h);
+            LC.fextra_base = (long)cH; LC.fextra_scalar = n;          // L_C = msm(G_R, c_L) + <c_L,d_R> H
+            RC.fextra_base = (long)cH; RC.fextra_scalar = n + 1;      // R_C = msm(G_L, c_R) + <c_R,d_L> H
+            build_stage(p, p->st_ipa[k], {LC, LD, RC, RD}, 2 * n + 2);
+            // same_multiscalar_argument.rs:107-112; scalars: xw (n, G_with_blinders over the original bases) | x_L | x_R (folded T, U)
+            SegSpec LA = fix_half(0, 0, n / 2, h, h), RA = fix_half(0, 0, n / 2, h, 0);
+            LA.remap_from = RA.remap_from = gs_from; LA.remap_delta = RA.remap_delta = gs_delta;
+            build_stage(p, p->st_sm[k], {LA, {p->o_T + h, false, n, h, -1}, {p->o_U + h, false, n, h, -1},
+                                         RA, {p->o_T, false, n + h, h, -1}, {p->o_U, false, n + h, h, -1}},
+                        n + 2 * h);
+            build_fold(p, p->f_sm[k], {{p->o_T + h, p->o_T, p->o_T, true, 0, 0}, {p->o_U + h, p->o_U, p->o_U, true, 0, 0}},   // :128-129
+                       h, 1);
+        } else {
+            // the reference's own form over the materialised vectors (regM: G (ns) | G' (ns); regS: G_with_blinders (ns)), all variable-base:
+            //   scalars at 2n: c_L (h) | ipL | c_R (h) | ipR | d (2h)
+            auto reg_seg = [&](size_t region, size_t stride, size_t rel, size_t scal_rel, size_t cnt, long extra) {
+                SegSpec sgm;
+                sgm.pts_rel = rel; sgm.scal_rel = scal_rel; sgm.n = cnt; sgm.extra_abs = extra;
+                sgm.region_base = (long)region; sgm.region_stride = stride;
+                return sgm;
+            };
+            const size_t F = 2 * n;
+            build_stage(p, p->st_ipa[k], {reg_seg(p->regM, 2 * ns, h, F, h, (long)cH),                      // L_C = msm(G_R, c_L) + ipL H
+                                          reg_seg(p->regM, 2 * ns, ns, F + 2 * h + 2 + h, h, -1),           // L_D = msm(G'_L, d_R)
+                                          reg_seg(p->regM, 2 * ns, 0, F + h + 1, h, (long)cH),              // R_C = msm(G_L, c_R) + ipR H
+                                          reg_seg(p->regM, 2 * ns, ns + h, F + 2 * h + 2, h, -1)},          // R_D = msm(G'_R, d_L)
+                        SPPF);
+            build_stage(p, p->st_sm[k], {reg_seg(p->regS, ns, h, n, h, -1), {p->o_T + h, false, n, h, -1}, {p->o_U + h, false, n, h, -1},
+                                         reg_seg(p->regS, ns, 0, n + h, h, -1), {p->o_T, false, n + h, h, -1}, {p->o_U, false, n + h, h, -1}},
+                        n + 2 * h);
+            JobSpec jg = {h, 0, 0, true, 0, 0}, jgp = {ns + h, ns, ns, true, 1, 0}, js = {h, 0, 0, true, 0, 0};
+            jg.region_base = jgp.region_base = (long)p->regM; jg.region_stride = jgp.region_stride = 2 * ns;
+            js.region_base = (long)p->regS; js.region_stride = ns;
+            if (h >= 1) build_fold(p, p->f_ipa[k], {jg, jgp}, h, 2);                                        // G_L + gamma G_R, G'_L + gamma^-1 G'_R  (:177-178)
+            build_fold(p, p->f_sm[k], {{p->o_T + h, p->o_T, p->o_T, true, 0, 0}, {p->o_U + h, p->o_U, p->o_U, true, 0, 0}, js}, h, 1);
+        }
     }
 
     // ---- device buffers
@@ -691,6 +769,7 @@ static int lane_prove_device(Lane *p, size_t B, const cdp_prove_inputs *in, uint
     P.d_state = p->d_tstate; P.d_vec_a = p->d_veca; P.d_perm = p->d_perm; P.d_witness = p->d_wit; P.d_random = p->d_rnd; P.d_work = p->d_work;
     P.d_comp0_vecs = p->d_comp0; P.d_comp0_M = p->d_comp0 + B * 4 * ell * 48; P.d_comp_H = p->d_compH; P.d_comp = p->d_comp;
     P.d_side = p->d_side; P.d_proofs = p->d_proofs; P.d_scalars = p->d_scal; P.d_fold_scalars = p->d_fscal;
+    P.switch_round = (uint32_t)p->k0;
 
     if (int rc = enqueue_prove_stage(p, P, CDP_PS_S1, 0, nullptr, p->st1.scalars_per_proof)) return rc;
     if (int rc = enqueue_msm_stage(p, p->st1, B)) return rc;
@@ -703,16 +782,23 @@ static int lane_prove_device(Lane *p, size_t B, const cdp_prove_inputs *in, uint
     PTRY(cdp_gather_dev(p->ctx, p->d_pts, p->d_pts, p->d_x2src, p->d_x2dst, B));      // B (affine, from stage 2) -> X block
     if (int rc = enqueue_msm_stage(p, p->st4, B)) return rc;
     if (int rc = enqueue_prove_stage(p, P, CDP_PS_IPA0, 0, &p->st4, p->st_ipa[0].scalars_per_proof)) return rc;
+    const size_t k0 = p->k0;
     for (size_t k = 0; k < m; k++) {
+        if (k == k0)  // G^(k0), G'^(k0) into regM
+            if (int rc = enqueue_msm_stage(p, p->st_ipa_mat, B)) return rc;
         if (int rc = enqueue_msm_stage(p, p->st_ipa[k], B)) return rc;
-        const size_t next_spp = k + 1 < m ? p->st_ipa[k + 1].scalars_per_proof : p->st_sm[0].scalars_per_proof;
+        const size_t next_spp = k + 1 >= m ? p->st_sm[0].scalars_per_proof : k + 1 >= k0 ? p->st_ipa[k0].scalars_per_proof : p->st_ipa[k + 1].scalars_per_proof;
         if (int rc = enqueue_prove_stage(p, P, CDP_PS_IPA_ROUND, (unsigned)k, &p->st_ipa[k], next_spp)) return rc;
+        if (k >= k0 && (n >> (k + 1)) > 1)
+            PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, p->f_ipa[k].d_jobs, B * p->f_ipa[k].J, p->f_ipa[k].epj));  // G, G' folds (:177-178)
     }
     for (size_t k = 0; k < m; k++) {
+        if (k == k0)  // G_with_blinders^(k0) into regS
+            if (int rc = enqueue_msm_stage(p, p->st_sm_mat, B)) return rc;
         if (int rc = enqueue_msm_stage(p, p->st_sm[k], B)) return rc;
         const size_t next_spp = p->st_sm[k + 1 < m ? k + 1 : k].scalars_per_proof;
         if (int rc = enqueue_prove_stage(p, P, CDP_PS_SM_ROUND, (unsigned)k, &p->st_sm[k], next_spp)) return rc;
-        if ((n >> (k + 1)) > 1) PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, p->f_sm[k].d_jobs, B * p->f_sm[k].J, p->f_sm[k].epj));  // T, U folds (:128-129)
+        if ((n >> (k + 1)) > 1) PTRY(cdp_smul_jobs_dev(p->ctx, p->d_pts, p->d_fscal, p->f_sm[k].d_jobs, B * p->f_sm[k].J, p->f_sm[k].epj));  // T, U (, G) folds (:128-130)
     }
     PTRY(cdp_d2h(p->ctx, p->h_proofs, p->d_proofs, B * proof_size));
     p->d2h_bytes += B * proof_size;

@@ -173,6 +173,7 @@ int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base_off, const
  *   half pattern of a vector folded down to 2h entries, which is how the IPA / SameMSM round MSMs over *folded* bases
  *   (src/inner_product_argument.rs:158-161, src/same_multiscalar_argument.rs:107-112) are written over the original ones;
  *   gap(j) = remap_delta for j >= remap_from (a base list that skips some table entries), else 0;
+ *   pos_off / pos_stride: see the struct;
  *   extra_base != 0 adds the pair (d_scalars[scalars_off + extra_scalar], B[extra_base - 1]) -- the `+ ip * H` term;
  *   addv_n (<= 32) != 0 adds the device-resident affine points d_var_pts[addv_off .. addv_off + addv_n) with coefficient 1, so
  *   short sums like D = B - beta^-1 G_sum + alpha H_sum (src/grand_product_argument.rs:223) are one segment.
@@ -180,6 +181,9 @@ int cdp_msm_fixed(cdp_ctx *ctx, const cdp_fixed_table *t, size_t base_off, const
 typedef struct {
     uint32_t base_off, scalars_off, n, sel_h, sel_val, remap_from, remap_delta, extra_base, extra_scalar, out_idx;
     uint32_t addv_off, addv_n;
+    uint32_t pos_off, pos_stride; /* the pair of range position j uses base position pos_off + j * pos_stride (pos_stride 0 = 1) in place of j
+                                     -- also in the remap test -- while its scalar stays d_scalars[scalars_off + j]: a strided walk over the
+                                     bases, e.g. the Q bases i, i + n', i + 2n', ... that fold into entry i of a vector folded down to n' entries */
 } cdp_fixed_seg;
 int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
                             size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac);
@@ -291,6 +295,12 @@ typedef struct {
     uint32_t ell, m, batch;          /* m = log2(ell + 4) */
     uint32_t proof_bytes;            /* cdp_proof_size(ell): stride of d_proofs */
     uint32_t scalars_per_proof;      /* stride (in scalars) of d_scalars for the stage being EMITTED */
+    uint32_t switch_round;           /* k0 in 1 .. m: rounds k < k0 of the IPA / SameMSM arguments are written over the ORIGINAL CRS bases (scalars =
+                                        prefix weight x folded vector entry); the step before round k0 also emits the scalars that MATERIALISE the
+                                        folded bases (n each for G, G' -- and for G_with_blinders in the SameMSM argument --, entry (i, q) at i 2^k0 + q),
+                                        and rounds k >= k0 run over those folded vectors like the reference's: scalars at offset 2n
+                                        (c_L | ipL | c_R | ipR | d) resp. n (x), the fold challenges (gamma, gamma^-1 | gamma) in d_fold_scalars.
+                                        k0 = m: never switch */
     uint32_t out_map[12];            /* where output q of the CONSUMED stage sits in d_comp, per proof pr: encoding index
                                         batch * (e >> 16) + pr * ((e >> 8) & 255) + (e & 255) */
     uint8_t *d_state;                /* batch x 208 B, the STROBE states cdp_transcript_open_dev left; in/out */
@@ -309,7 +319,7 @@ typedef struct {
     uint8_t *d_side;                 /* batch x 2 encodings kept for later transcript messages: A', D */
     uint8_t *d_proofs;               /* batch x proof_bytes */
     uint8_t *d_scalars;              /* out: batch x scalars_per_proof canonical scalars */
-    uint8_t *d_fold_scalars;         /* out (CDP_PS_SM_ROUND): batch canonical scalars, gamma of the T / U fold */
+    uint8_t *d_fold_scalars;         /* out: batch x 2 canonical scalars: gamma (| gamma^-1 in IPA rounds >= switch_round) of the fold launches */
 } cdp_prove_dev;
 size_t cdp_prove_work_scalars(size_t ell);
 size_t cdp_prove_random_scalars(size_t ell);

@@ -124,7 +124,8 @@ int cdp_msm_fixed_batch_dev(cdp_ctx *c, const cdp_fixed_table *t, const uint8_t 
                 const uint32_t lo = i & (g.sel_h - 1);
                 j = ((i - lo) << 1) | lo | g.sel_val;
             }
-            const uint32_t b = g.base_off + j + (j >= g.remap_from ? g.remap_delta : 0u);
+            const uint32_t pj = g.pos_off + j * (g.pos_stride ? g.pos_stride : 1u);
+            const uint32_t b = g.base_off + pj + (pj >= g.remap_from ? g.remap_delta : 0u);
             if (b >= t->n) { c->err = "mock: base out of range"; return CDP_ERR_INVALID_ARG; }
             push(t->bases.data() + 96 * (size_t)b, sc + 32 * ((size_t)g.scalars_off + j));
         }
