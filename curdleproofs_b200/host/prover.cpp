@@ -482,12 +482,15 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
     p->PW = 2 * n + 2 * ell + X_COUNT;
     p->reg1 = p->crs_n + max_batch * p->PW;
     p->reg2 = p->reg1 + max_batch * S1_COUNT;
-    // switch round: by default the vectors are materialised when they are down to 16 entries (CDP_PROVE_SWITCH_LEN: that length; 0: never);
-    // only the device-side prover knows the folded form
+    // switch round: CDP_PROVE_SWITCH_LEN = L materialises the folded bases when the vectors are down to L entries and runs the remaining
+    // rounds like the reference's (small variable-base MSMs + folds).  OFF by default: measured at ell = 252, 4096 proofs per step
+    // (profiles/r02_switch_round.txt): never 731.9 ms, L = 8: 735.6, 16: 745.5, 32: 812.9, 64: 892.0 -- a table pair costs 16 additions
+    // whatever the round, while h-point variable-base MSMs, folds and their normalisations are latency-bound launches.  Only the
+    // device-side prover knows the folded form.
     {
         bool dev_prove = true;
         if (const char *e = getenv("CDP_PROVE_HOST_TRANSCRIPT")) dev_prove = atoi(e) == 0;
-        size_t sw_len = 16;
+        size_t sw_len = 0;
         if (const char *e = getenv("CDP_PROVE_SWITCH_LEN")) sw_len = (size_t)atoll(e);
         p->k0 = m;
         if (dev_prove && sw_len >= 2 && (sw_len & (sw_len - 1)) == 0 && sw_len * 2 <= n) {
