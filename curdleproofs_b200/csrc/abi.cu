@@ -158,6 +158,23 @@ int msm_buckets_dev(cdp_ctx *ctx, const msm_cfg &g, const uint8_t *d_pts, const 
 }
 
 int combine_dev(cdp_ctx *ctx, const msm_cfg &g, const uint32_t *d_win, size_t count, uint32_t *d_out_jac) {
+    // few MSMs in flight: the combine is a latency chain (130 dependent doublings); run it with a quad of lanes per (MSM, bucket index)
+    // (k_msm_horner_quad, ~2.4x shorter), then the weighted reduction over the bucket indices as a combine with one window.
+    // CDP_COMBINE_QUAD_MAX: largest launch (in MSMs) that takes this route (0 disables).
+    static const size_t quad_max = [] { const char *e = getenv("CDP_COMBINE_QUAD_MAX"); return e ? (size_t)atoll(e) : (size_t)1024; }();
+    if (count <= quad_max && g.nwin > 1) {
+        const size_t nb = (size_t)1 << (g.c - 1);
+        TRY(ensure_dev(ctx, ctx->d_aux, count * nb * 144));
+        uint32_t *S = reinterpret_cast<uint32_t *>(ctx->d_aux.ptr);
+        {
+            launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, count);
+            CUDA_TRY(ctx, launch_msm_horner_quad(ctx->stream, d_win, S, (uint32_t)count, g.c, g.nwin));
+        }
+        launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, count);
+        if (g.c >= 2) CUDA_TRY(ctx, launch_msm_reduce_quad(ctx->stream, S, d_out_jac, (uint32_t)count, g.c));
+        else CUDA_TRY(ctx, launch_msm_combine(ctx->stream, S, d_out_jac, (uint32_t)count, g.c, 1));
+        return CDP_OK;
+    }
     launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, count);
     CUDA_TRY(ctx, launch_msm_combine(ctx->stream, d_win, d_out_jac, (uint32_t)count, g.c, g.nwin));
     return CDP_OK;

@@ -1,5 +1,6 @@
 #include "launch.h"
 #include "msm_common.cuh"
+#include "g1_quad.cuh"
 
 namespace cdp {
 
@@ -17,7 +18,9 @@ __global__ void __launch_bounds__(128) k_msm_combine(const uint32_t *__restrict_
     const bool valid = i < n_msm;
     g1j acc;
     g1j_set_inf(acc);
-    if (valid) {
+    if (valid && nwin == 1) {  // the windows are already combined (k_msm_horner_quad): bucket_sums = S_b, only the reduction over b is left
+        g1j_load(acc, bucket_sums + 36 * ((size_t)i * nb + b));
+    } else if (valid) {
         const uint32_t *B = bucket_sums + 36 * ((size_t)i * nwin * nb + b);
         // top window: bucket b < nbt is spread over sp slots b*sp .. b*sp + sp - 1 (k_msm_buckets); the other lanes start from infinity
         const int tb = 128 - c * (nwin - 1), nbt = tb > 0 ? (1 << tb) : 1, sp = nb / nbt >= 1 ? nb / nbt : 1;
@@ -52,6 +55,96 @@ __global__ void __launch_bounds__(128) k_msm_combine(const uint32_t *__restrict_
     if (valid && b == 0) g1j_store(out_jac + 36 * (size_t)i, acc);
 }
 
+
+// The Horner part of k_msm_combine with a QUAD of lanes per (MSM, bucket index) -- g1_quad.cuh: the ~130 dependent doublings and nwin
+// additions run at 3 resp. 5 product latencies each instead of 7 resp. 16.  Writes S_b = sum_w 2^(c w) B_{w,b} per (MSM, b); the weighted
+// reduction over b is then k_msm_combine with nwin = 1.  For launches of FEW MSMs only (a lone `util::msm`, small proof batches): with many
+// MSMs in flight the plain kernel keeps the machine just as busy with a quarter of the threads.
+__global__ void __launch_bounds__(128) k_msm_horner_quad(const uint32_t *__restrict__ bucket_sums, uint32_t *__restrict__ S_out, uint32_t n_msm, int c,
+                                                         int nwin) {
+    const int nb = 1 << (c - 1);
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, quad = gid >> 2;
+    const int s = (int)(threadIdx.x & 3);
+    const uint32_t i = quad / nb;
+    const int b = (int)(quad % nb);
+    const bool valid = i < n_msm;
+    g1j acc;
+    g1j_set_inf(acc);
+    const uint32_t *B = bucket_sums + 36 * ((size_t)(valid ? i : 0) * nwin * nb + b);
+    // top window: bucket b < nbt is spread over sp slots b*sp .. b*sp + sp - 1 (k_msm_buckets); the other quads start from infinity
+    const int tb = 128 - c * (nwin - 1), nbt = tb > 0 ? (1 << tb) : 1, sp = nb / nbt >= 1 ? nb / nbt : 1;
+    const bool has_top = valid && b < nbt;
+    const uint32_t *T = bucket_sums + 36 * (((size_t)(valid ? i : 0) * nwin + (nwin - 1)) * nb + (size_t)(has_top ? b : 0) * sp);
+#pragma unroll 1
+    for (int k = 0; k < sp; k++) {  // sp is the same for every quad: the shuffles inside stay warp-uniform
+        g1j W;
+        g1j_set_inf(W);
+        if (has_top) g1j_load(W, T + 36 * (size_t)k);
+        g1j_add_quad(acc, acc, W, s);
+    }
+#pragma unroll 1
+    for (int w = nwin - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int k = 0; k < c; k++) g1j_dbl_quad(acc, s);
+        g1j W;
+        g1j_set_inf(W);
+        if (valid) g1j_load(W, B + 36 * (size_t)w * nb);
+        g1j_add_quad(acc, acc, W, s);
+    }
+    if (valid && s == 0) g1j_store(S_out + 36 * ((size_t)i * nb + b), acc);
+}
+
+// The reduction over the bucket indices (out = sum_b (b + 1) S_b: suffix scan + tree sum, as the tail of k_msm_combine) with a quad per
+// bucket index: one CTA per MSM, partners exchanged through shared memory (nb quads = up to 128 lanes do not fit a warp's shuffles).
+__global__ void __launch_bounds__(128) k_msm_reduce_quad(const uint32_t *__restrict__ S, uint32_t *__restrict__ out_jac, int c) {
+    __shared__ uint32_t sm[32 * 36];
+    const int nb = 1 << (c - 1);
+    const int b = (int)(threadIdx.x >> 2), s = (int)(threadIdx.x & 3);
+    const uint32_t i = blockIdx.x;
+    g1j acc;
+    g1j_set_inf(acc);
+    if (b < nb) g1j_load(acc, S + 36 * ((size_t)i * nb + b));  // the CTA is padded to a whole warp: quads beyond nb carry infinity
+#pragma unroll 1
+    for (int step = 0; step < 2 * (c - 1); step++) {
+        const bool scan = step < c - 1;
+        const int d = scan ? (1 << step) : (nb >> (step - (c - 1) + 1));
+        const bool take = b < nb && (scan ? (b + d < nb) : (b < d));
+        if (s == 0 && b < nb) g1j_store(sm + 36 * b, acc);
+        __syncthreads();
+        g1j o;
+        g1j_set_inf(o);
+        if (take) g1j_load(o, sm + 36 * (b + d));
+        __syncthreads();
+        g1j_add_quad(acc, acc, o, s);
+    }
+    if (b == 0 && s == 0) g1j_store(out_jac + 36 * (size_t)i, acc);
+}
+
+// k_sum_groups with a quad per partial sum (8 quads per output point): for launches of few outputs, where the plain kernel is a chain of
+// ~per_out / 32 + 5 dependent full additions
+__global__ void __launch_bounds__(128) k_sum_groups_quad(const uint32_t *__restrict__ A, uint32_t per_a, uint32_t sa, uint32_t ga, uint32_t *__restrict__ out,
+                                                         uint32_t n_out) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_out) return;  // whole warps leave together
+    const uint32_t qd = lane >> 2;
+    const int s = (int)(lane & 3);
+    g1j acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t base = 0; base < per_a; base += 8) {
+        g1j q;
+        g1j_set_inf(q);
+        if (base + qd < per_a) g1j_load(q, A + 36 * ((size_t)(base + qd) * sa + (size_t)warp * ga));
+        g1j_add_quad(acc, acc, q, s);
+    }
+#pragma unroll 1
+    for (int d = 4; d >= 1; d >>= 1) {
+        g1j o;
+        shfl_down_g1j(o, acc, 4 * d, 32);
+        g1j_add_quad(acc, acc, o, s);
+    }
+    if (lane == 0) g1j_store(out + 36 * (size_t)warp, acc);
+}
 
 // out[g] = sum_{s < per_a} A[s * sa + g * ga]  (+ sum_{s < per_b} B[s * sb + g * gb])   -- one warp per output point
 __global__ void __launch_bounds__(128) k_sum_groups(const uint32_t *__restrict__ A, uint32_t per_a, uint32_t sa, uint32_t ga,
@@ -95,7 +188,21 @@ cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *bucket_sums, uin
     k_msm_combine<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(bucket_sums, out_jac, n_msm, c, nwin);
     return cudaGetLastError();
 }
+cudaError_t launch_msm_horner_quad(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *S_out, uint32_t n_msm, int c, int nwin) {
+    const uint64_t threads = ((uint64_t)n_msm << (c - 1)) * 4;
+    k_msm_horner_quad<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(bucket_sums, S_out, n_msm, c, nwin);
+    return cudaGetLastError();
+}
+cudaError_t launch_msm_reduce_quad(cudaStream_t st, const uint32_t *S, uint32_t *out_jac, uint32_t n_msm, int c) {
+    const unsigned threads = 4u << (c - 1);
+    k_msm_reduce_quad<<<n_msm, threads < 32 ? 32 : threads, 0, st>>>(S, out_jac, c);
+    return cudaGetLastError();
+}
 cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride) {
+    if (n_out <= 2048 && per_out >= 2) {  // few outputs: latency matters, not lane efficiency
+        k_sum_groups_quad<<<(n_out * 32 + 127) / 128, 128, 0, st>>>(in, per_out, group_stride, 1, out, n_out);
+        return cudaGetLastError();
+    }
     k_sum_groups<<<(n_out * 32 + 127) / 128, 128, 0, st>>>(in, per_out, group_stride, 1, nullptr, 0, 0, 0, out, n_out);
     return cudaGetLastError();
 }
