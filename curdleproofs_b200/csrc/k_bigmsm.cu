@@ -17,6 +17,7 @@
 
 #include "launch.h"
 #include "msm_common.cuh"
+#include "g1_quad.cuh"
 
 namespace cdp {
 
@@ -276,24 +277,62 @@ __global__ void __launch_bounds__(128) k_big_reduce_level(const uint32_t *__rest
     g1j_store(Bout + 36 * (size_t)q, bsum);
 }
 
+// k_big_reduce_level with a quad of lanes per output node (g1_quad.cuh): the 2 g - 1 dependent full additions of a node run at 5 product
+// latencies each instead of 16.  For the upper levels of the hierarchy, which are a handful of threads deep in a latency chain.
+__global__ void __launch_bounds__(128) k_big_reduce_level_quad(const uint32_t *__restrict__ Ain, const uint32_t *__restrict__ Bin, uint32_t n_out,
+                                                               uint32_t g, int shift, uint32_t *__restrict__ Aout, uint32_t *__restrict__ Bout) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, q = gid >> 2;
+    const int s = (int)(threadIdx.x & 3);
+    const bool valid = q < n_out;  // idle quads of the last warp run along with points at infinity (full-mask shuffles inside)
+    g1j run, wsum, bsum;
+    g1j_set_inf(run);
+    g1j_set_inf(wsum);
+    g1j_set_inf(bsum);
+#pragma unroll 1
+    for (int k = (int)g - 1; k >= 0; k--) {
+        g1j a;
+        g1j_set_inf(a);
+        if (valid) g1j_load(a, Ain + 36 * ((size_t)q * g + k));
+        g1j_add_quad(run, run, a, s);
+        if (k >= 1) g1j_add_quad(wsum, wsum, run, s);
+    }
+    if (Bin) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < g; k++) {
+            g1j bb;
+            g1j_set_inf(bb);
+            if (valid) g1j_load(bb, Bin + 36 * ((size_t)q * g + k));
+            g1j_add_quad(bsum, bsum, bb, s);
+        }
+    }
+#pragma unroll 1
+    for (int s2 = 0; s2 < shift; s2++) g1j_dbl_quad(wsum, s);
+    g1j_add_quad(bsum, bsum, wsum, s);
+    if (valid && s == 0) {
+        g1j_store(Aout + 36 * (size_t)q, run);
+        g1j_store(Bout + 36 * (size_t)q, bsum);
+    }
+}
+
 // total = sum_w 2^(c w) * (Bv_w + A_w)   (weight of bucket b is b + 1); one thread, Horner from the top window down
-__global__ void k_big_horner(const uint32_t *__restrict__ A, const uint32_t *__restrict__ Bv, int nwin, int c, uint32_t *__restrict__ out_jac) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_big_horner(const uint32_t *__restrict__ A, const uint32_t *__restrict__ Bv, int nwin, int c, uint32_t *__restrict__ out_jac) {
+    // one warp; its eight quads all run the same chain (g1_quad.cuh: 3 product latencies per doubling instead of 7), quad 0 stores
+    const int s = (int)(threadIdx.x & 3);
     g1j total;
     g1j_set_inf(total);
 #pragma unroll 1
     for (int w = nwin - 1; w >= 0; w--) {
         if (w != nwin - 1) {
 #pragma unroll 1
-            for (int k = 0; k < c; k++) g1j_dbl(total, total);
+            for (int k = 0; k < c; k++) g1j_dbl_quad(total, s);
         }
         g1j a, b;
         g1j_load(a, A + 36 * (size_t)w);
         g1j_load(b, Bv + 36 * (size_t)w);
-        g1j_add(total, total, a);
-        g1j_add(total, total, b);
+        g1j_add_quad(total, total, a, s);
+        g1j_add_quad(total, total, b, s);
     }
-    g1j_store(out_jac, total);
+    if (threadIdx.x == 0) g1j_store(out_jac, total);
 }
 
 // top window fold, one step: out[j * nbt + b] = sum over r = j, j + nw, j + 2 nw, ... < sp of in[r * nbt + b]   (warp (b, j)).
@@ -387,7 +426,9 @@ cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const ui
 }
 cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
                                     uint32_t *Bout) {
-    k_big_reduce_level<<<(n_out + 127) / 128, 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
+    // a level of few nodes is a latency chain: a quad per node; the wide first levels keep one thread per node (same time, a quarter of the lanes)
+    if (n_out <= 32768) k_big_reduce_level_quad<<<(unsigned)(((size_t)n_out * 4 + 127) / 128), 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
+    else k_big_reduce_level<<<(n_out + 127) / 128, 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
     return cudaGetLastError();
 }
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac) {
