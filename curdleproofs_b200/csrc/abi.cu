@@ -582,16 +582,15 @@ static int msm_single_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
 }
 
 // ---- large Pippenger (k_bigmsm.cu) ---------------------------------------------------------------------------
-// below this size the chunked small-MSM path (more additions per pair, but no sort and a much shorter launch chain) is faster;
+// below this size (2^16 pairs) the chunked small-MSM path (more additions per pair, but no sort and a much shorter launch chain) is faster;
 // CDP_BIG_MIN_LOG2 overrides (tuning)
-static const size_t BIG_MSM_MIN_N = [] { const char *e = getenv("CDP_BIG_MIN_LOG2"); int v = e ? atoi(e) : 17; return size_t(1) << (v >= 11 && v <= 24 ? v : 17); }();
+static const size_t BIG_MSM_MIN_N = [] { const char *e = getenv("CDP_BIG_MIN_LOG2"); int v = e ? atoi(e) : 16; return size_t(1) << (v >= 11 && v <= 24 ? v : 16); }();
 static int big_c_for(size_t n) {
     static int forced = -1;
     if (forced < 0) { const char *e = getenv("CDP_BIG_C"); forced = e ? atoi(e) : 0; }
     if (forced >= 12 && forced <= 20) return forced;
-    // measured with load-ordered slots (tools/msm_latency.py, round 2): 2^17..2^19: 15, 2^20: 16, 2^21: 17, 2^22: 19 (7 windows)
-    return n < (size_t(1) << 14) ? 12 : n < (size_t(1) << 16) ? 13 : n < (size_t(1) << 17) ? 14 : n < (size_t(1) << 20) ? 15 : n < (size_t(1) << 21) ? 16 :
-           n < (size_t(1) << 22) ? 17 : 19;
+    // measured with load-ordered slots and quad reductions (tools/msm_latency.py, round 2): 2^16..2^19: 15, 2^20: 16, 2^21: 17, 2^22: 19 (7 windows)
+    return n < (size_t(1) << 14) ? 12 : n < (size_t(1) << 16) ? 13 : n < (size_t(1) << 20) ? 15 : n < (size_t(1) << 21) ? 16 : n < (size_t(1) << 22) ? 17 : 19;
 }
 static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
     const int c = big_c_for(n), nwin = (130 + c - 1) / c;

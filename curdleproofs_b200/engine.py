@@ -168,7 +168,7 @@ class Engine:
         return arr
 
     def set_big_msm_min(self, n_pairs: int):
-        """Pairs from which one MSM takes the sort-based large Pippenger on this engine (0 = the built-in 2^17)."""
+        """Pairs from which one MSM takes the sort-based large Pippenger on this engine (0 = the built-in 2^16)."""
         self._check(self._lib.cdp_set_big_msm_min(self._h, n_pairs), "cdp_set_big_msm_min")
 
     def sync(self):

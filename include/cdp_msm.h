@@ -121,7 +121,7 @@ void cdp_host_free(cdp_ctx *ctx, void *h_ptr);
 /* One MSM of any size over device-resident bases and scalars (n >= 1); asynchronous, result = one Jacobian point. */
 int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac);
 
-/* One MSM (cdp_msm, cdp_msm_dev) takes the chunked small-MSM kernels below 2^17 pairs and the sort-based large Pippenger from there on
+/* One MSM (cdp_msm, cdp_msm_dev) takes the chunked small-MSM kernels below 2^16 pairs and the sort-based large Pippenger from there on
  * (the crossover measured on a B200).  This moves the crossover for one context (n_pairs >= 2048; 0 restores the default): tuning, and the
  * tests that must reach the large path at sizes the CPU oracle finishes in seconds. */
 int cdp_set_big_msm_min(cdp_ctx *ctx, size_t n_pairs);

@@ -187,8 +187,8 @@ def test_generator_kat_through_gpu(engine, oracle):
 
 @pytest.fixture(params=["large_path", "chunked_small_path"])
 def msm_path(request, engine):
-    """One MSM of 2^13 .. 2^17 pairs through BOTH implementations: the sort-based large Pippenger (k_bigmsm.cu; forced from 2^13 here, the
-    default crossover is 2^17) and the chunked small-MSM kernels (the default below 2^17)."""
+    """One MSM of 2^13 .. 2^16 pairs through BOTH implementations: the sort-based large Pippenger (k_bigmsm.cu; forced from 2^13 here, the
+    default crossover is 2^16) and the chunked small-MSM kernels (the default below 2^16)."""
     engine.set_big_msm_min(8192 if request.param == "large_path" else 0)
     yield request.param
     engine.set_big_msm_min(0)
