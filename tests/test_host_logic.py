@@ -89,3 +89,15 @@ def test_device_verifier_transcript_code_matches_host_transcript_on_cpu():
         out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count(" ok ") == 3
+
+
+def test_device_fp_inversion_euclid_on_cpu():
+    """csrc/fp_inv_euclid.cuh (plain C++; the inversion of `into_affine` / `normalize_batch` on the device) against the oracle's field:
+    a * inverse(a) == 1 mod p for edge values and 3000 pseudo-random ones."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "fpinv")
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/fp_inv_check.cpp"), "-L" + os.path.join(ROOT, "oracle"),
+                        "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "fp inverse ok" in out.stdout, out.stdout
