@@ -145,6 +145,88 @@ __device__ __forceinline__ void g1j_add_mixed(g1j &r, const g1j &p, const g1a &q
     r.Z = Z3;
 }
 
+// ---- XYZZ accumulators: (X, Y, ZZ, ZZZ) with x = X / ZZ, y = Y / ZZZ, ZZ^3 = ZZZ^2; infinity <=> ZZ = 0.
+// The bucket / table accumulation loops add affine points into one running sum: in XYZZ that is 8M + 2S (madd-2008-s) instead of the Jacobian
+// 7M + 4S, with far less add / double glue between the products: 2.95 instead of 2.59 G additions/s in the chain micro-benchmark
+// (tools/madd_bench.py, +14 %), for 12 more live registers.  (X ZZ, Y ZZZ, ZZ) is the same point in Jacobian coordinates.
+struct g1x {
+    fp X, Y, ZZ, ZZZ;
+};
+__device__ __forceinline__ void g1x_set_inf(g1x &p) {
+    fp_set_one(p.X);
+    fp_set_one(p.Y);
+    fp_set_zero(p.ZZ);
+    fp_set_zero(p.ZZZ);
+}
+__device__ __forceinline__ bool g1x_is_inf(const g1x &p) { return fp_is_zero(p.ZZ); }
+// 2q for an affine q != infinity (mdbl-2008-s-1); the rare p == q branch of the addition below
+static __device__ __noinline__ void g1x_mdbl_outlined(g1x *r, const g1a *q) {
+    fp U, V, W, S, M, t;
+    fp_dbl(U, q->y);
+    fp_sqr(V, U);
+    fp_mul(W, U, V);
+    fp_mul(S, q->x, V);
+    fp_sqr(M, q->x);
+    fp_dbl(t, M);
+    fp_add(M, t, M);
+    fp_sqr(r->X, M);
+    fp_sub(r->X, r->X, S);
+    fp_sub(r->X, r->X, S);
+    fp_sub(t, S, r->X);
+    fp_mul(t, M, t);
+    fp_mul(S, W, q->y);
+    fp_sub(r->Y, t, S);
+    r->ZZ = V;
+    r->ZZZ = W;
+}
+// r = p + q, q affine; all special cases handled
+__device__ __forceinline__ void g1x_add_mixed(g1x &r, const g1x &p, const g1a &q) {
+    if (g1a_is_inf(q)) {
+        r = p;
+        return;
+    }
+    if (g1x_is_inf(p)) {
+        r.X = q.x;
+        r.Y = q.y;
+        fp_set_one(r.ZZ);
+        fp_set_one(r.ZZZ);
+        return;
+    }
+    fp U2, S2, P, R, PP, PPP, Q, t;
+    fp_mul(U2, q.x, p.ZZ);
+    fp_mul(S2, q.y, p.ZZZ);
+    fp_sub(P, U2, p.X);
+    fp_sub(R, S2, p.Y);
+    if (fp_is_zero(P)) {
+        if (fp_is_zero(R)) {
+            g1x_mdbl_outlined(&r, &q);
+        } else {
+            g1x_set_inf(r);
+        }
+        return;
+    }
+    fp_sqr(PP, P);
+    fp_mul(PPP, P, PP);
+    fp_mul(Q, p.X, PP);
+    fp X3;
+    fp_sqr(X3, R);
+    fp_sub(X3, X3, PPP);
+    fp_sub(X3, X3, Q);
+    fp_sub(X3, X3, Q);
+    fp_sub(t, Q, X3);
+    fp_mul(t, R, t);
+    fp_mul(S2, p.Y, PPP);
+    fp_sub(r.Y, t, S2);
+    fp_mul(r.ZZ, p.ZZ, PP);
+    fp_mul(r.ZZZ, p.ZZZ, PPP);
+    r.X = X3;
+}
+__device__ __forceinline__ void g1x_to_jac(g1j &r, const g1x &p) {
+    fp_mul(r.X, p.X, p.ZZ);
+    fp_mul(r.Y, p.Y, p.ZZZ);
+    r.Z = p.ZZ;
+}
+
 // The same mixed addition with the field products expanded in place (fp_mul_eo / fp_sqr_rw inlined) instead of called: ~55 KB of
 // straight-line SASS, but none of the ~36 register moves per call that the by-value ABI of fp_mul_fn / fp_sqr_fn costs -- ptxas emits those
 // as IMAD.MOV.U32, i.e. on the same fmaheavy pipe that the 2904 IMAD.WIDE of the addition already keep ~70 % busy

@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(128, 3) k_big_accumulate(const uint32_t *__res
             return;
         }
     }
+    g1x ax;  // running sum in XYZZ coordinates (8M + 2S per point), stored as the Jacobian (X ZZ, Y ZZZ, ZZ)
+    g1x_set_inf(ax);
 #pragma unroll 1
     for (uint32_t e = lo; e < hi; e += stride) {
         uint32_t id = v[e];
@@ -143,8 +145,9 @@ __global__ void __launch_bounds__(128, 3) k_big_accumulate(const uint32_t *__res
         g1a_load(q, pts + 24 * (size_t)(p >> 1));
         if (p & 1) fp_mul_beta(q.x, q.x);
         if (id & 0x80000000u) fp_neg(q.y, q.y);
-        g1j_add_mixed(acc, acc, q);
+        g1x_add_mixed(ax, ax, q);
     }
+    g1x_to_jac(acc, ax);
     g1j_store(buckets_jac + 36 * t, acc);
 }
 
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(128, 3) k_big_heavy(const uint32_t *__restrict
         const uint32_t w = it.slot / nb;
         const uint32_t *v = vals_sorted + (size_t)w * n2;
         g1j acc;
-        g1j_set_inf(acc);
+        g1x ax;
+        g1x_set_inf(ax);
 #pragma unroll 1
         for (uint32_t e = it.lo + threadIdx.x; e < it.hi; e += blockDim.x) {
             const uint32_t id = v[e], p = id & 0x7FFFFFFFu;
@@ -187,8 +191,9 @@ __global__ void __launch_bounds__(128, 3) k_big_heavy(const uint32_t *__restrict
             g1a_load(q, pts + 24 * (size_t)(p >> 1));
             if (p & 1) fp_mul_beta(q.x, q.x);
             if (id & 0x80000000u) fp_neg(q.y, q.y);
-            g1j_add_mixed(acc, acc, q);
+            g1x_add_mixed(ax, ax, q);
         }
+        g1x_to_jac(acc, ax);
 #pragma unroll 1
         for (int d = 16; d >= 1; d >>= 1) {
             g1j o;

@@ -191,20 +191,39 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
         have = fetch(q, cur, cur_neg);
         q += G;
     }
+    if (EXPANDED) {
 #pragma unroll 1
-    while (have) {
-        g1a nxt;
-        bool nxt_neg = false, hn = false;
-        while (q < items && !hn) {
-            hn = fetch(q, nxt, nxt_neg);
-            q += G;
+        while (have) {
+            g1a nxt;
+            bool nxt_neg = false, hn = false;
+            while (q < items && !hn) {
+                hn = fetch(q, nxt, nxt_neg);
+                q += G;
+            }
+            if (cur_neg) fp_neg(cur.y, cur.y);
+            g1j_add_mixed_expanded(acc, acc, cur);
+            cur = nxt;
+            cur_neg = nxt_neg;
+            have = hn;
         }
-        if (cur_neg) fp_neg(cur.y, cur.y);
-        if (EXPANDED) g1j_add_mixed_expanded(acc, acc, cur);
-        else g1j_add_mixed(acc, acc, cur);
-        cur = nxt;
-        cur_neg = nxt_neg;
-        have = hn;
+    } else {  // the lane's running sum in XYZZ coordinates (8M + 2S per table point), Jacobian again for the fold across lanes
+        g1x ax;
+        g1x_set_inf(ax);
+#pragma unroll 1
+        while (have) {
+            g1a nxt;
+            bool nxt_neg = false, hn = false;
+            while (q < items && !hn) {
+                hn = fetch(q, nxt, nxt_neg);
+                q += G;
+            }
+            if (cur_neg) fp_neg(cur.y, cur.y);
+            g1x_add_mixed(ax, ax, cur);
+            cur = nxt;
+            cur_neg = nxt_neg;
+            have = hn;
+        }
+        g1x_to_jac(acc, ax);
     }
 #pragma unroll 1
     for (uint32_t a = lane; a < seg.addv_n; a += G) {  // plain (coefficient 1) device-resident points of the sum

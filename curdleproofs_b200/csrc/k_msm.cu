@@ -206,13 +206,19 @@ __global__ void __launch_bounds__(128, OCC)
     const uint16_t *lstB = lists + (size_t)rB * (2 * nmax) + (cur[slB] - cnt[slB]);
     uint32_t *outA = bucket_sums + 36 * (((size_t)msm * NWIN + (w0 + rA)) * NB + (slA & (NB - 1)));
     uint32_t *outB = bucket_sums + 36 * (((size_t)msm * NWIN + (w0 + rB)) * NB + (slB & (NB - 1)));
-    g1j acc;
-    g1j_set_inf(acc);
+    // the running sum in XYZZ coordinates (8M + 2S per point instead of 7M + 4S), written as the Jacobian point (X ZZ, Y ZZZ, ZZ)
+    g1x acc;
+    g1x_set_inf(acc);
+    auto flush = [&](uint32_t *dst) {
+        g1j j;
+        g1x_to_jac(j, acc);
+        g1j_store(dst, j);
+    };
 #pragma unroll 1
     for (uint32_t e = 0; e < cA + cB; e++) {
         if (e == cA) {  // first list done (an empty slot A is written here too, at e = 0, as infinity)
-            if (okA) g1j_store(outA, acc);
-            g1j_set_inf(acc);
+            if (okA) flush(outA);
+            g1x_set_inf(acc);
         }
         const uint32_t id = e < cA ? lstA[e] : lstB[e - cA];
         const uint32_t p = id & 0x7FFFu;
@@ -220,14 +226,14 @@ __global__ void __launch_bounds__(128, OCC)
         g1a_load(q, (p >> 1) < n_plain ? P + 24 * (size_t)(p >> 1) : PX);
         if (p & 1) fp_load(q.x, bx + 12 * ((size_t)msm * nmax + (p >> 1)));  // phi(P): beta * x from the digit kernel
         if (id & 0x8000u) fp_neg(q.y, q.y);
-        g1j_add_mixed(acc, acc, q);
+        g1x_add_mixed(acc, acc, q);
     }
     if (cB == 0) {  // the loop never crossed into list B: acc is still slot A's sum (or infinity), slot B is empty
-        if (okA) g1j_store(outA, acc);
-        g1j_set_inf(acc);
-        if (okB) g1j_store(outB, acc);
+        if (okA) flush(outA);
+        g1x_set_inf(acc);
+        if (okB) flush(outB);
     } else if (okB) {
-        g1j_store(outB, acc);
+        flush(outB);
     }
 }
 

@@ -9,7 +9,7 @@ from curdleproofs_b200 import Engine  # noqa: E402
 
 eng = Engine(0)
 iters = 300
-for which, name in ((6, "by-value ABI"), (7, "pointer ABI")):
+for which, name in ((6, "by-value ABI"), (7, "pointer ABI"), (8, "XYZZ accum.")):
     for bps in (1, 2, 3, 4, 6, 8):
         blocks = 148 * bps
         ms = min(eng.bench_kernel(which, blocks, 128, iters) for _ in range(3))
