@@ -32,7 +32,7 @@ R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
 GX = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
 GY = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
 README_PROOFS_PER_S = 1.0 / 0.560  # reference README.md:49, ell = 252 proving on an i7-8550U
-IMAD_PER_MIXED_ADD = 7 * 288 + 4 * 222  # Jacobian + affine: 7 products, 4 squarings
+IMAD_PER_MIXED_ADD = 8 * 288 + 2 * 222  # XYZZ accumulator + affine point: 8 products, 2 squarings
 
 
 def mont(v):
