@@ -42,6 +42,7 @@ struct cdp_ctx {
     // pinned host staging
     scratch_t h_stage;
     int sm_count = 148;
+    size_t big_ba_min = 0;   // cdp_set_big_ba_min: pairs from which the large path sums its buckets by batched affine rounds (0 = built-in)
     size_t big_msm_min = 0;  // cdp_set_big_msm_min: pairs from which one MSM takes the sort-based path (0 = the built-in threshold)
     // optional per-kernel profiling (cdp_profile_*): CUDA events around every launch on the context's stream
     bool profiling = false;
@@ -592,7 +593,79 @@ static int big_c_for(size_t n) {
     // measured with load-ordered slots and quad reductions (tools/msm_latency.py, round 2): 2^16..2^19: 15, 2^20: 16, 2^21: 17, 2^22: 19 (7 windows)
     return n < (size_t(1) << 14) ? 12 : n < (size_t(1) << 16) ? 13 : n < (size_t(1) << 20) ? 15 : n < (size_t(1) << 21) ? 16 : n < (size_t(1) << 22) ? 17 : 19;
 }
+// Bucket sums by rounds of batched affine additions (k_batchaff.cu): the default; CDP_BIG_BA=0 keeps the one-thread-per-bucket XYZZ accumulate.
+static const bool BIG_BA = [] { const char *e = getenv("CDP_BIG_BA"); return !e || atoi(e) != 0; }();
+// from 2^20 pairs: below, the rounds' fixed costs (a scan, a job list and an inversion's latency per round, ~10 rounds) outweigh the cheaper additions
+static const size_t BIG_BA_MIN_N = [] { const char *e = getenv("CDP_BIG_BA_MIN_LOG2"); int v = e ? atoi(e) : 20; return size_t(1) << (v >= 11 && v <= 30 ? v : 20); }();
+static uint32_t env_u32(const char *name, uint32_t dflt) { const char *e = getenv(name); return e && atoi(e) > 0 ? (uint32_t)atoi(e) : dflt; }
+static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
+    const int c = big_c_for(n), nwin = (130 + c - 1) / c;
+    const uint32_t nb = 1u << (c - 1), n2 = (uint32_t)(2 * n);
+    const size_t slots = (size_t)nwin * nb, items = (size_t)nwin * n2;
+    const size_t sort_tmp = big_msm_sort_temp_bytes(n2, nwin, c), scan_tmp = ba_scan_temp_bytes(slots);
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t lvl = slots / 2 + nwin;
+    const size_t s0n = (items + slots) / 2 + 64, s1n = (s0n + slots) / 2 + 64;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += al(bytes); return at; };
+    const size_t o_keys = take(items * 4), o_vals = take(items * 4), o_keys2 = take(items * 4), o_vals2 = take(items * 4),
+                 o_start = take((size_t)nwin * (nb + 1) * 4), o_bx = take(n * 48), o_baff = take(slots * 96), o_act0 = take(3 * slots * 4),
+                 o_act1 = take(3 * slots * 4), o_sc0 = take(slots * 16), o_sc1 = take(slots * 16), o_incl = take(slots * 16),
+                 o_A0 = take(lvl * 144), o_B0 = take(lvl * 144), o_A1 = take(lvl * 144), o_B1 = take(lvl * 144), o_misc = take(BA_STATS_ROUNDS * 3 * 4);
+    // the sort's temporary storage is dead once the ids are sorted: the round buffers start there
+    const size_t o_tmp = o;
+    const size_t o_scan_tmp = take(scan_tmp), o_jobs = take((items / 2 + 1) * 16), o_s0 = take(s0n * 96), o_s1 = take(s1n * 96);
+    const size_t total = std::max(o, o_tmp + al(sort_tmp));
+    TRY(ensure_dev(ctx, ctx->d_big, total));
+    uint8_t *ws = (uint8_t *)ctx->d_big.ptr;
+    uint32_t *keys = (uint32_t *)(ws + o_keys), *vals = (uint32_t *)(ws + o_vals), *keys2 = (uint32_t *)(ws + o_keys2), *vals2 = (uint32_t *)(ws + o_vals2);
+    uint32_t *start = (uint32_t *)(ws + o_start), *bx = (uint32_t *)(ws + o_bx), *baff = (uint32_t *)(ws + o_baff);
+    const uint32_t *P = reinterpret_cast<const uint32_t *>(d_pts), *S = reinterpret_cast<const uint32_t *>(d_scalars);
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, n); CUDA_TRY(ctx, launch_big_digits(ctx->stream, P, S, (uint32_t)n, c, nwin, keys, vals, bx)); }
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_sort(ctx->stream, ws + o_tmp, sort_tmp, keys, keys2, vals, vals2, n2, nwin, c, nullptr)); }
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_offsets(ctx->stream, keys2, n2, nwin, nb, c, start)); }
+    uint32_t *act[2] = {(uint32_t *)(ws + o_act0), (uint32_t *)(ws + o_act1)};
+    void *sc[2] = {ws + o_sc0, ws + o_sc1};
+    uint32_t *stats = (uint32_t *)(ws + o_misc);
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, slots); CUDA_TRY(ctx, launch_ba_init(ctx->stream, start, n2, nwin, nb, P, bx, vals2, act[0], sc[0], baff, stats)); }
+    // (additions, elements kept, list length) of every round, exact: one read-back sizes all later launches
+    uint32_t h_stats[BA_STATS_ROUNDS * 3];
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // K additions share an inversion (~5 additions' worth of instructions): as many as still leave T_TARGET threads
+    static const uint32_t K_MAX = env_u32("CDP_BA_KMAX", 64), T_TARGET = env_u32("CDP_BA_THREADS", 148 * 3 * 128 * 2);
+    uint32_t *sbuf[2] = {(uint32_t *)(ws + o_s0), (uint32_t *)(ws + o_s1)};
+    for (int r = 0; r < BA_STATS_ROUNDS && h_stats[3 * r]; r++) {
+        const uint32_t pairs = h_stats[3 * r], list_len = r == 0 ? (uint32_t)slots : h_stats[3 * r + 2];
+        if (h_stats[3 * r + 1] > ((r & 1) ? s1n : s0n)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm: round buffer too small");  // cannot happen: sized for the worst case
+        const uint32_t K = std::min(K_MAX, std::max(1u, (pairs + T_TARGET - 1) / T_TARGET));
+        launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, r == 0 ? (uint64_t)n : 0);
+        CUDA_TRY(ctx, launch_ba_round(ctx->stream, r == 0, ws + o_scan_tmp, scan_tmp, sc[r & 1], ws + o_incl, list_len, pairs, K, act[r & 1], act[(r + 1) & 1],
+                                      slots, sc[(r + 1) & 1], P, bx, vals2, sbuf[(r + 1) & 1], sbuf[r & 1], baff, ws + o_jobs));
+        ctx->launches += 3;
+    }
+    // hierarchical reduction: sum_b (b+1) B_b = Bv_root + A_root per window; the leaves are affine
+    const uint32_t *Ain = nullptr, *Bin = nullptr;
+    uint32_t *Aout = (uint32_t *)(ws + o_A0), *Bout = (uint32_t *)(ws + o_B0);
+    uint32_t len = nb;
+    int shift = 0, flip = 0;
+    while (len > 1) {
+        uint32_t g = std::min<uint32_t>(16, len);
+        uint32_t n_out = (uint32_t)((size_t)nwin * (len / g));
+        launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, n_out);
+        if (!Ain) CUDA_TRY(ctx, launch_big_reduce_leaf_affine(ctx->stream, baff, n_out, g, Aout, Bout));
+        else CUDA_TRY(ctx, launch_big_reduce_level(ctx->stream, Ain, Bin, n_out, g, shift, Aout, Bout));
+        Ain = Aout; Bin = Bout;
+        flip ^= 1;
+        Aout = (uint32_t *)(ws + (flip ? o_A1 : o_A0)); Bout = (uint32_t *)(ws + (flip ? o_B1 : o_B0));
+        len /= g;
+        while (g > 1) { shift++; g >>= 1; }
+    }
+    { launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, nwin); CUDA_TRY(ctx, launch_big_horner(ctx->stream, Ain, Bin, nwin, c, reinterpret_cast<uint32_t *>(d_out_jac))); }
+    return CDP_OK;
+}
 static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
+    if (BIG_BA && n >= (ctx->big_ba_min ? ctx->big_ba_min : BIG_BA_MIN_N) && (size_t)((130 + big_c_for(n) - 1) / big_c_for(n)) * 2 * n < (size_t(1) << 30)) return msm_big_resident_ba(ctx, d_pts, d_scalars, n, d_out_jac);
     const int c = big_c_for(n), nwin = (130 + c - 1) / c;
     const uint32_t nb = 1u << (c - 1), n2 = (uint32_t)(2 * n);
     const int top_bits = 128 - c * (nwin - 1);
@@ -613,7 +686,7 @@ static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d
     uint32_t *keys = (uint32_t *)(ws + o_keys), *vals = (uint32_t *)(ws + o_vals), *keys2 = (uint32_t *)(ws + o_keys2), *vals2 = (uint32_t *)(ws + o_vals2);
     uint32_t *start = (uint32_t *)(ws + o_start), *bjac = (uint32_t *)(ws + o_bjac);
     const uint32_t *P = reinterpret_cast<const uint32_t *>(d_pts), *S = reinterpret_cast<const uint32_t *>(d_scalars);
-    { launch_scope ls(ctx, CDP_PROFILE_OTHER, n); CUDA_TRY(ctx, launch_big_digits(ctx->stream, P, S, (uint32_t)n, c, nwin, keys, vals)); }
+    { launch_scope ls(ctx, CDP_PROFILE_OTHER, n); CUDA_TRY(ctx, launch_big_digits(ctx->stream, P, S, (uint32_t)n, c, nwin, keys, vals, nullptr)); }
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_sort(ctx->stream, ws + o_tmp, sort_tmp, keys, keys2, vals, vals2, n2, nwin, c, nullptr)); }
     { launch_scope ls(ctx, CDP_PROFILE_OTHER, items); CUDA_TRY(ctx, launch_big_offsets(ctx->stream, keys2, n2, nwin, nb, c, start)); }
     uint32_t *order_ws = (uint32_t *)(ws + o_order);
@@ -686,6 +759,11 @@ extern "C" int cdp_sum_groups2_dev(cdp_ctx *ctx, const uint8_t *d_a, size_t per_
 extern "C" int cdp_set_big_msm_min(cdp_ctx *ctx, size_t n_pairs) {
     if (!ctx || (n_pairs && n_pairs < 2048)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_set_big_msm_min: the sort-based path needs at least 2048 pairs");
     ctx->big_msm_min = n_pairs;
+    return CDP_OK;
+}
+extern "C" int cdp_set_big_ba_min(cdp_ctx *ctx, size_t n_pairs) {
+    if (!ctx || (n_pairs && n_pairs < 2048)) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_set_big_ba_min: at least 2048 pairs");
+    ctx->big_ba_min = n_pairs;
     return CDP_OK;
 }
 extern "C" int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
@@ -1207,6 +1285,12 @@ extern "C" int cdp_bench_kernel(cdp_ctx *ctx, int which, int blocks, int threads
     if (!ctx || !ms_out || blocks <= 0 || threads <= 0 || threads > 256) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_bench_kernel: bad argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(ensure_dev(ctx, ctx->d_out, (size_t)blocks * threads * 4));
+    if (which >= 9 && which <= 16) TRY(ensure_dev(ctx, ctx->d_big, (size_t)blocks * threads * iters * 288));
+    auto launch_bench = [&](cudaStream_t st, int w, uint32_t *out, int b, int t, int it) {
+        // 9 + INL: batched affine additions (INL: which products are expanded in place, batch_affine.cuh), blocks * threads threads of `iters` additions each over a streamed operand array
+        if (w >= 9 && w <= 16) return launch_bench_ba(st, (uint32_t *)ctx->d_big.ptr, (uint32_t)(blocks * threads), (uint32_t)iters, it != iters, w - 9);
+        return cdp::launch_bench(st, w, out, b, t, it);
+    };
     cudaEvent_t e0, e1;
     CUDA_TRY(ctx, cudaEventCreate(&e0));
     CUDA_TRY(ctx, cudaEventCreate(&e1));

@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include "constants.cuh"
 #include "fp_inv_euclid.cuh"
+#include "fp_inv_safegcd.cuh"
 
 namespace cdp {
 
@@ -453,7 +454,11 @@ __device__ __forceinline__ void fp_inv_fermat(fp &r, const fp &a) { fp_pow_fixed
 // the Fermat ladder above and off the multiply pipe), one product with R^3 = 2^1152 mod p gives a^-1 R
 static __device__ __noinline__ void fp_inv_euclid_fn(fp *r, const fp *a) {
     fp t, r3;
+#ifdef CDP_FP_INV_BINARY_EUCLID
     euclid::inverse_int(t.v, a->v, [](bool done) { return done; });
+#else
+    safegcd::inverse_int(t.v, a->v, [](bool done) { return done; });  // ~10x fewer instructions than the binary Euclid (fp_inv_safegcd.cuh)
+#endif
     const uint32_t R3[12] = {0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au,
                              0x921e1761u, 0x34c04e5eu, 0x65724728u, 0x2512d435u, 0x91755d4du, 0x0aa63460u};
 #pragma unroll

@@ -1,0 +1,292 @@
+// Bucket sums of the large Pippenger MSM as ROUNDS of batched affine additions (batch_affine.cuh).
+//
+// After the sort (k_bigmsm.cu) the point ids of every (window, bucket) are contiguous.  A bucket of m points is summed as a balanced tree:
+// round r adds its elements pairwise (floor(m/2) additions, an odd leftover is carried along), leaving ceil(m/2) partial sums for the next
+// round; all buckets of all windows go through a round together, so a round is one flat list of independent additions -- thread t takes
+// jobs t, t + T, t + 2T, ... and shares one field inversion between them.  Compared with one thread per bucket running XYZZ additions
+// this (a) costs 5M + 1S instead of 8M + 2S per addition, (b) balances by construction -- a skewed input (all scalars equal: one bucket
+// per window holds every point) is just a deeper tree, no separate heavy-bucket path, no load ordering -- and (c) leaves AFFINE bucket
+// sums, so the first level of the bucket reduction is mixed additions.
+//
+//   k_ba_init        one thread per bucket: its element range -> the first round's list; empty / single-point buckets are final at once
+//   per round:       one cub::DeviceScan over the list (pair count, output position, next list index per bucket),
+//                    k_ba_jobs   one thread per pair: (source position, destination) by binary search in the scanned pair counts; moves an odd
+//                                leftover; appends the bucket to the next round's list
+//                    k_ba_round  the additions
+// Round 1 gathers its operands from the caller's bases (id -> point, its endomorphism image taken from a precomputed beta x array, the digit's
+// sign applied to y); later rounds read the previous round's output.  A bucket's last addition (m = 2) writes straight to bucket_aff.
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "launch.h"
+#include "batch_affine.cuh"
+#include "scalar.cuh"
+
+namespace cdp {
+
+struct ba_scan_t {
+    uint32_t p, o, nxt, pad;  // pairs, outputs kept for the next round, 1 if the bucket stays on the list
+};
+struct ba_scan_add {
+    __device__ __forceinline__ ba_scan_t operator()(const ba_scan_t &a, const ba_scan_t &b) const {
+        return {a.p + b.p, a.o + b.o, a.nxt + b.nxt, 0u};
+    }
+};
+__device__ __forceinline__ ba_scan_t ba_plan_of(uint32_t m) {
+    // m = 2: one addition, written to the bucket's final slot; m >= 3: floor(m/2) additions + a leftover -> ceil(m/2) elements next round
+    return {m >= 2 ? m / 2 : 0u, m >= 3 ? (m + 1) / 2 : 0u, m >= 3 ? 1u : 0u, 0u};
+}
+
+// A job is (a, b, destination): round 1 names its operands by (point id | sign), later rounds by position (b = a + 1) in the previous output.
+constexpr uint32_t BA_FINAL = 0x80000000u;
+constexpr int BA_JOBS_PER_THREAD = 8;
+#ifndef BA_INLINE
+#define BA_INLINE 3
+#endif
+struct ba_gather {
+    const uint32_t *pts, *bx, *vals;
+    __device__ __forceinline__ uint2 operands(uint32_t pos) const { return make_uint2(vals[pos], vals[pos + 1]); }
+    __device__ __forceinline__ uint32_t operand(uint32_t pos) const { return vals[pos]; }
+    __device__ __forceinline__ const uint32_t *x_ptr(uint32_t id) const {
+        const uint32_t p = id & 0x7FFFFFFFu;
+        return (p & 1) ? bx + 12 * (size_t)(p >> 1) : pts + 24 * (size_t)(p >> 1);
+    }
+    __device__ __forceinline__ const uint32_t *y_ptr(uint32_t id) const { return pts + 24 * (size_t)((id & 0x7FFFFFFFu) >> 1) + 12; }
+    __device__ __forceinline__ void x_of(uint32_t id, fp &x) const { fp_load(x, x_ptr(id)); }
+    __device__ __forceinline__ void point(uint32_t id, g1a &P) const {
+        fp_load(P.x, x_ptr(id));
+        fp_load(P.y, y_ptr(id));
+        if (id & 0x80000000u) fp_neg(P.y, P.y);
+    }
+    __device__ __forceinline__ void prefetch_x(uint32_t id) const { prefetch_fp(x_ptr(id)); }
+    __device__ __forceinline__ void prefetch(uint32_t id) const {
+        prefetch_fp(x_ptr(id));
+        prefetch_fp(y_ptr(id));
+    }
+};
+struct ba_array {
+    const uint32_t *in;
+    __device__ __forceinline__ uint2 operands(uint32_t pos) const { return make_uint2(pos, pos + 1); }
+    __device__ __forceinline__ uint32_t operand(uint32_t pos) const { return pos; }
+    __device__ __forceinline__ void x_of(uint32_t pos, fp &x) const { fp_load(x, in + 24 * (size_t)pos); }
+    __device__ __forceinline__ void point(uint32_t pos, g1a &P) const { g1a_load(P, in + 24 * (size_t)pos); }
+    __device__ __forceinline__ void prefetch_x(uint32_t pos) const { prefetch_fp(in + 24 * (size_t)pos); }
+    __device__ __forceinline__ void prefetch(uint32_t pos) const { prefetch_g1a(in + 24 * (size_t)pos); }
+};
+template <class In>
+struct ba_jobs_src {
+    In in;
+    const uint4 *jobs;
+    uint32_t *out, *bucket_aff;
+    typedef uint4 ref;
+    __device__ __forceinline__ ref resolve(uint32_t q) const { return jobs[q]; }
+    __device__ __forceinline__ uint32_t *dst(const ref &r) const {
+        return (r.z & BA_FINAL) ? bucket_aff + 24 * (size_t)(r.z & ~BA_FINAL) : out + 24 * (size_t)r.z;
+    }
+    __device__ __forceinline__ void prefetch_x(const ref &r) const {
+        in.prefetch_x(r.x);
+        in.prefetch_x(r.y);
+    }
+    __device__ __forceinline__ void prefetch(const ref &r) const {
+        in.prefetch(r.x);
+        in.prefetch(r.y);
+        prefetch_fp(dst(r));
+    }
+    __device__ __forceinline__ void load_x(const ref &r, fp &px, fp &qx) const {
+        in.x_of(r.x, px);
+        in.x_of(r.y, qx);
+    }
+    __device__ __forceinline__ void load(const ref &r, g1a &P, g1a &Q) const {
+        in.point(r.x, P);
+        in.point(r.y, Q);
+    }
+};
+
+// stats[r] = (additions, elements kept, buckets on the list) of round r, for every round: each bucket plays its own halving sequence forward.
+// The host reads them once and sizes every later launch exactly (list length, pair count, additions per inversion).
+constexpr int BA_MAX_ROUNDS = 32;
+__global__ void __launch_bounds__(256) k_ba_init(const uint32_t *__restrict__ start, uint32_t n2, int nwin, uint32_t nb, ba_gather g,
+                                                 uint32_t *__restrict__ act_pos, uint32_t *__restrict__ act_m, uint32_t *__restrict__ act_id,
+                                                 ba_scan_t *__restrict__ scan_in, uint32_t *__restrict__ bucket_aff, uint32_t *__restrict__ stats) {
+    __shared__ uint32_t sh[BA_MAX_ROUNDS * 3];
+    for (int i = threadIdx.x; i < BA_MAX_ROUNDS * 3; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t B = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t m = 0;
+    if (B < (uint32_t)nwin * nb) {
+        const uint32_t w = B / nb, b = B % nb;
+        const uint32_t *st = start + (size_t)w * (nb + 1);
+        const uint32_t lo = st[b];
+        m = st[b + 1] - lo;
+        const uint32_t pos = w * n2 + lo;
+        act_pos[B] = pos;
+        act_m[B] = m;
+        act_id[B] = B;
+        scan_in[B] = ba_plan_of(m);
+        if (m <= 1) {
+            g1a P;
+            g1a_set_inf(P);
+            if (m == 1) g.point(g.operand(pos), P);
+            g1a_store(bucket_aff + 24 * (size_t)B, P);
+        }
+    }
+#pragma unroll 1
+    for (int r = 0; r < BA_MAX_ROUNDS; r++) {
+        if (!__any_sync(0xffffffffu, m >= 2)) break;
+        const ba_scan_t pl = ba_plan_of(m);
+        const uint32_t p = __reduce_add_sync(0xffffffffu, pl.p), o = __reduce_add_sync(0xffffffffu, pl.o),
+                       l = __reduce_add_sync(0xffffffffu, m >= 2 ? 1u : 0u);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&sh[3 * r], p);
+            atomicAdd(&sh[3 * r + 1], o);
+            atomicAdd(&sh[3 * r + 2], l);
+        }
+        m = pl.o;  // 0 once the bucket is final
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BA_MAX_ROUNDS * 3; i += blockDim.x)
+        if (sh[i]) atomicAdd(&stats[i], sh[i]);
+}
+
+template <class In>
+__global__ void __launch_bounds__(256) k_ba_jobs(const ba_scan_t *__restrict__ incl, uint32_t bound, uint32_t total, const uint32_t *__restrict__ act_pos,
+                                                 const uint32_t *__restrict__ act_m, const uint32_t *__restrict__ act_id, In in, uint32_t *__restrict__ out,
+                                                 uint4 *__restrict__ jobs, uint32_t *__restrict__ nact_pos, uint32_t *__restrict__ nact_m,
+                                                 uint32_t *__restrict__ nact_id, ba_scan_t *__restrict__ nscan_in) {
+#pragma unroll 1
+    for (int rep = 0; rep < BA_JOBS_PER_THREAD; rep++) {  // several pairs per thread: a CTA per 256 pairs is bound by the CTA launch rate
+        const uint32_t q = (blockIdx.x * BA_JOBS_PER_THREAD + rep) * blockDim.x + threadIdx.x;
+        if (q >= total) return;
+        uint32_t lo = 0, hi = bound - 1;  // smallest a with incl[a].p > q
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (incl[mid].p > q) hi = mid;
+            else lo = mid + 1;
+        }
+        const uint32_t a = lo, m = act_m[a], p = m / 2;
+        const ba_scan_t sc = incl[a];
+        const uint32_t j = q - (sc.p - p), src = act_pos[a] + 2 * j;
+        const uint2 ops = in.operands(src);
+        if (m == 2) {
+            jobs[q] = make_uint4(ops.x, ops.y, BA_FINAL | act_id[a], 0u);
+            continue;
+        }
+        const uint32_t keep = (m + 1) / 2, oex = sc.o - keep;
+        jobs[q] = make_uint4(ops.x, ops.y, oex + j, 0u);
+        if (j == p - 1 && (m & 1)) {  // odd leftover: carried to the next round unchanged
+            g1a P;
+            in.point(in.operand(src + 2), P);
+            g1a_store(out + 24 * (size_t)(oex + p), P);
+        }
+        if (j == 0) {
+            const uint32_t nx = sc.nxt - 1;
+            nact_pos[nx] = oex;
+            nact_m[nx] = keep;
+            nact_id[nx] = act_id[a];
+            nscan_in[nx] = ba_plan_of(keep);
+        }
+    }
+}
+
+template <class In>
+__global__ void __launch_bounds__(128, 3) k_ba_round(uint32_t total, uint32_t K, uint32_t pf, ba_jobs_src<In> src) {
+    const uint32_t T = (total + K - 1) / K;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= T) return;
+    ba_run<ba_jobs_src<In>, BA_INLINE>(src, tid, T, total, K, pf);
+}
+
+size_t ba_scan_temp_bytes(size_t n) {
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, bytes, (const ba_scan_t *)nullptr, (ba_scan_t *)nullptr, ba_scan_add(), (int)n);
+    return bytes;
+}
+cudaError_t launch_ba_init(cudaStream_t st, const uint32_t *start, uint32_t n2, int nwin, uint32_t nb, const uint32_t *pts, const uint32_t *bx,
+                           const uint32_t *vals, uint32_t *act /* 3 arrays of nwin * nb */, void *scan_in, uint32_t *bucket_aff,
+                           uint32_t *stats /* BA_STATS_WORDS */) {
+    const uint32_t slots = (uint32_t)nwin * nb;
+    cudaError_t e = cudaMemsetAsync(stats, 0, BA_MAX_ROUNDS * 3 * 4, st);
+    if (e != cudaSuccess) return e;
+    k_ba_init<<<(slots + 255) / 256, 256, 0, st>>>(start, n2, nwin, nb, ba_gather{pts, bx, vals}, act, act + slots, act + 2 * (size_t)slots,
+                                                    reinterpret_cast<ba_scan_t *>(scan_in), bucket_aff, stats);
+    return cudaGetLastError();
+}
+// One round: `list_len` buckets on its list, `pairs` additions, K of them per inversion (all exact: k_ba_init's statistics).
+cudaError_t launch_ba_round(cudaStream_t st, bool first, void *scan_tmp, size_t scan_tmp_bytes, void *scan_in, void *scan_out, uint32_t list_len,
+                            uint32_t pairs, uint32_t K, const uint32_t *act, uint32_t *nact, size_t act_stride, void *nscan_in, const uint32_t *pts,
+                            const uint32_t *bx, const uint32_t *vals, const uint32_t *in, uint32_t *out, uint32_t *bucket_aff, void *jobs) {
+    const ba_scan_t *sin = reinterpret_cast<const ba_scan_t *>(scan_in);
+    ba_scan_t *incl = reinterpret_cast<ba_scan_t *>(scan_out), *nsin = reinterpret_cast<ba_scan_t *>(nscan_in);
+    cudaError_t e = cub::DeviceScan::InclusiveScan(scan_tmp, scan_tmp_bytes, sin, incl, ba_scan_add(), (int)list_len, st);
+    if (e != cudaSuccess) return e;
+    uint4 *jb = reinterpret_cast<uint4 *>(jobs);
+    static const uint32_t pf_first = getenv("CDP_BA_PF1") ? (uint32_t)atoi(getenv("CDP_BA_PF1")) : 0u, pf_later = getenv("CDP_BA_PF") ? (uint32_t)atoi(getenv("CDP_BA_PF")) : 0u;
+    const unsigned gj = (pairs + 256 * BA_JOBS_PER_THREAD - 1) / (256 * BA_JOBS_PER_THREAD), T = (pairs + K - 1) / K, gr = (T + 127) / 128;
+    if (first) {
+        const ba_gather g{pts, bx, vals};
+        k_ba_jobs<ba_gather><<<gj, 256, 0, st>>>(incl, list_len, pairs, act, act + act_stride, act + 2 * act_stride, g, out, jb, nact, nact + act_stride,
+                                                 nact + 2 * act_stride, nsin);
+        k_ba_round<ba_gather><<<gr, 128, 0, st>>>(pairs, K, pf_first, ba_jobs_src<ba_gather>{g, jb, out, bucket_aff});
+    } else {
+        const ba_array g{in};
+        k_ba_jobs<ba_array><<<gj, 256, 0, st>>>(incl, list_len, pairs, act, act + act_stride, act + 2 * act_stride, g, out, jb, nact, nact + act_stride,
+                                                nact + 2 * act_stride, nsin);
+        k_ba_round<ba_array><<<gr, 128, 0, st>>>(pairs, K, pf_later, ba_jobs_src<ba_array>{g, jb, out, bucket_aff});
+    }
+    return cudaGetLastError();
+}
+
+// ---- micro-benchmark: T threads, K additions each, operands streamed from an array of 2 T K pseudo-random "points" (cdp_bench_kernel 9)
+struct ba_bench_src {
+    const uint32_t *in;
+    uint32_t *out;
+    typedef uint32_t ref;
+    __device__ __forceinline__ ref resolve(uint32_t q) const { return q; }
+    __device__ __forceinline__ uint32_t *dst(ref q) const { return out + 24 * (size_t)q; }
+    __device__ __forceinline__ void prefetch_x(ref q) const {
+        prefetch_fp(in + 48 * (size_t)q);
+        prefetch_fp(in + 48 * (size_t)q + 24);
+    }
+    __device__ __forceinline__ void prefetch(ref q) const {
+        prefetch_g1a(in + 48 * (size_t)q);
+        prefetch_g1a(in + 48 * (size_t)q + 24);
+        prefetch_fp(dst(q));
+    }
+    __device__ __forceinline__ void load_x(ref q, fp &px, fp &qx) const {
+        fp_load(px, in + 48 * (size_t)q);
+        fp_load(qx, in + 48 * (size_t)q + 24);
+    }
+    __device__ __forceinline__ void load(ref q, g1a &P, g1a &Q) const {
+        g1a_load(P, in + 48 * (size_t)q);
+        g1a_load(Q, in + 48 * (size_t)q + 24);
+    }
+};
+__global__ void __launch_bounds__(256) k_ba_bench_fill(uint32_t *buf, size_t words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i * 2654435761u + (uint32_t)(i >> 32) + 0x9e3779b9u;
+        x ^= x >> 15; x *= 0x85ebca6bu; x ^= x >> 13;
+        buf[i] = (i % 12 == 11) ? (x & 0x0fffffffu) : x;  // below p
+    }
+}
+template <int INL>
+__global__ void __launch_bounds__(128, 3) k_ba_bench(ba_bench_src src, uint32_t T, uint32_t K) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= T) return;
+    ba_run<ba_bench_src, INL>(src, tid, T, T * K, K);
+}
+cudaError_t launch_bench_ba(cudaStream_t st, uint32_t *buf, uint32_t T, uint32_t K, bool fill, int inl) {
+    const size_t pairs = (size_t)T * K;
+    if (fill) k_ba_bench_fill<<<148 * 8, 256, 0, st>>>(buf, pairs * 48);
+    const ba_bench_src src{buf, buf + pairs * 48};
+    const unsigned g = (T + 127) / 128;
+    if (inl == 1) k_ba_bench<1><<<g, 128, 0, st>>>(src, T, K);
+    else if (inl == 3) k_ba_bench<3><<<g, 128, 0, st>>>(src, T, K);
+    else if (inl == 7) k_ba_bench<7><<<g, 128, 0, st>>>(src, T, K);
+    else if (inl == 5) k_ba_bench<5><<<g, 128, 0, st>>>(src, T, K);
+    else k_ba_bench<0><<<g, 128, 0, st>>>(src, T, K);
+    return cudaGetLastError();
+}
+
+}  // namespace cdp

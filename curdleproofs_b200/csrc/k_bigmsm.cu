@@ -22,7 +22,7 @@
 namespace cdp {
 
 __global__ void __launch_bounds__(256) k_big_digits(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars, uint32_t n, int c,
-                                                    int nwin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                                    int nwin, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ bx) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t k[8];
@@ -36,6 +36,12 @@ __global__ void __launch_bounds__(256) k_big_digits(const uint32_t *__restrict__
         uint4 v = pp[q];
         nz |= v.x | v.y | v.z | v.w;
     }
+    if (bx) {  // beta x, the x coordinate of the endomorphism image: once per base here instead of once per (window, point) in the gather
+        fp x;
+        fp_load(x, pts + 24 * (size_t)j);
+        fp_mul_beta(x, x);
+        fp_store(bx + 12 * (size_t)j, x);
+    }
     glv_t g;
     glv_split(g, k);
     if (nz == 0) {  // infinity base contributes nothing
@@ -43,47 +49,48 @@ __global__ void __launch_bounds__(256) k_big_digits(const uint32_t *__restrict__
         for (int q = 0; q < 4; q++) g.k1[q] = g.k2[q] = 0;
     }
     const uint32_t nb = 1u << (c - 1), n2 = 2 * n;
+    // both halves of a pair go out as one 8-byte store per window (ids 2j, 2j + 1 are neighbours): fully coalesced
+    uint32_t kk[2][5] = {{g.k1[0], g.k1[1], g.k1[2], g.k1[3], 0}, {g.k2[0], g.k2[1], g.k2[2], g.k2[3], 0}};
+    uint32_t carry[2] = {0, 0};
+    for (int w = 0; w < nwin; w++) {
+        const int bit = w * c, li = bit >> 5, sh = bit & 31;
+        uint32_t key[2], val[2];
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        uint32_t kk[5] = {half ? g.k2[0] : g.k1[0], half ? g.k2[1] : g.k1[1], half ? g.k2[2] : g.k1[2], half ? g.k2[3] : g.k1[3], 0};
-        uint32_t carry = 0;
-        const uint32_t id = 2 * j + half;
-        for (int w = 0; w < nwin; w++) {
-            int bit = w * c, li = bit >> 5, sh = bit & 31;
+        for (int half = 0; half < 2; half++) {
             uint32_t v = 0;
             if (li < 4) {
-                v = kk[li] >> sh;
-                if (sh + c > 32) v |= kk[li + 1] << (32 - sh);
+                v = kk[half][li] >> sh;
+                if (sh + c > 32) v |= kk[half][li + 1] << (32 - sh);
             }
-            v = (v & ((1u << c) - 1)) + carry;
-            carry = (v + nb) >> c;
-            int d = (int)v - (int)(carry << c);
-            uint32_t ad = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            v = (v & ((1u << c) - 1)) + carry[half];
+            carry[half] = (v + nb) >> c;
+            const int d = (int)v - (int)(carry[half] << c);
+            const uint32_t ad = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
             // key = window | bucket; bucket nb = "digit zero", sorted behind every real bucket of its window
-            keys[(size_t)w * n2 + id] = ((uint32_t)w << c) | (ad ? ad - 1 : nb);
-            vals[(size_t)w * n2 + id] = id | (d < 0 ? 0x80000000u : 0u);
+            key[half] = ((uint32_t)w << c) | (ad ? ad - 1 : nb);
+            val[half] = (2 * j + half) | (d < 0 ? 0x80000000u : 0u);
         }
+        *reinterpret_cast<uint2 *>(keys + (size_t)w * n2 + 2 * j) = make_uint2(key[0], key[1]);
+        *reinterpret_cast<uint2 *>(vals + (size_t)w * n2 + 2 * j) = make_uint2(val[0], val[1]);
     }
 }
 
-// start[w][b] = first position (inside window w's sorted segment) whose key is >= b, for b = 0..nb (inclusive)
+// start[w][b] = first position (inside window w's sorted segment) whose key is >= b, for b = 0..nb (inclusive): one thread per (window, b),
+// a binary search in the sorted keys (neighbouring threads walk almost the same path, so the probes coalesce).  Scanning the keys for
+// boundaries instead leaves long runs of empty buckets -- the top window uses 2^14 of its 2^18 -- to single threads: 1 ms of serial stores.
 __global__ void __launch_bounds__(256) k_big_offsets(const uint32_t *__restrict__ keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c,
                                                      uint32_t *__restrict__ start) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (size_t)nwin * n2) return;
-    uint32_t w = (uint32_t)(t / n2), i = (uint32_t)(t % n2);
+    const uint32_t w = blockIdx.y, b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > nb) return;
     const uint32_t mask = (1u << c) - 1;
-    uint32_t key = keys_sorted[t] & mask;
-    uint32_t prev = i ? (keys_sorted[t - 1] & mask) : 0xFFFFFFFFu;
-    uint32_t *st = start + (size_t)w * (nb + 1);
-    if (i == 0) {
-        for (uint32_t b = 0; b <= key && b <= nb; b++) st[b] = 0;
-    } else if (key != prev) {
-        for (uint32_t b = prev + 1; b <= key && b <= nb; b++) st[b] = i;
+    const uint32_t *k = keys_sorted + (size_t)w * n2;
+    uint32_t lo = 0, hi = n2;  // first i with key(i) >= b
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((k[mid] & mask) >= b) hi = mid;
+        else lo = mid + 1;
     }
-    if (i == n2 - 1) {
-        for (uint32_t b = key + 1; b <= nb; b++) st[b] = n2;
-    }
+    start[(size_t)w * (nb + 1) + b] = lo;
 }
 
 // Every window owns nb slots (threads).  In an ordinary window slot = bucket.  The top window only sees the few leftover
@@ -282,6 +289,39 @@ __global__ void __launch_bounds__(128) k_big_reduce_level(const uint32_t *__rest
     g1j_store(Bout + 36 * (size_t)q, bsum);
 }
 
+// First level over AFFINE bucket sums (k_batchaff.cu leaves them so; x = y = 0 is the empty bucket): the running sum takes mixed additions.
+// QUAD: a quad of lanes per node, as below (levels of few nodes).
+template <bool QUAD>
+__global__ void __launch_bounds__(128) k_big_reduce_leaf_affine(const uint32_t *__restrict__ bucket_aff, uint32_t n_out, uint32_t g,
+                                                                uint32_t *__restrict__ Aout, uint32_t *__restrict__ Bout) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, q = QUAD ? gid >> 2 : gid;
+    const int s = (int)(threadIdx.x & 3);
+    const bool valid = q < n_out;
+    if (!QUAD && !valid) return;
+    g1j run, wsum;
+    g1j_set_inf(run);
+    g1j_set_inf(wsum);
+#pragma unroll 1
+    for (int k = (int)g - 1; k >= 0; k--) {
+        g1a a;
+        g1a_set_inf(a);
+        if (valid) g1a_load(a, bucket_aff + 24 * ((size_t)q * g + k));
+        if (QUAD) {
+            g1j aj;
+            g1j_from_affine(aj, a);
+            g1j_add_quad(run, run, aj, s);
+            if (k >= 1) g1j_add_quad(wsum, wsum, run, s);
+        } else {
+            g1j_add_mixed(run, run, a);
+            if (k >= 1) g1j_add(wsum, wsum, run);
+        }
+    }
+    if (valid && (!QUAD || s == 0)) {
+        g1j_store(Aout + 36 * (size_t)q, run);
+        g1j_store(Bout + 36 * (size_t)q, wsum);
+    }
+}
+
 // k_big_reduce_level with a quad of lanes per output node (g1_quad.cuh): the 2 g - 1 dependent full additions of a node run at 5 product
 // latencies each instead of 16.  For the upper levels of the hierarchy, which are a handful of threads deep in a latency chain.
 __global__ void __launch_bounds__(128) k_big_reduce_level_quad(const uint32_t *__restrict__ Ain, const uint32_t *__restrict__ Bin, uint32_t n_out,
@@ -377,8 +417,8 @@ size_t big_msm_sort_temp_bytes(uint32_t n2, int nwin, int c) {
 }
 
 cudaError_t launch_big_digits(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, uint32_t n, int c, int nwin, uint32_t *keys,
-                              uint32_t *vals) {
-    k_big_digits<<<(n + 255) / 256, 256, 0, st>>>(pts, scalars, n, c, nwin, keys, vals);
+                              uint32_t *vals, uint32_t *bx) {
+    k_big_digits<<<(n + 255) / 256, 256, 0, st>>>(pts, scalars, n, c, nwin, keys, vals, bx);
     return cudaGetLastError();
 }
 cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, const uint32_t *keys, uint32_t *keys_out, const uint32_t *vals,
@@ -387,8 +427,7 @@ cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, cons
     return cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys, keys_out, vals, vals_out, (size_t)n2 * nwin, 0, c + 4, st);
 }
 cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c, uint32_t *start) {
-    size_t total = (size_t)nwin * n2;
-    k_big_offsets<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys_sorted, n2, nwin, nb, c, start);
+    k_big_offsets<<<dim3((nb + 1 + 255) / 256, (unsigned)nwin), 256, 0, st>>>(keys_sorted, n2, nwin, nb, c, start);
     return cudaGetLastError();
 }
 size_t big_order_temp_bytes(size_t slots) {
@@ -434,6 +473,11 @@ cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const 
     // a level of few nodes is a latency chain: a quad per node; the wide first levels keep one thread per node (same time, a quarter of the lanes)
     if (n_out <= 32768) k_big_reduce_level_quad<<<(unsigned)(((size_t)n_out * 4 + 127) / 128), 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
     else k_big_reduce_level<<<(n_out + 127) / 128, 128, 0, st>>>(Ain, Bin, n_out, g, shift, Aout, Bout);
+    return cudaGetLastError();
+}
+cudaError_t launch_big_reduce_leaf_affine(cudaStream_t st, const uint32_t *bucket_aff, uint32_t n_out, uint32_t g, uint32_t *Aout, uint32_t *Bout) {
+    if (n_out <= 32768) k_big_reduce_leaf_affine<true><<<(unsigned)(((size_t)n_out * 4 + 127) / 128), 128, 0, st>>>(bucket_aff, n_out, g, Aout, Bout);
+    else k_big_reduce_leaf_affine<false><<<(n_out + 127) / 128, 128, 0, st>>>(bucket_aff, n_out, g, Aout, Bout);
     return cudaGetLastError();
 }
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac) {

@@ -93,7 +93,8 @@ cudaError_t launch_sum_groups2(cudaStream_t st, const uint32_t *A, uint32_t per_
 
 // large Pippenger MSM (k_bigmsm.cu)
 size_t big_msm_sort_temp_bytes(uint32_t n2, int nwin, int c);
-cudaError_t launch_big_digits(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, uint32_t n, int c, int nwin, uint32_t *keys, uint32_t *vals);
+cudaError_t launch_big_digits(cudaStream_t st, const uint32_t *pts, const uint32_t *scalars, uint32_t n, int c, int nwin, uint32_t *keys, uint32_t *vals,
+                              uint32_t *bx /* beta x per base, or nullptr */);
 cudaError_t launch_big_sort(cudaStream_t st, void *temp, size_t temp_bytes, const uint32_t *keys, uint32_t *keys_out, const uint32_t *vals,
                             uint32_t *vals_out, uint32_t n2, int nwin, int c, const uint32_t *seg_offsets);
 cudaError_t launch_big_offsets(cudaStream_t st, const uint32_t *keys_sorted, uint32_t n2, int nwin, uint32_t nb, int c, uint32_t *start);
@@ -106,6 +107,16 @@ cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const 
                                     uint32_t *Bout);
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac);
 cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out);
+cudaError_t launch_big_reduce_leaf_affine(cudaStream_t st, const uint32_t *bucket_aff, uint32_t n_out, uint32_t g, uint32_t *Aout, uint32_t *Bout);
+// bucket sums by rounds of batched affine additions (k_batchaff.cu)
+size_t ba_scan_temp_bytes(size_t n);
+constexpr int BA_STATS_ROUNDS = 32;  // k_ba_init writes (additions, elements kept, list length) for up to this many rounds
+cudaError_t launch_ba_init(cudaStream_t st, const uint32_t *start, uint32_t n2, int nwin, uint32_t nb, const uint32_t *pts, const uint32_t *bx,
+                           const uint32_t *vals, uint32_t *act, void *scan_in, uint32_t *bucket_aff, uint32_t *stats);
+cudaError_t launch_ba_round(cudaStream_t st, bool first, void *scan_tmp, size_t scan_tmp_bytes, void *scan_in, void *scan_out, uint32_t list_len,
+                            uint32_t pairs, uint32_t K, const uint32_t *act, uint32_t *nact, size_t act_stride, void *nscan_in, const uint32_t *pts,
+                            const uint32_t *bx, const uint32_t *vals, const uint32_t *in, uint32_t *out, uint32_t *bucket_aff, void *jobs);
+cudaError_t launch_bench_ba(cudaStream_t st, uint32_t *buf, uint32_t T, uint32_t K, bool fill, int inl);
 
 // fixed-base MSM over a precomputed digit table (k_fixed.cu).  Table layout: affine points, 96 B each,
 //   table[(base * nw + w) * nd + (d - 1)] = d * 2^(c w) * B_base      d = 1 .. nd = 2^(c-1),  w < nw = ceil(256 / c)

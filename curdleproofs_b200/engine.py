@@ -72,6 +72,7 @@ _SIGS = {
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
     "cdp_set_big_msm_min": (c_int, [c_void_p, c_size_t]),
+    "cdp_set_big_ba_min": (c_int, [c_void_p, c_size_t]),
     "cdp_host_is_pinned": (c_int, [c_void_p]),
     "cdp_h2d_2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t]),
     "cdp_comm_unique_id": (c_int, [c_void_p]),
@@ -170,6 +171,10 @@ class Engine:
     def set_big_msm_min(self, n_pairs: int):
         """Pairs from which one MSM takes the sort-based large Pippenger on this engine (0 = the built-in 2^16)."""
         self._check(self._lib.cdp_set_big_msm_min(self._h, n_pairs), "cdp_set_big_msm_min")
+
+    def set_big_ba_min(self, n_pairs: int):
+        """Pairs from which the large Pippenger sums its buckets by rounds of batched affine additions (0 = the built-in 2^20)."""
+        self._check(self._lib.cdp_set_big_ba_min(self._h, n_pairs), "cdp_set_big_ba_min")
 
     def sync(self):
         self._check(self._lib.cdp_sync(self._h), "cdp_sync")

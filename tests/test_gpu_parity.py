@@ -185,13 +185,15 @@ def test_generator_kat_through_gpu(engine, oracle):
     assert engine.compress_batch(jac).hex() == want
 
 
-@pytest.fixture(params=["large_path", "chunked_small_path"])
+@pytest.fixture(params=["large_path", "large_path_batched_affine", "chunked_small_path"])
 def msm_path(request, engine):
     """One MSM of 2^13 .. 2^16 pairs through BOTH implementations: the sort-based large Pippenger (k_bigmsm.cu; forced from 2^13 here, the
     default crossover is 2^16) and the chunked small-MSM kernels (the default below 2^16)."""
-    engine.set_big_msm_min(8192 if request.param == "large_path" else 0)
+    engine.set_big_msm_min(8192 if request.param.startswith("large_path") else 0)
+    engine.set_big_ba_min(8192 if request.param == "large_path_batched_affine" else 1 << 30)
     yield request.param
     engine.set_big_msm_min(0)
+    engine.set_big_ba_min(0)
 
 
 @pytest.mark.parametrize("n", [8192, 8192 + 37, 20000])
@@ -230,3 +232,19 @@ def test_msm_large_pippenger_skewed_scalars(engine, oracle, pool, kind, msm_path
         two = pr.fr_to_bytes(pr.R_ORDER - 2)
         sc = b"".join(one if rnd.random() < 0.7 else two for _ in range(n))
     assert oracle.compress_jac(engine.msm(pts, sc)) == oracle.compress_jac(oracle.msm(pts, sc, threads=8))
+
+
+@pytest.mark.parametrize("n", [131072 + 11, 300000, 1 << 20])
+def test_msm_large_pippenger_round_geometry(engine, oracle, n):
+    """The bucket sums of the large path are rounds of batched affine additions (k_batchaff.cu) whose thread count and additions per inversion
+    depend on the round's size: sizes on either side of every regime (K = minimum, K growing with the round, K = maximum), on DISTINCT random
+    subgroup points (multiples of the generator made on the device), bit-exact vs the oracle's `util::msm` (/root/reference/src/util.rs:19-22)."""
+    import numpy as np
+    rng = np.random.Generator(np.random.Philox(key=n))
+    t = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    t[:, 3] &= np.uint64((1 << 62) - 1)
+    s = rng.integers(0, 2 ** 64, size=(n, 4), dtype=np.uint64)
+    s[:, 3] &= np.uint64((1 << 62) - 1)
+    pts = engine.scalar_mul_batch(oracle.generator() * n, t.tobytes())
+    sc = s.tobytes()
+    assert oracle.compress_jac(engine.msm(pts, sc)) == oracle.compress_jac(oracle.msm(pts, sc, threads=16))

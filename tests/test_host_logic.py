@@ -91,9 +91,10 @@ def test_device_verifier_transcript_code_matches_host_transcript_on_cpu():
     assert out.stdout.count(" ok ") == 3
 
 
-def test_device_fp_inversion_euclid_on_cpu():
-    """csrc/fp_inv_euclid.cuh (plain C++; the inversion of `into_affine` / `normalize_batch` on the device) against the oracle's field:
-    a * inverse(a) == 1 mod p for edge values and 3000 pseudo-random ones."""
+def test_device_fp_inversion_on_cpu():
+    """csrc/fp_inv_safegcd.cuh (Bernstein-Yang division steps: the inversion of `into_affine` / `normalize_batch` and of the batched affine
+    additions on the device) and csrc/fp_inv_euclid.cuh (binary Euclid), both plain C++, against each other and the oracle's field:
+    a * inverse(a) == 1 mod p for edge values and 20 000 pseudo-random ones."""
     with tempfile.TemporaryDirectory() as d:
         exe = os.path.join(d, "fpinv")
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
@@ -101,3 +102,13 @@ def test_device_fp_inversion_euclid_on_cpu():
                         "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
         out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "fp inverse ok" in out.stdout, out.stdout
+
+
+def test_device_glv_split_on_cpu():
+    """csrc/glv_split.cuh (plain C++; Barrett division by lambda in front of every device MSM / scalar multiplication): k = k2 lambda + k1 with
+    0 <= k1 < lambda, checked by multiplying back, for edge values and 180 000 pseudo-random scalars below r."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "glv")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/glv_check.cpp")], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "glv split ok" in out.stdout, out.stdout
