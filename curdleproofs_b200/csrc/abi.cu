@@ -632,13 +632,15 @@ static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
     uint32_t h_stats[BA_STATS_ROUNDS * 3];
     CUDA_TRY(ctx, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    // K additions share an inversion (~5 additions' worth of instructions): as many as still leave T_TARGET threads
-    static const uint32_t K_MAX = env_u32("CDP_BA_KMAX", 64), T_TARGET = env_u32("CDP_BA_THREADS", 148 * 3 * 128 * 2);
+    // K additions share an inversion (~5 additions' worth of instructions).  All threads of a round do the same work, so the grid runs in
+    // waves of WAVE resident threads: K is the smallest that packs the round into w FULL waves, w the fewest waves with K <= K_MAX
+    static const uint32_t K_MAX = env_u32("CDP_BA_KMAX", 128), WAVE = env_u32("CDP_BA_WAVE", 148 * 3 * 128);
     uint32_t *sbuf[2] = {(uint32_t *)(ws + o_s0), (uint32_t *)(ws + o_s1)};
     for (int r = 0; r < BA_STATS_ROUNDS && h_stats[3 * r]; r++) {
         const uint32_t pairs = h_stats[3 * r], list_len = r == 0 ? (uint32_t)slots : h_stats[3 * r + 2];
         if (h_stats[3 * r + 1] > ((r & 1) ? s1n : s0n)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm: round buffer too small");  // cannot happen: sized for the worst case
-        const uint32_t K = std::min(K_MAX, std::max(1u, (pairs + T_TARGET - 1) / T_TARGET));
+        const uint32_t waves = std::max(1u, (uint32_t)(((uint64_t)pairs + (uint64_t)K_MAX * WAVE - 1) / ((uint64_t)K_MAX * WAVE)));
+        const uint32_t K = std::max(1u, (uint32_t)(((uint64_t)pairs + (uint64_t)waves * WAVE - 1) / ((uint64_t)waves * WAVE)));
         launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, r == 0 ? (uint64_t)n : 0);
         CUDA_TRY(ctx, launch_ba_round(ctx->stream, r == 0, ws + o_scan_tmp, scan_tmp, sc[r & 1], ws + o_incl, list_len, pairs, K, act[r & 1], act[(r + 1) & 1],
                                       slots, sc[(r + 1) & 1], P, bx, vals2, sbuf[(r + 1) & 1], sbuf[r & 1], baff, ws + o_jobs));
@@ -1020,6 +1022,27 @@ extern "C" int cdp_msm_fixed_batch_dev_lanes(cdp_ctx *ctx, const cdp_fixed_table
     CUDA_TRY(ctx, launch_fixed_msm(ctx->stream, t->d_table, reinterpret_cast<const uint32_t *>(d_scalars), reinterpret_cast<const fixed_seg_t *>(d_segs),
                                    (uint32_t)count, t->kp, reinterpret_cast<const uint32_t *>(d_var_pts), reinterpret_cast<uint32_t *>(d_out_jac),
                                    lanes_per_segment ? lanes_per_segment : 32));
+    return CDP_OK;
+}
+// The same sums as a tree of batched affine additions (k_fixed.cu): for launches of many long segments.  CDP_FIXED_TREE_ROUNDS (default 5),
+// CDP_FIXED_TREE_KMAX (64) and CDP_FIXED_TREE_THREADS are tuning knobs.
+extern "C" int cdp_msm_fixed_batch_dev_tree(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                                            size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac, size_t max_pairs_per_segment) {
+    if (!ctx || !t || (count && (!d_scalars || !d_segs || !d_out_jac))) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev_tree: null argument");
+    if (count == 0) return CDP_OK;
+    if (t->device != ctx->device) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev_tree: table lives on another device");
+    static const int rounds = (int)env_u32("CDP_FIXED_TREE_ROUNDS", 5);
+    static const uint32_t kmax = env_u32("CDP_FIXED_TREE_KMAX", 128), t_target = env_u32("CDP_FIXED_TREE_WAVE", 148 * 3 * 128);
+    if (max_pairs_per_segment == 0 || max_pairs_per_segment * (size_t)t->kp.nw < (size_t(4) << rounds) ||
+        count * (max_pairs_per_segment * (size_t)t->kp.nw + 64) >= (size_t(1) << 30))  // too short for a tree (or too many slots for 30-bit job numbers): the lane kernel
+        return cdp_msm_fixed_batch_dev_lanes(ctx, t, d_scalars, d_segs, count, total_pairs, d_var_pts, d_out_jac, 32);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    TRY(ensure_dev(ctx, ctx->d_big, fixed_ba_scratch_bytes((uint32_t)count, (uint32_t)max_pairs_per_segment, t->kp.nw, rounds)));
+    launch_scope ls(ctx, CDP_PROFILE_MSM_FIXED, total_pairs);
+    CUDA_TRY(ctx, launch_fixed_msm_ba(ctx->stream, t->d_table, reinterpret_cast<const uint32_t *>(d_scalars), reinterpret_cast<const fixed_seg_t *>(d_segs),
+                                      (uint32_t)count, t->kp, reinterpret_cast<const uint32_t *>(d_var_pts), reinterpret_cast<uint32_t *>(d_out_jac),
+                                      (uint32_t)max_pairs_per_segment, rounds, (uint32_t *)ctx->d_big.ptr, t_target, kmax));
+    ctx->launches += (uint64_t)rounds;
     return CDP_OK;
 }
 extern "C" int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,

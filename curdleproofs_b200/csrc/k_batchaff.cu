@@ -155,22 +155,31 @@ __global__ void __launch_bounds__(256) k_ba_jobs(const ba_scan_t *__restrict__ i
                                                  const uint32_t *__restrict__ act_m, const uint32_t *__restrict__ act_id, In in, uint32_t *__restrict__ out,
                                                  uint4 *__restrict__ jobs, uint32_t *__restrict__ nact_pos, uint32_t *__restrict__ nact_m,
                                                  uint32_t *__restrict__ nact_id, ba_scan_t *__restrict__ nscan_in) {
+    // BA_JOBS_PER_THREAD consecutive pairs per thread: one binary search for the first, then a walk along the list (every listed bucket has a pair)
+    const uint32_t q0 = (blockIdx.x * blockDim.x + threadIdx.x) * BA_JOBS_PER_THREAD;
+    if (q0 >= total) return;
+    uint32_t lo = 0, hi = bound - 1;  // smallest a with incl[a].p > q0
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (incl[mid].p > q0) hi = mid;
+        else lo = mid + 1;
+    }
+    uint32_t a = lo;
+    ba_scan_t sc = incl[a];
+    uint32_t m = act_m[a], pos = act_pos[a], id = act_id[a];
 #pragma unroll 1
-    for (int rep = 0; rep < BA_JOBS_PER_THREAD; rep++) {  // several pairs per thread: a CTA per 256 pairs is bound by the CTA launch rate
-        const uint32_t q = (blockIdx.x * BA_JOBS_PER_THREAD + rep) * blockDim.x + threadIdx.x;
-        if (q >= total) return;
-        uint32_t lo = 0, hi = bound - 1;  // smallest a with incl[a].p > q
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (incl[mid].p > q) hi = mid;
-            else lo = mid + 1;
+    for (uint32_t q = q0; q < q0 + BA_JOBS_PER_THREAD && q < total; q++) {
+        while (sc.p <= q) {  // next bucket with a pair (entries without one -- round 0 lists every bucket -- repeat the count)
+            a++;
+            sc = incl[a];
+            m = act_m[a];
+            pos = act_pos[a];
+            id = act_id[a];
         }
-        const uint32_t a = lo, m = act_m[a], p = m / 2;
-        const ba_scan_t sc = incl[a];
-        const uint32_t j = q - (sc.p - p), src = act_pos[a] + 2 * j;
+        const uint32_t p = m / 2, j = q - (sc.p - p), src = pos + 2 * j;
         const uint2 ops = in.operands(src);
         if (m == 2) {
-            jobs[q] = make_uint4(ops.x, ops.y, BA_FINAL | act_id[a], 0u);
+            jobs[q] = make_uint4(ops.x, ops.y, BA_FINAL | id, 0u);
             continue;
         }
         const uint32_t keep = (m + 1) / 2, oex = sc.o - keep;
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(256) k_ba_jobs(const ba_scan_t *__restrict__ i
             const uint32_t nx = sc.nxt - 1;
             nact_pos[nx] = oex;
             nact_m[nx] = keep;
-            nact_id[nx] = act_id[a];
+            nact_id[nx] = id;
             nscan_in[nx] = ba_plan_of(keep);
         }
     }

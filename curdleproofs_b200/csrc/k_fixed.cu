@@ -9,8 +9,11 @@
 //   entries 96 bytes apart, or 128 -- one DRAM line per gathered entry -- with CDP_FIXED_STRIDE=128)
 // so one (scalar, base) pair costs nw = 16 mixed additions -- gathered 96-byte reads, no buckets, no doublings, no window
 // combine -- instead of ~52 bucket additions plus the bucket reduction of the variable-base kernel.
+#include <algorithm>
+
 #include "launch.h"
 #include "msm_common.cuh"
+#include "batch_affine.cuh"
 
 namespace cdp {
 
@@ -137,6 +140,31 @@ __device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint
     return (int)(v < kp.nd ? v : kp.nd);  // canonical scalars never exceed nd here; the clamp only keeps a non-canonical one in bounds
 }
 
+// Table entry of item q = (pair q / nw, window q % nw) of a segment: nullptr when its digit is zero, else the entry's address and the digit's sign.
+__device__ __forceinline__ const uint32_t *fixed_locate(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars, const fixed_seg_t &seg,
+                                                        const fixed_kparams_t &kp, uint32_t q, bool &neg) {
+    const uint32_t i = q / (uint32_t)kp.nw, w = q - i * (uint32_t)kp.nw;
+    uint32_t bidx, sidx2;
+    if (i < seg.n) {
+        uint32_t j = i;
+        if (seg.sel_h) {
+            const uint32_t lo = i & (seg.sel_h - 1);
+            j = ((i - lo) << 1) | lo | seg.sel_val;
+        }
+        sidx2 = seg.scalars_off + j;
+        const uint32_t pj = seg.pos_off + j * (seg.pos_stride ? seg.pos_stride : 1u);
+        bidx = seg.base_off + pj + (pj >= seg.remap_from ? seg.remap_delta : 0u);
+    } else {
+        bidx = seg.extra_base - 1;
+        sidx2 = seg.scalars_off + seg.extra_scalar;
+    }
+    const int d = fixed_digit(scalars + 8 * (size_t)sidx2, w, kp);
+    if (d == 0) return nullptr;
+    neg = d < 0;
+    const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
+    return table + (size_t)kp.es * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1));
+}
+
 // One warp per segment.  Work item q = (pair i, window w) = (q / nw, q % nw); lane l takes items l, l + 32, ...; every item is one
 // gathered 96-byte table read and one mixed addition into the lane's Jacobian accumulator; the next item's point is fetched before the
 // current addition is issued, so the HBM gather latency (~1 us) hides behind ~3300 integer instructions.  The 32 partial sums are
@@ -144,7 +172,8 @@ __device__ __forceinline__ int fixed_digit(const uint32_t *__restrict__ sp, uint
 template <int OCC, bool EXPANDED = false>
 __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restrict__ table, const uint32_t *__restrict__ scalars,
                                                        const fixed_seg_t *__restrict__ segs, uint32_t count, const fixed_kparams_t kp,
-                                                       const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac, uint32_t lg) {
+                                                       const uint32_t *__restrict__ var_pts, uint32_t *__restrict__ out_jac, uint32_t lg,
+                                                       const uint32_t *__restrict__ arr = nullptr, uint32_t arr_n = 0) {
     // G = 2^lg lanes per segment (32: a warp per segment).  With many segments in flight fewer lanes per segment mean longer per-lane chains
     // and fewer fold steps: the 5 full additions of a 32-lane fold are ~12 % of a 129-pair segment's work, the 3 of an 8-lane fold ~2 %.
     const uint32_t G = 1u << lg, gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -157,29 +186,18 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm(const uint32_t *__restri
         seg.n = 0; seg.extra_base = 0; seg.addv_n = 0; seg.base_off = 0; seg.scalars_off = 0; seg.sel_h = 0; seg.sel_val = 0;
         seg.remap_from = 0xFFFFFFFFu; seg.remap_delta = 0; seg.extra_scalar = 0; seg.out_idx = 0; seg.addv_off = 0; seg.pos_off = 0; seg.pos_stride = 0;
     }
-    const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
-    // returns true and the (un-negated) table point when item q has a non-zero digit
+    // arr: the segment's table points were already summed down to arr_n partial sums per segment by the batched affine rounds below
+    const uint32_t items = !active ? 0u : arr ? arr_n : (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
+    // returns true and the (un-negated) point of item q when there is one (non-zero digit / partial sum not at infinity)
     auto fetch = [&](uint32_t q, g1a &P, bool &neg) -> bool {
-        const uint32_t i = q / (uint32_t)kp.nw, w = q - i * (uint32_t)kp.nw;
-        uint32_t bidx, sidx2;
-        if (i < seg.n) {
-            uint32_t j = i;
-            if (seg.sel_h) {
-                const uint32_t lo = i & (seg.sel_h - 1);
-                j = ((i - lo) << 1) | lo | seg.sel_val;
-            }
-            sidx2 = seg.scalars_off + j;
-            const uint32_t pj = seg.pos_off + j * (seg.pos_stride ? seg.pos_stride : 1u);
-            bidx = seg.base_off + pj + (pj >= seg.remap_from ? seg.remap_delta : 0u);
-        } else {
-            bidx = seg.extra_base - 1;
-            sidx2 = seg.scalars_off + seg.extra_scalar;
+        if (arr) {
+            g1a_load(P, arr + 24 * ((size_t)sidx * arr_n + q));
+            neg = false;
+            return !g1a_is_inf(P);
         }
-        const int d = fixed_digit(scalars + 8 * (size_t)sidx2, w, kp);
-        if (d == 0) return false;
-        neg = d < 0;
-        const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-        g1a_load(P, table + (size_t)kp.es * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1)));
+        const uint32_t *e = fixed_locate(table, scalars, seg, kp, q, neg);
+        if (!e) return false;
+        g1a_load(P, e);
         return true;
     };
     g1j acc;
@@ -278,29 +296,7 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm_bulk(const uint32_t *__r
     if (warp >= count) return;
     const fixed_seg_t seg = segs[warp];
     const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
-    // address of the table entry of item q (nullptr: zero digit) and the sign of its digit
-    auto locate = [&](uint32_t q, bool &neg) -> const uint32_t * {
-        const uint32_t i = q / (uint32_t)kp.nw, w = q - i * (uint32_t)kp.nw;
-        uint32_t bidx, sidx;
-        if (i < seg.n) {
-            uint32_t j = i;
-            if (seg.sel_h) {
-                const uint32_t lo = i & (seg.sel_h - 1);
-                j = ((i - lo) << 1) | lo | seg.sel_val;
-            }
-            sidx = seg.scalars_off + j;
-            const uint32_t pj = seg.pos_off + j * (seg.pos_stride ? seg.pos_stride : 1u);
-            bidx = seg.base_off + pj + (pj >= seg.remap_from ? seg.remap_delta : 0u);
-        } else {
-            bidx = seg.extra_base - 1;
-            sidx = seg.scalars_off + seg.extra_scalar;
-        }
-        const int d = fixed_digit(scalars + 8 * (size_t)sidx, w, kp);
-        if (d == 0) return nullptr;
-        neg = d < 0;
-        const uint32_t ad = (uint32_t)(d < 0 ? -d : d);
-        return table + (size_t)kp.es * (((size_t)bidx * kp.nw + w) * kp.nd + (ad - 1));
-    };
+    auto locate = [&](uint32_t q, bool &neg) -> const uint32_t * { return fixed_locate(table, scalars, seg, kp, q, neg); };
     g1j acc;
     g1j_set_inf(acc);
     bool cur_neg = false, have = false;
@@ -356,6 +352,87 @@ __global__ void __launch_bounds__(128, OCC) k_fixed_msm_bulk(const uint32_t *__r
     if (lane == 0) g1j_store(out_jac + 36 * (size_t)seg.out_idx, acc);
 }
 
+// ---- the sum of a segment's table points as a tree of batched affine additions (batch_affine.cuh: 5M + 1S each instead of the 8M + 2S of
+// the XYZZ accumulator above).  Every segment owns `ipad` item slots (its items, padded with "absent" to a multiple of 2^rounds); round 0
+// adds items 2t and 2t + 1 of a segment straight from the table, round r the neighbours of round r - 1's output -- flat arrays, halving, no
+// index structure at all -- and k_fixed_msm (array source) sums the ipad / 2^rounds partial sums left per segment, plus the plain points.
+struct fixed_ba_src {
+    const uint32_t *table, *scalars;
+    const fixed_seg_t *segs;
+    fixed_kparams_t kp;
+    uint32_t half_ipad;  // jobs per segment
+    uint32_t *out;
+    struct ref {
+        const uint32_t *p, *q;  // table entries (nullptr: absent); the sign bits ride in the destination index
+        uint32_t d;
+    };
+    __device__ __forceinline__ ref resolve(uint32_t job) const {
+        const uint32_t sidx = job / half_ipad, t = job - sidx * half_ipad;
+        const fixed_seg_t seg = segs[sidx];
+        const uint32_t items = (seg.n + (seg.extra_base ? 1u : 0u)) * (uint32_t)kp.nw;
+        bool n0 = false, n1 = false;
+        ref r;
+        r.p = 2 * t < items ? fixed_locate(table, scalars, seg, kp, 2 * t, n0) : nullptr;
+        r.q = 2 * t + 1 < items ? fixed_locate(table, scalars, seg, kp, 2 * t + 1, n1) : nullptr;
+        r.d = job | (n0 ? 0x80000000u : 0u) | (n1 ? 0x40000000u : 0u);
+        return r;
+    }
+    __device__ __forceinline__ uint32_t *dst(const ref &r) const { return out + 24 * (size_t)(r.d & 0x3FFFFFFFu); }
+    __device__ __forceinline__ void prefetch_x(const ref &r) const {
+        if (r.p) prefetch_fp(r.p);
+        if (r.q) prefetch_fp(r.q);
+    }
+    __device__ __forceinline__ void prefetch(const ref &r) const {
+        if (r.p) prefetch_g1a(r.p);
+        if (r.q) prefetch_g1a(r.q);
+    }
+    __device__ __forceinline__ void load_x(const ref &r, fp &px, fp &qx) const {
+        fp_set_zero(px);
+        fp_set_zero(qx);
+        if (r.p) fp_load(px, r.p);
+        if (r.q) fp_load(qx, r.q);
+    }
+    __device__ __forceinline__ void load(const ref &r, g1a &P, g1a &Q) const {
+        g1a_set_inf(P);
+        g1a_set_inf(Q);
+        if (r.p) {
+            g1a_load(P, r.p);
+            if (r.d & 0x80000000u) fp_neg(P.y, P.y);
+        }
+        if (r.q) {
+            g1a_load(Q, r.q);
+            if (r.d & 0x40000000u) fp_neg(Q.y, Q.y);
+        }
+    }
+};
+struct fixed_ba_arr_src {
+    const uint32_t *in;
+    uint32_t *out;
+    typedef uint32_t ref;
+    __device__ __forceinline__ ref resolve(uint32_t q) const { return q; }
+    __device__ __forceinline__ uint32_t *dst(ref q) const { return out + 24 * (size_t)q; }
+    __device__ __forceinline__ void prefetch_x(ref) const {}
+    __device__ __forceinline__ void prefetch(ref) const {}
+    __device__ __forceinline__ void load_x(ref q, fp &px, fp &qx) const {
+        fp_load(px, in + 48 * (size_t)q);
+        fp_load(qx, in + 48 * (size_t)q + 24);
+    }
+    __device__ __forceinline__ void load(ref q, g1a &P, g1a &Q) const {
+        g1a_load(P, in + 48 * (size_t)q);
+        g1a_load(Q, in + 48 * (size_t)q + 24);
+    }
+};
+__global__ void __launch_bounds__(128, 3) k_fixed_ba_first(fixed_ba_src src, uint32_t total, uint32_t K, uint32_t pf) {
+    const uint32_t T = (total + K - 1) / K, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= T) return;
+    ba_run<fixed_ba_src, 3>(src, tid, T, total, K, pf);
+}
+__global__ void __launch_bounds__(128, 3) k_fixed_ba_next(fixed_ba_arr_src src, uint32_t total, uint32_t K) {
+    const uint32_t T = (total + K - 1) / K, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= T) return;
+    ba_run<fixed_ba_arr_src, 3>(src, tid, T, total, K);
+}
+
 cudaError_t launch_fixed_pow(cudaStream_t st, const uint32_t *bases_affine, uint32_t n_bases, int c, int nw, uint32_t *jac_out) {
     k_fixed_pow<<<(n_bases + 63) / 64, 64, 0, st>>>(bases_affine, n_bases, c, nw, jac_out);
     return cudaGetLastError();
@@ -394,6 +471,41 @@ cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint3
     if (occ == 5) k_fixed_msm<5><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
     else if (occ == 4) k_fixed_msm<4><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
     else k_fixed_msm<3><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg);
+    return cudaGetLastError();
+}
+
+// scratch words needed by launch_fixed_msm_ba: round 0 writes count * ipad / 2 points, round 1 half of that (ping-pong from there on)
+uint32_t fixed_ba_ipad(uint32_t max_pairs, int nw, int rounds) { return ((max_pairs * (uint32_t)nw + (1u << rounds) - 1) >> rounds) << rounds; }
+size_t fixed_ba_scratch_bytes(uint32_t count, uint32_t max_pairs, int nw, int rounds) {
+    const size_t ipad = fixed_ba_ipad(max_pairs, nw, rounds);
+    return ((size_t)count * ipad / 2 + (size_t)count * ipad / 4) * 96;
+}
+cudaError_t launch_fixed_msm_ba(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
+                                const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac, uint32_t max_pairs, int rounds, uint32_t *scratch,
+                                uint32_t t_target, uint32_t kmax) {
+    if (count == 0) return cudaSuccess;
+    const uint32_t ipad = fixed_ba_ipad(max_pairs, kp.nw, rounds);
+    uint32_t *buf[2] = {scratch, scratch + (size_t)count * (ipad / 2) * 24};
+    // all threads of a round do the same work: K packs the round into w full waves of t_target resident threads, w the fewest with K <= kmax
+    auto k_for = [&](uint32_t pairs) {
+        const uint64_t w = std::max<uint64_t>(1, ((uint64_t)pairs + (uint64_t)kmax * t_target - 1) / ((uint64_t)kmax * t_target));
+        return std::max(4u, (uint32_t)((pairs + w * t_target - 1) / (w * t_target)));
+    };
+    uint32_t pairs = count * (ipad / 2);
+    {
+        const uint32_t K = k_for(pairs), T = (pairs + K - 1) / K;
+        static const uint32_t pf = getenv("CDP_FIXED_TREE_PF") ? (uint32_t)atoi(getenv("CDP_FIXED_TREE_PF")) : 0u;
+        k_fixed_ba_first<<<(T + 127) / 128, 128, 0, st>>>(fixed_ba_src{table, scalars, segs, kp, ipad / 2, buf[0]}, pairs, K, pf);
+    }
+    for (int r = 1; r < rounds; r++) {
+        pairs >>= 1;
+        const uint32_t K = k_for(pairs), T = (pairs + K - 1) / K;
+        k_fixed_ba_next<<<(T + 127) / 128, 128, 0, st>>>(fixed_ba_arr_src{buf[(r + 1) & 1], buf[r & 1]}, pairs, K);
+    }
+    // ipad >> rounds partial sums per segment, plus its plain points, by 8 lanes per segment
+    const uint32_t left = ipad >> rounds, lg = left > 256 ? 4u : 3u;
+    const unsigned blocks = (unsigned)((((size_t)count << lg) + 127) / 128);
+    k_fixed_msm<3><<<blocks, 128, 0, st>>>(table, scalars, segs, count, kp, var_pts, out_jac, lg, buf[(rounds + 1) & 1], left);
     return cudaGetLastError();
 }
 

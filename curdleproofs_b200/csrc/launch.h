@@ -147,6 +147,11 @@ cudaError_t launch_fixed_seed(cudaStream_t st, const uint32_t *aff, uint32_t cha
 cudaError_t launch_fixed_level(cudaStream_t st, uint32_t *table, uint32_t chains, uint32_t nd, uint32_t half, uint32_t es);
 cudaError_t launch_fixed_msm(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
                              const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac, int lanes_per_seg = 32);
+// the same sums as a tree of batched affine additions: `rounds` halving rounds, then the lane kernel over what is left (k_fixed.cu)
+size_t fixed_ba_scratch_bytes(uint32_t count, uint32_t max_pairs, int nw, int rounds);
+cudaError_t launch_fixed_msm_ba(cudaStream_t st, const uint32_t *table, const uint32_t *scalars, const fixed_seg_t *segs, uint32_t count,
+                                const fixed_kparams_t &kp, const uint32_t *var_pts, uint32_t *out_jac, uint32_t max_pairs, int rounds, uint32_t *scratch,
+                                uint32_t t_target, uint32_t kmax);
 
 // which: 0 = raw IMAD.WIDE chains (128 multiply-adds / thread / iteration), 1 = Fp mul chain, 2 = Fp sqr chain (1 / thread / iteration)
 cudaError_t launch_bench(cudaStream_t st, int which, uint32_t *out, int blocks, int threads, int iters);

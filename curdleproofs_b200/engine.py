@@ -60,6 +60,7 @@ _SIGS = {
     "cdp_fixed_table_bases": (c_size_t, [c_void_p]),
     "cdp_msm_fixed": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "cdp_msm_fixed_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "cdp_msm_fixed_batch_dev_tree": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t]),
     "cdp_profile_enable": (c_int, [c_void_p, c_int]),
     "cdp_profile_reset": (c_int, [c_void_p]),
     "cdp_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(c_uint64)]),
@@ -303,8 +304,9 @@ class Engine:
         self._check(self._lib.cdp_msm_fixed(self._h, table.handle, base_off, _buf(scalars) if n else None, n, out), "cdp_msm_fixed")
         return bytes(out)
 
-    def msm_fixed_batch(self, table: "FixedTable", scalars: bytes, segs: list, var_pts: bytes = b"") -> list[bytes]:
-        """A batch of cdp_fixed_seg segments over one scalar array (host convenience over cdp_msm_fixed_batch_dev)."""
+    def msm_fixed_batch(self, table: "FixedTable", scalars: bytes, segs: list, var_pts: bytes = b"", tree_max_pairs: int = 0) -> list[bytes]:
+        """A batch of cdp_fixed_seg segments over one scalar array (host convenience over cdp_msm_fixed_batch_dev); with
+        ``tree_max_pairs`` (>= the longest segment, extra pair included) through cdp_msm_fixed_batch_dev_tree."""
         lib, h = self._lib, self._h
         n_out = max(s.out_idx for s in segs) + 1
         arr = (FixedSeg * len(segs))(*segs)
@@ -320,7 +322,10 @@ class Engine:
                 vb = _buf(var_pts)
                 self._check(lib.cdp_h2d(h, d_vp, vb, len(var_pts)), "cdp_h2d")
             self.sync()
-            self._check(lib.cdp_msm_fixed_batch_dev(h, table.handle, d_sc, d_sg, len(segs), 0, d_vp, d_out), "cdp_msm_fixed_batch_dev")
+            if tree_max_pairs:
+                self._check(lib.cdp_msm_fixed_batch_dev_tree(h, table.handle, d_sc, d_sg, len(segs), 0, d_vp, d_out, tree_max_pairs), "cdp_msm_fixed_batch_dev_tree")
+            else:
+                self._check(lib.cdp_msm_fixed_batch_dev(h, table.handle, d_sc, d_sg, len(segs), 0, d_vp, d_out), "cdp_msm_fixed_batch_dev")
             out = (ctypes.c_uint8 * (n_out * JACOBIAN_BYTES))()
             self._check(lib.cdp_d2h(h, out, d_out, n_out * JACOBIAN_BYTES), "cdp_d2h")
             self.sync()

@@ -383,6 +383,19 @@ int upload_tables(Lane *p) {
 // lanes of a warp per fixed-base segment: 16 for a launch of many equally long segments (measured, 4096 proofs over 8 lanes: 731 vs 745 ms
 // per step; 8 lanes per segment: 756 ms), a whole warp otherwise
 int fixed_lanes(const SubLaunch &sl, size_t B) { return sl.uniform && B * sl.K >= 2048 ? 16 : 32; }
+// a launch of many equally long segments sums its table points as a tree of batched affine additions (cdp_msm_fixed_batch_dev_tree);
+// CDP_FIXED_TREE=0 keeps the lane kernel, CDP_FIXED_TREE_MIN_SEGS / _MIN_PAIRS move the thresholds
+bool fixed_tree(const SubLaunch &sl, size_t B) {
+    static const int on = [] { const char *e = getenv("CDP_FIXED_TREE"); return e ? atoi(e) : 1; }();
+    static const size_t min_segs = [] { const char *e = getenv("CDP_FIXED_TREE_MIN_SEGS"); return e ? (size_t)atol(e) : (size_t)512; }();
+    static const size_t min_pairs = [] { const char *e = getenv("CDP_FIXED_TREE_MIN_PAIRS"); return e ? (size_t)atol(e) : (size_t)64; }();
+    return on && sl.uniform && sl.max_n >= min_pairs && B * sl.K >= min_segs;
+}
+int launch_fixed_sub(Lane *p, const SubLaunch &sl, size_t B, size_t out_off) {
+    if (fixed_tree(sl, B))
+        return cdp_msm_fixed_batch_dev_tree(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144, sl.max_n);
+    return cdp_msm_fixed_batch_dev_lanes(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144, fixed_lanes(sl, B));
+}
 
 // ---- running a stage -----------------------------------------------------------------------------------------
 // scalars for all proofs are already in p->h_scal (proof-major, st.scalars_per_proof each)
@@ -402,7 +415,7 @@ int run_msm_stage(Lane *p, MsmStage &st, size_t B, double &t_wait, double &t_cop
     }
     size_t out_off = 0;
     for (auto &sl : st.subs) {
-        if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev_lanes(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144, fixed_lanes(sl, B)));
+        if (sl.fixed) PTRY(launch_fixed_sub(p, sl, B, out_off));
         else PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
         out_off += B * sl.K;
     }
@@ -714,7 +727,7 @@ uint32_t out_map_entry(const MsmStage &st, size_t q) {
 int enqueue_msm_stage(Lane *p, MsmStage &st, size_t B) {
     size_t out_off = 0;
     for (auto &sl : st.subs) {
-        if (sl.fixed) PTRY(cdp_msm_fixed_batch_dev_lanes(p->ctx, p->table, p->d_scal, sl.d_fsegs, B * sl.K, B * sl.pairs_per_proof, p->d_pts, p->d_jac + out_off * 144, fixed_lanes(sl, B)));
+        if (sl.fixed) PTRY(launch_fixed_sub(p, sl, B, out_off));
         else PTRY(cdp_msm_batch_dev(p->ctx, p->d_pts, p->d_scal, sl.d_segs, B * sl.K, sl.max_n, B * sl.pairs_per_proof, p->d_jac + out_off * 144));
         out_off += B * sl.K;
     }

@@ -194,6 +194,12 @@ int cdp_msm_fixed_batch_dev(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_
  * equally long segments are in flight (longer per-lane addition chains, fewer fold steps per segment). */
 int cdp_msm_fixed_batch_dev_lanes(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
                                   size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac, int lanes_per_segment);
+/* The same batch with every segment's table points summed as a TREE of batched affine additions (5M + 1S each, one shared inversion per
+ * thread, against 8M + 2S for the lane accumulators): a few halving rounds over all segments at once, then the lane kernel over the partial
+ * sums that are left.  For launches of many long segments; `max_pairs_per_segment` (the extra pair included) sizes the scratch and the
+ * padding -- segments may be shorter.  Short segments fall back to cdp_msm_fixed_batch_dev_lanes.  Same results, bit for bit. */
+int cdp_msm_fixed_batch_dev_tree(cdp_ctx *ctx, const cdp_fixed_table *t, const uint8_t *d_scalars, const cdp_fixed_seg *d_segs, size_t count,
+                                 size_t total_pairs, const uint8_t *d_var_pts, uint8_t *d_out_jac, size_t max_pairs_per_segment);
 
 /* Batched scalar multiplication / fold over device-resident points.  For every job j and element e < elems_per_job:
  *   d_pts[out_off + e] = ( (add_off != CDP_NONE ? d_pts[add_off + e] : O)

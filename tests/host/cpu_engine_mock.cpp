@@ -139,6 +139,10 @@ int cdp_msm_fixed_batch_dev_lanes(cdp_ctx *c, const cdp_fixed_table *t, const ui
                                   const uint8_t *var_pts, uint8_t *out_jac, int) {
     return cdp_msm_fixed_batch_dev(c, t, sc, segs, count, pairs, var_pts, out_jac);
 }
+int cdp_msm_fixed_batch_dev_tree(cdp_ctx *c, const cdp_fixed_table *t, const uint8_t *sc, const cdp_fixed_seg *segs, size_t count, size_t pairs,
+                                 const uint8_t *var_pts, uint8_t *out_jac, size_t) {
+    return cdp_msm_fixed_batch_dev(c, t, sc, segs, count, pairs, var_pts, out_jac);
+}
 int cdp_msm_batch_dev(cdp_ctx *c, const uint8_t *pts, const uint8_t *sc, const cdp_msm_seg *segs, size_t count, size_t, size_t, uint8_t *out_jac) {
     c->launches++;
     for (size_t s = 0; s < count; s++) {

@@ -116,3 +116,54 @@ def test_fixed_segments_select_remap_extra(engine, oracle, bases, table):
     got = engine.msm_fixed_batch(table, sc, segs, var)
     for i, (g, w) in enumerate(zip(got, want)):
         assert oracle.compress_jac(g) == oracle.compress_jac(w), i
+
+
+def test_fixed_tree_of_batched_affine_additions(engine, oracle, bases, table):
+    """cdp_msm_fixed_batch_dev_tree: the table points of every segment summed as a tree of batched affine additions (k_fixed.cu), against the
+    oracle's `util::msm` (/root/reference/src/util.rs:19-22): segments of unequal length (shorter than the padding), an extra pair, half
+    selection, plain points, scalars with zero digits / all-equal / 0 / r - 1, an empty segment, and the lane-kernel fallback for short ones."""
+    from curdleproofs_b200 import FixedSeg
+    rnd = random.Random(8)
+    nb = len(bases) // 96
+    n = min(nb - 1, 40)
+    vals = [rnd.randrange(pr.R_ORDER) for _ in range(n + 2)]
+    vals[3] = 0
+    vals[4] = pr.R_ORDER - 1
+    vals[5] = 1 << 16
+    vals[6] = (1 << 200) + 5          # long runs of zero digits
+    vals[7] = vals[8] = vals[9]       # equal scalars on different bases
+    sc = b"".join(pr.fr_to_bytes(v) for v in vals)
+    var = bases[96 * 2:96 * 5]
+
+    def want_of(idx, extra=None, addv=b""):
+        p = b"".join(bases[96 * i:96 * i + 96] for i in idx)
+        s = b"".join(sc[32 * i:32 * i + 32] for i in idx)
+        if extra is not None:
+            p += bases[96 * extra[0]:96 * extra[0] + 96]
+            s += sc[32 * extra[1]:32 * extra[1] + 32]
+        p += addv
+        s += pr.fr_to_bytes(1) * (len(addv) // 96)
+        return oracle.msm(p, s) if p else None
+
+    segs, want = [], []
+    def add(**kw):
+        base = dict(base_off=0, scalars_off=0, n=0, sel_h=0, sel_val=0, remap_from=0xFFFFFFFF, remap_delta=0, extra_base=0, extra_scalar=0,
+                    out_idx=len(segs))
+        base.update(kw)
+        segs.append(FixedSeg(**base))
+    add(n=n); want.append(want_of(range(n)))
+    add(n=n - 1, extra_base=1 + 2, extra_scalar=n + 1); want.append(want_of(range(n - 1), extra=(2, n + 1)))
+    add(n=n // 2, sel_h=4, sel_val=4); want.append(want_of([j for j in range(n) if j & 4][:n // 2]))
+    add(n=17, addv_off=0, addv_n=3); want.append(want_of(range(17), addv=var))
+    add(n=0); want.append(None)
+    add(n=1, scalars_off=3); want.append(None)   # scalar 0 on base 0: infinity
+    for mp in (n, n + 7):
+        got = engine.msm_fixed_batch(table, sc, segs, var, tree_max_pairs=mp)
+        for i, (g, w) in enumerate(zip(got, want)):
+            if w is None:
+                assert pr.jacobian_from_bytes(g) is pr.INF, i
+            else:
+                assert oracle.compress_jac(g) == oracle.compress_jac(w), (mp, i)
+    # fewer than 4 * 2^rounds items per segment: served by the lane kernel
+    got = engine.msm_fixed_batch(table, sc, segs[3:4], var, tree_max_pairs=1)
+    assert oracle.compress_jac(got[3]) == oracle.compress_jac(want[3])

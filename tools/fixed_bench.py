@@ -48,5 +48,17 @@ for (B, K, n) in ((1024, 4, 128), (128, 4, 128), (1024, 5, 256), (128, 5, 256), 
     ms = p["ms"] / p["launches"]
     nw = (256 + bits - 1) // bits
     print(f"B={B} K={K} n={n}: {ms:.3f} ms/launch, {nsc / ms / 1e3:.2f} M pairs/s, {nsc * nw / ms / 1e6:.3f} G adds/s")
+    # the same batch as a tree of batched affine additions
+    for it in range(2):
+        lib.cdp_msm_fixed_batch_dev_tree(h, tab.handle, d_sc, d_sg, B * K, nsc, None, d_out, n)
+    eng.sync()
+    eng.profile_reset(); eng.profile_enable(True)
+    for it in range(5):
+        lib.cdp_msm_fixed_batch_dev_tree(h, tab.handle, d_sc, d_sg, B * K, nsc, None, d_out, n)
+    eng.sync()
+    p = eng.profile_read()["msm_fixed"]
+    eng.profile_enable(False)
+    ms = p["ms"] / p["launches"]
+    print(f"   tree: {ms:.3f} ms/launch, {nsc / ms / 1e3:.2f} M pairs/s, {nsc * nw / ms / 1e6:.3f} G adds/s")
     for d in (d_sc, d_sg, d_out):
         lib.cdp_dev_free(h, d)
