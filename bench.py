@@ -33,6 +33,9 @@ GX = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF
 GY = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
 README_PROOFS_PER_S = 1.0 / 0.560  # reference README.md:49, ell = 252 proving on an i7-8550U
 IMAD_PER_MIXED_ADD = 8 * 288 + 2 * 222  # XYZZ accumulator + affine point: 8 products, 2 squarings
+IMAD_PER_AFFINE_ADD = 5 * 288 + 222     # batched affine addition: 5 products, 1 squaring (shared inversion not counted)
+# a table point summed by the tree path (cdp_msm_fixed_batch_dev_tree): 5 halving rounds of affine additions, the last 1/32 by the lane kernel
+IMAD_PER_TREE_POINT = (31 * IMAD_PER_AFFINE_ADD + IMAD_PER_MIXED_ADD) / 32
 
 
 def mont(v):
@@ -491,9 +494,13 @@ def main():
         roofline["table_gather_bytes_per_pair"] = gather_bytes
         roofline["table_gather_achieved_GBps"] = gather_bytes * units_per_launch / (avg_ms * 1e-3) / 1e9
         roofline["table_gather_frac"] = roofline["table_gather_achieved_GBps"] / hbm_peak
+        # most table points of a prover step are summed by the tree path (long uniform segments); the rest by the lane kernel's XYZZ accumulators.
+        # The fraction is quoted on the tree's count -- the fewest multiply-adds the method in use needs -- and the lane count is given beside it.
         roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)",
-                                "achieved": adds_per_s * IMAD_PER_MIXED_ADD, "frac": adds_per_s * IMAD_PER_MIXED_ADD / imad_peak,
-                                "mixed_adds_per_s": adds_per_s, "imad_wide_per_mixed_add": IMAD_PER_MIXED_ADD}
+                                "achieved": adds_per_s * IMAD_PER_TREE_POINT, "frac": adds_per_s * IMAD_PER_TREE_POINT / imad_peak,
+                                "table_points_per_s": adds_per_s, "imad_wide_per_table_point": IMAD_PER_TREE_POINT,
+                                "imad_wide_per_affine_add": IMAD_PER_AFFINE_ADD, "imad_wide_per_xyzz_mixed_add": IMAD_PER_MIXED_ADD,
+                                "frac_if_all_xyzz": adds_per_s * IMAD_PER_MIXED_ADD / imad_peak}
     else:
         roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)"}
     # ---- the same kernel timed ALONE on synthetic scalars (nothing else on the GPU): one fixed-base launch of the IPA-round shape for the whole batch
@@ -514,26 +521,37 @@ def main():
         lib, h = eng.lib, eng.handle
         d_sc, d_sg, d_out = lib.cdp_dev_alloc(h, len(sc)), lib.cdp_dev_alloc(h, ctypes.sizeof(segs)), lib.cdp_dev_alloc(h, nseg * 144)
         lib.cdp_h2d(h, d_sc, arr(bytes(sc)), len(sc)); lib.cdp_h2d(h, d_sg, segs, ctypes.sizeof(segs)); eng.sync()
-        for _ in range(3):
-            lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, nseg, B * (2 * n_ + 2), None, d_out)
-        eng.sync(); eng.profile_reset(); eng.profile_enable(True)
-        for _ in range(5):
-            with torch.cuda.stream(stream):
-                flush_buf.zero_()
-            lib.cdp_msm_fixed_batch_dev(h, tab.handle, d_sc, d_sg, nseg, B * (2 * n_ + 2), None, d_out)
-        eng.sync()
-        pf = eng.profile_read()["msm_fixed"]
-        eng.profile_enable(False)
-        iso_ms = pf["ms"] / pf["launches"]
         pairs = B * (2 * n_ + 2)
+
+        def isolated(call):
+            for _ in range(3):
+                call()
+            eng.sync(); eng.profile_reset(); eng.profile_enable(True)
+            for _ in range(5):
+                with torch.cuda.stream(stream):
+                    flush_buf.zero_()
+                call()
+            eng.sync()
+            pf = eng.profile_read()["msm_fixed"]
+            eng.profile_enable(False)
+            return pf["ms"] / pf["launches"]
+
+        iso_tree = isolated(lambda: lib.cdp_msm_fixed_batch_dev_tree(h, tab.handle, d_sc, d_sg, nseg, pairs, None, d_out, n_ // 2 + 1))
+        iso_lanes = isolated(lambda: lib.cdp_msm_fixed_batch_dev_lanes(h, tab.handle, d_sc, d_sg, nseg, pairs, None, d_out, 16))
+        iso_ms = iso_tree
         madds = pairs * 16 / (iso_ms * 1e-3)
-        roofline["isolated"] = {"kernel": "k_fixed_msm, IPA-round shape, whole batch in one launch, nothing else running", "ms": iso_ms,
+        roofline["isolated"] = {"kernel": "fixed-base MSM as the prover launches it (tree of batched affine additions: k_fixed_ba_first / _next + k_fixed_msm), "
+                                          "IPA-round shape, whole batch in one call, nothing else running", "ms": iso_ms,
                                 "pairs_per_s": pairs / (iso_ms * 1e-3),
                                 "achieved_GBps_128B_per_pair": pairs * 128 / (iso_ms * 1e-3) / 1e9, "hbm_frac_128B_per_pair": pairs * 128 / (iso_ms * 1e-3) / 1e9 / hbm_peak,
                                 "achieved_GBps_table_gather": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9,
                                 "hbm_frac_table_gather": pairs * (32 + 16 * 96) / (iso_ms * 1e-3) / 1e9 / hbm_peak,
-                                "mixed_adds_per_s": madds, "imad_wide_per_mixed_add": IMAD_PER_MIXED_ADD,
-                                "int_pipe_frac": madds * IMAD_PER_MIXED_ADD / imad_peak}
+                                "table_points_per_s": madds, "imad_wide_per_table_point": IMAD_PER_TREE_POINT,
+                                "int_pipe_frac": madds * IMAD_PER_TREE_POINT / imad_peak,
+                                "lane_kernel": {"kernel": "k_fixed_msm alone, 16 lanes per segment, XYZZ accumulators", "ms": iso_lanes,
+                                                "pairs_per_s": pairs / (iso_lanes * 1e-3), "mixed_adds_per_s": pairs * 16 / (iso_lanes * 1e-3),
+                                                "imad_wide_per_mixed_add": IMAD_PER_MIXED_ADD,
+                                                "int_pipe_frac": pairs * 16 / (iso_lanes * 1e-3) * IMAD_PER_MIXED_ADD / imad_peak}}
         for dd in (d_sc, d_sg, d_out):
             lib.cdp_dev_free(h, dd)
         tab.close()

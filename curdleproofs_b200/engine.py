@@ -61,6 +61,7 @@ _SIGS = {
     "cdp_msm_fixed": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "cdp_msm_fixed_batch_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "cdp_msm_fixed_batch_dev_tree": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t]),
+    "cdp_msm_fixed_batch_dev_lanes": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_int]),
     "cdp_profile_enable": (c_int, [c_void_p, c_int]),
     "cdp_profile_reset": (c_int, [c_void_p]),
     "cdp_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_uint64), POINTER(c_uint64)]),
