@@ -13,8 +13,9 @@ namespace cdp {
 // One thread per element.  The two 128-bit GLV halves (k1, k2) are recoded into the joint sparse form (Solinas): digits in {0, +-1},
 // on average only every second column non-zero (plain binary: three out of four).  The addends of a column:
 //   (+-1, 0) -> +-P = (x, +-y)      (0, +-1) -> +-phi(P) = (beta x, +-y)      +-(1, 1) -> +-(P + phi(P)) = -+phi^2(P) = (beta^2 x, -+y)
-// are affine and free; +-(1, -1) -> +-(P - phi(P)) is computed once per element (Jacobian) and added with a full addition.
-// So: 128 doublings, ~48 mixed and ~16 full additions per element instead of 128 doublings and ~96 mixed additions.  Within one fold
+// are affine and free; +-(1, -1) -> +-(P - phi(P)) is computed once per element and made affine (one inversion by division steps,
+// fp_inv_safegcd.cuh: integer-ALU work beside a multiply-pipe-bound loop), so that its ~16 additions are mixed ones as well (7M + 4S
+// instead of 11M + 5S).  So: 128 doublings and ~64 mixed additions per element instead of 128 doublings and ~96.  Within one fold
 // job all threads share the scalar, so the column pattern is warp-uniform whenever a job spans whole warps.
 template <int OCC>
 __global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restrict__ pts, const uint32_t *__restrict__ scalars,
@@ -67,15 +68,21 @@ __global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restri
     fp_mul_beta(bx, P.x);
     fp_mul_beta(bbx, bx);
     fp_neg(ny, P.y);
-    // D = P - phi(P), Jacobian (P + (beta x, -y)); infinity stays infinity
-    g1j D;
+    // D = P - phi(P) = P + (beta x, -y), affine; infinity stays infinity (x = y = 0)
+    g1a D;
     {
-        g1j Pj;
+        g1j Pj, Dj;
         g1j_from_affine(Pj, P);
         g1a nphi;
         nphi.x = bx; nphi.y = ny;
         if (g1a_is_inf(P)) g1a_set_inf(nphi);
-        g1j_add_mixed(D, Pj, nphi);
+        g1j_add_mixed(Dj, Pj, nphi);
+        fp zi, zi2;
+        fp_inv(zi, Dj.Z);  // 0 -> 0: infinity comes out as (0, 0)
+        fp_sqr(zi2, zi);
+        fp_mul(D.x, Dj.X, zi2);
+        fp_mul(zi2, zi2, zi);
+        fp_mul(D.y, Dj.Y, zi2);
     }
     g1j acc;
     g1j_set_inf(acc);
@@ -83,14 +90,15 @@ __global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restri
 #pragma unroll 1
     for (int col = top; col >= -1; col--) {
         g1a q;
-        bool do_madd = false, do_jadd = false, neg_d = false;
+        bool do_madd = false;
         if (col >= 0) {
             g1j_dbl(acc, acc);
             const uint32_t w = (uint32_t)col >> 5, bit = 1u << (col & 31);
             const bool z0 = (nz0[w] & bit) != 0, z1 = (nz1[w] & bit) != 0, n0 = (sg0[w] & bit) != 0, n1 = (sg1[w] & bit) != 0;
             if (z0 && z1 && n0 != n1) {
-                do_jadd = true;
-                neg_d = n0;                                            // (-1, +1) = -(P - phi P)
+                do_madd = true;
+                q = D;
+                if (n0) fp_neg(q.y, q.y);                              // (-1, +1) = -(P - phi P)
             } else if (z0 || z1) {
                 do_madd = true;
                 const bool both = z0 && z1;                            // same signs: +-(P + phi P) = (beta^2 x, -+y)
@@ -104,11 +112,6 @@ __global__ void __launch_bounds__(128, OCC) k_smul_jobs(const uint32_t *__restri
             if (do_madd) g1a_load(q, pts + 24 * ((size_t)job.add_off + e));
         }
         if (do_madd) g1j_add_mixed(acc, acc, q);
-        if (do_jadd) {
-            g1j t = D;
-            if (neg_d) fp_neg(t.Y, t.Y);
-            g1j_add(acc, acc, t);
-        }
     }
     g1j_store(out_jac + 36 * (size_t)i, acc);
 }
