@@ -633,8 +633,8 @@ static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
     CUDA_TRY(ctx, cudaMemcpyAsync(h_stats, stats, sizeof(h_stats), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // K additions share an inversion (~5 additions' worth of instructions).  All threads of a round do the same work, so the grid runs in
-    // waves of WAVE resident threads: K is the smallest that packs the round into w FULL waves, w the fewest waves with K <= K_MAX
-    static const uint32_t K_MAX = env_u32("CDP_BA_KMAX", 128), WAVE = env_u32("CDP_BA_WAVE", 148 * 3 * 128);
+    // waves of WAVE resident threads (4 CTAs of 128 per SM at 128 registers): K is the smallest that packs the round into w FULL waves, w the fewest waves with K <= K_MAX
+    static const uint32_t K_MAX = env_u32("CDP_BA_KMAX", 128), WAVE = env_u32("CDP_BA_WAVE", 148 * 4 * 128);
     uint32_t *sbuf[2] = {(uint32_t *)(ws + o_s0), (uint32_t *)(ws + o_s1)};
     for (int r = 0; r < BA_STATS_ROUNDS && h_stats[3 * r]; r++) {
         const uint32_t pairs = h_stats[3 * r], list_len = r == 0 ? (uint32_t)slots : h_stats[3 * r + 2];
@@ -1032,7 +1032,7 @@ extern "C" int cdp_msm_fixed_batch_dev_tree(cdp_ctx *ctx, const cdp_fixed_table 
     if (count == 0) return CDP_OK;
     if (t->device != ctx->device) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_msm_fixed_batch_dev_tree: table lives on another device");
     static const int rounds = (int)env_u32("CDP_FIXED_TREE_ROUNDS", 5);
-    static const uint32_t kmax = env_u32("CDP_FIXED_TREE_KMAX", 128), t_target = env_u32("CDP_FIXED_TREE_WAVE", 148 * 3 * 128);
+    static const uint32_t kmax = env_u32("CDP_FIXED_TREE_KMAX", 128), t_target = env_u32("CDP_FIXED_TREE_WAVE", 148 * 4 * 128);
     if (max_pairs_per_segment == 0 || max_pairs_per_segment * (size_t)t->kp.nw < (size_t(4) << rounds) ||
         count * (max_pairs_per_segment * (size_t)t->kp.nw + 64) >= (size_t(1) << 30))  // too short for a tree (or too many slots for 30-bit job numbers): the lane kernel
         return cdp_msm_fixed_batch_dev_lanes(ctx, t, d_scalars, d_segs, count, total_pairs, d_var_pts, d_out_jac, 32);
@@ -1308,10 +1308,10 @@ extern "C" int cdp_bench_kernel(cdp_ctx *ctx, int which, int blocks, int threads
     if (!ctx || !ms_out || blocks <= 0 || threads <= 0 || threads > 256) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_bench_kernel: bad argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     TRY(ensure_dev(ctx, ctx->d_out, (size_t)blocks * threads * 4));
-    if (which >= 9 && which <= 16) TRY(ensure_dev(ctx, ctx->d_big, (size_t)blocks * threads * iters * 288));
+    if (which >= 9 && which <= 32) TRY(ensure_dev(ctx, ctx->d_big, (size_t)blocks * threads * iters * 288));
     auto launch_bench = [&](cudaStream_t st, int w, uint32_t *out, int b, int t, int it) {
         // 9 + INL: batched affine additions (INL: which products are expanded in place, batch_affine.cuh), blocks * threads threads of `iters` additions each over a streamed operand array
-        if (w >= 9 && w <= 16) return launch_bench_ba(st, (uint32_t *)ctx->d_big.ptr, (uint32_t)(blocks * threads), (uint32_t)iters, it != iters, w - 9);
+        if (w >= 9 && w <= 32) return launch_bench_ba(st, (uint32_t *)ctx->d_big.ptr, (uint32_t)(blocks * threads), (uint32_t)iters, it != iters, w - 9);
         return cdp::launch_bench(st, w, out, b, t, it);
     };
     cudaEvent_t e0, e1;

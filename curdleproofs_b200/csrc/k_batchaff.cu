@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) k_ba_jobs(const ba_scan_t *__restrict__ i
 }
 
 template <class In>
-__global__ void __launch_bounds__(128, 3) k_ba_round(uint32_t total, uint32_t K, uint32_t pf, ba_jobs_src<In> src) {
+__global__ void __launch_bounds__(128, 4) k_ba_round(uint32_t total, uint32_t K, uint32_t pf, ba_jobs_src<In> src) {
     const uint32_t T = (total + K - 1) / K;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= T) return;
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(256) k_ba_bench_fill(uint32_t *buf, size_t wor
         buf[i] = (i % 12 == 11) ? (x & 0x0fffffffu) : x;  // below p
     }
 }
-template <int INL>
-__global__ void __launch_bounds__(128, 3) k_ba_bench(ba_bench_src src, uint32_t T, uint32_t K) {
+template <int INL, int OCC>
+__global__ void __launch_bounds__(128, OCC) k_ba_bench(ba_bench_src src, uint32_t T, uint32_t K) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= T) return;
     ba_run<ba_bench_src, INL>(src, tid, T, T * K, K);
@@ -290,11 +290,19 @@ cudaError_t launch_bench_ba(cudaStream_t st, uint32_t *buf, uint32_t T, uint32_t
     if (fill) k_ba_bench_fill<<<148 * 8, 256, 0, st>>>(buf, pairs * 48);
     const ba_bench_src src{buf, buf + pairs * 48};
     const unsigned g = (T + 127) / 128;
-    if (inl == 1) k_ba_bench<1><<<g, 128, 0, st>>>(src, T, K);
-    else if (inl == 3) k_ba_bench<3><<<g, 128, 0, st>>>(src, T, K);
-    else if (inl == 7) k_ba_bench<7><<<g, 128, 0, st>>>(src, T, K);
-    else if (inl == 5) k_ba_bench<5><<<g, 128, 0, st>>>(src, T, K);
-    else k_ba_bench<0><<<g, 128, 0, st>>>(src, T, K);
+    const int occ = inl >> 3;  // 0: 3 CTAs per SM, 1: 4, 2: 5
+    inl &= 7;
+    if (occ == 1) {
+        if (inl == 3) k_ba_bench<3, 4><<<g, 128, 0, st>>>(src, T, K);
+        else k_ba_bench<0, 4><<<g, 128, 0, st>>>(src, T, K);
+    } else if (occ == 2) {
+        if (inl == 3) k_ba_bench<3, 5><<<g, 128, 0, st>>>(src, T, K);
+        else k_ba_bench<0, 5><<<g, 128, 0, st>>>(src, T, K);
+    } else if (inl == 1) k_ba_bench<1, 3><<<g, 128, 0, st>>>(src, T, K);
+    else if (inl == 3) k_ba_bench<3, 3><<<g, 128, 0, st>>>(src, T, K);
+    else if (inl == 7) k_ba_bench<7, 3><<<g, 128, 0, st>>>(src, T, K);
+    else if (inl == 5) k_ba_bench<5, 3><<<g, 128, 0, st>>>(src, T, K);
+    else k_ba_bench<0, 3><<<g, 128, 0, st>>>(src, T, K);
     return cudaGetLastError();
 }
 

@@ -422,12 +422,12 @@ struct fixed_ba_arr_src {
         g1a_load(Q, in + 48 * (size_t)q + 24);
     }
 };
-__global__ void __launch_bounds__(128, 3) k_fixed_ba_first(fixed_ba_src src, uint32_t total, uint32_t K, uint32_t pf) {
+__global__ void __launch_bounds__(128, 4) k_fixed_ba_first(fixed_ba_src src, uint32_t total, uint32_t K, uint32_t pf) {
     const uint32_t T = (total + K - 1) / K, tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= T) return;
     ba_run<fixed_ba_src, 3>(src, tid, T, total, K, pf);
 }
-__global__ void __launch_bounds__(128, 3) k_fixed_ba_next(fixed_ba_arr_src src, uint32_t total, uint32_t K) {
+__global__ void __launch_bounds__(128, 4) k_fixed_ba_next(fixed_ba_arr_src src, uint32_t total, uint32_t K) {
     const uint32_t T = (total + K - 1) / K, tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= T) return;
     ba_run<fixed_ba_arr_src, 3>(src, tid, T, total, K);
