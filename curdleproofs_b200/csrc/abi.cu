@@ -593,6 +593,37 @@ static int big_c_for(size_t n) {
     // measured with load-ordered slots and quad reductions (tools/msm_latency.py, round 2): 2^16..2^19: 15, 2^20: 16, 2^21: 17, 2^22: 19 (7 windows)
     return n < (size_t(1) << 14) ? 12 : n < (size_t(1) << 16) ? 13 : n < (size_t(1) << 20) ? 15 : n < (size_t(1) << 21) ? 16 : n < (size_t(1) << 22) ? 17 : 19;
 }
+// The bucket reduction of the large Pippenger, shared by both accumulate paths: 16-ary running-sum levels while a window still has many nodes
+// (throughput-bound), then -- from BITSUM_MAX nodes per window down -- the window totals as bit-decomposed plain sums and the final Horner
+// (k_big_bitsums / k_big_horner2: ~45 dependent quad operations instead of ~50 per remaining level).  CDP_BIG_BITSUM=0 keeps the levels.
+static int big_reduce_tail(cdp_ctx *ctx, const uint32_t *buckets, bool affine, uint32_t nb, int nwin, int c, uint8_t *ws, size_t o_A0, size_t o_B0,
+                           size_t o_A1, size_t o_B1, uint8_t *d_out_jac) {
+    static const uint32_t BITSUM_MAX = [] { const char *e = getenv("CDP_BIG_BITSUM"); int v = e ? atoi(e) : 1024; return (uint32_t)(v < 0 ? 0 : v); }();
+    const uint32_t *Ain = nullptr, *Bin = nullptr;
+    uint32_t *Aout = (uint32_t *)(ws + o_A0), *Bout = (uint32_t *)(ws + o_B0);
+    uint32_t len = nb;
+    int shift = 0, flip = 0;
+    while (len > 1) {
+        if (Ain && len <= BITSUM_MAX && nwin <= 16) {
+            launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, nwin);
+            CUDA_TRY(ctx, launch_big_bitsum_horner(ctx->stream, Ain, Bin, len, shift, nwin, c, Aout, reinterpret_cast<uint32_t *>(d_out_jac)));
+            ctx->launches++;
+            return CDP_OK;
+        }
+        uint32_t g = std::min<uint32_t>(16, len);
+        uint32_t n_out = (uint32_t)((size_t)nwin * (len / g));
+        launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, n_out);
+        if (!Ain && affine) CUDA_TRY(ctx, launch_big_reduce_leaf_affine(ctx->stream, buckets, n_out, g, Aout, Bout));
+        else CUDA_TRY(ctx, launch_big_reduce_level(ctx->stream, Ain ? Ain : buckets, Bin, n_out, g, shift, Aout, Bout));
+        Ain = Aout; Bin = Bout;
+        flip ^= 1;
+        Aout = (uint32_t *)(ws + (flip ? o_A1 : o_A0)); Bout = (uint32_t *)(ws + (flip ? o_B1 : o_B0));
+        len /= g;
+        while (g > 1) { shift++; g >>= 1; }
+    }
+    { launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, nwin); CUDA_TRY(ctx, launch_big_horner(ctx->stream, Ain, Bin, nwin, c, reinterpret_cast<uint32_t *>(d_out_jac))); }
+    return CDP_OK;
+}
 // Bucket sums by rounds of batched affine additions (k_batchaff.cu): the default; CDP_BIG_BA=0 keeps the one-thread-per-bucket XYZZ accumulate.
 static const bool BIG_BA = [] { const char *e = getenv("CDP_BIG_BA"); return !e || atoi(e) != 0; }();
 // from 2^20 pairs: below, the rounds' fixed costs (a scan, a job list and an inversion's latency per round, ~10 rounds) outweigh the cheaper additions
@@ -646,25 +677,8 @@ static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
                                       slots, sc[(r + 1) & 1], P, bx, vals2, sbuf[(r + 1) & 1], sbuf[r & 1], baff, ws + o_jobs));
         ctx->launches += 3;
     }
-    // hierarchical reduction: sum_b (b+1) B_b = Bv_root + A_root per window; the leaves are affine
-    const uint32_t *Ain = nullptr, *Bin = nullptr;
-    uint32_t *Aout = (uint32_t *)(ws + o_A0), *Bout = (uint32_t *)(ws + o_B0);
-    uint32_t len = nb;
-    int shift = 0, flip = 0;
-    while (len > 1) {
-        uint32_t g = std::min<uint32_t>(16, len);
-        uint32_t n_out = (uint32_t)((size_t)nwin * (len / g));
-        launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, n_out);
-        if (!Ain) CUDA_TRY(ctx, launch_big_reduce_leaf_affine(ctx->stream, baff, n_out, g, Aout, Bout));
-        else CUDA_TRY(ctx, launch_big_reduce_level(ctx->stream, Ain, Bin, n_out, g, shift, Aout, Bout));
-        Ain = Aout; Bin = Bout;
-        flip ^= 1;
-        Aout = (uint32_t *)(ws + (flip ? o_A1 : o_A0)); Bout = (uint32_t *)(ws + (flip ? o_B1 : o_B0));
-        len /= g;
-        while (g > 1) { shift++; g >>= 1; }
-    }
-    { launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, nwin); CUDA_TRY(ctx, launch_big_horner(ctx->stream, Ain, Bin, nwin, c, reinterpret_cast<uint32_t *>(d_out_jac))); }
-    return CDP_OK;
+    // hierarchical reduction: sum_b (b+1) B_b per window (the leaves are affine), Horner over the windows
+    return big_reduce_tail(ctx, baff, true, nb, nwin, c, ws, o_A0, o_B0, o_A1, o_B1, d_out_jac);
 }
 static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d_scalars, size_t n, uint8_t *d_out_jac) {
     if (BIG_BA && n >= (ctx->big_ba_min ? ctx->big_ba_min : BIG_BA_MIN_N) && (size_t)((130 + big_c_for(n) - 1) / big_c_for(n)) * 2 * n < (size_t(1) << 30)) return msm_big_resident_ba(ctx, d_pts, d_scalars, n, d_out_jac);
@@ -707,24 +721,8 @@ static int msm_big_resident(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t *d
         CUDA_TRY(ctx, launch_big_fold_top(ctx->stream, top_slots, nbt, nw > 1 ? nw : sp_top, 1, nb, tmp));
         CUDA_TRY(ctx, cudaMemcpyAsync(top_slots, tmp, (size_t)nb * 144, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    // hierarchical reduction: sum_b (b+1) B_b = Bv_root + A_root per window
-    const uint32_t *Ain = bjac, *Bin = nullptr;
-    uint32_t *Aout = (uint32_t *)(ws + o_A0), *Bout = (uint32_t *)(ws + o_B0);
-    uint32_t len = nb;
-    int shift = 0, flip = 0;
-    while (len > 1) {
-        uint32_t g = std::min<uint32_t>(16, len);
-        uint32_t n_out = (uint32_t)((size_t)nwin * (len / g));
-        launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, n_out);
-        CUDA_TRY(ctx, launch_big_reduce_level(ctx->stream, Ain, Bin, n_out, g, shift, Aout, Bout));
-        Ain = Aout; Bin = Bout;
-        flip ^= 1;
-        Aout = (uint32_t *)(ws + (flip ? o_A1 : o_A0)); Bout = (uint32_t *)(ws + (flip ? o_B1 : o_B0));
-        len /= g;
-        while (g > 1) { shift++; g >>= 1; }
-    }
-    { launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, nwin); CUDA_TRY(ctx, launch_big_horner(ctx->stream, Ain, Bin, nwin, c, reinterpret_cast<uint32_t *>(d_out_jac))); }
-    return CDP_OK;
+    // hierarchical reduction: sum_b (b+1) B_b per window, Horner over the windows
+    return big_reduce_tail(ctx, bjac, false, nb, nwin, c, ws, o_A0, o_B0, o_A1, o_B1, d_out_jac);
 }
 
 extern "C" int cdp_sum_jacobian_dev(cdp_ctx *ctx, const uint8_t *d_jac_in, size_t count, uint8_t *d_out_jac) {

@@ -380,6 +380,116 @@ __global__ void __launch_bounds__(32) k_big_horner(const uint32_t *__restrict__ 
     if (threadIdx.x == 0) g1j_store(out_jac, total);
 }
 
+// ---- the upper part of the bucket reduction as PLAIN sums.  After the 16-ary levels above a window is N nodes (A_k, Bv_k), k < N, and its
+// total is  T = sum_k (A_k + Bv_k) + 2^shift * sum_k k A_k .  Writing k in binary,  sum_k k A_k = sum_j 2^j S_j  with  S_j = sum over the k
+// that have bit j set of A_k : log2 N + 1 plain sums per window, each a tree -- ~14 dependent quad additions instead of the ~50 per level
+// (x 3 levels) of the running-sum hierarchy, whose last levels are a handful of threads deep in a latency chain.
+//   k_big_bitsums   one CTA of 64 quads per (window, sum): strided partial sums, folded by shuffles and shared memory
+//   k_big_horner2   one warp per window: T_w by Horner over the bits; then warp 0: Horner over the windows
+constexpr int BITSUM_PARTS = 4;  // CTAs per sum (4 warps each: one per scheduler -- more warps on an SM only share its multiply pipe)
+__global__ void __launch_bounds__(128) k_big_bitsums(const uint32_t *__restrict__ A, const uint32_t *__restrict__ Bv, uint32_t N, int nbits,
+                                                     uint32_t *__restrict__ sums /* [nwin][nbits + 1][BITSUM_PARTS] */) {
+    __shared__ uint32_t sm[4 * 36];
+    const int sidx = blockIdx.x, w = blockIdx.y, part = blockIdx.z;
+    const int s = (int)(threadIdx.x & 3);
+    const uint32_t quad = (threadIdx.x >> 2) + 32 * part, nquads = 32 * BITSUM_PARTS;
+    const uint32_t *Aw = A + 36 * (size_t)w * N, *Bw = Bv + 36 * (size_t)w * N;
+    const uint32_t count = sidx < nbits ? N / 2 : 2 * N;
+    g1j acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t e0 = 0; e0 < count; e0 += nquads) {
+        const uint32_t e = e0 + quad;
+        g1j q;
+        g1j_set_inf(q);
+        if (e < count) {
+            if (sidx < nbits) {  // the e-th index with bit sidx set
+                const uint32_t k = ((e >> sidx) << (sidx + 1)) | (1u << sidx) | (e & ((1u << sidx) - 1u));
+                g1j_load(q, Aw + 36 * (size_t)k);
+            } else {
+                g1j_load(q, e < N ? Aw + 36 * (size_t)e : Bw + 36 * (size_t)(e - N));
+            }
+        }
+        g1j_add_quad(acc, acc, q, s);
+    }
+#pragma unroll 1
+    for (int d = 4; d < 32; d <<= 1) {  // the 8 quads of a warp
+        g1j o;
+        shfl_down_g1j(o, acc, d, 32);
+        g1j_add_quad(acc, acc, o, s);
+    }
+    if ((threadIdx.x & 31) == 0) g1j_store(sm + 36 * (threadIdx.x >> 5), acc);
+    __syncthreads();
+    if (threadIdx.x < 32) {  // the 4 warps: quads 0..3 hold them, the others infinity
+        g1j_set_inf(acc);
+        if (threadIdx.x < 16) g1j_load(acc, sm + 36 * (threadIdx.x >> 2));
+#pragma unroll 1
+        for (int d = 4; d < 16; d <<= 1) {
+            g1j o;
+            shfl_down_g1j(o, acc, d, 32);
+            g1j_add_quad(acc, acc, o, s);
+        }
+        if (threadIdx.x == 0) g1j_store(sums + 36 * (((size_t)w * (nbits + 1) + sidx) * BITSUM_PARTS + part), acc);
+    }
+}
+__global__ void __launch_bounds__(512) k_big_horner2(const uint32_t *__restrict__ sums, int nbits, int shift, int nwin, int c, uint32_t *__restrict__ out_jac) {
+    __shared__ uint32_t sm[16 * 36];
+    extern __shared__ uint32_t smj[];  // [nwin][nbits + 1] merged sums
+    const int s = (int)(threadIdx.x & 3), w = (int)(threadIdx.x >> 5), quad = (int)((threadIdx.x >> 2) & 7);
+    {
+        // merge the parts of every sum: quad q of warp w takes sums q, q + 8, ... of window w (every quad runs the same number of steps)
+        const uint32_t *S = sums + 36 * (size_t)w * (nbits + 1) * BITSUM_PARTS;
+        uint32_t *M = smj + 36 * (size_t)w * (nbits + 1);
+#pragma unroll 1
+        for (int j0 = 0; j0 <= nbits; j0 += 8) {
+            const int j = j0 + quad;
+            g1j t;
+            g1j_set_inf(t);
+#pragma unroll 1
+            for (int pt = 0; pt < BITSUM_PARTS; pt++) {
+                g1j q;
+                g1j_set_inf(q);
+                if (j <= nbits) g1j_load(q, S + 36 * ((size_t)j * BITSUM_PARTS + pt));
+                g1j_add_quad(t, t, q, s);
+            }
+            if (j <= nbits && s == 0) g1j_store(M + 36 * (size_t)j, t);
+        }
+        __syncwarp();
+        // every quad of warp w runs the same chain
+        g1j t;
+        g1j_set_inf(t);
+#pragma unroll 1
+        for (int j = nbits - 1; j >= 0; j--) {
+            g1j_dbl_quad(t, s);
+            g1j q;
+            g1j_load(q, M + 36 * (size_t)j);
+            g1j_add_quad(t, t, q, s);
+        }
+#pragma unroll 1
+        for (int k = 0; k < shift; k++) g1j_dbl_quad(t, s);
+        g1j u;
+        g1j_load(u, M + 36 * (size_t)nbits);
+        g1j_add_quad(t, t, u, s);
+        if ((threadIdx.x & 31) == 0) g1j_store(sm + 36 * w, t);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        g1j total;
+        g1j_set_inf(total);
+#pragma unroll 1
+        for (int ww = nwin - 1; ww >= 0; ww--) {
+            if (ww != nwin - 1) {
+#pragma unroll 1
+                for (int k = 0; k < c; k++) g1j_dbl_quad(total, s);
+            }
+            g1j a;
+            g1j_load(a, sm + 36 * ww);
+            g1j_add_quad(total, total, a, s);
+        }
+        if (threadIdx.x == 0) g1j_store(out_jac, total);
+    }
+}
+
 // top window fold, one step: out[j * nbt + b] = sum over r = j, j + nw, j + 2 nw, ... < sp of in[r * nbt + b]   (warp (b, j)).
 // Called twice (sp -> nw partial sums per bucket, then nw -> 1); the last call (nw == 1) also pads out[nbt .. nb) with infinity.
 __global__ void __launch_bounds__(128) k_big_fold_top(const uint32_t *__restrict__ in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to,
@@ -482,6 +592,15 @@ cudaError_t launch_big_reduce_leaf_affine(cudaStream_t st, const uint32_t *bucke
 }
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac) {
     k_big_horner<<<1, 32, 0, st>>>(A, Bv, nwin, c, out_jac);
+    return cudaGetLastError();
+}
+// window totals and the final Horner from N nodes per window (N a power of two >= 2, nwin <= 16); sums: 4 nwin (log2 N + 1) Jacobian points of scratch
+cudaError_t launch_big_bitsum_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, uint32_t N, int shift, int nwin, int c, uint32_t *sums,
+                                     uint32_t *out_jac) {
+    int nbits = 0;
+    while ((1u << nbits) < N) nbits++;
+    k_big_bitsums<<<dim3((unsigned)nbits + 1, (unsigned)nwin, BITSUM_PARTS), 128, 0, st>>>(A, Bv, N, nbits, sums);
+    k_big_horner2<<<1, 32 * nwin, (size_t)nwin * (nbits + 1) * 144, st>>>(sums, nbits, shift, nwin, c, out_jac);
     return cudaGetLastError();
 }
 cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out) {

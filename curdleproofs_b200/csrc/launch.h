@@ -106,6 +106,8 @@ cudaError_t launch_big_accumulate(cudaStream_t st, const uint32_t *pts, const ui
 cudaError_t launch_big_reduce_level(cudaStream_t st, const uint32_t *Ain, const uint32_t *Bin, uint32_t n_out, uint32_t g, int shift, uint32_t *Aout,
                                     uint32_t *Bout);
 cudaError_t launch_big_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, int nwin, int c, uint32_t *out_jac);
+cudaError_t launch_big_bitsum_horner(cudaStream_t st, const uint32_t *A, const uint32_t *Bv, uint32_t N, int shift, int nwin, int c, uint32_t *sums,
+                                     uint32_t *out_jac);
 cudaError_t launch_big_fold_top(cudaStream_t st, const uint32_t *in, uint32_t nbt, uint32_t sp, uint32_t nw, uint32_t pad_to, uint32_t *out);
 cudaError_t launch_big_reduce_leaf_affine(cudaStream_t st, const uint32_t *bucket_aff, uint32_t n_out, uint32_t g, uint32_t *Aout, uint32_t *Bout);
 // bucket sums by rounds of batched affine additions (k_batchaff.cu)

@@ -1,5 +1,3 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_fixed.py -x -q -m gpu -k "large_pippenger or tree" 2>&1 | tail -2
-python tools/msm_latency.py 20 22 2>&1 | tail -3
-python tools/fixed_bench.py 2>&1 | tail -10
-python tools/prover_timing.py 252 4096 8 2>&1 | tail -2 | cut -c1-130
-python tools/prover_timing.py 252 4096 8 2>&1 | tail -2 | cut -c1-130
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "large_pippenger" 2>&1 | tail -2
+python tools/msm_latency.py 16 22 2>&1 | tail -7
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/ba_launches.csv python tools/msm_latency.py 22 22 > gpurun_out/ba_lat.log 2>&1
