@@ -429,10 +429,86 @@ __global__ void __launch_bounds__(32) k_verify_transcript_b(const uint8_t *__res
 }
 
 #ifndef CDP_TRANSCRIPT_HOST_HARNESS
+// ---- the same opening with ONE WARP per proof (cstrobe.cuh): the STROBE state in shared memory, message bytes XORed in by all lanes,
+// Keccak-f[1600] by 25 lanes.  One thread per proof (k_transcript_open above, kept: it is the form the CPU harness checks, and the GPU test
+// compares this kernel's output with it byte for byte) spends ~8 ms per launch on ~640 dependent permutations of ~9 us each; here a
+// permutation is ~2 us.
+#define CTA_FOR(i, cnt) for (uint32_t i = threadIdx.x; i < (uint32_t)(cnt); i += blockDim.x)
+#define CTA_SYNC() __syncwarp()
+#define CTA_LEADER (threadIdx.x == 0)
+}  // namespace cdp
+#include "cstrobe.cuh"
+namespace cdp {
+__global__ void __launch_bounds__(32) k_transcript_open_warp(const uint8_t *__restrict__ comp_vecs, const uint8_t *__restrict__ comp_M, uint32_t ell,
+                                                             uint32_t B, uint8_t *__restrict__ vec_a_out, uint64_t *__restrict__ state_out) {
+    using namespace cstr;
+    __shared__ __align__(8) uint8_t st[200];
+    __shared__ __align__(8) uint8_t buf[64];
+    const uint32_t pr = blockIdx.x, lane = threadIdx.x;
+    cstrobe s{st, 0, 0};
+    for (uint32_t i = lane; i < 200; i += 32) st[i] = 0;
+    __syncwarp();
+    if (lane == 0) {  // Strobe128::new("Merlin v1.0")
+        const uint8_t init[6] = {1, (uint8_t)(SR + 2), 1, 0, 1, 96};
+        for (uint32_t i = 0; i < 6; i++) st[i] = init[i];
+        for (uint32_t i = 0; i < 12; i++) st[6 + i] = L_STROBE[i];
+    }
+    keccak_f1600_warp(reinterpret_cast<uint64_t *>(st));
+    cs_begin(s, cstr::FLAG_M | cstr::FLAG_A);
+    cs_absorb(s, L_MERLIN, 11);
+    cs_append(s, L_DOMSEP, 7, L_PROTO, 12);  // Transcript::new(b"curdleproofs")
+    // append_list: every Vec<G1Affine> is one message, u64-LE length then the elements (ark-serialize)
+#pragma unroll 1
+    for (int v = 0; v < 4; v++) {
+        cs_append_header(s, L_STEP1, 18, 8 + ell * 48);
+        cs_value(s, (uint64_t)ell, 8);
+        cs_absorb(s, comp_vecs + ((size_t)pr * 4 + v) * ell * 48, ell * 48);
+    }
+    cs_append(s, L_STEP1, 18, comp_M + (size_t)pr * 48, 48);
+    // get_and_append_challenge (src/transcript.rs:41-54), as in k_transcript_open
+#pragma unroll 1
+    for (uint32_t i = 0; i < ell; i++) {
+        for (;;) {
+            cs_challenge_bytes(s, L_VEC_A, 18, buf, 64);
+            uint32_t w[8];
+            uint32_t nz = 0;
+            for (int k = 0; k < 8; k++) {
+                w[k] = (uint32_t)buf[4 * k] | ((uint32_t)buf[4 * k + 1] << 8) | ((uint32_t)buf[4 * k + 2] << 16) | ((uint32_t)buf[4 * k + 3] << 24);
+                if (k == 7) w[k] &= 0x7FFFFFFFu;
+                nz |= w[k];
+            }
+            bool lt = false, decided = false;
+            for (int k = 7; k >= 0; k--) {
+                if (!decided && w[k] != FR_R[k]) {
+                    lt = w[k] < FR_R[k];
+                    decided = true;
+                }
+            }
+            __syncwarp();  // every lane has read the bytes before another draw may overwrite them
+            if (lt && nz) break;
+        }
+        if (lane == 0) buf[31] &= 0x7F;
+        __syncwarp();
+        cs_append(s, L_VEC_A, 18, buf, 32);
+        vec_a_out[((size_t)pr * ell + i) * 32 + lane] = buf[lane];
+        __syncwarp();
+    }
+    uint64_t *so = state_out + (size_t)pr * 26;
+    if (lane < 25) so[lane] = reinterpret_cast<const uint64_t *>(st)[lane];
+    if (lane == 0) so[25] = (uint64_t)s.pos | ((uint64_t)s.pos_begin << 8);
+}
+#undef CTA_FOR
+#undef CTA_SYNC
+#undef CTA_LEADER
+#endif
+
+#ifndef CDP_TRANSCRIPT_HOST_HARNESS
 cudaError_t launch_transcript_open(cudaStream_t st, const uint8_t *comp_vecs, const uint8_t *comp_M, uint32_t ell, uint32_t B, uint8_t *vec_a_out,
                                    uint64_t *state_out) {
     if (B == 0) return cudaSuccess;
-    k_transcript_open<<<(B + 31) / 32, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
+    static const bool warp = [] { const char *e = getenv("CDP_TRANSCRIPT_WARP"); return !e || atoi(e) != 0; }();
+    if (warp) k_transcript_open_warp<<<B, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
+    else k_transcript_open<<<(B + 31) / 32, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
     return cudaGetLastError();
 }
 cudaError_t launch_verify_transcript_a(cudaStream_t st, const uint8_t *pcomp, const uint8_t *pscal, const uint8_t *comp_M, const uint8_t *vec_a,
