@@ -282,6 +282,8 @@ __device__ vcoef::fr_t draw_challenge(strobe_t &s, const uint8_t *label, uint32_
 __device__ __forceinline__ void chal_store(uint32_t *dst, const vcoef::fr_t &x) {
     for (int k = 0; k < 8; k++) dst[k] = x.v[k];
 }
+// the thread that writes a proof's results: with one thread per proof, that thread
+__device__ __forceinline__ bool is_leader(const strobe_t &) { return true; }
 
 }  // namespace
 
@@ -289,15 +291,12 @@ __device__ __forceinline__ void chal_store(uint32_t *dst, const vcoef::fr_t &x) 
 // z_u, x_final), comp_M: B encodings, vec_a: B x ell canonical, state: B x 26 u64 (in/out).  Outputs: chal[pr][12..15] (Montgomery),
 // tmp[pr][0..1] = grand product, beta_g (Montgomery), stage_scal[pr][6] canonical = {1, -beta_g^-1, alpha_g, 1, 1, 1}, flags[pr] = 1 when
 // vec_T[0] (first encoding of the T block of comp_vecs, B x 4 x ell encodings) is the identity.
-__global__ void __launch_bounds__(32) k_verify_transcript_a(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
-                                                            const uint8_t *__restrict__ comp_M, const uint8_t *__restrict__ vec_a, uint32_t ell,
-                                                            uint32_t np, uint32_t vch, uint32_t B, uint64_t *__restrict__ state,
-                                                            uint32_t *__restrict__ chal, uint32_t *__restrict__ tmp, uint32_t *__restrict__ stage_scal,
-                                                            const uint8_t *__restrict__ comp_vecs, uint8_t *__restrict__ flags) {
+template <class S>
+__device__ __forceinline__ void verify_transcript_a_body(S &s, uint32_t pr, const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                         const uint8_t *__restrict__ comp_M, const uint8_t *__restrict__ vec_a, uint32_t ell, uint32_t np,
+                                                         uint32_t vch, uint64_t *__restrict__ state, uint32_t *__restrict__ chal, uint32_t *__restrict__ tmp,
+                                                         uint32_t *__restrict__ stage_scal, const uint8_t *__restrict__ comp_vecs, uint8_t *__restrict__ flags) {
     using namespace vcoef;
-    const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pr >= B) return;
-    strobe_t s;
     state_load(s, state + (size_t)pr * 26);
     const uint8_t *pc = pcomp + (size_t)pr * np * 48;
     const uint8_t *va = vec_a + (size_t)pr * ell * 32;
@@ -323,6 +322,7 @@ __global__ void __launch_bounds__(32) k_verify_transcript_a(const uint8_t *__res
     const fr_t beta_g = draw_challenge(s, L_GPB, 10);
     const fr_t beta_inv = fr_inverse(beta_g);
     state_store(state + (size_t)pr * 26, s);
+    if (!is_leader(s)) return;
     uint32_t *ch = chal + 8 * (size_t)pr * vch;
     chal_store(ch + 8 * CH_ALPHA_SP, alpha_sp); chal_store(ch + 8 * CH_BETA_SP, beta_sp);
     chal_store(ch + 8 * CH_ALPHA_G, alpha_g); chal_store(ch + 8 * CH_BETA_INV, beta_inv);
@@ -335,17 +335,25 @@ __global__ void __launch_bounds__(32) k_verify_transcript_a(const uint8_t *__res
     if (flags) flags[pr] = (comp_vecs[(((size_t)pr * 4 + 2) * ell) * 48] & 0x40) ? 1 : 0;
 }
 
-// da_comp: B x 2 encodings (D, A'), comp_T / comp_U: the instance's vec_T / vec_U encodings of proof pr at comp_vecs + ((pr * 4 + 2 | 3) * ell) * 48,
-// H_comp: the encoding of crs.H.  Completes chal[pr][16..26] and the four challenge vectors.
-__global__ void __launch_bounds__(32) k_verify_transcript_b(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
-                                                            const uint8_t *__restrict__ da_comp, const uint8_t *__restrict__ comp_vecs,
-                                                            const uint8_t *__restrict__ H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch,
-                                                            uint32_t B, uint64_t *__restrict__ state, uint32_t *__restrict__ chal,
-                                                            const uint32_t *__restrict__ tmp) {
-    using namespace vcoef;
+__global__ void __launch_bounds__(32) k_verify_transcript_a(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                            const uint8_t *__restrict__ comp_M, const uint8_t *__restrict__ vec_a, uint32_t ell,
+                                                            uint32_t np, uint32_t vch, uint32_t B, uint64_t *__restrict__ state,
+                                                            uint32_t *__restrict__ chal, uint32_t *__restrict__ tmp, uint32_t *__restrict__ stage_scal,
+                                                            const uint8_t *__restrict__ comp_vecs, uint8_t *__restrict__ flags) {
     const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
     if (pr >= B) return;
     strobe_t s;
+    verify_transcript_a_body(s, pr, pcomp, pscal, comp_M, vec_a, ell, np, vch, state, chal, tmp, stage_scal, comp_vecs, flags);
+}
+
+// da_comp: B x 2 encodings (D, A'), comp_T / comp_U: the instance's vec_T / vec_U encodings of proof pr at comp_vecs + ((pr * 4 + 2 | 3) * ell) * 48,
+// H_comp: the encoding of crs.H.  Completes chal[pr][16..26] and the four challenge vectors.
+template <class S>
+__device__ __forceinline__ void verify_transcript_b_body(S &s, uint32_t pr, const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                         const uint8_t *__restrict__ da_comp, const uint8_t *__restrict__ comp_vecs,
+                                                         const uint8_t *__restrict__ H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch,
+                                                         uint64_t *__restrict__ state, uint32_t *__restrict__ chal, const uint32_t *__restrict__ tmp) {
+    using namespace vcoef;
     state_load(s, state + (size_t)pr * 26);
     const uint8_t *pc = pcomp + (size_t)pr * np * 48;
     const uint32_t n = ell + 4;
@@ -374,10 +382,10 @@ __global__ void __launch_bounds__(32) k_verify_transcript_b(const uint8_t *__res
         append_point(s, L_IPL, 8, pc + 48 * (L_LC + k)); append_point(s, L_IPL, 8, pc + 48 * (L_LD + k));
         append_point(s, L_IPL, 8, pc + 48 * (L_RC + k)); append_point(s, L_IPL, 8, pc + 48 * (L_RD + k));
         g[k] = draw_challenge(s, L_IPG, 9);
-        chal_store(ch + 8 * (CH_VEC + k), g[k]);
+        if (is_leader(s)) chal_store(ch + 8 * (CH_VEC + k), g[k]);
     }
     fr_batch_inverse(g, m);
-    for (uint32_t k = 0; k < m; k++) chal_store(ch + 8 * (CH_VEC + m + k), g[k]);
+    if (is_leader(s)) for (uint32_t k = 0; k < m; k++) chal_store(ch + 8 * (CH_VEC + m + k), g[k]);
     // SameScalar
     {
         const uint32_t ss[10] = {L_R, L_S, L_T1, L_T2, L_U1, L_U2, L_A1, L_A2, L_B1, L_B2};
@@ -417,15 +425,27 @@ __global__ void __launch_bounds__(32) k_verify_transcript_b(const uint8_t *__res
 #pragma unroll 1
         for (int q = 0; q < 6; q++) append_point(s, L_SML, 13, pc + 48 * (o[q] + k));
         g[k] = draw_challenge(s, L_SMG, 14);
-        chal_store(ch + 8 * (CH_VEC + 2 * m + k), g[k]);
+        if (is_leader(s)) chal_store(ch + 8 * (CH_VEC + 2 * m + k), g[k]);
     }
     fr_batch_inverse(g, m);
-    for (uint32_t k = 0; k < m; k++) chal_store(ch + 8 * (CH_VEC + 3 * m + k), g[k]);
+    if (is_leader(s)) for (uint32_t k = 0; k < m; k++) chal_store(ch + 8 * (CH_VEC + 3 * m + k), g[k]);
     state_store(state + (size_t)pr * 26, s);
+    if (!is_leader(s)) return;
     chal_store(ch + 8 * CH_ALPHA_I, alpha_i); chal_store(ch + 8 * CH_BETA_I, beta_i); chal_store(ch + 8 * CH_Z, z);
     chal_store(ch + 8 * CH_C, PS(1)); chal_store(ch + 8 * CH_D, PS(2)); chal_store(ch + 8 * CH_X, PS(6));
     chal_store(ch + 8 * CH_ALPHA_SM, alpha_sm); chal_store(ch + 8 * CH_ALPHA_SS, alpha_ss);
     chal_store(ch + 8 * CH_ZK, PS(3)); chal_store(ch + 8 * CH_ZT, PS(4)); chal_store(ch + 8 * CH_ZU, PS(5));
+}
+
+__global__ void __launch_bounds__(32) k_verify_transcript_b(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                            const uint8_t *__restrict__ da_comp, const uint8_t *__restrict__ comp_vecs,
+                                                            const uint8_t *__restrict__ H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch,
+                                                            uint32_t B, uint64_t *__restrict__ state, uint32_t *__restrict__ chal,
+                                                            const uint32_t *__restrict__ tmp) {
+    const uint32_t pr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pr >= B) return;
+    strobe_t s;
+    verify_transcript_b_body(s, pr, pcomp, pscal, da_comp, comp_vecs, H_comp, ell, m, np, vch, state, chal, tmp);
 }
 
 #ifndef CDP_TRANSCRIPT_HOST_HARNESS
@@ -497,17 +517,107 @@ __global__ void __launch_bounds__(32) k_transcript_open_warp(const uint8_t *__re
     if (lane < 25) so[lane] = reinterpret_cast<const uint64_t *>(st)[lane];
     if (lane == 0) so[25] = (uint64_t)s.pos | ((uint64_t)s.pos_begin << 8);
 }
+// ---- the verifier's transcript kernels with one warp per proof: the same bodies (verify_transcript_a_body / _b_body) over a STROBE state in
+// shared memory.  Every lane runs the scalar algebra redundantly (same latency as one thread), lane 0 writes the results.
+namespace {
+struct wstrobe {
+    cstr::cstrobe c;
+    uint8_t *buf;  // 64 shared bytes
+};
+__device__ __forceinline__ bool is_leader(const wstrobe &) { return threadIdx.x == 0; }
+__device__ __forceinline__ void state_load(wstrobe &s, const uint64_t *src) {
+    if (threadIdx.x < 25) reinterpret_cast<uint64_t *>(s.c.st)[threadIdx.x] = src[threadIdx.x];
+    s.c.pos = (uint32_t)(src[25] & 0xFF);
+    s.c.pos_begin = (uint32_t)((src[25] >> 8) & 0xFF);
+    __syncwarp();
+}
+__device__ __forceinline__ void state_store(uint64_t *dst, const wstrobe &s) {
+    __syncwarp();
+    if (threadIdx.x < 25) dst[threadIdx.x] = reinterpret_cast<const uint64_t *>(s.c.st)[threadIdx.x];
+    if (threadIdx.x == 0) dst[25] = (uint64_t)s.c.pos | ((uint64_t)s.c.pos_begin << 8);
+}
+__device__ __forceinline__ void strobe_begin(wstrobe &s, uint32_t flags, bool more) {
+    if (!more) cstr::cs_begin(s.c, flags);
+}
+__device__ __forceinline__ void strobe_meta_ad(wstrobe &s, const uint8_t *d, uint32_t n, bool more) {
+    if (!more) cstr::cs_begin(s.c, cstr::FLAG_M | cstr::FLAG_A);
+    cstr::cs_absorb(s.c, d, n);
+}
+__device__ __forceinline__ void strobe_absorb_value(wstrobe &s, uint64_t v, uint32_t nbytes) { cstr::cs_value(s.c, v, nbytes); }
+__device__ __forceinline__ void strobe_absorb(wstrobe &s, const uint8_t *d, uint32_t n) { cstr::cs_absorb(s.c, d, n); }
+__device__ __forceinline__ void strobe_absorb_byte(wstrobe &s, uint32_t v) { cstr::cs_byte(s.c, v); }
+__device__ __forceinline__ void merlin_append(wstrobe &s, const uint8_t *label, uint32_t llen, uint64_t prefix, uint32_t plen, const uint8_t *body,
+                                              uint32_t blen) {
+    cstr::cs_append_header(s.c, label, llen, plen + blen);
+    cstr::cs_value(s.c, prefix, plen);
+    cstr::cs_absorb(s.c, body, blen);
+}
+__device__ __forceinline__ void append_point(wstrobe &s, const uint8_t *label, uint32_t llen, const uint8_t *comp) {
+    cstr::cs_append(s.c, label, llen, comp, 48);
+}
+__device__ void append_fr(wstrobe &s, const uint8_t *label, uint32_t llen, const vcoef::fr_t &x_mont) {
+    if (threadIdx.x == 0) vcoef::fr_store_canonical(reinterpret_cast<uint32_t *>(s.buf), x_mont);
+    __syncwarp();
+    cstr::cs_append(s.c, label, llen, s.buf, 32);
+    __syncwarp();
+}
+__device__ vcoef::fr_t draw_challenge(wstrobe &s, const uint8_t *label, uint32_t llen) {
+    vcoef::fr_t c;
+    for (;;) {
+        cstr::cs_challenge_bytes(s.c, label, llen, s.buf, 64);
+        uint32_t nz = 0;
+        for (int k = 0; k < 8; k++) {
+            c.v[k] = reinterpret_cast<const uint32_t *>(s.buf)[k];
+            if (k == 7) c.v[k] &= 0x7FFFFFFFu;
+            nz |= c.v[k];
+        }
+        const bool ok = nz && !vcoef::fr_geq_mod(c.v);
+        __syncwarp();  // every lane has read the bytes before another draw may overwrite them
+        if (ok) break;
+    }
+    if (threadIdx.x == 0) s.buf[31] &= 0x7F;
+    __syncwarp();
+    cstr::cs_append(s.c, label, llen, s.buf, 32);
+    __syncwarp();
+    return vcoef::fr_to_mont(c);
+}
+}  // namespace
+__global__ void __launch_bounds__(32) k_verify_transcript_a_warp(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                                 const uint8_t *__restrict__ comp_M, const uint8_t *__restrict__ vec_a, uint32_t ell,
+                                                                 uint32_t np, uint32_t vch, uint32_t B, uint64_t *__restrict__ state,
+                                                                 uint32_t *__restrict__ chal, uint32_t *__restrict__ tmp,
+                                                                 uint32_t *__restrict__ stage_scal, const uint8_t *__restrict__ comp_vecs,
+                                                                 uint8_t *__restrict__ flags) {
+    __shared__ __align__(8) uint8_t st[200];
+    __shared__ __align__(8) uint8_t buf[64];
+    wstrobe s{{st, 0, 0}, buf};
+    verify_transcript_a_body(s, blockIdx.x, pcomp, pscal, comp_M, vec_a, ell, np, vch, state, chal, tmp, stage_scal, comp_vecs, flags);
+}
+__global__ void __launch_bounds__(32) k_verify_transcript_b_warp(const uint8_t *__restrict__ pcomp, const uint8_t *__restrict__ pscal,
+                                                                 const uint8_t *__restrict__ da_comp, const uint8_t *__restrict__ comp_vecs,
+                                                                 const uint8_t *__restrict__ H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch,
+                                                                 uint32_t B, uint64_t *__restrict__ state, uint32_t *__restrict__ chal,
+                                                                 const uint32_t *__restrict__ tmp) {
+    __shared__ __align__(8) uint8_t st[200];
+    __shared__ __align__(8) uint8_t buf[64];
+    wstrobe s{{st, 0, 0}, buf};
+    verify_transcript_b_body(s, blockIdx.x, pcomp, pscal, da_comp, comp_vecs, H_comp, ell, m, np, vch, state, chal, tmp);
+}
 #undef CTA_FOR
 #undef CTA_SYNC
 #undef CTA_LEADER
 #endif
 
 #ifndef CDP_TRANSCRIPT_HOST_HARNESS
+// one warp per proof (default) or the one-thread-per-proof kernels (CDP_TRANSCRIPT_WARP=0)
+static bool transcript_warp() {
+    static const bool warp = [] { const char *e = getenv("CDP_TRANSCRIPT_WARP"); return !e || atoi(e) != 0; }();
+    return warp;
+}
 cudaError_t launch_transcript_open(cudaStream_t st, const uint8_t *comp_vecs, const uint8_t *comp_M, uint32_t ell, uint32_t B, uint8_t *vec_a_out,
                                    uint64_t *state_out) {
     if (B == 0) return cudaSuccess;
-    static const bool warp = [] { const char *e = getenv("CDP_TRANSCRIPT_WARP"); return !e || atoi(e) != 0; }();
-    if (warp) k_transcript_open_warp<<<B, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
+    if (transcript_warp()) k_transcript_open_warp<<<B, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
     else k_transcript_open<<<(B + 31) / 32, 32, 0, st>>>(comp_vecs, comp_M, ell, B, vec_a_out, state_out);
     return cudaGetLastError();
 }
@@ -515,14 +625,16 @@ cudaError_t launch_verify_transcript_a(cudaStream_t st, const uint8_t *pcomp, co
                                        uint32_t ell, uint32_t np, uint32_t vch, uint32_t B, uint64_t *state, uint32_t *chal, uint32_t *tmp,
                                        uint32_t *stage_scal, const uint8_t *comp_vecs, uint8_t *flags) {
     if (B == 0) return cudaSuccess;
-    k_verify_transcript_a<<<(B + 31) / 32, 32, 0, st>>>(pcomp, pscal, comp_M, vec_a, ell, np, vch, B, state, chal, tmp, stage_scal, comp_vecs, flags);
+    if (transcript_warp()) k_verify_transcript_a_warp<<<B, 32, 0, st>>>(pcomp, pscal, comp_M, vec_a, ell, np, vch, B, state, chal, tmp, stage_scal, comp_vecs, flags);
+    else k_verify_transcript_a<<<(B + 31) / 32, 32, 0, st>>>(pcomp, pscal, comp_M, vec_a, ell, np, vch, B, state, chal, tmp, stage_scal, comp_vecs, flags);
     return cudaGetLastError();
 }
 cudaError_t launch_verify_transcript_b(cudaStream_t st, const uint8_t *pcomp, const uint8_t *pscal, const uint8_t *da_comp, const uint8_t *comp_vecs,
                                        const uint8_t *H_comp, uint32_t ell, uint32_t m, uint32_t np, uint32_t vch, uint32_t B, uint64_t *state,
                                        uint32_t *chal, const uint32_t *tmp) {
     if (B == 0) return cudaSuccess;
-    k_verify_transcript_b<<<(B + 31) / 32, 32, 0, st>>>(pcomp, pscal, da_comp, comp_vecs, H_comp, ell, m, np, vch, B, state, chal, tmp);
+    if (transcript_warp()) k_verify_transcript_b_warp<<<B, 32, 0, st>>>(pcomp, pscal, da_comp, comp_vecs, H_comp, ell, m, np, vch, B, state, chal, tmp);
+    else k_verify_transcript_b<<<(B + 31) / 32, 32, 0, st>>>(pcomp, pscal, da_comp, comp_vecs, H_comp, ell, m, np, vch, B, state, chal, tmp);
     return cudaGetLastError();
 }
 #endif

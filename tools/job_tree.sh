@@ -1,6 +1,3 @@
-python -m pytest tests/test_gpu_transcript.py tests/test_gpu_prover.py tests/test_gpu_verifier.py -x -q -m gpu 2>&1 | tail -3
-python tools/prover_profile.py 252 512 1 2>&1 | grep "prove_stage\|transcript\|sum\|ell=" | cut -c1-120
-python tools/verifier_profile.py 252 512 1 2>&1 | grep "transcript\|sum\|ell=" | cut -c1-150
-python tools/verifier_profile.py 252 4096 8 2>&1 | grep "transcript\|sum\|ell=" | cut -c1-150
-python tools/prover_timing.py 252 128 4 2>&1 | grep "B=128" | cut -c1-150
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/vlaunches.csv python tools/verifier_profile.py 252 512 1 > /dev/null 2>&1
+for w in 1 0 1 0; do CDP_TRANSCRIPT_WARP=$w python bench.py --no-cpu-baseline --msm-sizes '' --no-extras --steps 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('warp=$w proofs/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'verifies/s', round(d['verify']['value']), 'ms', d['verify']['ms_per_step'])"; done
