@@ -667,8 +667,17 @@ static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
     // waves of WAVE resident threads (4 CTAs of 128 per SM at 128 registers): K is the smallest that packs the round into w FULL waves, w the fewest waves with K <= K_MAX
     static const uint32_t K_MAX = env_u32("CDP_BA_KMAX", 128), WAVE = env_u32("CDP_BA_WAVE", 148 * 4 * 128);
     uint32_t *sbuf[2] = {(uint32_t *)(ws + o_s0), (uint32_t *)(ws + o_s1)};
-    for (int r = 0; r < BA_STATS_ROUNDS && h_stats[3 * r]; r++) {
+    int total_rounds = 0;
+    while (total_rounds < BA_STATS_ROUNDS && h_stats[3 * total_rounds]) total_rounds++;
+    // the tail of a deep tree (short list, at most 2^FIN_ROUNDS elements per bucket left; 0 = never): one thread per bucket instead of more rounds
+    static const uint32_t FIN_LIST = env_u32("CDP_BA_FINISH_LIST", 32768), FIN_ROUNDS = getenv("CDP_BA_FINISH_ROUNDS") ? (uint32_t)atoi(getenv("CDP_BA_FINISH_ROUNDS")) : 5u;
+    for (int r = 0; r < total_rounds; r++) {
         const uint32_t pairs = h_stats[3 * r], list_len = r == 0 ? (uint32_t)slots : h_stats[3 * r + 2];
+        if (list_len <= FIN_LIST && (uint32_t)(total_rounds - r) <= FIN_ROUNDS && total_rounds - r >= 2) {
+            launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, 0);
+            CUDA_TRY(ctx, launch_ba_finish(ctx->stream, r == 0, act[r & 1], slots, list_len, P, bx, vals2, sbuf[(r + 1) & 1], baff));
+            break;
+        }
         if (h_stats[3 * r + 1] > ((r & 1) ? s1n : s0n)) return fail(ctx, CDP_ERR_TOO_LARGE, "cdp_msm: round buffer too small");  // cannot happen: sized for the worst case
         const uint32_t waves = std::max(1u, (uint32_t)(((uint64_t)pairs + (uint64_t)K_MAX * WAVE - 1) / ((uint64_t)K_MAX * WAVE)));
         const uint32_t K = std::max(1u, (uint32_t)(((uint64_t)pairs + (uint64_t)waves * WAVE - 1) / ((uint64_t)waves * WAVE)));

@@ -207,6 +207,43 @@ __global__ void __launch_bounds__(128, 4) k_ba_round(uint32_t total, uint32_t K,
     ba_run<ba_jobs_src<In>, BA_INLINE>(src, tid, T, total, K, pf);
 }
 
+// The last few rounds of a deep tree are short lists of buckets with a handful of elements each (the top window: 2^14 buckets of 512 points
+// are 16 elements after five rounds) -- every one a scan, a job list and an inversion's latency for almost no work.  Once the list is short
+// and at most 2^5 elements are left per bucket, one thread per bucket sums what is left (XYZZ mixed additions) and normalises it itself.
+template <class In>
+__global__ void __launch_bounds__(128, 3) k_ba_finish(const uint32_t *__restrict__ act_pos, const uint32_t *__restrict__ act_m,
+                                                      const uint32_t *__restrict__ act_id, uint32_t list_len, In in, uint32_t *__restrict__ bucket_aff) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= list_len) return;
+    const uint32_t m = act_m[a], pos = act_pos[a];
+    if (m < 2) return;  // round 0 lists every bucket; those were final at once
+    g1x acc;
+    g1x_set_inf(acc);
+#pragma unroll 1
+    for (uint32_t i = 0; i < m; i++) {
+        g1a q;
+        in.point(in.operand(pos + i), q);
+        g1x_add_mixed(acc, acc, q);
+    }
+    g1j j;
+    g1x_to_jac(j, acc);
+    g1a R;
+    fp zi, zi2;
+    fp_inv(zi, j.Z);  // 0 -> 0: infinity comes out as (0, 0)
+    fp_sqr(zi2, zi);
+    fp_mul(R.x, j.X, zi2);
+    fp_mul(zi2, zi2, zi);
+    fp_mul(R.y, j.Y, zi2);
+    g1a_store(bucket_aff + 24 * (size_t)act_id[a], R);
+}
+cudaError_t launch_ba_finish(cudaStream_t st, bool first, const uint32_t *act, size_t act_stride, uint32_t list_len, const uint32_t *pts, const uint32_t *bx,
+                             const uint32_t *vals, const uint32_t *in, uint32_t *bucket_aff) {
+    const unsigned g = (list_len + 127) / 128;
+    if (first) k_ba_finish<ba_gather><<<g, 128, 0, st>>>(act, act + act_stride, act + 2 * act_stride, list_len, ba_gather{pts, bx, vals}, bucket_aff);
+    else k_ba_finish<ba_array><<<g, 128, 0, st>>>(act, act + act_stride, act + 2 * act_stride, list_len, ba_array{in}, bucket_aff);
+    return cudaGetLastError();
+}
+
 size_t ba_scan_temp_bytes(size_t n) {
     size_t bytes = 0;
     cub::DeviceScan::InclusiveScan(nullptr, bytes, (const ba_scan_t *)nullptr, (ba_scan_t *)nullptr, ba_scan_add(), (int)n);

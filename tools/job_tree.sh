@@ -1,3 +1,5 @@
-for w in 1 0 1 0; do CDP_TRANSCRIPT_WARP=$w python bench.py --no-cpu-baseline --msm-sizes '' --no-extras --steps 3 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('warp=$w proofs/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'verifies/s', round(d['verify']['value']), 'ms', d['verify']['ms_per_step'])"; done
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "large_pippenger" 2>&1 | tail -2
+python tools/msm_latency.py 20 22 2>&1 | tail -3
+CDP_BA_FINISH_ROUNDS=0 python tools/msm_latency.py 20 22 2>&1 | tail -3
+CDP_BA_FINISH_ROUNDS=5 python tools/msm_latency.py 20 22 2>&1 | tail -3
+CDP_BIG_BA_MIN_LOG2=16 python tools/msm_latency.py 16 19 2>&1 | tail -4
