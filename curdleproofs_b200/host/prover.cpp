@@ -266,10 +266,19 @@ void build_stage(Lane *p, MsmStage &st, const std::vector<SegSpec> &specs, size_
             if (!specs[i].fixed && eff(specs[i]) * 8 <= big && eff(specs[i]) < 12) { cls[i] = 1; split = true; }
     }
     const int n_var = any_var ? (split ? 2 : 1) : 0;
+    // fixed-base: the long, equally long segments (>= 64 pairs: what the tree path of cdp_msm_fixed_batch_dev_tree wants) apart from the short ones
+    size_t flo = (size_t)-1, fhi = 0, n_long = 0, n_fixed = 0;
+    for (auto &s : specs) {
+        if (!s.fixed) continue;
+        n_fixed++;
+        if (eff(s) >= 64) { n_long++; flo = std::min(flo, eff(s)); fhi = std::max(fhi, eff(s)); }
+    }
+    const bool fsplit = n_long > 0 && n_long < n_fixed && fhi <= flo + 1;
     for (size_t i = 0; i < specs.size(); i++)
-        if (specs[i].fixed) cls[i] = n_var;
-    st.subs.assign(n_var + (any_fixed ? 1 : 0), SubLaunch());
+        if (specs[i].fixed) cls[i] = n_var + (fsplit && eff(specs[i]) < 64 ? 1 : 0);
+    st.subs.assign(n_var + (any_fixed ? (fsplit ? 2 : 1) : 0), SubLaunch());
     if (any_fixed) st.subs[n_var].fixed = true;
+    if (fsplit) st.subs[n_var + 1].fixed = true;
     st.where.resize(specs.size());
     for (size_t i = 0; i < specs.size(); i++) {
         SubLaunch &sl = st.subs[cls[i]];
