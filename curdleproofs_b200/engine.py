@@ -175,7 +175,7 @@ class Engine:
         self._check(self._lib.cdp_set_big_msm_min(self._h, n_pairs), "cdp_set_big_msm_min")
 
     def set_big_ba_min(self, n_pairs: int):
-        """Pairs from which the large Pippenger sums its buckets by rounds of batched affine additions (0 = the built-in 2^20)."""
+        """Pairs from which the large Pippenger sums its buckets by rounds of batched affine additions (0 = the built-in 2^19)."""
         self._check(self._lib.cdp_set_big_ba_min(self._h, n_pairs), "cdp_set_big_ba_min")
 
     def sync(self):

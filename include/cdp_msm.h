@@ -126,7 +126,7 @@ int cdp_msm_dev(cdp_ctx *ctx, const uint8_t *d_affine_pts, const uint8_t *d_scal
  * tests that must reach the large path at sizes the CPU oracle finishes in seconds. */
 int cdp_set_big_msm_min(cdp_ctx *ctx, size_t n_pairs);
 /* Inside the large Pippenger the bucket sums are rounds of batched affine additions (5M + 1S per addition, one shared inversion per
- * thread) from 2^20 pairs on, and one thread per bucket with XYZZ additions below.  Same purpose and argument rules as above. */
+ * thread) from 2^19 pairs on, and one thread per bucket with XYZZ additions below.  Same purpose and argument rules as above. */
 int cdp_set_big_ba_min(cdp_ctx *ctx, size_t n_pairs);
 
 /* d_out_jac = sum of `count` Jacobian points.  The multi-GPU combine of a base-range-sharded MSM: every rank all-gathers the
