@@ -481,6 +481,15 @@ extern "C" int cdp_round_expand_dev(cdp_ctx *ctx, const uint8_t *d_compact, cons
 
 extern "C" size_t cdp_prove_work_scalars(size_t ell) { return 11 * (ell + 4) + 64; }
 extern "C" size_t cdp_prove_random_scalars(size_t ell) { return 3 * (ell + 4) + 11; }
+extern "C" int cdp_prove_random_dev(cdp_ctx *ctx, const uint8_t *d_keys, const uint64_t *d_skip_words, size_t batch, size_t ell, uint8_t *d_random) {
+    if (!ctx || !d_keys || !d_random || ell < 4) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_random_dev: bad argument");
+    if (batch == 0) return CDP_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    launch_scope ls(ctx, CDP_PROFILE_PROVE_STAGE, batch);
+    CUDA_TRY(ctx, launch_prove_random(ctx->stream, reinterpret_cast<const uint32_t *>(d_keys), d_skip_words, (uint32_t)ell, (uint32_t)batch,
+                                      reinterpret_cast<uint32_t *>(d_random)));
+    return CDP_OK;
+}
 extern "C" int cdp_prove_stage_dev(cdp_ctx *ctx, const cdp_prove_dev *P, int stage, unsigned round) {
     if (!ctx || !P || stage < CDP_PS_S1 || stage > CDP_PS_SM_ROUND) return fail(ctx, CDP_ERR_INVALID_ARG, "cdp_prove_stage_dev: bad argument");
     if (P->batch == 0) return CDP_OK;

@@ -663,6 +663,70 @@ __global__ void __launch_bounds__(256) k_prove_stage(const __grid_constant__ cdp
 }
 
 #ifndef CDP_PROVE_HOST_HARNESS
+// ---- the prover's randomness on the device.  The reference takes `rng: &mut impl RngCore` (/root/reference/src/curdleproofs.rs:74; its tests:
+// `StdRng` = ChaCha12, rand 0.8) and every draw of `CurdleproofsProof::new` is `Fr::rand` (ark-ff: four u64 = eight consecutive words of the
+// stream, top bit cleared, rejected when >= r, taken as the Montgomery representation).  So attempt a of a proof sits at words
+// [skip + 8a, skip + 8a + 8) of its keystream -- independent of every other attempt -- and the i-th ACCEPTED one is the i-th draw.  One warp
+// per proof: lane l computes the ChaCha12 blocks of attempt a0 + l, a ballot ranks the accepted ones, and they are stored in the draw order
+// of host/prover.cpp (the two r_d entries the device solves for are left zero).  The host hands over 32-byte keys instead of 25 KB of
+// scalars per proof and no longer runs the cipher (it was most of the host's time per step).
+__device__ __forceinline__ uint32_t cc_rotl(uint32_t v, int n) { return (v << n) | (v >> (32 - n)); }
+__device__ __forceinline__ void cc_qr(uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+    a += b; d = cc_rotl(d ^ a, 16);
+    c += d; b = cc_rotl(b ^ c, 12);
+    a += b; d = cc_rotl(d ^ a, 8);
+    c += d; b = cc_rotl(b ^ c, 7);
+}
+// block `ctr` of the ChaCha12 keystream (64-bit counter, stream 0: rand_chacha's ChaCha12Rng) to out[0..16)
+__device__ __forceinline__ void chacha12_block(const uint32_t *key, uint64_t ctr, uint32_t *out) {
+    const uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                             key[4], key[5], key[6], key[7], (uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t x0 = in[0], x1 = in[1], x2 = in[2], x3 = in[3], x4 = in[4], x5 = in[5], x6 = in[6], x7 = in[7], x8 = in[8], x9 = in[9], x10 = in[10],
+             x11 = in[11], x12 = in[12], x13 = in[13], x14 = in[14], x15 = in[15];
+#pragma unroll 1
+    for (int r = 0; r < 6; r++) {
+        cc_qr(x0, x4, x8, x12); cc_qr(x1, x5, x9, x13); cc_qr(x2, x6, x10, x14); cc_qr(x3, x7, x11, x15);
+        cc_qr(x0, x5, x10, x15); cc_qr(x1, x6, x11, x12); cc_qr(x2, x7, x8, x13); cc_qr(x3, x4, x9, x14);
+    }
+    out[0] = x0 + in[0]; out[1] = x1 + in[1]; out[2] = x2 + in[2]; out[3] = x3 + in[3]; out[4] = x4 + in[4]; out[5] = x5 + in[5];
+    out[6] = x6 + in[6]; out[7] = x7 + in[7]; out[8] = x8 + in[8]; out[9] = x9 + in[9]; out[10] = x10 + in[10]; out[11] = x11 + in[11];
+    out[12] = x12 + in[12]; out[13] = x13 + in[13]; out[14] = x14 + in[14]; out[15] = x15 + in[15];
+}
+__global__ void __launch_bounds__(32) k_prove_random(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ skip_words, uint32_t n,
+                                                     uint32_t nrnd, uint32_t *__restrict__ out) {
+    __shared__ uint32_t sm[32][33];  // lane l's two blocks (32 words) in row l
+    const uint32_t pr = blockIdx.x, lane = threadIdx.x;
+    uint32_t key[8];
+    for (int k = 0; k < 8; k++) key[k] = keys[8 * (size_t)pr + k];
+    const uint64_t sk = skip_words ? skip_words[pr] : 0;
+    uint32_t *o = out + 8 * (size_t)pr * nrnd;
+    const uint32_t need = 3 * n + 9, solved = 6 + 2 * n - 2;  // draws; first of the two slots the device solves for (left zero)
+    if (lane < 16) o[8 * (size_t)solved + lane] = 0;
+    uint32_t accepted = 0;
+#pragma unroll 1
+    for (uint64_t a0 = 0; accepted < need; a0 += 32) {
+        const uint64_t wo = sk + 8 * (a0 + lane);
+        const uint32_t off = (uint32_t)(wo & 15);
+        chacha12_block(key, wo >> 4, &sm[lane][0]);
+        if (off > 8) chacha12_block(key, (wo >> 4) + 1, &sm[lane][16]);  // the eight words run into the next block
+        vcoef::fr_t v;
+        for (int k = 0; k < 8; k++) v.v[k] = sm[lane][off + k];
+        v.v[7] &= 0x7FFFFFFFu;
+        const bool ok = !vcoef::fr_geq_mod(v.v);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, ok);
+        const uint32_t pos = accepted + __popc(ballot & ((1u << lane) - 1u));
+        if (ok && pos < need) {
+            uint32_t *dst = o + 8 * (size_t)(pos < solved ? pos : pos + 2);
+            for (int k = 0; k < 8; k++) dst[k] = v.v[k];
+        }
+        accepted += __popc(ballot);
+    }
+}
+cudaError_t launch_prove_random(cudaStream_t st, const uint32_t *keys, const uint64_t *skip_words, uint32_t ell, uint32_t batch, uint32_t *out) {
+    if (batch == 0) return cudaSuccess;
+    k_prove_random<<<batch, 32, 0, st>>>(keys, skip_words, ell + 4, 3 * (ell + 4) + 11, out);
+    return cudaGetLastError();
+}
 cudaError_t launch_prove_stage(cudaStream_t st, const cdp_prove_dev &P, int stage, uint32_t round) {
     if (P.batch == 0) return cudaSuccess;
     // one warp per proof by default: the steps are latency-bound (one thread hashes), so a CTA should hold as little of an SM as possible

@@ -73,6 +73,7 @@ cudaError_t launch_verify_coeffs(cudaStream_t st, const uint32_t *chal, const ui
 cudaError_t launch_transcript_open(cudaStream_t st, const uint8_t *comp_vecs, const uint8_t *comp_M, uint32_t ell, uint32_t B, uint8_t *vec_a_out,
                                    uint64_t *state_out);
 // k_prove.cu: one step of the prover's transcript + scalar algebra for a batch, one CTA per proof
+cudaError_t launch_prove_random(cudaStream_t st, const uint32_t *keys, const uint64_t *skip_words, uint32_t ell, uint32_t batch, uint32_t *out);
 cudaError_t launch_prove_stage(cudaStream_t st, const cdp_prove_dev &P, int stage, uint32_t round);
 cudaError_t launch_gather_points(cudaStream_t st, uint32_t *pts, const uint32_t *src, const uint32_t *src_idx, const uint32_t *dst_idx, uint32_t n);
 // window sums of `count` MSM segments; c in 2..6 selects the kernel instantiation

@@ -137,6 +137,7 @@ struct Lane {
     uint8_t *d_comp0 = nullptr;    // encodings of the instance (4 ell per proof, then one M per proof): read again by same_msm_step1
     uint8_t *d_compH = nullptr;    // encoding of crs.H
     uint32_t *d_perm = nullptr, *h_perm = nullptr;
+    uint8_t *d_keys = nullptr, *h_keys = nullptr;  // per proof: 32-byte ChaCha12 key | u64 stream position (cdp_prove_random_dev)
     uint8_t *d_wit = nullptr, *h_wit = nullptr, *d_rnd = nullptr, *h_rnd = nullptr, *d_work = nullptr, *d_side = nullptr, *d_proofs = nullptr,
             *h_proofs = nullptr;
     uint8_t *h_scal = nullptr, *h_fscal = nullptr, *h_comp = nullptr, *h_in = nullptr;
@@ -480,7 +481,7 @@ static void lane_destroy(Lane *p) {
                     (void *)p->d_idst, (void *)p->d_cidx, (void *)p->d_x1src, (void *)p->d_x1dst, (void *)p->d_x2src, (void *)p->d_x2dst, (void *)p->d_scal, (void *)p->d_fscal, (void *)p->d_cmp, (void *)p->d_ucan, (void *)p->d_jac, (void *)p->d_comp, (void *)p->d_veca, (void *)p->d_tstate, (void *)p->d_comp0, (void *)p->d_compH,
                     (void *)p->d_perm, (void *)p->d_wit, (void *)p->d_rnd, (void *)p->d_work, (void *)p->d_side, (void *)p->d_proofs})
         cdp_dev_free(c, d);
-    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_cmp, (void *)p->h_ucan, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_perm, (void *)p->h_wit, (void *)p->h_rnd, (void *)p->h_proofs}) cdp_host_free(c, h);
+    for (void *h : {(void *)p->h_scal, (void *)p->h_fscal, (void *)p->h_cmp, (void *)p->h_ucan, (void *)p->h_comp, (void *)p->h_in, (void *)p->h_veca, (void *)p->h_tstate, (void *)p->h_perm, (void *)p->h_wit, (void *)p->h_rnd, (void *)p->h_keys, (void *)p->h_proofs}) cdp_host_free(c, h);
     delete p;
 }
 
@@ -656,6 +657,7 @@ static int lane_create(Lane **out, cdp_ctx *ctx, const cdp_fixed_table *table, s
         p->d_perm = (uint32_t *)dalloc(max_batch * ell * 4); p->h_perm = (uint32_t *)halloc(max_batch * ell * 4);
         p->d_wit = (uint8_t *)dalloc(max_batch * 5 * 32); p->h_wit = (uint8_t *)halloc(max_batch * 5 * 32);
         p->d_rnd = (uint8_t *)dalloc(max_batch * nrnd * 32); p->h_rnd = (uint8_t *)halloc(max_batch * nrnd * 32);
+        p->d_keys = (uint8_t *)dalloc(max_batch * 40); p->h_keys = (uint8_t *)halloc(max_batch * 40);
         p->d_work = (uint8_t *)dalloc(max_batch * cdp_prove_work_scalars(ell) * 32);
         p->d_side = (uint8_t *)dalloc(max_batch * 96);
         p->d_proofs = (uint8_t *)dalloc(max_batch * psz); p->h_proofs = (uint8_t *)halloc(max_batch * psz);
@@ -762,13 +764,23 @@ static int lane_prove_device(Lane *p, size_t B, const cdp_prove_inputs *in, uint
     const int T = p->threads;
     const size_t proof_size = cdp_proof_size(ell), nrnd = cdp_prove_random_scalars(ell);
     double t0 = now_ms(), t_host = 0, t_wait = 0;
-    // witnesses and randomness (all draws in the reference's order; they do not depend on the transcript)
+    // witnesses and randomness (all draws in the reference's order; they do not depend on the transcript).  The generator runs on the device
+    // (cdp_prove_random_dev: the host hands over each proof's ChaCha12 key and stream position); CDP_PROVE_HOST_RNG=1 draws here instead
+    static const bool host_rng = [] { const char *e = getenv("CDP_PROVE_HOST_RNG"); return e && atoi(e) != 0; }();
     std::vector<int> rng_ok(B, 1);
     parallel_for(T, B, [&](size_t pr) {
         memcpy(p->h_perm + pr * ell, in->permutation + pr * ell, ell * 4);
         memcpy(p->h_wit + pr * 160, in->k + 32 * pr, 32);
         memcpy(p->h_wit + pr * 160 + 32, in->vec_m_blinders + 128 * pr, 128);
         StdRng rng(0);
+        if (!host_rng) {  // key and position only
+            if (in->rng_key) memcpy(p->h_keys + 32 * pr, in->rng_key + 32 * pr, 32);
+            else if (in->rng_seed) { rng = StdRng(in->rng_seed[pr]); memcpy(p->h_keys + 32 * pr, rng.key(), 32); }
+            else if (!StdRng::os_key(p->h_keys + 32 * pr)) { rng_ok[pr] = 0; return; }
+            const uint64_t skip = in->rng_skip_words ? in->rng_skip_words[pr] : 0;
+            memcpy(p->h_keys + 32 * B + 8 * pr, &skip, 8);
+            return;
+        }
         if (!make_rng(in, pr, rng)) { rng_ok[pr] = 0; return; }
         uint64_t *w = reinterpret_cast<uint64_t *>(p->h_rnd + pr * nrnd * 32);
         auto draw = [&](size_t slot) { Fr x = rng.fr_rand(); memcpy(w + 4 * slot, x.v, 32); };
@@ -785,8 +797,14 @@ static int lane_prove_device(Lane *p, size_t B, const cdp_prove_inputs *in, uint
     t0 = now_ms();
     PTRY(cdp_h2d(p->ctx, p->d_perm, p->h_perm, B * ell * 4));
     PTRY(cdp_h2d(p->ctx, p->d_wit, p->h_wit, B * 160));
-    PTRY(cdp_h2d(p->ctx, p->d_rnd, p->h_rnd, B * nrnd * 32));
-    p->h2d_bytes += B * (ell * 4 + 160 + nrnd * 32);
+    if (host_rng) {
+        PTRY(cdp_h2d(p->ctx, p->d_rnd, p->h_rnd, B * nrnd * 32));
+        p->h2d_bytes += B * (ell * 4 + 160 + nrnd * 32);
+    } else {
+        PTRY(cdp_h2d(p->ctx, p->d_keys, p->h_keys, B * 40));
+        PTRY(cdp_prove_random_dev(p->ctx, p->d_keys, reinterpret_cast<const uint64_t *>(p->d_keys + 32 * B), B, ell, p->d_rnd));
+        p->h2d_bytes += B * (ell * 4 + 160 + 40);
+    }
 
     cdp_prove_dev P;
     memset(&P, 0, sizeof P);

@@ -33,6 +33,8 @@ class StdRng {
         if (idx_ >= 64) { refill(); idx_ = 0; }
         return buf_[idx_++];
     }
+    // the ChaCha12 key (what cdp_prove_random_dev continues the stream from on the device)
+    const uint32_t *key() const { return key_; }
     // 32-bit words produced so far (what a caller hands over as `rng_skip_words` when it passes the same stream on)
     uint64_t words_consumed() const { return consumed_; }
     // rand 0.8 `gen_range(0..range)` on u32 (widening multiply, rejection zone) and `SliceRandom::shuffle` (Fisher-Yates from the

@@ -333,6 +333,11 @@ typedef struct {
 size_t cdp_prove_work_scalars(size_t ell);
 size_t cdp_prove_random_scalars(size_t ell);
 int cdp_prove_stage_dev(cdp_ctx *ctx, const cdp_prove_dev *params, int stage, unsigned round);
+/* The prover's `rng` on the device (`rng: &mut impl RngCore`, /root/reference/src/curdleproofs.rs:74, as rand 0.8's StdRng = ChaCha12): fills
+ * d_random (batch x cdp_prove_random_scalars(ell) x 32 B, the layout cdp_prove_dev.d_random documents) with the `Fr::rand` draws of
+ * `CurdleproofsProof::new` in the reference's order, proof i from the keystream of the 32-byte key d_keys[32 i ..] starting at 32-bit word
+ * d_skip_words[i] of it (NULL = 0: a fresh generator).  Same values as the host generator (host/rng.hpp) for the same key and position. */
+int cdp_prove_random_dev(cdp_ctx *ctx, const uint8_t *d_keys, const uint64_t *d_skip_words, size_t batch, size_t ell, uint8_t *d_random);
 
 /* d_out[i] = sum over r < rows of d_scalars[r * row_stride + i] (mod r), canonical 32-byte scalars, i < cols: the coefficients that several
  * proofs put on the same CRS base, added up for the merged check (`*entry += a * x_i`, /root/reference/src/msm_accumulator.rs:47-51). */

@@ -38,6 +38,7 @@ struct vcoef_params_t { uint32_t ell, n, m, big_n, vw, o_R, o_S, o_T, o_U, o_M, 
 #include "../../curdleproofs_b200/csrc/k_transcript.cu"
 #include "../../curdleproofs_b200/csrc/k_vcoeffs.cu"
 #include "../../curdleproofs_b200/csrc/k_prove.cu"
+#include "../../curdleproofs_b200/host/rng.hpp"
 
 extern "C" {
 int oracle_msm(const uint8_t *pts, const uint8_t *scalars, size_t n, uint8_t out_jac[144], int threads);
@@ -206,6 +207,21 @@ int cdp_round_expand_dev(cdp_ctx *c, const uint8_t *cmp, const uint8_t *ucan, si
 }
 size_t cdp_prove_work_scalars(size_t ell) { return 11 * (ell + 4) + 64; }
 size_t cdp_prove_random_scalars(size_t ell) { return 3 * (ell + 4) + 11; }
+// the device generator (k_prove_random) stood in for by the host's StdRng on the same key and stream position
+int cdp_prove_random_dev(cdp_ctx *c, const uint8_t *keys, const uint64_t *skip, size_t batch, size_t ell, uint8_t *out) {
+    c->launches++;
+    const size_t n = ell + 4, nrnd = 3 * n + 11;
+    for (size_t pr = 0; pr < batch; pr++) {
+        cdp_host::StdRng rng(cdp_host::StdRng::from_key_t{}, keys + 32 * pr);
+        if (skip) rng.skip_words(skip[pr]);
+        uint64_t *w = reinterpret_cast<uint64_t *>(out + pr * nrnd * 32);
+        auto draw = [&](size_t slot) { cdp_host::Fr x = rng.fr_rand(); memcpy(w + 4 * slot, x.v, 32); };
+        for (size_t i = 0; i < 6 + 2 * n - 2; i++) draw(i);
+        memset(w + 4 * (6 + 2 * n - 2), 0, 64);
+        for (size_t i = 0; i < 5 + n; i++) draw(6 + 2 * n + i);
+    }
+    return CDP_OK;
+}
 int cdp_prove_stage_dev(cdp_ctx *c, const cdp_prove_dev *P, int stage, unsigned round) {
     c->launches++;
     for (uint32_t pr = 0; pr < P->batch; pr++) {
