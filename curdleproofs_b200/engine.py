@@ -73,6 +73,8 @@ _SIGS = {
     "cdp_compress_affine_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "cdp_normalize_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "cdp_bench_kernel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float)]),
+    "cdp_prove_random_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
+    "cdp_prove_random_scalars": (c_size_t, [c_size_t]),
     "cdp_set_big_msm_min": (c_int, [c_void_p, c_size_t]),
     "cdp_set_big_ba_min": (c_int, [c_void_p, c_size_t]),
     "cdp_host_is_pinned": (c_int, [c_void_p]),
@@ -173,6 +175,27 @@ class Engine:
     def set_big_msm_min(self, n_pairs: int):
         """Pairs from which one MSM takes the sort-based large Pippenger on this engine (0 = the built-in 2^16)."""
         self._check(self._lib.cdp_set_big_msm_min(self._h, n_pairs), "cdp_set_big_msm_min")
+
+    def prove_random(self, keys: bytes, ell: int, skip_words=None) -> bytes:
+        """The prover's `Fr::rand` draws for len(keys) / 32 proofs from their ChaCha12 keys (cdp_prove_random_dev): per proof
+        cdp_prove_random_scalars(ell) raw 32-byte Montgomery representations in the layout of cdp_prove_dev.d_random."""
+        import struct
+        lib, h = self._lib, self._h
+        batch = len(keys) // 32
+        nrnd = int(lib.cdp_prove_random_scalars(ell))
+        d_k = lib.cdp_dev_alloc(h, 40 * batch)
+        d_o = lib.cdp_dev_alloc(h, 32 * nrnd * batch)
+        try:
+            blob = keys + struct.pack("<%dQ" % batch, *(skip_words or [0] * batch))
+            self._check(lib.cdp_h2d(h, d_k, _buf(blob), len(blob)), "cdp_h2d")
+            self._check(lib.cdp_prove_random_dev(h, d_k, (d_k + 32 * batch) if skip_words else None, batch, ell, d_o), "cdp_prove_random_dev")
+            out = (ctypes.c_uint8 * (32 * nrnd * batch))()
+            self._check(lib.cdp_d2h(h, out, d_o, 32 * nrnd * batch), "cdp_d2h")
+            self.sync()
+        finally:
+            lib.cdp_dev_free(h, d_k)
+            lib.cdp_dev_free(h, d_o)
+        return bytes(out)
 
     def set_big_ba_min(self, n_pairs: int):
         """Pairs from which the large Pippenger sums its buckets by rounds of batched affine additions (0 = the built-in 2^19)."""

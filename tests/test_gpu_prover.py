@@ -116,3 +116,61 @@ def test_ell1020_proof_and_verdict_parity(engine, oracle):
     assert bv.verify_batch([inst, bad], proofs) == [1, 0]
     assert oracle.verify(bad, proofs[1], threads=8) == 0
     bv.close()
+
+
+def _chacha12_words(key: bytes, first_word: int, count: int):
+    """Words [first_word, first_word + count) of the ChaCha12 keystream of rand 0.8's StdRng (64-bit block counter, stream 0)."""
+    import struct
+    k = struct.unpack("<8I", key)
+    M = 0xFFFFFFFF
+
+    def rotl(v, n):
+        return ((v << n) | (v >> (32 - n))) & M
+
+    def block(ctr):
+        s = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574, *k, ctr & M, ctr >> 32, 0, 0]
+        x = list(s)
+
+        def qr(a, b, c, d):
+            x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 16)
+            x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 12)
+            x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 8)
+            x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 7)
+        for _ in range(6):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        return [(a + b) & M for a, b in zip(x, s)]
+    out = []
+    b = first_word // 16
+    while len(out) < first_word % 16 + count:
+        out += block(b)
+        b += 1
+    return out[first_word % 16:first_word % 16 + count]
+
+
+@pytest.mark.parametrize("ell", [4, 28])
+def test_prover_randomness_on_the_device(engine, oracle, ell):
+    """cdp_prove_random_dev against a plain-Python restatement of `StdRng` (ChaCha12) + ark-ff `Fr::rand` (eight consecutive stream words, top
+    bit cleared, rejected when >= r, taken as they are): keys from the u64 test seeds and raw 32-byte keys, stream positions that are aligned,
+    odd, and straddle a ChaCha block -- /root/reference/src/curdleproofs.rs:74 takes `rng: &mut impl RngCore` at whatever position the caller left it."""
+    import struct
+    R_MOD = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    n = ell + 4
+    nrnd = 3 * n + 11
+    keys = [oracle.stdrng_seed_bytes(7), oracle.stdrng_seed_bytes(2 ** 63 + 5), bytes(range(32)), bytes(32), b"\xff" * 32]
+    skips = [0, 3, 13, 16 * 5 + 9, 2 ** 33 + 7]
+    got = engine.prove_random(b"".join(keys), ell, skips)
+    got0 = engine.prove_random(b"".join(keys), ell)      # NULL positions = fresh generators
+    for i, (key, skip) in enumerate(zip(keys, skips)):
+        for blob, sk in ((got, skip), (got0, 0)):
+            words = _chacha12_words(key, sk, 8 * (nrnd + 200))
+            draws, a = [], 0
+            while len(draws) < 3 * n + 9:
+                w = words[8 * a:8 * a + 8]
+                a += 1
+                v = sum(x << (32 * j) for j, x in enumerate(w)) & ((1 << 255) - 1)
+                if v < R_MOD:
+                    draws.append(v)
+            want = draws[:6 + 2 * n - 2] + [0, 0] + draws[6 + 2 * n - 2:]
+            have = [int.from_bytes(blob[32 * (i * nrnd + j):32 * (i * nrnd + j + 1)], "little") for j in range(nrnd)]
+            assert have == want, (i, sk)
