@@ -4,6 +4,7 @@
 // C++ (no PTX) and also compiles with g++ for the CPU harnesses under tests/host/.
 #pragma once
 #include <stdint.h>
+#include "fp_inv_safegcd.cuh"
 
 namespace cdp {
 
@@ -251,6 +252,15 @@ static __device__ __noinline__ fr_t fr_inverse_euclid(const fr_t &x) {
     for (int i = 0; i < 8; i++) r3.v[i] = R3[i];
     return fr_mul(u256_is_one(u.v) ? x1 : x2, r3);
 }
+// x^-1 by division steps (fp_inv_safegcd.cuh, the scalar field's modulus: ~17 batches of ~350 instructions; 0 -> 0): what the device code uses.
+// The Fermat ladder and the binary Euclid above stay as cross-checks (tests/host/cpu_engine_mock.cpp compares all three).
+static __device__ __noinline__ fr_t fr_inverse_safegcd(const fr_t &x) {
+    fr_t t, r3;
+    safegcd::inverse_int_fr(t.v, x.v, [](bool done) { return done; });
+    const uint32_t R3[8] = {0x439b73afu, 0xc62c1807u, 0x8cf06990u, 0x1b3e0d18u, 0xc7b5f418u, 0x73d13c71u, 0xc8db33e9u, 0x6e2a5bb9u};  // 2^768 mod r
+    for (int i = 0; i < 8; i++) r3.v[i] = R3[i];
+    return fr_mul(t, r3);
+}
 // xs[k] <- xs[k]^-1 for k < n <= 16 with one inversion (Montgomery's trick; no element may be zero: challenges never are)
 __device__ __forceinline__ void fr_batch_inverse(fr_t *xs, uint32_t n) {
     fr_t pre[16];
@@ -259,7 +269,7 @@ __device__ __forceinline__ void fr_batch_inverse(fr_t *xs, uint32_t n) {
         pre[k] = acc;
         acc = fr_mul(acc, xs[k]);
     }
-    fr_t inv = fr_inverse(acc);
+    fr_t inv = fr_inverse_safegcd(acc);
     for (uint32_t k = n; k-- > 0;) {
         const fr_t t = fr_mul(inv, pre[k]);
         inv = fr_mul(inv, xs[k]);

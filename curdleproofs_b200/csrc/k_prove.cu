@@ -200,7 +200,7 @@ __device__ void cta_reduce_add(fr_t *arr, uint32_t cnt) {
 }
 // x^-1 computed by the leader and handed to every thread through `slot`
 __device__ fr_t cta_inverse(const fr_t &x, fr_t *slot) {
-    if (CTA_LEADER) *slot = fr_inverse_euclid(x);
+    if (CTA_LEADER) *slot = fr_inverse_safegcd(x);
     CTA_SYNC();
     const fr_t r = *slot;
     CTA_SYNC();
@@ -412,7 +412,7 @@ __device__ void stage_gprod2(pctx &c) {
     // 1 / (r_c[n-1] - r_c[n-2] c[n-1] / c[n-2]) = c[n-2] / E
     if (CTA_LEADER) {
         const fr_t c2 = c.w.c[n - 2], E = fr_sub(fr_mul(rc[n - 1], c2), fr_mul(rc[n - 2], c.w.c[n - 1]));
-        const fr_t p01 = fr_mul(beta, c2), inv = fr_inverse_euclid(fr_mul(p01, E));
+        const fr_t p01 = fr_mul(beta, c2), inv = fr_inverse_safegcd(fr_mul(p01, E));
         const fr_t invE = fr_mul(inv, p01), inv01 = fr_mul(inv, E);
         c.w.sm[SM_T0] = fr_mul(inv01, c2);      // beta^-1
         c.w.sm[SM_T1] = fr_mul(inv01, beta);    // c[n-2]^-1

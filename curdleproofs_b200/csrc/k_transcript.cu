@@ -320,7 +320,7 @@ __device__ __forceinline__ void verify_transcript_a_body(S &s, uint32_t pr, cons
     const fr_t r_p = fr_to_mont(fr_load(reinterpret_cast<const uint32_t *>(pscal + ((size_t)pr * 7 + 0) * 32)));
     append_fr(s, L_GP2, 11, r_p);
     const fr_t beta_g = draw_challenge(s, L_GPB, 10);
-    const fr_t beta_inv = fr_inverse(beta_g);
+    const fr_t beta_inv = fr_inverse_safegcd(beta_g);
     state_store(state + (size_t)pr * 26, s);
     if (!is_leader(s)) return;
     uint32_t *ch = chal + 8 * (size_t)pr * vch;

@@ -231,7 +231,7 @@ int cdp_prove_stage_dev(cdp_ctx *c, const cdp_prove_dev *P, int stage, unsigned 
     return CDP_OK;
 }
 
-// the single-thread Euclidean inversion of csrc/fr256.cuh against the Fermat ladder: edge values and `count` pseudo-random ones; returns the number of mismatches
+// the division-step and the binary Euclidean inversion of csrc/fr256.cuh against the Fermat ladder: edge values and `count` pseudo-random ones; returns the number of mismatches
 int mock_check_fr_inverse(int count) {
     using namespace cdp::vcoef;
     int bad = 0;
@@ -246,9 +246,9 @@ int mock_check_fr_inverse(int count) {
         else if (t == 4) x.v[7] = 0x40000000u;
         else if (t == 5) { /* zero */ }
         else { for (int i = 0; i < 8; i++) x.v[i] = next(); x.v[7] &= 0x3FFFFFFFu; }
-        const fr_t a = fr_inverse(x), b = fr_inverse_euclid(x);
+        const fr_t a = fr_inverse(x), b = fr_inverse_euclid(x), c = fr_inverse_safegcd(x);
         bool same = true;
-        for (int i = 0; i < 8; i++) same = same && a.v[i] == b.v[i];
+        for (int i = 0; i < 8; i++) same = same && a.v[i] == b.v[i] && a.v[i] == c.v[i];
         if (t != 5) {
             const fr_t one = fr_mul(x, b), want = fr_one();
             for (int i = 0; i < 8; i++) same = same && one.v[i] == want.v[i];

@@ -1,3 +1,4 @@
-for st in 0 1000 3000 8000; do CDP_LANE_STAGGER_US=$st python bench.py --no-cpu-baseline --msm-sizes '' --no-extras --steps 3 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('stagger=$st proofs/s', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', round(d['ms_per_step'],1))"; done
+python -m pytest tests/test_gpu_prover.py tests/test_gpu_verifier.py tests/test_gpu_transcript.py -x -q -m gpu 2>&1 | tail -2
+python tools/prover_profile.py 252 512 1 2>&1 | grep "prove_stage\|sum\|ell=" | cut -c1-120
+python tools/prover_timing.py 252 128 4 2>&1 | grep "B=128" | cut -c1-150
+python tools/verifier_profile.py 252 512 1 2>&1 | grep "transcript\|sum\|ell=" | cut -c1-150
