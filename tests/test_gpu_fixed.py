@@ -167,3 +167,13 @@ def test_fixed_tree_of_batched_affine_additions(engine, oracle, bases, table):
     # fewer than 4 * 2^rounds items per segment: served by the lane kernel
     got = engine.msm_fixed_batch(table, sc, segs[3:4], var, tree_max_pairs=1)
     assert oracle.compress_jac(got[3]) == oracle.compress_jac(want[3])
+
+
+def test_tuning_setters_reject_bad_arguments(engine):
+    """cdp_set_big_msm_min / cdp_set_big_ba_min: sizes below 2048 pairs are refused (the sort-based path has no sensible geometry there), 0 restores the default."""
+    from curdleproofs_b200 import CdpError
+    for setter in (engine.set_big_msm_min, engine.set_big_ba_min):
+        with pytest.raises(CdpError):
+            setter(100)
+        setter(4096)
+        setter(0)
