@@ -165,11 +165,14 @@ int combine_dev(cdp_ctx *ctx, const msm_cfg &g, const uint32_t *d_win, size_t co
     static const size_t quad_max = [] { const char *e = getenv("CDP_COMBINE_QUAD_MAX"); return e ? (size_t)atoll(e) : (size_t)1024; }();
     if (count <= quad_max && g.nwin > 1) {
         const size_t nb = (size_t)1 << (g.c - 1);
-        TRY(ensure_dev(ctx, ctx->d_aux, count * nb * 144));
+        // S, then (for launches of very few MSMs) the group sums of the two-step Horner
+        const bool groups = count <= horner_groups_max();
+        TRY(ensure_dev(ctx, ctx->d_aux, count * nb * 144 + (groups ? horner_groups_scratch_bytes((uint32_t)count, g.c, g.nwin) : 0)));
         uint32_t *S = reinterpret_cast<uint32_t *>(ctx->d_aux.ptr);
         {
             launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, count);
-            CUDA_TRY(ctx, launch_msm_horner_quad(ctx->stream, d_win, S, (uint32_t)count, g.c, g.nwin));
+            CUDA_TRY(ctx, launch_msm_horner_quad(ctx->stream, d_win, S, (uint32_t)count, g.c, g.nwin, groups ? S + 36 * count * nb : nullptr));
+            if (groups) ctx->launches++;
         }
         launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, count);
         if (g.c >= 2) CUDA_TRY(ctx, launch_msm_reduce_quad(ctx->stream, S, d_out_jac, (uint32_t)count, g.c));

@@ -1,3 +1,5 @@
+#include <cstdlib>
+
 #include "launch.h"
 #include "msm_common.cuh"
 #include "g1_quad.cuh"
@@ -89,6 +91,72 @@ __global__ void __launch_bounds__(128) k_msm_horner_quad(const uint32_t *__restr
         g1j W;
         g1j_set_inf(W);
         if (valid) g1j_load(W, B + 36 * (size_t)w * nb);
+        g1j_add_quad(acc, acc, W, s);
+    }
+    if (valid && s == 0) g1j_store(S_out + 36 * ((size_t)i * nb + b), acc);
+}
+
+// k_msm_horner_quad with the ADDITIONS of the chain taken out of it: the windows are first combined in groups of G (k_msm_horner_part1: a quad
+// per (MSM, group, bucket index), all in parallel, (G - 1) c doublings and G additions deep), then one quad per (MSM, bucket index) runs Horner
+// over the ceil(nwin / G) group sums (k_msm_horner_part2).  The ~128 doublings of the chain are inherent, but its additions drop from nwin (26 at
+// c = 5, ~10 us each for a lone quad) to G + ceil(nwin / G): ~0.1 ms of the ~0.6 ms a lone `util::msm` spends here.
+__global__ void __launch_bounds__(128) k_msm_horner_part1(const uint32_t *__restrict__ bucket_sums, uint32_t *__restrict__ V, uint32_t n_msm, int c, int nwin,
+                                                          int G) {
+    const int nb = 1 << (c - 1), ng = (nwin + G - 1) / G;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, quad = gid >> 2;
+    const int s = (int)(threadIdx.x & 3);
+    const uint32_t i = quad / (uint32_t)(ng * nb);
+    const int j = (int)(quad / nb) % ng, b = (int)(quad % nb);
+    const bool valid = i < n_msm;
+    const int tb = 128 - c * (nwin - 1), nbt = tb > 0 ? (1 << tb) : 1, sp = nb / nbt >= 1 ? nb / nbt : 1;
+    // the top window: bucket b < nbt is spread over sp slots (k_msm_buckets); only the last group's quads have something to add here
+    const bool has_top = valid && j == ng - 1 && b < nbt;
+    const uint32_t *T = bucket_sums + 36 * (((size_t)(valid ? i : 0) * nwin + (nwin - 1)) * nb + (size_t)(has_top ? b : 0) * sp);
+    g1j top;
+    g1j_set_inf(top);
+#pragma unroll 1
+    for (int k = 0; k < sp; k++) {
+        g1j W;
+        g1j_set_inf(W);
+        if (has_top) g1j_load(W, T + 36 * (size_t)k);
+        g1j_add_quad(top, top, W, s);
+    }
+    const uint32_t *B = bucket_sums + 36 * ((size_t)(valid ? i : 0) * nwin * nb + b);
+    g1j acc;
+    g1j_set_inf(acc);
+#pragma unroll 1
+    for (int t = G - 1; t >= 0; t--) {
+        if (t != G - 1) {
+#pragma unroll 1
+            for (int k = 0; k < c; k++) g1j_dbl_quad(acc, s);
+        }
+        const int w = j * G + t;
+        g1j W;
+        g1j_set_inf(W);
+        if (valid && w < nwin - 1) g1j_load(W, B + 36 * (size_t)w * nb);
+        else if (valid && w == nwin - 1) W = top;
+        g1j_add_quad(acc, acc, W, s);
+    }
+    if (valid && s == 0) g1j_store(V + 36 * (((size_t)i * ng + j) * nb + b), acc);
+}
+__global__ void __launch_bounds__(128) k_msm_horner_part2(const uint32_t *__restrict__ V, uint32_t *__restrict__ S_out, uint32_t n_msm, int nb, int ng,
+                                                          int dbl_per_step) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, quad = gid >> 2;
+    const int s = (int)(threadIdx.x & 3);
+    const uint32_t i = quad / (uint32_t)nb;
+    const int b = (int)(quad % nb);
+    const bool valid = i < n_msm;
+    const uint32_t *Vi = V + 36 * ((size_t)(valid ? i : 0) * ng * nb + b);
+    g1j acc;
+    g1j_set_inf(acc);
+    if (valid) g1j_load(acc, Vi + 36 * (size_t)(ng - 1) * nb);
+#pragma unroll 1
+    for (int jj = ng - 2; jj >= 0; jj--) {
+#pragma unroll 1
+        for (int k = 0; k < dbl_per_step; k++) g1j_dbl_quad(acc, s);
+        g1j W;
+        g1j_set_inf(W);
+        if (valid) g1j_load(W, Vi + 36 * (size_t)jj * nb);
         g1j_add_quad(acc, acc, W, s);
     }
     if (valid && s == 0) g1j_store(S_out + 36 * ((size_t)i * nb + b), acc);
@@ -188,7 +256,24 @@ cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *bucket_sums, uin
     k_msm_combine<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(bucket_sums, out_jac, n_msm, c, nwin);
     return cudaGetLastError();
 }
-cudaError_t launch_msm_horner_quad(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *S_out, uint32_t n_msm, int c, int nwin) {
+uint32_t horner_groups_max() {
+    static const uint32_t v = [] { const char *e = getenv("CDP_HORNER_GROUP_MAX"); return e ? (uint32_t)atoi(e) : 64u; }();
+    return v;
+}
+size_t horner_groups_scratch_bytes(uint32_t n_msm, int c, int nwin) {  // for any G >= 2
+    return (size_t)n_msm * ((nwin + 1) / 2) * ((size_t)1 << (c - 1)) * 144;
+}
+cudaError_t launch_msm_horner_quad(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *S_out, uint32_t n_msm, int c, int nwin, uint32_t *scratch) {
+    // few MSMs (a lone `util::msm`, small batches): the windows combined in groups first; CDP_HORNER_GROUP = 0 keeps the plain chain.
+    // `scratch` holds n_msm * ceil(nwin / G) * nb Jacobian group sums
+    static const int G = [] { const char *e = getenv("CDP_HORNER_GROUP"); return e ? atoi(e) : 3; }();  // measured: 2, 3 < 4 < 6
+    if (G >= 2 && scratch && n_msm <= horner_groups_max()) {
+        const int nb = 1 << (c - 1), ng = (nwin + G - 1) / G;
+        const uint64_t q1 = (uint64_t)n_msm * ng * nb * 4, q2 = (uint64_t)n_msm * nb * 4;
+        k_msm_horner_part1<<<(unsigned)((q1 + 127) / 128), 128, 0, st>>>(bucket_sums, scratch, n_msm, c, nwin, G);
+        k_msm_horner_part2<<<(unsigned)((q2 + 127) / 128), 128, 0, st>>>(scratch, S_out, n_msm, nb, ng, G * c);
+        return cudaGetLastError();
+    }
     const uint64_t threads = ((uint64_t)n_msm << (c - 1)) * 4;
     k_msm_horner_quad<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(bucket_sums, S_out, n_msm, c, nwin);
     return cudaGetLastError();

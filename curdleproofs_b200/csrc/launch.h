@@ -87,7 +87,10 @@ CDP_DECL_MSM(2) CDP_DECL_MSM(3) CDP_DECL_MSM(4) CDP_DECL_MSM(5) CDP_DECL_MSM(6)
 #undef CDP_DECL_MSM
 cudaError_t launch_msm_combine(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *out_jac, uint32_t n_msm, int c, int nwin);
 cudaError_t launch_msm_reduce_quad(cudaStream_t st, const uint32_t *S, uint32_t *out_jac, uint32_t n_msm, int c);
-cudaError_t launch_msm_horner_quad(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *S_out, uint32_t n_msm, int c, int nwin);
+uint32_t horner_groups_max();
+size_t horner_groups_scratch_bytes(uint32_t n_msm, int c, int nwin);
+cudaError_t launch_msm_horner_quad(cudaStream_t st, const uint32_t *bucket_sums, uint32_t *S_out, uint32_t n_msm, int c, int nwin,
+                                   uint32_t *scratch = nullptr /* horner_groups_scratch_bytes, for n_msm <= horner_groups_max() */);
 cudaError_t launch_sum_groups(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t n_out, uint32_t per_out, uint32_t group_stride);
 cudaError_t launch_sum_groups2(cudaStream_t st, const uint32_t *A, uint32_t per_a, uint32_t sa, uint32_t ga, const uint32_t *B, uint32_t per_b,
                                uint32_t sb, uint32_t gb, uint32_t *out, uint32_t n_out);
