@@ -622,7 +622,9 @@ static int big_reduce_tail(cdp_ctx *ctx, const uint32_t *buckets, bool affine, u
             ctx->launches++;
             return CDP_OK;
         }
-        uint32_t g = std::min<uint32_t>(16, len);
+        // first level: LEAF_G buckets per thread (tuning: CDP_BIG_LEAF_G), 16 per node above
+        static const uint32_t LEAF_G = [] { const char *e = getenv("CDP_BIG_LEAF_G"); int v = e ? atoi(e) : 16; return (uint32_t)(v == 8 || v == 32 || v == 64 ? v : 16); }();
+        uint32_t g = std::min<uint32_t>(Ain ? 16 : LEAF_G, len);
         uint32_t n_out = (uint32_t)((size_t)nwin * (len / g));
         launch_scope ls(ctx, CDP_PROFILE_MSM_COMBINE, n_out);
         if (!Ain && affine) CUDA_TRY(ctx, launch_big_reduce_leaf_affine(ctx->stream, buckets, n_out, g, Aout, Bout));
