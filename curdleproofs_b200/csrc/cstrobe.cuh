@@ -51,7 +51,7 @@ __device__ __forceinline__ void keccak_f1600_warp(uint64_t *st) {
     const int dm = (x + 4) % 5 + 5 * y, dp = (x + 1) % 5 + 5 * y, c2 = (x + 2) % 5 + 5 * y;
     const int pi_src = (x + 3 * y) % 5 + 5 * x;  // B[X][Y] = rot(a[(X + 3Y) % 5][X])
     __syncwarp();
-    uint64_t a = st[t];
+    uint64_t a = lane < 25 ? st[lane] : 0;  // the idle lanes only take part in the shuffles
 #pragma unroll 1
     for (int round = 0; round < 24; round++) {
         const uint64_t c = a ^ __shfl_sync(0xffffffffu, a, th1) ^ __shfl_sync(0xffffffffu, a, th2) ^ __shfl_sync(0xffffffffu, a, th3) ^
