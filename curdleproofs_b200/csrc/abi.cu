@@ -661,7 +661,9 @@ static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
                  o_A0 = take(lvl * 144), o_B0 = take(lvl * 144), o_A1 = take(lvl * 144), o_B1 = take(lvl * 144), o_misc = take(BA_STATS_ROUNDS * 3 * 4);
     // the sort's temporary storage is dead once the ids are sorted: the round buffers start there
     const size_t o_tmp = o;
-    const size_t o_scan_tmp = take(scan_tmp), o_jobs = take((items / 2 + 1) * 16), o_s0 = take(s0n * 96), o_s1 = take(s1n * 96);
+    static const bool BA_STASH = [] { const char *e = getenv("CDP_BA_STASH"); return e && atoi(e) != 0; }();
+    const size_t o_scan_tmp = take(scan_tmp), o_jobs = take((items / 2 + 1) * 16), o_s0 = take(s0n * 96), o_s1 = take(s1n * 96),
+                 o_stash = take(BA_STASH ? (items / 2 + 1) * 192 : 0);
     const size_t total = std::max(o, o_tmp + al(sort_tmp));
     TRY(ensure_dev(ctx, ctx->d_big, total));
     uint8_t *ws = (uint8_t *)ctx->d_big.ptr;
@@ -699,7 +701,8 @@ static int msm_big_resident_ba(cdp_ctx *ctx, const uint8_t *d_pts, const uint8_t
         const uint32_t K = std::max(1u, (uint32_t)(((uint64_t)pairs + (uint64_t)waves * WAVE - 1) / ((uint64_t)waves * WAVE)));
         launch_scope ls(ctx, CDP_PROFILE_MSM_BUCKETS, r == 0 ? (uint64_t)n : 0);
         CUDA_TRY(ctx, launch_ba_round(ctx->stream, r == 0, ws + o_scan_tmp, scan_tmp, sc[r & 1], ws + o_incl, list_len, pairs, K, act[r & 1], act[(r + 1) & 1],
-                                      slots, sc[(r + 1) & 1], P, bx, vals2, sbuf[(r + 1) & 1], sbuf[r & 1], baff, ws + o_jobs));
+                                      slots, sc[(r + 1) & 1], P, bx, vals2, sbuf[(r + 1) & 1], sbuf[r & 1], baff, ws + o_jobs,
+                                      BA_STASH && r == 0 ? (uint32_t *)(ws + o_stash) : nullptr));
         ctx->launches += 3;
     }
     // hierarchical reduction: sum_b (b+1) B_b per window (the leaves are affine), Horner over the windows

@@ -70,7 +70,9 @@ __device__ __forceinline__ void ba_mul(fp &r, const fp &a, const fp &b) {
         else fp_mul(r, a, b);
     }
 }
-template <class Src, int INL = 0>
+// STASH: pass 1 reads both points in full and parks them in src.stash(q) (192 bytes, streamed); pass 2 reads them back from there instead of
+// gathering them a second time -- for sources whose operands are random 128-byte lines (the caller's bases, the digit table)
+template <class Src, int INL = 0, bool STASH = false>
 __device__ __forceinline__ void ba_run(const Src &src, uint32_t tid, uint32_t T, uint32_t total, uint32_t K, uint32_t pf = 0) {
     if (tid >= total) return;
     uint32_t cnt = (total - tid + T - 1) / T;
@@ -85,7 +87,14 @@ __device__ __forceinline__ void ba_run(const Src &src, uint32_t tid, uint32_t T,
         for (uint32_t i = 0; i < cnt; i++) {
             const ref r2 = src.resolve(i + 2 < cnt ? tid + (i + 2) * T : tid);
             fp den;
-            {
+            if (STASH) {
+                g1a P, Q;
+                src.load(r0, P, Q);
+                ba_classify(den, P, Q);
+                uint32_t *sp = src.stash(tid + i * T);
+                g1a_store(sp, P);
+                g1a_store(sp + 24, Q);
+            } else {
                 fp px, qx;
                 src.load_x(r0, px, qx);
                 if (fp_is_zero(px) || fp_is_zero(qx) || fp_eq(px, qx)) {  // rare: infinity (x = 0 is necessary), tangent, cancellation
@@ -111,7 +120,13 @@ __device__ __forceinline__ void ba_run(const Src &src, uint32_t tid, uint32_t T,
     for (uint32_t i = cnt; i-- > 0;) {
         const ref r2 = src.resolve(i >= 2 ? tid + (i - 2) * T : tid);
         g1a P, Q;
-        src.load(r0, P, Q);
+        if (STASH) {
+            const uint32_t *sp = src.stash(tid + i * T);
+            g1a_load(P, sp);
+            g1a_load(Q, sp + 24);
+        } else {
+            src.load(r0, P, Q);
+        }
         fp den;
         const int kind = ba_classify(den, P, Q);
         fp dinv = inv;

@@ -80,7 +80,9 @@ struct ba_jobs_src {
     In in;
     const uint4 *jobs;
     uint32_t *out, *bucket_aff;
+    uint32_t *stash_base;  // 48 words per job, or nullptr
     typedef uint4 ref;
+    __device__ __forceinline__ uint32_t *stash(uint32_t q) const { return stash_base + 48 * (size_t)q; }
     __device__ __forceinline__ ref resolve(uint32_t q) const { return jobs[q]; }
     __device__ __forceinline__ uint32_t *dst(const ref &r) const {
         return (r.z & BA_FINAL) ? bucket_aff + 24 * (size_t)(r.z & ~BA_FINAL) : out + 24 * (size_t)r.z;
@@ -199,12 +201,12 @@ __global__ void __launch_bounds__(256) k_ba_jobs(const ba_scan_t *__restrict__ i
     }
 }
 
-template <class In>
+template <class In, bool STASH = false>
 __global__ void __launch_bounds__(128, 4) k_ba_round(uint32_t total, uint32_t K, uint32_t pf, ba_jobs_src<In> src) {
     const uint32_t T = (total + K - 1) / K;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= T) return;
-    ba_run<ba_jobs_src<In>, BA_INLINE>(src, tid, T, total, K, pf);
+    ba_run<ba_jobs_src<In>, BA_INLINE, STASH>(src, tid, T, total, K, pf);
 }
 
 // The last few rounds of a deep tree are short lists of buckets with a handful of elements each (the top window: 2^14 buckets of 512 points
@@ -262,7 +264,7 @@ cudaError_t launch_ba_init(cudaStream_t st, const uint32_t *start, uint32_t n2, 
 // One round: `list_len` buckets on its list, `pairs` additions, K of them per inversion (all exact: k_ba_init's statistics).
 cudaError_t launch_ba_round(cudaStream_t st, bool first, void *scan_tmp, size_t scan_tmp_bytes, void *scan_in, void *scan_out, uint32_t list_len,
                             uint32_t pairs, uint32_t K, const uint32_t *act, uint32_t *nact, size_t act_stride, void *nscan_in, const uint32_t *pts,
-                            const uint32_t *bx, const uint32_t *vals, const uint32_t *in, uint32_t *out, uint32_t *bucket_aff, void *jobs) {
+                            const uint32_t *bx, const uint32_t *vals, const uint32_t *in, uint32_t *out, uint32_t *bucket_aff, void *jobs, uint32_t *stash) {
     const ba_scan_t *sin = reinterpret_cast<const ba_scan_t *>(scan_in);
     ba_scan_t *incl = reinterpret_cast<ba_scan_t *>(scan_out), *nsin = reinterpret_cast<ba_scan_t *>(nscan_in);
     cudaError_t e = cub::DeviceScan::InclusiveScan(scan_tmp, scan_tmp_bytes, sin, incl, ba_scan_add(), (int)list_len, st);
@@ -274,12 +276,13 @@ cudaError_t launch_ba_round(cudaStream_t st, bool first, void *scan_tmp, size_t 
         const ba_gather g{pts, bx, vals};
         k_ba_jobs<ba_gather><<<gj, 256, 0, st>>>(incl, list_len, pairs, act, act + act_stride, act + 2 * act_stride, g, out, jb, nact, nact + act_stride,
                                                  nact + 2 * act_stride, nsin);
-        k_ba_round<ba_gather><<<gr, 128, 0, st>>>(pairs, K, pf_first, ba_jobs_src<ba_gather>{g, jb, out, bucket_aff});
+        if (stash) k_ba_round<ba_gather, true><<<gr, 128, 0, st>>>(pairs, K, pf_first, ba_jobs_src<ba_gather>{g, jb, out, bucket_aff, stash});
+        else k_ba_round<ba_gather><<<gr, 128, 0, st>>>(pairs, K, pf_first, ba_jobs_src<ba_gather>{g, jb, out, bucket_aff, nullptr});
     } else {
         const ba_array g{in};
         k_ba_jobs<ba_array><<<gj, 256, 0, st>>>(incl, list_len, pairs, act, act + act_stride, act + 2 * act_stride, g, out, jb, nact, nact + act_stride,
                                                 nact + 2 * act_stride, nsin);
-        k_ba_round<ba_array><<<gr, 128, 0, st>>>(pairs, K, pf_later, ba_jobs_src<ba_array>{g, jb, out, bucket_aff});
+        k_ba_round<ba_array><<<gr, 128, 0, st>>>(pairs, K, pf_later, ba_jobs_src<ba_array>{g, jb, out, bucket_aff, nullptr});
     }
     return cudaGetLastError();
 }
@@ -289,6 +292,7 @@ struct ba_bench_src {
     const uint32_t *in;
     uint32_t *out;
     typedef uint32_t ref;
+    __device__ __forceinline__ uint32_t *stash(uint32_t) const { return nullptr; }
     __device__ __forceinline__ ref resolve(uint32_t q) const { return q; }
     __device__ __forceinline__ uint32_t *dst(ref q) const { return out + 24 * (size_t)q; }
     __device__ __forceinline__ void prefetch_x(ref q) const {

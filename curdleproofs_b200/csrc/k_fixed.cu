@@ -362,6 +362,7 @@ struct fixed_ba_src {
     fixed_kparams_t kp;
     uint32_t half_ipad;  // jobs per segment
     uint32_t *out;
+    __device__ __forceinline__ uint32_t *stash(uint32_t) const { return nullptr; }
     struct ref {
         const uint32_t *p, *q;  // table entries (nullptr: absent); the sign bits ride in the destination index
         uint32_t d;
@@ -409,6 +410,7 @@ struct fixed_ba_arr_src {
     const uint32_t *in;
     uint32_t *out;
     typedef uint32_t ref;
+    __device__ __forceinline__ uint32_t *stash(uint32_t) const { return nullptr; }
     __device__ __forceinline__ ref resolve(uint32_t q) const { return q; }
     __device__ __forceinline__ uint32_t *dst(ref q) const { return out + 24 * (size_t)q; }
     __device__ __forceinline__ void prefetch_x(ref) const {}

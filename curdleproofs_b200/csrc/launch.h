@@ -121,7 +121,8 @@ cudaError_t launch_ba_init(cudaStream_t st, const uint32_t *start, uint32_t n2, 
                            const uint32_t *vals, uint32_t *act, void *scan_in, uint32_t *bucket_aff, uint32_t *stats);
 cudaError_t launch_ba_round(cudaStream_t st, bool first, void *scan_tmp, size_t scan_tmp_bytes, void *scan_in, void *scan_out, uint32_t list_len,
                             uint32_t pairs, uint32_t K, const uint32_t *act, uint32_t *nact, size_t act_stride, void *nscan_in, const uint32_t *pts,
-                            const uint32_t *bx, const uint32_t *vals, const uint32_t *in, uint32_t *out, uint32_t *bucket_aff, void *jobs);
+                            const uint32_t *bx, const uint32_t *vals, const uint32_t *in, uint32_t *out, uint32_t *bucket_aff, void *jobs,
+                            uint32_t *stash /* round 0 only: 192 B per pair, or nullptr */);
 cudaError_t launch_ba_finish(cudaStream_t st, bool first, const uint32_t *act, size_t act_stride, uint32_t list_len, const uint32_t *pts, const uint32_t *bx,
                              const uint32_t *vals, const uint32_t *in, uint32_t *bucket_aff);
 cudaError_t launch_bench_ba(cudaStream_t st, uint32_t *buf, uint32_t T, uint32_t K, bool fill, int inl);
