@@ -501,8 +501,22 @@ def main():
                                 "table_points_per_s": adds_per_s, "imad_wide_per_table_point": IMAD_PER_TREE_POINT,
                                 "imad_wide_per_affine_add": IMAD_PER_AFFINE_ADD, "imad_wide_per_xyzz_mixed_add": IMAD_PER_MIXED_ADD,
                                 "frac_if_all_xyzz": adds_per_s * IMAD_PER_MIXED_ADD / imad_peak}
+    elif dom == "msm_buckets":
+        # XYZZ mixed additions per pair of the bucket kernel: 2 GLV halves x the windows of the launch's width; over the launches of an
+        # ell = 252 step (1792 pairs at c = 5 -> 52 additions, 192 at c = 4 -> 66, 48 at c = 3 -> 88, 15 at c = 2 -> 130) 54.7 on average
+        adds_per_pair = 54.7
+        adds_per_s = adds_per_pair * units_per_launch / (avg_ms * 1e-3)
+        roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)",
+                                "achieved": adds_per_s * IMAD_PER_MIXED_ADD, "frac": adds_per_s * IMAD_PER_MIXED_ADD / imad_peak,
+                                "mixed_adds_per_s": adds_per_s, "mixed_adds_per_pair": adds_per_pair, "imad_wide_per_xyzz_mixed_add": IMAD_PER_MIXED_ADD,
+                                "note": "bucket accumulation only; the window combine is a separate kernel (kernel_ms.msm_combine)"}
     else:
-        roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)"}
+        # fold elements: 128 doublings (2M + 5S) + ~64 mixed additions (7M + 4S) each
+        imad_per_elem = 128 * (2 * 288 + 5 * 222) + 64 * (7 * 288 + 4 * 222)
+        elems_per_s = units_per_launch / (avg_ms * 1e-3)
+        roofline["int_pipe"] = {"peak": imad_peak, "unit": "IMAD.WIDE.U32/s", "peak_source": "measured live (k_bench_imad, register-only)",
+                                "achieved": elems_per_s * imad_per_elem, "frac": elems_per_s * imad_per_elem / imad_peak,
+                                "elements_per_s": elems_per_s, "imad_wide_per_element": imad_per_elem}
     # ---- the same kernel timed ALONE on synthetic scalars (nothing else on the GPU): one fixed-base launch of the IPA-round shape for the whole batch
     try:
         from curdleproofs_b200 import FixedSeg

@@ -30,9 +30,10 @@ size_t cdp_proof_size(size_t ell);
  * `ctx` must outlive the prover.  `host_threads` <= 0 selects all host cores. */
 int cdp_prover_create(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads);
 /* Same, with an explicit number of concurrent lanes.  A lane is an independent sub-batch pipeline with its own CUDA stream
- * (lane 0 uses `ctx`, the others create private contexts on the same device) and its own host threads, so that host-side
- * transcript work and latency-bound launches of one lane overlap with GPU work of the others.  lanes <= 0 picks a default
- * (8 for max_batch >= 512, 4 for >= 128).  cdp_prover_create is cdp_prover_create_lanes with lanes = 0. */
+ * (lane 0 uses `ctx`, the others create private contexts on the same device) and its own host threads, so that the copies, the
+ * staging and the latency-bound launches of one lane overlap with GPU work of the others.  lanes <= 0 picks a default (2 for
+ * max_batch >= 256, else 1: with the whole protocol on the device larger launches beat more overlap).  cdp_prover_create is
+ * cdp_prover_create_lanes with lanes = 0. */
 int cdp_prover_create_lanes(cdp_prover **out, cdp_ctx *ctx, size_t ell, const uint8_t *crs_points, size_t max_batch, int host_threads,
                             int lanes);
 int cdp_prover_lane_count(const cdp_prover *p);

@@ -59,15 +59,15 @@ def test_full_size_ell252_multi_lane_round_trip(engine, oracle):
     base = [oracle.random_instance(ell, crs, seed=500 + i, threads=8) for i in range(3)]
     insts = [base[i % 3] for i in range(batch)]
     seeds = [9000 + i for i in range(batch)]
-    bp = BatchProver(engine, ell, crs, max_batch=batch)
-    assert bp.lanes >= 2
+    bp = BatchProver(engine, ell, crs, max_batch=batch, lanes=4)
+    assert bp.lanes == 4
     proofs = bp.prove_batch(insts, seeds)
     bp.close()
     for i in (0, batch - 1):
         assert proofs[i] == oracle.prove(insts[i], rng_seed=seeds[i], threads=8)
         assert oracle.verify(insts[i], proofs[i], threads=8) == 1
     assert len(set(proofs)) == batch  # different RNG streams: all proofs distinct
-    bv = BatchVerifier(engine, ell, crs, max_batch=batch)
+    bv = BatchVerifier(engine, ell, crs, max_batch=batch, lanes=3)
     assert bv.verify_batch(insts, proofs) == [1] * batch
     shifted = insts[1:] + insts[:1]   # every proof now sits on a different instance
     assert bv.verify_batch(shifted, proofs) == [0] * batch
